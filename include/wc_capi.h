@@ -1,0 +1,314 @@
+/*
+ * wc_capi.h — C ABI of the B200-native batched walking-controllers hot path.
+ *
+ * The reference (lia2790/walking-controllers) has no FFI layer: its boundary for
+ * this path is two C++ class interfaces called once per 10 ms control tick from
+ * WalkingModule::updateModule (modules/Walking_module/src/WalkingModule.cpp:601-637
+ * for the MPC block, :709-745 and :367-425 for the QP-IK block).  This header is the
+ * C-ABI a replacement of that path binds: plain pointers and sizes, no C++/torch
+ * types.  The drop-in C++ classes in walking-controllers_b200/host/ are thin views
+ * over these entry points.
+ *
+ * Conventions
+ *  - every entry point returns wc_status (0 = ok, <0 = error) and never throws;
+ *  - B = number of independent controller instances owned by the handle;
+ *  - all batched arrays are fp64 structure-of-arrays: element k of instance i is at
+ *    ptr[k*B + i] ("field-major"), so that consecutive instances are consecutive
+ *    in memory and warp loads coalesce;
+ *  - `stream` is a cudaStream_t passed as void* (NULL = default stream); calls are
+ *    asynchronous on that stream; one stream per handle; handles are not thread-safe;
+ *  - *_dev entry points take DEVICE pointers; *_host entry points take HOST pointers
+ *    and stage through pinned memory inside the call (these are what the B=1 drop-in
+ *    classes and the end-to-end benchmark use);
+ *  - per-instance failures never poison the batch: they are reported through the
+ *    int32 status arrays (OSQP / qpOASES-style codes below), the call still returns 0.
+ */
+#ifndef WC_CAPI_H
+#define WC_CAPI_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int32_t wc_status;
+
+enum {
+    WC_OK = 0,
+    WC_ERR_INVALID_ARG = -1,
+    WC_ERR_CUDA = -2,
+    WC_ERR_UNSUPPORTED = -3, /* e.g. non-diagonal Q/R on the fast MPC path */
+    WC_ERR_NO_DEVICE = -4,
+    WC_ERR_ALLOC = -5,
+    WC_ERR_STATE = -6 /* call order violated (e.g. get_output before solve) */
+};
+
+/* ---- OSQP status codes (osqp 0.6 constants.h), returned per instance by the MPC ---- */
+enum {
+    WC_OSQP_DUAL_INFEASIBLE_INACCURATE = 4,
+    WC_OSQP_PRIMAL_INFEASIBLE_INACCURATE = 3,
+    WC_OSQP_SOLVED_INACCURATE = 2,
+    WC_OSQP_SOLVED = 1,
+    WC_OSQP_MAX_ITER_REACHED = -2,
+    WC_OSQP_PRIMAL_INFEASIBLE = -3,
+    WC_OSQP_DUAL_INFEASIBLE = -4,
+    WC_OSQP_NON_CVX = -7,
+    WC_OSQP_UNSOLVED = -10
+};
+
+/* Per-instance controller-level flags of one MPC tick (bit mask, `flags` output).
+ * The reference collapses all of these into the bool returned by
+ * WalkingController::{setConvexHullConstraint,solve}
+ * (WalkingDCMModelPredictiveController.cpp:364-435,491-521). */
+enum {
+    WC_MPC_FLAG_OK = 0,
+    WC_MPC_FLAG_NO_CONTACT = 1,   /* (false,false) contact pair: "None foot is in contact" (:404-408) */
+    WC_MPC_FLAG_NO_SOLVER = 2,    /* no MPCSolver exists yet (reference would dereference null) */
+    WC_MPC_FLAG_NOT_SOLVED = 4,   /* OsqpEigen::Solver::solve() false: status != OSQP_SOLVED */
+    WC_MPC_FLAG_OUTSIDE_HULL = 8, /* computeMargin(u0) < -convex_hull_tolerance (:513-517) */
+    WC_MPC_FLAG_NEW_SOLVER = 16   /* informational: support phase changed, cold OSQP setup ran */
+};
+
+/* OSQP settings; defaults = osqp 0.6 defaults, which the reference uses untouched
+ * except verbose=0 (MPCSolver.cpp:51).  adaptive_rho_interval: the reference leaves 0
+ * (= chosen from wall-clock timings inside OSQP, non-deterministic); this
+ * implementation and its oracle use OSQP's own non-profiling fallback
+ * 4*check_termination = 100 when 0 is given. */
+typedef struct wc_osqp_settings {
+    double rho;                    /* 0.1 */
+    double sigma;                  /* 1e-6 */
+    double alpha;                  /* 1.6 */
+    double eps_abs;                /* 1e-3 */
+    double eps_rel;                /* 1e-3 */
+    double eps_prim_inf;           /* 1e-4 */
+    double eps_dual_inf;           /* 1e-4 */
+    double adaptive_rho_tolerance; /* 5 */
+    double infty;                  /* OSQP_INFTY = 1e30 */
+    int32_t max_iter;              /* 4000 */
+    int32_t scaling;               /* 10 Ruiz passes */
+    int32_t check_termination;     /* 25 */
+    int32_t adaptive_rho;          /* 1 */
+    int32_t adaptive_rho_interval; /* 0 -> 4*check_termination */
+    int32_t warm_start;            /* 1 */
+    int32_t reserved0;
+    int32_t reserved1;
+} wc_osqp_settings;
+
+/* Configuration of the DCM-MPC (WalkingController::initialize,
+ * WalkingDCMModelPredictiveController.cpp:170-362; values from
+ * app/robots/<robot>/controllerParams.ini + the GENERAL group). */
+typedef struct wc_mpc_config {
+    int32_t horizon;         /* N = round(controllerHorizon / sampling_time)  (:185-187) */
+    int32_t reserved;
+    double sampling_time;    /* dT   (:182, default 0.016) */
+    double com_height;       /* (:225) */
+    double gravity;          /* (:230, default 9.81) */
+    double Q[4];             /* state weight, row-major 2x2, AS SEEN BY THE SOLVER
+                                (i.e. after getTripletsFromValues' (col,row) swap, Utils.cpp:93-101) */
+    double R[4];             /* input weight, same convention */
+    double foot_x[2];        /* foot_size x limits as written in the ini (min max) (:262-263) */
+    double foot_y[2];        /* foot_size y limits (:280-281) */
+    double initial_zmp[2];   /* initial_zmp_position (:317-344) */
+    double hull_tolerance;   /* convex_hull_tolerance (:306, default 0.01) */
+    wc_osqp_settings osqp;
+} wc_mpc_config;
+
+void wc_osqp_default_settings(wc_osqp_settings* s);
+/* iCubGazeboV2_5 shipped parameters with the given horizon (25 = BASELINE configs, 200 = shipped). */
+void wc_mpc_default_config(wc_mpc_config* cfg, int32_t horizon);
+
+/* ---------------------------------------------------------------------------------- */
+/* Batched DCM-MPC:  replaces WalkingController + MPCSolver + OsqpEigen/OSQP            */
+/* (WalkingDCMModelPredictiveController.hpp:190-250, MPCSolver.hpp:27-139).             */
+/* ---------------------------------------------------------------------------------- */
+typedef struct wc_mpc wc_mpc;
+
+/* WalkingController::initialize (:311-362) for B instances on CUDA device `device`.
+ * Optional per-instance weight overrides (gain sweeps, BASELINE config 4) via
+ * wc_mpc_set_weights_*. */
+wc_status wc_mpc_create(const wc_mpc_config* cfg, int32_t B, int32_t device, wc_mpc** out);
+void wc_mpc_destroy(wc_mpc* h);
+int32_t wc_mpc_batch(const wc_mpc* h);
+int32_t wc_mpc_horizon(const wc_mpc* h);
+
+/* Per-instance diagonal weights q_diag[2*B], r_diag[2*B] (field-major), host pointers.
+ * Must be called before the first tick or right after wc_mpc_reset. */
+wc_status wc_mpc_set_weights_host(wc_mpc* h, const double* q_diag, const double* r_diag);
+
+/* WalkingController::reset (:537-543): forget the feet status for the masked instances
+ * (mask == NULL: all), so that the next tick rebuilds hull + solver. mask is a HOST array. */
+wc_status wc_mpc_reset(wc_mpc* h, const uint8_t* mask_host);
+
+/* One control tick of the MPC block (WalkingModule.cpp:601-637), fused:
+ *   setConvexHullConstraint(left.front(), right.front(), leftInContact.front(), rightInContact.front())
+ *   setFeedback(dcm_meas) ; setReferenceSignal(ref, reset) ; solve() ; getControllerOutput(zmp)
+ * Inputs (field-major SoA, B instances):
+ *   lf_H, rf_H   [12*B]  world_H_foot, row-major 3x4 ([R|p]) per instance: element e at [e*B+i]
+ *   l_contact, r_contact [B] uint8
+ *   dcm_meas     [2*B]
+ *   ref          [(N+1)*2*B]  DCM reference window: sample k, axis a at [(2*k+a)*B + i]
+ *                (a shorter deque is padded with its last sample by the caller, MPCSolver.cpp:201-215)
+ *   reset        [B] uint8 or NULL (= all 0)  resetTrajectory flag
+ * Outputs:
+ *   zmp [2*B] desired ZMP u0 (m_output: the last accepted output when the solve fails);
+ *   osqp_status [B], iters [B], flags [B] (WC_MPC_FLAG_* mask); any may be NULL. */
+wc_status wc_mpc_tick_dev(wc_mpc* h,
+                          const double* lf_H, const double* rf_H,
+                          const uint8_t* l_contact, const uint8_t* r_contact,
+                          const double* dcm_meas, const double* ref, const uint8_t* reset,
+                          double* zmp, int32_t* osqp_status, int32_t* iters, int32_t* flags,
+                          void* stream);
+/* Same with HOST pointers (pinned staging + H2D/D2H inside the call, synchronous on return). */
+wc_status wc_mpc_tick_host(wc_mpc* h,
+                           const double* lf_H, const double* rf_H,
+                           const uint8_t* l_contact, const uint8_t* r_contact,
+                           const double* dcm_meas, const double* ref, const uint8_t* reset,
+                           double* zmp, int32_t* osqp_status, int32_t* iters, int32_t* flags);
+
+/* Debug / parity taps (device -> host copies, synchronous): full primal solution
+ * z = [x_0..x_N, u_0..u_{N-1}] per instance ([n*B], field-major, n = 4N+2), the current
+ * rho and number of rho updates of the instance's solver.  Any pointer may be NULL. */
+wc_status wc_mpc_debug_get_host(wc_mpc* h, double* primal, double* rho, int32_t* rho_updates);
+
+/* Number of kernels launched by this handle since creation (bench.py's gpu_launches). */
+int64_t wc_mpc_launch_count(const wc_mpc* h);
+
+/* ---------------------------------------------------------------------------------- */
+/* Kinematic model table (replaces the iDynTree::Model loaded from model.urdf,          */
+/* WalkingModule.cpp:104-119; the URDF is not part of the reference repository).        */
+/* ---------------------------------------------------------------------------------- */
+#define WC_MAX_LINKS 40
+#define WC_MAX_DOFS 32
+
+typedef struct wc_model {
+    int32_t n_links;                    /* link 0 is the URDF root (root_link) */
+    int32_t n_dofs;                     /* actuated joints, reference order (robotControl.ini:3-7) */
+    int32_t parent[WC_MAX_LINKS];       /* parent link (-1 for link 0); parent[i] < i */
+    int32_t dof[WC_MAX_LINKS];          /* dof index of the joint parent->link, -1 = fixed joint */
+    double  joint_R[WC_MAX_LINKS][9];   /* parent_R_jointframe, row-major */
+    double  joint_p[WC_MAX_LINKS][3];   /* origin of the joint frame in the parent link frame */
+    double  axis[WC_MAX_LINKS][3];      /* revolute axis in the joint (= child link) frame, unit */
+    double  mass[WC_MAX_LINKS];
+    double  com[WC_MAX_LINKS][3];       /* link CoM in link frame */
+    int32_t l_sole_link, r_sole_link, neck_link; /* links the three task frames are attached to */
+    int32_t reserved;
+    double  l_sole_R[9], l_sole_p[3];   /* link_H_frame of l_sole */
+    double  r_sole_R[9], r_sole_p[3];
+    double  neck_R[9], neck_p[3];
+} wc_model;
+
+/* Built-in iCub-like 23-DoF model (synthetic geometry/inertia; joint order =
+ * app/robots/iCubGazeboV2_5/robotControl.ini:3-7). */
+void wc_model_icub_like(wc_model* m);
+
+/* Configuration of the QP-IK (WalkingQPIK::initializeMatrices,
+ * WalkingQPInverseKinematics.cpp:25-116; WalkingQPIK_qpOASES::initialize,
+ * WalkingQPInverseKinematics_qpOASES.cpp:53-133; values from qpInverseKinematics.ini). */
+typedef struct wc_ik_config {
+    int32_t n_dofs;                     /* actuatedDOFs (23) */
+    int32_t use_com_as_constraint;      /* useCoMAsConstraint (:66) */
+    double com_weight[9];               /* comWeightTriplets as seen by the solver (only if !constraint) */
+    double neck_weight[9];              /* neckWeightTriplets as seen by the solver, row-major 3x3 */
+    double additional_rotation[9];      /* additional_rotation, row-major (:118) */
+    double joint_reg_rad[WC_MAX_DOFS];  /* jointRegularization, already deg->rad (:94-103) */
+    double joint_reg_weight[WC_MAX_DOFS]; /* jointRegularizationWeights */
+    double joint_reg_gain[WC_MAX_DOFS]; /* jointRegularizationGains */
+    double k_pos_foot, k_att_foot, k_neck, k_pos_com;
+    double min_vel[WC_MAX_DOFS];        /* minJointsLimit passed to initialize (rad/s) */
+    double max_vel[WC_MAX_DOFS];
+    int32_t nwsr;                       /* 100 (:312) */
+    int32_t reserved;
+} wc_ik_config;
+
+void wc_ik_default_config(wc_ik_config* cfg); /* iCubGazeboV2_5 values, v_max = 1 rad/s placeholder */
+
+/* qpOASES-style return codes of the batched QP-IK solve (names follow qpOASES
+ * MessageHandling.hpp; numeric values are ours - the reference collapses them to bool,
+ * WalkingQPInverseKinematics_qpOASES.cpp:316-335). */
+enum {
+    WC_QP_SUCCESSFUL_RETURN = 0,
+    WC_QP_MAX_NWSR_REACHED = 1,
+    WC_QP_INFEASIBLE = 2,     /* RET_INIT_FAILED_INFEASIBILITY / RET_HOTSTART_STOPPED_INFEASIBILITY */
+    WC_QP_NOT_CONVEX = 3      /* projected Hessian not positive definite (RET_*_UNBOUNDEDNESS) */
+};
+
+/* ---------------------------------------------------------------------------------- */
+/* Batched FK + QP-IK: replaces WalkingFK (KinDynComputations) + WalkingQPIK_qpOASES    */
+/* (WalkingForwardKinematics.hpp:73-220, WalkingQPInverseKinematics.hpp:25-209).        */
+/* ---------------------------------------------------------------------------------- */
+typedef struct wc_ik wc_ik;
+
+wc_status wc_ik_create(const wc_ik_config* cfg, const wc_model* model, int32_t B, int32_t device, wc_ik** out);
+void wc_ik_destroy(wc_ik* h);
+int32_t wc_ik_batch(const wc_ik* h);
+
+/* Per-instance gain overrides k_pos_foot[B], k_att_foot[B] (gain sweeps). Host pointers. */
+wc_status wc_ik_set_gains_host(wc_ik* h, const double* k_pos_foot, const double* k_att_foot);
+
+/* One control tick of the FK + QP-IK block (WalkingModule.cpp:715-744 + solveQPIK :367-425):
+ *   WalkingFK::evaluateWorldToBaseTransformation / setInternalRobotState(q_lin, .)
+ *   setRobotState(q_meas, FK(l_sole), FK(r_sole), FK(neck), com_meas)
+ *   setDesiredNeckOrientation(neck_R_des) ; setDesiredFeetTransformation ; setDesiredFeetTwist
+ *   setDesiredCoMVelocity ; setDesiredCoMPosition ; set*Jacobian(FK) ; solve() ; getSolution(dq)
+ * Inputs (field-major SoA):
+ *   q_meas [nJ*B]  measured joint positions (regularisation term, quirk 9 of SURVEY §8)
+ *   q_lin  [nJ*B]  joint positions the kinematics is linearised about (integrated desired)
+ *   base_H [12*B]  world_H_stancefoot-SOLE frame (desired foot transform on the stance side)
+ *   left_is_fixed [B] uint8  stance flag (base link = l_foot / r_foot link)
+ *   lf_H_des, rf_H_des [12*B], lf_twist, rf_twist [6*B] (mixed: linear then angular),
+ *   com_pos_des, com_vel_des, com_meas [3*B], neck_R_des [9*B] (the matrix passed to
+ *   setDesiredNeckOrientation, BEFORE right-multiplication by additional_rotation).
+ * Outputs: dq [nJ*B]; lf_err, rf_err [6*B] (getLeftFootError/getRightFootError);
+ *          qp_status [B] (WC_QP_*), nwsr [B] working-set changes.  May be NULL. */
+wc_status wc_ik_tick_dev(wc_ik* h,
+                         const double* q_meas, const double* q_lin,
+                         const double* base_H, const uint8_t* left_is_fixed,
+                         const double* lf_H_des, const double* rf_H_des,
+                         const double* lf_twist, const double* rf_twist,
+                         const double* com_pos_des, const double* com_vel_des,
+                         const double* com_meas, const double* neck_R_des,
+                         double* dq, double* lf_err, double* rf_err,
+                         int32_t* qp_status, int32_t* nwsr, void* stream);
+wc_status wc_ik_tick_host(wc_ik* h,
+                          const double* q_meas, const double* q_lin,
+                          const double* base_H, const uint8_t* left_is_fixed,
+                          const double* lf_H_des, const double* rf_H_des,
+                          const double* lf_twist, const double* rf_twist,
+                          const double* com_pos_des, const double* com_vel_des,
+                          const double* com_meas, const double* neck_R_des,
+                          double* dq, double* lf_err, double* rf_err,
+                          int32_t* qp_status, int32_t* nwsr);
+
+/* Forward kinematics only (WalkingFK getters, WalkingForwardKinematics.cpp:411-454):
+ * for each instance the world transforms of l_sole, r_sole [12*B each], neck rotation [9*B],
+ * CoM position [3*B] and the four Jacobians in MIXED representation, row-major per
+ * instance, field-major across instances: J_lf, J_rf, J_neck [6*(nJ+6)*B], J_com [3*(nJ+6)*B].
+ * Device pointers; any output may be NULL. */
+wc_status wc_fk_dev(wc_ik* h, const double* q, const double* base_H, const uint8_t* left_is_fixed,
+                    double* lf_H, double* rf_H, double* neck_R, double* com,
+                    double* J_lf, double* J_rf, double* J_neck, double* J_com, void* stream);
+
+/* QP-IK with CALLER-SUPPLIED kinematics (the WalkingQPIK drop-in at B=1 / arbitrary models):
+ * bypasses the FK kernel; same QP build + solve.  Jacobians 6x(nJ+6) (neck: full 6 rows, rows 3-5
+ * are used, WalkingQPInverseKinematics.cpp:214-215), J_com 3x(nJ+6); lf_H, rf_H [12*B] and
+ * neck_R [9*B] are the CURRENT transforms (setRobotState).  Device pointers. */
+wc_status wc_ik_solve_with_jacobians_dev(wc_ik* h,
+                         const double* q_meas,
+                         const double* lf_H, const double* rf_H, const double* neck_R, const double* com_meas,
+                         const double* J_lf, const double* J_rf, const double* J_neck, const double* J_com,
+                         const double* lf_H_des, const double* rf_H_des,
+                         const double* lf_twist, const double* rf_twist,
+                         const double* com_pos_des, const double* com_vel_des, const double* neck_R_des,
+                         double* dq, double* lf_err, double* rf_err,
+                         int32_t* qp_status, int32_t* nwsr, void* stream);
+
+int64_t wc_ik_launch_count(const wc_ik* h);
+
+/* Library/ABI version string, e.g. "wc_b200 0.1 sm_100a". */
+const char* wc_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WC_CAPI_H */

@@ -1,0 +1,245 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY.
+
+ctypes binding of oracle/liboracle.so, the CPU restatement of the reference hot path
+(see oracle/README.md).  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs may import this module; the product package never does.
+
+PARITY UNPINNED: the reference holds no tests/golden vectors for this path and its solvers
+(OSQP, qpOASES, iDynTree) are not available offline; see DESIGN.md.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+WCO_MAX_HULL = 8
+WC_MAX_LINKS = 40
+WC_MAX_DOFS = 32
+
+
+class OsqpSettings(C.Structure):
+    _fields_ = [("rho", C.c_double), ("sigma", C.c_double), ("alpha", C.c_double),
+                ("eps_abs", C.c_double), ("eps_rel", C.c_double),
+                ("eps_prim_inf", C.c_double), ("eps_dual_inf", C.c_double),
+                ("adaptive_rho_tolerance", C.c_double), ("infty", C.c_double),
+                ("max_iter", C.c_int32), ("scaling", C.c_int32), ("check_termination", C.c_int32),
+                ("adaptive_rho", C.c_int32), ("adaptive_rho_interval", C.c_int32),
+                ("warm_start", C.c_int32), ("reserved0", C.c_int32), ("reserved1", C.c_int32)]
+
+
+class MpcConfig(C.Structure):
+    _fields_ = [("horizon", C.c_int32), ("reserved", C.c_int32),
+                ("sampling_time", C.c_double), ("com_height", C.c_double), ("gravity", C.c_double),
+                ("Q", C.c_double * 4), ("R", C.c_double * 4),
+                ("foot_x", C.c_double * 2), ("foot_y", C.c_double * 2),
+                ("initial_zmp", C.c_double * 2), ("hull_tolerance", C.c_double),
+                ("osqp", OsqpSettings)]
+
+
+class Model(C.Structure):
+    _fields_ = [("n_links", C.c_int32), ("n_dofs", C.c_int32),
+                ("parent", C.c_int32 * WC_MAX_LINKS), ("dof", C.c_int32 * WC_MAX_LINKS),
+                ("joint_R", (C.c_double * 9) * WC_MAX_LINKS),
+                ("joint_p", (C.c_double * 3) * WC_MAX_LINKS),
+                ("axis", (C.c_double * 3) * WC_MAX_LINKS),
+                ("mass", C.c_double * WC_MAX_LINKS),
+                ("com", (C.c_double * 3) * WC_MAX_LINKS),
+                ("l_sole_link", C.c_int32), ("r_sole_link", C.c_int32), ("neck_link", C.c_int32),
+                ("reserved", C.c_int32),
+                ("l_sole_R", C.c_double * 9), ("l_sole_p", C.c_double * 3),
+                ("r_sole_R", C.c_double * 9), ("r_sole_p", C.c_double * 3),
+                ("neck_R", C.c_double * 9), ("neck_p", C.c_double * 3)]
+
+
+class IkConfig(C.Structure):
+    _fields_ = [("n_dofs", C.c_int32), ("use_com_as_constraint", C.c_int32),
+                ("com_weight", C.c_double * 9), ("neck_weight", C.c_double * 9),
+                ("additional_rotation", C.c_double * 9),
+                ("joint_reg_rad", C.c_double * WC_MAX_DOFS),
+                ("joint_reg_weight", C.c_double * WC_MAX_DOFS),
+                ("joint_reg_gain", C.c_double * WC_MAX_DOFS),
+                ("k_pos_foot", C.c_double), ("k_att_foot", C.c_double),
+                ("k_neck", C.c_double), ("k_pos_com", C.c_double),
+                ("min_vel", C.c_double * WC_MAX_DOFS), ("max_vel", C.c_double * WC_MAX_DOFS),
+                ("nwsr", C.c_int32), ("reserved", C.c_int32)]
+
+
+def build(force=False):
+    """Compile oracle/liboracle.so (gcc, plain C) if missing or stale."""
+    so = os.path.join(_HERE, "liboracle.so")
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".c", ".h"))]
+    srcs.append(os.path.join(_HERE, "..", "include", "wc_capi.h"))
+    srcs.append(os.path.join(_HERE, "..", "walking-controllers_b200", "csrc", "wc_defaults.c"))
+    stale = force or not os.path.exists(so) or any(
+        os.path.getmtime(s) > os.path.getmtime(so) for s in srcs if os.path.exists(s))
+    if stale:
+        subprocess.check_call(["make", "-C", _HERE, "-B"], stdout=subprocess.DEVNULL)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        so = os.path.join(_HERE, "liboracle.so")
+        if not os.path.exists(so):
+            build()
+        L = C.CDLL(so)
+        dp = C.POINTER(C.c_double)
+        ip = C.POINTER(C.c_int32)
+        up = C.POINTER(C.c_uint8)
+        L.wc_mpc_default_config.argtypes = [C.POINTER(MpcConfig), C.c_int32]
+        L.wc_osqp_default_settings.argtypes = [C.POINTER(OsqpSettings)]
+        L.wc_ik_default_config.argtypes = [C.POINTER(IkConfig)]
+        L.wc_model_icub_like.argtypes = [C.POINTER(Model)]
+        L.wco_hull_build.argtypes = [dp, C.c_int, dp, dp, dp]
+        L.wco_hull_build.restype = C.c_int
+        L.wco_hull_margin.argtypes = [dp, dp, dp, C.c_int, dp]
+        L.wco_hull_margin.restype = C.c_double
+        L.wco_mpc_batch_create.argtypes = [C.POINTER(MpcConfig), C.c_int]
+        L.wco_mpc_batch_create.restype = C.c_void_p
+        L.wco_mpc_batch_free.argtypes = [C.c_void_p]
+        L.wco_mpc_batch_get.argtypes = [C.c_void_p, C.c_int]
+        L.wco_mpc_batch_get.restype = C.c_void_p
+        L.wco_mpc_batch_set_weights.argtypes = [C.c_void_p, dp, dp]
+        L.wco_mpc_batch_reset.argtypes = [C.c_void_p, up]
+        L.wco_mpc_batch_tick.argtypes = [C.c_void_p, dp, dp, up, up, dp, dp, up, dp, ip, ip, ip, C.c_int]
+        L.wco_mpc_batch_get_solution.argtypes = [C.c_void_p, dp, dp, ip]
+        L.wco_mpc_set_linsys.argtypes = [C.c_void_p, C.c_int]
+        L.wco_mpc_n_hull.argtypes = [C.c_void_p]
+        L.wco_mpc_n_hull.restype = C.c_int
+        L.wco_mpc_get_hull.argtypes = [C.c_void_p, dp, dp]
+        L.wco_mpc_get_qp_dense.argtypes = [C.c_void_p, dp, dp, dp, dp, dp]
+        L.wco_mpc_get_qp_dense.restype = C.c_int
+        L.wco_osqp_solve_dense.argtypes = [C.c_int, C.c_int, dp, dp, dp, dp, dp,
+                                           C.POINTER(OsqpSettings), C.c_int, dp, dp, dp]
+        L.wco_osqp_solve_dense.restype = C.c_int
+        _LIB = L
+    return _LIB
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double)) if a is not None else None
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int32)) if a is not None else None
+
+
+def _up(a):
+    return a.ctypes.data_as(C.POINTER(C.c_uint8)) if a is not None else None
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _u8(a):
+    return np.ascontiguousarray(a, dtype=np.uint8)
+
+
+def mpc_default_config(horizon=25):
+    cfg = MpcConfig()
+    lib().wc_mpc_default_config(C.byref(cfg), horizon)
+    return cfg
+
+
+def osqp_default_settings():
+    s = OsqpSettings()
+    lib().wc_osqp_default_settings(C.byref(s))
+    return s
+
+
+def ik_default_config():
+    cfg = IkConfig()
+    lib().wc_ik_default_config(C.byref(cfg))
+    return cfg
+
+
+def model_icub_like():
+    m = Model()
+    lib().wc_model_icub_like(C.byref(m))
+    return m
+
+
+def hull_build(points):
+    pts = _f64(points).reshape(-1, 2)
+    A = np.zeros((WCO_MAX_HULL, 2)); b = np.zeros(WCO_MAX_HULL); v = np.zeros((WCO_MAX_HULL, 2))
+    nh = lib().wco_hull_build(_dp(pts), pts.shape[0], _dp(A), _dp(b), _dp(v))
+    return A[:nh].copy(), b[:nh].copy(), v[:nh].copy()
+
+
+def hull_margin(A, b, v, z):
+    A = _f64(A); b = _f64(b); v = _f64(v); z = _f64(z)
+    return lib().wco_hull_margin(_dp(A), _dp(b), _dp(v), A.shape[0], _dp(z))
+
+
+def osqp_solve_dense(P, A, q, l, u, settings=None, linsys=0):
+    P = _f64(P); A = _f64(A); q = _f64(q); l = _f64(l); u = _f64(u)
+    n, m = P.shape[0], A.shape[0]
+    s = settings or osqp_default_settings()
+    x = np.zeros(n); y = np.zeros(max(m, 1)); info = np.zeros(5)
+    st = lib().wco_osqp_solve_dense(n, m, _dp(P), _dp(A), _dp(q), _dp(l), _dp(u), C.byref(s), linsys,
+                                    _dp(x), _dp(y), _dp(info))
+    return dict(status=st, x=x, y=y[:m], iter=int(info[0]), rho_updates=int(info[1]), rho=info[2],
+                pri_res=info[3], dua_res=info[4])
+
+
+class MpcBatch:
+    """Batched oracle MPC with the same SoA layout as wc_mpc_tick_host (include/wc_capi.h)."""
+
+    def __init__(self, cfg, B, linsys=0):
+        self.cfg, self.B, self.N = cfg, B, cfg.horizon
+        self.h = lib().wco_mpc_batch_create(C.byref(cfg), B)
+        if linsys:
+            for i in range(B):
+                lib().wco_mpc_set_linsys(lib().wco_mpc_batch_get(self.h, i), linsys)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().wco_mpc_batch_free(self.h)
+            self.h = None
+
+    def set_weights(self, q_diag, r_diag):
+        q = _f64(q_diag); r = _f64(r_diag)
+        lib().wco_mpc_batch_set_weights(self.h, _dp(q), _dp(r))
+
+    def reset(self, mask=None):
+        m = _u8(mask) if mask is not None else None
+        lib().wco_mpc_batch_reset(self.h, _up(m))
+
+    def tick(self, lf_H, rf_H, l_contact, r_contact, dcm, ref, reset=None, threads=1):
+        B = self.B
+        lf_H = _f64(lf_H); rf_H = _f64(rf_H); dcm = _f64(dcm); ref = _f64(ref)
+        lc = _u8(l_contact); rc = _u8(r_contact)
+        rs = _u8(reset) if reset is not None else None
+        assert lf_H.size == 12 * B and ref.size == 2 * (self.N + 1) * B
+        zmp = np.zeros((2, B)); st = np.zeros(B, np.int32); it = np.zeros(B, np.int32); fl = np.zeros(B, np.int32)
+        lib().wco_mpc_batch_tick(self.h, _dp(lf_H), _dp(rf_H), _up(lc), _up(rc), _dp(dcm), _dp(ref), _up(rs),
+                                 _dp(zmp), _ip(st), _ip(it), _ip(fl), threads)
+        return zmp, st, it, fl
+
+    def solution(self):
+        n = 4 * self.N + 2
+        primal = np.zeros((n, self.B)); rho = np.zeros(self.B); ru = np.zeros(self.B, np.int32)
+        lib().wco_mpc_batch_get_solution(self.h, _dp(primal), _dp(rho), _ip(ru))
+        return primal, rho, ru
+
+    def qp_dense(self, i):
+        n = 4 * self.N + 2
+        mmax = 2 * (self.N + 1) + WCO_MAX_HULL
+        P = np.zeros((n, n)); A = np.zeros((mmax, n)); q = np.zeros(n); l = np.zeros(mmax); u = np.zeros(mmax)
+        inst = lib().wco_mpc_batch_get(self.h, i)
+        m = lib().wco_mpc_get_qp_dense(inst, _dp(P), _dp(A), _dp(q), _dp(l), _dp(u))
+        A = A.reshape(-1)[: m * n].reshape(m, n).copy()
+        return P, A, q, l[:m].copy(), u[:m].copy()
+
+    def hull(self, i):
+        inst = lib().wco_mpc_batch_get(self.h, i)
+        nh = lib().wco_mpc_n_hull(inst)
+        A = np.zeros((WCO_MAX_HULL, 2)); b = np.zeros(WCO_MAX_HULL)
+        lib().wco_mpc_get_hull(inst, _dp(A), _dp(b))
+        return A[:nh].copy(), b[:nh].copy()

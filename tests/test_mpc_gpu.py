@@ -1,0 +1,129 @@
+"""GPU parity of the batched DCM-MPC (K1 problem build + K2 ADMM) against the oracle.
+
+Tolerance (BASELINE.json north_star): relative 1e-6 on the MPC ZMP output, identical OSQP
+status codes and iteration counts.  Calls go through the C ABI (wc_mpc_tick_dev / _host)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-6
+
+
+def run_both(wc, syn, oracle, cuda_device, B, T, N, seed=0x5EED, host_api=False, weights=None, noise=0.002,
+             settings=None):
+    g = syn.GaitBatch(B, T, N, seed=seed, noise_dcm=noise)
+    traj = g.trajectory()
+    cfg_o = oracle.mpc_default_config(N)
+    cfg_g = wc.mpc_default_config(N)
+    if settings:
+        for k, v in settings.items():
+            setattr(cfg_o.osqp, k, v); setattr(cfg_g.osqp, k, v)
+    mo = oracle.MpcBatch(cfg_o, B)
+    mg = wc.MpcBatch(cfg_g, B)
+    if weights is not None:
+        q, r = weights
+        mo.set_weights(q, r); mg.set_weights(np.ascontiguousarray(q), np.ascontiguousarray(r))
+    traj_d = traj.to(cuda_device)
+    worst = 0.0
+    stats = dict(iters=[], status=[], new=0)
+    for t in range(T):
+        f = g.feet(t)
+        dcm = g.measured_dcm(t)
+        ref = traj[2 * t: 2 * t + 2 * (N + 1)].contiguous()
+        zo, so, io_, fo = mo.tick(f["lf_H"].numpy(), f["rf_H"].numpy(), f["l_contact"].numpy(), f["r_contact"].numpy(),
+                                  dcm.numpy(), ref.numpy())
+        if host_api:
+            out = mg.tick_host(f["lf_H"].numpy(), f["rf_H"].numpy(), f["l_contact"].numpy(), f["r_contact"].numpy(),
+                               dcm.numpy(), ref.numpy())
+            zg, sg, ig, fg = out["zmp"], out["status"], out["iters"], out["flags"]
+        else:
+            out = mg.tick(f["lf_H"].to(cuda_device), f["rf_H"].to(cuda_device), f["l_contact"].to(cuda_device),
+                          f["r_contact"].to(cuda_device), dcm.to(cuda_device),
+                          traj_d[2 * t: 2 * t + 2 * (N + 1)])
+            torch.cuda.synchronize()
+            zg, sg, ig, fg = (out[k].cpu().numpy() for k in ("zmp", "status", "iters", "flags"))
+        assert np.array_equal(sg, so), f"tick {t}: status differs {sg[sg != so]} vs {so[sg != so]}"
+        assert np.array_equal(ig, io_), f"tick {t}: iteration count differs at {np.nonzero(ig != io_)[0]}: {ig[ig != io_]} vs {io_[ig != io_]}"
+        assert np.array_equal(fg, fo), f"tick {t}: flags differ"
+        err = np.abs(zg - zo) / np.maximum(1.0, np.abs(zo))
+        worst = max(worst, float(err.max()))
+        assert err.max() <= REL, f"tick {t}: zmp rel err {err.max()}"
+        stats["iters"].append(ig.copy()); stats["status"].append(sg.copy()); stats["new"] += int(((fg & 16) != 0).sum())
+    # full primal solution + rho of the final tick
+    po, rho_o, ru_o = mo.solution()
+    pg, rho_g, ru_g = mg.debug()
+    assert np.allclose(rho_g, rho_o, rtol=1e-9)
+    assert np.array_equal(ru_g, ru_o)
+    scale = np.maximum(1.0, np.abs(po))
+    assert (np.abs(pg - po) / scale).max() <= REL
+    stats["worst"] = worst
+    mg.close()
+    return stats
+
+
+def test_mpc_parity_walking_n25(wc, syn, oracle, cuda_device):
+    st = run_both(wc, syn, oracle, cuda_device, B=96, T=120, N=25)
+    assert st["new"] >= 96  # every instance built at least one solver
+    print("worst rel err", st["worst"])
+
+
+def test_mpc_parity_host_api(wc, syn, oracle, cuda_device):
+    run_both(wc, syn, oracle, cuda_device, B=33, T=40, N=25, host_api=True, seed=7)
+
+
+@pytest.mark.parametrize("N", [1, 2, 10, 50, 100])
+def test_mpc_parity_horizons(wc, syn, oracle, cuda_device, N):
+    run_both(wc, syn, oracle, cuda_device, B=20, T=30, N=N, seed=100 + N)
+
+
+def test_mpc_parity_gain_sweep_and_disturbance(wc, syn, oracle, cuda_device):
+    """BASELINE config 4: Q in 7500*{0.1..10}, R in 9e6*{0.1,1,10}; large DCM noise makes OSQP run long
+    enough to exercise the adaptive-rho re-factorisation path."""
+    B = 60
+    rng = np.random.default_rng(3)
+    q = 7500.0 * rng.choice([0.1, 0.3, 1, 3, 10], size=B)
+    r = 9e6 * rng.choice([0.1, 1, 10], size=B)
+    qd = np.stack([q, q]); rd = np.stack([r, r])
+    st = run_both(wc, syn, oracle, cuda_device, B=B, T=60, N=25, weights=(qd, rd), noise=0.03, seed=11)
+    its = np.concatenate(st["iters"])
+    print("iteration histogram", np.unique(its, return_counts=True))
+
+
+def test_mpc_parity_rho_adaptation(wc, syn, oracle, cuda_device):
+    """tight tolerances force >100 iterations so that adapt_rho + re-factorisation are covered"""
+    st = run_both(wc, syn, oracle, cuda_device, B=24, T=12, N=25, seed=5, noise=0.02,
+                  settings=dict(eps_abs=1e-7, eps_rel=1e-7))
+    its = np.concatenate(st["iters"])
+    assert its.max() > 100
+
+
+def test_mpc_max_iter_status(wc, syn, oracle, cuda_device):
+    run_both(wc, syn, oracle, cuda_device, B=16, T=6, N=10, seed=9,
+             settings=dict(eps_abs=1e-12, eps_rel=1e-12, max_iter=60))
+    run_both(wc, syn, oracle, cuda_device, B=16, T=6, N=10, seed=9,
+             settings=dict(eps_abs=1e-12, eps_rel=1e-12, max_iter=50))
+
+
+def test_mpc_no_contact_and_reset(wc, syn, oracle, cuda_device):
+    B, N = 8, 10
+    g = syn.GaitBatch(B, 10, N, seed=1)
+    traj = g.trajectory()
+    mo = oracle.MpcBatch(oracle.mpc_default_config(N), B)
+    mg = wc.MpcBatch(wc.mpc_default_config(N), B)
+    for t in range(8):
+        f = g.feet(t)
+        lc = f["l_contact"].numpy().copy(); rc = f["r_contact"].numpy().copy()
+        if t in (0, 4):
+            lc[:3] = 0; rc[:3] = 0       # "None foot is in contact" (Controller.cpp:404-408)
+        if t == 6:
+            mo.reset(np.array([1, 0] * 4, np.uint8)); mg.reset(np.array([1, 0] * 4, np.uint8))
+        dcm = g.measured_dcm(t).numpy(); ref = traj[2 * t: 2 * t + 2 * (N + 1)].contiguous().numpy()
+        zo, so, io_, fo = mo.tick(f["lf_H"].numpy(), f["rf_H"].numpy(), lc, rc, dcm, ref)
+        out = mg.tick_host(f["lf_H"].numpy(), f["rf_H"].numpy(), lc, rc, dcm, ref)
+        assert np.array_equal(out["flags"], fo), (t, out["flags"], fo)
+        assert np.array_equal(out["status"], so)
+        assert np.array_equal(out["iters"], io_)
+        assert np.allclose(out["zmp"], zo, rtol=REL, atol=REL)
+    mg.close()

@@ -1,0 +1,232 @@
+"""walking-controllers_b200 — B200-native batched MPC + QP-IK hot path of walking-controllers.
+
+Python here is plumbing only: a ctypes view of the C ABI in include/wc_capi.h (the product is
+walking-controllers_b200/libwc_b200.so, hand-written CUDA for sm_100a) plus torch tensors for
+device memory / streams.  The directory name is not a Python identifier; import it with
+    importlib.import_module("walking-controllers_b200")
+There is NO CPU fallback: every compute entry point raises if the CUDA library is missing.
+"""
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libwc_b200.so")
+CSRC = os.path.join(_HERE, "csrc")
+
+WC_MAX_LINKS = 40
+WC_MAX_DOFS = 32
+
+# status / flag constants (include/wc_capi.h)
+OSQP_SOLVED = 1
+OSQP_SOLVED_INACCURATE = 2
+OSQP_MAX_ITER_REACHED = -2
+OSQP_PRIMAL_INFEASIBLE = -3
+OSQP_DUAL_INFEASIBLE = -4
+OSQP_UNSOLVED = -10
+MPC_FLAG_NO_CONTACT, MPC_FLAG_NO_SOLVER, MPC_FLAG_NOT_SOLVED, MPC_FLAG_OUTSIDE_HULL, MPC_FLAG_NEW_SOLVER = 1, 2, 4, 8, 16
+QP_SUCCESSFUL_RETURN, QP_MAX_NWSR_REACHED, QP_INFEASIBLE, QP_NOT_CONVEX = 0, 1, 2, 3
+
+
+class OsqpSettings(C.Structure):
+    _fields_ = [("rho", C.c_double), ("sigma", C.c_double), ("alpha", C.c_double),
+                ("eps_abs", C.c_double), ("eps_rel", C.c_double),
+                ("eps_prim_inf", C.c_double), ("eps_dual_inf", C.c_double),
+                ("adaptive_rho_tolerance", C.c_double), ("infty", C.c_double),
+                ("max_iter", C.c_int32), ("scaling", C.c_int32), ("check_termination", C.c_int32),
+                ("adaptive_rho", C.c_int32), ("adaptive_rho_interval", C.c_int32),
+                ("warm_start", C.c_int32), ("reserved0", C.c_int32), ("reserved1", C.c_int32)]
+
+
+class MpcConfig(C.Structure):
+    _fields_ = [("horizon", C.c_int32), ("reserved", C.c_int32),
+                ("sampling_time", C.c_double), ("com_height", C.c_double), ("gravity", C.c_double),
+                ("Q", C.c_double * 4), ("R", C.c_double * 4),
+                ("foot_x", C.c_double * 2), ("foot_y", C.c_double * 2),
+                ("initial_zmp", C.c_double * 2), ("hull_tolerance", C.c_double),
+                ("osqp", OsqpSettings)]
+
+
+class Model(C.Structure):
+    _fields_ = [("n_links", C.c_int32), ("n_dofs", C.c_int32),
+                ("parent", C.c_int32 * WC_MAX_LINKS), ("dof", C.c_int32 * WC_MAX_LINKS),
+                ("joint_R", (C.c_double * 9) * WC_MAX_LINKS),
+                ("joint_p", (C.c_double * 3) * WC_MAX_LINKS),
+                ("axis", (C.c_double * 3) * WC_MAX_LINKS),
+                ("mass", C.c_double * WC_MAX_LINKS),
+                ("com", (C.c_double * 3) * WC_MAX_LINKS),
+                ("l_sole_link", C.c_int32), ("r_sole_link", C.c_int32), ("neck_link", C.c_int32),
+                ("reserved", C.c_int32),
+                ("l_sole_R", C.c_double * 9), ("l_sole_p", C.c_double * 3),
+                ("r_sole_R", C.c_double * 9), ("r_sole_p", C.c_double * 3),
+                ("neck_R", C.c_double * 9), ("neck_p", C.c_double * 3)]
+
+
+class IkConfig(C.Structure):
+    _fields_ = [("n_dofs", C.c_int32), ("use_com_as_constraint", C.c_int32),
+                ("com_weight", C.c_double * 9), ("neck_weight", C.c_double * 9),
+                ("additional_rotation", C.c_double * 9),
+                ("joint_reg_rad", C.c_double * WC_MAX_DOFS),
+                ("joint_reg_weight", C.c_double * WC_MAX_DOFS),
+                ("joint_reg_gain", C.c_double * WC_MAX_DOFS),
+                ("k_pos_foot", C.c_double), ("k_att_foot", C.c_double),
+                ("k_neck", C.c_double), ("k_pos_com", C.c_double),
+                ("min_vel", C.c_double * WC_MAX_DOFS), ("max_vel", C.c_double * WC_MAX_DOFS),
+                ("nwsr", C.c_int32), ("reserved", C.c_int32)]
+
+
+def build(verbose=False):
+    """Compile libwc_b200.so for sm_100a with nvcc (cross-compiles without a GPU)."""
+    out = subprocess.run(["make", "-C", CSRC], capture_output=True, text=True)
+    if verbose or out.returncode != 0:
+        print(out.stdout[-4000:])
+        print(out.stderr[-4000:])
+    if out.returncode != 0:
+        raise RuntimeError("building libwc_b200.so failed")
+    return LIB_PATH
+
+
+_LIB = None
+_VP = C.c_void_p
+
+
+def lib():
+    """The C-ABI library.  Raises if it has not been built: there is no fallback path."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(the product has no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    i32, i64 = C.c_int32, C.c_int64
+    L.wc_version.restype = C.c_char_p
+    L.wc_osqp_default_settings.argtypes = [C.POINTER(OsqpSettings)]
+    L.wc_mpc_default_config.argtypes = [C.POINTER(MpcConfig), i32]
+    L.wc_ik_default_config.argtypes = [C.POINTER(IkConfig)]
+    L.wc_model_icub_like.argtypes = [C.POINTER(Model)]
+    L.wc_mpc_create.argtypes = [C.POINTER(MpcConfig), i32, i32, C.POINTER(_VP)]
+    L.wc_mpc_create.restype = i32
+    L.wc_mpc_destroy.argtypes = [_VP]
+    L.wc_mpc_batch.argtypes = [_VP]; L.wc_mpc_batch.restype = i32
+    L.wc_mpc_horizon.argtypes = [_VP]; L.wc_mpc_horizon.restype = i32
+    L.wc_mpc_set_weights_host.argtypes = [_VP, _VP, _VP]; L.wc_mpc_set_weights_host.restype = i32
+    L.wc_mpc_reset.argtypes = [_VP, _VP]; L.wc_mpc_reset.restype = i32
+    L.wc_mpc_tick_dev.argtypes = [_VP] + [_VP] * 11 + [_VP]; L.wc_mpc_tick_dev.restype = i32
+    L.wc_mpc_tick_host.argtypes = [_VP] + [_VP] * 11; L.wc_mpc_tick_host.restype = i32
+    L.wc_mpc_debug_get_host.argtypes = [_VP, _VP, _VP, _VP]; L.wc_mpc_debug_get_host.restype = i32
+    L.wc_mpc_launch_count.argtypes = [_VP]; L.wc_mpc_launch_count.restype = i64
+    if hasattr(L, "wc_ik_create"):
+        L.wc_ik_create.argtypes = [C.POINTER(IkConfig), C.POINTER(Model), i32, i32, C.POINTER(_VP)]
+        L.wc_ik_create.restype = i32
+        L.wc_ik_destroy.argtypes = [_VP]
+        L.wc_ik_batch.argtypes = [_VP]; L.wc_ik_batch.restype = i32
+        L.wc_ik_set_gains_host.argtypes = [_VP, _VP, _VP]; L.wc_ik_set_gains_host.restype = i32
+        L.wc_ik_tick_dev.argtypes = [_VP] + [_VP] * 17 + [_VP]; L.wc_ik_tick_dev.restype = i32
+        L.wc_ik_tick_host.argtypes = [_VP] + [_VP] * 17; L.wc_ik_tick_host.restype = i32
+        L.wc_fk_dev.argtypes = [_VP] + [_VP] * 11 + [_VP]; L.wc_fk_dev.restype = i32
+        L.wc_ik_solve_with_jacobians_dev.argtypes = [_VP] + [_VP] * 21 + [_VP]
+        L.wc_ik_solve_with_jacobians_dev.restype = i32
+        L.wc_ik_launch_count.argtypes = [_VP]; L.wc_ik_launch_count.restype = i64
+    _LIB = L
+    return L
+
+
+def mpc_default_config(horizon=25):
+    cfg = MpcConfig()
+    lib().wc_mpc_default_config(C.byref(cfg), horizon)
+    return cfg
+
+
+def ik_default_config():
+    cfg = IkConfig()
+    lib().wc_ik_default_config(C.byref(cfg))
+    return cfg
+
+
+def model_icub_like():
+    m = Model()
+    lib().wc_model_icub_like(C.byref(m))
+    return m
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise RuntimeError(f"{what} failed with wc_status {rc}")
+
+
+def _ptr(t):
+    """device/host pointer of a torch tensor or numpy array (None -> NULL)"""
+    if t is None:
+        return None
+    if hasattr(t, "data_ptr"):
+        return t.data_ptr()
+    return t.ctypes.data
+
+
+class MpcBatch:
+    """Batched DCM-MPC handle (mirrors WalkingController for B instances).
+
+    tick(...) takes torch CUDA tensors (field-major SoA, float64 / uint8) and launches on the
+    current torch stream; tick_host(...) takes numpy arrays / CPU tensors and copies inside."""
+
+    def __init__(self, cfg, B, device=0):
+        self.cfg, self.B, self.N, self.device = cfg, B, cfg.horizon, device
+        h = _VP()
+        _check(lib().wc_mpc_create(C.byref(cfg), B, device, C.byref(h)), "wc_mpc_create")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().wc_mpc_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_weights(self, q_diag, r_diag):
+        _check(lib().wc_mpc_set_weights_host(self.h, _ptr(q_diag), _ptr(r_diag)), "wc_mpc_set_weights_host")
+
+    def reset(self, mask=None):
+        _check(lib().wc_mpc_reset(self.h, _ptr(mask)), "wc_mpc_reset")
+
+    def tick(self, lf_H, rf_H, l_contact, r_contact, dcm, ref, reset=None, out=None, stream=None):
+        import torch
+        B = self.B
+        if out is None:
+            dev = lf_H.device
+            out = dict(zmp=torch.empty(2, B, dtype=torch.float64, device=dev),
+                       status=torch.empty(B, dtype=torch.int32, device=dev),
+                       iters=torch.empty(B, dtype=torch.int32, device=dev),
+                       flags=torch.empty(B, dtype=torch.int32, device=dev))
+        if stream is None:
+            stream = torch.cuda.current_stream(lf_H.device).cuda_stream
+        _check(lib().wc_mpc_tick_dev(self.h, _ptr(lf_H), _ptr(rf_H), _ptr(l_contact), _ptr(r_contact), _ptr(dcm),
+                                     _ptr(ref), _ptr(reset), _ptr(out["zmp"]), _ptr(out["status"]),
+                                     _ptr(out["iters"]), _ptr(out["flags"]), stream), "wc_mpc_tick_dev")
+        return out
+
+    def tick_host(self, lf_H, rf_H, l_contact, r_contact, dcm, ref, reset=None, out=None):
+        import numpy as np
+        B = self.B
+        if out is None:
+            out = dict(zmp=np.empty((2, B)), status=np.empty(B, np.int32), iters=np.empty(B, np.int32),
+                       flags=np.empty(B, np.int32))
+        _check(lib().wc_mpc_tick_host(self.h, _ptr(lf_H), _ptr(rf_H), _ptr(l_contact), _ptr(r_contact), _ptr(dcm),
+                                      _ptr(ref), _ptr(reset), _ptr(out["zmp"]), _ptr(out["status"]),
+                                      _ptr(out["iters"]), _ptr(out["flags"])), "wc_mpc_tick_host")
+        return out
+
+    def debug(self):
+        import numpy as np
+        n = 4 * self.N + 2
+        primal = np.empty((n, self.B)); rho = np.empty(self.B); ru = np.empty(self.B, np.int32)
+        _check(lib().wc_mpc_debug_get_host(self.h, _ptr(primal), _ptr(rho), _ptr(ru)), "wc_mpc_debug_get_host")
+        return primal, rho, ru
+
+    @property
+    def launches(self):
+        return lib().wc_mpc_launch_count(self.h)

@@ -1,0 +1,935 @@
+// mpc_kernels.cu — see mpc_kernels.cuh for the mapping to the reference.
+#include "mpc_kernels.cuh"
+
+#include <cmath>
+
+namespace wcb {
+
+// chain order per axis: x_k <-> 2(N-k), u_k <-> 2(N-k)-1
+__device__ __forceinline__ int cx(int N, int k) { return 2 * (N - k); }
+__device__ __forceinline__ int cu(int N, int k) { return 2 * (N - k) - 1; }
+
+__device__ __forceinline__ double limit_scaling(double v)
+{
+    v = v < kMinScaling ? 1.0 : v;
+    v = v > kMaxScaling ? kMaxScaling : v;
+    return v;
+}
+
+// =====================================================================================
+// K1: per-instance problem build.  One thread per instance (the heavy branch, Ruiz
+// equilibration, only runs when the support phase changed).
+//   WalkingController::setConvexHullConstraint  (Controller.cpp:364-435)
+//   buildConvexHull -> iDynTree ConvexHullProjectionConstraint (external; restated)
+//   MPCSolver::MPCSolver / setGradient          (MPCSolver.cpp:16-52,183-266)
+//   osqp_setup: scale_data + cold start          (external; restated from OSQP 0.6)
+// =====================================================================================
+__device__ double cross2(const double* o, const double* a, const double* b)
+{
+    return (a[0] - o[0]) * (b[1] - o[1]) - (a[1] - o[1]) * (b[0] - o[0]);
+}
+
+__device__ int build_hull(const double (*pts)[2], int npts, double* A, double* b, double* v)
+{
+    double p[16][2], h[32][2];
+    int k = 0;
+    for (int i = 0; i < npts; i++) { p[i][0] = pts[i][0]; p[i][1] = pts[i][1]; }
+    for (int i = 1; i < npts; i++) {
+        const double x = p[i][0], y = p[i][1];
+        int j = i - 1;
+        while (j >= 0 && (p[j][0] > x || (p[j][0] == x && p[j][1] > y))) {
+            p[j + 1][0] = p[j][0]; p[j + 1][1] = p[j][1]; j--;
+        }
+        p[j + 1][0] = x; p[j + 1][1] = y;
+    }
+    for (int i = 0; i < npts; i++) {
+        while (k >= 2 && cross2(h[k - 2], h[k - 1], p[i]) <= 0) k--;
+        h[k][0] = p[i][0]; h[k][1] = p[i][1]; k++;
+    }
+    for (int i = npts - 2, j = k + 1; i >= 0; i--) {
+        while (k >= j && cross2(h[k - 2], h[k - 1], p[i]) <= 0) k--;
+        h[k][0] = p[i][0]; h[k][1] = p[i][1]; k++;
+    }
+    k--;
+    if (k > kMaxHull) k = kMaxHull;
+    for (int i = 0; i < k; i++) {
+        const double* p0 = h[i];
+        const double* p1 = h[(i + 1) % k];
+        A[2 * i] = p1[1] - p0[1];
+        A[2 * i + 1] = -(p1[0] - p0[0]);
+        b[i] = A[2 * i] * p0[0] + A[2 * i + 1] * p0[1];
+        v[2 * i] = p0[0]; v[2 * i + 1] = p0[1];
+    }
+    return k;
+}
+
+__device__ void foot_points(const MpcDev& d, const double* H, size_t B, int i, double (*out)[2])
+{
+    const double vx[4] = {d.foot_front, -d.foot_back, -d.foot_back, d.foot_front};
+    const double vy[4] = {d.foot_left, d.foot_left, -d.foot_right, -d.foot_right};
+    const double r00 = H[0 * B + i], r01 = H[1 * B + i], px = H[3 * B + i];
+    const double r10 = H[4 * B + i], r11 = H[5 * B + i], py = H[7 * B + i];
+    for (int k = 0; k < 4; k++) {
+        out[k][0] = r00 * vx[k] + r01 * vy[k] + px;
+        out[k][1] = r10 * vx[k] + r11 * vy[k] + py;
+    }
+}
+
+__global__ void __launch_bounds__(128) mpc_prepare_kernel(MpcDev d, MpcTickIO io)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d.B) return;
+    const size_t B = (size_t)d.B;
+    const int N = d.N, nA = 2 * N + 1, nR = N + 1;
+    const uint8_t cur = (uint8_t)((io.l_contact[i] ? 1 : 0) | (io.r_contact[i] ? 2 : 0));
+    int flags = 0;
+    if (cur != d.feet[i]) {
+        d.feet[i] = cur;
+        if (cur == 0) { d.tick_flags[i] = WC_MPC_FLAG_NO_CONTACT; return; }
+        double pts[8][2], A[16], b[8], v[16];
+        int npts = 0;
+        if (cur == 3) { foot_points(d, io.lf_H, B, i, pts); foot_points(d, io.rf_H, B, i, pts + 4); npts = 8; }
+        else if (cur == 1) { foot_points(d, io.lf_H, B, i, pts); npts = 4; }
+        else { foot_points(d, io.rf_H, B, i, pts); npts = 4; }
+        const int nh = build_hull(pts, npts, A, b, v);
+        d.nhull[i] = nh;
+        for (int h = 0; h < kMaxHull; h++) {
+            const bool on = h < nh;
+            d.hullA[(2 * h) * B + i] = on ? A[2 * h] : 0.0;
+            d.hullA[(2 * h + 1) * B + i] = on ? A[2 * h + 1] : 0.0;
+            d.hullb[h * B + i] = on ? b[h] : 0.0;
+            d.hullv[(2 * h) * B + i] = on ? v[2 * h] : 0.0;
+            d.hullv[(2 * h + 1) * B + i] = on ? v[2 * h + 1] : 0.0;
+        }
+        d.have_solver[i] = 1;
+        d.inited[i] = 0;
+        flags |= WC_MPC_FLAG_NEW_SOLVER;
+    }
+    if (!d.have_solver[i]) { d.tick_flags[i] = flags | WC_MPC_FLAG_NO_SOLVER; return; }
+    const bool inited = d.inited[i] != 0;
+    const bool reset = io.reset ? (io.reset[i] != 0) : false;
+    const double Q[2] = {d.Qd[i], d.Qd[B + i]};
+    const double R[2] = {d.Rd[i], d.Rd[B + i]};
+    const int head = d.ring_head;
+
+    // ---- MPCSolver::setGradient (state block; the input block -R u_prev is formed in K2)
+    if (!inited || reset) {
+        for (int k = 0; k <= N; k++) {
+            const int slot = (head + k) % nR;
+            d.grad[(size_t)(slot)*B + i] = -Q[0] * io.ref[(size_t)(2 * k) * B + i];
+            d.grad[(size_t)(nR + slot) * B + i] = -Q[1] * io.ref[(size_t)(2 * k + 1) * B + i];
+        }
+    } else {
+        const int slot = (head + N) % nR;
+        d.grad[(size_t)(slot)*B + i] = -Q[0] * io.ref[(size_t)(2 * N) * B + i];
+        d.grad[(size_t)(nR + slot) * B + i] = -Q[1] * io.ref[(size_t)(2 * N + 1) * B + i];
+    }
+
+    if (!inited) {
+        // ---- osqp_setup: Ruiz equilibration of [[P, A'],[A, 0]] with cost normalisation.
+        // P and A are never formed: their scaled entries follow from D, E, c in closed form.
+        // D -> d.D, E -> d.Eeq / d.Eh in place; d.x / d.yeq / d.yh serve as scratch (zeroed below).
+        const int nh = d.nhull[i];
+        const double ad = fabs(d.a_dyn), bd = fabs(d.b_dyn);
+        double c = 1.0;
+        for (int j = 0; j < 2 * nA; j++) d.D[(size_t)j * B + i] = 1.0;
+        for (int j = 0; j < 2 * nR; j++) d.Eeq[(size_t)j * B + i] = 1.0;
+        for (int h = 0; h < kMaxHull; h++) d.Eh[(size_t)h * B + i] = 1.0;
+        const double up[2] = {d.uprev[i], d.uprev[B + i]};
+#define DX(a, k) d.D[(size_t)((a)*nA + cx(N, (k))) * B + i]
+#define DU(a, k) d.D[(size_t)((a)*nA + cu(N, (k))) * B + i]
+#define EE(a, k) d.Eeq[(size_t)((a)*nR + (k)) * B + i]
+#define EH(h) d.Eh[(size_t)(h)*B + i]
+#define TX(a, k) d.x[(size_t)((a)*nA + cx(N, (k))) * B + i]
+#define TU(a, k) d.x[(size_t)((a)*nA + cu(N, (k))) * B + i]
+#define TE(a, k) d.yeq[(size_t)((a)*nR + (k)) * B + i]
+#define TH(h) d.yh[(size_t)(h)*B + i]
+#define HA(h, a) d.hullA[(size_t)(2 * (h) + (a)) * B + i]
+        for (int it = 0; it < d.st.scaling; it++) {
+            for (int a = 0; a < 2; a++) {
+                for (int k = 0; k <= N; k++) {
+                    const double dx = DX(a, k);
+                    double nrm = fabs(c * Q[a] * dx * dx);
+                    nrm = fmax(nrm, EE(a, k) * dx);
+                    if (k < N) nrm = fmax(nrm, ad * EE(a, k + 1) * dx);
+                    TX(a, k) = 1.0 / sqrt(limit_scaling(nrm));
+                }
+                for (int k = 0; k < N; k++) {
+                    const double du = DU(a, k);
+                    const double s = (k < N - 1) ? 2.0 : 1.0;
+                    double nrm = fabs(c * s * R[a] * du * du);
+                    if (k >= 1) nrm = fmax(nrm, fabs(c * R[a] * du * DU(a, k - 1)));
+                    if (k < N - 1) nrm = fmax(nrm, fabs(c * R[a] * du * DU(a, k + 1)));
+                    nrm = fmax(nrm, bd * EE(a, k + 1) * du);
+                    if (k == 0)
+                        for (int h = 0; h < nh; h++) nrm = fmax(nrm, fabs(EH(h) * HA(h, a)) * du);
+                    TU(a, k) = 1.0 / sqrt(limit_scaling(nrm));
+                }
+                for (int k = 0; k <= N; k++) {
+                    double nrm = EE(a, k) * DX(a, k);
+                    if (k >= 1) {
+                        nrm = fmax(nrm, ad * EE(a, k) * DX(a, k - 1));
+                        nrm = fmax(nrm, bd * EE(a, k) * DU(a, k - 1));
+                    }
+                    TE(a, k) = 1.0 / sqrt(limit_scaling(nrm));
+                }
+            }
+            for (int h = 0; h < nh; h++) {
+                double nrm = fmax(fabs(EH(h) * HA(h, 0)) * DU(0, 0), fabs(EH(h) * HA(h, 1)) * DU(1, 0));
+                TH(h) = 1.0 / sqrt(limit_scaling(nrm));
+            }
+            for (int j = 0; j < 2 * nA; j++) d.D[(size_t)j * B + i] *= d.x[(size_t)j * B + i];
+            for (int j = 0; j < 2 * nR; j++) d.Eeq[(size_t)j * B + i] *= d.yeq[(size_t)j * B + i];
+            for (int h = 0; h < nh; h++) EH(h) *= TH(h);
+            // cost normalisation
+            double sum = 0.0, qn = 0.0;
+            for (int a = 0; a < 2; a++) {
+                for (int k = 0; k <= N; k++) {
+                    const double dx = DX(a, k);
+                    sum += fabs(c * Q[a] * dx * dx);
+                    const int slot = (head + k) % nR;
+                    qn = fmax(qn, fabs(c * dx * d.grad[(size_t)(a * nR + slot) * B + i]));
+                }
+                for (int k = 0; k < N; k++) {
+                    const double du = DU(a, k);
+                    const double s = (k < N - 1) ? 2.0 : 1.0;
+                    double nrm = fabs(c * s * R[a] * du * du);
+                    if (k >= 1) nrm = fmax(nrm, fabs(c * R[a] * du * DU(a, k - 1)));
+                    if (k < N - 1) nrm = fmax(nrm, fabs(c * R[a] * du * DU(a, k + 1)));
+                    sum += nrm;
+                }
+                qn = fmax(qn, fabs(c * DU(a, 0) * R[a] * up[a]));
+            }
+            double c_temp = sum / (double)(2 * nA);
+            qn = limit_scaling(qn);
+            c_temp = fmax(c_temp, qn);
+            c_temp = limit_scaling(c_temp);
+            c *= 1.0 / c_temp;
+        }
+#undef DX
+#undef DU
+#undef EE
+#undef EH
+#undef TX
+#undef TU
+#undef TE
+#undef TH
+#undef HA
+        d.cscale[i] = c;
+        double rho = d.st.rho;
+        rho = rho < kRhoMin ? kRhoMin : (rho > kRhoMax ? kRhoMax : rho);
+        d.rho[i] = rho;
+        // cold start (osqp_setup -> cold_start)
+        for (int j = 0; j < 2 * nA; j++) d.x[(size_t)j * B + i] = 0.0;
+        for (int j = 0; j < 2 * nR; j++) d.yeq[(size_t)j * B + i] = 0.0;
+        for (int h = 0; h < kMaxHull; h++) { d.yh[(size_t)h * B + i] = 0.0; d.zh[(size_t)h * B + i] = 0.0; }
+        d.z0[i] = 0.0; d.z0[B + i] = 0.0;
+        d.inited[i] = 1;
+    }
+    d.tick_flags[i] = flags;
+}
+
+void launch_mpc_prepare(const MpcDev& d, const MpcTickIO& io, cudaStream_t s)
+{
+    const int threads = 128;
+    const int blocks = (d.B + threads - 1) / threads;
+    mpc_prepare_kernel<<<blocks, threads, 0, s>>>(d, io);
+}
+
+// =====================================================================================
+// K2: batched OSQP-equivalent ADMM.  G lanes per instance, 32/G instances per warp, every warp
+// independent (only __syncwarp).  Shared memory per instance (doubles), nA = 2N+1, nR = N+1:
+//   X  [2][nA] iterate          QB [2][nA] scaled q          W  [2][nA] rhs / x~ / delta_x
+//   L1 [2][nA] L2 [2][nA] DI [2][nA]  pentadiagonal LDL^T   DD [2][nA] Ruiz D
+//   YE [2][nR] y eq   DYE [2][nR] delta_y eq   CM/CA/CB [2][nR] scaled A coefficients   EE [2][nR]
+//   HX,HY,UH,LH,ZH,YH,DYH,EH [8]  hull rows     CF [16] corner factor   RS [8] scratch
+// =====================================================================================
+struct Smem {
+    double *X, *QB, *W, *L1, *L2, *DI, *DD, *YE, *DYE, *CM, *CA, *CB, *EE;
+    double *HX, *HY, *UH, *LH, *ZH, *YH, *DYH, *EH, *CF, *RS;
+};
+
+__device__ __forceinline__ Smem carve(double* base, int N)
+{
+    const int nA = 2 * N + 1, nR = N + 1;
+    Smem s;
+    double* p = base;
+    s.X = p; p += 2 * nA; s.QB = p; p += 2 * nA; s.W = p; p += 2 * nA;
+    s.L1 = p; p += 2 * nA; s.L2 = p; p += 2 * nA; s.DI = p; p += 2 * nA; s.DD = p; p += 2 * nA;
+    s.YE = p; p += 2 * nR; s.DYE = p; p += 2 * nR; s.CM = p; p += 2 * nR; s.CA = p; p += 2 * nR;
+    s.CB = p; p += 2 * nR; s.EE = p; p += 2 * nR;
+    s.HX = p; p += 8; s.HY = p; p += 8; s.UH = p; p += 8; s.LH = p; p += 8;
+    s.ZH = p; p += 8; s.YH = p; p += 8; s.DYH = p; p += 8; s.EH = p; p += 8;
+    s.CF = p; p += 16; s.RS = p;
+    return s;
+}
+
+template <int G>
+__device__ __forceinline__ double group_max(double v, unsigned mask)
+{
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(mask, v, o, 32));
+    return v;
+}
+template <int G>
+__device__ __forceinline__ double group_sum(double v, unsigned mask)
+{
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o, 32);
+    return v;
+}
+
+// Pentadiagonal LDL^T of one axis chain + Schur complement on its (u_0, x_0) corner.
+// Writes L1, L2, DI for rows 0..2N and the 2x2 corner (S11, S12, S22) to out3.
+__device__ void factor_axis(const Smem& s, int a, int N, double cQ, double cR, double sigma, double rho_e,
+                            double hull_diag, double* out3)
+{
+    const int nA = 2 * N + 1, nR = N + 1;
+    const double* CM = s.CM + a * nR; const double* CA = s.CA + a * nR; const double* CB = s.CB + a * nR;
+    const double* DD = s.DD + a * nA;
+    double* L1 = s.L1 + a * nA; double* L2 = s.L2 + a * nA; double* DI = s.DI + a * nA;
+    // running values of the previous two pivots / sub-diagonals
+    double Dm1 = 0.0, Dm2 = 0.0, l1m1 = 0.0, e1m1 = 0.0, e2m2 = 0.0, e2m1 = 0.0;
+    for (int j = 0; j < nA; j++) {
+        // diagonal and super-diagonals of K at chain position j
+        double dj, e1j = 0.0, e2j = 0.0;
+        if ((j & 1) == 0) { // x_k
+            const int k = N - (j >> 1);
+            const double dx = DD[j];
+            dj = cQ * dx * dx + sigma + rho_e * (CM[k] * CM[k] + (k < N ? CA[k + 1] * CA[k + 1] : 0.0));
+            if (k >= 1) { e1j = rho_e * CM[k] * CB[k]; e2j = rho_e * CM[k] * CA[k]; }
+        } else { // u_k
+            const int k = N - ((j + 1) >> 1);
+            const double du = DD[j];
+            const double sc = (k < N - 1) ? 2.0 : 1.0;
+            dj = cR * sc * du * du + sigma + rho_e * CB[k + 1] * CB[k + 1] + (k == 0 ? hull_diag : 0.0);
+            e1j = rho_e * CA[k + 1] * CB[k + 1];
+            if (k >= 1) e2j = -cR * du * DD[j + 2];
+        }
+        if (j < nA - 2) {
+            const double l2 = (j >= 2) ? e2m2 / Dm2 : 0.0;
+            const double l1 = (j >= 1) ? (e1m1 - l2 * Dm2 * l1m1) / Dm1 : 0.0;
+            const double Dj = dj - l1 * l1 * Dm1 - l2 * l2 * Dm2;
+            L1[j] = l1; L2[j] = l2; DI[j] = 1.0 / Dj;
+            e2m2 = e2m1; e2m1 = e2j; e1m1 = e1j; Dm2 = Dm1; Dm1 = Dj; l1m1 = l1;
+        } else if (j == nA - 2) { // u_0: first corner row
+            const double l2 = (j >= 2) ? e2m2 / Dm2 : 0.0;
+            const double l1 = (j >= 1) ? (e1m1 - l2 * Dm2 * l1m1) / Dm1 : 0.0;
+            L1[j] = l1; L2[j] = l2; DI[j] = 0.0;
+            out3[0] = dj - l1 * l1 * Dm1 - l2 * l2 * Dm2; // S11
+            // keep Dm1 (= D_{2N-2}), l1 for the x_0 row; e2m1 is e2_{2N-2} (x_1 - x_0 coupling)
+            const double l2x = (j >= 1) ? e2m1 / Dm1 : 0.0; // L[2N, 2N-2]
+            out3[1] = e1j - l2x * Dm1 * l1;                 // S12 = K[u0,x0] - l2x D l1
+            L1[j + 1] = 0.0; L2[j + 1] = l2x; DI[j + 1] = 0.0;
+            e1m1 = l2x * l2x * Dm1; // reuse as carry for S22
+        } else { // x_0: second corner row
+            out3[2] = dj - e1m1; // S22
+        }
+    }
+}
+
+// dense 4x4 LDL^T of the corner, order [u0x, u0y, x0x, x0y]; CF: L (6 strict-lower, row-major) + 4 Dinv
+__device__ void factor_corner(const double* Sx, const double* Sy, double kxy, double* CF)
+{
+    double A[4][4] = {{Sx[0], kxy, Sx[1], 0.0}, {kxy, Sy[0], 0.0, Sy[1]}, {Sx[1], 0.0, Sx[2], 0.0}, {0.0, Sy[1], 0.0, Sy[2]}};
+    double L[4][4], Dv[4];
+    for (int j = 0; j < 4; j++) {
+        double dj = A[j][j];
+        for (int k = 0; k < j; k++) dj -= L[j][k] * L[j][k] * Dv[k];
+        Dv[j] = dj;
+        for (int i = j + 1; i < 4; i++) {
+            double v = A[i][j];
+            for (int k = 0; k < j; k++) v -= L[i][k] * L[j][k] * Dv[k];
+            L[i][j] = v / dj;
+        }
+    }
+    CF[0] = L[1][0]; CF[1] = L[2][0]; CF[2] = L[2][1]; CF[3] = L[3][0]; CF[4] = L[3][1]; CF[5] = L[3][2];
+    CF[6] = 1.0 / Dv[0]; CF[7] = 1.0 / Dv[1]; CF[8] = 1.0 / Dv[2]; CF[9] = 1.0 / Dv[3];
+}
+
+__device__ __forceinline__ void solve_corner(const double* CF, double* r)
+{
+    // r: [u0x, u0y, x0x, x0y] in/out
+    double t0 = r[0];
+    double t1 = r[1] - CF[0] * t0;
+    double t2 = r[2] - CF[1] * t0 - CF[2] * t1;
+    double t3 = r[3] - CF[3] * t0 - CF[4] * t1 - CF[5] * t2;
+    t0 *= CF[6]; t1 *= CF[7]; t2 *= CF[8]; t3 *= CF[9];
+    t2 -= CF[5] * t3;
+    t1 -= CF[2] * t2 + CF[4] * t3;
+    t0 -= CF[0] * t1 + CF[1] * t2 + CF[3] * t3;
+    r[0] = t0; r[1] = t1; r[2] = t2; r[3] = t3;
+}
+
+template <int G>
+__global__ void __launch_bounds__(128) mpc_admm_kernel(MpcDev d, MpcTickIO io, int smem_stride)
+{
+    extern __shared__ double smem_all[];
+    constexpr int IPW = 32 / G; // instances per warp
+    const int lane = threadIdx.x & 31;
+    const int warp_in_block = threadIdx.x >> 5;
+    const int warps_per_block = blockDim.x >> 5;
+    const int grp = lane / G;   // instance slot in the warp
+    const int gl = lane % G;    // lane in group
+    const int slot = warp_in_block * IPW + grp;
+    const long long inst_ll = ((long long)blockIdx.x * warps_per_block + warp_in_block) * IPW + grp;
+    const size_t B = (size_t)d.B;
+    const int N = d.N, nA = 2 * N + 1, nR = N + 1;
+    const bool valid = inst_ll < (long long)d.B;
+    const int i = valid ? (int)inst_ll : d.B - 1;
+    const unsigned FULL = 0xffffffffu;
+    // lanes of this instance's group: group collectives run under group-uniform control flow
+    const unsigned gmask = (G == 32) ? FULL : (((1u << G) - 1u) << (grp * G));
+    Smem s = carve(smem_all + (size_t)slot * smem_stride, N);
+
+    const wc_osqp_settings& st = d.st;
+    const double sigma = st.sigma, alpha = st.alpha, infty = st.infty;
+
+    const int kflags = d.tick_flags[i];
+    const bool skip = !valid || (kflags & (WC_MPC_FLAG_NO_CONTACT | WC_MPC_FLAG_NO_SOLVER)) != 0;
+    const int nh = skip ? 0 : d.nhull[i];
+    const double Q[2] = {d.Qd[i], d.Qd[B + i]};
+    const double R[2] = {d.Rd[i], d.Rd[B + i]};
+    const double c = d.cscale[i];
+    const double cinv = 1.0 / c;
+    double rho = d.rho[i];
+    const double up[2] = {d.uprev[i], d.uprev[B + i]};
+    const int head = d.ring_head;
+
+    // ------------------------------------------------------------------ stage in
+    for (int j = gl; j < 2 * nA; j += G) {
+        s.X[j] = d.x[(size_t)j * B + i];
+        s.DD[j] = d.D[(size_t)j * B + i];
+    }
+    for (int j = gl; j < 2 * nR; j += G) {
+        s.YE[j] = d.yeq[(size_t)j * B + i];
+        s.EE[j] = d.Eeq[(size_t)j * B + i];
+        s.DYE[j] = 0.0;
+    }
+    for (int h = gl; h < kMaxHull; h += G) {
+        s.YH[h] = d.yh[(size_t)h * B + i];
+        s.ZH[h] = d.zh[(size_t)h * B + i];
+        s.EH[h] = d.Eh[(size_t)h * B + i];
+        s.DYH[h] = 0.0;
+    }
+    __syncwarp();
+    // scaled problem data: q (osqp_update_lin_cost), A coefficients, bounds (osqp_update_bounds)
+    for (int j = gl; j < 2 * nA; j += G) {
+        const int a = j / nA, jj = j - a * nA;
+        double q;
+        if ((jj & 1) == 0) {
+            const int k = N - (jj >> 1);
+            q = d.grad[(size_t)(a * nR + (head + k) % nR) * B + i];
+        } else {
+            const int k = N - ((jj + 1) >> 1);
+            q = (k == 0) ? -(R[a] * up[a]) : 0.0; // G u_prev, G = -Theta' R~ e1 (MPCSolver.cpp:244-245)
+        }
+        s.QB[j] = (q * s.DD[j]) * c;
+    }
+    for (int j = gl; j < 2 * nR; j += G) {
+        const int a = j / nR, k = j - a * nR;
+        const double e = s.EE[j];
+        s.CM[j] = -e * s.DD[a * nA + cx(N, k)];
+        s.CA[j] = (k >= 1) ? d.a_dyn * e * s.DD[a * nA + cx(N, k - 1)] : 0.0;
+        s.CB[j] = (k >= 1) ? d.b_dyn * e * s.DD[a * nA + cu(N, k - 1)] : 0.0;
+    }
+    for (int h = gl; h < kMaxHull; h += G) {
+        const bool on = h < nh;
+        const double e = s.EH[h];
+        s.HX[h] = on ? e * d.hullA[(size_t)(2 * h) * B + i] * s.DD[0 * nA + cu(N, 0)] : 0.0;
+        s.HY[h] = on ? e * d.hullA[(size_t)(2 * h + 1) * B + i] * s.DD[1 * nA + cu(N, 0)] : 0.0;
+        s.UH[h] = on ? e * d.hullb[(size_t)h * B + i] : 0.0;
+        s.LH[h] = on ? e * (-infty) : 0.0;
+    }
+    // equality row 0: l = u = -dcm (MPCSolver.cpp:143-146), scaled by E
+    const double lb0[2] = {-io.dcm[i] * d.Eeq[(size_t)(0 * nR) * B + i], -io.dcm[B + i] * d.Eeq[(size_t)(1 * nR) * B + i]};
+    double z0prev[2] = {d.z0[i], d.z0[B + i]};
+    __syncwarp();
+
+    // ------------------------------------------------------------------ factorisation
+    auto factor = [&](double rho_now) {
+        const double rho_e = kRhoEqOverIneq * rho_now;
+        if (gl < 2) {
+            double hd = 0.0;
+            for (int h = 0; h < nh; h++) { const double v = (gl == 0) ? s.HX[h] : s.HY[h]; hd += rho_now * v * v; }
+            factor_axis(s, gl, N, c * Q[gl], c * R[gl], sigma, rho_e, hd, s.RS + 3 * gl);
+        }
+        if (G == 1) {
+            double hd = 0.0;
+            for (int h = 0; h < nh; h++) hd += rho_now * s.HY[h] * s.HY[h];
+            factor_axis(s, 1, N, c * Q[1], c * R[1], sigma, rho_e, hd, s.RS + 3);
+        }
+        __syncwarp();
+        if (gl == 0) {
+            double kxy = 0.0;
+            for (int h = 0; h < nh; h++) kxy += rho_now * s.HX[h] * s.HY[h];
+            factor_corner(s.RS, s.RS + 3, kxy, s.CF);
+        }
+        __syncwarp();
+    };
+    factor(rho);
+
+    // ------------------------------------------------------------------ ADMM (osqp_solve)
+    int status = WC_OSQP_UNSOLVED;
+    int iter_done = 0, rho_updates = 0;
+    bool done = skip;
+    double pri_res = 0.0, dua_res = 0.0;
+    // norms kept from the last update_info (needed by check_termination and compute_rho_estimate)
+    double nz_u = 0, nAx_u = 0, nq_u = 0, nAty_u = 0, nPx_u = 0;
+    double rp_s = 0, rd_s = 0, nz_s = 0, nAx_s = 0, nq_s = 0, nAty_s = 0, nPx_s = 0;
+    int prim_inf = 0, dual_inf = 0;
+
+    // evaluates residual information for the CURRENT (x, z, y) (update_info + the norms of check_termination)
+    auto update_info = [&]() {
+        double m_rp_u = 0, m_rp_s = 0, m_z_u = 0, m_z_s = 0, m_ax_u = 0, m_ax_s = 0;
+        for (int j = gl; j < 2 * nR; j += G) {
+            const int a = j / nR, k = j - a * nR;
+            const double* Xa = s.X + a * nA;
+            double ax = s.CM[j] * Xa[cx(N, k)];
+            if (k >= 1) ax += s.CA[j] * Xa[cx(N, k - 1)] + s.CB[j] * Xa[cu(N, k - 1)];
+            const double z = (k == 0) ? lb0[a] : 0.0;
+            const double einv = 1.0 / s.EE[j];
+            const double r = ax - z;
+            m_rp_s = fmax(m_rp_s, fabs(r)); m_rp_u = fmax(m_rp_u, fabs(einv * r));
+            m_z_s = fmax(m_z_s, fabs(z)); m_z_u = fmax(m_z_u, fabs(einv * z));
+            m_ax_s = fmax(m_ax_s, fabs(ax)); m_ax_u = fmax(m_ax_u, fabs(einv * ax));
+        }
+        for (int h = gl; h < nh; h += G) {
+            const double ax = s.HX[h] * s.X[0 * nA + cu(N, 0)] + s.HY[h] * s.X[1 * nA + cu(N, 0)];
+            const double z = s.ZH[h];
+            const double einv = 1.0 / s.EH[h];
+            const double r = ax - z;
+            m_rp_s = fmax(m_rp_s, fabs(r)); m_rp_u = fmax(m_rp_u, fabs(einv * r));
+            m_z_s = fmax(m_z_s, fabs(z)); m_z_u = fmax(m_z_u, fabs(einv * z));
+            m_ax_s = fmax(m_ax_s, fabs(ax)); m_ax_u = fmax(m_ax_u, fabs(einv * ax));
+        }
+        double m_rd_u = 0, m_rd_s = 0, m_q_u = 0, m_q_s = 0, m_aty_u = 0, m_aty_s = 0, m_px_u = 0, m_px_s = 0;
+        for (int j = gl; j < 2 * nA; j += G) {
+            const int a = j / nA, jj = j - a * nA;
+            const double* Xa = s.X + a * nA; const double* Da = s.DD + a * nA;
+            const double* Ya = s.YE + a * nR;
+            const double* CMa = s.CM + a * nR; const double* CAa = s.CA + a * nR; const double* CBa = s.CB + a * nR;
+            double px, aty;
+            if ((jj & 1) == 0) {
+                const int k = N - (jj >> 1);
+                px = (c * Q[a]) * Da[jj] * Da[jj] * Xa[jj];
+                aty = CMa[k] * Ya[k] + (k < N ? CAa[k + 1] * Ya[k + 1] : 0.0);
+            } else {
+                const int k = N - ((jj + 1) >> 1);
+                const double sc = (k < N - 1) ? 2.0 : 1.0;
+                double t = sc * Da[jj] * Xa[jj];
+                if (k >= 1) t -= Da[jj + 2] * Xa[jj + 2];
+                if (k < N - 1) t -= Da[jj - 2] * Xa[jj - 2];
+                px = (c * R[a]) * Da[jj] * t;
+                aty = CBa[k + 1] * Ya[k + 1];
+                if (k == 0) {
+                    const double* Hc = (a == 0) ? s.HX : s.HY;
+                    for (int h = 0; h < nh; h++) aty += Hc[h] * s.YH[h];
+                }
+            }
+            const double q = s.QB[j];
+            const double dinv = 1.0 / Da[jj];
+            const double r = q + px + aty;
+            m_rd_s = fmax(m_rd_s, fabs(r)); m_rd_u = fmax(m_rd_u, fabs(dinv * r));
+            m_q_s = fmax(m_q_s, fabs(q)); m_q_u = fmax(m_q_u, fabs(dinv * q));
+            m_aty_s = fmax(m_aty_s, fabs(aty)); m_aty_u = fmax(m_aty_u, fabs(dinv * aty));
+            m_px_s = fmax(m_px_s, fabs(px)); m_px_u = fmax(m_px_u, fabs(dinv * px));
+        }
+        const unsigned mk = gmask;
+        pri_res = group_max<G>(m_rp_u, mk); rp_s = group_max<G>(m_rp_s, mk);
+        nz_u = group_max<G>(m_z_u, mk); nz_s = group_max<G>(m_z_s, mk);
+        nAx_u = group_max<G>(m_ax_u, mk); nAx_s = group_max<G>(m_ax_s, mk);
+        dua_res = cinv * group_max<G>(m_rd_u, mk); rd_s = group_max<G>(m_rd_s, mk);
+        nq_u = cinv * group_max<G>(m_q_u, mk); nq_s = group_max<G>(m_q_s, mk);
+        nAty_u = cinv * group_max<G>(m_aty_u, mk); nAty_s = group_max<G>(m_aty_s, mk);
+        nPx_u = cinv * group_max<G>(m_px_u, mk); nPx_s = group_max<G>(m_px_s, mk);
+    };
+
+    // is_primal_infeasible / is_dual_infeasible (OSQP auxil.c) on delta_y (DYE, DYH) and delta_x (W)
+    auto primal_infeasible = [&](double eps) -> int {
+        // project delta_y on the polar of the recession cone: hull rows have l = -inf -> max(dy, 0)
+        double nrm = 0.0, lhs = 0.0;
+        for (int j = gl; j < 2 * nR; j += G) {
+            const int a = j / nR, k = j - a * nR;
+            const double dy = s.DYE[j];
+            nrm = fmax(nrm, fabs(s.EE[j] * dy));
+            const double bnd = (k == 0) ? lb0[a] : 0.0;
+            lhs += bnd * fmax(dy, 0.0) + bnd * fmin(dy, 0.0);
+        }
+        for (int h = gl; h < nh; h += G) {
+            double dy = s.DYH[h];
+            const bool u_inf = s.UH[h] > infty * kMinScaling, l_inf = s.LH[h] < -infty * kMinScaling;
+            if (u_inf) dy = l_inf ? 0.0 : fmin(dy, 0.0);
+            else if (l_inf) dy = fmax(dy, 0.0);
+            s.DYH[h] = dy;
+            nrm = fmax(nrm, fabs(s.EH[h] * dy));
+            lhs += s.UH[h] * fmax(dy, 0.0) + s.LH[h] * fmin(dy, 0.0);
+        }
+        nrm = group_max<G>(nrm, gmask);
+        lhs = group_sum<G>(lhs, gmask);
+        __syncwarp(gmask);
+        int res = 0;
+        if (nrm > 1.0 / infty && lhs < -eps * nrm) {
+            double m = 0.0;
+            for (int j = gl; j < 2 * nA; j += G) {
+                const int a = j / nA, jj = j - a * nA;
+                const double* Ya = s.DYE + a * nR;
+                const double* CMa = s.CM + a * nR; const double* CAa = s.CA + a * nR; const double* CBa = s.CB + a * nR;
+                double aty;
+                if ((jj & 1) == 0) {
+                    const int k = N - (jj >> 1);
+                    aty = CMa[k] * Ya[k] + (k < N ? CAa[k + 1] * Ya[k + 1] : 0.0);
+                } else {
+                    const int k = N - ((jj + 1) >> 1);
+                    aty = CBa[k + 1] * Ya[k + 1];
+                    if (k == 0) {
+                        const double* Hc = (a == 0) ? s.HX : s.HY;
+                        for (int h = 0; h < nh; h++) aty += Hc[h] * s.DYH[h];
+                    }
+                }
+                m = fmax(m, fabs(aty / s.DD[j]));
+            }
+            m = group_max<G>(m, gmask);
+            res = m < eps * nrm;
+        }
+        return res;
+    };
+    auto dual_infeasible = [&](double eps) -> int {
+        double nrm = 0.0, qdx = 0.0;
+        for (int j = gl; j < 2 * nA; j += G) {
+            nrm = fmax(nrm, fabs(s.DD[j] * s.W[j]));
+            qdx += s.QB[j] * s.W[j];
+        }
+        nrm = group_max<G>(nrm, gmask);
+        qdx = group_sum<G>(qdx, gmask);
+        int res = 0;
+        if (nrm > 1.0 / infty && qdx < -c * eps * nrm) {
+            double m = 0.0;
+            for (int j = gl; j < 2 * nA; j += G) {
+                const int a = j / nA, jj = j - a * nA;
+                const double* Xa = s.W + a * nA; const double* Da = s.DD + a * nA;
+                double px;
+                if ((jj & 1) == 0) px = (c * Q[a]) * Da[jj] * Da[jj] * Xa[jj];
+                else {
+                    const int k = N - ((jj + 1) >> 1);
+                    const double sc = (k < N - 1) ? 2.0 : 1.0;
+                    double t = sc * Da[jj] * Xa[jj];
+                    if (k >= 1) t -= Da[jj + 2] * Xa[jj + 2];
+                    if (k < N - 1) t -= Da[jj - 2] * Xa[jj - 2];
+                    px = (c * R[a]) * Da[jj] * t;
+                }
+                m = fmax(m, fabs(px / Da[jj]));
+            }
+            m = group_max<G>(m, gmask);
+            if (m < c * eps * nrm) {
+                int bad = 0;
+                for (int j = gl; j < 2 * nR; j += G) {
+                    const int a = j / nR, k = j - a * nR;
+                    const double* Xa = s.W + a * nA;
+                    double ax = s.CM[j] * Xa[cx(N, k)];
+                    if (k >= 1) ax += s.CA[j] * Xa[cx(N, k - 1)] + s.CB[j] * Xa[cu(N, k - 1)];
+                    ax /= s.EE[j];
+                    if (ax > eps * nrm || ax < -eps * nrm) bad = 1; // both bounds finite on equality rows
+                }
+                for (int h = gl; h < nh; h += G) {
+                    double ax = s.HX[h] * s.W[0 * nA + cu(N, 0)] + s.HY[h] * s.W[1 * nA + cu(N, 0)];
+                    ax /= s.EH[h];
+                    if ((s.UH[h] < infty * kMinScaling && ax > eps * nrm) ||
+                        (s.LH[h] > -infty * kMinScaling && ax < -eps * nrm)) bad = 1;
+                }
+                bad = (int)group_max<G>((double)bad, gmask);
+                res = !bad;
+            }
+        }
+        return res;
+    };
+    // check_termination (OSQP auxil.c); returns 1 when the algorithm stops, sets status
+    auto check_termination = [&](int approximate) -> int {
+        double eps_abs = st.eps_abs, eps_rel = st.eps_rel, epi = st.eps_prim_inf, edi = st.eps_dual_inf;
+        if (pri_res > infty || dua_res > infty) { status = WC_OSQP_NON_CVX; return 1; }
+        if (approximate) { eps_abs *= 10; eps_rel *= 10; epi *= 10; edi *= 10; }
+        int prc = 0, drc = 0;
+        prim_inf = 0; dual_inf = 0;
+        const double eps_prim = eps_abs + eps_rel * fmax(nz_u, nAx_u);
+        if (pri_res < eps_prim) prc = 1; else prim_inf = primal_infeasible(epi);
+        const double eps_dual = eps_abs + eps_rel * fmax(fmax(nq_u, nAty_u), nPx_u);
+        if (dua_res < eps_dual) drc = 1; else dual_inf = dual_infeasible(edi);
+        if (prc && drc) { status = approximate ? WC_OSQP_SOLVED_INACCURATE : WC_OSQP_SOLVED; return 1; }
+        if (prim_inf) { status = approximate ? WC_OSQP_PRIMAL_INFEASIBLE_INACCURATE : WC_OSQP_PRIMAL_INFEASIBLE; return 1; }
+        if (dual_inf) { status = approximate ? WC_OSQP_DUAL_INFEASIBLE_INACCURATE : WC_OSQP_DUAL_INFEASIBLE; return 1; }
+        return 0;
+    };
+
+    const int max_iter = st.max_iter;
+    const int chk = st.check_termination;
+    const int rint = d.rho_interval;
+    int iter = 0;
+    bool warp_busy = __any_sync(FULL, !done);
+    while (warp_busy) {
+        iter++;
+        const bool act = !done;
+        const double rho_e = kRhoEqOverIneq * rho;
+        const double rho_e_inv = 1.0 / rho_e, rho_inv = 1.0 / rho;
+        const bool check_now = chk && (iter % chk == 0);
+        const bool keep_delta = check_now || iter >= max_iter; // delta_x / delta_y feed the infeasibility tests only
+        // ---- update_xz_tilde: right-hand side  sigma x - q + A' (rho z - y)
+        if (act) {
+            for (int j = gl; j < 2 * nA; j += G) {
+                const int a = j / nA, jj = j - a * nA;
+                const double* Ya = s.YE + a * nR;
+                const double* CMa = s.CM + a * nR; const double* CAa = s.CA + a * nR; const double* CBa = s.CB + a * nR;
+                double r = sigma * s.X[j] - s.QB[j];
+                if ((jj & 1) == 0) {
+                    const int k = N - (jj >> 1);
+                    // w_k = rho_e (z_k - y_k / rho_e), z_k = 0 except equality row 0
+                    const double zk = (k == 0) ? z0prev[a] : 0.0;
+                    r += CMa[k] * (rho_e * (zk - rho_e_inv * Ya[k]));
+                    if (k < N) r += CAa[k + 1] * (rho_e * (0.0 - rho_e_inv * Ya[k + 1]));
+                } else {
+                    const int k = N - ((jj + 1) >> 1);
+                    r += CBa[k + 1] * (rho_e * (0.0 - rho_e_inv * Ya[k + 1]));
+                    if (k == 0) {
+                        const double* Hc = (a == 0) ? s.HX : s.HY;
+                        for (int h = 0; h < nh; h++) r += Hc[h] * (rho * (s.ZH[h] - rho_inv * s.YH[h]));
+                    }
+                }
+                s.W[j] = r;
+            }
+        }
+        __syncwarp();
+        // ---- reduced KKT solve: forward sweeps (two axis chains on two lanes)
+        if (act && (gl < 2 || G == 1)) {
+            for (int a = (G == 1 ? 0 : gl); a < (G == 1 ? 2 : gl + 1); a++) {
+                double* W = s.W + a * nA; const double* L1 = s.L1 + a * nA; const double* L2 = s.L2 + a * nA;
+                double t1 = 0.0, t2 = 0.0; // t_{j-1}, t_{j-2}
+                for (int j = 0; j < nA - 2; j++) {
+                    const double t = W[j] - L1[j] * t1 - L2[j] * t2;
+                    W[j] = t; t2 = t1; t1 = t;
+                }
+                // corner rows: u_0 (nA-2), x_0 (nA-1)
+                W[nA - 2] = W[nA - 2] - L1[nA - 2] * t1 - L2[nA - 2] * t2;
+                W[nA - 1] = W[nA - 1] - L2[nA - 1] * t1;
+            }
+        }
+        __syncwarp();
+        if (act && gl == 0) {
+            double r[4] = {s.W[nA - 2], s.W[nA + nA - 2], s.W[nA - 1], s.W[nA + nA - 1]};
+            solve_corner(s.CF, r);
+            s.W[nA - 2] = r[0]; s.W[nA + nA - 2] = r[1]; s.W[nA - 1] = r[2]; s.W[nA + nA - 1] = r[3];
+        }
+        __syncwarp();
+        if (act && (gl < 2 || G == 1)) {
+            for (int a = (G == 1 ? 0 : gl); a < (G == 1 ? 2 : gl + 1); a++) {
+                double* W = s.W + a * nA; const double* L1 = s.L1 + a * nA; const double* L2 = s.L2 + a * nA;
+                const double* DI = s.DI + a * nA;
+                double x1 = W[nA - 2], x2 = W[nA - 1]; // x_{j+1}, x_{j+2}
+                for (int j = nA - 3; j >= 0; j--) {
+                    const double xj = W[j] * DI[j] - L1[j + 1] * x1 - L2[j + 2] * x2;
+                    W[j] = xj; x2 = x1; x1 = xj;
+                }
+            }
+        }
+        __syncwarp();
+        // ---- update_z / update_y on the rows (z~ = A x~), then update_x
+        if (act) {
+            for (int j = gl; j < 2 * nR; j += G) {
+                const int a = j / nR, k = j - a * nR;
+                const double* Wa = s.W + a * nA;
+                double zt = s.CM[j] * Wa[cx(N, k)];
+                if (k >= 1) zt += s.CA[j] * Wa[cx(N, k - 1)] + s.CB[j] * Wa[cu(N, k - 1)];
+                const double zprev = (k == 0) ? z0prev[a] : 0.0;
+                const double znew = (k == 0) ? lb0[a] : 0.0; // projection on [l, u] with l == u
+                const double dy = rho_e * (alpha * zt + (1.0 - alpha) * zprev - znew);
+                s.YE[j] += dy;
+                if (keep_delta) s.DYE[j] = dy;
+            }
+            for (int h = gl; h < nh; h += G) {
+                const double zt = s.HX[h] * s.W[0 * nA + cu(N, 0)] + s.HY[h] * s.W[1 * nA + cu(N, 0)];
+                const double zp = s.ZH[h], y = s.YH[h];
+                const double zr = alpha * zt + (1.0 - alpha) * zp;
+                double zn = zr + rho_inv * y;
+                zn = fmax(zn, s.LH[h]);
+                zn = fmin(zn, s.UH[h]);
+                const double dy = rho * (zr - zn);
+                s.ZH[h] = zn;
+                s.YH[h] = y + dy;
+                if (keep_delta) s.DYH[h] = dy;
+            }
+        }
+        __syncwarp();
+        if (act) {
+            for (int j = gl; j < 2 * nA; j += G) {
+                const double xp = s.X[j];
+                const double xn = alpha * s.W[j] + (1.0 - alpha) * xp;
+                s.X[j] = xn;
+                if (keep_delta) s.W[j] = xn - xp;
+            }
+            z0prev[0] = lb0[0]; z0prev[1] = lb0[1];
+            iter_done = iter;
+        }
+        __syncwarp();
+        // ---- termination / adaptive rho (group-uniform control flow, warp-uniform barriers)
+        if (check_now) {
+            update_info();
+            if (act) { if (check_termination(0)) done = true; }
+        }
+        const bool adapt_now = st.adaptive_rho && rint && (iter % rint == 0);
+        if (adapt_now) {
+            if (!check_now) update_info();
+            if (act && !done) {
+                // compute_rho_estimate + adapt_rho
+                const double pr = rp_s / (fmax(nz_s, nAx_s) + 1e-10);
+                const double dr = rd_s / (fmax(fmax(nq_s, nAty_s), nPx_s) + 1e-10);
+                double rn = rho * sqrt(pr / (dr + 1e-10));
+                rn = fmin(fmax(rn, kRhoMin), kRhoMax);
+                if (rn > rho * st.adaptive_rho_tolerance || rn < rho / st.adaptive_rho_tolerance) {
+                    rho = rn;
+                    rho_updates++;
+                }
+            }
+            __syncwarp();
+            factor(rho); // warp-uniform; a no-op numerically for groups whose rho did not change
+        }
+        if (iter >= max_iter) { // warp-uniform: osqp_solve leaves the loop
+            if (!check_now) {
+                update_info();
+                if (act && !done && check_termination(0)) done = true;
+            }
+            if (act && !done) {
+                if (!check_termination(1)) status = WC_OSQP_MAX_ITER_REACHED;
+                done = true;
+            }
+        }
+        warp_busy = __any_sync(FULL, !done);
+    }
+    __syncwarp();
+
+    // ------------------------------------------------------------------ epilogue: store_solution + controller checks
+    const bool has_sol = !(status == WC_OSQP_PRIMAL_INFEASIBLE || status == WC_OSQP_PRIMAL_INFEASIBLE_INACCURATE ||
+                           status == WC_OSQP_DUAL_INFEASIBLE || status == WC_OSQP_DUAL_INFEASIBLE_INACCURATE ||
+                           status == WC_OSQP_UNSOLVED || status == WC_OSQP_NON_CVX);
+    if (!skip) {
+        for (int j = gl; j < 2 * nA; j += G) d.x[(size_t)j * B + i] = has_sol ? s.X[j] : 0.0;
+        for (int j = gl; j < 2 * nR; j += G) d.yeq[(size_t)j * B + i] = has_sol ? s.YE[j] : 0.0;
+        for (int h = gl; h < kMaxHull; h += G) {
+            d.yh[(size_t)h * B + i] = has_sol ? s.YH[h] : 0.0;
+            d.zh[(size_t)h * B + i] = has_sol ? s.ZH[h] : 0.0;
+        }
+    }
+    if (gl == 0 && valid) {
+        int flags = kflags;
+        double out[2] = {up[0], up[1]};
+        if (!skip) {
+            d.z0[i] = has_sol ? z0prev[0] : 0.0;
+            d.z0[B + i] = has_sol ? z0prev[1] : 0.0;
+            d.rho[i] = rho;
+            d.rho_updates[i] = rho_updates;
+            if (status == WC_OSQP_SOLVED) {
+                out[0] = s.X[0 * nA + cu(N, 0)] * s.DD[0 * nA + cu(N, 0)];
+                out[1] = s.X[1 * nA + cu(N, 0)] * s.DD[1 * nA + cu(N, 0)];
+                d.uprev[i] = out[0]; d.uprev[B + i] = out[1];
+                // ConvexHullProjectionConstraint::computeMargin (Controller.cpp:513-517)
+                bool inside = true;
+                double best = INFINITY;
+                for (int h = 0; h < nh; h++) {
+                    const double a0 = d.hullA[(size_t)(2 * h) * B + i], a1 = d.hullA[(size_t)(2 * h + 1) * B + i];
+                    if (!(a0 * out[0] + a1 * out[1] <= d.hullb[(size_t)h * B + i])) inside = false;
+                }
+                for (int h = 0; h < nh; h++) {
+                    const int h1 = (h + 1) % nh;
+                    const double p0x = d.hullv[(size_t)(2 * h) * B + i], p0y = d.hullv[(size_t)(2 * h + 1) * B + i];
+                    const double p1x = d.hullv[(size_t)(2 * h1) * B + i], p1y = d.hullv[(size_t)(2 * h1 + 1) * B + i];
+                    const double dx = p1x - p0x, dy = p1y - p0y;
+                    const double len2 = dx * dx + dy * dy;
+                    double t = len2 > 0 ? ((out[0] - p0x) * dx + (out[1] - p0y) * dy) / len2 : 0.0;
+                    t = t < 0 ? 0 : (t > 1 ? 1 : t);
+                    const double ex = out[0] - (p0x + t * dx), ey = out[1] - (p0y + t * dy);
+                    best = fmin(best, sqrt(ex * ex + ey * ey));
+                }
+                const double margin = inside ? best : -best;
+                if (margin < -d.hull_tol) flags |= WC_MPC_FLAG_OUTSIDE_HULL;
+            } else {
+                flags |= WC_MPC_FLAG_NOT_SOLVED;
+            }
+        }
+        if (io.zmp) { io.zmp[i] = out[0]; io.zmp[B + i] = out[1]; }
+        if (io.status) io.status[i] = skip ? WC_OSQP_UNSOLVED : status;
+        if (io.iters) io.iters[i] = skip ? 0 : iter_done;
+        if (io.flags) io.flags[i] = flags;
+        d.tick_flags[i] = flags;
+    }
+}
+
+int mpc_admm_max_smem()
+{
+    int dev = 0, v = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    return v;
+}
+
+template <int G>
+static cudaError_t launch_admm_t(const MpcDev& d, const MpcTickIO& io, cudaStream_t s)
+{
+    constexpr int IPW = 32 / G;
+    int stride = mpc_smem_doubles(d.N);
+    // keep the per-instance stride == 8 (mod 16) doubles so that the two half-warps of a
+    // cooperative access hit disjoint bank groups
+    while ((stride % 16) != 8) stride++;
+    const size_t per_inst = (size_t)stride * sizeof(double);
+    const int max_smem = mpc_admm_max_smem();
+    // aim for two resident CTAs per SM (228 KB total, 1 KB reserved per CTA)
+    const size_t budget = (size_t)(max_smem > 116 * 1024 ? 113 * 1024 : max_smem);
+    int warps = (int)(budget / (per_inst * IPW));
+    if (warps < 1) {
+        warps = 1;
+        if (per_inst * IPW > (size_t)max_smem) return cudaErrorInvalidConfiguration;
+    }
+    if (warps > 4) warps = 4;
+    const size_t smem = per_inst * IPW * warps;
+    const int inst_per_block = warps * IPW;
+    const int blocks = (d.B + inst_per_block - 1) / inst_per_block;
+    cudaError_t e = cudaFuncSetAttribute(mpc_admm_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    mpc_admm_kernel<G><<<blocks, warps * 32, smem, s>>>(d, io, stride);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_mpc_admm(const MpcDev& d, const MpcTickIO& io, int lanes, cudaStream_t s)
+{
+    switch (lanes) {
+    case 2: return launch_admm_t<2>(d, io, s);
+    case 4: return launch_admm_t<4>(d, io, s);
+    case 8: return launch_admm_t<8>(d, io, s);
+    case 16: return launch_admm_t<16>(d, io, s);
+    case 32: return launch_admm_t<32>(d, io, s);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+// primal solution in the reference's variable order z = [x_0..x_N, u_0..u_{N-1}], unscaled (D x)
+__global__ void mpc_export_primal_kernel(MpcDev d, double* out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d.B) return;
+    const size_t B = (size_t)d.B;
+    const int N = d.N, nA = 2 * N + 1;
+    for (int a = 0; a < 2; a++) {
+        for (int k = 0; k <= N; k++) {
+            const size_t j = (size_t)(a * nA + cx(N, k));
+            out[(size_t)(2 * k + a) * B + i] = d.x[j * B + i] * d.D[j * B + i];
+        }
+        for (int k = 0; k < N; k++) {
+            const size_t j = (size_t)(a * nA + cu(N, k));
+            out[(size_t)(2 * (N + 1) + 2 * k + a) * B + i] = d.x[j * B + i] * d.D[j * B + i];
+        }
+    }
+}
+
+void launch_mpc_export_primal(const MpcDev& d, double* primal_out, cudaStream_t s)
+{
+    const int threads = 128;
+    mpc_export_primal_kernel<<<(d.B + threads - 1) / threads, threads, 0, s>>>(d, primal_out);
+}
+
+} // namespace wcb

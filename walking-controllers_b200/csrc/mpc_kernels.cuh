@@ -1,0 +1,100 @@
+// mpc_kernels.cuh — batched DCM-MPC for sm_100a: problem build (K1) + OSQP-equivalent ADMM (K2).
+//
+// Replaces, per controller instance and per 10 ms tick, the reference chain
+//   WalkingController::{setConvexHullConstraint,setFeedback,setReferenceSignal,solve}
+//     (modules/Walking_module/src/WalkingDCMModelPredictiveController.cpp:364-521)
+//   MPCSolver::{setConstraintsMatrix,setBounds,setGradient,initialize,solve,getSolution}
+//     (modules/Walking_module/src/MPCSolver.cpp:76-322)
+//   OsqpEigen::Solver -> OSQP (Ruiz scaling, KKT LDL^T, ADMM, adaptive rho; external).
+//
+// Formulation: exactly the reference's sparse (non-condensed) QP, z = [x_0..x_N, u_0..u_{N-1}],
+// n = 4N+2, m = 2(N+1) + n_hull.  OSQP's KKT solve  [[P+sI, A'],[A, -1/rho]] [x~;nu] = rhs  is done
+// on the mathematically identical reduced SPD system  (P + sI + A' rho A) x~ = rhs_x + A' rho rhs_z,
+// z~ = A x~.  With diagonal Q, R (all shipped configurations) the two axes decouple except for the
+// hull rows on u_0, so with the per-axis "chain" order  x_N, u_{N-1}, x_{N-1}, ..., x_1, u_0, x_0
+// the reduced matrix is pentadiagonal per axis plus one dense 4x4 corner (u_0, x_0 of both axes).
+//
+// Data layout: every per-instance quantity lives in HBM as field-major SoA ([field][B]); one
+// instance is handled by G cooperating lanes of a warp with its working set staged in shared
+// memory; the two axis chains of the sequential triangular solves run on two lanes.
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/wc_capi.h"
+
+namespace wcb {
+
+constexpr int kMaxHull = 8;
+
+constexpr double kRhoMin = 1e-6;
+constexpr double kRhoMax = 1e6;
+constexpr double kRhoEqOverIneq = 1e3;
+constexpr double kMinScaling = 1e-4;
+constexpr double kMaxScaling = 1e4;
+
+// Device-side view of one handle's state.  All arrays are [rows][B] (element (r,i) at r*B+i).
+struct MpcDev {
+    int B, N;
+    // constants
+    double a_dyn, b_dyn;
+    double foot_front, foot_back, foot_left, foot_right;
+    double init_zmp[2];
+    double hull_tol;
+    wc_osqp_settings st;
+    int rho_interval; // resolved adaptive_rho_interval
+    int ring_head;    // slot of stage 0 in the gradient ring for THIS tick
+    // per-instance weights
+    double* Qd; // [2][B]
+    double* Rd; // [2][B]
+    // persistent solver state (chain order per axis: index a*nA + j)
+    double* x;      // [2*nA][B] scaled primal iterate
+    double* yeq;    // [2*nR][B] scaled duals of the equality rows (index a*nR + k)
+    double* yh;     // [8][B]
+    double* zh;     // [8][B]
+    double* z0;     // [2][B]  z of equality row 0 (the only equality z that is not identically its bound)
+    double* D;      // [2*nA][B]
+    double* Eeq;    // [2*nR][B]
+    double* Eh;     // [8][B]
+    double* cscale; // [B]
+    double* rho;    // [B]
+    double* grad;   // [2*nR][B] unscaled gradient of the state block, ring-buffered over stages
+    double* hullA;  // [16][B]  (row h: [2h], [2h+1])
+    double* hullb;  // [8][B]
+    double* hullv;  // [16][B]
+    double* uprev;  // [2][B]  m_output
+    int32_t* nhull;      // [B]
+    uint8_t* feet;       // [B] bit0 left, bit1 right (m_feetStatus)
+    uint8_t* have_solver;// [B]
+    uint8_t* inited;     // [B] OSQP workspace exists (initSolver done)
+    int32_t* rho_updates;// [B]
+    int32_t* tick_flags; // [B] K1 -> K2 (WC_MPC_FLAG_*), also the tick's flag output
+};
+
+struct MpcTickIO {
+    const double* lf_H; const double* rf_H;
+    const uint8_t* l_contact; const uint8_t* r_contact;
+    const double* dcm; const double* ref; const uint8_t* reset;
+    double* zmp; int32_t* status; int32_t* iters; int32_t* flags;
+};
+
+__host__ __device__ inline int mpc_nA(int N) { return 2 * N + 1; }
+__host__ __device__ inline int mpc_nR(int N) { return N + 1; }
+// doubles of shared memory per instance in K2
+__host__ __device__ inline int mpc_smem_doubles(int N)
+{
+    const int nA = mpc_nA(N), nR = mpc_nR(N);
+    return 2 * nA * 7   // X, QB, W, L1, L2, DI, DD
+         + 2 * nR * 6   // YE, DYE, CM, CA, CB, EE
+         + 8 * 8        // HX, HY, UH, LH, ZH, YH, DYH, EH
+         + 16           // corner factor + scratch
+         + 8;           // reduction scratch / pad (keeps the stride == 8 mod 16 for N == 25)
+}
+
+void launch_mpc_prepare(const MpcDev& d, const MpcTickIO& io, cudaStream_t s);
+cudaError_t launch_mpc_admm(const MpcDev& d, const MpcTickIO& io, int lanes_per_instance, cudaStream_t s);
+void launch_mpc_export_primal(const MpcDev& d, double* primal_out, cudaStream_t s);
+int mpc_admm_max_smem();
+
+} // namespace wcb

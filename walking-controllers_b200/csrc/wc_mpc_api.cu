@@ -1,0 +1,291 @@
+// wc_mpc_api.cu — C ABI of the batched DCM-MPC (include/wc_capi.h): handle management,
+// device state allocation, kernel launches, pinned host staging.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/wc_capi.h"
+#include "mpc_kernels.cuh"
+
+using namespace wcb;
+
+struct wc_mpc {
+    MpcDev d;
+    wc_mpc_config cfg;
+    int device;
+    int lanes;
+    int64_t launches;
+    int64_t tick;
+    std::vector<void*> allocs;
+    // staging for the *_host entry points
+    void* pin_in; void* pin_out; void* dev_in; void* dev_out;
+    size_t in_bytes, out_bytes;
+    cudaStream_t host_stream;
+};
+
+namespace {
+
+template <typename T>
+cudaError_t dalloc(wc_mpc* h, T** p, size_t count)
+{
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, count * sizeof(T));
+    if (e != cudaSuccess) return e;
+    e = cudaMemset(q, 0, count * sizeof(T));
+    if (e != cudaSuccess) return e;
+    h->allocs.push_back(q);
+    *p = static_cast<T*>(q);
+    return cudaSuccess;
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int env_int(const char* name, int dflt)
+{
+    const char* v = std::getenv(name);
+    return v ? std::atoi(v) : dflt;
+}
+
+} // namespace
+
+extern "C" {
+
+const char* wc_version(void) { return "wc_b200 0.1 sm_100a"; }
+
+wc_status wc_mpc_create(const wc_mpc_config* cfg, int32_t B, int32_t device, wc_mpc** out)
+{
+    if (!cfg || !out || B < 1 || cfg->horizon < 1) return WC_ERR_INVALID_ARG;
+    *out = nullptr;
+    // fast path: diagonal weights (all shipped configurations); see DESIGN.md
+    if (cfg->Q[1] != 0.0 || cfg->Q[2] != 0.0 || cfg->R[1] != 0.0 || cfg->R[2] != 0.0) return WC_ERR_UNSUPPORTED;
+    if (!(cfg->sampling_time > 0) || !(cfg->com_height > 0) || !(cfg->gravity > 0)) return WC_ERR_INVALID_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) return WC_ERR_NO_DEVICE;
+    if (device < 0 || device >= ndev) return WC_ERR_INVALID_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) return WC_ERR_CUDA;
+
+    wc_mpc* h = new (std::nothrow) wc_mpc();
+    if (!h) return WC_ERR_ALLOC;
+    h->cfg = *cfg;
+    h->device = device;
+    h->launches = 0;
+    h->tick = 0;
+    h->pin_in = h->pin_out = h->dev_in = h->dev_out = nullptr;
+    h->host_stream = nullptr;
+    MpcDev& d = h->d;
+    std::memset(&d, 0, sizeof(d));
+    d.B = B;
+    d.N = cfg->horizon;
+    const double omega = std::sqrt(cfg->gravity / cfg->com_height);
+    d.a_dyn = std::exp(omega * cfg->sampling_time);
+    d.b_dyn = 1.0 - std::exp(omega * cfg->sampling_time);
+    const double x1 = cfg->foot_x[0], x2 = cfg->foot_x[1], y1 = cfg->foot_y[0], y2 = cfg->foot_y[1];
+    d.foot_front = std::fabs(x1 > x2 ? x1 : x2);
+    d.foot_back = std::fabs(x1 < x2 ? x1 : x2);
+    d.foot_left = std::fabs(y1 > y2 ? y1 : y2);
+    d.foot_right = std::fabs(y1 < y2 ? y1 : y2);
+    d.init_zmp[0] = cfg->initial_zmp[0];
+    d.init_zmp[1] = cfg->initial_zmp[1];
+    d.hull_tol = cfg->hull_tolerance;
+    d.st = cfg->osqp;
+    d.rho_interval = cfg->osqp.adaptive_rho_interval;
+    if (cfg->osqp.adaptive_rho && d.rho_interval == 0)
+        d.rho_interval = cfg->osqp.check_termination ? 4 * cfg->osqp.check_termination : 100;
+    d.ring_head = 0;
+
+    const size_t Bz = (size_t)B;
+    const int nA = mpc_nA(d.N), nR = mpc_nR(d.N);
+    cudaError_t e = cudaSuccess;
+#define TRY(x) do { if (e == cudaSuccess) e = (x); } while (0)
+    TRY(dalloc(h, &d.Qd, 2 * Bz)); TRY(dalloc(h, &d.Rd, 2 * Bz));
+    TRY(dalloc(h, &d.x, 2 * nA * Bz)); TRY(dalloc(h, &d.yeq, 2 * nR * Bz));
+    TRY(dalloc(h, &d.yh, 8 * Bz)); TRY(dalloc(h, &d.zh, 8 * Bz)); TRY(dalloc(h, &d.z0, 2 * Bz));
+    TRY(dalloc(h, &d.D, 2 * nA * Bz)); TRY(dalloc(h, &d.Eeq, 2 * nR * Bz)); TRY(dalloc(h, &d.Eh, 8 * Bz));
+    TRY(dalloc(h, &d.cscale, Bz)); TRY(dalloc(h, &d.rho, Bz));
+    TRY(dalloc(h, &d.grad, 2 * nR * Bz));
+    TRY(dalloc(h, &d.hullA, 16 * Bz)); TRY(dalloc(h, &d.hullb, 8 * Bz)); TRY(dalloc(h, &d.hullv, 16 * Bz));
+    TRY(dalloc(h, &d.uprev, 2 * Bz));
+    TRY(dalloc(h, &d.nhull, Bz)); TRY(dalloc(h, &d.feet, Bz)); TRY(dalloc(h, &d.have_solver, Bz));
+    TRY(dalloc(h, &d.inited, Bz)); TRY(dalloc(h, &d.rho_updates, Bz)); TRY(dalloc(h, &d.tick_flags, Bz));
+    if (e != cudaSuccess) { wc_mpc_destroy(h); return e == cudaErrorMemoryAllocation ? WC_ERR_ALLOC : WC_ERR_CUDA; }
+    {
+        std::vector<double> w(2 * Bz), r(2 * Bz), c1(Bz, 1.0), rho(Bz, cfg->osqp.rho), up(2 * Bz);
+        for (size_t i = 0; i < Bz; i++) {
+            w[i] = cfg->Q[0]; w[Bz + i] = cfg->Q[3];
+            r[i] = cfg->R[0]; r[Bz + i] = cfg->R[3];
+            up[i] = cfg->initial_zmp[0]; up[Bz + i] = cfg->initial_zmp[1];
+        }
+        TRY(cudaMemcpy(d.Qd, w.data(), 2 * Bz * sizeof(double), cudaMemcpyHostToDevice));
+        TRY(cudaMemcpy(d.Rd, r.data(), 2 * Bz * sizeof(double), cudaMemcpyHostToDevice));
+        TRY(cudaMemcpy(d.cscale, c1.data(), Bz * sizeof(double), cudaMemcpyHostToDevice));
+        TRY(cudaMemcpy(d.rho, rho.data(), Bz * sizeof(double), cudaMemcpyHostToDevice));
+        TRY(cudaMemcpy(d.uprev, up.data(), 2 * Bz * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    if (e != cudaSuccess) { wc_mpc_destroy(h); return WC_ERR_CUDA; }
+#undef TRY
+    // lanes per instance for the ADMM kernel: more lanes for longer horizons (more parallel
+    // vector work per sequential sweep).  WC_MPC_LANES overrides (tuning / tests).
+    int lanes = d.N <= 16 ? 4 : (d.N <= 64 ? 8 : (d.N <= 128 ? 16 : 32));
+    lanes = env_int("WC_MPC_LANES", lanes);
+    if (!(lanes == 2 || lanes == 4 || lanes == 8 || lanes == 16 || lanes == 32)) lanes = 8;
+    // the per-instance working set must fit in one CTA's shared memory
+    int stride = mpc_smem_doubles(d.N);
+    while ((stride % 16) != 8) stride++;
+    while (lanes < 32 && (size_t)stride * 8 * (32 / lanes) > (size_t)mpc_admm_max_smem()) lanes *= 2;
+    if ((size_t)stride * 8 * (32 / lanes) > (size_t)mpc_admm_max_smem()) { wc_mpc_destroy(h); return WC_ERR_UNSUPPORTED; }
+    h->lanes = lanes;
+    *out = h;
+    return WC_OK;
+}
+
+void wc_mpc_destroy(wc_mpc* h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    for (void* p : h->allocs) cudaFree(p);
+    if (h->pin_in) cudaFreeHost(h->pin_in);
+    if (h->pin_out) cudaFreeHost(h->pin_out);
+    if (h->dev_in) cudaFree(h->dev_in);
+    if (h->dev_out) cudaFree(h->dev_out);
+    if (h->host_stream) cudaStreamDestroy(h->host_stream);
+    delete h;
+}
+
+int32_t wc_mpc_batch(const wc_mpc* h) { return h ? h->d.B : 0; }
+int32_t wc_mpc_horizon(const wc_mpc* h) { return h ? h->d.N : 0; }
+int64_t wc_mpc_launch_count(const wc_mpc* h) { return h ? h->launches : 0; }
+
+wc_status wc_mpc_set_weights_host(wc_mpc* h, const double* q_diag, const double* r_diag)
+{
+    if (!h || !q_diag || !r_diag) return WC_ERR_INVALID_ARG;
+    cudaSetDevice(h->device);
+    const size_t bytes = 2 * (size_t)h->d.B * sizeof(double);
+    if (cudaMemcpy(h->d.Qd, q_diag, bytes, cudaMemcpyHostToDevice) != cudaSuccess) return WC_ERR_CUDA;
+    if (cudaMemcpy(h->d.Rd, r_diag, bytes, cudaMemcpyHostToDevice) != cudaSuccess) return WC_ERR_CUDA;
+    return WC_OK;
+}
+
+wc_status wc_mpc_reset(wc_mpc* h, const uint8_t* mask_host)
+{
+    if (!h) return WC_ERR_INVALID_ARG;
+    cudaSetDevice(h->device);
+    const size_t B = (size_t)h->d.B;
+    if (!mask_host) {
+        if (cudaMemset(h->d.feet, 0, B) != cudaSuccess) return WC_ERR_CUDA;
+        return WC_OK;
+    }
+    std::vector<uint8_t> f(B);
+    if (cudaMemcpy(f.data(), h->d.feet, B, cudaMemcpyDeviceToHost) != cudaSuccess) return WC_ERR_CUDA;
+    for (size_t i = 0; i < B; i++) if (mask_host[i]) f[i] = 0;
+    if (cudaMemcpy(h->d.feet, f.data(), B, cudaMemcpyHostToDevice) != cudaSuccess) return WC_ERR_CUDA;
+    return WC_OK;
+}
+
+wc_status wc_mpc_tick_dev(wc_mpc* h, const double* lf_H, const double* rf_H,
+                          const uint8_t* l_contact, const uint8_t* r_contact,
+                          const double* dcm_meas, const double* ref, const uint8_t* reset,
+                          double* zmp, int32_t* osqp_status, int32_t* iters, int32_t* flags, void* stream)
+{
+    if (!h || !lf_H || !rf_H || !l_contact || !r_contact || !dcm_meas || !ref) return WC_ERR_INVALID_ARG;
+    if (cudaSetDevice(h->device) != cudaSuccess) return WC_ERR_CUDA;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    MpcTickIO io{lf_H, rf_H, l_contact, r_contact, dcm_meas, ref, reset, zmp, osqp_status, iters, flags};
+    // gradient ring: stage k of this tick lives in slot (head + k) mod (N+1); advancing the head by
+    // one per tick is MPCSolver::setGradient's block shift (MPCSolver.cpp:216-221)
+    h->d.ring_head = (int)(h->tick % (int64_t)(h->d.N + 1));
+    launch_mpc_prepare(h->d, io, s);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = launch_mpc_admm(h->d, io, h->lanes, s);
+    h->launches += 2;
+    h->tick += 1;
+    if (e != cudaSuccess) {
+        std::fprintf(stderr, "[wc_mpc_tick_dev] CUDA error: %s\n", cudaGetErrorString(e));
+        return WC_ERR_CUDA;
+    }
+    return WC_OK;
+}
+
+wc_status wc_mpc_tick_host(wc_mpc* h, const double* lf_H, const double* rf_H,
+                           const uint8_t* l_contact, const uint8_t* r_contact,
+                           const double* dcm_meas, const double* ref, const uint8_t* reset,
+                           double* zmp, int32_t* osqp_status, int32_t* iters, int32_t* flags)
+{
+    if (!h || !lf_H || !rf_H || !l_contact || !r_contact || !dcm_meas || !ref) return WC_ERR_INVALID_ARG;
+    if (cudaSetDevice(h->device) != cudaSuccess) return WC_ERR_CUDA;
+    const size_t B = (size_t)h->d.B;
+    const int N = h->d.N;
+    // one packed input block and one packed output block -> one H2D and one D2H copy per tick
+    const size_t o_lf = 0, o_rf = o_lf + 12 * B * 8, o_dcm = o_rf + 12 * B * 8, o_ref = o_dcm + 2 * B * 8;
+    const size_t o_lc = o_ref + (size_t)2 * (N + 1) * B * 8, o_rc = o_lc + align_up(B, 8), o_rs = o_rc + align_up(B, 8);
+    const size_t in_bytes = o_rs + align_up(B, 8);
+    const size_t p_zmp = 0, p_st = p_zmp + 2 * B * 8, p_it = p_st + align_up(B * 4, 8), p_fl = p_it + align_up(B * 4, 8);
+    const size_t out_bytes = p_fl + align_up(B * 4, 8);
+    if (!h->pin_in) {
+        if (cudaMallocHost(&h->pin_in, in_bytes) != cudaSuccess) return WC_ERR_ALLOC;
+        if (cudaMallocHost(&h->pin_out, out_bytes) != cudaSuccess) return WC_ERR_ALLOC;
+        if (cudaMalloc(&h->dev_in, in_bytes) != cudaSuccess) return WC_ERR_ALLOC;
+        if (cudaMalloc(&h->dev_out, out_bytes) != cudaSuccess) return WC_ERR_ALLOC;
+        if (cudaStreamCreateWithFlags(&h->host_stream, cudaStreamNonBlocking) != cudaSuccess) return WC_ERR_CUDA;
+        h->in_bytes = in_bytes; h->out_bytes = out_bytes;
+    }
+    char* pi = static_cast<char*>(h->pin_in);
+    std::memcpy(pi + o_lf, lf_H, 12 * B * 8);
+    std::memcpy(pi + o_rf, rf_H, 12 * B * 8);
+    std::memcpy(pi + o_dcm, dcm_meas, 2 * B * 8);
+    std::memcpy(pi + o_ref, ref, (size_t)2 * (N + 1) * B * 8);
+    std::memcpy(pi + o_lc, l_contact, B);
+    std::memcpy(pi + o_rc, r_contact, B);
+    if (reset) std::memcpy(pi + o_rs, reset, B); else std::memset(pi + o_rs, 0, B);
+    cudaStream_t s = h->host_stream;
+    if (cudaMemcpyAsync(h->dev_in, h->pin_in, in_bytes, cudaMemcpyHostToDevice, s) != cudaSuccess) return WC_ERR_CUDA;
+    char* di = static_cast<char*>(h->dev_in);
+    char* dout = static_cast<char*>(h->dev_out);
+    wc_status rc = wc_mpc_tick_dev(h, (const double*)(di + o_lf), (const double*)(di + o_rf),
+                                   (const uint8_t*)(di + o_lc), (const uint8_t*)(di + o_rc),
+                                   (const double*)(di + o_dcm), (const double*)(di + o_ref),
+                                   (const uint8_t*)(di + o_rs),
+                                   (double*)(dout + p_zmp), (int32_t*)(dout + p_st), (int32_t*)(dout + p_it),
+                                   (int32_t*)(dout + p_fl), s);
+    if (rc != WC_OK) return rc;
+    if (cudaMemcpyAsync(h->pin_out, h->dev_out, out_bytes, cudaMemcpyDeviceToHost, s) != cudaSuccess) return WC_ERR_CUDA;
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) {
+        std::fprintf(stderr, "[wc_mpc_tick_host] CUDA error: %s\n", cudaGetErrorString(e));
+        return WC_ERR_CUDA;
+    }
+    const char* po = static_cast<const char*>(h->pin_out);
+    if (zmp) std::memcpy(zmp, po + p_zmp, 2 * B * 8);
+    if (osqp_status) std::memcpy(osqp_status, po + p_st, B * 4);
+    if (iters) std::memcpy(iters, po + p_it, B * 4);
+    if (flags) std::memcpy(flags, po + p_fl, B * 4);
+    return WC_OK;
+}
+
+wc_status wc_mpc_debug_get_host(wc_mpc* h, double* primal, double* rho, int32_t* rho_updates)
+{
+    if (!h) return WC_ERR_INVALID_ARG;
+    if (cudaSetDevice(h->device) != cudaSuccess) return WC_ERR_CUDA;
+    const size_t B = (size_t)h->d.B;
+    const size_t n = (size_t)(4 * h->d.N + 2);
+    if (cudaDeviceSynchronize() != cudaSuccess) return WC_ERR_CUDA;
+    if (primal) {
+        double* tmp = nullptr;
+        if (cudaMalloc(&tmp, n * B * sizeof(double)) != cudaSuccess) return WC_ERR_ALLOC;
+        launch_mpc_export_primal(h->d, tmp, nullptr);
+        h->launches += 1;
+        cudaError_t e = cudaMemcpy(primal, tmp, n * B * sizeof(double), cudaMemcpyDeviceToHost);
+        cudaFree(tmp);
+        if (e != cudaSuccess) return WC_ERR_CUDA;
+    }
+    if (rho && cudaMemcpy(rho, h->d.rho, B * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) return WC_ERR_CUDA;
+    if (rho_updates && cudaMemcpy(rho_updates, h->d.rho_updates, B * sizeof(int32_t), cudaMemcpyDeviceToHost) != cudaSuccess)
+        return WC_ERR_CUDA;
+    return WC_OK;
+}
+
+} // extern "C"
