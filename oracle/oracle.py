@@ -243,3 +243,89 @@ class MpcBatch:
         A = np.zeros((WCO_MAX_HULL, 2)); b = np.zeros(WCO_MAX_HULL)
         lib().wco_mpc_get_hull(inst, _dp(A), _dp(b))
         return A[:nh].copy(), b[:nh].copy()
+
+
+# ------------------------------------------------------------------------------------ kinematics / QP-IK
+def _bind_ik():
+    L = lib()
+    if getattr(L, "_ik_bound", False):
+        return L
+    dp = C.POINTER(C.c_double); ip = C.POINTER(C.c_int32); up = C.POINTER(C.c_uint8)
+    L.wco_fk.argtypes = [C.POINTER(Model), dp, dp, C.c_int] + [dp] * 8
+    L.wco_fk_batch.argtypes = [C.POINTER(Model), C.c_int, dp, dp, up] + [dp] * 8
+    L.wco_qp_solve.argtypes = [C.c_int, dp, dp, C.c_int, dp, dp, dp, dp, C.c_int, dp, ip]
+    L.wco_qp_solve.restype = C.c_int
+    L.wco_ik_solve.argtypes = [C.POINTER(IkConfig)] + [dp] * 16 + [dp, dp, dp, ip] + [dp] * 5
+    L.wco_ik_solve.restype = C.c_int
+    L.wco_ik_batch_tick.argtypes = [C.POINTER(IkConfig), C.POINTER(Model), C.c_int, dp, dp, dp, up] + [dp] * 8 + \
+                                   [dp, dp, dp, dp, dp, ip, ip, C.c_int]
+    L._ik_bound = True
+    return L
+
+
+def fk(model, q, base_H, left_is_fixed):
+    """single instance; returns dict of row-major arrays"""
+    L = _bind_ik()
+    nV = model.n_dofs + 6
+    q = _f64(q); base_H = _f64(base_H)
+    o = dict(lf_H=np.zeros(12), rf_H=np.zeros(12), neck_R=np.zeros(9), com=np.zeros(3),
+             J_lf=np.zeros((6, nV)), J_rf=np.zeros((6, nV)), J_neck=np.zeros((6, nV)), J_com=np.zeros((3, nV)))
+    L.wco_fk(C.byref(model), _dp(q), _dp(base_H), int(left_is_fixed), _dp(o["lf_H"]), _dp(o["rf_H"]), _dp(o["neck_R"]),
+             _dp(o["com"]), _dp(o["J_lf"]), _dp(o["J_rf"]), _dp(o["J_neck"]), _dp(o["J_com"]))
+    return o
+
+
+def fk_batch(model, q, base_H, left_is_fixed, jacobians=True):
+    """SoA batch: q [nJ,B], base_H [12,B], left_is_fixed [B] -> dict of [rows,B] arrays"""
+    L = _bind_ik()
+    q = _f64(q); base_H = _f64(base_H); lif = _u8(left_is_fixed)
+    B = q.shape[1]; nV = model.n_dofs + 6
+    o = dict(lf_H=np.zeros((12, B)), rf_H=np.zeros((12, B)), neck_R=np.zeros((9, B)), com=np.zeros((3, B)))
+    if jacobians:
+        o.update(J_lf=np.zeros((6 * nV, B)), J_rf=np.zeros((6 * nV, B)), J_neck=np.zeros((6 * nV, B)),
+                 J_com=np.zeros((3 * nV, B)))
+    L.wco_fk_batch(C.byref(model), B, _dp(q), _dp(base_H), _up(lif), _dp(o["lf_H"]), _dp(o["rf_H"]), _dp(o["neck_R"]),
+                   _dp(o["com"]), _dp(o.get("J_lf")), _dp(o.get("J_rf")), _dp(o.get("J_neck")), _dp(o.get("J_com")))
+    return o
+
+
+def qp_solve(H, g, A, b, lb, ub, nwsr_max=100):
+    L = _bind_ik()
+    H = _f64(H); g = _f64(g); A = _f64(A); b = _f64(b); lb = _f64(lb); ub = _f64(ub)
+    n = H.shape[0]; mE = A.shape[0] if A.size else 0
+    x = np.zeros(n); nw = np.zeros(1, np.int32)
+    st = L.wco_qp_solve(n, _dp(H), _dp(g), mE, _dp(A), _dp(b), _dp(lb), _dp(ub), nwsr_max, _dp(x), _ip(nw))
+    return st, x, int(nw[0])
+
+
+def ik_solve(cfg, q_meas, lf_H, rf_H, neck_R, com_meas, J_lf, J_rf, J_neck, J_com, lf_H_des, rf_H_des, lf_twist,
+             rf_twist, com_pos_des, com_vel_des, neck_R_des):
+    """single instance with caller-supplied kinematics; also returns the assembled QP"""
+    L = _bind_ik()
+    nJ = cfg.n_dofs; nV = nJ + 6; nC = 15 if cfg.use_com_as_constraint else 12
+    a = [_f64(v) for v in (q_meas, lf_H, rf_H, neck_R, com_meas, J_lf, J_rf, J_neck, J_com, lf_H_des, rf_H_des,
+                           lf_twist, rf_twist, com_pos_des, com_vel_des, neck_R_des)]
+    dq = np.zeros(nJ); le = np.zeros(6); re = np.zeros(6); nw = np.zeros(1, np.int32)
+    H = np.zeros((nV, nV)); g = np.zeros(nV); A = np.zeros((nC, nV)); b = np.zeros(nC); v = np.zeros(nV)
+    st = L.wco_ik_solve(C.byref(cfg), *[_dp(x) for x in a], _dp(dq), _dp(le), _dp(re), _ip(nw),
+                        _dp(H), _dp(g), _dp(A), _dp(b), _dp(v))
+    return dict(status=st, dq=dq, lf_err=le, rf_err=re, nwsr=int(nw[0]), H=H, g=g, A=A, b=b, v=v)
+
+
+def ik_batch_tick(cfg, model, inp, kpos=None, katt=None, threads=1):
+    """inp: dict with the SoA arrays of wc_ik_tick_host (numpy); returns dict"""
+    L = _bind_ik()
+    B = inp["q_meas"].shape[1]; nJ = cfg.n_dofs
+    keys = ("q_meas", "q_lin", "base_H")
+    a = {k: _f64(inp[k]) for k in ("q_meas", "q_lin", "base_H", "lf_H_des", "rf_H_des", "lf_twist", "rf_twist",
+                                   "com_pos_des", "com_vel_des", "com_meas", "neck_R_des")}
+    lif = _u8(inp["left_is_fixed"])
+    kp = _f64(kpos) if kpos is not None else None
+    ka = _f64(katt) if katt is not None else None
+    dq = np.zeros((nJ, B)); le = np.zeros((6, B)); re = np.zeros((6, B))
+    st = np.zeros(B, np.int32); nw = np.zeros(B, np.int32)
+    L.wco_ik_batch_tick(C.byref(cfg), C.byref(model), B, _dp(a["q_meas"]), _dp(a["q_lin"]), _dp(a["base_H"]), _up(lif),
+                        _dp(a["lf_H_des"]), _dp(a["rf_H_des"]), _dp(a["lf_twist"]), _dp(a["rf_twist"]),
+                        _dp(a["com_pos_des"]), _dp(a["com_vel_des"]), _dp(a["com_meas"]), _dp(a["neck_R_des"]),
+                        _dp(kp), _dp(ka), _dp(dq), _dp(le), _dp(re), _ip(st), _ip(nw), threads)
+    return dict(dq=dq, lf_err=le, rf_err=re, status=st, nwsr=nw)

@@ -56,6 +56,31 @@ void wco_mpc_batch_tick(wco_mpc_batch* b, const double* lf_H, const double* rf_H
                         double* zmp, int* osqp_status, int* iters, int* flags, int n_threads);
 void wco_mpc_batch_get_solution(wco_mpc_batch* b, double* primal, double* rho, int* rho_updates);
 
+/* ---- kinematics (iDynTree KinDynComputations restatement), single instance, row-major ---- */
+void wco_fk(const wc_model* m, const double* q, const double* base_H12, int left_is_fixed,
+            double* lf_H12, double* rf_H12, double* neck_R9, double* com3,
+            double* J_lf, double* J_rf, double* J_neck, double* J_com);
+void wco_fk_batch(const wc_model* model, int B, const double* q, const double* base_H, const unsigned char* left_is_fixed,
+                  double* lf_H, double* rf_H, double* neck_R, double* com,
+                  double* J_lf, double* J_rf, double* J_neck, double* J_com);
+
+/* ---- exact dense QP (qpOASES stand-in) and WalkingQPIK_qpOASES restatement ---- */
+int wco_qp_solve(int n, const double* H, const double* g, int mE, const double* A, const double* b,
+                 const double* lb, const double* ub, int nwsr_max, double* x, int* nwsr_out);
+int wco_ik_solve(const wc_ik_config* cfg,
+                 const double* q_meas, const double* lf_H, const double* rf_H, const double* neck_R, const double* com_meas,
+                 const double* J_lf, const double* J_rf, const double* J_neck6, const double* J_com,
+                 const double* lf_H_des, const double* rf_H_des, const double* lf_twist, const double* rf_twist,
+                 const double* com_pos_des, const double* com_vel_des, const double* neck_R_des,
+                 double* dq, double* lf_err, double* rf_err, int* nwsr,
+                 double* H_out, double* g_out, double* A_out, double* b_out, double* v_out);
+void wco_ik_batch_tick(const wc_ik_config* cfg, const wc_model* model, int B,
+                       const double* q_meas, const double* q_lin, const double* base_H, const unsigned char* left_is_fixed,
+                       const double* lf_H_des, const double* rf_H_des, const double* lf_twist, const double* rf_twist,
+                       const double* com_pos_des, const double* com_vel_des, const double* com_meas, const double* neck_R_des,
+                       const double* kpos, const double* katt,
+                       double* dq, double* lf_err, double* rf_err, int* status, int* nwsr, int n_threads);
+
 /* ---- generic OSQP restatement on dense input (for cross-checks from Python) ---- */
 /* P: n x n row-major symmetric (upper triangle is used), A: m x n row-major.
  * Returns status; x_out [n], y_out [m], info_out = {iter, rho_updates, rho, pri_res, dua_res}. */

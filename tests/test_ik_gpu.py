@@ -1,0 +1,129 @@
+"""GPU parity of the batched FK/Jacobian kernel (K3) and QP-IK solve (K4) against the oracle.
+
+Tolerances (BASELINE.json north_star): 1e-5 rad/s on IK joint velocities for strictly convex
+instances (we hold 1e-8), identical solver status; FK/Jacobians 1e-12 absolute."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+DQ_TOL = 1e-8
+
+
+def make_inputs(syn, oracle, B, seed, perturb=1.0):
+    m = oracle.model_icub_like()
+    cfg = oracle.ik_default_config()
+    qreg = torch.tensor(list(cfg.joint_reg_rad[:23]), dtype=torch.float64)
+
+    def fkb(ql, bH, lif):
+        o = oracle.fk_batch(m, ql.numpy(), bH.numpy(), lif.numpy(), jacobians=False)
+        return {k: torch.from_numpy(v) for k, v in o.items()}
+
+    return syn.ik_inputs(B, seed, qreg, fkb, perturb=perturb)
+
+
+def test_fk_jacobians_parity(wc, syn, oracle, cuda_device):
+    B = 257
+    inp = make_inputs(syn, oracle, B, 3)
+    ik = wc.IkBatch(wc.ik_default_config(), wc.model_icub_like(), B)
+    g = ik.fk(inp["q_lin"].to(cuda_device), inp["base_H"].to(cuda_device), inp["left_is_fixed"].to(cuda_device))
+    torch.cuda.synchronize()
+    o = oracle.fk_batch(oracle.model_icub_like(), inp["q_lin"].numpy(), inp["base_H"].numpy(), inp["left_is_fixed"].numpy())
+    for k in ("lf_H", "rf_H", "neck_R", "com", "J_lf", "J_rf", "J_neck", "J_com"):
+        err = np.abs(g[k].cpu().numpy() - o[k]).max()
+        assert err < 1e-12, (k, err)
+    ik.close()
+
+
+def _compare(out_g, out_o, tag=""):
+    sg = out_g["status"]; so = out_o["status"]
+    assert np.array_equal(sg, so), f"{tag} status differs at {np.nonzero(sg != so)[0][:10]}"
+    ok = so == 0
+    err = np.abs(out_g["dq"] - out_o["dq"])[:, ok].max() if ok.any() else 0.0
+    assert err <= DQ_TOL, f"{tag} dq err {err}"
+    assert np.abs(out_g["lf_err"] - out_o["lf_err"])[:, ok].max() <= 1e-8
+    assert np.abs(out_g["rf_err"] - out_o["rf_err"])[:, ok].max() <= 1e-8
+    assert np.array_equal(out_g["nwsr"][ok], out_o["nwsr"][ok]), f"{tag} nWSR differs"
+    return err
+
+
+@pytest.mark.parametrize("vmax,perturb", [(1.0, 1.0), (10.0, 1.0), (0.4, 1.0), (0.25, 0.5)])
+def test_ik_tick_parity(wc, syn, oracle, cuda_device, vmax, perturb):
+    B = 300
+    inp = make_inputs(syn, oracle, B, 11, perturb)
+    cfg_o = oracle.ik_default_config(); cfg_g = wc.ik_default_config()
+    for c in (cfg_o, cfg_g):
+        for i in range(23):
+            c.min_vel[i] = -vmax; c.max_vel[i] = vmax
+    out_o = oracle.ik_batch_tick(cfg_o, oracle.model_icub_like(), {k: v.numpy() for k, v in inp.items()})
+    ik = wc.IkBatch(cfg_g, wc.model_icub_like(), B)
+    out = ik.tick({k: v.to(cuda_device) for k, v in inp.items()})
+    torch.cuda.synchronize()
+    out_g = {k: v.cpu().numpy() for k, v in out.items()}
+    err = _compare(out_g, out_o, f"vmax={vmax}")
+    print("vmax", vmax, "dq err", err, "status", np.unique(out_o["status"], return_counts=True),
+          "nwsr", np.unique(out_o["nwsr"], return_counts=True))
+    # the host-pointer entry point gives the same answer
+    out_h = ik.tick_host({k: np.ascontiguousarray(v.numpy()) for k, v in inp.items()})
+    for k in ("dq", "status", "nwsr"):
+        assert np.array_equal(out_h[k], out_g[k])
+    ik.close()
+
+
+def test_ik_com_in_cost_and_gains(wc, syn, oracle, cuda_device):
+    """useCoMAsConstraint = 0 (12 equality rows, CoM task in the cost) and per-instance gains (config 4)."""
+    B = 128
+    inp = make_inputs(syn, oracle, B, 5)
+    cfg_o = oracle.ik_default_config(); cfg_g = wc.ik_default_config()
+    cfg_o.use_com_as_constraint = 0; cfg_g.use_com_as_constraint = 0
+    rng = np.random.default_rng(0)
+    kp = rng.choice([2.5, 4.0, 7.0], size=B); ka = rng.choice([2.0, 5.0], size=B)
+    out_o = oracle.ik_batch_tick(cfg_o, oracle.model_icub_like(), {k: v.numpy() for k, v in inp.items()}, kpos=kp, katt=ka)
+    ik = wc.IkBatch(cfg_g, wc.model_icub_like(), B)
+    ik.set_gains(kp, ka)
+    out = ik.tick({k: v.to(cuda_device) for k, v in inp.items()})
+    torch.cuda.synchronize()
+    _compare({k: v.cpu().numpy() for k, v in out.items()}, out_o, "com-in-cost")
+    ik.close()
+
+
+def test_ik_external_jacobians(wc, syn, oracle, cuda_device):
+    """WalkingQPIK drop-in path: caller-supplied transforms and Jacobians (set*Jacobian/setRobotState)."""
+    B = 64
+    inp = make_inputs(syn, oracle, B, 9)
+    m = oracle.model_icub_like()
+    kin = oracle.fk_batch(m, inp["q_lin"].numpy(), inp["base_H"].numpy(), inp["left_is_fixed"].numpy())
+    out_o = oracle.ik_batch_tick(oracle.ik_default_config(), m, {k: v.numpy() for k, v in inp.items()})
+    ik = wc.IkBatch(wc.ik_default_config(), wc.model_icub_like(), B)
+    out = ik.solve_with_jacobians({k: torch.from_numpy(v).to(cuda_device) for k, v in kin.items()},
+                                  {k: v.to(cuda_device) for k, v in inp.items()})
+    torch.cuda.synchronize()
+    _compare({k: v.cpu().numpy() for k, v in out.items()}, out_o, "ext-jac")
+    ik.close()
+
+
+def test_ik_rank_deficient_rows_flagged(wc, syn, oracle, cuda_device):
+    """identical left/right foot Jacobians make the equality rows dependent -> status must match the oracle"""
+    B = 32
+    inp = make_inputs(syn, oracle, B, 2)
+    m = oracle.model_icub_like()
+    kin = oracle.fk_batch(m, inp["q_lin"].numpy(), inp["base_H"].numpy(), inp["left_is_fixed"].numpy())
+    kin["J_rf"] = kin["J_lf"].copy()
+    cfg = oracle.ik_default_config()
+    st_o = []
+    for i in range(B):
+        g = lambda a, r: np.ascontiguousarray(a[:, i]).reshape(r)
+        o = oracle.ik_solve(cfg, inp["q_meas"].numpy()[:, i], kin["lf_H"][:, i], kin["rf_H"][:, i], kin["neck_R"][:, i],
+                            inp["com_meas"].numpy()[:, i], g(kin["J_lf"], (6, 29)), g(kin["J_rf"], (6, 29)),
+                            g(kin["J_neck"], (6, 29)), g(kin["J_com"], (3, 29)), inp["lf_H_des"].numpy()[:, i],
+                            inp["rf_H_des"].numpy()[:, i], inp["lf_twist"].numpy()[:, i], inp["rf_twist"].numpy()[:, i],
+                            inp["com_pos_des"].numpy()[:, i], inp["com_vel_des"].numpy()[:, i], inp["neck_R_des"].numpy()[:, i])
+        st_o.append(o["status"])
+    ik = wc.IkBatch(wc.ik_default_config(), wc.model_icub_like(), B)
+    out = ik.solve_with_jacobians({k: torch.from_numpy(v).to(cuda_device) for k, v in kin.items()},
+                                  {k: v.to(cuda_device) for k, v in inp.items()})
+    torch.cuda.synchronize()
+    assert np.array_equal(out["status"].cpu().numpy(), np.array(st_o, np.int32))
+    assert (np.array(st_o) != 0).all()
+    ik.close()

@@ -230,3 +230,99 @@ class MpcBatch:
     @property
     def launches(self):
         return lib().wc_mpc_launch_count(self.h)
+
+
+IK_INPUT_KEYS = ("q_meas", "q_lin", "base_H", "left_is_fixed", "lf_H_des", "rf_H_des", "lf_twist", "rf_twist",
+                 "com_pos_des", "com_vel_des", "com_meas", "neck_R_des")
+
+
+class IkBatch:
+    """Batched FK + QP-IK handle (mirrors WalkingFK + WalkingQPIK_qpOASES for B instances)."""
+
+    def __init__(self, cfg, model, B, device=0):
+        self.cfg, self.model, self.B, self.nJ, self.device = cfg, model, B, cfg.n_dofs, device
+        h = _VP()
+        _check(lib().wc_ik_create(C.byref(cfg), C.byref(model), B, device, C.byref(h)), "wc_ik_create")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().wc_ik_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_gains(self, k_pos_foot, k_att_foot):
+        _check(lib().wc_ik_set_gains_host(self.h, _ptr(k_pos_foot), _ptr(k_att_foot)), "wc_ik_set_gains_host")
+
+    def _outs(self, dev):
+        import torch
+        B, nJ = self.B, self.nJ
+        return dict(dq=torch.empty(nJ, B, dtype=torch.float64, device=dev),
+                    lf_err=torch.empty(6, B, dtype=torch.float64, device=dev),
+                    rf_err=torch.empty(6, B, dtype=torch.float64, device=dev),
+                    status=torch.empty(B, dtype=torch.int32, device=dev),
+                    nwsr=torch.empty(B, dtype=torch.int32, device=dev))
+
+    def tick(self, inp, out=None, stream=None):
+        """inp: dict of CUDA tensors keyed by IK_INPUT_KEYS"""
+        import torch
+        dev = inp["q_meas"].device
+        if out is None:
+            out = self._outs(dev)
+        if stream is None:
+            stream = torch.cuda.current_stream(dev).cuda_stream
+        _check(lib().wc_ik_tick_dev(self.h, *[_ptr(inp[k]) for k in IK_INPUT_KEYS], _ptr(out["dq"]), _ptr(out["lf_err"]),
+                                    _ptr(out["rf_err"]), _ptr(out["status"]), _ptr(out["nwsr"]), stream), "wc_ik_tick_dev")
+        return out
+
+    def tick_host(self, inp, out=None):
+        import numpy as np
+        B, nJ = self.B, self.nJ
+        if out is None:
+            out = dict(dq=np.empty((nJ, B)), lf_err=np.empty((6, B)), rf_err=np.empty((6, B)),
+                       status=np.empty(B, np.int32), nwsr=np.empty(B, np.int32))
+        _check(lib().wc_ik_tick_host(self.h, *[_ptr(inp[k]) for k in IK_INPUT_KEYS], _ptr(out["dq"]), _ptr(out["lf_err"]),
+                                     _ptr(out["rf_err"]), _ptr(out["status"]), _ptr(out["nwsr"])), "wc_ik_tick_host")
+        return out
+
+    def fk(self, q, base_H, left_is_fixed, jacobians=True, stream=None):
+        import torch
+        dev, B, nV = q.device, self.B, self.nJ + 6
+        f64 = torch.float64
+        o = dict(lf_H=torch.empty(12, B, dtype=f64, device=dev), rf_H=torch.empty(12, B, dtype=f64, device=dev),
+                 neck_R=torch.empty(9, B, dtype=f64, device=dev), com=torch.empty(3, B, dtype=f64, device=dev))
+        if jacobians:
+            o.update(J_lf=torch.empty(6 * nV, B, dtype=f64, device=dev), J_rf=torch.empty(6 * nV, B, dtype=f64, device=dev),
+                     J_neck=torch.empty(6 * nV, B, dtype=f64, device=dev), J_com=torch.empty(3 * nV, B, dtype=f64, device=dev))
+        if stream is None:
+            stream = torch.cuda.current_stream(dev).cuda_stream
+        _check(lib().wc_fk_dev(self.h, _ptr(q), _ptr(base_H), _ptr(left_is_fixed), _ptr(o["lf_H"]), _ptr(o["rf_H"]),
+                               _ptr(o["neck_R"]), _ptr(o["com"]), _ptr(o.get("J_lf")), _ptr(o.get("J_rf")),
+                               _ptr(o.get("J_neck")), _ptr(o.get("J_com")), stream), "wc_fk_dev")
+        return o
+
+    def solve_with_jacobians(self, kin, inp, out=None, stream=None):
+        """kin: dict lf_H, rf_H, neck_R, J_lf, J_rf, J_neck, J_com (CUDA tensors); inp as for tick()"""
+        import torch
+        dev = inp["q_meas"].device
+        if out is None:
+            out = self._outs(dev)
+        if stream is None:
+            stream = torch.cuda.current_stream(dev).cuda_stream
+        _check(lib().wc_ik_solve_with_jacobians_dev(
+            self.h, _ptr(inp["q_meas"]), _ptr(kin["lf_H"]), _ptr(kin["rf_H"]), _ptr(kin["neck_R"]), _ptr(inp["com_meas"]),
+            _ptr(kin["J_lf"]), _ptr(kin["J_rf"]), _ptr(kin["J_neck"]), _ptr(kin["J_com"]),
+            _ptr(inp["lf_H_des"]), _ptr(inp["rf_H_des"]), _ptr(inp["lf_twist"]), _ptr(inp["rf_twist"]),
+            _ptr(inp["com_pos_des"]), _ptr(inp["com_vel_des"]), _ptr(inp["neck_R_des"]),
+            _ptr(out["dq"]), _ptr(out["lf_err"]), _ptr(out["rf_err"]), _ptr(out["status"]), _ptr(out["nwsr"]), stream),
+            "wc_ik_solve_with_jacobians_dev")
+        return out
+
+    @property
+    def launches(self):
+        return lib().wc_ik_launch_count(self.h)

@@ -1,0 +1,801 @@
+// ik_kernels.cu — see ik_kernels.cuh for the mapping to the reference.
+#include "ik_kernels.cuh"
+
+#include <cfloat>
+#include <cmath>
+
+namespace wcb {
+
+namespace {
+
+constexpr double kQpInf = 1e20;      // qpOASES INFTY
+constexpr double kViolTol = 1e-10;
+constexpr double kRankTol = 1e-11;
+
+constexpr int kWarpsPerBlock = 4;
+
+// ---- small 3x3 / rigid transform helpers (row-major R[9], p[3]) ---------------------------------
+__device__ __forceinline__ void mat3_mul(const double* a, const double* b, double* o)
+{
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+#pragma unroll
+        for (int c = 0; c < 3; c++) o[3 * r + c] = a[3 * r] * b[c] + a[3 * r + 1] * b[3 + c] + a[3 * r + 2] * b[6 + c];
+}
+__device__ __forceinline__ void mat3_mul_bt(const double* a, const double* b, double* o)
+{
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+#pragma unroll
+        for (int c = 0; c < 3; c++) o[3 * r + c] = a[3 * r] * b[3 * c] + a[3 * r + 1] * b[3 * c + 1] + a[3 * r + 2] * b[3 * c + 2];
+}
+__device__ __forceinline__ void xf_mul(const double* Ra, const double* pa, const double* Rb, const double* pb, double* Ro, double* po)
+{
+    double R[9], p[3];
+    mat3_mul(Ra, Rb, R);
+#pragma unroll
+    for (int r = 0; r < 3; r++) p[r] = Ra[3 * r] * pb[0] + Ra[3 * r + 1] * pb[1] + Ra[3 * r + 2] * pb[2] + pa[r];
+#pragma unroll
+    for (int k = 0; k < 9; k++) Ro[k] = R[k];
+#pragma unroll
+    for (int k = 0; k < 3; k++) po[k] = p[k];
+}
+__device__ __forceinline__ void cross3(const double* a, const double* b, double* o)
+{
+    o[0] = a[1] * b[2] - a[2] * b[1];
+    o[1] = a[2] * b[0] - a[0] * b[2];
+    o[2] = a[0] * b[1] - a[1] * b[0];
+}
+// unskew(1/2 (M - M')), M = R Rdes'   (Utils.cpp:22-27 + iDynTree::unskew)
+__device__ __forceinline__ void rot_error(const double* R, const double* Rdes, double* e)
+{
+    double M[9];
+    mat3_mul_bt(R, Rdes, M);
+    e[0] = 0.5 * (M[7] - M[5]);
+    e[1] = 0.5 * (M[2] - M[6]);
+    e[2] = 0.5 * (M[3] - M[1]);
+}
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// ---- Goldfarb-Idnani dual active set on the bounds, reduced space (sequential, one lane) ----------
+// Mirrors oracle/qpik_ref.c step 5.  All arrays live in shared memory.
+template <int NV, int NZ>
+__device__ __noinline__ int gi_bounds(const double* ZS /*[NV][NZ+1]*/, const double* XP, const double* LB, const double* UB,
+                                      const double* LS /*[NZ][NZ+1] chol*/, double* JS, double* RS, double* W,
+                                      double* NP, double* DV, double* ZV, double* RV, double* U, int* act,
+                                      unsigned char* is_act, int nwsr_max, int* nwsr_out)
+{
+    constexpr int LDZ = NZ + 1, LDL = NZ + 1;
+    int q = 0, nwsr = 0;
+    // J = L^-T
+    for (int c = 0; c < NZ; c++)
+        for (int i = NZ - 1; i >= 0; i--) {
+            double s = (i == c) ? 1.0 : 0.0;
+            for (int k = i + 1; k < NZ; k++) s -= LS[k * LDL + i] * JS[k * LDL + c];
+            JS[i * LDL + c] = s / LS[i * LDL + i];
+        }
+    for (int j = 0; j < 2 * NV; j++) is_act[j] = 0;
+    for (;;) {
+        int p = -1;
+        double sp = -kViolTol;
+        for (int j = 0; j < NV; j++) {
+            double xj = XP[j];
+            for (int c = 0; c < NZ; c++) xj += ZS[j * LDZ + c] * W[c];
+            if (LB[j] > -kQpInf && !is_act[2 * j]) { const double s = xj - LB[j]; if (s < sp) { sp = s; p = 2 * j; } }
+            if (UB[j] < kQpInf && !is_act[2 * j + 1]) { const double s = UB[j] - xj; if (s < sp) { sp = s; p = 2 * j + 1; } }
+        }
+        if (p < 0) break;
+        const int pv = p >> 1;
+        const double sgn = (p & 1) ? -1.0 : 1.0;
+        for (int c = 0; c < NZ; c++) NP[c] = sgn * ZS[pv * LDZ + c];
+        double up_ = 0.0;
+        bool added = false;
+        while (!added) {
+            for (int c = 0; c < NZ; c++) { double s = 0.0; for (int i = 0; i < NZ; i++) s += JS[i * LDL + c] * NP[i]; DV[c] = s; }
+            for (int i = 0; i < NZ; i++) { double s = 0.0; for (int c = q; c < NZ; c++) s += JS[i * LDL + c] * DV[c]; ZV[i] = s; }
+            for (int i = q - 1; i >= 0; i--) { double s = DV[i]; for (int k = i + 1; k < q; k++) s -= RS[i * LDL + k] * RV[k]; RV[i] = s / RS[i * LDL + i]; }
+            double zn = 0.0, dd = 0.0;
+            for (int i = 0; i < NZ; i++) zn += ZV[i] * NP[i];
+            for (int c = 0; c < NZ; c++) dd += DV[c] * DV[c];
+            const bool have_z = zn > 1e-12 * dd && zn > 0.0;
+            const double t2 = have_z ? -sp / zn : INFINITY;
+            double t1 = INFINITY; int l = -1;
+            for (int k = 0; k < q; k++) if (RV[k] > 0.0 && U[k] / RV[k] < t1) { t1 = U[k] / RV[k]; l = k; }
+            const double tt = t1 < t2 ? t1 : t2;
+            if (!(tt < INFINITY)) { *nwsr_out = nwsr; return WC_QP_INFEASIBLE; }
+            if (have_z) for (int i = 0; i < NZ; i++) W[i] += tt * ZV[i];
+            for (int k = 0; k < q; k++) U[k] -= tt * RV[k];
+            up_ += tt;
+            if (have_z && t2 <= t1) {
+                for (int j = NZ - 1; j > q; j--) {
+                    const double a0 = DV[j - 1], a1 = DV[j];
+                    const double hh = hypot(a0, a1);
+                    if (hh == 0.0) continue;
+                    const double cs = a0 / hh, sn = a1 / hh;
+                    DV[j - 1] = hh; DV[j] = 0.0;
+                    for (int i = 0; i < NZ; i++) {
+                        const double j0 = JS[i * LDL + j - 1], j1 = JS[i * LDL + j];
+                        JS[i * LDL + j - 1] = cs * j0 + sn * j1;
+                        JS[i * LDL + j] = -sn * j0 + cs * j1;
+                    }
+                }
+                for (int i = 0; i <= q; i++) RS[i * LDL + q] = DV[i];
+                act[q] = p; U[q] = up_; is_act[p] = 1; q++;
+                added = true;
+            } else {
+                is_act[act[l]] = 0;
+                for (int k = l; k < q - 1; k++) {
+                    act[k] = act[k + 1]; U[k] = U[k + 1];
+                    for (int i = 0; i <= k + 1; i++) RS[i * LDL + k] = RS[i * LDL + k + 1];
+                }
+                q--;
+                for (int k = l; k < q; k++) {
+                    const double a0 = RS[k * LDL + k], a1 = RS[(k + 1) * LDL + k];
+                    const double hh = hypot(a0, a1);
+                    if (hh == 0.0) continue;
+                    const double cs = a0 / hh, sn = a1 / hh;
+                    RS[k * LDL + k] = hh; RS[(k + 1) * LDL + k] = 0.0;
+                    for (int c = k + 1; c < q; c++) {
+                        const double r0 = RS[k * LDL + c], r1 = RS[(k + 1) * LDL + c];
+                        RS[k * LDL + c] = cs * r0 + sn * r1;
+                        RS[(k + 1) * LDL + c] = -sn * r0 + cs * r1;
+                    }
+                    for (int i = 0; i < NZ; i++) {
+                        const double j0 = JS[i * LDL + k], j1 = JS[i * LDL + k + 1];
+                        JS[i * LDL + k] = cs * j0 + sn * j1;
+                        JS[i * LDL + k + 1] = -sn * j0 + cs * j1;
+                    }
+                }
+                double xj = XP[pv];
+                for (int c = 0; c < NZ; c++) xj += ZS[pv * LDZ + c] * W[c];
+                sp = (p & 1) ? UB[pv] - xj : xj - LB[pv];
+            }
+            nwsr++;
+            if (nwsr > nwsr_max) { *nwsr_out = nwsr; return WC_QP_MAX_NWSR_REACHED; }
+        }
+    }
+    *nwsr_out = nwsr;
+    return WC_QP_SUCCESSFUL_RETURN;
+}
+
+template <int NJ, bool COMC>
+struct IkLayout {
+    static constexpr int NV = NJ + 6;
+    static constexpr int NC = COMC ? 15 : 12;
+    static constexpr int NZ = NV - NC;
+    static constexpr int LDA = 33;
+    static constexpr int LDZ = NZ + 1;
+    static constexpr int LDL = NZ + 1;
+    // region 1: kinematics scratch, later Z and the Cholesky factor
+    static constexpr int R1_KIN = WC_MAX_LINKS * 12 + WC_MAX_LINKS * 4;
+    static constexpr int R1_QP = 32 * LDZ + NZ * LDL;
+    static constexpr int R1 = R1_KIN > R1_QP ? R1_KIN : R1_QP;
+    static constexpr int O_WL = 0, O_MC = WC_MAX_LINKS * 12;
+    static constexpr int O_ZS = 0, O_LS = 32 * LDZ;
+    static constexpr int O_AS = R1;
+    static constexpr int O_JN = O_AS + 15 * LDA;
+    static constexpr int O_JC = O_JN + 3 * 32;
+    static constexpr int O_JS = O_JC + 3 * 32;
+    static constexpr int O_RS = O_JS + NZ * LDL;
+    static constexpr int O_XP = O_RS + NZ * LDL;
+    static constexpr int O_LB = O_XP + 32, O_UB = O_LB + 32, O_TS = O_UB + 32, O_LAM = O_TS + 32;
+    static constexpr int O_W = O_LAM + 32, O_HR = O_W + 32, O_NP = O_HR + 32, O_DV = O_NP + 32, O_ZV = O_DV + 32;
+    static constexpr int O_RV = O_ZV + 32, O_U = O_RV + 32, O_P = O_U + 32, O_WP = O_P + 3 * 32;
+    static constexpr int O_BV = O_WP + 3 * 32;  // equality right-hand side b[16]
+    static constexpr int O_VS = O_BV + 16;      // Householder vector broadcast, double-buffered 2 x 32
+    static constexpr int O_INT = O_VS + 64;     // act[32] ints + is_act[64] bytes = 24 doubles
+    static constexpr int TOTAL = ((O_INT + 24 + 15) / 16) * 16 + 8;
+};
+
+template <int NJ, bool COMC>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) ik_kernel(IkDev d, IkTickIO io, int mode)
+{
+    using LY = IkLayout<NJ, COMC>;
+    constexpr int NV = LY::NV, NC = LY::NC, NZ = LY::NZ, LDA = LY::LDA, LDZ = LY::LDZ, LDL = LY::LDL;
+    constexpr unsigned FULL = 0xffffffffu;
+    extern __shared__ double smem_all[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const long long inst = (long long)blockIdx.x * kWarpsPerBlock + warp;
+    if (inst >= d.B) return; // whole warp exits together
+    const int i = (int)inst;
+    const size_t B = (size_t)d.B;
+    double* sm = smem_all + (size_t)warp * LY::TOTAL;
+    double* WL = sm + LY::O_WL; double* MC = sm + LY::O_MC;
+    double* ZS = sm + LY::O_ZS; double* LS = sm + LY::O_LS;
+    double* AS = sm + LY::O_AS; double* JN = sm + LY::O_JN; double* JC = sm + LY::O_JC;
+    double* JS = sm + LY::O_JS; double* RS = sm + LY::O_RS;
+    double* XP = sm + LY::O_XP; double* LBs = sm + LY::O_LB; double* UBs = sm + LY::O_UB;
+    double* TS = sm + LY::O_TS; double* LAM = sm + LY::O_LAM;
+    double* Ws = sm + LY::O_W; double* HR = sm + LY::O_HR; double* NPs = sm + LY::O_NP; double* DVs = sm + LY::O_DV;
+    double* ZVs = sm + LY::O_ZV; double* RVs = sm + LY::O_RV; double* Us = sm + LY::O_U;
+    double* Ps = sm + LY::O_P; double* WPs = sm + LY::O_WP;
+    double* BV = sm + LY::O_BV; double* VS = sm + LY::O_VS;
+    int* acts = reinterpret_cast<int*>(sm + LY::O_INT);
+    unsigned char* is_act = reinterpret_cast<unsigned char*>(sm + LY::O_INT + 16);
+
+    const IkModelDev& M = *d.model;
+    const wc_ik_config& cfg = d.cfg;
+    const int j = lane;            // QP variable of this lane
+    const bool isvar = j < NV;
+    const bool isjoint = j >= 6 && j < NV;
+
+    // this lane's Jacobian columns and the replicated frame data
+    double colLf[6] = {0, 0, 0, 0, 0, 0}, colRf[6] = {0, 0, 0, 0, 0, 0}, colN[3] = {0, 0, 0}, colC[3] = {0, 0, 0};
+    double lfH[12], rfH[12], nR[9], com[3];
+
+    if (mode != IK_MODE_EXT_KIN) {
+        // ================================================================= K3: forward kinematics
+        const int left = io.left_is_fixed[i] ? 1 : 0;
+        const int L = M.n_links;
+        const int l = lane; // link of this lane (first pass), links >= 32 in a second pass
+        for (int base = 0; base < L; base += 32) {
+            const int lk = base + l;
+            if (lk < L) {
+                double R[9], p[3];
+#pragma unroll
+                for (int k = 0; k < 9; k++) R[k] = M.joint_R[lk][k];
+#pragma unroll
+                for (int k = 0; k < 3; k++) p[k] = M.joint_p[lk][k];
+                const int dj = M.dof[lk];
+                if (dj >= 0) {
+                    const double q = io.q_lin[(size_t)dj * B + i];
+                    double s, c;
+                    sincos(q, &s, &c);
+                    const double v = 1.0 - c, x = M.axis[lk][0], y = M.axis[lk][1], z = M.axis[lk][2];
+                    const double Rq[9] = {c + x * x * v, x * y * v - z * s, x * z * v + y * s,
+                                          y * x * v + z * s, c + y * y * v, y * z * v - x * s,
+                                          z * x * v - y * s, z * y * v + x * s, c + z * z * v};
+                    double Rn[9];
+                    mat3_mul(R, Rq, Rn);
+#pragma unroll
+                    for (int k = 0; k < 9; k++) R[k] = Rn[k];
+                }
+                // local transform parked in WL; composed level by level below
+#pragma unroll
+                for (int k = 0; k < 9; k++) WL[lk * 12 + k] = R[k];
+#pragma unroll
+                for (int k = 0; k < 3; k++) WL[lk * 12 + 9 + k] = p[k];
+            }
+        }
+        __syncwarp();
+        // root_H_link by tree depth (parent[l] < l, depth known on the host)
+        for (int dep = 1; dep <= M.max_depth; dep++) {
+            for (int base = 0; base < L; base += 32) {
+                const int lk = base + l;
+                if (lk < L && M.depth[lk] == dep) {
+                    const int pa = M.parent[lk];
+                    double Ro[9], po[3];
+                    xf_mul(WL + pa * 12, WL + pa * 12 + 9, WL + lk * 12, WL + lk * 12 + 9, Ro, po);
+#pragma unroll
+                    for (int k = 0; k < 9; k++) WL[lk * 12 + k] = Ro[k];
+#pragma unroll
+                    for (int k = 0; k < 3; k++) WL[lk * 12 + 9 + k] = po[k];
+                }
+            }
+            __syncwarp();
+        }
+        // link 0 holds its "joint" transform (identity for a proper root); world_H_root from the stance sole
+        const int bl = M.base_link[left];
+        double wR[9], wp[3];
+        {
+            const int fidx = left ? 0 : 1;
+            double Rs[9], ps[3];
+            xf_mul(WL + bl * 12, WL + bl * 12 + 9, M.frame_R[fidx], M.frame_p[fidx], Rs, ps); // root_H_sole
+            // inverse
+            double Ri[9], pi[3];
+#pragma unroll
+            for (int r = 0; r < 3; r++)
+#pragma unroll
+                for (int c = 0; c < 3; c++) Ri[3 * r + c] = Rs[3 * c + r];
+#pragma unroll
+            for (int r = 0; r < 3; r++) pi[r] = -(Ri[3 * r] * ps[0] + Ri[3 * r + 1] * ps[1] + Ri[3 * r + 2] * ps[2]);
+            double bR[9], bp[3];
+            bR[0] = io.base_H[0 * B + i]; bR[1] = io.base_H[1 * B + i]; bR[2] = io.base_H[2 * B + i]; bp[0] = io.base_H[3 * B + i];
+            bR[3] = io.base_H[4 * B + i]; bR[4] = io.base_H[5 * B + i]; bR[5] = io.base_H[6 * B + i]; bp[1] = io.base_H[7 * B + i];
+            bR[6] = io.base_H[8 * B + i]; bR[7] = io.base_H[9 * B + i]; bR[8] = io.base_H[10 * B + i]; bp[2] = io.base_H[11 * B + i];
+            xf_mul(bR, bp, Ri, pi, wR, wp);
+        }
+        __syncwarp();
+        for (int base = 0; base < L; base += 32) {
+            const int lk = base + l;
+            if (lk < L) {
+                double Ro[9], po[3];
+                xf_mul(wR, wp, WL + lk * 12, WL + lk * 12 + 9, Ro, po);
+#pragma unroll
+                for (int k = 0; k < 9; k++) WL[lk * 12 + k] = Ro[k];
+#pragma unroll
+                for (int k = 0; k < 3; k++) WL[lk * 12 + 9 + k] = po[k];
+                const double m = M.mass[lk];
+#pragma unroll
+                for (int r = 0; r < 3; r++)
+                    MC[lk * 4 + r] = m * (Ro[3 * r] * M.com[lk][0] + Ro[3 * r + 1] * M.com[lk][1] + Ro[3 * r + 2] * M.com[lk][2] + po[r]);
+            }
+        }
+        __syncwarp();
+        // task frames (replicated) and total first moment
+        {
+            double R[9], p[3];
+            xf_mul(WL + M.frame_link[0] * 12, WL + M.frame_link[0] * 12 + 9, M.frame_R[0], M.frame_p[0], R, p);
+            lfH[0] = R[0]; lfH[1] = R[1]; lfH[2] = R[2]; lfH[3] = p[0]; lfH[4] = R[3]; lfH[5] = R[4]; lfH[6] = R[5]; lfH[7] = p[1];
+            lfH[8] = R[6]; lfH[9] = R[7]; lfH[10] = R[8]; lfH[11] = p[2];
+            xf_mul(WL + M.frame_link[1] * 12, WL + M.frame_link[1] * 12 + 9, M.frame_R[1], M.frame_p[1], R, p);
+            rfH[0] = R[0]; rfH[1] = R[1]; rfH[2] = R[2]; rfH[3] = p[0]; rfH[4] = R[3]; rfH[5] = R[4]; rfH[6] = R[5]; rfH[7] = p[1];
+            rfH[8] = R[6]; rfH[9] = R[7]; rfH[10] = R[8]; rfH[11] = p[2];
+            mat3_mul(WL + M.frame_link[2] * 12, M.frame_R[2], nR);
+        }
+        double Mc[3] = {0, 0, 0};
+        for (int k = 0; k < L; k++) { Mc[0] += MC[k * 4]; Mc[1] += MC[k * 4 + 1]; Mc[2] += MC[k * 4 + 2]; }
+        const double Mtot = M.total_mass;
+#pragma unroll
+        for (int r = 0; r < 3; r++) com[r] = Mc[r] / Mtot;
+        const double pB[3] = {WL[bl * 12 + 9], WL[bl * 12 + 10], WL[bl * 12 + 11]};
+        const double pL[3] = {lfH[3], lfH[7], lfH[11]}, pR[3] = {rfH[3], rfH[7], rfH[11]};
+        // ---- Jacobian column of this lane (MIXED representation, WalkingForwardKinematics.cpp:31,436-454)
+        if (j < 3) {
+            colLf[j] = 1.0; colRf[j] = 1.0; colC[j] = 1.0;
+        } else if (j < 6) {
+            const int k = j - 3;
+            double e[3] = {0, 0, 0}; e[k] = 1.0;
+            double r[3], o[3];
+            r[0] = pL[0] - pB[0]; r[1] = pL[1] - pB[1]; r[2] = pL[2] - pB[2];
+            cross3(e, r, o); colLf[0] = o[0]; colLf[1] = o[1]; colLf[2] = o[2]; colLf[3 + k] = 1.0;
+            r[0] = pR[0] - pB[0]; r[1] = pR[1] - pB[1]; r[2] = pR[2] - pB[2];
+            cross3(e, r, o); colRf[0] = o[0]; colRf[1] = o[1]; colRf[2] = o[2]; colRf[3 + k] = 1.0;
+            colN[k] = 1.0;
+            r[0] = com[0] - pB[0]; r[1] = com[1] - pB[1]; r[2] = com[2] - pB[2];
+            cross3(e, r, o); colC[0] = o[0]; colC[1] = o[1]; colC[2] = o[2];
+        } else if (j < NV) {
+            const int dj = j - 6;
+            const int c = M.link_of_dof[dj];
+            const double* Rc = WL + c * 12;
+            const double o[3] = {WL[c * 12 + 9], WL[c * 12 + 10], WL[c * 12 + 11]};
+            double a[3];
+#pragma unroll
+            for (int r = 0; r < 3; r++) a[r] = Rc[3 * r] * M.axis[c][0] + Rc[3 * r + 1] * M.axis[c][1] + Rc[3 * r + 2] * M.axis[c][2];
+            double r3[3], lin[3];
+            const double sl = (double)M.s_frame[left][0][dj], sr = (double)M.s_frame[left][1][dj], sn = (double)M.s_frame[left][2][dj];
+            r3[0] = pL[0] - o[0]; r3[1] = pL[1] - o[1]; r3[2] = pL[2] - o[2];
+            cross3(a, r3, lin);
+#pragma unroll
+            for (int r = 0; r < 3; r++) { colLf[r] = sl * lin[r]; colLf[3 + r] = sl * a[r]; }
+            r3[0] = pR[0] - o[0]; r3[1] = pR[1] - o[1]; r3[2] = pR[2] - o[2];
+            cross3(a, r3, lin);
+#pragma unroll
+            for (int r = 0; r < 3; r++) { colRf[r] = sr * lin[r]; colRf[3 + r] = sr * a[r]; }
+#pragma unroll
+            for (int r = 0; r < 3; r++) colN[r] = sn * a[r];
+            // CoM: first moment of the sub-tree hanging from this joint (or of its complement when the
+            // base link sits inside that sub-tree)
+            double S[3] = {0, 0, 0};
+            const unsigned long long mask = M.sub_mask[c];
+            for (int k = 0; k < L; k++)
+                if ((mask >> k) & 1ull) { S[0] += MC[k * 4]; S[1] += MC[k * 4 + 1]; S[2] += MC[k * 4 + 2]; }
+            const double ms = M.sub_mass[c];
+            double mom[3];
+            if (!M.base_in_sub[left][dj]) {
+#pragma unroll
+                for (int r = 0; r < 3; r++) mom[r] = (S[r] - ms * o[r]) / Mtot;
+            } else {
+#pragma unroll
+                for (int r = 0; r < 3; r++) mom[r] = -((Mc[r] - S[r]) - (Mtot - ms) * o[r]) / Mtot;
+            }
+            cross3(a, mom, lin);
+#pragma unroll
+            for (int r = 0; r < 3; r++) colC[r] = lin[r];
+        }
+        __syncwarp();
+        if (mode == IK_MODE_FK_ONLY) {
+            if (lane < 12) {
+                if (io.o_lf_H) io.o_lf_H[(size_t)lane * B + i] = lfH[lane];
+                if (io.o_rf_H) io.o_rf_H[(size_t)lane * B + i] = rfH[lane];
+            }
+            if (lane < 9 && io.o_neck_R) io.o_neck_R[(size_t)lane * B + i] = nR[lane];
+            if (lane < 3 && io.o_com) io.o_com[(size_t)lane * B + i] = com[lane];
+            if (isvar) {
+#pragma unroll
+                for (int r = 0; r < 6; r++) {
+                    if (io.o_J_lf) io.o_J_lf[(size_t)(r * NV + j) * B + i] = colLf[r];
+                    if (io.o_J_rf) io.o_J_rf[(size_t)(r * NV + j) * B + i] = colRf[r];
+                }
+                if (io.o_J_neck) {
+                    // linear rows of the neck Jacobian are not used by the QP; emit them for the WalkingFK getter
+                    double lin[3] = {0, 0, 0};
+                    const double pN[3] = {0, 0, 0};
+                    (void)pN;
+                    // recompute: point = neck frame origin
+                    double Rn[9], pn[3];
+                    xf_mul(WL + M.frame_link[2] * 12, WL + M.frame_link[2] * 12 + 9, M.frame_R[2], M.frame_p[2], Rn, pn);
+                    if (j < 3) lin[j] = 1.0;
+                    else if (j < 6) {
+                        double e[3] = {0, 0, 0}; e[j - 3] = 1.0;
+                        const double r[3] = {pn[0] - pB[0], pn[1] - pB[1], pn[2] - pB[2]};
+                        cross3(e, r, lin);
+                    } else {
+                        const int c = M.link_of_dof[j - 6];
+                        const double r[3] = {pn[0] - WL[c * 12 + 9], pn[1] - WL[c * 12 + 10], pn[2] - WL[c * 12 + 11]};
+                        cross3(colN, r, lin); // colN already carries the path sign
+                    }
+#pragma unroll
+                    for (int r = 0; r < 3; r++) {
+                        io.o_J_neck[(size_t)(r * NV + j) * B + i] = lin[r];
+                        io.o_J_neck[(size_t)((3 + r) * NV + j) * B + i] = colN[r];
+                    }
+                }
+                if (io.o_J_com)
+#pragma unroll
+                    for (int r = 0; r < 3; r++) io.o_J_com[(size_t)(r * NV + j) * B + i] = colC[r];
+            }
+            return;
+        }
+    } else {
+        // caller-supplied kinematics (WalkingQPIK drop-in: set*Jacobian + setRobotState)
+#pragma unroll
+        for (int k = 0; k < 12; k++) { lfH[k] = io.lf_H[(size_t)k * B + i]; rfH[k] = io.rf_H[(size_t)k * B + i]; }
+#pragma unroll
+        for (int k = 0; k < 9; k++) nR[k] = io.neck_R[(size_t)k * B + i];
+        if (isvar) {
+#pragma unroll
+            for (int r = 0; r < 6; r++) {
+                colLf[r] = io.J_lf[(size_t)(r * NV + j) * B + i];
+                colRf[r] = io.J_rf[(size_t)(r * NV + j) * B + i];
+            }
+#pragma unroll
+            for (int r = 0; r < 3; r++) {
+                colN[r] = io.J_neck[(size_t)((3 + r) * NV + j) * B + i]; // setNeckJacobian keeps rows 3..5
+                colC[r] = io.J_com[(size_t)(r * NV + j) * B + i];
+            }
+        }
+        com[0] = com[1] = com[2] = 0.0;
+    }
+
+    // ===================================================================== K3b: QP data (no dense H)
+    const double kpos = d.kpos ? d.kpos[i] : cfg.k_pos_foot;
+    const double katt = d.katt ? d.katt[i] : cfg.k_att_foot;
+    { // equality right-hand side (setBounds, _qpOASES.cpp:216-282), gradient, bounds
+        double bvec[15];
+        double Hd[12], tw[6], R[9], Rd[9], e[3];
+#pragma unroll
+        for (int f = 0; f < 2; f++) {
+            const double* src = f == 0 ? io.lf_H_des : io.rf_H_des;
+            const double* tws = f == 0 ? io.lf_twist : io.rf_twist;
+            const double* Hc = f == 0 ? lfH : rfH;
+#pragma unroll
+            for (int k = 0; k < 12; k++) Hd[k] = src[(size_t)k * B + i];
+#pragma unroll
+            for (int k = 0; k < 6; k++) tw[k] = tws[(size_t)k * B + i];
+#pragma unroll
+            for (int r = 0; r < 3; r++)
+#pragma unroll
+                for (int c = 0; c < 3; c++) { R[3 * r + c] = Hc[4 * r + c]; Rd[3 * r + c] = Hd[4 * r + c]; }
+            rot_error(R, Rd, e);
+#pragma unroll
+            for (int r = 0; r < 3; r++) {
+                bvec[6 * f + r] = tw[r] - kpos * (Hc[4 * r + 3] - Hd[4 * r + 3]);
+                bvec[6 * f + 3 + r] = tw[3 + r] - katt * e[r];
+            }
+        }
+        double cv[3];
+#pragma unroll
+        for (int r = 0; r < 3; r++) cv[r] = io.com_vel_des[(size_t)r * B + i];
+        if (COMC) {
+#pragma unroll
+            for (int r = 0; r < 3; r++)
+                bvec[12 + r] = cv[r] - cfg.k_pos_com * (io.com_meas[(size_t)r * B + i] - io.com_pos_des[(size_t)r * B + i]);
+        } else {
+            bvec[12] = bvec[13] = bvec[14] = 0.0;
+        }
+        // gradient (setGradientVector, :155-182)
+        double Rdes[9], nd[9], en[3], We[3];
+#pragma unroll
+        for (int k = 0; k < 9; k++) nd[k] = io.neck_R_des[(size_t)k * B + i];
+        mat3_mul(nd, cfg.additional_rotation, Rdes); // setDesiredNeckOrientation (QPIK.cpp:143-146)
+        rot_error(nR, Rdes, en);
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+            We[r] = cfg.neck_weight[3 * r] * (-cfg.k_neck * en[0]) + cfg.neck_weight[3 * r + 1] * (-cfg.k_neck * en[1]) +
+                    cfg.neck_weight[3 * r + 2] * (-cfg.k_neck * en[2]);
+        double gj = -(colN[0] * We[0] + colN[1] * We[1] + colN[2] * We[2]);
+        double lam = 0.0;
+        if (isjoint) {
+            lam = cfg.joint_reg_weight[j - 6];
+            gj -= lam * (cfg.joint_reg_gain[j - 6] * (cfg.joint_reg_rad[j - 6] - io.q_meas[(size_t)(j - 6) * B + i]));
+        }
+        if (!COMC) {
+            double Wv[3];
+#pragma unroll
+            for (int r = 0; r < 3; r++) Wv[r] = cfg.com_weight[3 * r] * cv[0] + cfg.com_weight[3 * r + 1] * cv[1] + cfg.com_weight[3 * r + 2] * cv[2];
+            gj -= colC[0] * Wv[0] + colC[1] * Wv[1] + colC[2] * Wv[2];
+        }
+        TS[lane] = isvar ? gj : 0.0; // g parked in TS
+        if (lane < 15) {
+#pragma unroll
+            for (int k = 0; k < 15; k++) if (lane == k) BV[k] = bvec[k];
+        }
+        LAM[lane] = lam;
+        LBs[lane] = isjoint ? cfg.min_vel[j - 6] : -DBL_MAX; // setVelocityBounds (:23-51)
+        UBs[lane] = isjoint ? cfg.max_vel[j - 6] : DBL_MAX;
+    }
+    // constraint matrix rows to shared memory (setLinearConstraintMatrix, :184-214): A[r][j]
+#pragma unroll
+    for (int r = 0; r < 6; r++) { AS[r * LDA + lane] = isvar ? colLf[r] : 0.0; AS[(6 + r) * LDA + lane] = isvar ? colRf[r] : 0.0; }
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+        if (COMC) AS[(12 + r) * LDA + lane] = isvar ? colC[r] : 0.0;
+        JN[r * 32 + lane] = isvar ? colN[r] : 0.0;
+        JC[r * 32 + lane] = isvar ? colC[r] : 0.0;
+    }
+    __syncwarp();
+
+    // ===================================================================== K4: exact QP
+    // ---- Householder QR of A' with one column per lane: T = column `lane` of A' (lanes < NC),
+    //      G = column `lane` of Q' (starts as the identity); reflectors are broadcast by shuffles.
+    double T[NV], G[NV];
+#pragma unroll
+    for (int r = 0; r < NV; r++) {
+        T[r] = (lane < NC) ? AS[lane * LDA + r] : 0.0;
+        G[r] = (r == lane) ? 1.0 : 0.0;
+    }
+    double amax = 0.0;
+#pragma unroll
+    for (int r = 0; r < NV; r++) amax = fmax(amax, fabs(T[r]));
+    amax = warp_max(amax);
+    int status = WC_QP_SUCCESSFUL_RETURN;
+    bool rank_def = false;
+#pragma unroll
+    for (int k = 0; k < NC; k++) {
+        // owner lane k builds the reflector and publishes it (double-buffered) in shared memory
+        double* vs = VS + (k & 1) * 32;
+        if (lane == k) {
+            double sig = 0.0;
+#pragma unroll
+            for (int r = k; r < NV; r++) sig += T[r] * T[r];
+            const double nrm = sqrt(sig);
+            const double alpha = T[k] > 0 ? -nrm : nrm;
+            vs[k] = T[k] - alpha;
+#pragma unroll
+            for (int r = k + 1; r < NV; r++) vs[r] = T[r];
+            vs[29] = nrm;
+            vs[30] = 1.0 / (sig - T[k] * alpha);
+            T[k] = alpha;
+#pragma unroll
+            for (int r = k + 1; r < NV; r++) T[r] = 0.0;
+        }
+        __syncwarp();
+        const double nrm_b = vs[29], beta = vs[30];
+        if (nrm_b <= kRankTol * (amax > 1.0 ? amax : 1.0)) { rank_def = true; break; }
+        double tauT = 0.0, tauG = 0.0;
+#pragma unroll
+        for (int r = k; r < NV; r++) {
+            const double v = vs[r];
+            tauT += v * T[r];
+            tauG += v * G[r];
+        }
+        tauT *= beta; tauG *= beta;
+        const bool upd = lane > k && lane < NC;
+#pragma unroll
+        for (int r = k; r < NV; r++) {
+            const double v = vs[r];
+            if (upd) T[r] -= tauT * v;
+            G[r] -= tauG * v;
+        }
+    }
+    double nu = 0.0;
+    int nwsr = 0;
+    if (rank_def) {
+        status = WC_QP_INFEASIBLE; // linearly dependent equality rows
+    } else {
+        // ---- R' y = b   (lane c holds column c of R)
+        double s = (lane < NC) ? BV[lane] : 0.0;
+        double y[NC];
+#pragma unroll
+        for (int k = 0; k < NC; k++) {
+            const double cand = s / T[k];
+            y[k] = __shfl_sync(FULL, cand, k);
+            if (lane > k) s -= T[k] * y[k];
+        }
+        // particular solution and null-space basis row of this lane
+        double xp = 0.0;
+#pragma unroll
+        for (int k = 0; k < NC; k++) xp += G[k] * y[k];
+        double Zr[NZ];
+#pragma unroll
+        for (int c = 0; c < NZ; c++) Zr[c] = G[NC + c];
+        if (!isvar) { xp = 0.0;
+#pragma unroll
+            for (int c = 0; c < NZ; c++) Zr[c] = 0.0; }
+        // ---- t = H xp + g with H = Lambda + Jn' W Jn (+ Jc' Wc Jc)
+        double u3[3], wu[3];
+#pragma unroll
+        for (int r = 0; r < 3; r++) u3[r] = warp_sum(JN[r * 32 + lane] * xp);
+#pragma unroll
+        for (int r = 0; r < 3; r++) wu[r] = cfg.neck_weight[3 * r] * u3[0] + cfg.neck_weight[3 * r + 1] * u3[1] + cfg.neck_weight[3 * r + 2] * u3[2];
+        double tj = LAM[lane] * xp + JN[lane] * wu[0] + JN[32 + lane] * wu[1] + JN[64 + lane] * wu[2] + TS[lane];
+        if (!COMC) {
+            double uc[3], wc3[3];
+#pragma unroll
+            for (int r = 0; r < 3; r++) uc[r] = warp_sum(JC[r * 32 + lane] * xp);
+#pragma unroll
+            for (int r = 0; r < 3; r++) wc3[r] = cfg.com_weight[3 * r] * uc[0] + cfg.com_weight[3 * r + 1] * uc[1] + cfg.com_weight[3 * r + 2] * uc[2];
+            tj += JC[lane] * wc3[0] + JC[32 + lane] * wc3[1] + JC[64 + lane] * wc3[2];
+        }
+        __syncwarp(); // kinematics scratch (WL/MC) is dead: region 1 becomes ZS/LS
+#pragma unroll
+        for (int c = 0; c < NZ; c++) ZS[lane * LDZ + c] = Zr[c];
+        ZS[lane * LDZ + NZ] = 0.0;
+        XP[lane] = xp;
+        TS[lane] = isvar ? tj : 0.0;
+        __syncwarp();
+        // ---- reduced Hessian row `lane` (lanes < NZ): M = Z' Lambda Z + (Jn Z)' W (Jn Z) [+ CoM term]
+        double Mr[NZ];
+#pragma unroll
+        for (int b = 0; b < NZ; b++) Mr[b] = 0.0;
+        double hr = 0.0;
+        const int a = lane < NZ ? lane : 0;
+        {
+            double P[3] = {0, 0, 0}, PC[3] = {0, 0, 0};
+            for (int jj = 0; jj < NV; jj++) {
+                const double za = ZS[jj * LDZ + a];
+                const double zl = za * LAM[jj];
+#pragma unroll
+                for (int b = 0; b < NZ; b++) Mr[b] += zl * ZS[jj * LDZ + b];
+                hr += za * TS[jj];
+#pragma unroll
+                for (int r = 0; r < 3; r++) P[r] += JN[r * 32 + jj] * za;
+                if (!COMC) {
+#pragma unroll
+                    for (int r = 0; r < 3; r++) PC[r] += JC[r * 32 + jj] * za;
+                }
+            }
+            double WP[3];
+#pragma unroll
+            for (int r = 0; r < 3; r++) WP[r] = cfg.neck_weight[3 * r] * P[0] + cfg.neck_weight[3 * r + 1] * P[1] + cfg.neck_weight[3 * r + 2] * P[2];
+            if (lane < NZ) {
+#pragma unroll
+                for (int r = 0; r < 3; r++) { Ps[r * 32 + lane] = P[r]; WPs[r * 32 + lane] = WP[r]; }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int b = 0; b < NZ; b++)
+                Mr[b] += P[0] * WPs[b] + P[1] * WPs[32 + b] + P[2] * WPs[64 + b];
+            if (!COMC) {
+                __syncwarp();
+                double WC3[3];
+#pragma unroll
+                for (int r = 0; r < 3; r++) WC3[r] = cfg.com_weight[3 * r] * PC[0] + cfg.com_weight[3 * r + 1] * PC[1] + cfg.com_weight[3 * r + 2] * PC[2];
+                if (lane < NZ) {
+#pragma unroll
+                    for (int r = 0; r < 3; r++) WPs[r * 32 + lane] = WC3[r];
+                }
+                __syncwarp();
+#pragma unroll
+                for (int b = 0; b < NZ; b++)
+                    Mr[b] += PC[0] * WPs[b] + PC[1] * WPs[32 + b] + PC[2] * WPs[64 + b];
+            }
+        }
+        // ---- Cholesky M = L L' (row per lane, right-looking, pivots broadcast)
+        double mmax = (lane < NZ) ? 0.0 : 0.0;
+#pragma unroll
+        for (int b = 0; b < NZ; b++) if (lane == b) mmax = fabs(Mr[b]);
+        mmax = warp_max(lane < NZ ? mmax : 0.0);
+        bool not_pd = false;
+#pragma unroll
+        for (int jc = 0; jc < NZ; jc++) {
+            const double djj = __shfl_sync(FULL, Mr[jc], jc);
+            if (!(djj > 1e-13 * (mmax > 1.0 ? mmax : 1.0))) { not_pd = true; break; }
+            const double piv = sqrt(djj);
+            const double lij = (lane == jc) ? piv : Mr[jc] / piv;
+            if (lane >= jc) Mr[jc] = lij;
+#pragma unroll
+            for (int k = jc + 1; k < NZ; k++) {
+                const double lkj = __shfl_sync(FULL, Mr[jc], k);
+                if (lane >= k) Mr[k] -= lij * lkj;
+            }
+        }
+        if (not_pd) {
+            status = WC_QP_NOT_CONVEX;
+        } else {
+            // L to shared memory (needed transposed below and by the active-set path)
+            if (lane < NZ) {
+#pragma unroll
+                for (int b = 0; b < NZ; b++) LS[lane * LDL + b] = (b <= lane) ? Mr[b] : 0.0;
+            }
+            __syncwarp();
+            // w = -M^-1 hr
+            double acc = -hr;
+            double wv[NZ];
+#pragma unroll
+            for (int k = 0; k < NZ; k++) {
+                const double cand = acc / Mr[k];
+                const double sk = __shfl_sync(FULL, cand, k);
+                if (lane > k) acc -= Mr[k] * sk;
+                if (lane == k) acc = sk;
+            }
+#pragma unroll
+            for (int k = NZ - 1; k >= 0; k--) {
+                const double cand = acc / Mr[k];
+                wv[k] = __shfl_sync(FULL, cand, k);
+                if (lane < k) acc -= LS[k * LDL + (lane < NZ ? lane : 0)] * wv[k];
+            }
+            nu = xp;
+#pragma unroll
+            for (int c = 0; c < NZ; c++) nu += Zr[c] * wv[c];
+            // ---- velocity bounds: equality-constrained optimum feasible -> done (nWSR = 0)
+            const bool viol = isjoint && ((LBs[lane] > -kQpInf && nu < LBs[lane] - kViolTol) ||
+                                          (UBs[lane] < kQpInf && nu > UBs[lane] + kViolTol));
+            if (__any_sync(FULL, viol)) {
+#pragma unroll
+                for (int c = 0; c < NZ; c++) if (lane == c) Ws[c] = wv[c];
+                __syncwarp();
+                int st = 0, nw = 0;
+                if (lane == 0)
+                    st = gi_bounds<NV, NZ>(ZS, XP, LBs, UBs, LS, JS, RS, Ws, NPs, DVs, ZVs, RVs, Us, acts, is_act, cfg.nwsr, &nw);
+                st = __shfl_sync(FULL, st, 0);
+                nw = __shfl_sync(FULL, nw, 0);
+                __syncwarp();
+                status = st; nwsr = nw;
+                nu = xp;
+#pragma unroll
+                for (int c = 0; c < NZ; c++) nu += Zr[c] * Ws[c];
+            }
+        }
+    }
+    const bool ok = status == WC_QP_SUCCESSFUL_RETURN;
+    if (!ok) nu = 0.0;
+    if (!isvar) nu = 0.0;
+    // ---- outputs: getSolution (:341-362), get{Left,Right}FootError (:364-401)
+    if (isjoint && io.dq) io.dq[(size_t)(j - 6) * B + i] = nu;
+    if (io.lf_err || io.rf_err) {
+        double el[6], er[6];
+#pragma unroll
+        for (int r = 0; r < 6; r++) {
+            el[r] = BV[r] - warp_sum(AS[r * LDA + lane] * nu);
+            er[r] = BV[6 + r] - warp_sum(AS[(6 + r) * LDA + lane] * nu);
+        }
+#pragma unroll
+        for (int r = 0; r < 6; r++) {
+            if (lane == r && io.lf_err) io.lf_err[(size_t)r * B + i] = ok ? el[r] : 0.0;
+            if (lane == r && io.rf_err) io.rf_err[(size_t)r * B + i] = ok ? er[r] : 0.0;
+        }
+    }
+    if (lane == 0) {
+        if (io.status) io.status[i] = status;
+        if (io.nwsr) io.nwsr[i] = nwsr;
+    }
+}
+
+template <int NJ, bool COMC>
+cudaError_t launch_t(const IkDev& d, const IkTickIO& io, int mode, cudaStream_t s)
+{
+    using LY = IkLayout<NJ, COMC>;
+    const size_t smem = (size_t)LY::TOTAL * sizeof(double) * kWarpsPerBlock;
+    cudaError_t e = cudaFuncSetAttribute(ik_kernel<NJ, COMC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const int blocks = (d.B + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    ik_kernel<NJ, COMC><<<blocks, kWarpsPerBlock * 32, smem, s>>>(d, io, mode);
+    return cudaGetLastError();
+}
+
+} // namespace
+
+bool ik_supported(int n_dofs) { return n_dofs == 23; }
+
+cudaError_t launch_ik(const IkDev& d, const IkTickIO& io, int mode, cudaStream_t s)
+{
+    if (d.nJ != 23) return cudaErrorInvalidValue;
+    if (d.cfg.use_com_as_constraint) return launch_t<23, true>(d, io, mode, s);
+    return launch_t<23, false>(d, io, mode, s);
+}
+
+} // namespace wcb

@@ -1,0 +1,78 @@
+// ik_kernels.cuh — batched iCub floating-base FK/Jacobians + QP inverse kinematics for sm_100a.
+//
+// Replaces, per controller instance and per 10 ms tick,
+//   WalkingFK (iDynTree::KinDynComputations)   modules/Walking_module/src/WalkingForwardKinematics.cpp:217-276,411-454
+//   WalkingQPIK setters                        modules/Walking_module/src/WalkingQPInverseKinematics.cpp:121-256
+//   WalkingQPIK_qpOASES::{setHessianMatrix,setGradientVector,setLinearConstraintMatrix,setBounds,solve,
+//                         getSolution,getLeftFootError,getRightFootError}
+//                                              modules/Walking_module/src/WalkingQPInverseKinematics_qpOASES.cpp:135-401
+//   qpOASES::SQProblem::{init,hotstart}        (external)
+//
+// One warp per instance, lane j <-> QP variable j (6 base + nJ joints <= 32).  The Hessian
+// H = Lambda + Jn' Wn Jn (+ Jc' Wc Jc) is never formed: only its diagonal-plus-rank-3 action is used.
+// The equality-constrained QP is solved exactly by the null-space method (Householder QR of A' held
+// column-per-lane in registers, reflectors broadcast by shuffles; Cholesky of Z'HZ), and instances
+// whose velocity bounds are violated continue with the Goldfarb-Idnani dual active-set method in
+// the reduced space — the same exact algorithm as the CPU oracle's qpOASES stand-in.
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/wc_capi.h"
+
+namespace wcb {
+
+struct IkModelDev {
+    int n_links, n_dofs, max_depth, pad0;
+    int parent[WC_MAX_LINKS];
+    int dof[WC_MAX_LINKS];
+    int depth[WC_MAX_LINKS];
+    int link_of_dof[WC_MAX_DOFS];
+    double joint_R[WC_MAX_LINKS][9];
+    double joint_p[WC_MAX_LINKS][3];
+    double axis[WC_MAX_LINKS][3];
+    double mass[WC_MAX_LINKS];
+    double com[WC_MAX_LINKS][3];
+    double sub_mass[WC_MAX_LINKS];
+    unsigned long long sub_mask[WC_MAX_LINKS];
+    double total_mass;
+    int base_link[2];          // [left_is_fixed]
+    int frame_link[3];         // l_sole, r_sole, neck
+    int pad1;
+    double frame_R[3][9];
+    double frame_p[3][3];
+    // per base choice and dof: path signs of the three task frames, and "base inside the joint's subtree"
+    signed char s_frame[2][3][WC_MAX_DOFS];
+    signed char base_in_sub[2][WC_MAX_DOFS];
+};
+
+struct IkDev {
+    int B, nJ;
+    wc_ik_config cfg;
+    const IkModelDev* model; // device memory
+    const double* kpos;      // [B] per-instance gains (device) or nullptr
+    const double* katt;
+};
+
+enum { IK_MODE_TICK = 0, IK_MODE_FK_ONLY = 1, IK_MODE_EXT_KIN = 2 };
+
+struct IkTickIO {
+    // inputs
+    const double* q_meas; const double* q_lin; const double* base_H; const uint8_t* left_is_fixed;
+    const double* lf_H_des; const double* rf_H_des; const double* lf_twist; const double* rf_twist;
+    const double* com_pos_des; const double* com_vel_des; const double* com_meas; const double* neck_R_des;
+    // externally supplied kinematics (IK_MODE_EXT_KIN)
+    const double* lf_H; const double* rf_H; const double* neck_R;
+    const double* J_lf; const double* J_rf; const double* J_neck; const double* J_com;
+    // outputs
+    double* dq; double* lf_err; double* rf_err; int32_t* status; int32_t* nwsr;
+    // FK outputs (IK_MODE_FK_ONLY)
+    double* o_lf_H; double* o_rf_H; double* o_neck_R; double* o_com;
+    double* o_J_lf; double* o_J_rf; double* o_J_neck; double* o_J_com;
+};
+
+cudaError_t launch_ik(const IkDev& d, const IkTickIO& io, int mode, cudaStream_t s);
+bool ik_supported(int n_dofs);
+
+} // namespace wcb

@@ -1,0 +1,271 @@
+// wc_ik_api.cu — C ABI of the batched FK + QP-IK (include/wc_capi.h): model pre-processing,
+// handle management, kernel launches, pinned host staging.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/wc_capi.h"
+#include "ik_kernels.cuh"
+
+using namespace wcb;
+
+struct wc_ik {
+    IkDev d;
+    int device;
+    int64_t launches;
+    IkModelDev* model_dev;
+    double* kpos; double* katt;
+    void* pin_in; void* pin_out; void* dev_in; void* dev_out;
+    cudaStream_t host_stream;
+};
+
+namespace {
+
+bool anc_or_self(const wc_model* m, int anc, int link)
+{
+    while (link >= 0) { if (link == anc) return true; link = m->parent[link]; }
+    return false;
+}
+
+// host-side pre-processing of the kinematic tree (what iDynTree::Traversal caches for a base link)
+bool build_model(const wc_model* m, IkModelDev* o)
+{
+    std::memset(o, 0, sizeof(*o));
+    const int L = m->n_links;
+    if (L < 1 || L > WC_MAX_LINKS || m->n_dofs < 1 || m->n_dofs > WC_MAX_DOFS) return false;
+    o->n_links = L; o->n_dofs = m->n_dofs;
+    for (int d = 0; d < WC_MAX_DOFS; d++) o->link_of_dof[d] = -1;
+    double total = 0.0;
+    for (int i = 0; i < L; i++) {
+        if (i == 0 ? m->parent[i] != -1 : (m->parent[i] < 0 || m->parent[i] >= i)) return false;
+        o->parent[i] = m->parent[i];
+        o->dof[i] = m->dof[i];
+        if (m->dof[i] >= m->n_dofs) return false;
+        if (m->dof[i] >= 0) { if (o->link_of_dof[m->dof[i]] != -1) return false; o->link_of_dof[m->dof[i]] = i; }
+        o->depth[i] = i == 0 ? 0 : o->depth[m->parent[i]] + 1;
+        if (o->depth[i] > o->max_depth) o->max_depth = o->depth[i];
+        std::memcpy(o->joint_R[i], m->joint_R[i], sizeof(double) * 9);
+        std::memcpy(o->joint_p[i], m->joint_p[i], sizeof(double) * 3);
+        std::memcpy(o->axis[i], m->axis[i], sizeof(double) * 3);
+        std::memcpy(o->com[i], m->com[i], sizeof(double) * 3);
+        o->mass[i] = m->mass[i];
+        total += m->mass[i];
+    }
+    if (!(total > 0.0)) return false;
+    for (int d = 0; d < m->n_dofs; d++) if (o->link_of_dof[d] < 0) return false;
+    o->total_mass = total;
+    for (int c = 0; c < L; c++) {
+        unsigned long long mask = 0; double ms = 0.0;
+        for (int k = 0; k < L; k++) if (anc_or_self(m, c, k)) { mask |= 1ull << k; ms += m->mass[k]; }
+        o->sub_mask[c] = mask; o->sub_mass[c] = ms;
+    }
+    const int fl[3] = {m->l_sole_link, m->r_sole_link, m->neck_link};
+    for (int f = 0; f < 3; f++) if (fl[f] < 0 || fl[f] >= L) return false;
+    o->base_link[1] = m->l_sole_link; o->base_link[0] = m->r_sole_link;
+    for (int f = 0; f < 3; f++) o->frame_link[f] = fl[f];
+    std::memcpy(o->frame_R[0], m->l_sole_R, sizeof(double) * 9); std::memcpy(o->frame_p[0], m->l_sole_p, sizeof(double) * 3);
+    std::memcpy(o->frame_R[1], m->r_sole_R, sizeof(double) * 9); std::memcpy(o->frame_p[1], m->r_sole_p, sizeof(double) * 3);
+    std::memcpy(o->frame_R[2], m->neck_R, sizeof(double) * 9); std::memcpy(o->frame_p[2], m->neck_p, sizeof(double) * 3);
+    for (int left = 0; left < 2; left++) {
+        const int base = o->base_link[left];
+        for (int d = 0; d < m->n_dofs; d++) {
+            const int c = o->link_of_dof[d];
+            const bool on_b = anc_or_self(m, c, base);
+            o->base_in_sub[left][d] = on_b ? 1 : 0;
+            for (int f = 0; f < 3; f++) {
+                const bool on_f = anc_or_self(m, c, fl[f]);
+                o->s_frame[left][f][d] = (on_f == on_b) ? 0 : (on_f ? 1 : -1);
+            }
+        }
+    }
+    return true;
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+} // namespace
+
+extern "C" {
+
+wc_status wc_ik_create(const wc_ik_config* cfg, const wc_model* model, int32_t B, int32_t device, wc_ik** out)
+{
+    if (!cfg || !model || !out || B < 1) return WC_ERR_INVALID_ARG;
+    *out = nullptr;
+    if (cfg->n_dofs != model->n_dofs) return WC_ERR_INVALID_ARG;
+    if (!ik_supported(cfg->n_dofs)) return WC_ERR_UNSUPPORTED; // kernels are instantiated for the 23-DoF iCub set
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) return WC_ERR_NO_DEVICE;
+    if (device < 0 || device >= ndev) return WC_ERR_INVALID_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) return WC_ERR_CUDA;
+    IkModelDev hm;
+    if (!build_model(model, &hm)) return WC_ERR_INVALID_ARG;
+    wc_ik* h = new (std::nothrow) wc_ik();
+    if (!h) return WC_ERR_ALLOC;
+    std::memset(h, 0, sizeof(*h));
+    h->device = device;
+    h->d.B = B; h->d.nJ = cfg->n_dofs; h->d.cfg = *cfg;
+    if (cudaMalloc(&h->model_dev, sizeof(IkModelDev)) != cudaSuccess) { delete h; return WC_ERR_ALLOC; }
+    if (cudaMemcpy(h->model_dev, &hm, sizeof(IkModelDev), cudaMemcpyHostToDevice) != cudaSuccess) { wc_ik_destroy(h); return WC_ERR_CUDA; }
+    h->d.model = h->model_dev;
+    *out = h;
+    return WC_OK;
+}
+
+void wc_ik_destroy(wc_ik* h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->model_dev) cudaFree(h->model_dev);
+    if (h->kpos) cudaFree(h->kpos);
+    if (h->katt) cudaFree(h->katt);
+    if (h->pin_in) cudaFreeHost(h->pin_in);
+    if (h->pin_out) cudaFreeHost(h->pin_out);
+    if (h->dev_in) cudaFree(h->dev_in);
+    if (h->dev_out) cudaFree(h->dev_out);
+    if (h->host_stream) cudaStreamDestroy(h->host_stream);
+    delete h;
+}
+
+int32_t wc_ik_batch(const wc_ik* h) { return h ? h->d.B : 0; }
+int64_t wc_ik_launch_count(const wc_ik* h) { return h ? h->launches : 0; }
+
+wc_status wc_ik_set_gains_host(wc_ik* h, const double* k_pos_foot, const double* k_att_foot)
+{
+    if (!h || !k_pos_foot || !k_att_foot) return WC_ERR_INVALID_ARG;
+    cudaSetDevice(h->device);
+    const size_t bytes = (size_t)h->d.B * sizeof(double);
+    if (!h->kpos && cudaMalloc(&h->kpos, bytes) != cudaSuccess) return WC_ERR_ALLOC;
+    if (!h->katt && cudaMalloc(&h->katt, bytes) != cudaSuccess) return WC_ERR_ALLOC;
+    if (cudaMemcpy(h->kpos, k_pos_foot, bytes, cudaMemcpyHostToDevice) != cudaSuccess) return WC_ERR_CUDA;
+    if (cudaMemcpy(h->katt, k_att_foot, bytes, cudaMemcpyHostToDevice) != cudaSuccess) return WC_ERR_CUDA;
+    h->d.kpos = h->kpos; h->d.katt = h->katt;
+    return WC_OK;
+}
+
+static wc_status launch_checked(wc_ik* h, const IkTickIO& io, int mode, cudaStream_t s, const char* who)
+{
+    cudaError_t e = launch_ik(h->d, io, mode, s);
+    h->launches += 1;
+    if (e != cudaSuccess) {
+        std::fprintf(stderr, "[%s] CUDA error: %s\n", who, cudaGetErrorString(e));
+        return WC_ERR_CUDA;
+    }
+    return WC_OK;
+}
+
+wc_status wc_ik_tick_dev(wc_ik* h, const double* q_meas, const double* q_lin, const double* base_H,
+                         const uint8_t* left_is_fixed, const double* lf_H_des, const double* rf_H_des,
+                         const double* lf_twist, const double* rf_twist, const double* com_pos_des,
+                         const double* com_vel_des, const double* com_meas, const double* neck_R_des,
+                         double* dq, double* lf_err, double* rf_err, int32_t* qp_status, int32_t* nwsr, void* stream)
+{
+    if (!h || !q_meas || !q_lin || !base_H || !left_is_fixed || !lf_H_des || !rf_H_des || !lf_twist || !rf_twist ||
+        !com_pos_des || !com_vel_des || !com_meas || !neck_R_des)
+        return WC_ERR_INVALID_ARG;
+    if (cudaSetDevice(h->device) != cudaSuccess) return WC_ERR_CUDA;
+    IkTickIO io;
+    std::memset(&io, 0, sizeof(io));
+    io.q_meas = q_meas; io.q_lin = q_lin; io.base_H = base_H; io.left_is_fixed = left_is_fixed;
+    io.lf_H_des = lf_H_des; io.rf_H_des = rf_H_des; io.lf_twist = lf_twist; io.rf_twist = rf_twist;
+    io.com_pos_des = com_pos_des; io.com_vel_des = com_vel_des; io.com_meas = com_meas; io.neck_R_des = neck_R_des;
+    io.dq = dq; io.lf_err = lf_err; io.rf_err = rf_err; io.status = qp_status; io.nwsr = nwsr;
+    return launch_checked(h, io, IK_MODE_TICK, static_cast<cudaStream_t>(stream), "wc_ik_tick_dev");
+}
+
+wc_status wc_fk_dev(wc_ik* h, const double* q, const double* base_H, const uint8_t* left_is_fixed,
+                    double* lf_H, double* rf_H, double* neck_R, double* com,
+                    double* J_lf, double* J_rf, double* J_neck, double* J_com, void* stream)
+{
+    if (!h || !q || !base_H || !left_is_fixed) return WC_ERR_INVALID_ARG;
+    if (cudaSetDevice(h->device) != cudaSuccess) return WC_ERR_CUDA;
+    IkTickIO io;
+    std::memset(&io, 0, sizeof(io));
+    io.q_lin = q; io.base_H = base_H; io.left_is_fixed = left_is_fixed;
+    io.o_lf_H = lf_H; io.o_rf_H = rf_H; io.o_neck_R = neck_R; io.o_com = com;
+    io.o_J_lf = J_lf; io.o_J_rf = J_rf; io.o_J_neck = J_neck; io.o_J_com = J_com;
+    return launch_checked(h, io, IK_MODE_FK_ONLY, static_cast<cudaStream_t>(stream), "wc_fk_dev");
+}
+
+wc_status wc_ik_solve_with_jacobians_dev(wc_ik* h, const double* q_meas,
+                         const double* lf_H, const double* rf_H, const double* neck_R, const double* com_meas,
+                         const double* J_lf, const double* J_rf, const double* J_neck, const double* J_com,
+                         const double* lf_H_des, const double* rf_H_des, const double* lf_twist, const double* rf_twist,
+                         const double* com_pos_des, const double* com_vel_des, const double* neck_R_des,
+                         double* dq, double* lf_err, double* rf_err, int32_t* qp_status, int32_t* nwsr, void* stream)
+{
+    if (!h || !q_meas || !lf_H || !rf_H || !neck_R || !com_meas || !J_lf || !J_rf || !J_neck || !J_com || !lf_H_des ||
+        !rf_H_des || !lf_twist || !rf_twist || !com_pos_des || !com_vel_des || !neck_R_des)
+        return WC_ERR_INVALID_ARG;
+    if (cudaSetDevice(h->device) != cudaSuccess) return WC_ERR_CUDA;
+    IkTickIO io;
+    std::memset(&io, 0, sizeof(io));
+    io.q_meas = q_meas; io.lf_H = lf_H; io.rf_H = rf_H; io.neck_R = neck_R; io.com_meas = com_meas;
+    io.J_lf = J_lf; io.J_rf = J_rf; io.J_neck = J_neck; io.J_com = J_com;
+    io.lf_H_des = lf_H_des; io.rf_H_des = rf_H_des; io.lf_twist = lf_twist; io.rf_twist = rf_twist;
+    io.com_pos_des = com_pos_des; io.com_vel_des = com_vel_des; io.neck_R_des = neck_R_des;
+    io.dq = dq; io.lf_err = lf_err; io.rf_err = rf_err; io.status = qp_status; io.nwsr = nwsr;
+    return launch_checked(h, io, IK_MODE_EXT_KIN, static_cast<cudaStream_t>(stream), "wc_ik_solve_with_jacobians_dev");
+}
+
+wc_status wc_ik_tick_host(wc_ik* h, const double* q_meas, const double* q_lin, const double* base_H,
+                          const uint8_t* left_is_fixed, const double* lf_H_des, const double* rf_H_des,
+                          const double* lf_twist, const double* rf_twist, const double* com_pos_des,
+                          const double* com_vel_des, const double* com_meas, const double* neck_R_des,
+                          double* dq, double* lf_err, double* rf_err, int32_t* qp_status, int32_t* nwsr)
+{
+    if (!h || !q_meas || !q_lin || !base_H || !left_is_fixed || !lf_H_des || !rf_H_des || !lf_twist || !rf_twist ||
+        !com_pos_des || !com_vel_des || !com_meas || !neck_R_des)
+        return WC_ERR_INVALID_ARG;
+    if (cudaSetDevice(h->device) != cudaSuccess) return WC_ERR_CUDA;
+    const size_t B = (size_t)h->d.B, nJ = (size_t)h->d.nJ;
+    // rows of each packed double input, in order
+    const size_t rows[11] = {nJ, nJ, 12, 12, 12, 6, 6, 3, 3, 3, 9};
+    const double* src[11] = {q_meas, q_lin, base_H, lf_H_des, rf_H_des, lf_twist, rf_twist, com_pos_des, com_vel_des, com_meas, neck_R_des};
+    size_t off[12]; off[0] = 0;
+    for (int k = 0; k < 11; k++) off[k + 1] = off[k] + rows[k] * B * 8;
+    const size_t o_flag = off[11];
+    const size_t in_bytes = o_flag + align_up(B, 8);
+    const size_t p_dq = 0, p_le = p_dq + nJ * B * 8, p_re = p_le + 6 * B * 8, p_st = p_re + 6 * B * 8;
+    const size_t p_nw = p_st + align_up(B * 4, 8), out_bytes = p_nw + align_up(B * 4, 8);
+    if (!h->pin_in) {
+        if (cudaMallocHost(&h->pin_in, in_bytes) != cudaSuccess) return WC_ERR_ALLOC;
+        if (cudaMallocHost(&h->pin_out, out_bytes) != cudaSuccess) return WC_ERR_ALLOC;
+        if (cudaMalloc(&h->dev_in, in_bytes) != cudaSuccess) return WC_ERR_ALLOC;
+        if (cudaMalloc(&h->dev_out, out_bytes) != cudaSuccess) return WC_ERR_ALLOC;
+        if (cudaStreamCreateWithFlags(&h->host_stream, cudaStreamNonBlocking) != cudaSuccess) return WC_ERR_CUDA;
+    }
+    char* pi = static_cast<char*>(h->pin_in);
+    for (int k = 0; k < 11; k++) std::memcpy(pi + off[k], src[k], rows[k] * B * 8);
+    std::memcpy(pi + o_flag, left_is_fixed, B);
+    cudaStream_t s = h->host_stream;
+    if (cudaMemcpyAsync(h->dev_in, h->pin_in, in_bytes, cudaMemcpyHostToDevice, s) != cudaSuccess) return WC_ERR_CUDA;
+    const char* di = static_cast<const char*>(h->dev_in);
+    char* dout = static_cast<char*>(h->dev_out);
+    auto D = [&](int k) { return reinterpret_cast<const double*>(di + off[k]); };
+    wc_status rc = wc_ik_tick_dev(h, D(0), D(1), D(2), reinterpret_cast<const uint8_t*>(di + o_flag), D(3), D(4), D(5), D(6),
+                                  D(7), D(8), D(9), D(10),
+                                  reinterpret_cast<double*>(dout + p_dq), reinterpret_cast<double*>(dout + p_le),
+                                  reinterpret_cast<double*>(dout + p_re), reinterpret_cast<int32_t*>(dout + p_st),
+                                  reinterpret_cast<int32_t*>(dout + p_nw), s);
+    if (rc != WC_OK) return rc;
+    if (cudaMemcpyAsync(h->pin_out, h->dev_out, out_bytes, cudaMemcpyDeviceToHost, s) != cudaSuccess) return WC_ERR_CUDA;
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) {
+        std::fprintf(stderr, "[wc_ik_tick_host] CUDA error: %s\n", cudaGetErrorString(e));
+        return WC_ERR_CUDA;
+    }
+    const char* po = static_cast<const char*>(h->pin_out);
+    if (dq) std::memcpy(dq, po + p_dq, nJ * B * 8);
+    if (lf_err) std::memcpy(lf_err, po + p_le, 6 * B * 8);
+    if (rf_err) std::memcpy(rf_err, po + p_re, 6 * B * 8);
+    if (qp_status) std::memcpy(qp_status, po + p_st, B * 4);
+    if (nwsr) std::memcpy(nwsr, po + p_nw, B * 4);
+    return WC_OK;
+}
+
+} // extern "C"
