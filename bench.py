@@ -1,0 +1,415 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the batched MPC + QP-IK controller tick on B200.
+
+Metric (BASELINE.json): combined MPC+QP-IK controller ticks/sec at B=65536 iCub instances,
+plus the batch tick latency distribution (p50/p99).  One step = one full control tick
+(wc_mpc_tick + wc_ik_tick) of every instance of the batch on synthetic iCub walking inputs
+(walking-controllers_b200/synthetic.py).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+* `value`   device-resident inputs, CUDA-event timed, max over ranks (weak scaling: B per GPU fixed).
+* `e2e`     same ticks through the host-pointer C ABI (wc_*_tick_host): pinned host inputs -> H2D,
+            kernels, D2H of the results, inside the timed region.
+* `roofline` dominant kernel (the ADMM kernel) against the measured HBM peak — reported as the
+            contract asks, although the path is FP64-latency bound: the FP64 view is in
+            `fp64`.
+* `cpu_baseline` / `--impl reference`: the oracle restatement of the reference CPU path
+            (oracle/, the reference itself cannot be built here), one instance per thread.
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+B_PER_GPU = 65536
+HORIZON = 25
+IK_RING = 8            # distinct IK input sets cycled over the ticks (IK is stateless per tick)
+CPU_SAMPLE_B = 2048    # bounded CPU sample: instances x ticks
+CPU_SAMPLE_TICKS = 12
+
+
+def bytes_per_tick(N):
+    """algorithmic HBM bytes per instance-tick"""
+    return dict(mpc=128 * N + 464, ik=1540)
+
+
+def flops_per_tick(N, iters, refactors, wsc):
+    n, m, nnzA = 4 * N + 2, 2 * N + 10, 6 * N + 18
+    f_iter = 4 * nnzA + 21 * n + 12 * (n + m)
+    return iters * f_iter + refactors * 36 * n, 43500 + 3900 * wsc
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """samples nvidia-smi clocks / throttle reasons during the timed region"""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(",") for r in open(self.f.name) if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for k, nm in enumerate(names):
+                if len(r) > 5 + k and "Active" in r[5 + k] and "Not" not in r[5 + k]:
+                    reasons.add(nm)
+        if sm:
+            sm.sort()
+            out["sm_mhz"] = sm[len(sm) // 2]
+            out["sm_max_mhz"] = max(mx)
+        out["reasons"] = sorted(reasons)
+        out["samples"] = len(sm)
+        return out
+
+
+def pct(v, q):
+    v = sorted(v)
+    return v[min(len(v) - 1, int(round(q * (len(v) - 1))))]
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args, world, rank):
+    """--impl reference: the reference's CPU path (oracle restatement, all host threads) on a bounded
+    sample of the same workload.  Rank 0 only."""
+    if rank != 0:
+        return
+    import numpy as np
+    import torch
+    from oracle import oracle as O
+    syn = importlib.import_module("walking-controllers_b200.synthetic")
+    O.build()
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
+    B, N = CPU_SAMPLE_B, HORIZON
+    steps, warm = args.steps, args.warmup
+    T = steps + warm
+    g = syn.GaitBatch(B, T, N)
+    traj = g.trajectory().numpy()
+    model = O.model_icub_like(); icfg = O.ik_default_config()
+    qreg = torch.tensor(list(icfg.joint_reg_rad[:23]), dtype=torch.float64)
+
+    def fkb(ql, bH, lif):
+        o = O.fk_batch(model, ql.numpy(), bH.numpy(), lif.numpy(), jacobians=False)
+        return {k: torch.from_numpy(v) for k, v in o.items()}
+
+    ik_in = [{k: v.numpy() for k, v in syn.ik_inputs(B, 100 + r, qreg, fkb, perturb=0.5).items()} for r in range(2)]
+    mb = O.MpcBatch(O.mpc_default_config(N), B)
+    feet = [g.feet(t) for t in range(T)]
+    dcm = [g.measured_dcm(t).numpy() for t in range(T)]
+    times = []
+    for t in range(T):
+        f = feet[t]
+        a = (f["lf_H"].numpy(), f["rf_H"].numpy(), f["l_contact"].numpy(), f["r_contact"].numpy(), dcm[t],
+             np.ascontiguousarray(traj[2 * t: 2 * t + 2 * (N + 1)]))
+        t0 = time.perf_counter()
+        mb.tick(*a, threads=cores)
+        O.ik_batch_tick(icfg, model, ik_in[t % 2], threads=cores)
+        dt = time.perf_counter() - t0
+        if t >= warm:
+            times.append(dt)
+    tot = sum(times)
+    val = B * len(times) / tot
+    sample = f"{B} instances x {len(times)} ticks of the same synthetic workload (N={N}), one instance per thread"
+    line = {"impl": "reference", "metric": "controller_ticks_per_sec", "value": val, "unit": "ticks/s",
+            "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": tot / len(times) * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "full tick: DCM-MPC (N=25) + FK + QP-IK, iCub 23-DoF", "instances": B,
+                       "horizon": N, "note": "CPU restatement of the reference path (osqp-eigen/qpOASES/iDynTree "
+                                             "cannot be built offline)"},
+            "cpu_baseline": {"value": val, "unit": "ticks/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "ticks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_leg(N):
+    import numpy as np
+    import torch
+    from oracle import oracle as O
+    syn = importlib.import_module("walking-controllers_b200.synthetic")
+    O.build()
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
+    B, T = CPU_SAMPLE_B, CPU_SAMPLE_TICKS
+    g = syn.GaitBatch(B, T, N)
+    traj = g.trajectory().numpy()
+    model = O.model_icub_like(); icfg = O.ik_default_config()
+    qreg = torch.tensor(list(icfg.joint_reg_rad[:23]), dtype=torch.float64)
+
+    def fkb(ql, bH, lif):
+        o = O.fk_batch(model, ql.numpy(), bH.numpy(), lif.numpy(), jacobians=False)
+        return {k: torch.from_numpy(v) for k, v in o.items()}
+
+    ik_in = {k: v.numpy() for k, v in syn.ik_inputs(B, 100, qreg, fkb, perturb=0.5).items()}
+    mb = O.MpcBatch(O.mpc_default_config(N), B)
+    tot = 0.0
+    t_mpc = t_ik = 0.0
+    for t in range(T):
+        f = g.feet(t)
+        a = (f["lf_H"].numpy(), f["rf_H"].numpy(), f["l_contact"].numpy(), f["r_contact"].numpy(),
+             g.measured_dcm(t).numpy(), np.ascontiguousarray(traj[2 * t: 2 * t + 2 * (N + 1)]))
+        t0 = time.perf_counter()
+        mb.tick(*a, threads=cores)
+        t1 = time.perf_counter()
+        O.ik_batch_tick(icfg, model, ik_in, threads=cores)
+        t2 = time.perf_counter()
+        if t >= 2:
+            tot += t2 - t0; t_mpc += t1 - t0; t_ik += t2 - t1
+    n = T - 2
+    return {"value": B * n / tot, "unit": "ticks/s", "cores": cores, "kind": "port",
+            "sample": f"{B} instances x {n} ticks (after 2 warm-up) of the same workload, one instance per thread; "
+                      f"MPC {t_mpc / n * 1e3:.1f} ms + IK {t_ik / n * 1e3:.1f} ms per batch tick"}
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args, world, rank, local_rank):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    wc = importlib.import_module("walking-controllers_b200")
+    syn = importlib.import_module("walking-controllers_b200.synthetic")
+    wc.lib()  # fail loudly if the CUDA library is missing
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the product has no CPU fallback")
+    dev = torch.device(f"cuda:{local_rank}")
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, N = B_PER_GPU, HORIZON
+    steps, warm = args.steps, args.warmup
+    T = warm + steps
+
+    # ---------------- synthetic inputs, resident in HBM before the timed region
+    g = syn.GaitBatch(B, T, N, seed=0x5EED + rank, device=dev)
+    traj = g.trajectory()
+    mpc_in = []
+    for t in range(T):
+        f = g.feet(t)
+        mpc_in.append((f["lf_H"], f["rf_H"], f["l_contact"], f["r_contact"], g.measured_dcm(t)))
+    mcfg = wc.mpc_default_config(N)
+    icfg = wc.ik_default_config()
+    model = wc.model_icub_like()
+    ik = wc.IkBatch(icfg, model, B, device=local_rank)
+    qreg = torch.tensor(list(icfg.joint_reg_rad[:23]), dtype=torch.float64)
+
+    def fkb(ql, bH, lif):
+        return ik.fk(ql, bH, lif, jacobians=False)
+
+    ik_in = [syn.ik_inputs(B, 1000 * rank + r, qreg, fkb, device=dev, perturb=0.5) for r in range(IK_RING)]
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- arm 1: device-resident inputs
+    mpc = wc.MpcBatch(mcfg, B, device=local_rank)
+    mo = io_ = None
+    for t in range(warm):
+        a = mpc_in[t]
+        mo = mpc.tick(a[0], a[1], a[2], a[3], a[4], traj[2 * t: 2 * t + 2 * (N + 1)], out=mo)
+        io_ = ik.tick(ik_in[t % IK_RING], out=io_)
+    barrier()
+    mpc.enable_profiling(True); ik.enable_profiling(True)
+    l0 = mpc.launches + ik.launches
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    it_sum = torch.zeros((), dtype=torch.float64, device=dev)
+    it_max = torch.zeros((), dtype=torch.int32, device=dev)
+    new_sum = torch.zeros((), dtype=torch.float64, device=dev)
+    ws_sum = torch.zeros((), dtype=torch.float64, device=dev)
+    evs[0].record()
+    for k in range(steps):
+        t = warm + k
+        a = mpc_in[t]
+        mo = mpc.tick(a[0], a[1], a[2], a[3], a[4], traj[2 * t: 2 * t + 2 * (N + 1)], out=mo)
+        io_ = ik.tick(ik_in[t % IK_RING], out=io_)
+        evs[k + 1].record()
+    launches = mpc.launches + ik.launches - l0
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    step_ms = [evs[k].elapsed_time(evs[k + 1]) for k in range(steps)]
+    total_ms = evs[0].elapsed_time(evs[steps])
+    prep_ms, admm_ms, nt = mpc.kernel_times_ms()
+    ik_ms, nik = ik.kernel_times_ms()
+    mpc.enable_profiling(False); ik.enable_profiling(False)
+    # statistics of the last tick (outside the timed region)
+    it_mean = mo["iters"].double().mean().item(); it_max = int(mo["iters"].max().item())
+    solved = (mo["status"] == 1).double().mean().item()
+    new_frac = ((mo["flags"] & 16) != 0).double().mean().item()
+    ik_ok = (io_["status"] == 0).double().mean().item()
+    wsc_mean = io_["nwsr"].double().mean().item()
+    ws_frac = (io_["nwsr"] > 0).double().mean().item()
+
+    t_ms = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    total_ms_max = t_ms.item()
+
+    # ---------------- NCCL result collection (off the tick's critical path)
+    gather_ms = None
+    if world > 1:
+        res = torch.cat([mo["zmp"], io_["dq"]], 0).contiguous()
+        outbuf = [torch.empty_like(res) for _ in range(world)] if rank == 0 else None
+        stats = torch.tensor([solved, ik_ok, it_mean, wsc_mean], dtype=torch.float64, device=dev)
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        dist.gather(res, outbuf, dst=0)
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+        torch.cuda.synchronize(); gather_ms = (time.perf_counter() - t0) * 1e3
+        solved, ik_ok, it_mean, wsc_mean = (stats / world).tolist()
+
+    # ---------------- arm 2: end to end through the host-pointer C ABI (pinned host buffers)
+    mpc2 = wc.MpcBatch(mcfg, B, device=local_rank)
+    e2e_steps = min(steps, 20)
+    e2e_warm = min(warm, 5)
+    Te = e2e_steps + e2e_warm
+
+    def pin(x):
+        return x.cpu().pin_memory()
+
+    h_mpc = [tuple(pin(v) for v in mpc_in[t]) + (pin(traj[2 * t: 2 * t + 2 * (N + 1)]),) for t in range(Te)]
+    h_ik = [{k: pin(v) for k, v in ik_in[r].items()} for r in range(min(IK_RING, 4))]
+    h_mo = dict(zmp=torch.empty(2, B, dtype=torch.float64).pin_memory(), status=torch.empty(B, dtype=torch.int32).pin_memory(),
+                iters=torch.empty(B, dtype=torch.int32).pin_memory(), flags=torch.empty(B, dtype=torch.int32).pin_memory())
+    h_io = dict(dq=torch.empty(23, B, dtype=torch.float64).pin_memory(), lf_err=torch.empty(6, B, dtype=torch.float64).pin_memory(),
+                rf_err=torch.empty(6, B, dtype=torch.float64).pin_memory(), status=torch.empty(B, dtype=torch.int32).pin_memory(),
+                nwsr=torch.empty(B, dtype=torch.int32).pin_memory())
+    h2d = sum(v.numel() * v.element_size() for v in h_mpc[0]) + sum(v.numel() * v.element_size() for v in h_ik[0].values())
+    d2h = sum(v.numel() * v.element_size() for v in h_mo.values()) + sum(v.numel() * v.element_size() for v in h_io.values())
+    for t in range(e2e_warm):
+        a = h_mpc[t]
+        mpc2.tick_host(a[0], a[1], a[2], a[3], a[4], a[5], out=h_mo)
+        ik.tick_host(h_ik[t % len(h_ik)], out=h_io)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(e2e_steps):
+        t = e2e_warm + k
+        a = h_mpc[t]
+        mpc2.tick_host(a[0], a[1], a[2], a[3], a[4], a[5], out=h_mo)
+        ik.tick_host(h_ik[t % len(h_ik)], out=h_io)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    e = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e, op=dist.ReduceOp.MAX)
+    e2e_s = e.item()
+    barrier()
+
+    if rank == 0:
+        hbm_peak, peak_src = peaks()
+        fp64_peak = wc.measure_fp64_peak(local_rank)
+        bt = bytes_per_tick(N)
+        admm_avg_ms = admm_ms / max(nt, 1)
+        ik_avg_ms = ik_ms / max(nik, 1)
+        prep_avg_ms = prep_ms / max(nt, 1)
+        achieved = bt["mpc"] * B / (admm_avg_ms * 1e-3) * 1e-9
+        f_mpc, f_ik = flops_per_tick(N, it_mean, 0.0, wsc_mean)
+        value = world * B * steps / (total_ms_max * 1e-3)
+        line = {
+            "metric": "controller_ticks_per_sec", "value": value, "unit": "ticks/s", "n_gpus": world, "steps": steps,
+            "warmup": warm, "ms_per_step": total_ms_max / steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "full tick: DCM-MPC (horizon 25) + FK + QP-IK, iCub 23-DoF + floating base "
+                                   "(BASELINE configs[2])", "instances_per_gpu": B, "instances_total": world * B,
+                       "horizon": N, "mpc_lanes_per_instance": os.environ.get("WC_MPC_LANES", "auto"),
+                       "l2": "per-tick working set (solver state 6 KB x 65536 + inputs) exceeds the 126 MB L2; "
+                             "inputs change every tick"},
+            "tick_latency_ms": {"p50": pct(step_ms, 0.5), "p99": pct(step_ms, 0.99), "max": max(step_ms)},
+            "kernels_ms": {"mpc_prepare": prep_avg_ms, "mpc_admm": admm_avg_ms, "fk_qpik": ik_avg_ms},
+            "stats": {"osqp_solved_frac": solved, "osqp_iters_mean": it_mean, "osqp_iters_max_last_tick": it_max,
+                      "new_solver_frac": new_frac, "qpik_success_frac": ik_ok, "qpik_nwsr_mean": wsc_mean,
+                      "qpik_active_set_frac": ws_frac},
+            "roofline": {"bound": "hbm", "kernel": "mpc_admm_kernel", "achieved": achieved, "peak": hbm_peak,
+                         "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": bt["mpc"] * B,
+                         "note": "path is FP64-latency/issue bound, not HBM bound (DESIGN.md); see fp64"},
+            "fp64": {"peak_gflops_measured": fp64_peak,
+                     "mpc_admm_gflops": f_mpc * B / (admm_avg_ms * 1e-3) * 1e-9,
+                     "fk_qpik_gflops": f_ik * B / (ik_avg_ms * 1e-3) * 1e-9,
+                     "mpc_admm_frac": f_mpc * B / (admm_avg_ms * 1e-3) * 1e-9 / fp64_peak,
+                     "fk_qpik_frac": f_ik * B / (ik_avg_ms * 1e-3) * 1e-9 / fp64_peak,
+                     "flops_per_tick_model": {"mpc": f_mpc, "ik": f_ik}},
+            "e2e": {"value": world * B * e2e_steps / e2e_s, "unit": "ticks/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        if gather_ms is not None:
+            line["nccl_gather_ms"] = gather_ms
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline_leg(N)
+        print(json.dumps(line), flush=True)
+    mpc.close(); mpc2.close(); ik.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args, world, rank)
+        return
+    run_ours(args, world, rank, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -174,6 +174,12 @@ wc_status wc_mpc_debug_get_host(wc_mpc* h, double* primal, double* rho, int32_t*
 /* Number of kernels launched by this handle since creation (bench.py's gpu_launches). */
 int64_t wc_mpc_launch_count(const wc_mpc* h);
 
+/* Per-kernel device timing: when enabled, every wc_mpc_tick_* brackets K1 (problem build) and K2
+ * (ADMM) with CUDA events on the launch stream.  wc_mpc_kernel_times_ms synchronises, returns the
+ * accumulated milliseconds and tick count since the previous call and clears them. */
+wc_status wc_mpc_enable_profiling(wc_mpc* h, int32_t on);
+wc_status wc_mpc_kernel_times_ms(wc_mpc* h, double* prepare_ms, double* admm_ms, int64_t* ticks);
+
 /* ---------------------------------------------------------------------------------- */
 /* Kinematic model table (replaces the iDynTree::Model loaded from model.urdf,          */
 /* WalkingModule.cpp:104-119; the URDF is not part of the reference repository).        */
@@ -304,6 +310,13 @@ wc_status wc_ik_solve_with_jacobians_dev(wc_ik* h,
                          int32_t* qp_status, int32_t* nwsr, void* stream);
 
 int64_t wc_ik_launch_count(const wc_ik* h);
+wc_status wc_ik_enable_profiling(wc_ik* h, int32_t on);
+wc_status wc_ik_kernel_times_ms(wc_ik* h, double* ik_ms, int64_t* launches);
+
+/* Measured FP64 FMA throughput of the device (register-resident FMA chains, all SMs), in GFLOP/s:
+ * the denominator of the FP64 roofline fraction that bench.py reports next to the HBM one
+ * (MEASURED_PEAKS.json carries no FP64 entry). */
+wc_status wc_measure_fp64_peak(int32_t device, double* gflops);
 
 /* Library/ABI version string, e.g. "wc_b200 0.1 sm_100a". */
 const char* wc_version(void);

@@ -116,6 +116,10 @@ def lib():
     L.wc_mpc_tick_host.argtypes = [_VP] + [_VP] * 11; L.wc_mpc_tick_host.restype = i32
     L.wc_mpc_debug_get_host.argtypes = [_VP, _VP, _VP, _VP]; L.wc_mpc_debug_get_host.restype = i32
     L.wc_mpc_launch_count.argtypes = [_VP]; L.wc_mpc_launch_count.restype = i64
+    L.wc_mpc_enable_profiling.argtypes = [_VP, i32]; L.wc_mpc_enable_profiling.restype = i32
+    L.wc_mpc_kernel_times_ms.argtypes = [_VP, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i64)]
+    L.wc_mpc_kernel_times_ms.restype = i32
+    L.wc_measure_fp64_peak.argtypes = [i32, C.POINTER(C.c_double)]; L.wc_measure_fp64_peak.restype = i32
     if hasattr(L, "wc_ik_create"):
         L.wc_ik_create.argtypes = [C.POINTER(IkConfig), C.POINTER(Model), i32, i32, C.POINTER(_VP)]
         L.wc_ik_create.restype = i32
@@ -128,6 +132,9 @@ def lib():
         L.wc_ik_solve_with_jacobians_dev.argtypes = [_VP] + [_VP] * 21 + [_VP]
         L.wc_ik_solve_with_jacobians_dev.restype = i32
         L.wc_ik_launch_count.argtypes = [_VP]; L.wc_ik_launch_count.restype = i64
+        L.wc_ik_enable_profiling.argtypes = [_VP, i32]; L.wc_ik_enable_profiling.restype = i32
+        L.wc_ik_kernel_times_ms.argtypes = [_VP, C.POINTER(C.c_double), C.POINTER(i64)]
+        L.wc_ik_kernel_times_ms.restype = i32
     _LIB = L
     return L
 
@@ -231,6 +238,15 @@ class MpcBatch:
     def launches(self):
         return lib().wc_mpc_launch_count(self.h)
 
+    def enable_profiling(self, on=True):
+        _check(lib().wc_mpc_enable_profiling(self.h, 1 if on else 0), "wc_mpc_enable_profiling")
+
+    def kernel_times_ms(self):
+        """(prepare_ms, admm_ms, ticks) accumulated since the last call (device-synchronising)"""
+        a, b, n = C.c_double(), C.c_double(), C.c_int64()
+        _check(lib().wc_mpc_kernel_times_ms(self.h, C.byref(a), C.byref(b), C.byref(n)), "wc_mpc_kernel_times_ms")
+        return a.value, b.value, n.value
+
 
 IK_INPUT_KEYS = ("q_meas", "q_lin", "base_H", "left_is_fixed", "lf_H_des", "rf_H_des", "lf_twist", "rf_twist",
                  "com_pos_des", "com_vel_des", "com_meas", "neck_R_des")
@@ -326,3 +342,18 @@ class IkBatch:
     @property
     def launches(self):
         return lib().wc_ik_launch_count(self.h)
+
+    def enable_profiling(self, on=True):
+        _check(lib().wc_ik_enable_profiling(self.h, 1 if on else 0), "wc_ik_enable_profiling")
+
+    def kernel_times_ms(self):
+        a, n = C.c_double(), C.c_int64()
+        _check(lib().wc_ik_kernel_times_ms(self.h, C.byref(a), C.byref(n)), "wc_ik_kernel_times_ms")
+        return a.value, n.value
+
+
+def measure_fp64_peak(device=0):
+    """measured FP64 FMA throughput of the device in GFLOP/s"""
+    g = C.c_double()
+    _check(lib().wc_measure_fp64_peak(device, C.byref(g)), "wc_measure_fp64_peak")
+    return g.value

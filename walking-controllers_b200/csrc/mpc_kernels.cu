@@ -17,8 +17,9 @@ __device__ __forceinline__ double limit_scaling(double v)
 }
 
 // =====================================================================================
-// K1: per-instance problem build.  One thread per instance (the heavy branch, Ruiz
-// equilibration, only runs when the support phase changed).
+// K1: per-instance problem build.  One thread per instance: contact-pair change detection, convex
+// hull of the support polygon, gradient ring update.  (OSQP's setup-time Ruiz equilibration of a new
+// solver runs cooperatively at the head of K2, where the instance's data is staged in shared memory.)
 //   WalkingController::setConvexHullConstraint  (Controller.cpp:364-435)
 //   buildConvexHull -> iDynTree ConvexHullProjectionConstraint (external; restated)
 //   MPCSolver::MPCSolver / setGradient          (MPCSolver.cpp:16-52,183-266)
@@ -125,107 +126,6 @@ __global__ void __launch_bounds__(128) mpc_prepare_kernel(MpcDev d, MpcTickIO io
         d.grad[(size_t)(nR + slot) * B + i] = -Q[1] * io.ref[(size_t)(2 * N + 1) * B + i];
     }
 
-    if (!inited) {
-        // ---- osqp_setup: Ruiz equilibration of [[P, A'],[A, 0]] with cost normalisation.
-        // P and A are never formed: their scaled entries follow from D, E, c in closed form.
-        // D -> d.D, E -> d.Eeq / d.Eh in place; d.x / d.yeq / d.yh serve as scratch (zeroed below).
-        const int nh = d.nhull[i];
-        const double ad = fabs(d.a_dyn), bd = fabs(d.b_dyn);
-        double c = 1.0;
-        for (int j = 0; j < 2 * nA; j++) d.D[(size_t)j * B + i] = 1.0;
-        for (int j = 0; j < 2 * nR; j++) d.Eeq[(size_t)j * B + i] = 1.0;
-        for (int h = 0; h < kMaxHull; h++) d.Eh[(size_t)h * B + i] = 1.0;
-        const double up[2] = {d.uprev[i], d.uprev[B + i]};
-#define DX(a, k) d.D[(size_t)((a)*nA + cx(N, (k))) * B + i]
-#define DU(a, k) d.D[(size_t)((a)*nA + cu(N, (k))) * B + i]
-#define EE(a, k) d.Eeq[(size_t)((a)*nR + (k)) * B + i]
-#define EH(h) d.Eh[(size_t)(h)*B + i]
-#define TX(a, k) d.x[(size_t)((a)*nA + cx(N, (k))) * B + i]
-#define TU(a, k) d.x[(size_t)((a)*nA + cu(N, (k))) * B + i]
-#define TE(a, k) d.yeq[(size_t)((a)*nR + (k)) * B + i]
-#define TH(h) d.yh[(size_t)(h)*B + i]
-#define HA(h, a) d.hullA[(size_t)(2 * (h) + (a)) * B + i]
-        for (int it = 0; it < d.st.scaling; it++) {
-            for (int a = 0; a < 2; a++) {
-                for (int k = 0; k <= N; k++) {
-                    const double dx = DX(a, k);
-                    double nrm = fabs(c * Q[a] * dx * dx);
-                    nrm = fmax(nrm, EE(a, k) * dx);
-                    if (k < N) nrm = fmax(nrm, ad * EE(a, k + 1) * dx);
-                    TX(a, k) = 1.0 / sqrt(limit_scaling(nrm));
-                }
-                for (int k = 0; k < N; k++) {
-                    const double du = DU(a, k);
-                    const double s = (k < N - 1) ? 2.0 : 1.0;
-                    double nrm = fabs(c * s * R[a] * du * du);
-                    if (k >= 1) nrm = fmax(nrm, fabs(c * R[a] * du * DU(a, k - 1)));
-                    if (k < N - 1) nrm = fmax(nrm, fabs(c * R[a] * du * DU(a, k + 1)));
-                    nrm = fmax(nrm, bd * EE(a, k + 1) * du);
-                    if (k == 0)
-                        for (int h = 0; h < nh; h++) nrm = fmax(nrm, fabs(EH(h) * HA(h, a)) * du);
-                    TU(a, k) = 1.0 / sqrt(limit_scaling(nrm));
-                }
-                for (int k = 0; k <= N; k++) {
-                    double nrm = EE(a, k) * DX(a, k);
-                    if (k >= 1) {
-                        nrm = fmax(nrm, ad * EE(a, k) * DX(a, k - 1));
-                        nrm = fmax(nrm, bd * EE(a, k) * DU(a, k - 1));
-                    }
-                    TE(a, k) = 1.0 / sqrt(limit_scaling(nrm));
-                }
-            }
-            for (int h = 0; h < nh; h++) {
-                double nrm = fmax(fabs(EH(h) * HA(h, 0)) * DU(0, 0), fabs(EH(h) * HA(h, 1)) * DU(1, 0));
-                TH(h) = 1.0 / sqrt(limit_scaling(nrm));
-            }
-            for (int j = 0; j < 2 * nA; j++) d.D[(size_t)j * B + i] *= d.x[(size_t)j * B + i];
-            for (int j = 0; j < 2 * nR; j++) d.Eeq[(size_t)j * B + i] *= d.yeq[(size_t)j * B + i];
-            for (int h = 0; h < nh; h++) EH(h) *= TH(h);
-            // cost normalisation
-            double sum = 0.0, qn = 0.0;
-            for (int a = 0; a < 2; a++) {
-                for (int k = 0; k <= N; k++) {
-                    const double dx = DX(a, k);
-                    sum += fabs(c * Q[a] * dx * dx);
-                    const int slot = (head + k) % nR;
-                    qn = fmax(qn, fabs(c * dx * d.grad[(size_t)(a * nR + slot) * B + i]));
-                }
-                for (int k = 0; k < N; k++) {
-                    const double du = DU(a, k);
-                    const double s = (k < N - 1) ? 2.0 : 1.0;
-                    double nrm = fabs(c * s * R[a] * du * du);
-                    if (k >= 1) nrm = fmax(nrm, fabs(c * R[a] * du * DU(a, k - 1)));
-                    if (k < N - 1) nrm = fmax(nrm, fabs(c * R[a] * du * DU(a, k + 1)));
-                    sum += nrm;
-                }
-                qn = fmax(qn, fabs(c * DU(a, 0) * R[a] * up[a]));
-            }
-            double c_temp = sum / (double)(2 * nA);
-            qn = limit_scaling(qn);
-            c_temp = fmax(c_temp, qn);
-            c_temp = limit_scaling(c_temp);
-            c *= 1.0 / c_temp;
-        }
-#undef DX
-#undef DU
-#undef EE
-#undef EH
-#undef TX
-#undef TU
-#undef TE
-#undef TH
-#undef HA
-        d.cscale[i] = c;
-        double rho = d.st.rho;
-        rho = rho < kRhoMin ? kRhoMin : (rho > kRhoMax ? kRhoMax : rho);
-        d.rho[i] = rho;
-        // cold start (osqp_setup -> cold_start)
-        for (int j = 0; j < 2 * nA; j++) d.x[(size_t)j * B + i] = 0.0;
-        for (int j = 0; j < 2 * nR; j++) d.yeq[(size_t)j * B + i] = 0.0;
-        for (int h = 0; h < kMaxHull; h++) { d.yh[(size_t)h * B + i] = 0.0; d.zh[(size_t)h * B + i] = 0.0; }
-        d.z0[i] = 0.0; d.z0[B + i] = 0.0;
-        d.inited[i] = 1;
-    }
     d.tick_flags[i] = flags;
 }
 
@@ -390,31 +290,18 @@ __global__ void __launch_bounds__(128) mpc_admm_kernel(MpcDev d, MpcTickIO io, i
     const int nh = skip ? 0 : d.nhull[i];
     const double Q[2] = {d.Qd[i], d.Qd[B + i]};
     const double R[2] = {d.Rd[i], d.Rd[B + i]};
-    const double c = d.cscale[i];
-    const double cinv = 1.0 / c;
-    double rho = d.rho[i];
+    // a new MPCSolver (support phase changed) has no OSQP workspace yet: osqp_setup runs below
+    const bool setup = !skip && d.inited[i] == 0;
+    double c = setup ? 1.0 : d.cscale[i];
+    double rho = setup ? fmin(fmax(st.rho, kRhoMin), kRhoMax) : d.rho[i];
     const double up[2] = {d.uprev[i], d.uprev[B + i]};
     const int head = d.ring_head;
 
     // ------------------------------------------------------------------ stage in
     for (int j = gl; j < 2 * nA; j += G) {
-        s.X[j] = d.x[(size_t)j * B + i];
-        s.DD[j] = d.D[(size_t)j * B + i];
-    }
-    for (int j = gl; j < 2 * nR; j += G) {
-        s.YE[j] = d.yeq[(size_t)j * B + i];
-        s.EE[j] = d.Eeq[(size_t)j * B + i];
-        s.DYE[j] = 0.0;
-    }
-    for (int h = gl; h < kMaxHull; h += G) {
-        s.YH[h] = d.yh[(size_t)h * B + i];
-        s.ZH[h] = d.zh[(size_t)h * B + i];
-        s.EH[h] = d.Eh[(size_t)h * B + i];
-        s.DYH[h] = 0.0;
-    }
-    __syncwarp();
-    // scaled problem data: q (osqp_update_lin_cost), A coefficients, bounds (osqp_update_bounds)
-    for (int j = gl; j < 2 * nA; j += G) {
+        s.X[j] = setup ? 0.0 : d.x[(size_t)j * B + i];
+        s.DD[j] = setup ? 1.0 : d.D[(size_t)j * B + i];
+        // unscaled gradient (MPCSolver::setGradient): state block from the ring, input block G u_prev
         const int a = j / nA, jj = j - a * nA;
         double q;
         if ((jj & 1) == 0) {
@@ -422,10 +309,111 @@ __global__ void __launch_bounds__(128) mpc_admm_kernel(MpcDev d, MpcTickIO io, i
             q = d.grad[(size_t)(a * nR + (head + k) % nR) * B + i];
         } else {
             const int k = N - ((jj + 1) >> 1);
-            q = (k == 0) ? -(R[a] * up[a]) : 0.0; // G u_prev, G = -Theta' R~ e1 (MPCSolver.cpp:244-245)
+            q = (k == 0) ? -(R[a] * up[a]) : 0.0; // G = -Theta' R~ e1 (MPCSolver.cpp:244-245)
         }
-        s.QB[j] = (q * s.DD[j]) * c;
+        s.QB[j] = q;
     }
+    for (int j = gl; j < 2 * nR; j += G) {
+        s.YE[j] = setup ? 0.0 : d.yeq[(size_t)j * B + i];
+        s.EE[j] = setup ? 1.0 : d.Eeq[(size_t)j * B + i];
+        s.DYE[j] = 0.0;
+    }
+    for (int h = gl; h < kMaxHull; h += G) {
+        s.YH[h] = setup ? 0.0 : d.yh[(size_t)h * B + i];
+        s.ZH[h] = setup ? 0.0 : d.zh[(size_t)h * B + i];
+        s.EH[h] = setup ? 1.0 : d.Eh[(size_t)h * B + i];
+        s.DYH[h] = 0.0;
+        // raw hull rows parked in HX/HY until the scaled coefficients replace them
+        s.HX[h] = (h < nh) ? d.hullA[(size_t)(2 * h) * B + i] : 0.0;
+        s.HY[h] = (h < nh) ? d.hullA[(size_t)(2 * h + 1) * B + i] : 0.0;
+    }
+    __syncwarp();
+    if (setup) {
+        // ---- osqp_setup -> scale_data: Ruiz equilibration of [[P, A'],[A, 0]] with cost normalisation
+        // (OSQP scaling.c).  P and A are never formed: their scaled entries follow from D, E, c in
+        // closed form.  Group-uniform branch: only group-scope collectives / barriers inside.
+        const double ad = fabs(d.a_dyn), bd = fabs(d.b_dyn);
+        for (int it = 0; it < st.scaling; it++) {
+            for (int j = gl; j < 2 * nA; j += G) {
+                const int a = j / nA, jj = j - a * nA;
+                const double* Da = s.DD + a * nA; const double* Ea = s.EE + a * nR;
+                const double dj = Da[jj];
+                double nrm;
+                if ((jj & 1) == 0) {
+                    const int k = N - (jj >> 1);
+                    nrm = fabs(c * Q[a] * dj * dj);
+                    nrm = fmax(nrm, Ea[k] * dj);
+                    if (k < N) nrm = fmax(nrm, ad * Ea[k + 1] * dj);
+                } else {
+                    const int k = N - ((jj + 1) >> 1);
+                    const double sc = (k < N - 1) ? 2.0 : 1.0;
+                    nrm = fabs(c * sc * R[a] * dj * dj);
+                    if (k >= 1) nrm = fmax(nrm, fabs(c * R[a] * dj * Da[jj + 2]));
+                    if (k < N - 1) nrm = fmax(nrm, fabs(c * R[a] * dj * Da[jj - 2]));
+                    nrm = fmax(nrm, bd * Ea[k + 1] * dj);
+                    if (k == 0) {
+                        const double* Hc = (a == 0) ? s.HX : s.HY;
+                        for (int h = 0; h < nh; h++) nrm = fmax(nrm, fabs(s.EH[h] * Hc[h]) * dj);
+                    }
+                }
+                s.W[j] = 1.0 / sqrt(limit_scaling(nrm));
+            }
+            for (int j = gl; j < 2 * nR; j += G) {
+                const int a = j / nR, k = j - a * nR;
+                const double* Da = s.DD + a * nA;
+                double nrm = s.EE[j] * Da[cx(N, k)];
+                if (k >= 1) {
+                    nrm = fmax(nrm, ad * s.EE[j] * Da[cx(N, k - 1)]);
+                    nrm = fmax(nrm, bd * s.EE[j] * Da[cu(N, k - 1)]);
+                }
+                s.DYE[j] = 1.0 / sqrt(limit_scaling(nrm));
+            }
+            for (int h = gl; h < nh; h += G) {
+                const double nrm = fmax(fabs(s.EH[h] * s.HX[h]) * s.DD[cu(N, 0)], fabs(s.EH[h] * s.HY[h]) * s.DD[nA + cu(N, 0)]);
+                s.DYH[h] = 1.0 / sqrt(limit_scaling(nrm));
+            }
+            __syncwarp(gmask);
+            for (int j = gl; j < 2 * nA; j += G) s.DD[j] *= s.W[j];
+            for (int j = gl; j < 2 * nR; j += G) s.EE[j] *= s.DYE[j];
+            for (int h = gl; h < nh; h += G) s.EH[h] *= s.DYH[h];
+            __syncwarp(gmask);
+            // cost normalisation: c <- c / max(mean_j ||P_j||_inf, ||q||_inf)
+            double sum = 0.0, qn = 0.0;
+            for (int j = gl; j < 2 * nA; j += G) {
+                const int a = j / nA, jj = j - a * nA;
+                const double* Da = s.DD + a * nA;
+                const double dj = Da[jj];
+                double nrm;
+                if ((jj & 1) == 0) nrm = fabs(c * Q[a] * dj * dj);
+                else {
+                    const int k = N - ((jj + 1) >> 1);
+                    const double sc = (k < N - 1) ? 2.0 : 1.0;
+                    nrm = fabs(c * sc * R[a] * dj * dj);
+                    if (k >= 1) nrm = fmax(nrm, fabs(c * R[a] * dj * Da[jj + 2]));
+                    if (k < N - 1) nrm = fmax(nrm, fabs(c * R[a] * dj * Da[jj - 2]));
+                }
+                sum += nrm;
+                qn = fmax(qn, fabs(c * dj * s.QB[j]));
+            }
+            sum = group_sum<G>(sum, gmask);
+            qn = group_max<G>(qn, gmask);
+            double c_temp = sum / (double)(2 * nA);
+            c_temp = fmax(c_temp, limit_scaling(qn));
+            c_temp = limit_scaling(c_temp);
+            c *= 1.0 / c_temp;
+        }
+        for (int j = gl; j < 2 * nR; j += G) s.DYE[j] = 0.0;
+        for (int h = gl; h < kMaxHull; h += G) s.DYH[h] = 0.0;
+        // publish the scaling of the new solver
+        for (int j = gl; j < 2 * nA; j += G) d.D[(size_t)j * B + i] = s.DD[j];
+        for (int j = gl; j < 2 * nR; j += G) d.Eeq[(size_t)j * B + i] = s.EE[j];
+        for (int h = gl; h < kMaxHull; h += G) d.Eh[(size_t)h * B + i] = s.EH[h];
+        if (gl == 0) { d.cscale[i] = c; d.inited[i] = 1; }
+    }
+    __syncwarp();
+    const double cinv = 1.0 / c;
+    // scaled problem data: q (osqp_update_lin_cost), A coefficients, bounds (osqp_update_bounds)
+    for (int j = gl; j < 2 * nA; j += G) s.QB[j] = (s.QB[j] * s.DD[j]) * c;
     for (int j = gl; j < 2 * nR; j += G) {
         const int a = j / nR, k = j - a * nR;
         const double e = s.EE[j];
@@ -436,14 +424,14 @@ __global__ void __launch_bounds__(128) mpc_admm_kernel(MpcDev d, MpcTickIO io, i
     for (int h = gl; h < kMaxHull; h += G) {
         const bool on = h < nh;
         const double e = s.EH[h];
-        s.HX[h] = on ? e * d.hullA[(size_t)(2 * h) * B + i] * s.DD[0 * nA + cu(N, 0)] : 0.0;
-        s.HY[h] = on ? e * d.hullA[(size_t)(2 * h + 1) * B + i] * s.DD[1 * nA + cu(N, 0)] : 0.0;
+        s.HX[h] = on ? e * s.HX[h] * s.DD[0 * nA + cu(N, 0)] : 0.0;
+        s.HY[h] = on ? e * s.HY[h] * s.DD[1 * nA + cu(N, 0)] : 0.0;
         s.UH[h] = on ? e * d.hullb[(size_t)h * B + i] : 0.0;
         s.LH[h] = on ? e * (-infty) : 0.0;
     }
     // equality row 0: l = u = -dcm (MPCSolver.cpp:143-146), scaled by E
-    const double lb0[2] = {-io.dcm[i] * d.Eeq[(size_t)(0 * nR) * B + i], -io.dcm[B + i] * d.Eeq[(size_t)(1 * nR) * B + i]};
-    double z0prev[2] = {d.z0[i], d.z0[B + i]};
+    const double lb0[2] = {-io.dcm[i] * s.EE[0], -io.dcm[B + i] * s.EE[nR]};
+    double z0prev[2] = {setup ? 0.0 : d.z0[i], setup ? 0.0 : d.z0[B + i]};
     __syncwarp();
 
     // ------------------------------------------------------------------ factorisation

@@ -22,6 +22,9 @@ struct wc_ik {
     double* kpos; double* katt;
     void* pin_in; void* pin_out; void* dev_in; void* dev_out;
     cudaStream_t host_stream;
+    int profiling;
+    std::vector<cudaEvent_t> ev; // pairs
+    double ms_acc; int64_t timed;
 };
 
 namespace {
@@ -106,7 +109,10 @@ wc_status wc_ik_create(const wc_ik_config* cfg, const wc_model* model, int32_t B
     if (!build_model(model, &hm)) return WC_ERR_INVALID_ARG;
     wc_ik* h = new (std::nothrow) wc_ik();
     if (!h) return WC_ERR_ALLOC;
-    std::memset(h, 0, sizeof(*h));
+    h->launches = 0; h->model_dev = nullptr; h->kpos = h->katt = nullptr;
+    h->pin_in = h->pin_out = h->dev_in = h->dev_out = nullptr; h->host_stream = nullptr;
+    h->profiling = 0; h->ms_acc = 0; h->timed = 0;
+    std::memset(&h->d, 0, sizeof(h->d));
     h->device = device;
     h->d.B = B; h->d.nJ = cfg->n_dofs; h->d.cfg = *cfg;
     if (cudaMalloc(&h->model_dev, sizeof(IkModelDev)) != cudaSuccess) { delete h; return WC_ERR_ALLOC; }
@@ -128,6 +134,7 @@ void wc_ik_destroy(wc_ik* h)
     if (h->dev_in) cudaFree(h->dev_in);
     if (h->dev_out) cudaFree(h->dev_out);
     if (h->host_stream) cudaStreamDestroy(h->host_stream);
+    for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
     delete h;
 }
 
@@ -149,7 +156,10 @@ wc_status wc_ik_set_gains_host(wc_ik* h, const double* k_pos_foot, const double*
 
 static wc_status launch_checked(wc_ik* h, const IkTickIO& io, int mode, cudaStream_t s, const char* who)
 {
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (h->profiling) { cudaEventCreate(&e0); cudaEventCreate(&e1); h->ev.push_back(e0); h->ev.push_back(e1); cudaEventRecord(e0, s); }
     cudaError_t e = launch_ik(h->d, io, mode, s);
+    if (h->profiling) cudaEventRecord(e1, s);
     h->launches += 1;
     if (e != cudaSuccess) {
         std::fprintf(stderr, "[%s] CUDA error: %s\n", who, cudaGetErrorString(e));
@@ -232,18 +242,17 @@ wc_status wc_ik_tick_host(wc_ik* h, const double* q_meas, const double* q_lin, c
     const size_t in_bytes = o_flag + align_up(B, 8);
     const size_t p_dq = 0, p_le = p_dq + nJ * B * 8, p_re = p_le + 6 * B * 8, p_st = p_re + 6 * B * 8;
     const size_t p_nw = p_st + align_up(B * 4, 8), out_bytes = p_nw + align_up(B * 4, 8);
-    if (!h->pin_in) {
-        if (cudaMallocHost(&h->pin_in, in_bytes) != cudaSuccess) return WC_ERR_ALLOC;
-        if (cudaMallocHost(&h->pin_out, out_bytes) != cudaSuccess) return WC_ERR_ALLOC;
+    if (!h->dev_in) {
         if (cudaMalloc(&h->dev_in, in_bytes) != cudaSuccess) return WC_ERR_ALLOC;
         if (cudaMalloc(&h->dev_out, out_bytes) != cudaSuccess) return WC_ERR_ALLOC;
         if (cudaStreamCreateWithFlags(&h->host_stream, cudaStreamNonBlocking) != cudaSuccess) return WC_ERR_CUDA;
     }
-    char* pi = static_cast<char*>(h->pin_in);
-    for (int k = 0; k < 11; k++) std::memcpy(pi + off[k], src[k], rows[k] * B * 8);
-    std::memcpy(pi + o_flag, left_is_fixed, B);
+    // direct copies from / to the caller's (ideally pinned) buffers
     cudaStream_t s = h->host_stream;
-    if (cudaMemcpyAsync(h->dev_in, h->pin_in, in_bytes, cudaMemcpyHostToDevice, s) != cudaSuccess) return WC_ERR_CUDA;
+    char* dbase = static_cast<char*>(h->dev_in);
+    for (int k = 0; k < 11; k++)
+        if (cudaMemcpyAsync(dbase + off[k], src[k], rows[k] * B * 8, cudaMemcpyHostToDevice, s) != cudaSuccess) return WC_ERR_CUDA;
+    if (cudaMemcpyAsync(dbase + o_flag, left_is_fixed, B, cudaMemcpyHostToDevice, s) != cudaSuccess) return WC_ERR_CUDA;
     const char* di = static_cast<const char*>(h->dev_in);
     char* dout = static_cast<char*>(h->dev_out);
     auto D = [&](int k) { return reinterpret_cast<const double*>(di + off[k]); };
@@ -253,18 +262,41 @@ wc_status wc_ik_tick_host(wc_ik* h, const double* q_meas, const double* q_lin, c
                                   reinterpret_cast<double*>(dout + p_re), reinterpret_cast<int32_t*>(dout + p_st),
                                   reinterpret_cast<int32_t*>(dout + p_nw), s);
     if (rc != WC_OK) return rc;
-    if (cudaMemcpyAsync(h->pin_out, h->dev_out, out_bytes, cudaMemcpyDeviceToHost, s) != cudaSuccess) return WC_ERR_CUDA;
-    cudaError_t e = cudaStreamSynchronize(s);
+    cudaError_t e = cudaSuccess;
+#define D2H(dst, off_, bytes) do { if ((dst) && e == cudaSuccess) e = cudaMemcpyAsync((dst), dout + (off_), (bytes), cudaMemcpyDeviceToHost, s); } while (0)
+    D2H(dq, p_dq, nJ * B * 8); D2H(lf_err, p_le, 6 * B * 8); D2H(rf_err, p_re, 6 * B * 8);
+    D2H(qp_status, p_st, B * 4); D2H(nwsr, p_nw, B * 4);
+#undef D2H
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
     if (e != cudaSuccess) {
         std::fprintf(stderr, "[wc_ik_tick_host] CUDA error: %s\n", cudaGetErrorString(e));
         return WC_ERR_CUDA;
     }
-    const char* po = static_cast<const char*>(h->pin_out);
-    if (dq) std::memcpy(dq, po + p_dq, nJ * B * 8);
-    if (lf_err) std::memcpy(lf_err, po + p_le, 6 * B * 8);
-    if (rf_err) std::memcpy(rf_err, po + p_re, 6 * B * 8);
-    if (qp_status) std::memcpy(qp_status, po + p_st, B * 4);
-    if (nwsr) std::memcpy(nwsr, po + p_nw, B * 4);
+    return WC_OK;
+}
+
+wc_status wc_ik_enable_profiling(wc_ik* h, int32_t on)
+{
+    if (!h) return WC_ERR_INVALID_ARG;
+    h->profiling = on ? 1 : 0;
+    return WC_OK;
+}
+
+wc_status wc_ik_kernel_times_ms(wc_ik* h, double* ik_ms, int64_t* launches)
+{
+    if (!h) return WC_ERR_INVALID_ARG;
+    if (cudaSetDevice(h->device) != cudaSuccess) return WC_ERR_CUDA;
+    if (cudaDeviceSynchronize() != cudaSuccess) return WC_ERR_CUDA;
+    for (size_t k = 0; k + 1 < h->ev.size(); k += 2) {
+        float a = 0;
+        cudaEventElapsedTime(&a, h->ev[k], h->ev[k + 1]);
+        h->ms_acc += a; h->timed += 1;
+    }
+    for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
+    h->ev.clear();
+    if (ik_ms) *ik_ms = h->ms_acc;
+    if (launches) *launches = h->timed;
+    h->ms_acc = 0; h->timed = 0;
     return WC_OK;
 }
 

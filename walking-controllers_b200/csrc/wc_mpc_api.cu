@@ -26,6 +26,11 @@ struct wc_mpc {
     void* pin_in; void* pin_out; void* dev_in; void* dev_out;
     size_t in_bytes, out_bytes;
     cudaStream_t host_stream;
+    // optional per-kernel timing (wc_mpc_enable_profiling): events recorded on the launch stream
+    int profiling;
+    std::vector<cudaEvent_t> ev; // triples (start, after K1, after K2)
+    double prep_ms_acc, admm_ms_acc;
+    int64_t timed_ticks;
 };
 
 namespace {
@@ -77,6 +82,7 @@ wc_status wc_mpc_create(const wc_mpc_config* cfg, int32_t B, int32_t device, wc_
     h->tick = 0;
     h->pin_in = h->pin_out = h->dev_in = h->dev_out = nullptr;
     h->host_stream = nullptr;
+    h->profiling = 0; h->prep_ms_acc = 0; h->admm_ms_acc = 0; h->timed_ticks = 0;
     MpcDev& d = h->d;
     std::memset(&d, 0, sizeof(d));
     d.B = B;
@@ -130,7 +136,7 @@ wc_status wc_mpc_create(const wc_mpc_config* cfg, int32_t B, int32_t device, wc_
 #undef TRY
     // lanes per instance for the ADMM kernel: more lanes for longer horizons (more parallel
     // vector work per sequential sweep).  WC_MPC_LANES overrides (tuning / tests).
-    int lanes = d.N <= 16 ? 4 : (d.N <= 64 ? 8 : (d.N <= 128 ? 16 : 32));
+    int lanes = d.N <= 8 ? 8 : (d.N <= 128 ? 16 : 32);
     lanes = env_int("WC_MPC_LANES", lanes);
     if (!(lanes == 2 || lanes == 4 || lanes == 8 || lanes == 16 || lanes == 32)) lanes = 8;
     // the per-instance working set must fit in one CTA's shared memory
@@ -153,6 +159,7 @@ void wc_mpc_destroy(wc_mpc* h)
     if (h->dev_in) cudaFree(h->dev_in);
     if (h->dev_out) cudaFree(h->dev_out);
     if (h->host_stream) cudaStreamDestroy(h->host_stream);
+    for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
     delete h;
 }
 
@@ -198,9 +205,16 @@ wc_status wc_mpc_tick_dev(wc_mpc* h, const double* lf_H, const double* rf_H,
     // gradient ring: stage k of this tick lives in slot (head + k) mod (N+1); advancing the head by
     // one per tick is MPCSolver::setGradient's block shift (MPCSolver.cpp:216-221)
     h->d.ring_head = (int)(h->tick % (int64_t)(h->d.N + 1));
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    if (h->profiling) {
+        for (int k = 0; k < 3; k++) { cudaEventCreate(&ev[k]); h->ev.push_back(ev[k]); }
+        cudaEventRecord(ev[0], s);
+    }
     launch_mpc_prepare(h->d, io, s);
     cudaError_t e = cudaGetLastError();
+    if (h->profiling) cudaEventRecord(ev[1], s);
     if (e == cudaSuccess) e = launch_mpc_admm(h->d, io, h->lanes, s);
+    if (h->profiling) cudaEventRecord(ev[2], s);
     h->launches += 2;
     h->tick += 1;
     if (e != cudaSuccess) {
@@ -225,24 +239,24 @@ wc_status wc_mpc_tick_host(wc_mpc* h, const double* lf_H, const double* rf_H,
     const size_t in_bytes = o_rs + align_up(B, 8);
     const size_t p_zmp = 0, p_st = p_zmp + 2 * B * 8, p_it = p_st + align_up(B * 4, 8), p_fl = p_it + align_up(B * 4, 8);
     const size_t out_bytes = p_fl + align_up(B * 4, 8);
-    if (!h->pin_in) {
-        if (cudaMallocHost(&h->pin_in, in_bytes) != cudaSuccess) return WC_ERR_ALLOC;
-        if (cudaMallocHost(&h->pin_out, out_bytes) != cudaSuccess) return WC_ERR_ALLOC;
+    if (!h->dev_in) {
         if (cudaMalloc(&h->dev_in, in_bytes) != cudaSuccess) return WC_ERR_ALLOC;
         if (cudaMalloc(&h->dev_out, out_bytes) != cudaSuccess) return WC_ERR_ALLOC;
         if (cudaStreamCreateWithFlags(&h->host_stream, cudaStreamNonBlocking) != cudaSuccess) return WC_ERR_CUDA;
         h->in_bytes = in_bytes; h->out_bytes = out_bytes;
     }
-    char* pi = static_cast<char*>(h->pin_in);
-    std::memcpy(pi + o_lf, lf_H, 12 * B * 8);
-    std::memcpy(pi + o_rf, rf_H, 12 * B * 8);
-    std::memcpy(pi + o_dcm, dcm_meas, 2 * B * 8);
-    std::memcpy(pi + o_ref, ref, (size_t)2 * (N + 1) * B * 8);
-    std::memcpy(pi + o_lc, l_contact, B);
-    std::memcpy(pi + o_rc, r_contact, B);
-    if (reset) std::memcpy(pi + o_rs, reset, B); else std::memset(pi + o_rs, 0, B);
+    // copies go straight from / to the caller's buffers: pinned buffers (cudaHostAlloc / torch
+    // pin_memory) make them true async DMA transfers, pageable ones are staged by the driver
     cudaStream_t s = h->host_stream;
-    if (cudaMemcpyAsync(h->dev_in, h->pin_in, in_bytes, cudaMemcpyHostToDevice, s) != cudaSuccess) return WC_ERR_CUDA;
+    char* dbase = static_cast<char*>(h->dev_in);
+    cudaError_t ce = cudaSuccess;
+#define H2D(off, src, bytes) do { if (ce == cudaSuccess) ce = cudaMemcpyAsync(dbase + (off), (src), (bytes), cudaMemcpyHostToDevice, s); } while (0)
+    H2D(o_lf, lf_H, 12 * B * 8); H2D(o_rf, rf_H, 12 * B * 8); H2D(o_dcm, dcm_meas, 2 * B * 8);
+    H2D(o_ref, ref, (size_t)2 * (N + 1) * B * 8); H2D(o_lc, l_contact, B); H2D(o_rc, r_contact, B);
+    if (reset) H2D(o_rs, reset, B);
+    else if (ce == cudaSuccess) ce = cudaMemsetAsync(dbase + o_rs, 0, B, s);
+#undef H2D
+    if (ce != cudaSuccess) return WC_ERR_CUDA;
     char* di = static_cast<char*>(h->dev_in);
     char* dout = static_cast<char*>(h->dev_out);
     wc_status rc = wc_mpc_tick_dev(h, (const double*)(di + o_lf), (const double*)(di + o_rf),
@@ -252,17 +266,15 @@ wc_status wc_mpc_tick_host(wc_mpc* h, const double* lf_H, const double* rf_H,
                                    (double*)(dout + p_zmp), (int32_t*)(dout + p_st), (int32_t*)(dout + p_it),
                                    (int32_t*)(dout + p_fl), s);
     if (rc != WC_OK) return rc;
-    if (cudaMemcpyAsync(h->pin_out, h->dev_out, out_bytes, cudaMemcpyDeviceToHost, s) != cudaSuccess) return WC_ERR_CUDA;
-    cudaError_t e = cudaStreamSynchronize(s);
+    cudaError_t e = cudaSuccess;
+#define D2H(dst, off, bytes) do { if ((dst) && e == cudaSuccess) e = cudaMemcpyAsync((dst), dout + (off), (bytes), cudaMemcpyDeviceToHost, s); } while (0)
+    D2H(zmp, p_zmp, 2 * B * 8); D2H(osqp_status, p_st, B * 4); D2H(iters, p_it, B * 4); D2H(flags, p_fl, B * 4);
+#undef D2H
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
     if (e != cudaSuccess) {
         std::fprintf(stderr, "[wc_mpc_tick_host] CUDA error: %s\n", cudaGetErrorString(e));
         return WC_ERR_CUDA;
     }
-    const char* po = static_cast<const char*>(h->pin_out);
-    if (zmp) std::memcpy(zmp, po + p_zmp, 2 * B * 8);
-    if (osqp_status) std::memcpy(osqp_status, po + p_st, B * 4);
-    if (iters) std::memcpy(iters, po + p_it, B * 4);
-    if (flags) std::memcpy(flags, po + p_fl, B * 4);
     return WC_OK;
 }
 
@@ -285,6 +297,33 @@ wc_status wc_mpc_debug_get_host(wc_mpc* h, double* primal, double* rho, int32_t*
     if (rho && cudaMemcpy(rho, h->d.rho, B * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) return WC_ERR_CUDA;
     if (rho_updates && cudaMemcpy(rho_updates, h->d.rho_updates, B * sizeof(int32_t), cudaMemcpyDeviceToHost) != cudaSuccess)
         return WC_ERR_CUDA;
+    return WC_OK;
+}
+
+wc_status wc_mpc_enable_profiling(wc_mpc* h, int32_t on)
+{
+    if (!h) return WC_ERR_INVALID_ARG;
+    h->profiling = on ? 1 : 0;
+    return WC_OK;
+}
+
+wc_status wc_mpc_kernel_times_ms(wc_mpc* h, double* prepare_ms, double* admm_ms, int64_t* ticks)
+{
+    if (!h) return WC_ERR_INVALID_ARG;
+    if (cudaSetDevice(h->device) != cudaSuccess) return WC_ERR_CUDA;
+    if (cudaDeviceSynchronize() != cudaSuccess) return WC_ERR_CUDA;
+    for (size_t k = 0; k + 2 < h->ev.size(); k += 3) {
+        float a = 0, b = 0;
+        cudaEventElapsedTime(&a, h->ev[k], h->ev[k + 1]);
+        cudaEventElapsedTime(&b, h->ev[k + 1], h->ev[k + 2]);
+        h->prep_ms_acc += a; h->admm_ms_acc += b; h->timed_ticks += 1;
+    }
+    for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
+    h->ev.clear();
+    if (prepare_ms) *prepare_ms = h->prep_ms_acc;
+    if (admm_ms) *admm_ms = h->admm_ms_acc;
+    if (ticks) *ticks = h->timed_ticks;
+    h->prep_ms_acc = 0; h->admm_ms_acc = 0; h->timed_ticks = 0;
     return WC_OK;
 }
 

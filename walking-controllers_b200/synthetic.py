@@ -185,11 +185,12 @@ def ik_inputs(B, seed, q_reg, fk, device="cpu", perturb=1.0):
     is the forward kinematics used to make desired quantities consistent with the posture (the GPU
     kernel in bench/smoke, the oracle in CPU tests).  Desired feet = actual feet composed with a
     small perturbation, so that task errors have the size seen in closed loop."""
-    g = torch.Generator(device="cpu").manual_seed(seed)
+    gdev = "cuda" if str(device).startswith("cuda") else "cpu"   # draw on the target device (no PCIe for the bench)
+    g = torch.Generator(device=device if gdev == "cuda" else "cpu").manual_seed(seed)
     f64 = torch.float64
 
     def U(*shape, lo=-1.0, hi=1.0):
-        return (lo + (hi - lo) * torch.rand(*shape, generator=g, dtype=f64)).to(device)
+        return lo + (hi - lo) * torch.rand(*shape, generator=g, dtype=f64, device=device)
 
     nJ = q_reg.numel()
     q_reg = q_reg.to(device=device, dtype=f64)
@@ -197,7 +198,7 @@ def ik_inputs(B, seed, q_reg, fk, device="cpu", perturb=1.0):
     q_meas = q_lin + 0.005 * U(nJ, B)
     yaw = math.pi * U(B)
     base_H = GaitBatch._H(2.0 * U(B), 2.0 * U(B), torch.zeros(B, dtype=f64, device=device), yaw)
-    left_is_fixed = (torch.rand(B, generator=g) < 0.5).to(torch.uint8).to(device)
+    left_is_fixed = (torch.rand(B, generator=g, device=device) < 0.5).to(torch.uint8)
     kin = fk(q_lin.contiguous(), base_H.contiguous(), left_is_fixed)
 
     def perturb_H(H):
