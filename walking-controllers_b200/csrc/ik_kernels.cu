@@ -68,94 +68,133 @@ __device__ __forceinline__ double warp_max(double v)
     return v;
 }
 
-// ---- Goldfarb-Idnani dual active set on the bounds, reduced space (sequential, one lane) ----------
-// Mirrors oracle/qpik_ref.c step 5.  All arrays live in shared memory.
+// ---- Goldfarb-Idnani dual active set on the bounds, reduced space, warp-cooperative ---------------
+// Same algorithm as oracle/qpik_ref.c step 5.  Lane c <-> component c of the reduced-space vectors,
+// lane j <-> variable j for the primal point and the bound slacks; matrices live in shared memory
+// (J by columns per lane for J'n, by rows per lane for J2 d2 and the Givens updates; the odd leading
+// dimension keeps both access patterns conflict-free).  Called by the whole warp.
 template <int NV, int NZ>
-__device__ __noinline__ int gi_bounds(const double* ZS /*[NV][NZ+1]*/, const double* XP, const double* LB, const double* UB,
-                                      const double* LS /*[NZ][NZ+1] chol*/, double* JS, double* RS, double* W,
-                                      double* NP, double* DV, double* ZV, double* RV, double* U, int* act,
+__device__ __noinline__ int gi_bounds(int lane, const double* ZS /*[NV][NZ+1]*/, const double* XP, const double* LB,
+                                      const double* UB, const double* LS /*[NZ][NZ+1] chol*/, double* JS, double* RS,
+                                      double* W, double* NP, double* DV, double* ZV, double* RV, double* U, int* act,
                                       unsigned char* is_act, int nwsr_max, int* nwsr_out)
 {
     constexpr int LDZ = NZ + 1, LDL = NZ + 1;
+    constexpr unsigned FULL = 0xffffffffu;
     int q = 0, nwsr = 0;
-    // J = L^-T
-    for (int c = 0; c < NZ; c++)
+    // J = L^-T : lane c solves L' J[:,c] = e_c
+    if (lane < NZ) {
+        const int c = lane;
         for (int i = NZ - 1; i >= 0; i--) {
             double s = (i == c) ? 1.0 : 0.0;
             for (int k = i + 1; k < NZ; k++) s -= LS[k * LDL + i] * JS[k * LDL + c];
             JS[i * LDL + c] = s / LS[i * LDL + i];
         }
-    for (int j = 0; j < 2 * NV; j++) is_act[j] = 0;
+    }
+    for (int j = lane; j < 2 * NV; j += 32) is_act[j] = 0;
+    __syncwarp();
     for (;;) {
-        int p = -1;
-        double sp = -kViolTol;
-        for (int j = 0; j < NV; j++) {
-            double xj = XP[j];
-            for (int c = 0; c < NZ; c++) xj += ZS[j * LDZ + c] * W[c];
-            if (LB[j] > -kQpInf && !is_act[2 * j]) { const double s = xj - LB[j]; if (s < sp) { sp = s; p = 2 * j; } }
-            if (UB[j] < kQpInf && !is_act[2 * j + 1]) { const double s = UB[j] - xj; if (s < sp) { sp = s; p = 2 * j + 1; } }
+        // most violated inactive bound: min over (slack, id), ties to the smaller id (the oracle's scan order)
+        double best = INFINITY; int id = 0x7fffffff;
+        if (lane < NV) {
+            double xj = XP[lane];
+            for (int c = 0; c < NZ; c++) xj += ZS[lane * LDZ + c] * W[c];
+            if (LB[lane] > -kQpInf && !is_act[2 * lane]) { best = xj - LB[lane]; id = 2 * lane; }
+            if (UB[lane] < kQpInf && !is_act[2 * lane + 1]) { const double s = UB[lane] - xj; if (s < best) { best = s; id = 2 * lane + 1; } }
         }
-        if (p < 0) break;
-        const int pv = p >> 1;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ob = __shfl_xor_sync(FULL, best, o);
+            const int oi = __shfl_xor_sync(FULL, id, o);
+            if (ob < best || (ob == best && oi < id)) { best = ob; id = oi; }
+        }
+        if (!(best < -kViolTol)) break; // optimal
+        const int p = id, pv = p >> 1;
         const double sgn = (p & 1) ? -1.0 : 1.0;
-        for (int c = 0; c < NZ; c++) NP[c] = sgn * ZS[pv * LDZ + c];
+        double sp = best;
+        if (lane < NZ) NP[lane] = sgn * ZS[pv * LDZ + lane];
+        __syncwarp();
         double up_ = 0.0;
         bool added = false;
         while (!added) {
-            for (int c = 0; c < NZ; c++) { double s = 0.0; for (int i = 0; i < NZ; i++) s += JS[i * LDL + c] * NP[i]; DV[c] = s; }
-            for (int i = 0; i < NZ; i++) { double s = 0.0; for (int c = q; c < NZ; c++) s += JS[i * LDL + c] * DV[c]; ZV[i] = s; }
-            for (int i = q - 1; i >= 0; i--) { double s = DV[i]; for (int k = i + 1; k < q; k++) s -= RS[i * LDL + k] * RV[k]; RV[i] = s / RS[i * LDL + i]; }
-            double zn = 0.0, dd = 0.0;
-            for (int i = 0; i < NZ; i++) zn += ZV[i] * NP[i];
-            for (int c = 0; c < NZ; c++) dd += DV[c] * DV[c];
+            // d = J' np (lane c), z = J2 d2 (lane i), r = R^-1 d1 (lane 0)
+            double dc = 0.0;
+            if (lane < NZ) { for (int i = 0; i < NZ; i++) dc += JS[i * LDL + lane] * NP[i]; DV[lane] = dc; }
+            __syncwarp();
+            double zi = 0.0;
+            if (lane < NZ) { for (int c = q; c < NZ; c++) zi += JS[lane * LDL + c] * DV[c]; ZV[lane] = zi; }
+            if (lane == 0)
+                for (int i = q - 1; i >= 0; i--) { double s = DV[i]; for (int k = i + 1; k < q; k++) s -= RS[i * LDL + k] * RV[k]; RV[i] = s / RS[i * LDL + i]; }
+            __syncwarp();
+            double zn = (lane < NZ) ? zi * NP[lane] : 0.0, dd = (lane < NZ) ? dc * dc : 0.0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { zn += __shfl_xor_sync(FULL, zn, o); dd += __shfl_xor_sync(FULL, dd, o); }
             const bool have_z = zn > 1e-12 * dd && zn > 0.0;
             const double t2 = have_z ? -sp / zn : INFINITY;
-            double t1 = INFINITY; int l = -1;
-            for (int k = 0; k < q; k++) if (RV[k] > 0.0 && U[k] / RV[k] < t1) { t1 = U[k] / RV[k]; l = k; }
+            double t1 = INFINITY; int l = 0x7fffffff;
+            if (lane < q && RV[lane] > 0.0) { t1 = U[lane] / RV[lane]; l = lane; }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ot = __shfl_xor_sync(FULL, t1, o);
+                const int ol = __shfl_xor_sync(FULL, l, o);
+                if (ot < t1 || (ot == t1 && ol < l)) { t1 = ot; l = ol; }
+            }
             const double tt = t1 < t2 ? t1 : t2;
             if (!(tt < INFINITY)) { *nwsr_out = nwsr; return WC_QP_INFEASIBLE; }
-            if (have_z) for (int i = 0; i < NZ; i++) W[i] += tt * ZV[i];
-            for (int k = 0; k < q; k++) U[k] -= tt * RV[k];
+            if (have_z && lane < NZ) W[lane] += tt * zi;
+            if (lane < q) U[lane] -= tt * RV[lane];
             up_ += tt;
+            __syncwarp();
             if (have_z && t2 <= t1) {
+                // full step: add p.  Givens chain on d[q..NZ-1] (sequential, carried in a register),
+                // each rotation applied to two columns of J by the lanes (rows)
+                double carry = DV[NZ - 1];
                 for (int j = NZ - 1; j > q; j--) {
-                    const double a0 = DV[j - 1], a1 = DV[j];
+                    const double a0 = DV[j - 1], a1 = carry;
                     const double hh = hypot(a0, a1);
-                    if (hh == 0.0) continue;
+                    if (hh == 0.0) { carry = 0.0; continue; }
                     const double cs = a0 / hh, sn = a1 / hh;
-                    DV[j - 1] = hh; DV[j] = 0.0;
-                    for (int i = 0; i < NZ; i++) {
-                        const double j0 = JS[i * LDL + j - 1], j1 = JS[i * LDL + j];
-                        JS[i * LDL + j - 1] = cs * j0 + sn * j1;
-                        JS[i * LDL + j] = -sn * j0 + cs * j1;
+                    carry = hh;
+                    if (lane < NZ) {
+                        const double j0 = JS[lane * LDL + j - 1], j1 = JS[lane * LDL + j];
+                        JS[lane * LDL + j - 1] = cs * j0 + sn * j1;
+                        JS[lane * LDL + j] = -sn * j0 + cs * j1;
                     }
                 }
-                for (int i = 0; i <= q; i++) RS[i * LDL + q] = DV[i];
-                act[q] = p; U[q] = up_; is_act[p] = 1; q++;
+                if (lane <= q) RS[lane * LDL + q] = (lane < q) ? DV[lane] : carry;
+                if (lane == 0) { act[q] = p; U[q] = up_; is_act[p] = 1; }
+                q++;
                 added = true;
+                __syncwarp();
             } else {
-                is_act[act[l]] = 0;
-                for (int k = l; k < q - 1; k++) {
-                    act[k] = act[k + 1]; U[k] = U[k + 1];
-                    for (int i = 0; i <= k + 1; i++) RS[i * LDL + k] = RS[i * LDL + k + 1];
+                // drop constraint l: delete column l of R, re-triangularise with Givens on rows
+                if (lane == 0) {
+                    is_act[act[l]] = 0;
+                    for (int k = l; k < q - 1; k++) { act[k] = act[k + 1]; U[k] = U[k + 1]; }
                 }
+                if (lane < NZ)
+                    for (int k = l; k < q - 1; k++) if (lane <= k + 1) RS[lane * LDL + k] = RS[lane * LDL + k + 1];
                 q--;
+                __syncwarp();
                 for (int k = l; k < q; k++) {
                     const double a0 = RS[k * LDL + k], a1 = RS[(k + 1) * LDL + k];
                     const double hh = hypot(a0, a1);
-                    if (hh == 0.0) continue;
-                    const double cs = a0 / hh, sn = a1 / hh;
-                    RS[k * LDL + k] = hh; RS[(k + 1) * LDL + k] = 0.0;
-                    for (int c = k + 1; c < q; c++) {
-                        const double r0 = RS[k * LDL + c], r1 = RS[(k + 1) * LDL + c];
-                        RS[k * LDL + c] = cs * r0 + sn * r1;
-                        RS[(k + 1) * LDL + c] = -sn * r0 + cs * r1;
+                    __syncwarp();
+                    if (hh != 0.0) {
+                        const double cs = a0 / hh, sn = a1 / hh;
+                        if (lane == k) { RS[k * LDL + k] = hh; RS[(k + 1) * LDL + k] = 0.0; }
+                        if (lane > k && lane < q) {
+                            const double r0 = RS[k * LDL + lane], r1 = RS[(k + 1) * LDL + lane];
+                            RS[k * LDL + lane] = cs * r0 + sn * r1;
+                            RS[(k + 1) * LDL + lane] = -sn * r0 + cs * r1;
+                        }
+                        if (lane < NZ) {
+                            const double j0 = JS[lane * LDL + k], j1 = JS[lane * LDL + k + 1];
+                            JS[lane * LDL + k] = cs * j0 + sn * j1;
+                            JS[lane * LDL + k + 1] = -sn * j0 + cs * j1;
+                        }
                     }
-                    for (int i = 0; i < NZ; i++) {
-                        const double j0 = JS[i * LDL + k], j1 = JS[i * LDL + k + 1];
-                        JS[i * LDL + k] = cs * j0 + sn * j1;
-                        JS[i * LDL + k + 1] = -sn * j0 + cs * j1;
-                    }
+                    __syncwarp();
                 }
                 double xj = XP[pv];
                 for (int c = 0; c < NZ; c++) xj += ZS[pv * LDZ + c] * W[c];
@@ -553,41 +592,39 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) ik_kernel(IkDev d, IkTick
     amax = warp_max(amax);
     int status = WC_QP_SUCCESSFUL_RETURN;
     bool rank_def = false;
-#pragma unroll
-    for (int k = 0; k < NC; k++) {
+#pragma unroll 1
+    for (int k = 0; k < NC; k++) { // rolled on purpose: the body is ~29 x 8 instructions, 15 copies thrash the I-cache
         // owner lane k builds the reflector and publishes it (double-buffered) in shared memory
         double* vs = VS + (k & 1) * 32;
         if (lane == k) {
-            double sig = 0.0;
+            double sig = 0.0, tk = 0.0;
 #pragma unroll
-            for (int r = k; r < NV; r++) sig += T[r] * T[r];
+            for (int r = 0; r < NV; r++) { sig += (r >= k) ? T[r] * T[r] : 0.0; tk = (r == k) ? T[r] : tk; }
             const double nrm = sqrt(sig);
-            const double alpha = T[k] > 0 ? -nrm : nrm;
-            vs[k] = T[k] - alpha;
+            const double alpha = tk > 0 ? -nrm : nrm;
 #pragma unroll
-            for (int r = k + 1; r < NV; r++) vs[r] = T[r];
+            for (int r = 0; r < NV; r++) vs[r] = (r < k) ? 0.0 : ((r == k) ? tk - alpha : T[r]);
             vs[29] = nrm;
-            vs[30] = 1.0 / (sig - T[k] * alpha);
-            T[k] = alpha;
+            vs[30] = 1.0 / (sig - tk * alpha);
 #pragma unroll
-            for (int r = k + 1; r < NV; r++) T[r] = 0.0;
+            for (int r = 0; r < NV; r++) T[r] = (r < k) ? T[r] : ((r == k) ? alpha : 0.0);
         }
         __syncwarp();
         const double nrm_b = vs[29], beta = vs[30];
         if (nrm_b <= kRankTol * (amax > 1.0 ? amax : 1.0)) { rank_def = true; break; }
         double tauT = 0.0, tauG = 0.0;
 #pragma unroll
-        for (int r = k; r < NV; r++) {
+        for (int r = 0; r < NV; r++) {
             const double v = vs[r];
             tauT += v * T[r];
             tauG += v * G[r];
         }
         tauT *= beta; tauG *= beta;
-        const bool upd = lane > k && lane < NC;
+        if (!(lane > k && lane < NC)) tauT = 0.0;
 #pragma unroll
-        for (int r = k; r < NV; r++) {
+        for (int r = 0; r < NV; r++) {
             const double v = vs[r];
-            if (upd) T[r] -= tauT * v;
+            T[r] -= tauT * v;
             G[r] -= tauG * v;
         }
     }
@@ -598,11 +635,14 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) ik_kernel(IkDev d, IkTick
     } else {
         // ---- R' y = b   (lane c holds column c of R)
         double s = (lane < NC) ? BV[lane] : 0.0;
+        double tdiag = 1.0;
+#pragma unroll
+        for (int k = 0; k < NC; k++) tdiag = (lane == k) ? T[k] : tdiag;
+        const double tdinv = 1.0 / tdiag; // one division per lane instead of one per substitution step
         double y[NC];
 #pragma unroll
         for (int k = 0; k < NC; k++) {
-            const double cand = s / T[k];
-            y[k] = __shfl_sync(FULL, cand, k);
+            y[k] = __shfl_sync(FULL, s * tdinv, k);
             if (lane > k) s -= T[k] * y[k];
         }
         // particular solution and null-space basis row of this lane
@@ -690,12 +730,15 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) ik_kernel(IkDev d, IkTick
         for (int b = 0; b < NZ; b++) if (lane == b) mmax = fabs(Mr[b]);
         mmax = warp_max(lane < NZ ? mmax : 0.0);
         bool not_pd = false;
+        double ldinv = 1.0; // 1 / L[lane][lane]
 #pragma unroll
         for (int jc = 0; jc < NZ; jc++) {
             const double djj = __shfl_sync(FULL, Mr[jc], jc);
             if (!(djj > 1e-13 * (mmax > 1.0 ? mmax : 1.0))) { not_pd = true; break; }
             const double piv = sqrt(djj);
-            const double lij = (lane == jc) ? piv : Mr[jc] / piv;
+            const double pinv = 1.0 / piv;
+            const double lij = (lane == jc) ? piv : Mr[jc] * pinv;
+            if (lane == jc) ldinv = pinv;
             if (lane >= jc) Mr[jc] = lij;
 #pragma unroll
             for (int k = jc + 1; k < NZ; k++) {
@@ -717,15 +760,13 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) ik_kernel(IkDev d, IkTick
             double wv[NZ];
 #pragma unroll
             for (int k = 0; k < NZ; k++) {
-                const double cand = acc / Mr[k];
-                const double sk = __shfl_sync(FULL, cand, k);
+                const double sk = __shfl_sync(FULL, acc * ldinv, k);
                 if (lane > k) acc -= Mr[k] * sk;
                 if (lane == k) acc = sk;
             }
 #pragma unroll
             for (int k = NZ - 1; k >= 0; k--) {
-                const double cand = acc / Mr[k];
-                wv[k] = __shfl_sync(FULL, cand, k);
+                wv[k] = __shfl_sync(FULL, acc * ldinv, k);
                 if (lane < k) acc -= LS[k * LDL + (lane < NZ ? lane : 0)] * wv[k];
             }
             nu = xp;
@@ -738,11 +779,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) ik_kernel(IkDev d, IkTick
 #pragma unroll
                 for (int c = 0; c < NZ; c++) if (lane == c) Ws[c] = wv[c];
                 __syncwarp();
-                int st = 0, nw = 0;
-                if (lane == 0)
-                    st = gi_bounds<NV, NZ>(ZS, XP, LBs, UBs, LS, JS, RS, Ws, NPs, DVs, ZVs, RVs, Us, acts, is_act, cfg.nwsr, &nw);
-                st = __shfl_sync(FULL, st, 0);
-                nw = __shfl_sync(FULL, nw, 0);
+                int nw = 0;
+                const int st = gi_bounds<NV, NZ>(lane, ZS, XP, LBs, UBs, LS, JS, RS, Ws, NPs, DVs, ZVs, RVs, Us, acts, is_act,
+                                                 cfg.nwsr, &nw);
                 __syncwarp();
                 status = st; nwsr = nw;
                 nu = xp;

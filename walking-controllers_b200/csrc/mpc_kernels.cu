@@ -5,7 +5,7 @@
 
 namespace wcb {
 
-// chain order per axis: x_k <-> 2(N-k), u_k <-> 2(N-k)-1
+// (legacy chain-order helpers; K2 uses the split stage-indexed layout)
 __device__ __forceinline__ int cx(int N, int k) { return 2 * (N - k); }
 __device__ __forceinline__ int cu(int N, int k) { return 2 * (N - k) - 1; }
 
@@ -138,10 +138,12 @@ void launch_mpc_prepare(const MpcDev& d, const MpcTickIO& io, cudaStream_t s)
 
 // =====================================================================================
 // K2: batched OSQP-equivalent ADMM.  G lanes per instance, 32/G instances per warp, every warp
-// independent (only __syncwarp).  Shared memory per instance (doubles), nA = 2N+1, nR = N+1:
-//   X  [2][nA] iterate          QB [2][nA] scaled q          W  [2][nA] rhs / x~ / delta_x
-//   L1 [2][nA] L2 [2][nA] DI [2][nA]  pentadiagonal LDL^T   DD [2][nA] Ruiz D
-//   YE [2][nR] y eq   DYE [2][nR] delta_y eq   CM/CA/CB [2][nR] scaled A coefficients   EE [2][nR]
+// independent (only __syncwarp).  Per-axis vectors are stored "split": index a*nA + k for the state
+// x_k (k = 0..N) and a*nA + nR + k for the input u_k (k = 0..N-1), nA = 2N+1, nR = N+1, so that all
+// cooperative accesses are stride-1 in the stage index k.  Shared memory per instance (doubles):
+//   X  [2nA] iterate          QB [2nA] scaled q          W  [2nA] rhs / x~ / delta_x
+//   L1 [2nA] L2 [2nA] DI [2nA]  pentadiagonal LDL^T (chain order x_N,u_{N-1},...,x_1 | u_0,x_0)
+//   DD [2nA] Ruiz D            YE [2nR] y eq   DYE [2nR] delta_y eq   CM/CA/CB [2nR] scaled A   EE [2nR]
 //   HX,HY,UH,LH,ZH,YH,DYH,EH [8]  hull rows     CF [16] corner factor   RS [8] scratch
 // =====================================================================================
 struct Smem {
@@ -179,52 +181,62 @@ __device__ __forceinline__ double group_sum(double v, unsigned mask)
     return v;
 }
 
-// Pentadiagonal LDL^T of one axis chain + Schur complement on its (u_0, x_0) corner.
-// Writes L1, L2, DI for rows 0..2N and the 2x2 corner (S11, S12, S22) to out3.
+// Pentadiagonal LDL^T of one axis chain (x_N, u_{N-1}, x_{N-1}, ..., x_1) + Schur complement on its
+// (u_0, x_0) corner.  Rows are stored at the split index of their variable.  out3 = (S11, S12, S22).
 __device__ void factor_axis(const Smem& s, int a, int N, double cQ, double cR, double sigma, double rho_e,
                             double hull_diag, double* out3)
 {
     const int nA = 2 * N + 1, nR = N + 1;
-    const double* CM = s.CM + a * nR; const double* CA = s.CA + a * nR; const double* CB = s.CB + a * nR;
-    const double* DD = s.DD + a * nA;
-    double* L1 = s.L1 + a * nA; double* L2 = s.L2 + a * nA; double* DI = s.DI + a * nA;
-    // running values of the previous two pivots / sub-diagonals
-    double Dm1 = 0.0, Dm2 = 0.0, l1m1 = 0.0, e1m1 = 0.0, e2m2 = 0.0, e2m1 = 0.0;
-    for (int j = 0; j < nA; j++) {
-        // diagonal and super-diagonals of K at chain position j
-        double dj, e1j = 0.0, e2j = 0.0;
-        if ((j & 1) == 0) { // x_k
-            const int k = N - (j >> 1);
-            const double dx = DD[j];
-            dj = cQ * dx * dx + sigma + rho_e * (CM[k] * CM[k] + (k < N ? CA[k + 1] * CA[k + 1] : 0.0));
-            if (k >= 1) { e1j = rho_e * CM[k] * CB[k]; e2j = rho_e * CM[k] * CA[k]; }
-        } else { // u_k
-            const int k = N - ((j + 1) >> 1);
-            const double du = DD[j];
-            const double sc = (k < N - 1) ? 2.0 : 1.0;
-            dj = cR * sc * du * du + sigma + rho_e * CB[k + 1] * CB[k + 1] + (k == 0 ? hull_diag : 0.0);
-            e1j = rho_e * CA[k + 1] * CB[k + 1];
-            if (k >= 1) e2j = -cR * du * DD[j + 2];
-        }
-        if (j < nA - 2) {
-            const double l2 = (j >= 2) ? e2m2 / Dm2 : 0.0;
-            const double l1 = (j >= 1) ? (e1m1 - l2 * Dm2 * l1m1) / Dm1 : 0.0;
+    const double* __restrict__ CM = s.CM + a * nR;
+    const double* __restrict__ CA = s.CA + a * nR;
+    const double* __restrict__ CB = s.CB + a * nR;
+    const double* __restrict__ DX = s.DD + a * nA;
+    const double* __restrict__ DU = s.DD + a * nA + nR;
+    double* __restrict__ L1X = s.L1 + a * nA; double* __restrict__ L1U = s.L1 + a * nA + nR;
+    double* __restrict__ L2X = s.L2 + a * nA; double* __restrict__ L2U = s.L2 + a * nA + nR;
+    double* __restrict__ DIX = s.DI + a * nA; double* __restrict__ DIU = s.DI + a * nA + nR;
+    // pivots / sub-diagonals of the previous two chain positions
+    double Dm1 = 1.0, Dm2 = 1.0, l1m1 = 0.0, e1m1 = 0.0, e2m2 = 0.0, e2m1 = 0.0;
+    for (int k = N; k >= 1; k--) {
+        { // x_k : K entries  d, e1 (with u_{k-1}), e2 (with x_{k-1})
+            const double dx = DX[k];
+            const double dj = cQ * dx * dx + sigma + rho_e * (CM[k] * CM[k] + (k < N ? CA[k + 1] * CA[k + 1] : 0.0));
+            const double e1j = rho_e * CM[k] * CB[k], e2j = rho_e * CM[k] * CA[k];
+            const double l2 = e2m2 / Dm2;
+            const double l1 = (e1m1 - l2 * Dm2 * l1m1) / Dm1;
             const double Dj = dj - l1 * l1 * Dm1 - l2 * l2 * Dm2;
-            L1[j] = l1; L2[j] = l2; DI[j] = 1.0 / Dj;
+            L1X[k] = l1; L2X[k] = l2; DIX[k] = 1.0 / Dj;
             e2m2 = e2m1; e2m1 = e2j; e1m1 = e1j; Dm2 = Dm1; Dm1 = Dj; l1m1 = l1;
-        } else if (j == nA - 2) { // u_0: first corner row
-            const double l2 = (j >= 2) ? e2m2 / Dm2 : 0.0;
-            const double l1 = (j >= 1) ? (e1m1 - l2 * Dm2 * l1m1) / Dm1 : 0.0;
-            L1[j] = l1; L2[j] = l2; DI[j] = 0.0;
-            out3[0] = dj - l1 * l1 * Dm1 - l2 * l2 * Dm2; // S11
-            // keep Dm1 (= D_{2N-2}), l1 for the x_0 row; e2m1 is e2_{2N-2} (x_1 - x_0 coupling)
-            const double l2x = (j >= 1) ? e2m1 / Dm1 : 0.0; // L[2N, 2N-2]
-            out3[1] = e1j - l2x * Dm1 * l1;                 // S12 = K[u0,x0] - l2x D l1
-            L1[j + 1] = 0.0; L2[j + 1] = l2x; DI[j + 1] = 0.0;
-            e1m1 = l2x * l2x * Dm1; // reuse as carry for S22
-        } else { // x_0: second corner row
-            out3[2] = dj - e1m1; // S22
         }
+        if (k >= 2) { // u_{k-1} : d, e1 (with x_{k-1}), e2 (with u_{k-2})
+            const int ku = k - 1;
+            const double du = DU[ku];
+            const double sc = (ku < N - 1) ? 2.0 : 1.0;
+            const double dj = cR * sc * du * du + sigma + rho_e * CB[ku + 1] * CB[ku + 1];
+            const double e1j = rho_e * CA[ku + 1] * CB[ku + 1], e2j = -cR * du * DU[ku - 1];
+            const double l2 = e2m2 / Dm2;
+            const double l1 = (e1m1 - l2 * Dm2 * l1m1) / Dm1;
+            const double Dj = dj - l1 * l1 * Dm1 - l2 * l2 * Dm2;
+            L1U[ku] = l1; L2U[ku] = l2; DIU[ku] = 1.0 / Dj;
+            e2m2 = e2m1; e2m1 = e2j; e1m1 = e1j; Dm2 = Dm1; Dm1 = Dj; l1m1 = l1;
+        }
+    }
+    // corner rows: u_0 then x_0  (Dm1 = pivot of x_1, Dm2 = pivot of u_1)
+    {
+        const double du = DU[0];
+        const double sc = (0 < N - 1) ? 2.0 : 1.0;
+        const double dj = cR * sc * du * du + sigma + rho_e * CB[1] * CB[1] + hull_diag;
+        const double e1j = rho_e * CA[1] * CB[1]; // K[u_0, x_0]
+        const double l2 = e2m2 / Dm2;
+        const double l1 = (e1m1 - l2 * Dm2 * l1m1) / Dm1;
+        L1U[0] = l1; L2U[0] = l2; DIU[0] = 0.0;
+        out3[0] = dj - l1 * l1 * Dm1 - l2 * l2 * Dm2;   // S11
+        const double l2x = e2m1 / Dm1;                  // L[x_0, x_1]
+        out3[1] = e1j - l2x * Dm1 * l1;                 // S12
+        L1X[0] = 0.0; L2X[0] = l2x; DIX[0] = 0.0;
+        const double dx = DX[0];
+        const double d0 = cQ * dx * dx + sigma + rho_e * (CM[0] * CM[0] + CA[1] * CA[1]);
+        out3[2] = d0 - l2x * l2x * Dm1;                 // S22
     }
 }
 
@@ -233,12 +245,16 @@ __device__ void factor_corner(const double* Sx, const double* Sy, double kxy, do
 {
     double A[4][4] = {{Sx[0], kxy, Sx[1], 0.0}, {kxy, Sy[0], 0.0, Sy[1]}, {Sx[1], 0.0, Sx[2], 0.0}, {0.0, Sy[1], 0.0, Sy[2]}};
     double L[4][4], Dv[4];
+#pragma unroll
     for (int j = 0; j < 4; j++) {
         double dj = A[j][j];
+#pragma unroll
         for (int k = 0; k < j; k++) dj -= L[j][k] * L[j][k] * Dv[k];
         Dv[j] = dj;
+#pragma unroll
         for (int i = j + 1; i < 4; i++) {
             double v = A[i][j];
+#pragma unroll
             for (int k = 0; k < j; k++) v -= L[i][k] * L[j][k] * Dv[k];
             L[i][j] = v / dj;
         }
@@ -249,7 +265,6 @@ __device__ void factor_corner(const double* Sx, const double* Sy, double kxy, do
 
 __device__ __forceinline__ void solve_corner(const double* CF, double* r)
 {
-    // r: [u0x, u0y, x0x, x0y] in/out
     double t0 = r[0];
     double t1 = r[1] - CF[0] * t0;
     double t2 = r[2] - CF[1] * t0 - CF[2] * t1;
@@ -259,6 +274,52 @@ __device__ __forceinline__ void solve_corner(const double* CF, double* r)
     t1 -= CF[2] * t2 + CF[4] * t3;
     t0 -= CF[0] * t1 + CF[1] * t2 + CF[3] * t3;
     r[0] = t0; r[1] = t1; r[2] = t2; r[3] = t3;
+}
+
+// forward substitution on one axis chain; leaves the reduced corner right-hand sides in W[u_0], W[x_0]
+__device__ __forceinline__ void sweep_forward(const Smem& s, int a, int N)
+{
+    const int nA = 2 * N + 1, nR = N + 1;
+    double* __restrict__ WX = s.W + a * nA; double* __restrict__ WU = s.W + a * nA + nR;
+    const double* __restrict__ L1X = s.L1 + a * nA; const double* __restrict__ L1U = s.L1 + a * nA + nR;
+    const double* __restrict__ L2X = s.L2 + a * nA; const double* __restrict__ L2U = s.L2 + a * nA + nR;
+    double t1 = 0.0, t2 = 0.0; // t at the previous two chain positions
+#pragma unroll 2
+    for (int k = N; k >= 2; k--) {
+        // the term with the older value first: one FMA on the loop-carried critical path
+        const double tx = (WX[k] - L2X[k] * t2) - L1X[k] * t1;
+        WX[k] = tx;
+        const double tu = (WU[k - 1] - L2U[k - 1] * t1) - L1U[k - 1] * tx;
+        WU[k - 1] = tu;
+        t2 = tx; t1 = tu;
+    }
+    {
+        const double tx = (WX[1] - L2X[1] * t2) - L1X[1] * t1; // x_1
+        WX[1] = tx;
+        t2 = t1; t1 = tx;
+    }
+    WU[0] = (WU[0] - L2U[0] * t2) - L1U[0] * t1;
+    WX[0] = WX[0] - L2X[0] * t1;
+}
+
+// backward substitution, starting from the corner solution already stored in W[u_0], W[x_0]
+__device__ __forceinline__ void sweep_backward(const Smem& s, int a, int N)
+{
+    const int nA = 2 * N + 1, nR = N + 1;
+    double* __restrict__ WX = s.W + a * nA; double* __restrict__ WU = s.W + a * nA + nR;
+    const double* __restrict__ L1X = s.L1 + a * nA; const double* __restrict__ L1U = s.L1 + a * nA + nR;
+    const double* __restrict__ L2X = s.L2 + a * nA; const double* __restrict__ L2U = s.L2 + a * nA + nR;
+    const double* __restrict__ DIX = s.DI + a * nA; const double* __restrict__ DIU = s.DI + a * nA + nR;
+    double a1 = WU[0], a2 = WX[0]; // solution at chain positions j+1, j+2
+#pragma unroll 2
+    for (int k = 1; k < N; k++) {
+        const double xx = (WX[k] * DIX[k] - L2X[k - 1] * a2) - L1U[k - 1] * a1; // x_k
+        WX[k] = xx;
+        const double xu = (WU[k] * DIU[k] - L2U[k - 1] * a1) - L1X[k] * xx;     // u_k
+        WU[k] = xu;
+        a2 = xx; a1 = xu;
+    }
+    WX[N] = (WX[N] * DIX[N] - L2X[N - 1] * a2) - L1U[N - 1] * a1;
 }
 
 template <int G>
@@ -301,17 +362,7 @@ __global__ void __launch_bounds__(128) mpc_admm_kernel(MpcDev d, MpcTickIO io, i
     for (int j = gl; j < 2 * nA; j += G) {
         s.X[j] = setup ? 0.0 : d.x[(size_t)j * B + i];
         s.DD[j] = setup ? 1.0 : d.D[(size_t)j * B + i];
-        // unscaled gradient (MPCSolver::setGradient): state block from the ring, input block G u_prev
-        const int a = j / nA, jj = j - a * nA;
-        double q;
-        if ((jj & 1) == 0) {
-            const int k = N - (jj >> 1);
-            q = d.grad[(size_t)(a * nR + (head + k) % nR) * B + i];
-        } else {
-            const int k = N - ((jj + 1) >> 1);
-            q = (k == 0) ? -(R[a] * up[a]) : 0.0; // G = -Theta' R~ e1 (MPCSolver.cpp:244-245)
-        }
-        s.QB[j] = q;
+        s.QB[j] = 0.0;
     }
     for (int j = gl; j < 2 * nR; j += G) {
         s.YE[j] = setup ? 0.0 : d.yeq[(size_t)j * B + i];
@@ -328,48 +379,55 @@ __global__ void __launch_bounds__(128) mpc_admm_kernel(MpcDev d, MpcTickIO io, i
         s.HY[h] = (h < nh) ? d.hullA[(size_t)(2 * h + 1) * B + i] : 0.0;
     }
     __syncwarp();
+    // unscaled gradient (MPCSolver::setGradient): state block from the ring, input block G u_prev
+    for (int k = gl; k < nR; k += G) {
+        const int slot_k = (head + k) % nR;
+        s.QB[k] = d.grad[(size_t)(slot_k)*B + i];
+        s.QB[nA + k] = d.grad[(size_t)(nR + slot_k) * B + i];
+    }
+    if (gl == 0) { // G = -Theta' R~ e1 -> only the u_0 block (MPCSolver.cpp:244-245)
+        s.QB[nR] = -(R[0] * up[0]);
+        s.QB[nA + nR] = -(R[1] * up[1]);
+    }
+    __syncwarp();
     if (setup) {
         // ---- osqp_setup -> scale_data: Ruiz equilibration of [[P, A'],[A, 0]] with cost normalisation
         // (OSQP scaling.c).  P and A are never formed: their scaled entries follow from D, E, c in
         // closed form.  Group-uniform branch: only group-scope collectives / barriers inside.
         const double ad = fabs(d.a_dyn), bd = fabs(d.b_dyn);
         for (int it = 0; it < st.scaling; it++) {
-            for (int j = gl; j < 2 * nA; j += G) {
-                const int a = j / nA, jj = j - a * nA;
-                const double* Da = s.DD + a * nA; const double* Ea = s.EE + a * nR;
-                const double dj = Da[jj];
-                double nrm;
-                if ((jj & 1) == 0) {
-                    const int k = N - (jj >> 1);
-                    nrm = fabs(c * Q[a] * dj * dj);
-                    nrm = fmax(nrm, Ea[k] * dj);
-                    if (k < N) nrm = fmax(nrm, ad * Ea[k + 1] * dj);
-                } else {
-                    const int k = N - ((jj + 1) >> 1);
-                    const double sc = (k < N - 1) ? 2.0 : 1.0;
-                    nrm = fabs(c * sc * R[a] * dj * dj);
-                    if (k >= 1) nrm = fmax(nrm, fabs(c * R[a] * dj * Da[jj + 2]));
-                    if (k < N - 1) nrm = fmax(nrm, fabs(c * R[a] * dj * Da[jj - 2]));
-                    nrm = fmax(nrm, bd * Ea[k + 1] * dj);
-                    if (k == 0) {
-                        const double* Hc = (a == 0) ? s.HX : s.HY;
-                        for (int h = 0; h < nh; h++) nrm = fmax(nrm, fabs(s.EH[h] * Hc[h]) * dj);
+            for (int k = gl; k < nR; k += G) {
+#pragma unroll
+                for (int a = 0; a < 2; a++) {
+                    const double* DX = s.DD + a * nA; const double* DU = DX + nR; const double* Ea = s.EE + a * nR;
+                    const double dx = DX[k];
+                    double nrm = fabs(c * Q[a] * dx * dx);
+                    nrm = fmax(nrm, Ea[k] * dx);
+                    if (k < N) nrm = fmax(nrm, ad * Ea[k + 1] * dx);
+                    s.W[a * nA + k] = 1.0 / sqrt(limit_scaling(nrm));
+                    if (k < N) {
+                        const double du = DU[k];
+                        const double sc = (k < N - 1) ? 2.0 : 1.0;
+                        double nu = fabs(c * sc * R[a] * du * du);
+                        if (k >= 1) nu = fmax(nu, fabs(c * R[a] * du * DU[k - 1]));
+                        if (k < N - 1) nu = fmax(nu, fabs(c * R[a] * du * DU[k + 1]));
+                        nu = fmax(nu, bd * Ea[k + 1] * du);
+                        if (k == 0) {
+                            const double* Hc = (a == 0) ? s.HX : s.HY;
+                            for (int h = 0; h < nh; h++) nu = fmax(nu, fabs(s.EH[h] * Hc[h]) * du);
+                        }
+                        s.W[a * nA + nR + k] = 1.0 / sqrt(limit_scaling(nu));
                     }
+                    double nr = Ea[k] * dx;
+                    if (k >= 1) {
+                        nr = fmax(nr, ad * Ea[k] * DX[k - 1]);
+                        nr = fmax(nr, bd * Ea[k] * DU[k - 1]);
+                    }
+                    s.DYE[a * nR + k] = 1.0 / sqrt(limit_scaling(nr));
                 }
-                s.W[j] = 1.0 / sqrt(limit_scaling(nrm));
-            }
-            for (int j = gl; j < 2 * nR; j += G) {
-                const int a = j / nR, k = j - a * nR;
-                const double* Da = s.DD + a * nA;
-                double nrm = s.EE[j] * Da[cx(N, k)];
-                if (k >= 1) {
-                    nrm = fmax(nrm, ad * s.EE[j] * Da[cx(N, k - 1)]);
-                    nrm = fmax(nrm, bd * s.EE[j] * Da[cu(N, k - 1)]);
-                }
-                s.DYE[j] = 1.0 / sqrt(limit_scaling(nrm));
             }
             for (int h = gl; h < nh; h += G) {
-                const double nrm = fmax(fabs(s.EH[h] * s.HX[h]) * s.DD[cu(N, 0)], fabs(s.EH[h] * s.HY[h]) * s.DD[nA + cu(N, 0)]);
+                const double nrm = fmax(fabs(s.EH[h] * s.HX[h]) * s.DD[nR], fabs(s.EH[h] * s.HY[h]) * s.DD[nA + nR]);
                 s.DYH[h] = 1.0 / sqrt(limit_scaling(nrm));
             }
             __syncwarp(gmask);
@@ -379,21 +437,23 @@ __global__ void __launch_bounds__(128) mpc_admm_kernel(MpcDev d, MpcTickIO io, i
             __syncwarp(gmask);
             // cost normalisation: c <- c / max(mean_j ||P_j||_inf, ||q||_inf)
             double sum = 0.0, qn = 0.0;
-            for (int j = gl; j < 2 * nA; j += G) {
-                const int a = j / nA, jj = j - a * nA;
-                const double* Da = s.DD + a * nA;
-                const double dj = Da[jj];
-                double nrm;
-                if ((jj & 1) == 0) nrm = fabs(c * Q[a] * dj * dj);
-                else {
-                    const int k = N - ((jj + 1) >> 1);
-                    const double sc = (k < N - 1) ? 2.0 : 1.0;
-                    nrm = fabs(c * sc * R[a] * dj * dj);
-                    if (k >= 1) nrm = fmax(nrm, fabs(c * R[a] * dj * Da[jj + 2]));
-                    if (k < N - 1) nrm = fmax(nrm, fabs(c * R[a] * dj * Da[jj - 2]));
+            for (int k = gl; k < nR; k += G) {
+#pragma unroll
+                for (int a = 0; a < 2; a++) {
+                    const double* DX = s.DD + a * nA; const double* DU = DX + nR;
+                    const double dx = DX[k];
+                    sum += fabs(c * Q[a] * dx * dx);
+                    qn = fmax(qn, fabs(c * dx * s.QB[a * nA + k]));
+                    if (k < N) {
+                        const double du = DU[k];
+                        const double sc = (k < N - 1) ? 2.0 : 1.0;
+                        double nu = fabs(c * sc * R[a] * du * du);
+                        if (k >= 1) nu = fmax(nu, fabs(c * R[a] * du * DU[k - 1]));
+                        if (k < N - 1) nu = fmax(nu, fabs(c * R[a] * du * DU[k + 1]));
+                        sum += nu;
+                        qn = fmax(qn, fabs(c * du * s.QB[a * nA + nR + k]));
+                    }
                 }
-                sum += nrm;
-                qn = fmax(qn, fabs(c * dj * s.QB[j]));
             }
             sum = group_sum<G>(sum, gmask);
             qn = group_max<G>(qn, gmask);
@@ -414,18 +474,21 @@ __global__ void __launch_bounds__(128) mpc_admm_kernel(MpcDev d, MpcTickIO io, i
     const double cinv = 1.0 / c;
     // scaled problem data: q (osqp_update_lin_cost), A coefficients, bounds (osqp_update_bounds)
     for (int j = gl; j < 2 * nA; j += G) s.QB[j] = (s.QB[j] * s.DD[j]) * c;
-    for (int j = gl; j < 2 * nR; j += G) {
-        const int a = j / nR, k = j - a * nR;
-        const double e = s.EE[j];
-        s.CM[j] = -e * s.DD[a * nA + cx(N, k)];
-        s.CA[j] = (k >= 1) ? d.a_dyn * e * s.DD[a * nA + cx(N, k - 1)] : 0.0;
-        s.CB[j] = (k >= 1) ? d.b_dyn * e * s.DD[a * nA + cu(N, k - 1)] : 0.0;
+    for (int k = gl; k < nR; k += G) {
+#pragma unroll
+        for (int a = 0; a < 2; a++) {
+            const double* DX = s.DD + a * nA; const double* DU = DX + nR;
+            const double e = s.EE[a * nR + k];
+            s.CM[a * nR + k] = -e * DX[k];
+            s.CA[a * nR + k] = (k >= 1) ? d.a_dyn * e * DX[k - 1] : 0.0;
+            s.CB[a * nR + k] = (k >= 1) ? d.b_dyn * e * DU[k - 1] : 0.0;
+        }
     }
     for (int h = gl; h < kMaxHull; h += G) {
         const bool on = h < nh;
         const double e = s.EH[h];
-        s.HX[h] = on ? e * s.HX[h] * s.DD[0 * nA + cu(N, 0)] : 0.0;
-        s.HY[h] = on ? e * s.HY[h] * s.DD[1 * nA + cu(N, 0)] : 0.0;
+        s.HX[h] = on ? e * s.HX[h] * s.DD[nR] : 0.0;
+        s.HY[h] = on ? e * s.HY[h] * s.DD[nA + nR] : 0.0;
         s.UH[h] = on ? e * d.hullb[(size_t)h * B + i] : 0.0;
         s.LH[h] = on ? e * (-infty) : 0.0;
     }
@@ -441,11 +504,6 @@ __global__ void __launch_bounds__(128) mpc_admm_kernel(MpcDev d, MpcTickIO io, i
             double hd = 0.0;
             for (int h = 0; h < nh; h++) { const double v = (gl == 0) ? s.HX[h] : s.HY[h]; hd += rho_now * v * v; }
             factor_axis(s, gl, N, c * Q[gl], c * R[gl], sigma, rho_e, hd, s.RS + 3 * gl);
-        }
-        if (G == 1) {
-            double hd = 0.0;
-            for (int h = 0; h < nh; h++) hd += rho_now * s.HY[h] * s.HY[h];
-            factor_axis(s, 1, N, c * Q[1], c * R[1], sigma, rho_e, hd, s.RS + 3);
         }
         __syncwarp();
         if (gl == 0) {
@@ -467,61 +525,76 @@ __global__ void __launch_bounds__(128) mpc_admm_kernel(MpcDev d, MpcTickIO io, i
     double rp_s = 0, rd_s = 0, nz_s = 0, nAx_s = 0, nq_s = 0, nAty_s = 0, nPx_s = 0;
     int prim_inf = 0, dual_inf = 0;
 
+    // (A' y)_j and (P x)_j for the variables of stage k, axis a; V = vector playing the role of x, Y of y
+    // returns through references: x-variable (px_x, aty_x), u-variable (px_u, aty_u; only if k < N)
+    auto stage_products = [&](int a, int k, const double* V, const double* Yeq, const double* Yh,
+                              double& px_x, double& aty_x, double& px_u, double& aty_u) {
+        const double* DX = s.DD + a * nA; const double* DU = DX + nR;
+        const double* VX = V + a * nA; const double* VU = VX + nR;
+        const double* Ya = Yeq + a * nR;
+        const double* CMa = s.CM + a * nR; const double* CAa = s.CA + a * nR; const double* CBa = s.CB + a * nR;
+        px_x = (c * Q[a]) * DX[k] * DX[k] * VX[k];
+        aty_x = CMa[k] * Ya[k] + (k < N ? CAa[k + 1] * Ya[k + 1] : 0.0);
+        px_u = 0.0; aty_u = 0.0;
+        if (k < N) {
+            const double sc = (k < N - 1) ? 2.0 : 1.0;
+            double t = sc * DU[k] * VU[k];
+            if (k >= 1) t -= DU[k - 1] * VU[k - 1];
+            if (k < N - 1) t -= DU[k + 1] * VU[k + 1];
+            px_u = (c * R[a]) * DU[k] * t;
+            aty_u = CBa[k + 1] * Ya[k + 1];
+            if (k == 0) {
+                const double* Hc = (a == 0) ? s.HX : s.HY;
+                for (int h = 0; h < nh; h++) aty_u += Hc[h] * Yh[h];
+            }
+        }
+    };
+
     // evaluates residual information for the CURRENT (x, z, y) (update_info + the norms of check_termination)
     auto update_info = [&]() {
         double m_rp_u = 0, m_rp_s = 0, m_z_u = 0, m_z_s = 0, m_ax_u = 0, m_ax_s = 0;
-        for (int j = gl; j < 2 * nR; j += G) {
-            const int a = j / nR, k = j - a * nR;
-            const double* Xa = s.X + a * nA;
-            double ax = s.CM[j] * Xa[cx(N, k)];
-            if (k >= 1) ax += s.CA[j] * Xa[cx(N, k - 1)] + s.CB[j] * Xa[cu(N, k - 1)];
-            const double z = (k == 0) ? lb0[a] : 0.0;
-            const double einv = 1.0 / s.EE[j];
-            const double r = ax - z;
-            m_rp_s = fmax(m_rp_s, fabs(r)); m_rp_u = fmax(m_rp_u, fabs(einv * r));
-            m_z_s = fmax(m_z_s, fabs(z)); m_z_u = fmax(m_z_u, fabs(einv * z));
-            m_ax_s = fmax(m_ax_s, fabs(ax)); m_ax_u = fmax(m_ax_u, fabs(einv * ax));
+        double m_rd_u = 0, m_rd_s = 0, m_q_u = 0, m_q_s = 0, m_aty_u = 0, m_aty_s = 0, m_px_u = 0, m_px_s = 0;
+        for (int k = gl; k < nR; k += G) {
+#pragma unroll
+            for (int a = 0; a < 2; a++) {
+                const double* XX = s.X + a * nA; const double* XU = XX + nR;
+                const int j = a * nR + k;
+                double ax = s.CM[j] * XX[k];
+                if (k >= 1) ax += s.CA[j] * XX[k - 1] + s.CB[j] * XU[k - 1];
+                const double z = (k == 0) ? lb0[a] : 0.0;
+                const double einv = 1.0 / s.EE[j];
+                const double r = ax - z;
+                m_rp_s = fmax(m_rp_s, fabs(r)); m_rp_u = fmax(m_rp_u, fabs(einv * r));
+                m_z_s = fmax(m_z_s, fabs(z)); m_z_u = fmax(m_z_u, fabs(einv * z));
+                m_ax_s = fmax(m_ax_s, fabs(ax)); m_ax_u = fmax(m_ax_u, fabs(einv * ax));
+                double px_x, aty_x, px_u, aty_u;
+                stage_products(a, k, s.X, s.YE, s.YH, px_x, aty_x, px_u, aty_u);
+                {
+                    const double q = s.QB[a * nA + k], dinv = 1.0 / s.DD[a * nA + k];
+                    const double rr = q + px_x + aty_x;
+                    m_rd_s = fmax(m_rd_s, fabs(rr)); m_rd_u = fmax(m_rd_u, fabs(dinv * rr));
+                    m_q_s = fmax(m_q_s, fabs(q)); m_q_u = fmax(m_q_u, fabs(dinv * q));
+                    m_aty_s = fmax(m_aty_s, fabs(aty_x)); m_aty_u = fmax(m_aty_u, fabs(dinv * aty_x));
+                    m_px_s = fmax(m_px_s, fabs(px_x)); m_px_u = fmax(m_px_u, fabs(dinv * px_x));
+                }
+                if (k < N) {
+                    const double q = s.QB[a * nA + nR + k], dinv = 1.0 / s.DD[a * nA + nR + k];
+                    const double rr = q + px_u + aty_u;
+                    m_rd_s = fmax(m_rd_s, fabs(rr)); m_rd_u = fmax(m_rd_u, fabs(dinv * rr));
+                    m_q_s = fmax(m_q_s, fabs(q)); m_q_u = fmax(m_q_u, fabs(dinv * q));
+                    m_aty_s = fmax(m_aty_s, fabs(aty_u)); m_aty_u = fmax(m_aty_u, fabs(dinv * aty_u));
+                    m_px_s = fmax(m_px_s, fabs(px_u)); m_px_u = fmax(m_px_u, fabs(dinv * px_u));
+                }
+            }
         }
         for (int h = gl; h < nh; h += G) {
-            const double ax = s.HX[h] * s.X[0 * nA + cu(N, 0)] + s.HY[h] * s.X[1 * nA + cu(N, 0)];
+            const double ax = s.HX[h] * s.X[nR] + s.HY[h] * s.X[nA + nR];
             const double z = s.ZH[h];
             const double einv = 1.0 / s.EH[h];
             const double r = ax - z;
             m_rp_s = fmax(m_rp_s, fabs(r)); m_rp_u = fmax(m_rp_u, fabs(einv * r));
             m_z_s = fmax(m_z_s, fabs(z)); m_z_u = fmax(m_z_u, fabs(einv * z));
             m_ax_s = fmax(m_ax_s, fabs(ax)); m_ax_u = fmax(m_ax_u, fabs(einv * ax));
-        }
-        double m_rd_u = 0, m_rd_s = 0, m_q_u = 0, m_q_s = 0, m_aty_u = 0, m_aty_s = 0, m_px_u = 0, m_px_s = 0;
-        for (int j = gl; j < 2 * nA; j += G) {
-            const int a = j / nA, jj = j - a * nA;
-            const double* Xa = s.X + a * nA; const double* Da = s.DD + a * nA;
-            const double* Ya = s.YE + a * nR;
-            const double* CMa = s.CM + a * nR; const double* CAa = s.CA + a * nR; const double* CBa = s.CB + a * nR;
-            double px, aty;
-            if ((jj & 1) == 0) {
-                const int k = N - (jj >> 1);
-                px = (c * Q[a]) * Da[jj] * Da[jj] * Xa[jj];
-                aty = CMa[k] * Ya[k] + (k < N ? CAa[k + 1] * Ya[k + 1] : 0.0);
-            } else {
-                const int k = N - ((jj + 1) >> 1);
-                const double sc = (k < N - 1) ? 2.0 : 1.0;
-                double t = sc * Da[jj] * Xa[jj];
-                if (k >= 1) t -= Da[jj + 2] * Xa[jj + 2];
-                if (k < N - 1) t -= Da[jj - 2] * Xa[jj - 2];
-                px = (c * R[a]) * Da[jj] * t;
-                aty = CBa[k + 1] * Ya[k + 1];
-                if (k == 0) {
-                    const double* Hc = (a == 0) ? s.HX : s.HY;
-                    for (int h = 0; h < nh; h++) aty += Hc[h] * s.YH[h];
-                }
-            }
-            const double q = s.QB[j];
-            const double dinv = 1.0 / Da[jj];
-            const double r = q + px + aty;
-            m_rd_s = fmax(m_rd_s, fabs(r)); m_rd_u = fmax(m_rd_u, fabs(dinv * r));
-            m_q_s = fmax(m_q_s, fabs(q)); m_q_u = fmax(m_q_u, fabs(dinv * q));
-            m_aty_s = fmax(m_aty_s, fabs(aty)); m_aty_u = fmax(m_aty_u, fabs(dinv * aty));
-            m_px_s = fmax(m_px_s, fabs(px)); m_px_u = fmax(m_px_u, fabs(dinv * px));
         }
         const unsigned mk = gmask;
         pri_res = group_max<G>(m_rp_u, mk); rp_s = group_max<G>(m_rp_s, mk);
@@ -538,10 +611,9 @@ __global__ void __launch_bounds__(128) mpc_admm_kernel(MpcDev d, MpcTickIO io, i
         // project delta_y on the polar of the recession cone: hull rows have l = -inf -> max(dy, 0)
         double nrm = 0.0, lhs = 0.0;
         for (int j = gl; j < 2 * nR; j += G) {
-            const int a = j / nR, k = j - a * nR;
             const double dy = s.DYE[j];
             nrm = fmax(nrm, fabs(s.EE[j] * dy));
-            const double bnd = (k == 0) ? lb0[a] : 0.0;
+            const double bnd = (j == 0) ? lb0[0] : ((j == nR) ? lb0[1] : 0.0);
             lhs += bnd * fmax(dy, 0.0) + bnd * fmin(dy, 0.0);
         }
         for (int h = gl; h < nh; h += G) {
@@ -559,23 +631,14 @@ __global__ void __launch_bounds__(128) mpc_admm_kernel(MpcDev d, MpcTickIO io, i
         int res = 0;
         if (nrm > 1.0 / infty && lhs < -eps * nrm) {
             double m = 0.0;
-            for (int j = gl; j < 2 * nA; j += G) {
-                const int a = j / nA, jj = j - a * nA;
-                const double* Ya = s.DYE + a * nR;
-                const double* CMa = s.CM + a * nR; const double* CAa = s.CA + a * nR; const double* CBa = s.CB + a * nR;
-                double aty;
-                if ((jj & 1) == 0) {
-                    const int k = N - (jj >> 1);
-                    aty = CMa[k] * Ya[k] + (k < N ? CAa[k + 1] * Ya[k + 1] : 0.0);
-                } else {
-                    const int k = N - ((jj + 1) >> 1);
-                    aty = CBa[k + 1] * Ya[k + 1];
-                    if (k == 0) {
-                        const double* Hc = (a == 0) ? s.HX : s.HY;
-                        for (int h = 0; h < nh; h++) aty += Hc[h] * s.DYH[h];
-                    }
+            for (int k = gl; k < nR; k += G) {
+#pragma unroll
+                for (int a = 0; a < 2; a++) {
+                    double px_x, aty_x, px_u, aty_u;
+                    stage_products(a, k, s.X, s.DYE, s.DYH, px_x, aty_x, px_u, aty_u);
+                    m = fmax(m, fabs(aty_x / s.DD[a * nA + k]));
+                    if (k < N) m = fmax(m, fabs(aty_u / s.DD[a * nA + nR + k]));
                 }
-                m = fmax(m, fabs(aty / s.DD[j]));
             }
             m = group_max<G>(m, gmask);
             res = m < eps * nrm;
@@ -593,34 +656,31 @@ __global__ void __launch_bounds__(128) mpc_admm_kernel(MpcDev d, MpcTickIO io, i
         int res = 0;
         if (nrm > 1.0 / infty && qdx < -c * eps * nrm) {
             double m = 0.0;
-            for (int j = gl; j < 2 * nA; j += G) {
-                const int a = j / nA, jj = j - a * nA;
-                const double* Xa = s.W + a * nA; const double* Da = s.DD + a * nA;
-                double px;
-                if ((jj & 1) == 0) px = (c * Q[a]) * Da[jj] * Da[jj] * Xa[jj];
-                else {
-                    const int k = N - ((jj + 1) >> 1);
-                    const double sc = (k < N - 1) ? 2.0 : 1.0;
-                    double t = sc * Da[jj] * Xa[jj];
-                    if (k >= 1) t -= Da[jj + 2] * Xa[jj + 2];
-                    if (k < N - 1) t -= Da[jj - 2] * Xa[jj - 2];
-                    px = (c * R[a]) * Da[jj] * t;
+            for (int k = gl; k < nR; k += G) {
+#pragma unroll
+                for (int a = 0; a < 2; a++) {
+                    double px_x, aty_x, px_u, aty_u;
+                    stage_products(a, k, s.W, s.YE, s.YH, px_x, aty_x, px_u, aty_u);
+                    m = fmax(m, fabs(px_x / s.DD[a * nA + k]));
+                    if (k < N) m = fmax(m, fabs(px_u / s.DD[a * nA + nR + k]));
                 }
-                m = fmax(m, fabs(px / Da[jj]));
             }
             m = group_max<G>(m, gmask);
             if (m < c * eps * nrm) {
                 int bad = 0;
-                for (int j = gl; j < 2 * nR; j += G) {
-                    const int a = j / nR, k = j - a * nR;
-                    const double* Xa = s.W + a * nA;
-                    double ax = s.CM[j] * Xa[cx(N, k)];
-                    if (k >= 1) ax += s.CA[j] * Xa[cx(N, k - 1)] + s.CB[j] * Xa[cu(N, k - 1)];
-                    ax /= s.EE[j];
-                    if (ax > eps * nrm || ax < -eps * nrm) bad = 1; // both bounds finite on equality rows
+                for (int k = gl; k < nR; k += G) {
+#pragma unroll
+                    for (int a = 0; a < 2; a++) {
+                        const double* WX = s.W + a * nA; const double* WU = WX + nR;
+                        const int j = a * nR + k;
+                        double ax = s.CM[j] * WX[k];
+                        if (k >= 1) ax += s.CA[j] * WX[k - 1] + s.CB[j] * WU[k - 1];
+                        ax /= s.EE[j];
+                        if (ax > eps * nrm || ax < -eps * nrm) bad = 1; // both bounds finite on equality rows
+                    }
                 }
                 for (int h = gl; h < nh; h += G) {
-                    double ax = s.HX[h] * s.W[0 * nA + cu(N, 0)] + s.HY[h] * s.W[1 * nA + cu(N, 0)];
+                    double ax = s.HX[h] * s.W[nR] + s.HY[h] * s.W[nA + nR];
                     ax /= s.EH[h];
                     if ((s.UH[h] < infty * kMinScaling && ax > eps * nrm) ||
                         (s.LH[h] > -infty * kMinScaling && ax < -eps * nrm)) bad = 1;
@@ -652,87 +712,76 @@ __global__ void __launch_bounds__(128) mpc_admm_kernel(MpcDev d, MpcTickIO io, i
     const int chk = st.check_termination;
     const int rint = d.rho_interval;
     int iter = 0;
+    int to_check = chk, to_adapt = rint; // countdowns instead of modulo in the hot loop
     bool warp_busy = __any_sync(FULL, !done);
     while (warp_busy) {
         iter++;
         const bool act = !done;
         const double rho_e = kRhoEqOverIneq * rho;
         const double rho_e_inv = 1.0 / rho_e, rho_inv = 1.0 / rho;
-        const bool check_now = chk && (iter % chk == 0);
+        bool check_now = false, adapt_now = false;
+        if (chk) { if (--to_check == 0) { check_now = true; to_check = chk; } }
+        if (st.adaptive_rho && rint) { if (--to_adapt == 0) { adapt_now = true; to_adapt = rint; } }
         const bool keep_delta = check_now || iter >= max_iter; // delta_x / delta_y feed the infeasibility tests only
         // ---- update_xz_tilde: right-hand side  sigma x - q + A' (rho z - y)
         if (act) {
-            for (int j = gl; j < 2 * nA; j += G) {
-                const int a = j / nA, jj = j - a * nA;
-                const double* Ya = s.YE + a * nR;
-                const double* CMa = s.CM + a * nR; const double* CAa = s.CA + a * nR; const double* CBa = s.CB + a * nR;
-                double r = sigma * s.X[j] - s.QB[j];
-                if ((jj & 1) == 0) {
-                    const int k = N - (jj >> 1);
+            for (int k = gl; k < nR; k += G) {
+#pragma unroll
+                for (int a = 0; a < 2; a++) {
+                    const double* Ya = s.YE + a * nR;
+                    const double* CMa = s.CM + a * nR; const double* CAa = s.CA + a * nR; const double* CBa = s.CB + a * nR;
                     // w_k = rho_e (z_k - y_k / rho_e), z_k = 0 except equality row 0
                     const double zk = (k == 0) ? z0prev[a] : 0.0;
-                    r += CMa[k] * (rho_e * (zk - rho_e_inv * Ya[k]));
-                    if (k < N) r += CAa[k + 1] * (rho_e * (0.0 - rho_e_inv * Ya[k + 1]));
-                } else {
-                    const int k = N - ((jj + 1) >> 1);
-                    r += CBa[k + 1] * (rho_e * (0.0 - rho_e_inv * Ya[k + 1]));
-                    if (k == 0) {
-                        const double* Hc = (a == 0) ? s.HX : s.HY;
-                        for (int h = 0; h < nh; h++) r += Hc[h] * (rho * (s.ZH[h] - rho_inv * s.YH[h]));
+                    const double wk = rho_e * (zk - rho_e_inv * Ya[k]);
+                    const double wk1 = (k < N) ? rho_e * (0.0 - rho_e_inv * Ya[k + 1]) : 0.0;
+                    const int jx = a * nA + k;
+                    double r = sigma * s.X[jx] - s.QB[jx];
+                    r += CMa[k] * wk;
+                    if (k < N) r += CAa[k + 1] * wk1;
+                    s.W[jx] = r;
+                    if (k < N) {
+                        const int ju = a * nA + nR + k;
+                        double ru = sigma * s.X[ju] - s.QB[ju];
+                        ru += CBa[k + 1] * wk1;
+                        if (k == 0) {
+                            const double* Hc = (a == 0) ? s.HX : s.HY;
+                            for (int h = 0; h < nh; h++) ru += Hc[h] * (rho * (s.ZH[h] - rho_inv * s.YH[h]));
+                        }
+                        s.W[ju] = ru;
                     }
                 }
-                s.W[j] = r;
             }
         }
         __syncwarp();
-        // ---- reduced KKT solve: forward sweeps (two axis chains on two lanes)
-        if (act && (gl < 2 || G == 1)) {
-            for (int a = (G == 1 ? 0 : gl); a < (G == 1 ? 2 : gl + 1); a++) {
-                double* W = s.W + a * nA; const double* L1 = s.L1 + a * nA; const double* L2 = s.L2 + a * nA;
-                double t1 = 0.0, t2 = 0.0; // t_{j-1}, t_{j-2}
-                for (int j = 0; j < nA - 2; j++) {
-                    const double t = W[j] - L1[j] * t1 - L2[j] * t2;
-                    W[j] = t; t2 = t1; t1 = t;
-                }
-                // corner rows: u_0 (nA-2), x_0 (nA-1)
-                W[nA - 2] = W[nA - 2] - L1[nA - 2] * t1 - L2[nA - 2] * t2;
-                W[nA - 1] = W[nA - 1] - L2[nA - 1] * t1;
-            }
-        }
+        // ---- reduced KKT solve: the two axis chains run on two lanes
+        if (act && gl < 2) sweep_forward(s, gl, N);
         __syncwarp();
         if (act && gl == 0) {
-            double r[4] = {s.W[nA - 2], s.W[nA + nA - 2], s.W[nA - 1], s.W[nA + nA - 1]};
+            double r[4] = {s.W[nR], s.W[nA + nR], s.W[0], s.W[nA]};
             solve_corner(s.CF, r);
-            s.W[nA - 2] = r[0]; s.W[nA + nA - 2] = r[1]; s.W[nA - 1] = r[2]; s.W[nA + nA - 1] = r[3];
+            s.W[nR] = r[0]; s.W[nA + nR] = r[1]; s.W[0] = r[2]; s.W[nA] = r[3];
         }
         __syncwarp();
-        if (act && (gl < 2 || G == 1)) {
-            for (int a = (G == 1 ? 0 : gl); a < (G == 1 ? 2 : gl + 1); a++) {
-                double* W = s.W + a * nA; const double* L1 = s.L1 + a * nA; const double* L2 = s.L2 + a * nA;
-                const double* DI = s.DI + a * nA;
-                double x1 = W[nA - 2], x2 = W[nA - 1]; // x_{j+1}, x_{j+2}
-                for (int j = nA - 3; j >= 0; j--) {
-                    const double xj = W[j] * DI[j] - L1[j + 1] * x1 - L2[j + 2] * x2;
-                    W[j] = xj; x2 = x1; x1 = xj;
+        if (act && gl < 2) sweep_backward(s, gl, N);
+        __syncwarp();
+        // ---- update_z / update_y on the rows (z~ = A x~)
+        if (act) {
+            for (int k = gl; k < nR; k += G) {
+#pragma unroll
+                for (int a = 0; a < 2; a++) {
+                    const double* WX = s.W + a * nA; const double* WU = WX + nR;
+                    const int j = a * nR + k;
+                    double zt = s.CM[j] * WX[k];
+                    if (k >= 1) zt += s.CA[j] * WX[k - 1] + s.CB[j] * WU[k - 1];
+                    const double zprev = (k == 0) ? z0prev[a] : 0.0;
+                    const double znew = (k == 0) ? lb0[a] : 0.0; // projection on [l, u] with l == u
+                    const double dy = rho_e * (alpha * zt + (1.0 - alpha) * zprev - znew);
+                    s.YE[j] += dy;
+                    if (keep_delta) s.DYE[j] = dy;
                 }
             }
-        }
-        __syncwarp();
-        // ---- update_z / update_y on the rows (z~ = A x~), then update_x
-        if (act) {
-            for (int j = gl; j < 2 * nR; j += G) {
-                const int a = j / nR, k = j - a * nR;
-                const double* Wa = s.W + a * nA;
-                double zt = s.CM[j] * Wa[cx(N, k)];
-                if (k >= 1) zt += s.CA[j] * Wa[cx(N, k - 1)] + s.CB[j] * Wa[cu(N, k - 1)];
-                const double zprev = (k == 0) ? z0prev[a] : 0.0;
-                const double znew = (k == 0) ? lb0[a] : 0.0; // projection on [l, u] with l == u
-                const double dy = rho_e * (alpha * zt + (1.0 - alpha) * zprev - znew);
-                s.YE[j] += dy;
-                if (keep_delta) s.DYE[j] = dy;
-            }
             for (int h = gl; h < nh; h += G) {
-                const double zt = s.HX[h] * s.W[0 * nA + cu(N, 0)] + s.HY[h] * s.W[1 * nA + cu(N, 0)];
+                const double zt = s.HX[h] * s.W[nR] + s.HY[h] * s.W[nA + nR];
                 const double zp = s.ZH[h], y = s.YH[h];
                 const double zr = alpha * zt + (1.0 - alpha) * zp;
                 double zn = zr + rho_inv * y;
@@ -745,6 +794,7 @@ __global__ void __launch_bounds__(128) mpc_admm_kernel(MpcDev d, MpcTickIO io, i
             }
         }
         __syncwarp();
+        // ---- update_x
         if (act) {
             for (int j = gl; j < 2 * nA; j += G) {
                 const double xp = s.X[j];
@@ -761,7 +811,6 @@ __global__ void __launch_bounds__(128) mpc_admm_kernel(MpcDev d, MpcTickIO io, i
             update_info();
             if (act) { if (check_termination(0)) done = true; }
         }
-        const bool adapt_now = st.adaptive_rho && rint && (iter % rint == 0);
         if (adapt_now) {
             if (!check_now) update_info();
             if (act && !done) {
@@ -813,8 +862,8 @@ __global__ void __launch_bounds__(128) mpc_admm_kernel(MpcDev d, MpcTickIO io, i
             d.rho[i] = rho;
             d.rho_updates[i] = rho_updates;
             if (status == WC_OSQP_SOLVED) {
-                out[0] = s.X[0 * nA + cu(N, 0)] * s.DD[0 * nA + cu(N, 0)];
-                out[1] = s.X[1 * nA + cu(N, 0)] * s.DD[1 * nA + cu(N, 0)];
+                out[0] = s.X[nR] * s.DD[nR];
+                out[1] = s.X[nA + nR] * s.DD[nA + nR];
                 d.uprev[i] = out[0]; d.uprev[B + i] = out[1];
                 // ConvexHullProjectionConstraint::computeMargin (Controller.cpp:513-517)
                 bool inside = true;
@@ -901,14 +950,14 @@ __global__ void mpc_export_primal_kernel(MpcDev d, double* out)
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= d.B) return;
     const size_t B = (size_t)d.B;
-    const int N = d.N, nA = 2 * N + 1;
+    const int N = d.N, nA = 2 * N + 1, nR = N + 1;
     for (int a = 0; a < 2; a++) {
         for (int k = 0; k <= N; k++) {
-            const size_t j = (size_t)(a * nA + cx(N, k));
+            const size_t j = (size_t)(a * nA + k);
             out[(size_t)(2 * k + a) * B + i] = d.x[j * B + i] * d.D[j * B + i];
         }
         for (int k = 0; k < N; k++) {
-            const size_t j = (size_t)(a * nA + cu(N, k));
+            const size_t j = (size_t)(a * nA + nR + k);
             out[(size_t)(2 * (N + 1) + 2 * k + a) * B + i] = d.x[j * B + i] * d.D[j * B + i];
         }
     }
