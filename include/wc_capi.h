@@ -309,6 +309,21 @@ wc_status wc_ik_solve_with_jacobians_dev(wc_ik* h,
                          double* dq, double* lf_err, double* rf_err,
                          int32_t* qp_status, int32_t* nwsr, void* stream);
 
+/* HOST-pointer variants of the two entry points above (copies inside, synchronous on return):
+ * what the B=1 drop-in classes WalkingFK / WalkingQPIK_qpOASES in walking-controllers_b200/host use. */
+wc_status wc_fk_host(wc_ik* h, const double* q, const double* base_H, const uint8_t* left_is_fixed,
+                     double* lf_H, double* rf_H, double* neck_R, double* com,
+                     double* J_lf, double* J_rf, double* J_neck, double* J_com);
+wc_status wc_ik_solve_with_jacobians_host(wc_ik* h,
+                         const double* q_meas,
+                         const double* lf_H, const double* rf_H, const double* neck_R, const double* com_meas,
+                         const double* J_lf, const double* J_rf, const double* J_neck, const double* J_com,
+                         const double* lf_H_des, const double* rf_H_des,
+                         const double* lf_twist, const double* rf_twist,
+                         const double* com_pos_des, const double* com_vel_des, const double* neck_R_des,
+                         double* dq, double* lf_err, double* rf_err,
+                         int32_t* qp_status, int32_t* nwsr);
+
 int64_t wc_ik_launch_count(const wc_ik* h);
 wc_status wc_ik_enable_profiling(wc_ik* h, int32_t on);
 wc_status wc_ik_kernel_times_ms(wc_ik* h, double* ik_ms, int64_t* launches);

@@ -275,6 +275,93 @@ wc_status wc_ik_tick_host(wc_ik* h, const double* q_meas, const double* q_lin, c
     return WC_OK;
 }
 
+namespace {
+// scratch arena for the small host-pointer entry points
+struct Arena {
+    char* base = nullptr; size_t cap = 0, used = 0;
+    ~Arena() { if (base) cudaFree(base); }
+    void* take(size_t bytes) { void* p = base + used; used += (bytes + 255) / 256 * 256; return p; }
+};
+} // namespace
+
+wc_status wc_fk_host(wc_ik* h, const double* q, const double* base_H, const uint8_t* left_is_fixed,
+                     double* lf_H, double* rf_H, double* neck_R, double* com,
+                     double* J_lf, double* J_rf, double* J_neck, double* J_com)
+{
+    if (!h || !q || !base_H || !left_is_fixed) return WC_ERR_INVALID_ARG;
+    if (cudaSetDevice(h->device) != cudaSuccess) return WC_ERR_CUDA;
+    const size_t B = (size_t)h->d.B, nJ = (size_t)h->d.nJ, nV = nJ + 6;
+    const size_t rows_in[2] = {nJ, 12};
+    const double* src[2] = {q, base_H};
+    const size_t rows_out[8] = {12, 12, 9, 3, 6 * nV, 6 * nV, 6 * nV, 3 * nV};
+    double* dst[8] = {lf_H, rf_H, neck_R, com, J_lf, J_rf, J_neck, J_com};
+    Arena ar;
+    size_t total = 4096;
+    for (size_t r : rows_in) total += r * B * 8 + 256;
+    for (size_t r : rows_out) total += r * B * 8 + 256;
+    total += B + 256;
+    if (cudaMalloc(reinterpret_cast<void**>(&ar.base), total) != cudaSuccess) return WC_ERR_ALLOC;
+    ar.cap = total;
+    double* din[2]; double* dout[8];
+    for (int k = 0; k < 2; k++) {
+        din[k] = static_cast<double*>(ar.take(rows_in[k] * B * 8));
+        if (cudaMemcpy(din[k], src[k], rows_in[k] * B * 8, cudaMemcpyHostToDevice) != cudaSuccess) return WC_ERR_CUDA;
+    }
+    uint8_t* dflag = static_cast<uint8_t*>(ar.take(B));
+    if (cudaMemcpy(dflag, left_is_fixed, B, cudaMemcpyHostToDevice) != cudaSuccess) return WC_ERR_CUDA;
+    for (int k = 0; k < 8; k++) dout[k] = dst[k] ? static_cast<double*>(ar.take(rows_out[k] * B * 8)) : nullptr;
+    wc_status rc = wc_fk_dev(h, din[0], din[1], dflag, dout[0], dout[1], dout[2], dout[3], dout[4], dout[5], dout[6], dout[7], nullptr);
+    if (rc != WC_OK) return rc;
+    if (cudaDeviceSynchronize() != cudaSuccess) return WC_ERR_CUDA;
+    for (int k = 0; k < 8; k++)
+        if (dst[k] && cudaMemcpy(dst[k], dout[k], rows_out[k] * B * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return WC_ERR_CUDA;
+    return WC_OK;
+}
+
+wc_status wc_ik_solve_with_jacobians_host(wc_ik* h, const double* q_meas,
+                         const double* lf_H, const double* rf_H, const double* neck_R, const double* com_meas,
+                         const double* J_lf, const double* J_rf, const double* J_neck, const double* J_com,
+                         const double* lf_H_des, const double* rf_H_des, const double* lf_twist, const double* rf_twist,
+                         const double* com_pos_des, const double* com_vel_des, const double* neck_R_des,
+                         double* dq, double* lf_err, double* rf_err, int32_t* qp_status, int32_t* nwsr)
+{
+    if (!h || !q_meas || !lf_H || !rf_H || !neck_R || !com_meas || !J_lf || !J_rf || !J_neck || !J_com || !lf_H_des ||
+        !rf_H_des || !lf_twist || !rf_twist || !com_pos_des || !com_vel_des || !neck_R_des)
+        return WC_ERR_INVALID_ARG;
+    if (cudaSetDevice(h->device) != cudaSuccess) return WC_ERR_CUDA;
+    const size_t B = (size_t)h->d.B, nJ = (size_t)h->d.nJ, nV = nJ + 6;
+    const size_t rows_in[16] = {nJ, 12, 12, 9, 3, 6 * nV, 6 * nV, 6 * nV, 3 * nV, 12, 12, 6, 6, 3, 3, 9};
+    const double* src[16] = {q_meas, lf_H, rf_H, neck_R, com_meas, J_lf, J_rf, J_neck, J_com, lf_H_des, rf_H_des,
+                             lf_twist, rf_twist, com_pos_des, com_vel_des, neck_R_des};
+    Arena ar;
+    size_t total = 8192 + (nJ + 12) * B * 8 + 2 * B * 4 + 2048;
+    for (size_t r : rows_in) total += r * B * 8 + 256;
+    if (cudaMalloc(reinterpret_cast<void**>(&ar.base), total) != cudaSuccess) return WC_ERR_ALLOC;
+    ar.cap = total;
+    double* din[16];
+    for (int k = 0; k < 16; k++) {
+        din[k] = static_cast<double*>(ar.take(rows_in[k] * B * 8));
+        if (cudaMemcpy(din[k], src[k], rows_in[k] * B * 8, cudaMemcpyHostToDevice) != cudaSuccess) return WC_ERR_CUDA;
+    }
+    double* d_dq = static_cast<double*>(ar.take(nJ * B * 8));
+    double* d_le = static_cast<double*>(ar.take(6 * B * 8));
+    double* d_re = static_cast<double*>(ar.take(6 * B * 8));
+    int32_t* d_st = static_cast<int32_t*>(ar.take(B * 4));
+    int32_t* d_nw = static_cast<int32_t*>(ar.take(B * 4));
+    wc_status rc = wc_ik_solve_with_jacobians_dev(h, din[0], din[1], din[2], din[3], din[4], din[5], din[6], din[7], din[8],
+                                                  din[9], din[10], din[11], din[12], din[13], din[14], din[15],
+                                                  d_dq, d_le, d_re, d_st, d_nw, nullptr);
+    if (rc != WC_OK) return rc;
+    if (cudaDeviceSynchronize() != cudaSuccess) return WC_ERR_CUDA;
+    cudaError_t e = cudaSuccess;
+    if (dq && e == cudaSuccess) e = cudaMemcpy(dq, d_dq, nJ * B * 8, cudaMemcpyDeviceToHost);
+    if (lf_err && e == cudaSuccess) e = cudaMemcpy(lf_err, d_le, 6 * B * 8, cudaMemcpyDeviceToHost);
+    if (rf_err && e == cudaSuccess) e = cudaMemcpy(rf_err, d_re, 6 * B * 8, cudaMemcpyDeviceToHost);
+    if (qp_status && e == cudaSuccess) e = cudaMemcpy(qp_status, d_st, B * 4, cudaMemcpyDeviceToHost);
+    if (nwsr && e == cudaSuccess) e = cudaMemcpy(nwsr, d_nw, B * 4, cudaMemcpyDeviceToHost);
+    return e == cudaSuccess ? WC_OK : WC_ERR_CUDA;
+}
+
 wc_status wc_ik_enable_profiling(wc_ik* h, int32_t on)
 {
     if (!h) return WC_ERR_INVALID_ARG;

@@ -1,0 +1,152 @@
+// test_dropin.cpp — exercises the drop-in C++ classes exactly in the reference's per-tick call order
+// (WalkingModule::updateModule, modules/Walking_module/src/WalkingModule.cpp:601-637 and :709-745 with
+// solveQPIK :367-425) for one robot on a synthetic straight walk, and checks every tick against the CPU
+// oracle (TEST ONLY: the oracle is linked into this test binary, never into the product library).
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <deque>
+#include <vector>
+
+#include "../../oracle/wc_oracle.h"
+#include "WalkingDCMModelPredictiveController.hpp"
+#include "WalkingForwardKinematics.hpp"
+#include "WalkingQPInverseKinematics.hpp"
+
+static iDynTree::Transform planar(double x, double y, double z, double yaw)
+{
+    iDynTree::Position p; p(0) = x; p(1) = y; p(2) = z;
+    return iDynTree::Transform(iDynTree::Rotation::RotZ(yaw), p);
+}
+
+int main(int argc, char** argv)
+{
+    const int N = argc > 1 ? std::atoi(argv[1]) : 25;
+    const int T = argc > 2 ? std::atoi(argv[2]) : 200;
+    const double dT = 0.01;
+    // ---- configuration: the values of app/robots/iCubGazeboV2_5/*.ini
+    yarp::os::Searchable mpcCfg, ikCfg, fkCfg;
+    mpcCfg.put("sampling_time", dT); mpcCfg.put("controllerHorizon", N * dT); mpcCfg.put("com_height", 0.53);
+    mpcCfg.put("stateWeightTriplets", std::vector<double>{0, 0, 7500, 1, 1, 7500});
+    mpcCfg.put("inputWeightTriplets", std::vector<double>{0, 0, 9000000, 1, 1, 9000000});
+    mpcCfg.put("foot_size", std::vector<double>{-0.02, 0.05, -0.025, 0.025});
+    mpcCfg.put("initial_zmp_position", std::vector<double>{0.0, 0.0});
+    mpcCfg.put("convex_hull_tolerance", 0.05);
+    ikCfg.put("useCoMAsConstraint", 1.0);
+    ikCfg.put("neckWeightTriplets", std::vector<double>{0, 0, 5, 1, 1, 5, 2, 2, 5});
+    ikCfg.put("additional_rotation", std::vector<double>{0, 0, 1, 1, 0, 0, 0, 1, 0});
+    ikCfg.put("jointRegularization", std::vector<double>{15, 0, 0, -7, 22, 11, 30, -7, 22, 11, 30, 5.082, 0.406, -0.131, -45.249,
+                                                         -26.454, -0.351, 5.082, 0.406, -0.131, -45.249, -26.454, -0.351});
+    ikCfg.put("jointRegularizationWeights", std::vector<double>{1, 1, 1, 2, 2, 2, 2, 2, 2, 2, 2, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1});
+    ikCfg.put("jointRegularizationGains", std::vector<double>(23, 5.0));
+    ikCfg.put("k_posCom", 1.0); ikCfg.put("k_posFoot", 4.0); ikCfg.put("k_attFoot", 2.0); ikCfg.put("k_neck", 1.0);
+    fkCfg.put("left_foot_frame", std::string("l_sole"));
+
+    WalkingController controller;
+    WalkingQPIK_qpOASES ik;
+    WalkingFK fk;
+    wc_model model; wc_model_icub_like(&model);
+    iDynTree::VectorDynSize vmin(23), vmax(23);
+    for (int i = 0; i < 23; i++) { vmin(i) = -1.0; vmax(i) = 1.0; }
+    if (!controller.initialize(mpcCfg) || !ik.initialize(ikCfg, 23, vmin, vmax) || !fk.initialize(fkCfg, model)) {
+        std::fprintf(stderr, "initialisation failed\n"); return 2;
+    }
+    // ---- oracle twins
+    wc_mpc_config ocfg; wc_mpc_default_config(&ocfg, N);
+    wco_mpc* ompc = wco_mpc_create(&ocfg);
+    wc_ik_config oik; wc_ik_default_config(&oik);
+
+    // ---- synthetic straight walk: step 0.1 m every 90 ticks, 37 ticks of double support
+    const int STEP = 90, DS = 37;
+    auto foot_x = [&](int k) { return 0.05 * k; };
+    auto foot_y = [&](int k) { return (k % 2 == 0) ? 0.08 : -0.08; };
+    const double omega = std::sqrt(9.81 / 0.53);
+    auto dcm_ref = [&](int s, double* r) { // smooth path between successive footstep ZMPs
+        const int k = s / STEP; const double tau = (s % STEP) / double(STEP);
+        const double w = tau * tau * (3 - 2 * tau);
+        r[0] = foot_x(k) + 0.03 + w * (foot_x(k + 1) - foot_x(k));
+        r[1] = foot_y(k) + w * (foot_y(k + 1) - foot_y(k));
+        (void)omega;
+    };
+    std::deque<iDynTree::Vector2> dcmDeque;
+    for (int s = 0; s <= N; s++) { double r[2]; dcm_ref(s, r); iDynTree::Vector2 v; v(0) = r[0]; v(1) = r[1]; dcmDeque.push_back(v); }
+
+    iDynTree::VectorDynSize qDesired(23), dqDesired(23), qMeas(23);
+    for (int i = 0; i < 23; i++) qDesired(i) = oik.joint_reg_rad[i];
+    double worst_zmp = 0.0, worst_dq = 0.0;
+    int failures = 0;
+    for (int t = 0; t < T; t++) {
+        const int k = t / STEP, i = t % STEP;
+        const bool ds = i < DS, stanceLeft = (k % 2 == 0);
+        const double u = ds ? 0.0 : (i - DS) / double(STEP - DS), bl = u * u * (3 - 2 * u);
+        const double ox = foot_x(k - 1) + bl * (foot_x(k + 1) - foot_x(k - 1)), oz = ds ? 0.0 : 4 * 0.025 * u * (1 - u);
+        iDynTree::Transform stance = planar(foot_x(k), foot_y(k), 0, 0), other = planar(ox, foot_y(k - 1), oz, 0);
+        std::deque<iDynTree::Transform> leftTraj{stanceLeft ? stance : other}, rightTraj{stanceLeft ? other : stance};
+        std::deque<bool> leftInContact{stanceLeft || ds}, rightInContact{!stanceLeft || ds};
+        iDynTree::Vector2 measuredDCM; measuredDCM(0) = dcmDeque.front()(0) + 0.002 * std::sin(0.37 * t);
+        measuredDCM(1) = dcmDeque.front()(1) + 0.002 * std::cos(0.21 * t);
+
+        // ======== MPC block (WalkingModule.cpp:605-634)
+        iDynTree::Vector2 desiredZMP;
+        bool ok = controller.setConvexHullConstraint(leftTraj, rightTraj, leftInContact, rightInContact) &&
+                  controller.setFeedback(measuredDCM) && controller.setReferenceSignal(dcmDeque, false) && controller.solve() &&
+                  controller.getControllerOutput(desiredZMP);
+        double lfH[12], rfH[12], dcm[2] = {measuredDCM(0), measuredDCM(1)}, zo[2];
+        leftTraj.front().toH12(lfH); rightTraj.front().toH12(rfH);
+        std::vector<double> ref(2 * (N + 1));
+        for (int s = 0; s <= N; s++) { ref[2 * s] = dcmDeque[s](0); ref[2 * s + 1] = dcmDeque[s](1); }
+        int ost = 0, oit = 0;
+        const int ofl = wco_mpc_tick(ompc, lfH, rfH, leftInContact.front(), rightInContact.front(), dcm, ref.data(), 0, zo, &ost, &oit);
+        const bool ook = (ofl & ~WC_MPC_FLAG_NEW_SOLVER) == 0;
+        if (ok != ook || controller.osqpStatus() != ost || controller.osqpIterations() != oit) {
+            std::fprintf(stderr, "tick %d: MPC status mismatch (ok %d/%d status %d/%d iters %d/%d)\n", t, ok, ook, controller.osqpStatus(), ost,
+                         controller.osqpIterations(), oit);
+            failures++;
+        }
+        for (int a = 0; a < 2; a++) worst_zmp = std::fmax(worst_zmp, std::fabs(desiredZMP(a) - zo[a]) / std::fmax(1.0, std::fabs(zo[a])));
+        iDynTree::Vector2 dummy;
+        if (controller.getControllerOutput(dummy)) { std::fprintf(stderr, "tick %d: output latch did not reset\n", t); failures++; }
+
+        // ======== QP-IK block (WalkingModule.cpp:715-744, solveQPIK :367-425)
+        for (int j = 0; j < 23; j++) qMeas(j) = qDesired(j) + 0.003 * std::sin(0.1 * t + j);
+        ok = fk.evaluateWorldToBaseTransformation(leftTraj.front(), rightTraj.front(), stanceLeft) && fk.setInternalRobotState(qDesired, dqDesired);
+        iDynTree::Position comMeas; fk.getCoMPosition(comMeas);
+        iDynTree::Position comDes = comMeas; comDes(0) += 0.002; comDes(1) -= 0.001;
+        iDynTree::Vector3 comVel; comVel(0) = 0.02; comVel(1) = 0.01 * std::sin(0.05 * t); comVel(2) = 0.0;
+        iDynTree::Twist lTw, rTw; lTw.zero(); rTw.zero();
+        if (!ds) { (stanceLeft ? rTw : lTw)(0) = 0.1 / ((STEP - DS) * dT) * 6 * u * (1 - u); (stanceLeft ? rTw : lTw)(2) = 4 * 0.025 * (1 - 2 * u) / ((STEP - DS) * dT); }
+        const iDynTree::Rotation yawRotation = iDynTree::Rotation::RotZ(0.0).inverse();
+        ok = ok && ik.setRobotState(qMeas, fk.getLeftFootToWorldTransform(), fk.getRightFootToWorldTransform(), fk.getNeckOrientation(), comMeas);
+        ik.setDesiredNeckOrientation(yawRotation.inverse());
+        ik.setDesiredFeetTransformation(leftTraj.front(), rightTraj.front());
+        ik.setDesiredFeetTwist(lTw, rTw);
+        ik.setDesiredCoMVelocity(comVel);
+        ik.setDesiredCoMPosition(comDes);
+        iDynTree::MatrixDynSize jac, comJac;
+        fk.getLeftFootJacobian(jac); ok = ok && ik.setLeftFootJacobian(jac);
+        fk.getRightFootJacobian(jac); ok = ok && ik.setRightFootJacobian(jac);
+        fk.getNeckJacobian(jac); ok = ok && ik.setNeckJacobian(jac);
+        fk.getCoMJacobian(comJac); ok = ok && ik.setCoMJacobian(comJac);
+        ok = ok && ik.solve() && ik.getSolution(dqDesired);
+        // oracle
+        double bH[12], olf[12], orf[12], onR[9], ocom[3], Jl[6 * 29], Jr[6 * 29], Jn[6 * 29], Jc[3 * 29], odq[23], ole[6], ore[6];
+        (stanceLeft ? leftTraj : rightTraj).front().toH12(bH);
+        wco_fk(&model, qDesired.data(), bH, stanceLeft, olf, orf, onR, ocom, Jl, Jr, Jn, Jc);
+        double lfd[12], rfd[12]; leftTraj.front().toH12(lfd); rightTraj.front().toH12(rfd);
+        int onw = 0;
+        const int ost2 = wco_ik_solve(&oik, qMeas.data(), olf, orf, onR, comMeas.data(), Jl, Jr, Jn, Jc, lfd, rfd, lTw.data(), rTw.data(),
+                                      comDes.data(), comVel.data(), yawRotation.inverse().data(), odq, ole, ore, &onw, nullptr, nullptr,
+                                      nullptr, nullptr, nullptr);
+        if (ok != (ost2 == 0) || ik.qpStatus() != ost2) { std::fprintf(stderr, "tick %d: IK status mismatch %d/%d\n", t, ik.qpStatus(), ost2); failures++; }
+        for (int j = 0; j < 23; j++) worst_dq = std::fmax(worst_dq, std::fabs(dqDesired(j) - odq[j]));
+        for (int j = 0; j < 23; j++) qDesired(j) += dT * dqDesired(j);   // stand-in for iCub::ctrl::Integrator (:741-744)
+
+        // advanceReferenceSignals (WalkingModule.cpp:35-96)
+        dcmDeque.pop_front();
+        { double r[2]; dcm_ref(t + N + 1, r); iDynTree::Vector2 v; v(0) = r[0]; v(1) = r[1]; dcmDeque.push_back(v); }
+    }
+    wco_mpc_free(ompc);
+    std::printf("drop-in test: %d ticks, horizon %d, worst rel ZMP err %.3e, worst dq err %.3e rad/s, failures %d\n", T, N, worst_zmp,
+                worst_dq, failures);
+    return (failures == 0 && worst_zmp <= 1e-6 && worst_dq <= 1e-5) ? 0 : 1;
+}
