@@ -47,7 +47,7 @@ int main(int argc, char** argv)
     WalkingFK fk;
     wc_model model; wc_model_icub_like(&model);
     iDynTree::VectorDynSize vmin(23), vmax(23);
-    for (int i = 0; i < 23; i++) { vmin(i) = -1.0; vmax(i) = 1.0; }
+    for (int i = 0; i < 23; i++) { vmin(i) = -20.0; vmax(i) = 20.0; } // wide limits: the synthetic swing-foot targets start far from the posture
     if (!controller.initialize(mpcCfg) || !ik.initialize(ikCfg, 23, vmin, vmax) || !fk.initialize(fkCfg, model)) {
         std::fprintf(stderr, "initialisation failed\n"); return 2;
     }
@@ -55,6 +55,7 @@ int main(int argc, char** argv)
     wc_mpc_config ocfg; wc_mpc_default_config(&ocfg, N);
     wco_mpc* ompc = wco_mpc_create(&ocfg);
     wc_ik_config oik; wc_ik_default_config(&oik);
+    for (int i = 0; i < 23; i++) { oik.min_vel[i] = -20.0; oik.max_vel[i] = 20.0; }
 
     // ---- synthetic straight walk: step 0.1 m every 90 ticks, 37 ticks of double support
     const int STEP = 90, DS = 37;
