@@ -11,6 +11,17 @@ pytestmark = pytest.mark.gpu
 REL = 1e-6
 
 
+@pytest.fixture(autouse=True, params=["auto", "coop"])
+def mpc_path(request, monkeypatch):
+    """every test runs on both ADMM kernels: "auto" = chain-per-thread kernel where the horizon fits in
+    shared memory (mpc_chain.cu) else the cooperative kernel; "coop" = cooperative kernel (mpc_kernels.cu)"""
+    if request.param == "coop":
+        monkeypatch.setenv("WC_MPC_PATH", "coop")
+    else:
+        monkeypatch.delenv("WC_MPC_PATH", raising=False)
+    return request.param
+
+
 def run_both(wc, syn, oracle, cuda_device, B, T, N, seed=0x5EED, host_api=False, weights=None, noise=0.002,
              settings=None):
     g = syn.GaitBatch(B, T, N, seed=seed, noise_dcm=noise)

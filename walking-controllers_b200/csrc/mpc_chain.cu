@@ -1,0 +1,1072 @@
+// mpc_chain.cu — "chain-per-thread" variant of the batched OSQP-equivalent ADMM (K2) for short horizons.
+//
+// Same mathematics, same iterates as mpc_admm_kernel (mpc_kernels.cu; mapping to the reference in
+// mpc_kernels.cuh): OSQP's KKT solve done on the reduced system (P + sI + A' rho A) x~ = rhs, which is
+// pentadiagonal per axis plus a dense 4x4 corner on (u_0, x_0) of both axes.
+//
+// Mapping.  The ncu profile of the cooperative kernel (profiles/r1a_*) shows it is ISSUE bound: the
+// sequential triangular sweeps run on 2 of the 16 lanes of an instance, so 45 % of all warp
+// instructions execute with 4 of 32 lanes active.  Here ONE THREAD owns ONE AXIS CHAIN of one
+// instance: a warp holds 16 instances (lanes 0-15 the x axes, lanes 16-31 the y axes of the same 16
+// instances; the pair meets by shfl_xor 16 for the corner and the hull rows).  Every lane is a
+// sweeper, and because a thread walks its chain stage by stage anyway, the right-hand-side build is
+// fused into the forward sweep and the z / y / x updates into the backward sweep: one pass down, one
+// pass up per ADMM iteration, ~20x fewer warp instructions per instance-iteration.
+//
+// Shared memory: every per-thread array is lane-interleaved (element k of lane l at [k*32 + l]) so
+// all accesses are bank-conflict free and the HBM <-> shared staging is coalesced (field-major SoA
+// in HBM: consecutive instances are consecutive addresses).  Per thread (doubles):
+//   XX[nR] XU[N] iterate | QX[nR] scaled q (state block; the input block is zero except u_0) |
+//   WX[nR] WU[N] forward-sweep result | L1X L1U L2X L2U DIX DIU  pentadiagonal LDL' |
+//   YE[nR] equality duals | CM CA CB [nR] scaled rows of A
+// Per instance: HX HY UH ZH YH EH [8] hull rows.  N = 25: 385 doubles/thread -> 104.7 KB per warp,
+// two single-warp CTAs per SM.
+//
+// The LDL' factors depend only on (D, E, c, rho), which change at osqp_setup and at a rho update,
+// so they live in HBM next to the rest of the workspace (OSQP keeps its factorisation in the workspace
+// too) and are staged in with it; chain_factor runs in the setup kernel and after adapt_rho only.
+// The horizon is a template parameter for the benchmark configuration (N = 25): all shared-memory
+// offsets fold into immediates and the stage loops unroll completely, which lets ptxas hoist the
+// loads of later stages above the dependent FMA chain of the current one.
+//
+// Work distribution: instances whose OSQP workspace is new (support phase changed, ~2 %/tick) are
+// compacted into a list by K1 and equilibrated by mpc_chain_setup_kernel; phase 1 runs every
+// instance up to the first termination check; the few that have not converged are compacted again
+// and finished by phase 2.  A warp therefore never idles 15 lanes while one instance runs the Ruiz
+// passes or another 25 iterations.
+#include "mpc_kernels.cuh"
+
+#include <cmath>
+#include <cstdio>
+#include <type_traits>
+
+namespace wcb {
+
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int kIPW = 16; // instances per warp
+
+__device__ __forceinline__ double limit_scaling_c(double v)
+{
+    v = v < kMinScaling ? 1.0 : v;
+    v = v > kMaxScaling ? kMaxScaling : v;
+    return v;
+}
+
+// lane-interleaved per-thread arrays
+struct ChainSmem {
+    double* base;  // + lane
+    double* hbase; // per-instance block, + slot
+    int nR, N;
+    __device__ __forceinline__ double& at(int arr_off, int k) const { return base[(arr_off + k) * 32]; }
+    __device__ __forceinline__ double& hat(int arr, int h) const { return hbase[(arr * 8 + h) * kIPW]; }
+};
+
+// array offsets (in elements per thread) for horizon N
+struct Off {
+    int XX, XU, QX, WX, WU, L1X, L1U, L2X, L2U, DIX, DIU, YE, CM, CA, CB, total;
+    __host__ __device__ explicit Off(int N)
+    {
+        const int nR = N + 1;
+        int p = 0;
+        XX = p; p += nR; XU = p; p += N; QX = p; p += nR; WX = p; p += nR; WU = p; p += N;
+        L1X = p; p += nR; L1U = p; p += N; L2X = p; p += nR; L2U = p; p += N; DIX = p; p += nR; DIU = p; p += N;
+        YE = p; p += nR; CM = p; p += nR; CA = p; p += nR; CB = p; p += nR;
+        total = p;
+    }
+};
+enum { H_HX = 0, H_HY, H_UH, H_ZH, H_YH, H_EH, H_COUNT };
+
+// 8-byte asynchronous copy HBM -> shared (LDGSTS): no register staging, so a thread can keep its whole
+// ~340-element stage-in in flight at once (two warps per SM cannot cover HBM latency with plain loads).
+// src_bytes = 0 zero-fills the destination (cold start: x = y = z = 0).
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc, bool nonzero)
+{
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int n = nonzero ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(sa), "l"(gsrc), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all()
+{
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+}
+
+// exchanges between the two axis lanes of an instance: always under the PAIR mask, so that they are
+// legal inside branches that are uniform for the pair but not for the warp
+__device__ __forceinline__ double pair_max(double v, unsigned pm) { return fmax(v, __shfl_xor_sync(pm, v, 16)); }
+
+// dense 4x4 LDL' of the corner, order [u0x, u0y, x0x, x0y]; CF: L (6 strict-lower, row-major) + 4 Dinv
+__device__ __forceinline__ void factor_corner_c(const double* Sx, const double* Sy, double kxy, double* CF)
+{
+    double A[4][4] = {{Sx[0], kxy, Sx[1], 0.0}, {kxy, Sy[0], 0.0, Sy[1]}, {Sx[1], 0.0, Sx[2], 0.0}, {0.0, Sy[1], 0.0, Sy[2]}};
+    double L[4][4], Dv[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        double dj = A[j][j];
+#pragma unroll
+        for (int k = 0; k < j; k++) dj -= L[j][k] * L[j][k] * Dv[k];
+        Dv[j] = dj;
+#pragma unroll
+        for (int i = j + 1; i < 4; i++) {
+            double v = A[i][j];
+#pragma unroll
+            for (int k = 0; k < j; k++) v -= L[i][k] * L[j][k] * Dv[k];
+            L[i][j] = v / dj;
+        }
+    }
+    CF[0] = L[1][0]; CF[1] = L[2][0]; CF[2] = L[2][1]; CF[3] = L[3][0]; CF[4] = L[3][1]; CF[5] = L[3][2];
+    CF[6] = 1.0 / Dv[0]; CF[7] = 1.0 / Dv[1]; CF[8] = 1.0 / Dv[2]; CF[9] = 1.0 / Dv[3];
+}
+
+__device__ __forceinline__ void solve_corner_c(const double* CF, double* r)
+{
+    double t0 = r[0];
+    double t1 = r[1] - CF[0] * t0;
+    double t2 = r[2] - CF[1] * t0 - CF[2] * t1;
+    double t3 = r[3] - CF[3] * t0 - CF[4] * t1 - CF[5] * t2;
+    t0 *= CF[6]; t1 *= CF[7]; t2 *= CF[8]; t3 *= CF[9];
+    t2 -= CF[5] * t3;
+    t1 -= CF[2] * t2 + CF[4] * t3;
+    t0 -= CF[0] * t1 + CF[1] * t2 + CF[3] * t3;
+    r[0] = t0; r[1] = t1; r[2] = t2; r[3] = t3;
+}
+
+} // namespace
+
+// Pentadiagonal LDL' of one axis chain (x_N, u_{N-1}, x_{N-1}, ..., x_1) + Schur complement on its
+// (u_0, x_0) corner + the dense 4x4 corner factor, from (D, E, E_hull, c, rho) in HBM to (L1, L2, DI, CF)
+// in HBM.  Called by both lanes of an instance (pair-uniform); `write` masks the stores.
+__device__ __noinline__ void chain_factor(const MpcDev& d, int i, int a, int N, double c, double rho_now, int nh,
+                                          unsigned pmask, bool write)
+{
+    const size_t B = (size_t)d.B;
+    const int nA = 2 * N + 1, nR = N + 1;
+    const double sigma = d.st.sigma;
+    const double rho_e = kRhoEqOverIneq * rho_now;
+    const double cQ = c * d.Qd[(size_t)a * B + i], cR = c * d.Rd[(size_t)a * B + i];
+    const double* Dg = d.D + (size_t)(a * nA) * B + i;
+    const double* Eg = d.Eeq + (size_t)(a * nR) * B + i;
+    double* l1g = d.L1 + (size_t)(a * nA) * B + i;
+    double* l2g = d.L2 + (size_t)(a * nA) * B + i;
+    double* dig = d.DI + (size_t)(a * nA) * B + i;
+    const double du0 = Dg[(size_t)nR * B];
+    const double du0o = __shfl_xor_sync(pmask, du0, 16);
+    const double dux = a == 0 ? du0 : du0o, duy = a == 0 ? du0o : du0;
+    double hd = 0.0, kxy = 0.0;
+    for (int h = 0; h < nh; h++) {
+        const double e = d.Eh[(size_t)h * B + i];
+        const double hx = e * d.hullA[(size_t)(2 * h) * B + i] * dux;
+        const double hy = e * d.hullA[(size_t)(2 * h + 1) * B + i] * duy;
+        const double v = (a == 0) ? hx : hy;
+        hd += rho_now * v * v;
+        kxy += rho_now * hx * hy;
+    }
+    double Dm1 = 1.0, Dm2 = 1.0, l1m1 = 0.0, e1m1 = 0.0, e2m2 = 0.0, e2m1 = 0.0;
+    double ca_next = 0.0; // CA[k+1]
+    for (int k = N; k >= 1; k--) {
+        const double e = Eg[(size_t)k * B];
+        const double dx = Dg[(size_t)k * B];
+        const double cm = -e * dx;
+        const double ca = d.a_dyn * e * Dg[(size_t)(k - 1) * B];
+        const double cb = d.b_dyn * e * Dg[(size_t)(nR + k - 1) * B];
+        { // x_k : d, e1 (with u_{k-1}), e2 (with x_{k-1})
+            const double dj = cQ * dx * dx + sigma + rho_e * (cm * cm + (k < N ? ca_next * ca_next : 0.0));
+            const double e1j = rho_e * cm * cb, e2j = rho_e * cm * ca;
+            const double l2 = e2m2 / Dm2;
+            const double l1 = (e1m1 - l2 * Dm2 * l1m1) / Dm1;
+            const double Dj = dj - l1 * l1 * Dm1 - l2 * l2 * Dm2;
+            if (write) { l1g[(size_t)k * B] = l1; l2g[(size_t)k * B] = l2; dig[(size_t)k * B] = 1.0 / Dj; }
+            e2m2 = e2m1; e2m1 = e2j; e1m1 = e1j; Dm2 = Dm1; Dm1 = Dj; l1m1 = l1;
+        }
+        if (k >= 2) { // u_{k-1} : d, e1 (with x_{k-1}), e2 (with u_{k-2})
+            const int ku = k - 1;
+            const double du = Dg[(size_t)(nR + ku) * B];
+            const double dum = Dg[(size_t)(nR + ku - 1) * B];
+            const double sc = (ku < N - 1) ? 2.0 : 1.0;
+            const double dj = cR * sc * du * du + sigma + rho_e * cb * cb;
+            const double e1j = rho_e * ca * cb, e2j = -cR * du * dum;
+            const double l2 = e2m2 / Dm2;
+            const double l1 = (e1m1 - l2 * Dm2 * l1m1) / Dm1;
+            const double Dj = dj - l1 * l1 * Dm1 - l2 * l2 * Dm2;
+            if (write) { l1g[(size_t)(nR + ku) * B] = l1; l2g[(size_t)(nR + ku) * B] = l2; dig[(size_t)(nR + ku) * B] = 1.0 / Dj; }
+            e2m2 = e2m1; e2m1 = e2j; e1m1 = e1j; Dm2 = Dm1; Dm1 = Dj; l1m1 = l1;
+        }
+        ca_next = ca;
+    }
+    double S3[3];
+    { // corner rows: u_0 then x_0  (Dm1 = pivot of x_1, Dm2 = pivot of u_1)
+        const double e1 = Eg[(size_t)1 * B], e0 = Eg[0];
+        const double dx0 = Dg[0];
+        const double cb1 = d.b_dyn * e1 * du0, ca1 = d.a_dyn * e1 * dx0, cm0 = -e0 * dx0;
+        const double sc = (0 < N - 1) ? 2.0 : 1.0;
+        const double dj = cR * sc * du0 * du0 + sigma + rho_e * cb1 * cb1 + hd;
+        const double e1j = rho_e * ca1 * cb1; // K[u_0, x_0]
+        const double l2 = e2m2 / Dm2;
+        const double l1 = (e1m1 - l2 * Dm2 * l1m1) / Dm1;
+        S3[0] = dj - l1 * l1 * Dm1 - l2 * l2 * Dm2;   // S11
+        const double l2x = e2m1 / Dm1;                  // L[x_0, x_1]
+        S3[1] = e1j - l2x * Dm1 * l1;                   // S12
+        const double d0 = cQ * dx0 * dx0 + sigma + rho_e * (cm0 * cm0 + ca1 * ca1);
+        S3[2] = d0 - l2x * l2x * Dm1;                   // S22
+        if (write) {
+            l1g[(size_t)nR * B] = l1; l2g[(size_t)nR * B] = l2; dig[(size_t)nR * B] = 0.0;
+            l1g[0] = 0.0; l2g[0] = l2x; dig[0] = 0.0;
+        }
+    }
+    double So[3], CF[10];
+#pragma unroll
+    for (int r = 0; r < 3; r++) So[r] = __shfl_xor_sync(pmask, S3[r], 16);
+    if (a == 0) factor_corner_c(S3, So, kxy, CF);
+    else factor_corner_c(So, S3, kxy, CF);
+    if (write && a == 0) {
+#pragma unroll
+        for (int r = 0; r < 10; r++) d.CF[(size_t)r * B + i] = CF[r];
+    }
+}
+
+// =====================================================================================
+// osqp_setup -> scale_data for the instances of the setup list: Ruiz equilibration of
+// [[P, A'],[A, 0]] with cost normalisation (OSQP scaling.c), thread per axis chain.
+// P and A are never formed: their scaled entries follow from D, E, c in closed form.
+// Shared memory per thread: DX[nR] DU[N] EE[nR] FX[nR] FU[N] FE[nR] QX[nR]; per instance HX HY EH FH [8].
+// =====================================================================================
+__global__ void __launch_bounds__(32) mpc_chain_setup_kernel(MpcDev d, int smem_thread_doubles)
+{
+    extern __shared__ double smem_all[];
+    const int lane = threadIdx.x;
+    const int slot = lane & 15, a = lane >> 4;
+    const unsigned pmask = (1u << slot) | (1u << (slot + 16));
+    const int count = *d.setup_count;
+    const int li = blockIdx.x * kIPW + slot;
+    if (blockIdx.x * kIPW >= count) return;
+    const bool valid = li < count;
+    const int i = d.setup_list[valid ? li : count - 1];
+    const size_t B = (size_t)d.B;
+    const int N = d.N, nA = 2 * N + 1, nR = N + 1;
+    const wc_osqp_settings& st = d.st;
+    double* base = smem_all + lane;
+    double* hb = smem_all + (size_t)smem_thread_doubles * 32 + slot;
+    int p = 0;
+    const int oDX = p; p += nR; const int oDU = p; p += N; const int oEE = p; p += nR;
+    const int oFX = p; p += nR; const int oFU = p; p += N; const int oFE = p; p += nR; const int oQX = p; p += nR;
+#define S_(o, k) base[((o) + (k)) * 32]
+#define SH_(arr, h) hb[((arr) * 8 + (h)) * kIPW]
+    const int nh = d.nhull[i];
+    const double Qa = d.Qd[(size_t)a * B + i], Ra = d.Rd[(size_t)a * B + i];
+    const double upa = d.uprev[(size_t)a * B + i];
+    const int head = d.ring_head;
+    for (int k = 0; k < nR; k++) {
+        S_(oDX, k) = 1.0; S_(oEE, k) = 1.0;
+        const int slot_k = (head + k) % nR;
+        S_(oQX, k) = d.grad[(size_t)(a * nR + slot_k) * B + i];
+    }
+    for (int k = 0; k < N; k++) S_(oDU, k) = 1.0;
+    if (a == 0) {
+        for (int h = 0; h < kMaxHull; h++) {
+            SH_(0, h) = (h < nh) ? d.hullA[(size_t)(2 * h) * B + i] : 0.0;
+            SH_(1, h) = (h < nh) ? d.hullA[(size_t)(2 * h + 1) * B + i] : 0.0;
+            SH_(2, h) = 1.0;
+        }
+    }
+    __syncwarp();
+    const double qu0 = -(Ra * upa); // unscaled gradient of u_0 (G u_prev, MPCSolver.cpp:244-245); other inputs 0
+    const double ad = fabs(d.a_dyn), bd = fabs(d.b_dyn);
+    double c = 1.0;
+    for (int it = 0; it < st.scaling; it++) {
+        // column / row norms from the CURRENT D, E (all factors first, then applied)
+        for (int k = 0; k < nR; k++) {
+            const double dx = S_(oDX, k);
+            const double ek = S_(oEE, k);
+            double nrm = fabs(c * Qa * dx * dx);
+            nrm = fmax(nrm, ek * dx);
+            if (k < N) nrm = fmax(nrm, ad * S_(oEE, k + 1) * dx);
+            S_(oFX, k) = 1.0 / sqrt(limit_scaling_c(nrm));
+            if (k < N) {
+                const double du = S_(oDU, k);
+                const double sc = (k < N - 1) ? 2.0 : 1.0;
+                double nu = fabs(c * sc * Ra * du * du);
+                if (k >= 1) nu = fmax(nu, fabs(c * Ra * du * S_(oDU, k - 1)));
+                if (k < N - 1) nu = fmax(nu, fabs(c * Ra * du * S_(oDU, k + 1)));
+                nu = fmax(nu, bd * S_(oEE, k + 1) * du);
+                if (k == 0)
+                    for (int h = 0; h < nh; h++) nu = fmax(nu, fabs(SH_(2, h) * SH_(a, h)) * du);
+                S_(oFU, k) = 1.0 / sqrt(limit_scaling_c(nu));
+            }
+            double nr = ek * dx;
+            if (k >= 1) {
+                nr = fmax(nr, ad * ek * S_(oDX, k - 1));
+                nr = fmax(nr, bd * ek * S_(oDU, k - 1));
+            }
+            S_(oFE, k) = 1.0 / sqrt(limit_scaling_c(nr));
+        }
+        // hull rows: both axes enter the row norm
+        const double du0 = S_(oDU, 0);
+        const double du0o = __shfl_xor_sync(pmask, du0, 16);
+        const double dux = a == 0 ? du0 : du0o, duy = a == 0 ? du0o : du0;
+        if (a == 0) {
+            for (int h = 0; h < nh; h++) {
+                const double nrm = fmax(fabs(SH_(2, h) * SH_(0, h)) * dux, fabs(SH_(2, h) * SH_(1, h)) * duy);
+                SH_(3, h) = 1.0 / sqrt(limit_scaling_c(nrm));
+            }
+        }
+        __syncwarp();
+        for (int k = 0; k < nR; k++) { S_(oDX, k) *= S_(oFX, k); S_(oEE, k) *= S_(oFE, k); }
+        for (int k = 0; k < N; k++) S_(oDU, k) *= S_(oFU, k);
+        if (a == 0)
+            for (int h = 0; h < nh; h++) SH_(2, h) *= SH_(3, h);
+        __syncwarp();
+        // cost normalisation: c <- c / max(mean_j ||P_j||_inf, ||q||_inf)
+        double sum = 0.0, qn = 0.0;
+        for (int k = 0; k < nR; k++) {
+            const double dx = S_(oDX, k);
+            sum += fabs(c * Qa * dx * dx);
+            qn = fmax(qn, fabs(c * dx * S_(oQX, k)));
+            if (k < N) {
+                const double du = S_(oDU, k);
+                const double sc = (k < N - 1) ? 2.0 : 1.0;
+                double nu = fabs(c * sc * Ra * du * du);
+                if (k >= 1) nu = fmax(nu, fabs(c * Ra * du * S_(oDU, k - 1)));
+                if (k < N - 1) nu = fmax(nu, fabs(c * Ra * du * S_(oDU, k + 1)));
+                sum += nu;
+                qn = fmax(qn, fabs(c * du * (k == 0 ? qu0 : 0.0)));
+            }
+        }
+        // x axis first, then y: the same association on both lanes of the pair
+        const double so = __shfl_xor_sync(pmask, sum, 16);
+        sum = a == 0 ? sum + so : so + sum;
+        qn = pair_max(qn, pmask);
+        double c_temp = sum / (double)(2 * nA);
+        c_temp = fmax(c_temp, limit_scaling_c(qn));
+        c_temp = limit_scaling_c(c_temp);
+        c *= 1.0 / c_temp;
+    }
+    if (valid) {
+        for (int k = 0; k < nR; k++) {
+            const double dx = S_(oDX, k), e = S_(oEE, k);
+            d.D[(size_t)(a * nA + k) * B + i] = dx;
+            d.Dinv[(size_t)(a * nA + k) * B + i] = 1.0 / dx;
+            d.Eeq[(size_t)(a * nR + k) * B + i] = e;
+            d.Einv[(size_t)(a * nR + k) * B + i] = 1.0 / e;
+        }
+        for (int k = 0; k < N; k++) {
+            const double du = S_(oDU, k);
+            d.D[(size_t)(a * nA + nR + k) * B + i] = du;
+            d.Dinv[(size_t)(a * nA + nR + k) * B + i] = 1.0 / du;
+        }
+        if (a == 0) {
+            for (int h = 0; h < kMaxHull; h++) {
+                const double e = SH_(2, h);
+                d.Eh[(size_t)h * B + i] = e;
+                d.Ehinv[(size_t)h * B + i] = 1.0 / e;
+            }
+            d.cscale[i] = c;
+            d.rho[i] = fmin(fmax(st.rho, kRhoMin), kRhoMax);
+            d.inited[i] = 2; // workspace exists, cold start pending (consumed by phase 1)
+        }
+    }
+    __syncwarp();
+    // numeric factorisation of the new workspace (osqp_setup -> init_linsys_solver)
+    chain_factor(d, i, a, N, c, fmin(fmax(st.rho, kRhoMin), kRhoMax), nh, pmask, valid);
+#undef S_
+#undef SH_
+}
+
+// =====================================================================================
+// ADMM.  PHASE2 == false: all instances, iterations 1 .. first termination check.
+//        PHASE2 == true : the instances of the continuation list, until osqp_solve returns.
+// =====================================================================================
+template <bool PHASE2, int NT>
+__global__ void __launch_bounds__(32) mpc_chain_kernel(MpcDev d, MpcTickIO io)
+{
+    extern __shared__ double smem_all[];
+    const int lane = threadIdx.x;
+    const int slot = lane & 15, a = lane >> 4;
+    const unsigned pmask = (1u << slot) | (1u << (slot + 16));
+    const size_t B = (size_t)d.B;
+    const int N = NT > 0 ? NT : d.N, nA = 2 * N + 1, nR = N + 1; // NT > 0: compile-time horizon
+    const Off O(N);
+    int i;
+    bool valid;
+    if (PHASE2) {
+        const int count = *d.cont_count;
+        if (blockIdx.x * kIPW >= count) return;
+        const int li = blockIdx.x * kIPW + slot;
+        valid = li < count;
+        i = d.cont_list[valid ? li : count - 1];
+    } else {
+        if (blockIdx.x == 0 && lane == 0) *d.setup_count = 0; // consumed by the setup kernel of this tick
+        const long long ii = (long long)blockIdx.x * kIPW + slot;
+        valid = ii < (long long)d.B;
+        i = valid ? (int)ii : d.B - 1;
+    }
+    ChainSmem s{smem_all + lane, smem_all + (size_t)O.total * 32 + slot, nR, N};
+#define A_(o, k) s.at(O.o, (k))
+#define H_(arr, h) s.hat((arr), (h))
+
+    const wc_osqp_settings& st = d.st;
+    const double sigma = st.sigma, alpha = st.alpha, infty = st.infty;
+    const int kflags = d.tick_flags[i];
+    const bool skip = !valid || (kflags & (WC_MPC_FLAG_NO_CONTACT | WC_MPC_FLAG_NO_SOLVER)) != 0;
+    const int nh = skip ? 0 : d.nhull[i];
+    const double Qa = d.Qd[(size_t)a * B + i], Ra = d.Rd[(size_t)a * B + i];
+    const int init_state = d.inited[i];
+    const bool cold = !PHASE2 && !skip && init_state == 2; // new OSQP workspace: x = y = z = 0
+    const double c = d.cscale[i];
+    double rho = d.rho[i];
+    const double upa = d.uprev[(size_t)a * B + i];
+    const int head = d.ring_head;
+    const double cQ = c * Qa, cR = c * Ra;
+
+    // ------------------------------------------------------------------ stage in (all copies in flight at once)
+    auto load_factor = [&]() {
+        const double* l1 = d.L1 + (size_t)(a * nA) * B + i;
+        const double* l2 = d.L2 + (size_t)(a * nA) * B + i;
+        const double* di = d.DI + (size_t)(a * nA) * B + i;
+#pragma unroll
+        for (int k = 0; k < nR; k++) {
+            cp_async8(&A_(L1X, k), l1 + (size_t)k * B, true);
+            cp_async8(&A_(L2X, k), l2 + (size_t)k * B, true);
+            cp_async8(&A_(DIX, k), di + (size_t)k * B, true);
+            if (k < N) {
+                cp_async8(&A_(L1U, k), l1 + (size_t)(nR + k) * B, true);
+                cp_async8(&A_(L2U, k), l2 + (size_t)(nR + k) * B, true);
+                cp_async8(&A_(DIU, k), di + (size_t)(nR + k) * B, true);
+            }
+        }
+    };
+    {
+        const double* Dg = d.D + (size_t)(a * nA) * B + i;
+        const double* Eg = d.Eeq + (size_t)(a * nR) * B + i;
+        const double* xg = d.x + (size_t)(a * nA) * B + i;
+        const double* yg = d.yeq + (size_t)(a * nR) * B + i;
+        const double* gg = d.grad + (size_t)(a * nR) * B + i;
+        // raw data: E parked in CM, D in WX / WU, the unscaled gradient in QX
+#pragma unroll
+        for (int k = 0; k < nR; k++) {
+            const int slot_k = head + k < nR ? head + k : head + k - nR;
+            cp_async8(&A_(XX, k), xg + (size_t)k * B, !cold);
+            cp_async8(&A_(YE, k), yg + (size_t)k * B, !cold);
+            cp_async8(&A_(QX, k), gg + (size_t)slot_k * B, true);
+            cp_async8(&A_(CM, k), Eg + (size_t)k * B, true);
+            cp_async8(&A_(WX, k), Dg + (size_t)k * B, true);
+            if (k < N) {
+                cp_async8(&A_(XU, k), xg + (size_t)(nR + k) * B, !cold);
+                cp_async8(&A_(WU, k), Dg + (size_t)(nR + k) * B, true);
+            }
+        }
+        load_factor();
+        if (a == 0) {
+#pragma unroll
+            for (int h = 0; h < kMaxHull; h++) {
+                cp_async8(&H_(H_EH, h), d.Eh + (size_t)h * B + i, true);
+                cp_async8(&H_(H_HX, h), d.hullA + (size_t)(2 * h) * B + i, true);
+                cp_async8(&H_(H_HY, h), d.hullA + (size_t)(2 * h + 1) * B + i, true);
+                cp_async8(&H_(H_UH, h), d.hullb + (size_t)h * B + i, true);
+                cp_async8(&H_(H_YH, h), d.yh + (size_t)h * B + i, !cold);
+                cp_async8(&H_(H_ZH, h), d.zh + (size_t)h * B + i, !cold);
+            }
+        }
+    }
+    double CF[10];
+#pragma unroll
+    for (int r = 0; r < 10; r++) CF[r] = d.CF[(size_t)r * B + i];
+    const double dcm_a = io.dcm[(size_t)a * B + i];
+    const double z0_in = d.z0[(size_t)a * B + i];
+    cp_async_wait_all();
+    // scaled problem data from the raw copies: q (osqp_update_lin_cost), rows of A, bounds
+    const double dx0_scale = A_(WX, 0), du0_scale = A_(WU, 0); // D of x_0 / u_0
+    const double e0 = A_(CM, 0);
+#pragma unroll
+    for (int k = nR - 1; k >= 0; k--) {
+        const double e = A_(CM, k), dx = A_(WX, k);
+        A_(CA, k) = (k >= 1) ? d.a_dyn * e * A_(WX, k - 1) : 0.0;
+        A_(CB, k) = (k >= 1) ? d.b_dyn * e * A_(WU, k - 1) : 0.0;
+        A_(CM, k) = -e * dx;
+        A_(QX, k) = (A_(QX, k) * dx) * c;
+    }
+    const double qu0 = ((-(Ra * upa)) * du0_scale) * c; // scaled q of u_0; the other input entries are zero
+    const double du0_other = __shfl_xor_sync(pmask, du0_scale, 16);
+    if (a == 0) {
+        const double dux = du0_scale, duy = du0_other;
+#pragma unroll
+        for (int h = 0; h < kMaxHull; h++) {
+            const bool on = h < nh;
+            const double e = H_(H_EH, h);
+            H_(H_HX, h) = on ? e * H_(H_HX, h) * dux : 0.0;
+            H_(H_HY, h) = on ? e * H_(H_HY, h) * duy : 0.0;
+            H_(H_UH, h) = on ? e * H_(H_UH, h) : 0.0;
+        }
+    }
+    // equality row 0: l = u = -dcm (MPCSolver.cpp:143-146), scaled by E
+    const double lb0 = -dcm_a * e0;
+    double z0prev = (cold || PHASE2) ? (PHASE2 ? lb0 : 0.0) : z0_in;
+    __syncwarp();
+
+    // ------------------------------------------------------------------ ADMM (osqp_solve)
+    int status = WC_OSQP_UNSOLVED;
+    int iter_done = 0, rho_updates = PHASE2 ? d.rho_updates[i] : 0;
+    bool done = skip;
+    double pri_res = 0.0, dua_res = 0.0;
+    double nz_u = 0, nAx_u = 0, nq_u = 0, nAty_u = 0, nPx_u = 0;
+    double rp_s = 0, rd_s = 0, nz_s = 0, nAx_s = 0, nq_s = 0, nAty_s = 0, nPx_s = 0;
+    const double cinv = 1.0 / c;
+    double* dyg = d.dy_scratch + (size_t)(a * nR) * B + i;      // delta_y of the equality rows (checks only)
+    double* dyhg = d.dy_scratch + (size_t)(2 * nR) * B + i;     // delta_y of the hull rows
+
+    // (A' y)_j and (P x)_j of stage k for this axis; V = vector in the role of x (VX/VU array offsets),
+    // Y in the role of y (shared array offset or global pointer)
+    auto aty_hull = [&](const double* yh_glob, bool from_glob) {
+        double acc = 0.0;
+        for (int h = 0; h < nh; h++) {
+            const double hc = (a == 0) ? H_(H_HX, h) : H_(H_HY, h);
+            acc += hc * (from_glob ? yh_glob[(size_t)h * B] : H_(H_YH, h));
+        }
+        return acc;
+    };
+
+    // update_info + the norms of check_termination for the CURRENT (x, z, y)
+    auto update_info = [&]() {
+        double m_rp_u = 0, m_rp_s = 0, m_z_u = 0, m_z_s = 0, m_ax_u = 0, m_ax_s = 0;
+        double m_rd_u = 0, m_rd_s = 0, m_q_u = 0, m_q_s = 0, m_aty_u = 0, m_aty_s = 0, m_px_u = 0, m_px_s = 0;
+        const double* Dg = d.D + (size_t)(a * nA) * B + i;
+        const double* Dig = d.Dinv + (size_t)(a * nA) * B + i;
+        const double* Eig = d.Einv + (size_t)(a * nR) * B + i;
+        if (!PHASE2) {
+            // Phase 1 evaluates the residuals exactly once, after its last iteration (phase1_len is the
+            // first check / rho update / max_iter): the factor arrays are dead (a rho update reloads
+            // them), so D, Dinv, Einv land there with every copy in flight at once.
+#pragma unroll
+            for (int k = 0; k < nR; k++) {
+                cp_async8(&A_(L1X, k), Dg + (size_t)k * B, true);
+                cp_async8(&A_(L2X, k), Dig + (size_t)k * B, true);
+                cp_async8(&A_(DIX, k), Eig + (size_t)k * B, true);
+                if (k < N) {
+                    cp_async8(&A_(L1U, k), Dg + (size_t)(nR + k) * B, true);
+                    cp_async8(&A_(L2U, k), Dig + (size_t)(nR + k) * B, true);
+                }
+            }
+            cp_async_wait_all();
+        }
+        auto DXv = [&](int k) { return PHASE2 ? Dg[(size_t)k * B] : A_(L1X, k); };
+        auto DUv = [&](int k) { return PHASE2 ? Dg[(size_t)(nR + k) * B] : A_(L1U, k); };
+        auto DIXv = [&](int k) { return PHASE2 ? Dig[(size_t)k * B] : A_(L2X, k); };
+        auto DIUv = [&](int k) { return PHASE2 ? Dig[(size_t)(nR + k) * B] : A_(L2U, k); };
+        auto EIv = [&](int k) { return PHASE2 ? Eig[(size_t)k * B] : A_(DIX, k); };
+        double xx_prev = 0.0, xu_prev = 0.0;     // X of stage k-1
+        double du_m1 = 0.0, vu_m1 = 0.0;         // DU, XU of stage k-1
+        double du_k = DUv(0), vu_k = A_(XU, 0);
+#pragma unroll 2
+        for (int k = 0; k < nR; k++) {
+            const double xxk = A_(XX, k);
+            const double cm = A_(CM, k);
+            double ax = cm * xxk;
+            if (k >= 1) ax += A_(CA, k) * xx_prev + A_(CB, k) * xu_prev;
+            const double z = (k == 0) ? lb0 : 0.0;
+            const double einv = EIv(k);
+            const double r = ax - z;
+            m_rp_s = fmax(m_rp_s, fabs(r)); m_rp_u = fmax(m_rp_u, fabs(einv * r));
+            m_z_s = fmax(m_z_s, fabs(z)); m_z_u = fmax(m_z_u, fabs(einv * z));
+            m_ax_s = fmax(m_ax_s, fabs(ax)); m_ax_u = fmax(m_ax_u, fabs(einv * ax));
+            const double yk = A_(YE, k);
+            const double yk1 = (k < N) ? A_(YE, k + 1) : 0.0;
+            {
+                const double dx = DXv(k);
+                const double px_x = cQ * dx * dx * xxk;
+                const double aty_x = cm * yk + (k < N ? A_(CA, k + 1) * yk1 : 0.0);
+                const double q = A_(QX, k), dinv = DIXv(k);
+                const double rr = q + px_x + aty_x;
+                m_rd_s = fmax(m_rd_s, fabs(rr)); m_rd_u = fmax(m_rd_u, fabs(dinv * rr));
+                m_q_s = fmax(m_q_s, fabs(q)); m_q_u = fmax(m_q_u, fabs(dinv * q));
+                m_aty_s = fmax(m_aty_s, fabs(aty_x)); m_aty_u = fmax(m_aty_u, fabs(dinv * aty_x));
+                m_px_s = fmax(m_px_s, fabs(px_x)); m_px_u = fmax(m_px_u, fabs(dinv * px_x));
+            }
+            if (k < N) {
+                const double du_p1 = (k < N - 1) ? DUv(k + 1) : 0.0;
+                const double vu_p1 = (k < N - 1) ? A_(XU, k + 1) : 0.0;
+                const double sc = (k < N - 1) ? 2.0 : 1.0;
+                double t = sc * du_k * vu_k;
+                if (k >= 1) t -= du_m1 * vu_m1;
+                if (k < N - 1) t -= du_p1 * vu_p1;
+                const double px_u = cR * du_k * t;
+                double aty_u = A_(CB, k + 1) * yk1;
+                if (k == 0) aty_u += aty_hull(nullptr, false);
+                const double q = (k == 0) ? qu0 : 0.0, dinv = DIUv(k);
+                const double rr = q + px_u + aty_u;
+                m_rd_s = fmax(m_rd_s, fabs(rr)); m_rd_u = fmax(m_rd_u, fabs(dinv * rr));
+                m_q_s = fmax(m_q_s, fabs(q)); m_q_u = fmax(m_q_u, fabs(dinv * q));
+                m_aty_s = fmax(m_aty_s, fabs(aty_u)); m_aty_u = fmax(m_aty_u, fabs(dinv * aty_u));
+                m_px_s = fmax(m_px_s, fabs(px_u)); m_px_u = fmax(m_px_u, fabs(dinv * px_u));
+                xu_prev = vu_k;
+                du_m1 = du_k; vu_m1 = vu_k; du_k = du_p1; vu_k = vu_p1;
+            }
+            xx_prev = xxk;
+        }
+        // hull rows: split between the two lanes of the pair
+        {
+            const double xu0 = A_(XU, 0);
+            const double xu0o = __shfl_xor_sync(pmask, xu0, 16);
+            const double ux = a == 0 ? xu0 : xu0o, uy = a == 0 ? xu0o : xu0;
+            for (int h = a; h < nh; h += 2) {
+                const double ax = H_(H_HX, h) * ux + H_(H_HY, h) * uy;
+                const double z = H_(H_ZH, h);
+                const double einv = 1.0 / H_(H_EH, h); // = Ehinv of osqp_setup
+                const double r = ax - z;
+                m_rp_s = fmax(m_rp_s, fabs(r)); m_rp_u = fmax(m_rp_u, fabs(einv * r));
+                m_z_s = fmax(m_z_s, fabs(z)); m_z_u = fmax(m_z_u, fabs(einv * z));
+                m_ax_s = fmax(m_ax_s, fabs(ax)); m_ax_u = fmax(m_ax_u, fabs(einv * ax));
+            }
+        }
+        pri_res = pair_max(m_rp_u, pmask); rp_s = pair_max(m_rp_s, pmask);
+        nz_u = pair_max(m_z_u, pmask); nz_s = pair_max(m_z_s, pmask);
+        nAx_u = pair_max(m_ax_u, pmask); nAx_s = pair_max(m_ax_s, pmask);
+        dua_res = cinv * pair_max(m_rd_u, pmask); rd_s = pair_max(m_rd_s, pmask);
+        nq_u = cinv * pair_max(m_q_u, pmask); nq_s = pair_max(m_q_s, pmask);
+        nAty_u = cinv * pair_max(m_aty_u, pmask); nAty_s = pair_max(m_aty_s, pmask);
+        nPx_u = cinv * pair_max(m_px_u, pmask); nPx_s = pair_max(m_px_s, pmask);
+    };
+
+    // is_primal_infeasible (OSQP auxil.c) on delta_y (global scratch written by the last iteration)
+    auto primal_infeasible = [&](double eps) -> int {
+        const double* Eg = d.Eeq + (size_t)(a * nR) * B + i;
+        double nrm = 0.0, lhs = 0.0;
+        for (int k = 0; k < nR; k++) {
+            const double dy = dyg[(size_t)k * B];
+            nrm = fmax(nrm, fabs(Eg[(size_t)k * B] * dy));
+            const double bnd = (k == 0) ? lb0 : 0.0;
+            lhs += bnd * fmax(dy, 0.0) + bnd * fmin(dy, 0.0);
+        }
+        if (a == 0) {
+            // project delta_y of the hull rows on the polar of the recession cone (l = -inf -> max(dy, 0))
+            for (int h = 0; h < nh; h++) {
+                double dy = dyhg[(size_t)h * B];
+                const double e = H_(H_EH, h);
+                const double uh = H_(H_UH, h), lh = e * (-infty);
+                const bool u_inf = uh > infty * kMinScaling, l_inf = lh < -infty * kMinScaling;
+                if (u_inf) dy = l_inf ? 0.0 : fmin(dy, 0.0);
+                else if (l_inf) dy = fmax(dy, 0.0);
+                dyhg[(size_t)h * B] = dy;
+                nrm = fmax(nrm, fabs(e * dy));
+                lhs += uh * fmax(dy, 0.0) + lh * fmin(dy, 0.0);
+            }
+        }
+        nrm = pair_max(nrm, pmask);
+        {
+            const double lo = __shfl_xor_sync(pmask, lhs, 16);
+            lhs = a == 0 ? lhs + lo : lo + lhs;
+        }
+        __syncwarp();
+        int res = 0;
+        if (nrm > 1.0 / infty && lhs < -eps * nrm) {
+            const double* Dig = d.Dinv + (size_t)(a * nA) * B + i;
+            double m = 0.0;
+            for (int k = 0; k < nR; k++) {
+                const double yk = dyg[(size_t)k * B];
+                const double yk1 = (k < N) ? dyg[(size_t)(k + 1) * B] : 0.0;
+                const double aty_x = A_(CM, k) * yk + (k < N ? A_(CA, k + 1) * yk1 : 0.0);
+                m = fmax(m, fabs(aty_x * Dig[(size_t)k * B])); // note: cooperative kernel divides by D
+                if (k < N) {
+                    double aty_u = A_(CB, k + 1) * yk1;
+                    if (k == 0) aty_u += aty_hull(dyhg, true);
+                    m = fmax(m, fabs(aty_u * Dig[(size_t)(nR + k) * B]));
+                }
+            }
+            m = pair_max(m, pmask);
+            res = m < eps * nrm;
+        }
+        return res;
+    };
+    // is_dual_infeasible on delta_x (left in WX / WU by the last iteration)
+    auto dual_infeasible = [&](double eps) -> int {
+        const double* Dg = d.D + (size_t)(a * nA) * B + i;
+        const double* Dig = d.Dinv + (size_t)(a * nA) * B + i;
+        const double* Eig = d.Einv + (size_t)(a * nR) * B + i;
+        double nrm = 0.0, qdx = 0.0;
+        for (int k = 0; k < nR; k++) {
+            const double wx = A_(WX, k);
+            nrm = fmax(nrm, fabs(Dg[(size_t)k * B] * wx));
+            qdx += A_(QX, k) * wx;
+        }
+        for (int k = 0; k < N; k++) {
+            const double wu = A_(WU, k);
+            nrm = fmax(nrm, fabs(Dg[(size_t)(nR + k) * B] * wu));
+            if (k == 0) qdx += qu0 * wu;
+        }
+        nrm = pair_max(nrm, pmask);
+        {
+            const double qo = __shfl_xor_sync(pmask, qdx, 16);
+            qdx = a == 0 ? qdx + qo : qo + qdx;
+        }
+        int res = 0;
+        if (nrm > 1.0 / infty && qdx < -c * eps * nrm) {
+            double m = 0.0;
+            for (int k = 0; k < nR; k++) {
+                const double dx = Dg[(size_t)k * B];
+                const double px_x = cQ * dx * dx * A_(WX, k);
+                m = fmax(m, fabs(px_x * Dig[(size_t)k * B]));
+                if (k < N) {
+                    const double sc = (k < N - 1) ? 2.0 : 1.0;
+                    const double du = Dg[(size_t)(nR + k) * B];
+                    double t = sc * du * A_(WU, k);
+                    if (k >= 1) t -= Dg[(size_t)(nR + k - 1) * B] * A_(WU, k - 1);
+                    if (k < N - 1) t -= Dg[(size_t)(nR + k + 1) * B] * A_(WU, k + 1);
+                    const double px_u = cR * du * t;
+                    m = fmax(m, fabs(px_u * Dig[(size_t)(nR + k) * B]));
+                }
+            }
+            m = pair_max(m, pmask);
+            if (m < c * eps * nrm) {
+                int bad = 0;
+                for (int k = 0; k < nR; k++) {
+                    double ax = A_(CM, k) * A_(WX, k);
+                    if (k >= 1) ax += A_(CA, k) * A_(WX, k - 1) + A_(CB, k) * A_(WU, k - 1);
+                    ax *= Eig[(size_t)k * B];
+                    if (ax > eps * nrm || ax < -eps * nrm) bad = 1; // both bounds finite on equality rows
+                }
+                {
+                    const double wu0 = A_(WU, 0);
+                    const double wu0o = __shfl_xor_sync(pmask, wu0, 16);
+                    const double ux = a == 0 ? wu0 : wu0o, uy = a == 0 ? wu0o : wu0;
+                    for (int h = a; h < nh; h += 2) {
+                        double ax = H_(H_HX, h) * ux + H_(H_HY, h) * uy;
+                        ax *= d.Ehinv[(size_t)h * B + i];
+                        const double e = H_(H_EH, h);
+                        const double uh = H_(H_UH, h), lh = e * (-infty);
+                        if ((uh < infty * kMinScaling && ax > eps * nrm) || (lh > -infty * kMinScaling && ax < -eps * nrm)) bad = 1;
+                    }
+                }
+                bad = (int)pair_max((double)bad, pmask);
+                res = !bad;
+            }
+        }
+        return res;
+    };
+    // check_termination (OSQP auxil.c).  Called by the whole warp (the infeasibility tests contain pair
+    // shuffles); returns the status the solve stops with, or 0 to continue.  The caller applies it
+    // only to lanes that are still iterating.
+    auto check_termination = [&](int approximate) -> int {
+        double eps_abs = st.eps_abs, eps_rel = st.eps_rel, epi = st.eps_prim_inf, edi = st.eps_dual_inf;
+        const bool non_cvx = pri_res > infty || dua_res > infty;
+        if (approximate) { eps_abs *= 10; eps_rel *= 10; epi *= 10; edi *= 10; }
+        int prc = 0, drc = 0, prim_inf = 0, dual_inf = 0;
+        const double eps_prim = eps_abs + eps_rel * fmax(nz_u, nAx_u);
+        if (pri_res < eps_prim) prc = 1;
+        const double eps_dual = eps_abs + eps_rel * fmax(fmax(nq_u, nAty_u), nPx_u);
+        if (dua_res < eps_dual) drc = 1;
+        const bool live = !done && !non_cvx;
+        const bool need_pi = live && !prc, need_di = live && !drc;
+        if (__any_sync(FULL, need_pi)) { const int r = primal_infeasible(epi); if (need_pi) prim_inf = r; }
+        if (__any_sync(FULL, need_di)) { const int r = dual_infeasible(edi); if (need_di) dual_inf = r; }
+        if (non_cvx) return WC_OSQP_NON_CVX;
+        if (prc && drc) return approximate ? WC_OSQP_SOLVED_INACCURATE : WC_OSQP_SOLVED;
+        if (prim_inf) return approximate ? WC_OSQP_PRIMAL_INFEASIBLE_INACCURATE : WC_OSQP_PRIMAL_INFEASIBLE;
+        if (dual_inf) return approximate ? WC_OSQP_DUAL_INFEASIBLE_INACCURATE : WC_OSQP_DUAL_INFEASIBLE;
+        return 0;
+    };
+
+    const int max_iter = st.max_iter;
+    const int chk = st.check_termination;
+    const int rint = d.rho_interval;
+    const bool adaptive = st.adaptive_rho && rint > 0;
+    // phase 1 stops after this many iterations (first termination check); 0 = run to the end
+    int phase1_len = chk > 0 ? chk : max_iter;
+    if (adaptive && rint < phase1_len) phase1_len = rint;
+    if (phase1_len > max_iter) phase1_len = max_iter;
+    int iter = PHASE2 ? phase1_len : 0;
+    int to_check = chk ? chk - (iter % chk) : 0;
+    int to_adapt = adaptive ? rint - (iter % rint) : 0;
+    bool warp_busy = __any_sync(FULL, !done);
+    while (warp_busy) {
+        iter++;
+        const bool act = !done;
+        const double rho_e = kRhoEqOverIneq * rho;
+        const double rho_e_inv = 1.0 / rho_e, rho_inv = 1.0 / rho;
+        bool check_now = false, adapt_now = false;
+        if (chk) { if (--to_check == 0) { check_now = true; to_check = chk; } }
+        if (adaptive) { if (--to_adapt == 0) { adapt_now = true; to_adapt = rint; } }
+        const bool keep_delta = check_now || iter >= max_iter; // delta_x / delta_y feed the infeasibility tests only
+        double xt_u0 = 0.0, xt_u0o = 0.0;
+        // ---- forward: right-hand side sigma x - q + A' (rho z - y) fused with L t = rhs
+        if (act) {
+            double t1 = 0.0, t2 = 0.0; // t at the previous two chain positions
+            double w_next = 0.0, ca_next = 0.0;
+#pragma unroll
+            for (int k = N; k >= 2; k--) {
+                const double wk = rho_e * (0.0 - rho_e_inv * A_(YE, k));
+                double rx = sigma * A_(XX, k) - A_(QX, k);
+                rx += A_(CM, k) * wk;
+                if (k < N) rx += ca_next * w_next;
+                const double tx = (rx - A_(L2X, k) * t2) - A_(L1X, k) * t1;
+                A_(WX, k) = tx;
+                double ru = sigma * A_(XU, k - 1);
+                ru += A_(CB, k) * wk;
+                const double tu = (ru - A_(L2U, k - 1) * t1) - A_(L1U, k - 1) * tx;
+                A_(WU, k - 1) = tu;
+                t2 = tx; t1 = tu;
+                w_next = wk; ca_next = A_(CA, k);
+            }
+            {
+                const double w1 = rho_e * (0.0 - rho_e_inv * A_(YE, 1));
+                double rx = sigma * A_(XX, 1) - A_(QX, 1);
+                rx += A_(CM, 1) * w1;
+                if (1 < N) rx += ca_next * w_next;
+                const double tx = (rx - A_(L2X, 1) * t2) - A_(L1X, 1) * t1; // x_1
+                A_(WX, 1) = tx;
+                t2 = t1; t1 = tx;
+                // corner right-hand sides: u_0 then x_0
+                double ru = sigma * A_(XU, 0) - qu0;
+                ru += A_(CB, 1) * w1;
+                for (int h = 0; h < nh; h++) {
+                    const double hc = (a == 0) ? H_(H_HX, h) : H_(H_HY, h);
+                    ru += hc * (rho * (H_(H_ZH, h) - rho_inv * H_(H_YH, h)));
+                }
+                const double w0 = rho_e * (z0prev - rho_e_inv * A_(YE, 0));
+                double r0 = sigma * A_(XX, 0) - A_(QX, 0);
+                r0 += A_(CM, 0) * w0;
+                r0 += A_(CA, 1) * w1;
+                xt_u0 = (ru - A_(L2U, 0) * t2) - A_(L1U, 0) * t1;
+                xt_u0o = r0 - A_(L2X, 0) * t1; // reduced rhs of x_0 (parked here until the corner solve)
+            }
+        }
+        // ---- corner: dense 4x4 on [u0x, u0y, x0x, x0y], redundantly on both lanes of the pair
+        double xt_x0;
+        {
+            const double ou = __shfl_xor_sync(pmask, xt_u0, 16), ox = __shfl_xor_sync(pmask, xt_u0o, 16);
+            double r[4];
+            if (a == 0) { r[0] = xt_u0; r[1] = ou; r[2] = xt_u0o; r[3] = ox; }
+            else { r[0] = ou; r[1] = xt_u0; r[2] = ox; r[3] = xt_u0o; }
+            solve_corner_c(CF, r);
+            xt_u0 = (a == 0) ? r[0] : r[1];
+            xt_x0 = (a == 0) ? r[2] : r[3];
+            // ---- hull rows (z~ = A x~): update_z / update_y, rows split between the two lanes
+            __syncwarp(); // all reads of ZH / YH by the forward pass are done
+            if (act) {
+                for (int h = a; h < nh; h += 2) {
+                    const double zt = H_(H_HX, h) * r[0] + H_(H_HY, h) * r[1];
+                    const double zp = H_(H_ZH, h), y = H_(H_YH, h);
+                    const double zr = alpha * zt + (1.0 - alpha) * zp;
+                    double zn = zr + rho_inv * y;
+                    zn = fmax(zn, H_(H_EH, h) * (-infty));
+                    zn = fmin(zn, H_(H_UH, h));
+                    const double dy = rho * (zr - zn);
+                    H_(H_ZH, h) = zn;
+                    H_(H_YH, h) = y + dy;
+                    if (keep_delta) dyhg[(size_t)h * B] = dy;
+                }
+            }
+        }
+        // ---- backward: L' x~ = D^-1 t fused with update_y (equality rows) and update_x
+        auto backward = [&](auto keep_tag) {
+            constexpr bool KEEP = decltype(keep_tag)::value; // delta_x / delta_y wanted (checks only)
+            double a1 = xt_u0, a2 = xt_x0; // x~ at chain positions j+1, j+2
+            { // stage 0
+                const double zt = A_(CM, 0) * xt_x0;
+                const double dy = rho_e * (alpha * zt + (1.0 - alpha) * z0prev - lb0);
+                A_(YE, 0) += dy;
+                if (KEEP) dyg[0] = dy;
+                const double xp = A_(XX, 0), xn = alpha * xt_x0 + (1.0 - alpha) * xp;
+                A_(XX, 0) = xn;
+                const double up = A_(XU, 0), un = alpha * xt_u0 + (1.0 - alpha) * up;
+                A_(XU, 0) = un;
+                if (KEEP) { A_(WX, 0) = xn - xp; A_(WU, 0) = un - up; }
+            }
+            double xx_prev = xt_x0, xu_prev = xt_u0;
+#pragma unroll
+            for (int k = 1; k < N; k++) {
+                const double xx = (A_(WX, k) * A_(DIX, k) - A_(L2X, k - 1) * a2) - A_(L1U, k - 1) * a1; // x_k
+                const double xu = (A_(WU, k) * A_(DIU, k) - A_(L2U, k - 1) * a1) - A_(L1X, k) * xx;     // u_k
+                double zt = A_(CM, k) * xx;
+                zt += A_(CA, k) * xx_prev + A_(CB, k) * xu_prev;
+                const double dy = rho_e * (alpha * zt + (1.0 - alpha) * 0.0 - 0.0);
+                A_(YE, k) += dy;
+                const double xp = A_(XX, k), xn = alpha * xx + (1.0 - alpha) * xp;
+                A_(XX, k) = xn;
+                const double up = A_(XU, k), un = alpha * xu + (1.0 - alpha) * up;
+                A_(XU, k) = un;
+                if (KEEP) { dyg[(size_t)k * B] = dy; A_(WX, k) = xn - xp; A_(WU, k) = un - up; }
+                a2 = xx; a1 = xu; xx_prev = xx; xu_prev = xu;
+            }
+            {
+                const double xx = (A_(WX, N) * A_(DIX, N) - A_(L2X, N - 1) * a2) - A_(L1U, N - 1) * a1;
+                double zt = A_(CM, N) * xx;
+                zt += A_(CA, N) * xx_prev + A_(CB, N) * xu_prev;
+                const double dy = rho_e * (alpha * zt + (1.0 - alpha) * 0.0 - 0.0);
+                A_(YE, N) += dy;
+                const double xp = A_(XX, N), xn = alpha * xx + (1.0 - alpha) * xp;
+                A_(XX, N) = xn;
+                if (KEEP) { dyg[(size_t)N * B] = dy; A_(WX, N) = xn - xp; }
+            }
+            z0prev = lb0;
+            iter_done = iter;
+        };
+        if (act) {
+            if (keep_delta) backward(std::true_type{});
+            else backward(std::false_type{});
+        }
+        __syncwarp(); // hull z / y of this iteration visible to both lanes
+        // ---- termination / adaptive rho (pair-uniform decisions, warp-uniform barriers)
+        if (check_now) {
+            update_info();
+#ifdef WC_DEBUG_CHAIN
+            if (d.B == 20 && i == 4 && valid) printf("phase %d a %d iter %d pri %.6e dua %.6e rho %.3e x0 %.6e y0 %.6e zh0 %.6e yh0 %.6e\n", (int)PHASE2, a, iter, pri_res, dua_res, rho, A_(XX, 0), A_(YE, 0), H_(H_ZH, 0), H_(H_YH, 0));
+#endif
+            const int stop = check_termination(0);
+            if (act && stop) { status = stop; done = true; }
+        }
+        if (adapt_now) {
+            if (!check_now) update_info();
+            if (act && !done) {
+                // compute_rho_estimate + adapt_rho
+                const double pr = rp_s / (fmax(nz_s, nAx_s) + 1e-10);
+                const double dr = rd_s / (fmax(fmax(nq_s, nAty_s), nPx_s) + 1e-10);
+                double rn = rho * sqrt(pr / (dr + 1e-10));
+                rn = fmin(fmax(rn, kRhoMin), kRhoMax);
+                if (rn > rho * st.adaptive_rho_tolerance || rn < rho / st.adaptive_rho_tolerance) {
+                    rho = rn;
+                    rho_updates++;
+                }
+            }
+            __syncwarp();
+            // warp-uniform; pairs whose rho did not change recompute the same factors
+            chain_factor(d, i, a, N, c, rho, nh, pmask, !skip);
+            __syncwarp();
+            load_factor();
+            cp_async_wait_all();
+#pragma unroll
+            for (int r = 0; r < 10; r++) CF[r] = d.CF[(size_t)r * B + i];
+            __syncwarp();
+        }
+        if (iter >= max_iter) { // warp-uniform: osqp_solve leaves the loop
+            if (!check_now) {
+                update_info();
+                const int stop = check_termination(0);
+                if (act && !done && stop) { status = stop; done = true; }
+            }
+            {
+                const int stop = check_termination(1);
+                if (act && !done) {
+                    status = stop ? stop : WC_OSQP_MAX_ITER_REACHED;
+                    done = true;
+                }
+            }
+        }
+        if (!PHASE2 && iter >= phase1_len) break; // unfinished instances go to the continuation list
+        warp_busy = __any_sync(FULL, !done);
+    }
+    __syncwarp();
+
+    // ------------------------------------------------------------------ epilogue: store_solution + controller checks
+    const bool unfinished = !skip && !done; // phase 1 only
+    const bool has_sol = !(status == WC_OSQP_PRIMAL_INFEASIBLE || status == WC_OSQP_PRIMAL_INFEASIBLE_INACCURATE ||
+                           status == WC_OSQP_DUAL_INFEASIBLE || status == WC_OSQP_DUAL_INFEASIBLE_INACCURATE ||
+                           status == WC_OSQP_UNSOLVED || status == WC_OSQP_NON_CVX) || unfinished;
+    if (!skip) {
+        double* xg = d.x + (size_t)(a * nA) * B + i;
+        double* yg = d.yeq + (size_t)(a * nR) * B + i;
+#pragma unroll
+        for (int k = 0; k < nR; k++) {
+            xg[(size_t)k * B] = has_sol ? A_(XX, k) : 0.0;
+            yg[(size_t)k * B] = has_sol ? A_(YE, k) : 0.0;
+            if (k < N) xg[(size_t)(nR + k) * B] = has_sol ? A_(XU, k) : 0.0;
+        }
+        for (int h = a; h < kMaxHull; h += 2) {
+            d.yh[(size_t)h * B + i] = has_sol ? H_(H_YH, h) : 0.0;
+            d.zh[(size_t)h * B + i] = has_sol ? H_(H_ZH, h) : 0.0;
+        }
+        d.z0[(size_t)a * B + i] = has_sol ? z0prev : 0.0;
+    }
+    // desired ZMP of both axes on the x lane
+    const double u0_mine = A_(XU, 0) * du0_scale;
+    const double u0_other = __shfl_xor_sync(pmask, u0_mine, 16);
+    const double up_other = __shfl_xor_sync(pmask, upa, 16);
+    if (a == 0 && valid) {
+        if (unfinished) {
+            const int idx = atomicAdd(d.cont_count, 1);
+            d.cont_list[idx] = i;
+            d.rho[i] = rho;
+            d.rho_updates[i] = rho_updates;
+            if (init_state == 2) d.inited[i] = 1;
+        } else {
+            int flags = kflags;
+            double out[2] = {upa, up_other};
+            if (!skip) {
+                d.rho[i] = rho;
+                d.rho_updates[i] = rho_updates;
+                if (init_state == 2) d.inited[i] = 1;
+                if (status == WC_OSQP_SOLVED) {
+                    out[0] = u0_mine; out[1] = u0_other;
+                    d.uprev[i] = out[0]; d.uprev[B + i] = out[1];
+                    // ConvexHullProjectionConstraint::computeMargin (Controller.cpp:513-517)
+                    bool inside = true;
+                    double best = INFINITY;
+                    for (int h = 0; h < nh; h++) {
+                        const double a0 = d.hullA[(size_t)(2 * h) * B + i], a1 = d.hullA[(size_t)(2 * h + 1) * B + i];
+                        if (!(a0 * out[0] + a1 * out[1] <= d.hullb[(size_t)h * B + i])) inside = false;
+                    }
+                    for (int h = 0; h < nh; h++) {
+                        const int h1 = (h + 1) % nh;
+                        const double p0x = d.hullv[(size_t)(2 * h) * B + i], p0y = d.hullv[(size_t)(2 * h + 1) * B + i];
+                        const double p1x = d.hullv[(size_t)(2 * h1) * B + i], p1y = d.hullv[(size_t)(2 * h1 + 1) * B + i];
+                        const double dx = p1x - p0x, dy = p1y - p0y;
+                        const double len2 = dx * dx + dy * dy;
+                        double t = len2 > 0 ? ((out[0] - p0x) * dx + (out[1] - p0y) * dy) / len2 : 0.0;
+                        t = t < 0 ? 0 : (t > 1 ? 1 : t);
+                        const double ex = out[0] - (p0x + t * dx), ey = out[1] - (p0y + t * dy);
+                        best = fmin(best, sqrt(ex * ex + ey * ey));
+                    }
+                    const double margin = inside ? best : -best;
+                    if (margin < -d.hull_tol) flags |= WC_MPC_FLAG_OUTSIDE_HULL;
+                } else {
+                    flags |= WC_MPC_FLAG_NOT_SOLVED;
+                }
+            }
+            if (io.zmp) { io.zmp[i] = out[0]; io.zmp[B + i] = out[1]; }
+            if (io.status) io.status[i] = skip ? WC_OSQP_UNSOLVED : status;
+            if (io.iters) io.iters[i] = skip ? 0 : iter_done;
+            if (io.flags) io.flags[i] = flags;
+            d.tick_flags[i] = flags;
+        }
+    }
+#undef A_
+#undef H_
+}
+
+// ------------------------------------------------------------------------------------------------
+size_t mpc_chain_smem_bytes(int N)
+{
+    const Off O(N);
+    return ((size_t)O.total * 32 + (size_t)H_COUNT * 8 * kIPW) * sizeof(double);
+}
+
+static size_t mpc_chain_setup_thread_doubles(int N) { return (size_t)(4 * (N + 1) + 2 * N + (N + 1)); }
+
+bool mpc_chain_supported(int N)
+{
+    return N >= 2 && mpc_chain_smem_bytes(N) <= (size_t)mpc_admm_max_smem();
+}
+
+cudaError_t launch_mpc_chain(const MpcDev& d, const MpcTickIO& io, cudaStream_t s)
+{
+    const int N = d.N;
+    const size_t smem = mpc_chain_smem_bytes(N);
+    const size_t td = mpc_chain_setup_thread_doubles(N);
+    const size_t smem_setup = (td * 32 + 4 * 8 * kIPW) * sizeof(double);
+    cudaError_t e;
+    // (the attribute is per function and per device; setting it again is cheap)
+    auto k1 = N == 25 ? mpc_chain_kernel<false, 25> : mpc_chain_kernel<false, 0>;
+    auto k2 = N == 25 ? mpc_chain_kernel<true, 25> : mpc_chain_kernel<true, 0>;
+    e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(mpc_chain_setup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_setup);
+    if (e != cudaSuccess) return e;
+    const int blocks = (d.B + kIPW - 1) / kIPW;
+    mpc_chain_setup_kernel<<<blocks, 32, smem_setup, s>>>(d, (int)td);
+    k1<<<blocks, 32, smem, s>>>(d, io);
+    k2<<<blocks, 32, smem, s>>>(d, io);
+    return cudaGetLastError();
+}
+
+} // namespace wcb

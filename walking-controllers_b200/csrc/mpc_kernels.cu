@@ -80,6 +80,7 @@ __global__ void __launch_bounds__(128) mpc_prepare_kernel(MpcDev d, MpcTickIO io
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= d.B) return;
+    if (i == 0 && d.cont_count) *d.cont_count = 0; // consumed by phase 2 of the previous tick
     const size_t B = (size_t)d.B;
     const int N = d.N, nA = 2 * N + 1, nR = N + 1;
     const uint8_t cur = (uint8_t)((io.l_contact[i] ? 1 : 0) | (io.r_contact[i] ? 2 : 0));
@@ -108,6 +109,7 @@ __global__ void __launch_bounds__(128) mpc_prepare_kernel(MpcDev d, MpcTickIO io
     }
     if (!d.have_solver[i]) { d.tick_flags[i] = flags | WC_MPC_FLAG_NO_SOLVER; return; }
     const bool inited = d.inited[i] != 0;
+    if (!inited && d.setup_list) d.setup_list[atomicAdd(d.setup_count, 1)] = i; // osqp_setup pending
     const bool reset = io.reset ? (io.reset[i] != 0) : false;
     const double Q[2] = {d.Qd[i], d.Qd[B + i]};
     const double R[2] = {d.Rd[i], d.Rd[B + i]};

@@ -70,6 +70,19 @@ struct MpcDev {
     uint8_t* inited;     // [B] OSQP workspace exists (initSolver done)
     int32_t* rho_updates;// [B]
     int32_t* tick_flags; // [B] K1 -> K2 (WC_MPC_FLAG_*), also the tick's flag output
+    // chain-per-thread path only (mpc_chain.cu); NULL on the cooperative path
+    double* Dinv;        // [2*nA][B] 1/D  (OSQP keeps Dinv, Einv next to D, E)
+    double* Einv;        // [2*nR][B]
+    double* Ehinv;       // [8][B]
+    double* dy_scratch;  // [2*nR + 8][B] delta_y of the last iteration (infeasibility tests only)
+    double* L1;          // [2*nA][B] pentadiagonal LDL' of the reduced KKT matrix: first sub-diagonal,
+    double* L2;          // [2*nA][B]   second sub-diagonal,
+    double* DI;          // [2*nA][B]   inverse pivots (split index like x)
+    double* CF;          // [10][B]   dense 4x4 corner factor
+    int32_t* setup_list; // [B] instances whose OSQP workspace must be set up this tick (filled by K1)
+    int32_t* setup_count;// [1]
+    int32_t* cont_list;  // [B] instances that did not stop at the first termination check
+    int32_t* cont_count; // [1]
 };
 
 struct MpcTickIO {
@@ -96,5 +109,9 @@ void launch_mpc_prepare(const MpcDev& d, const MpcTickIO& io, cudaStream_t s);
 cudaError_t launch_mpc_admm(const MpcDev& d, const MpcTickIO& io, int lanes_per_instance, cudaStream_t s);
 void launch_mpc_export_primal(const MpcDev& d, double* primal_out, cudaStream_t s);
 int mpc_admm_max_smem();
+// chain-per-thread path (mpc_chain.cu): setup of new workspaces + phase 1 + phase 2, three launches
+bool mpc_chain_supported(int N);
+size_t mpc_chain_smem_bytes(int N);
+cudaError_t launch_mpc_chain(const MpcDev& d, const MpcTickIO& io, cudaStream_t s);
 
 } // namespace wcb

@@ -19,6 +19,7 @@ struct wc_mpc {
     wc_mpc_config cfg;
     int device;
     int lanes;
+    int chain; // 1: chain-per-thread ADMM path (mpc_chain.cu), 0: cooperative path (mpc_kernels.cu)
     int64_t launches;
     int64_t tick;
     std::vector<void*> allocs;
@@ -145,6 +146,29 @@ wc_status wc_mpc_create(const wc_mpc_config* cfg, int32_t B, int32_t device, wc_
     while (lanes < 32 && (size_t)stride * 8 * (32 / lanes) > (size_t)mpc_admm_max_smem()) lanes *= 2;
     if ((size_t)stride * 8 * (32 / lanes) > (size_t)mpc_admm_max_smem()) { wc_mpc_destroy(h); return WC_ERR_UNSUPPORTED; }
     h->lanes = lanes;
+    // short horizons: one thread per axis chain (16 instances per warp) when the working set of a warp
+    // fits in shared memory; WC_MPC_PATH=coop|chain overrides (tuning / tests)
+    h->chain = mpc_chain_supported(d.N) ? 1 : 0;
+    if (const char* pth = std::getenv("WC_MPC_PATH")) {
+        if (!std::strcmp(pth, "coop")) h->chain = 0;
+        else if (!std::strcmp(pth, "chain") && !mpc_chain_supported(d.N)) { wc_mpc_destroy(h); return WC_ERR_UNSUPPORTED; }
+    }
+    if (h->chain) {
+        cudaError_t e2 = cudaSuccess;
+        if (e2 == cudaSuccess) e2 = dalloc(h, &d.Dinv, 2 * nA * Bz);
+        if (e2 == cudaSuccess) e2 = dalloc(h, &d.Einv, 2 * nR * Bz);
+        if (e2 == cudaSuccess) e2 = dalloc(h, &d.Ehinv, 8 * Bz);
+        if (e2 == cudaSuccess) e2 = dalloc(h, &d.dy_scratch, (2 * nR + 8) * Bz);
+        if (e2 == cudaSuccess) e2 = dalloc(h, &d.L1, 2 * nA * Bz);
+        if (e2 == cudaSuccess) e2 = dalloc(h, &d.L2, 2 * nA * Bz);
+        if (e2 == cudaSuccess) e2 = dalloc(h, &d.DI, 2 * nA * Bz);
+        if (e2 == cudaSuccess) e2 = dalloc(h, &d.CF, 10 * Bz);
+        if (e2 == cudaSuccess) e2 = dalloc(h, &d.setup_list, Bz);
+        if (e2 == cudaSuccess) e2 = dalloc(h, &d.setup_count, 1);
+        if (e2 == cudaSuccess) e2 = dalloc(h, &d.cont_list, Bz);
+        if (e2 == cudaSuccess) e2 = dalloc(h, &d.cont_count, 1);
+        if (e2 != cudaSuccess) { wc_mpc_destroy(h); return e2 == cudaErrorMemoryAllocation ? WC_ERR_ALLOC : WC_ERR_CUDA; }
+    }
     *out = h;
     return WC_OK;
 }
@@ -213,9 +237,9 @@ wc_status wc_mpc_tick_dev(wc_mpc* h, const double* lf_H, const double* rf_H,
     launch_mpc_prepare(h->d, io, s);
     cudaError_t e = cudaGetLastError();
     if (h->profiling) cudaEventRecord(ev[1], s);
-    if (e == cudaSuccess) e = launch_mpc_admm(h->d, io, h->lanes, s);
+    if (e == cudaSuccess) e = h->chain ? launch_mpc_chain(h->d, io, s) : launch_mpc_admm(h->d, io, h->lanes, s);
     if (h->profiling) cudaEventRecord(ev[2], s);
-    h->launches += 2;
+    h->launches += h->chain ? 4 : 2;
     h->tick += 1;
     if (e != cudaSuccess) {
         std::fprintf(stderr, "[wc_mpc_tick_dev] CUDA error: %s\n", cudaGetErrorString(e));
