@@ -8,6 +8,17 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
+
+@pytest.fixture(autouse=True, params=["auto", "general"])
+def ik_path(request, monkeypatch):
+    """every test runs with the fused-tick fast path (stance-foot elimination + Woodbury/Schur solve, general
+    kernel only for the compacted remainder) and with the general null-space kernel alone"""
+    if request.param == "general":
+        monkeypatch.setenv("WC_IK_PATH", "general")
+    else:
+        monkeypatch.delenv("WC_IK_PATH", raising=False)
+    return request.param
+
 DQ_TOL = 1e-8
 
 

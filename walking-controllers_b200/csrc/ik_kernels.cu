@@ -68,6 +68,248 @@ __device__ __forceinline__ double warp_max(double v)
     return v;
 }
 
+// ---- K3: floating-base forward kinematics + the Jacobian column of this lane's QP variable ---------
+// WalkingFK::{evaluateWorldToBaseTransformation,setInternalRobotState} + the getters of
+// WalkingForwardKinematics.cpp:278-340,411-454 (iDynTree KinDynComputations restated; MIXED representation).
+// Lane l owns link l (and l + 32) for the transforms, then QP variable j = lane for the columns.
+// WL [links][12] world_H_link and MC [links][4] mass-weighted link CoMs stay in shared memory.
+template <int NV>
+__device__ __forceinline__ void fk_stage(const IkModelDev& M, const IkTickIO& io, int i, size_t B, int lane,
+                                         double* WL, double* MC, double* colLf, double* colRf, double* colN,
+                                         double* colC, double* lfH, double* rfH, double* nR, double* com, double* pBo)
+{
+    const int j = lane;
+    const int left = io.left_is_fixed[i] ? 1 : 0;
+    const int L = M.n_links;
+    const int l = lane; // link of this lane (first pass), links >= 32 in a second pass
+    for (int base = 0; base < L; base += 32) {
+        const int lk = base + l;
+        if (lk < L) {
+            double R[9], p[3];
+#pragma unroll
+            for (int k = 0; k < 9; k++) R[k] = M.joint_R[lk][k];
+#pragma unroll
+            for (int k = 0; k < 3; k++) p[k] = M.joint_p[lk][k];
+            const int dj = M.dof[lk];
+            if (dj >= 0) {
+                const double q = io.q_lin[(size_t)dj * B + i];
+                double s, c;
+                sincos(q, &s, &c);
+                const double v = 1.0 - c, x = M.axis[lk][0], y = M.axis[lk][1], z = M.axis[lk][2];
+                const double Rq[9] = {c + x * x * v, x * y * v - z * s, x * z * v + y * s,
+                                      y * x * v + z * s, c + y * y * v, y * z * v - x * s,
+                                      z * x * v - y * s, z * y * v + x * s, c + z * z * v};
+                double Rn[9];
+                mat3_mul(R, Rq, Rn);
+#pragma unroll
+                for (int k = 0; k < 9; k++) R[k] = Rn[k];
+            }
+            // local transform parked in WL; composed level by level below
+#pragma unroll
+            for (int k = 0; k < 9; k++) WL[lk * 12 + k] = R[k];
+#pragma unroll
+            for (int k = 0; k < 3; k++) WL[lk * 12 + 9 + k] = p[k];
+        }
+    }
+    __syncwarp();
+    // root_H_link by tree depth (parent[l] < l, depth known on the host)
+    for (int dep = 1; dep <= M.max_depth; dep++) {
+        for (int base = 0; base < L; base += 32) {
+            const int lk = base + l;
+            if (lk < L && M.depth[lk] == dep) {
+                const int pa = M.parent[lk];
+                double Ro[9], po[3];
+                xf_mul(WL + pa * 12, WL + pa * 12 + 9, WL + lk * 12, WL + lk * 12 + 9, Ro, po);
+#pragma unroll
+                for (int k = 0; k < 9; k++) WL[lk * 12 + k] = Ro[k];
+#pragma unroll
+                for (int k = 0; k < 3; k++) WL[lk * 12 + 9 + k] = po[k];
+            }
+        }
+        __syncwarp();
+    }
+    // link 0 holds its "joint" transform (identity for a proper root); world_H_root from the stance sole
+    const int bl = M.base_link[left];
+    double wR[9], wp[3];
+    {
+        const int fidx = left ? 0 : 1;
+        double Rs[9], ps[3];
+        xf_mul(WL + bl * 12, WL + bl * 12 + 9, M.frame_R[fidx], M.frame_p[fidx], Rs, ps); // root_H_sole
+        // inverse
+        double Ri[9], pi[3];
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+#pragma unroll
+            for (int c = 0; c < 3; c++) Ri[3 * r + c] = Rs[3 * c + r];
+#pragma unroll
+        for (int r = 0; r < 3; r++) pi[r] = -(Ri[3 * r] * ps[0] + Ri[3 * r + 1] * ps[1] + Ri[3 * r + 2] * ps[2]);
+        double bR[9], bp[3];
+        bR[0] = io.base_H[0 * B + i]; bR[1] = io.base_H[1 * B + i]; bR[2] = io.base_H[2 * B + i]; bp[0] = io.base_H[3 * B + i];
+        bR[3] = io.base_H[4 * B + i]; bR[4] = io.base_H[5 * B + i]; bR[5] = io.base_H[6 * B + i]; bp[1] = io.base_H[7 * B + i];
+        bR[6] = io.base_H[8 * B + i]; bR[7] = io.base_H[9 * B + i]; bR[8] = io.base_H[10 * B + i]; bp[2] = io.base_H[11 * B + i];
+        xf_mul(bR, bp, Ri, pi, wR, wp);
+    }
+    __syncwarp();
+    for (int base = 0; base < L; base += 32) {
+        const int lk = base + l;
+        if (lk < L) {
+            double Ro[9], po[3];
+            xf_mul(wR, wp, WL + lk * 12, WL + lk * 12 + 9, Ro, po);
+#pragma unroll
+            for (int k = 0; k < 9; k++) WL[lk * 12 + k] = Ro[k];
+#pragma unroll
+            for (int k = 0; k < 3; k++) WL[lk * 12 + 9 + k] = po[k];
+            const double m = M.mass[lk];
+#pragma unroll
+            for (int r = 0; r < 3; r++)
+                MC[lk * 4 + r] = m * (Ro[3 * r] * M.com[lk][0] + Ro[3 * r + 1] * M.com[lk][1] + Ro[3 * r + 2] * M.com[lk][2] + po[r]);
+        }
+    }
+    __syncwarp();
+    // task frames (replicated) and total first moment
+    {
+        double R[9], p[3];
+        xf_mul(WL + M.frame_link[0] * 12, WL + M.frame_link[0] * 12 + 9, M.frame_R[0], M.frame_p[0], R, p);
+        lfH[0] = R[0]; lfH[1] = R[1]; lfH[2] = R[2]; lfH[3] = p[0]; lfH[4] = R[3]; lfH[5] = R[4]; lfH[6] = R[5]; lfH[7] = p[1];
+        lfH[8] = R[6]; lfH[9] = R[7]; lfH[10] = R[8]; lfH[11] = p[2];
+        xf_mul(WL + M.frame_link[1] * 12, WL + M.frame_link[1] * 12 + 9, M.frame_R[1], M.frame_p[1], R, p);
+        rfH[0] = R[0]; rfH[1] = R[1]; rfH[2] = R[2]; rfH[3] = p[0]; rfH[4] = R[3]; rfH[5] = R[4]; rfH[6] = R[5]; rfH[7] = p[1];
+        rfH[8] = R[6]; rfH[9] = R[7]; rfH[10] = R[8]; rfH[11] = p[2];
+        mat3_mul(WL + M.frame_link[2] * 12, M.frame_R[2], nR);
+    }
+    double Mc[3] = {0, 0, 0};
+    for (int k = 0; k < L; k++) { Mc[0] += MC[k * 4]; Mc[1] += MC[k * 4 + 1]; Mc[2] += MC[k * 4 + 2]; }
+    const double Mtot = M.total_mass;
+#pragma unroll
+    for (int r = 0; r < 3; r++) com[r] = Mc[r] / Mtot;
+    const double pB[3] = {WL[bl * 12 + 9], WL[bl * 12 + 10], WL[bl * 12 + 11]};
+    const double pL[3] = {lfH[3], lfH[7], lfH[11]}, pR[3] = {rfH[3], rfH[7], rfH[11]};
+    // ---- Jacobian column of this lane (MIXED representation, WalkingForwardKinematics.cpp:31,436-454)
+    if (j < 3) {
+        colLf[j] = 1.0; colRf[j] = 1.0; colC[j] = 1.0;
+    } else if (j < 6) {
+        const int k = j - 3;
+        double e[3] = {0, 0, 0}; e[k] = 1.0;
+        double r[3], o[3];
+        r[0] = pL[0] - pB[0]; r[1] = pL[1] - pB[1]; r[2] = pL[2] - pB[2];
+        cross3(e, r, o); colLf[0] = o[0]; colLf[1] = o[1]; colLf[2] = o[2]; colLf[3 + k] = 1.0;
+        r[0] = pR[0] - pB[0]; r[1] = pR[1] - pB[1]; r[2] = pR[2] - pB[2];
+        cross3(e, r, o); colRf[0] = o[0]; colRf[1] = o[1]; colRf[2] = o[2]; colRf[3 + k] = 1.0;
+        colN[k] = 1.0;
+        r[0] = com[0] - pB[0]; r[1] = com[1] - pB[1]; r[2] = com[2] - pB[2];
+        cross3(e, r, o); colC[0] = o[0]; colC[1] = o[1]; colC[2] = o[2];
+    } else if (j < NV) {
+        const int dj = j - 6;
+        const int c = M.link_of_dof[dj];
+        const double* Rc = WL + c * 12;
+        const double o[3] = {WL[c * 12 + 9], WL[c * 12 + 10], WL[c * 12 + 11]};
+        double a[3];
+#pragma unroll
+        for (int r = 0; r < 3; r++) a[r] = Rc[3 * r] * M.axis[c][0] + Rc[3 * r + 1] * M.axis[c][1] + Rc[3 * r + 2] * M.axis[c][2];
+        double r3[3], lin[3];
+        const double sl = (double)M.s_frame[left][0][dj], sr = (double)M.s_frame[left][1][dj], sn = (double)M.s_frame[left][2][dj];
+        r3[0] = pL[0] - o[0]; r3[1] = pL[1] - o[1]; r3[2] = pL[2] - o[2];
+        cross3(a, r3, lin);
+#pragma unroll
+        for (int r = 0; r < 3; r++) { colLf[r] = sl * lin[r]; colLf[3 + r] = sl * a[r]; }
+        r3[0] = pR[0] - o[0]; r3[1] = pR[1] - o[1]; r3[2] = pR[2] - o[2];
+        cross3(a, r3, lin);
+#pragma unroll
+        for (int r = 0; r < 3; r++) { colRf[r] = sr * lin[r]; colRf[3 + r] = sr * a[r]; }
+#pragma unroll
+        for (int r = 0; r < 3; r++) colN[r] = sn * a[r];
+        // CoM: first moment of the sub-tree hanging from this joint (or of its complement when the
+        // base link sits inside that sub-tree)
+        double S[3] = {0, 0, 0};
+        const unsigned long long mask = M.sub_mask[c];
+        for (int k = 0; k < L; k++)
+            if ((mask >> k) & 1ull) { S[0] += MC[k * 4]; S[1] += MC[k * 4 + 1]; S[2] += MC[k * 4 + 2]; }
+        const double ms = M.sub_mass[c];
+        double mom[3];
+        if (!M.base_in_sub[left][dj]) {
+#pragma unroll
+            for (int r = 0; r < 3; r++) mom[r] = (S[r] - ms * o[r]) / Mtot;
+        } else {
+#pragma unroll
+            for (int r = 0; r < 3; r++) mom[r] = -((Mc[r] - S[r]) - (Mtot - ms) * o[r]) / Mtot;
+        }
+        cross3(a, mom, lin);
+#pragma unroll
+        for (int r = 0; r < 3; r++) colC[r] = lin[r];
+    }
+    __syncwarp();
+    pBo[0] = pB[0]; pBo[1] = pB[1]; pBo[2] = pB[2];
+}
+
+// ---- K3b: the vectors of the QP: equality right-hand side b (setBounds), gradient entry g_j of this
+// lane's variable (setGradientVector), regularisation weight Lambda_jj (WalkingQPIK::initializeMatrices).
+template <bool COMC>
+__device__ __forceinline__ void qp_vectors(const IkDev& d, const IkTickIO& io, int i, size_t B, int lane,
+                                           const double* lfH, const double* rfH, const double* nR,
+                                           const double* colN, const double* colC, double* bvec, double& gj, double& lam)
+{
+    const wc_ik_config& cfg = d.cfg;
+    const int j = lane;
+    const bool isjoint = j >= 6 && j < d.nJ + 6;
+    const double kpos = d.kpos ? d.kpos[i] : cfg.k_pos_foot;
+    const double katt = d.katt ? d.katt[i] : cfg.k_att_foot;
+    // equality right-hand side (setBounds, _qpOASES.cpp:216-282)
+    double Hd[12], tw[6], R[9], Rd[9], e[3];
+#pragma unroll
+    for (int f = 0; f < 2; f++) {
+        const double* src = f == 0 ? io.lf_H_des : io.rf_H_des;
+        const double* tws = f == 0 ? io.lf_twist : io.rf_twist;
+        const double* Hc = f == 0 ? lfH : rfH;
+#pragma unroll
+        for (int k = 0; k < 12; k++) Hd[k] = src[(size_t)k * B + i];
+#pragma unroll
+        for (int k = 0; k < 6; k++) tw[k] = tws[(size_t)k * B + i];
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+#pragma unroll
+            for (int c = 0; c < 3; c++) { R[3 * r + c] = Hc[4 * r + c]; Rd[3 * r + c] = Hd[4 * r + c]; }
+        rot_error(R, Rd, e);
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            bvec[6 * f + r] = tw[r] - kpos * (Hc[4 * r + 3] - Hd[4 * r + 3]);
+            bvec[6 * f + 3 + r] = tw[3 + r] - katt * e[r];
+        }
+    }
+    double cv[3];
+#pragma unroll
+    for (int r = 0; r < 3; r++) cv[r] = io.com_vel_des[(size_t)r * B + i];
+    if (COMC) {
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+            bvec[12 + r] = cv[r] - cfg.k_pos_com * (io.com_meas[(size_t)r * B + i] - io.com_pos_des[(size_t)r * B + i]);
+    } else {
+        bvec[12] = bvec[13] = bvec[14] = 0.0;
+    }
+    // gradient (setGradientVector, :155-182)
+    double Rdes[9], nd[9], en[3], We[3];
+#pragma unroll
+    for (int k = 0; k < 9; k++) nd[k] = io.neck_R_des[(size_t)k * B + i];
+    mat3_mul(nd, cfg.additional_rotation, Rdes); // setDesiredNeckOrientation (QPIK.cpp:143-146)
+    rot_error(nR, Rdes, en);
+    // W * (-k_neck e_n): with colN it gives this lane's neck term; also returned for the base elimination
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+        We[r] = cfg.neck_weight[3 * r] * (-cfg.k_neck * en[0]) + cfg.neck_weight[3 * r + 1] * (-cfg.k_neck * en[1]) +
+                cfg.neck_weight[3 * r + 2] * (-cfg.k_neck * en[2]);
+    gj = -(colN[0] * We[0] + colN[1] * We[1] + colN[2] * We[2]);
+    lam = 0.0;
+    if (isjoint) {
+        lam = cfg.joint_reg_weight[j - 6];
+        gj -= lam * (cfg.joint_reg_gain[j - 6] * (cfg.joint_reg_rad[j - 6] - io.q_meas[(size_t)(j - 6) * B + i]));
+    }
+    if (!COMC) {
+        double Wv[3];
+#pragma unroll
+        for (int r = 0; r < 3; r++) Wv[r] = cfg.com_weight[3 * r] * cv[0] + cfg.com_weight[3 * r + 1] * cv[1] + cfg.com_weight[3 * r + 2] * cv[2];
+        gj -= colC[0] * Wv[0] + colC[1] * Wv[1] + colC[2] * Wv[2];
+    }
+}
+
 // ---- Goldfarb-Idnani dual active set on the bounds, reduced space, warp-cooperative ---------------
 // Same algorithm as oracle/qpik_ref.c step 5.  Lane c <-> component c of the reduced-space vectors,
 // lane j <-> variable j for the primal point and the bound slacks; matrices live in shared memory
@@ -238,7 +480,7 @@ struct IkLayout {
 };
 
 template <int NJ, bool COMC>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) ik_kernel(IkDev d, IkTickIO io, int mode)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) ik_kernel(IkDev d, IkTickIO io, int mode, int from_list)
 {
     using LY = IkLayout<NJ, COMC>;
     constexpr int NV = LY::NV, NC = LY::NC, NZ = LY::NZ, LDA = LY::LDA, LDZ = LY::LDZ, LDL = LY::LDL;
@@ -247,8 +489,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) ik_kernel(IkDev d, IkTick
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const long long inst = (long long)blockIdx.x * kWarpsPerBlock + warp;
-    if (inst >= d.B) return; // whole warp exits together
-    const int i = (int)inst;
+    // from_list: the instances the fast path handed over (active velocity bounds, near-singular tasks)
+    if (inst >= (from_list ? (long long)*d.slow_count : (long long)d.B)) return; // whole warp exits together
+    const int i = from_list ? d.slow_list[inst] : (int)inst;
     const size_t B = (size_t)d.B;
     double* sm = smem_all + (size_t)warp * LY::TOTAL;
     double* WL = sm + LY::O_WL; double* MC = sm + LY::O_MC;
@@ -272,169 +515,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) ik_kernel(IkDev d, IkTick
 
     // this lane's Jacobian columns and the replicated frame data
     double colLf[6] = {0, 0, 0, 0, 0, 0}, colRf[6] = {0, 0, 0, 0, 0, 0}, colN[3] = {0, 0, 0}, colC[3] = {0, 0, 0};
-    double lfH[12], rfH[12], nR[9], com[3];
+    double lfH[12], rfH[12], nR[9], com[3], pBv[3] = {0, 0, 0};
 
     if (mode != IK_MODE_EXT_KIN) {
-        // ================================================================= K3: forward kinematics
-        const int left = io.left_is_fixed[i] ? 1 : 0;
-        const int L = M.n_links;
-        const int l = lane; // link of this lane (first pass), links >= 32 in a second pass
-        for (int base = 0; base < L; base += 32) {
-            const int lk = base + l;
-            if (lk < L) {
-                double R[9], p[3];
-#pragma unroll
-                for (int k = 0; k < 9; k++) R[k] = M.joint_R[lk][k];
-#pragma unroll
-                for (int k = 0; k < 3; k++) p[k] = M.joint_p[lk][k];
-                const int dj = M.dof[lk];
-                if (dj >= 0) {
-                    const double q = io.q_lin[(size_t)dj * B + i];
-                    double s, c;
-                    sincos(q, &s, &c);
-                    const double v = 1.0 - c, x = M.axis[lk][0], y = M.axis[lk][1], z = M.axis[lk][2];
-                    const double Rq[9] = {c + x * x * v, x * y * v - z * s, x * z * v + y * s,
-                                          y * x * v + z * s, c + y * y * v, y * z * v - x * s,
-                                          z * x * v - y * s, z * y * v + x * s, c + z * z * v};
-                    double Rn[9];
-                    mat3_mul(R, Rq, Rn);
-#pragma unroll
-                    for (int k = 0; k < 9; k++) R[k] = Rn[k];
-                }
-                // local transform parked in WL; composed level by level below
-#pragma unroll
-                for (int k = 0; k < 9; k++) WL[lk * 12 + k] = R[k];
-#pragma unroll
-                for (int k = 0; k < 3; k++) WL[lk * 12 + 9 + k] = p[k];
-            }
-        }
-        __syncwarp();
-        // root_H_link by tree depth (parent[l] < l, depth known on the host)
-        for (int dep = 1; dep <= M.max_depth; dep++) {
-            for (int base = 0; base < L; base += 32) {
-                const int lk = base + l;
-                if (lk < L && M.depth[lk] == dep) {
-                    const int pa = M.parent[lk];
-                    double Ro[9], po[3];
-                    xf_mul(WL + pa * 12, WL + pa * 12 + 9, WL + lk * 12, WL + lk * 12 + 9, Ro, po);
-#pragma unroll
-                    for (int k = 0; k < 9; k++) WL[lk * 12 + k] = Ro[k];
-#pragma unroll
-                    for (int k = 0; k < 3; k++) WL[lk * 12 + 9 + k] = po[k];
-                }
-            }
-            __syncwarp();
-        }
-        // link 0 holds its "joint" transform (identity for a proper root); world_H_root from the stance sole
-        const int bl = M.base_link[left];
-        double wR[9], wp[3];
-        {
-            const int fidx = left ? 0 : 1;
-            double Rs[9], ps[3];
-            xf_mul(WL + bl * 12, WL + bl * 12 + 9, M.frame_R[fidx], M.frame_p[fidx], Rs, ps); // root_H_sole
-            // inverse
-            double Ri[9], pi[3];
-#pragma unroll
-            for (int r = 0; r < 3; r++)
-#pragma unroll
-                for (int c = 0; c < 3; c++) Ri[3 * r + c] = Rs[3 * c + r];
-#pragma unroll
-            for (int r = 0; r < 3; r++) pi[r] = -(Ri[3 * r] * ps[0] + Ri[3 * r + 1] * ps[1] + Ri[3 * r + 2] * ps[2]);
-            double bR[9], bp[3];
-            bR[0] = io.base_H[0 * B + i]; bR[1] = io.base_H[1 * B + i]; bR[2] = io.base_H[2 * B + i]; bp[0] = io.base_H[3 * B + i];
-            bR[3] = io.base_H[4 * B + i]; bR[4] = io.base_H[5 * B + i]; bR[5] = io.base_H[6 * B + i]; bp[1] = io.base_H[7 * B + i];
-            bR[6] = io.base_H[8 * B + i]; bR[7] = io.base_H[9 * B + i]; bR[8] = io.base_H[10 * B + i]; bp[2] = io.base_H[11 * B + i];
-            xf_mul(bR, bp, Ri, pi, wR, wp);
-        }
-        __syncwarp();
-        for (int base = 0; base < L; base += 32) {
-            const int lk = base + l;
-            if (lk < L) {
-                double Ro[9], po[3];
-                xf_mul(wR, wp, WL + lk * 12, WL + lk * 12 + 9, Ro, po);
-#pragma unroll
-                for (int k = 0; k < 9; k++) WL[lk * 12 + k] = Ro[k];
-#pragma unroll
-                for (int k = 0; k < 3; k++) WL[lk * 12 + 9 + k] = po[k];
-                const double m = M.mass[lk];
-#pragma unroll
-                for (int r = 0; r < 3; r++)
-                    MC[lk * 4 + r] = m * (Ro[3 * r] * M.com[lk][0] + Ro[3 * r + 1] * M.com[lk][1] + Ro[3 * r + 2] * M.com[lk][2] + po[r]);
-            }
-        }
-        __syncwarp();
-        // task frames (replicated) and total first moment
-        {
-            double R[9], p[3];
-            xf_mul(WL + M.frame_link[0] * 12, WL + M.frame_link[0] * 12 + 9, M.frame_R[0], M.frame_p[0], R, p);
-            lfH[0] = R[0]; lfH[1] = R[1]; lfH[2] = R[2]; lfH[3] = p[0]; lfH[4] = R[3]; lfH[5] = R[4]; lfH[6] = R[5]; lfH[7] = p[1];
-            lfH[8] = R[6]; lfH[9] = R[7]; lfH[10] = R[8]; lfH[11] = p[2];
-            xf_mul(WL + M.frame_link[1] * 12, WL + M.frame_link[1] * 12 + 9, M.frame_R[1], M.frame_p[1], R, p);
-            rfH[0] = R[0]; rfH[1] = R[1]; rfH[2] = R[2]; rfH[3] = p[0]; rfH[4] = R[3]; rfH[5] = R[4]; rfH[6] = R[5]; rfH[7] = p[1];
-            rfH[8] = R[6]; rfH[9] = R[7]; rfH[10] = R[8]; rfH[11] = p[2];
-            mat3_mul(WL + M.frame_link[2] * 12, M.frame_R[2], nR);
-        }
-        double Mc[3] = {0, 0, 0};
-        for (int k = 0; k < L; k++) { Mc[0] += MC[k * 4]; Mc[1] += MC[k * 4 + 1]; Mc[2] += MC[k * 4 + 2]; }
-        const double Mtot = M.total_mass;
-#pragma unroll
-        for (int r = 0; r < 3; r++) com[r] = Mc[r] / Mtot;
-        const double pB[3] = {WL[bl * 12 + 9], WL[bl * 12 + 10], WL[bl * 12 + 11]};
-        const double pL[3] = {lfH[3], lfH[7], lfH[11]}, pR[3] = {rfH[3], rfH[7], rfH[11]};
-        // ---- Jacobian column of this lane (MIXED representation, WalkingForwardKinematics.cpp:31,436-454)
-        if (j < 3) {
-            colLf[j] = 1.0; colRf[j] = 1.0; colC[j] = 1.0;
-        } else if (j < 6) {
-            const int k = j - 3;
-            double e[3] = {0, 0, 0}; e[k] = 1.0;
-            double r[3], o[3];
-            r[0] = pL[0] - pB[0]; r[1] = pL[1] - pB[1]; r[2] = pL[2] - pB[2];
-            cross3(e, r, o); colLf[0] = o[0]; colLf[1] = o[1]; colLf[2] = o[2]; colLf[3 + k] = 1.0;
-            r[0] = pR[0] - pB[0]; r[1] = pR[1] - pB[1]; r[2] = pR[2] - pB[2];
-            cross3(e, r, o); colRf[0] = o[0]; colRf[1] = o[1]; colRf[2] = o[2]; colRf[3 + k] = 1.0;
-            colN[k] = 1.0;
-            r[0] = com[0] - pB[0]; r[1] = com[1] - pB[1]; r[2] = com[2] - pB[2];
-            cross3(e, r, o); colC[0] = o[0]; colC[1] = o[1]; colC[2] = o[2];
-        } else if (j < NV) {
-            const int dj = j - 6;
-            const int c = M.link_of_dof[dj];
-            const double* Rc = WL + c * 12;
-            const double o[3] = {WL[c * 12 + 9], WL[c * 12 + 10], WL[c * 12 + 11]};
-            double a[3];
-#pragma unroll
-            for (int r = 0; r < 3; r++) a[r] = Rc[3 * r] * M.axis[c][0] + Rc[3 * r + 1] * M.axis[c][1] + Rc[3 * r + 2] * M.axis[c][2];
-            double r3[3], lin[3];
-            const double sl = (double)M.s_frame[left][0][dj], sr = (double)M.s_frame[left][1][dj], sn = (double)M.s_frame[left][2][dj];
-            r3[0] = pL[0] - o[0]; r3[1] = pL[1] - o[1]; r3[2] = pL[2] - o[2];
-            cross3(a, r3, lin);
-#pragma unroll
-            for (int r = 0; r < 3; r++) { colLf[r] = sl * lin[r]; colLf[3 + r] = sl * a[r]; }
-            r3[0] = pR[0] - o[0]; r3[1] = pR[1] - o[1]; r3[2] = pR[2] - o[2];
-            cross3(a, r3, lin);
-#pragma unroll
-            for (int r = 0; r < 3; r++) { colRf[r] = sr * lin[r]; colRf[3 + r] = sr * a[r]; }
-#pragma unroll
-            for (int r = 0; r < 3; r++) colN[r] = sn * a[r];
-            // CoM: first moment of the sub-tree hanging from this joint (or of its complement when the
-            // base link sits inside that sub-tree)
-            double S[3] = {0, 0, 0};
-            const unsigned long long mask = M.sub_mask[c];
-            for (int k = 0; k < L; k++)
-                if ((mask >> k) & 1ull) { S[0] += MC[k * 4]; S[1] += MC[k * 4 + 1]; S[2] += MC[k * 4 + 2]; }
-            const double ms = M.sub_mass[c];
-            double mom[3];
-            if (!M.base_in_sub[left][dj]) {
-#pragma unroll
-                for (int r = 0; r < 3; r++) mom[r] = (S[r] - ms * o[r]) / Mtot;
-            } else {
-#pragma unroll
-                for (int r = 0; r < 3; r++) mom[r] = -((Mc[r] - S[r]) - (Mtot - ms) * o[r]) / Mtot;
-            }
-            cross3(a, mom, lin);
-#pragma unroll
-            for (int r = 0; r < 3; r++) colC[r] = lin[r];
-        }
-        __syncwarp();
+        fk_stage<NV>(M, io, i, B, lane, WL, MC, colLf, colRf, colN, colC, lfH, rfH, nR, com, pBv);
         if (mode == IK_MODE_FK_ONLY) {
             if (lane < 12) {
                 if (io.o_lf_H) io.o_lf_H[(size_t)lane * B + i] = lfH[lane];
@@ -459,7 +543,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) ik_kernel(IkDev d, IkTick
                     if (j < 3) lin[j] = 1.0;
                     else if (j < 6) {
                         double e[3] = {0, 0, 0}; e[j - 3] = 1.0;
-                        const double r[3] = {pn[0] - pB[0], pn[1] - pB[1], pn[2] - pB[2]};
+                        const double r[3] = {pn[0] - pBv[0], pn[1] - pBv[1], pn[2] - pBv[2]};
                         cross3(e, r, lin);
                     } else {
                         const int c = M.link_of_dof[j - 6];
@@ -500,63 +584,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) ik_kernel(IkDev d, IkTick
     }
 
     // ===================================================================== K3b: QP data (no dense H)
-    const double kpos = d.kpos ? d.kpos[i] : cfg.k_pos_foot;
-    const double katt = d.katt ? d.katt[i] : cfg.k_att_foot;
-    { // equality right-hand side (setBounds, _qpOASES.cpp:216-282), gradient, bounds
+    double gj, lam;
+    {
         double bvec[15];
-        double Hd[12], tw[6], R[9], Rd[9], e[3];
-#pragma unroll
-        for (int f = 0; f < 2; f++) {
-            const double* src = f == 0 ? io.lf_H_des : io.rf_H_des;
-            const double* tws = f == 0 ? io.lf_twist : io.rf_twist;
-            const double* Hc = f == 0 ? lfH : rfH;
-#pragma unroll
-            for (int k = 0; k < 12; k++) Hd[k] = src[(size_t)k * B + i];
-#pragma unroll
-            for (int k = 0; k < 6; k++) tw[k] = tws[(size_t)k * B + i];
-#pragma unroll
-            for (int r = 0; r < 3; r++)
-#pragma unroll
-                for (int c = 0; c < 3; c++) { R[3 * r + c] = Hc[4 * r + c]; Rd[3 * r + c] = Hd[4 * r + c]; }
-            rot_error(R, Rd, e);
-#pragma unroll
-            for (int r = 0; r < 3; r++) {
-                bvec[6 * f + r] = tw[r] - kpos * (Hc[4 * r + 3] - Hd[4 * r + 3]);
-                bvec[6 * f + 3 + r] = tw[3 + r] - katt * e[r];
-            }
-        }
-        double cv[3];
-#pragma unroll
-        for (int r = 0; r < 3; r++) cv[r] = io.com_vel_des[(size_t)r * B + i];
-        if (COMC) {
-#pragma unroll
-            for (int r = 0; r < 3; r++)
-                bvec[12 + r] = cv[r] - cfg.k_pos_com * (io.com_meas[(size_t)r * B + i] - io.com_pos_des[(size_t)r * B + i]);
-        } else {
-            bvec[12] = bvec[13] = bvec[14] = 0.0;
-        }
-        // gradient (setGradientVector, :155-182)
-        double Rdes[9], nd[9], en[3], We[3];
-#pragma unroll
-        for (int k = 0; k < 9; k++) nd[k] = io.neck_R_des[(size_t)k * B + i];
-        mat3_mul(nd, cfg.additional_rotation, Rdes); // setDesiredNeckOrientation (QPIK.cpp:143-146)
-        rot_error(nR, Rdes, en);
-#pragma unroll
-        for (int r = 0; r < 3; r++)
-            We[r] = cfg.neck_weight[3 * r] * (-cfg.k_neck * en[0]) + cfg.neck_weight[3 * r + 1] * (-cfg.k_neck * en[1]) +
-                    cfg.neck_weight[3 * r + 2] * (-cfg.k_neck * en[2]);
-        double gj = -(colN[0] * We[0] + colN[1] * We[1] + colN[2] * We[2]);
-        double lam = 0.0;
-        if (isjoint) {
-            lam = cfg.joint_reg_weight[j - 6];
-            gj -= lam * (cfg.joint_reg_gain[j - 6] * (cfg.joint_reg_rad[j - 6] - io.q_meas[(size_t)(j - 6) * B + i]));
-        }
-        if (!COMC) {
-            double Wv[3];
-#pragma unroll
-            for (int r = 0; r < 3; r++) Wv[r] = cfg.com_weight[3 * r] * cv[0] + cfg.com_weight[3 * r + 1] * cv[1] + cfg.com_weight[3 * r + 2] * cv[2];
-            gj -= colC[0] * Wv[0] + colC[1] * Wv[1] + colC[2] * Wv[2];
-        }
+        qp_vectors<COMC>(d, io, i, B, lane, lfH, rfH, nR, colN, colC, bvec, gj, lam);
         TS[lane] = isvar ? gj : 0.0; // g parked in TS
         if (lane < 15) {
 #pragma unroll
@@ -814,6 +845,256 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) ik_kernel(IkDev d, IkTick
     }
 }
 
+
+// =====================================================================================================
+// Fast path of the fused tick (CoM as constraint, all shipped configurations).  The kinematics is rooted
+// at the stance foot, so the stance-foot rows of A are [X_s | 0] with X_s = [[I, -S(r_s)],[0, I]]: they
+// pin the base twist, v_b = X_s^-1 b_s, in closed form.  What remains is a strictly convex QP in the
+// joint velocities only,
+//     min 1/2 dq' (Lambda + U' W U) dq + g_r' dq    s.t.  A_r dq = b_r,     A_r = [J_swing ; J_com] (9 x nJ),
+// whose Hessian is diagonal plus rank 3 (U = neck angular Jacobian): H_r^-1 follows from the Woodbury
+// identity and the multipliers from the 9x9 Schur complement A_r H_r^-1 A_r'.  This is the unique
+// minimiser of the reference QP whenever no velocity bound is active (same point qpOASES returns with
+// nWSR = 0); it needs ~5x fewer instructions than the general null-space factorisation of the 29 x 15
+// problem.  Instances whose optimum violates a velocity bound, or whose Schur complement / weights are
+// not safely positive definite, are appended to slow_list and solved by ik_kernel (null space +
+// Goldfarb-Idnani) in a second, compacted launch: every status / nWSR decision stays with that kernel.
+// =====================================================================================================
+constexpr int kFastWarps = 4;
+
+template <int NJ>
+struct IkFastLayout {
+    static constexpr int NV = NJ + 6;
+    static constexpr int KIN = WC_MAX_LINKS * 12 + WC_MAX_LINKS * 4;
+    static constexpr int O_AS = 0;                  // a_j   [9][32]
+    static constexpr int O_UT = O_AS + 9 * 32;      // u~_j  [3][32]
+    static constexpr int O_HS = O_UT + 3 * 32;      // h_j   [9][32]
+    static constexpr int O_GR = O_HS + 9 * 32;      // g_r   [32]
+    static constexpr int O_GK = O_GR + 32;          // G K   [27]
+    static constexpr int O_SS = O_GK + 28;          // S     [81]
+    static constexpr int QP = O_SS + 82;
+    static constexpr int TOTAL = ((KIN > QP ? KIN : QP) + 15) / 16 * 16 + 8;
+};
+
+template <int NJ>
+__global__ void __launch_bounds__(kFastWarps * 32, 4) ik_fast_kernel(IkDev d, IkTickIO io)
+{
+    using LY = IkFastLayout<NJ>;
+    constexpr int NV = LY::NV;
+    constexpr unsigned FULL = 0xffffffffu;
+    extern __shared__ double smem_all[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const long long inst = (long long)blockIdx.x * kFastWarps + warp;
+    if (inst >= d.B) return;
+    const int i = (int)inst;
+    const size_t B = (size_t)d.B;
+    double* sm = smem_all + (size_t)warp * LY::TOTAL;
+    double* WL = sm; double* MC = sm + WC_MAX_LINKS * 12;
+    double* AS = sm + LY::O_AS; double* UT = sm + LY::O_UT; double* HS = sm + LY::O_HS;
+    double* GR = sm + LY::O_GR; double* GK = sm + LY::O_GK; double* SS = sm + LY::O_SS;
+    const IkModelDev& M = *d.model;
+    const wc_ik_config& cfg = d.cfg;
+    const int j = lane;
+    const bool isj = j >= 6 && j < NV;
+
+    double colLf[6] = {0, 0, 0, 0, 0, 0}, colRf[6] = {0, 0, 0, 0, 0, 0}, colN[3] = {0, 0, 0}, colC[3] = {0, 0, 0};
+    double lfH[12], rfH[12], nR[9], com[3], pB[3];
+    fk_stage<NV>(M, io, i, B, lane, WL, MC, colLf, colRf, colN, colC, lfH, rfH, nR, com, pB);
+    double bvec[15], gj, lam;
+    qp_vectors<true>(d, io, i, B, lane, lfH, rfH, nR, colN, colC, bvec, gj, lam);
+    const bool left = io.left_is_fixed[i] != 0;
+
+    // ---- base twist from the stance-foot rows: v_lin + w x r_s = b_lin, w = b_ang
+    double bs[6], bw[6], a[9], u[3];
+#pragma unroll
+    for (int r = 0; r < 6; r++) {
+        bs[r] = left ? bvec[r] : bvec[6 + r];
+        bw[r] = left ? bvec[6 + r] : bvec[r];
+        a[r] = isj ? (left ? colRf[r] : colLf[r]) : 0.0;
+    }
+#pragma unroll
+    for (int r = 0; r < 3; r++) { a[6 + r] = isj ? colC[r] : 0.0; u[r] = isj ? colN[r] : 0.0; }
+    const double pS[3] = {left ? lfH[3] : rfH[3], left ? lfH[7] : rfH[7], left ? lfH[11] : rfH[11]};
+    const double pW[3] = {left ? rfH[3] : lfH[3], left ? rfH[7] : lfH[7], left ? rfH[11] : lfH[11]};
+    const double om[3] = {bs[3], bs[4], bs[5]};
+    double rS[3], rW[3], rC[3], t3[3], vlin[3];
+#pragma unroll
+    for (int r = 0; r < 3; r++) { rS[r] = pS[r] - pB[r]; rW[r] = pW[r] - pB[r]; rC[r] = com[r] - pB[r]; }
+    cross3(om, rS, t3);
+#pragma unroll
+    for (int r = 0; r < 3; r++) vlin[r] = bs[r] - t3[r];
+    double br[9];
+    cross3(om, rW, t3);
+#pragma unroll
+    for (int r = 0; r < 3; r++) { br[r] = bw[r] - (vlin[r] + t3[r]); br[3 + r] = bw[3 + r] - om[r]; }
+    cross3(om, rC, t3);
+#pragma unroll
+    for (int r = 0; r < 3; r++) br[6 + r] = bvec[12 + r] - (vlin[r] + t3[r]);
+    // reduced gradient: g_j + (H_jb v_b)_j = g_j + u_j' W w
+    const double* Wn = cfg.neck_weight;
+    double Wom[3];
+#pragma unroll
+    for (int r = 0; r < 3; r++) Wom[r] = Wn[3 * r] * om[0] + Wn[3 * r + 1] * om[1] + Wn[3 * r + 2] * om[2];
+    const double gr = isj ? gj + (u[0] * Wom[0] + u[1] * Wom[1] + u[2] * Wom[2]) : 0.0;
+    bool fallback = __any_sync(FULL, isj && !(lam > 0.0));
+    const double linv = (isj && lam > 0.0) ? 1.0 / lam : 0.0;
+    double ut[3], at[9];
+#pragma unroll
+    for (int r = 0; r < 3; r++) ut[r] = u[r] * linv;
+#pragma unroll
+    for (int r = 0; r < 9; r++) at[r] = a[r] * linv;
+    // ---- Woodbury core: C = U Lambda^-1 U' (3x3), K = (I + W C)^-1 W
+    double Cm[9];
+    Cm[0] = warp_sum(ut[0] * u[0]); Cm[1] = warp_sum(ut[0] * u[1]); Cm[2] = warp_sum(ut[0] * u[2]);
+    Cm[4] = warp_sum(ut[1] * u[1]); Cm[5] = warp_sum(ut[1] * u[2]); Cm[8] = warp_sum(ut[2] * u[2]);
+    Cm[3] = Cm[1]; Cm[6] = Cm[2]; Cm[7] = Cm[5];
+    double M3[9], K3[9];
+    mat3_mul(Wn, Cm, M3);
+    M3[0] += 1.0; M3[4] += 1.0; M3[8] += 1.0;
+    {
+        const double c00 = M3[4] * M3[8] - M3[5] * M3[7], c01 = M3[5] * M3[6] - M3[3] * M3[8], c02 = M3[3] * M3[7] - M3[4] * M3[6];
+        const double det = M3[0] * c00 + M3[1] * c01 + M3[2] * c02;
+        if (!(fabs(det) > 1e-12)) fallback = true;
+        const double id = 1.0 / det;
+        const double Mi[9] = {c00 * id, (M3[2] * M3[7] - M3[1] * M3[8]) * id, (M3[1] * M3[5] - M3[2] * M3[4]) * id,
+                              c01 * id, (M3[0] * M3[8] - M3[2] * M3[6]) * id, (M3[2] * M3[3] - M3[0] * M3[5]) * id,
+                              c02 * id, (M3[1] * M3[6] - M3[0] * M3[7]) * id, (M3[0] * M3[4] - M3[1] * M3[3]) * id};
+        mat3_mul(Mi, Wn, K3);
+    }
+    __syncwarp(); // kinematics scratch is dead
+#pragma unroll
+    for (int r = 0; r < 9; r++) AS[r * 32 + lane] = a[r];
+#pragma unroll
+    for (int r = 0; r < 3; r++) UT[r * 32 + lane] = ut[r];
+    GR[lane] = gr;
+    __syncwarp();
+    // ---- G = A_r Lambda^-1 U' (9x3), lane r < 9 owns row r, then the row of G K
+    if (lane < 9) {
+        double g0 = 0.0, g1 = 0.0, g2 = 0.0;
+        for (int jj = 6; jj < NV; jj++) {
+            const double av = AS[lane * 32 + jj];
+            g0 += av * UT[jj]; g1 += av * UT[32 + jj]; g2 += av * UT[64 + jj];
+        }
+#pragma unroll
+        for (int c = 0; c < 3; c++) GK[lane * 3 + c] = g0 * K3[c] + g1 * K3[3 + c] + g2 * K3[6 + c];
+    }
+    __syncwarp();
+    // ---- h_j = column j of A_r H_r^-1
+    double h[9];
+#pragma unroll
+    for (int r = 0; r < 9; r++) h[r] = at[r] - (GK[r * 3] * ut[0] + GK[r * 3 + 1] * ut[1] + GK[r * 3 + 2] * ut[2]);
+#pragma unroll
+    for (int r = 0; r < 9; r++) HS[r * 32 + lane] = h[r];
+    __syncwarp();
+    // ---- S = A_r H_r^-1 A_r' (upper triangle: 45 entries on 32 lanes, two rounds) and the right-hand side
+#pragma unroll
+    for (int round = 0; round < 2; round++) {
+        int e = lane + 32 * round;
+        if (e < 45) {
+            int r = 0;
+            while (e >= 9 - r) { e -= 9 - r; r++; }
+            const int c = r + e;
+            double acc = 0.0;
+            for (int jj = 6; jj < NV; jj++) acc += HS[r * 32 + jj] * AS[c * 32 + jj];
+            SS[r * 9 + c] = acc; SS[c * 9 + r] = acc;
+        }
+    }
+    double rhs = 0.0;
+    if (lane < 9) {
+        double acc = 0.0;
+        for (int jj = 6; jj < NV; jj++) acc += HS[lane * 32 + jj] * GR[jj];
+        double brl = 0.0;
+#pragma unroll
+        for (int r = 0; r < 9; r++) brl = (lane == r) ? br[r] : brl;
+        rhs = -(brl + acc);
+    }
+    __syncwarp();
+    // ---- Cholesky S = L L' (row per lane, right-looking, pivots broadcast) and S mu = rhs
+    double Mr[9];
+#pragma unroll
+    for (int c = 0; c < 9; c++) Mr[c] = (lane < 9) ? SS[lane * 9 + c] : 0.0;
+    double mmax = 0.0;
+#pragma unroll
+    for (int c = 0; c < 9; c++) if (lane == c) mmax = fabs(Mr[c]);
+    mmax = warp_max(mmax);
+    double ldinv = 1.0;
+#pragma unroll
+    for (int jc = 0; jc < 9; jc++) {
+        const double djj = __shfl_sync(FULL, Mr[jc], jc);
+        if (!(djj > 1e-10 * (mmax > 1.0 ? mmax : 1.0))) { fallback = true; break; }
+        const double piv = sqrt(djj);
+        const double pinv = 1.0 / piv;
+        const double lij = (lane == jc) ? piv : Mr[jc] * pinv;
+        if (lane == jc) ldinv = pinv;
+        if (lane >= jc) Mr[jc] = lij;
+#pragma unroll
+        for (int k = jc + 1; k < 9; k++) {
+            const double lkj = __shfl_sync(FULL, Mr[jc], k);
+            if (lane >= k) Mr[k] -= lij * lkj;
+        }
+    }
+    double nu = 0.0;
+    if (!fallback) {
+        if (lane < 9) {
+#pragma unroll
+            for (int c = 0; c < 9; c++) SS[lane * 9 + c] = (c <= lane) ? Mr[c] : 0.0; // L (for the transposed solve)
+        }
+        __syncwarp();
+        double acc = rhs;
+        double mu[9];
+#pragma unroll
+        for (int k = 0; k < 9; k++) {
+            const double sk = __shfl_sync(FULL, acc * ldinv, k);
+            if (lane > k) acc -= Mr[k] * sk;
+            if (lane == k) acc = sk;
+        }
+#pragma unroll
+        for (int k = 8; k >= 0; k--) {
+            mu[k] = __shfl_sync(FULL, acc * ldinv, k);
+            if (lane < k) acc -= SS[k * 9 + (lane < 9 ? lane : 0)] * mu[k];
+        }
+        // ---- dq = -H_r^-1 (g_r + A_r' mu)
+        double t = gr;
+#pragma unroll
+        for (int r = 0; r < 9; r++) t += a[r] * mu[r];
+        const double tt = t * linv;
+        double s3[3], ks[3];
+#pragma unroll
+        for (int r = 0; r < 3; r++) s3[r] = warp_sum(u[r] * tt);
+#pragma unroll
+        for (int r = 0; r < 3; r++) ks[r] = K3[3 * r] * s3[0] + K3[3 * r + 1] * s3[1] + K3[3 * r + 2] * s3[2];
+        nu = isj ? -(tt - (ut[0] * ks[0] + ut[1] * ks[1] + ut[2] * ks[2])) : 0.0;
+        // velocity bounds (setVelocityBounds, :23-51): same feasibility test as the general kernel
+        const double lb = isj ? cfg.min_vel[j - 6] : -DBL_MAX, ub = isj ? cfg.max_vel[j - 6] : DBL_MAX;
+        const bool viol = isj && ((lb > -kQpInf && nu < lb - kViolTol) || (ub < kQpInf && nu > ub + kViolTol));
+        if (__any_sync(FULL, viol)) fallback = true;
+    }
+    if (fallback) {
+        if (lane == 0) d.slow_list[atomicAdd(d.slow_count, 1)] = i;
+        return;
+    }
+    // ---- outputs: getSolution (:341-362), get{Left,Right}FootError (:364-401) = b - J nu
+    if (isj && io.dq) io.dq[(size_t)(j - 6) * B + i] = nu;
+    if (io.lf_err || io.rf_err) {
+        double ew[6], es[6];
+#pragma unroll
+        for (int r = 0; r < 6; r++) ew[r] = br[r] - warp_sum(a[r] * nu);
+        cross3(om, rS, t3);
+#pragma unroll
+        for (int r = 0; r < 3; r++) { es[r] = bs[r] - (vlin[r] + t3[r]); es[3 + r] = 0.0; }
+#pragma unroll
+        for (int r = 0; r < 6; r++) {
+            if (lane == r && io.lf_err) io.lf_err[(size_t)r * B + i] = left ? es[r] : ew[r];
+            if (lane == r && io.rf_err) io.rf_err[(size_t)r * B + i] = left ? ew[r] : es[r];
+        }
+    }
+    if (lane == 0) {
+        if (io.status) io.status[i] = WC_QP_SUCCESSFUL_RETURN;
+        if (io.nwsr) io.nwsr[i] = 0;
+    }
+}
+
 template <int NJ, bool COMC>
 cudaError_t launch_t(const IkDev& d, const IkTickIO& io, int mode, cudaStream_t s)
 {
@@ -822,7 +1103,19 @@ cudaError_t launch_t(const IkDev& d, const IkTickIO& io, int mode, cudaStream_t 
     cudaError_t e = cudaFuncSetAttribute(ik_kernel<NJ, COMC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int blocks = (d.B + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    ik_kernel<NJ, COMC><<<blocks, kWarpsPerBlock * 32, smem, s>>>(d, io, mode);
+    if (COMC && mode == IK_MODE_TICK && d.slow_list) {
+        // fast path for every instance, then the general kernel on the compacted remainder
+        using LF = IkFastLayout<NJ>;
+        const size_t smem_f = (size_t)LF::TOTAL * sizeof(double) * kFastWarps;
+        e = cudaFuncSetAttribute(ik_fast_kernel<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f);
+        if (e != cudaSuccess) return e;
+        e = cudaMemsetAsync(d.slow_count, 0, sizeof(int32_t), s);
+        if (e != cudaSuccess) return e;
+        ik_fast_kernel<NJ><<<(d.B + kFastWarps - 1) / kFastWarps, kFastWarps * 32, smem_f, s>>>(d, io);
+        ik_kernel<NJ, COMC><<<blocks, kWarpsPerBlock * 32, smem, s>>>(d, io, mode, 1);
+        return cudaGetLastError();
+    }
+    ik_kernel<NJ, COMC><<<blocks, kWarpsPerBlock * 32, smem, s>>>(d, io, mode, 0);
     return cudaGetLastError();
 }
 

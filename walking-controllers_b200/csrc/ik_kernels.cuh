@@ -53,6 +53,9 @@ struct IkDev {
     const IkModelDev* model; // device memory
     const double* kpos;      // [B] per-instance gains (device) or nullptr
     const double* katt;
+    // fused-tick fast path (ik_fast_kernel): instances handed over to the general kernel
+    int32_t* slow_list;      // [B] or nullptr (fast path disabled)
+    int32_t* slow_count;     // [1]
 };
 
 enum { IK_MODE_TICK = 0, IK_MODE_FK_ONLY = 1, IK_MODE_EXT_KIN = 2 };

@@ -118,6 +118,16 @@ wc_status wc_ik_create(const wc_ik_config* cfg, const wc_model* model, int32_t B
     if (cudaMalloc(&h->model_dev, sizeof(IkModelDev)) != cudaSuccess) { delete h; return WC_ERR_ALLOC; }
     if (cudaMemcpy(h->model_dev, &hm, sizeof(IkModelDev), cudaMemcpyHostToDevice) != cudaSuccess) { wc_ik_destroy(h); return WC_ERR_CUDA; }
     h->d.model = h->model_dev;
+    // fused-tick fast path (ik_fast_kernel) + compacted general solve; WC_IK_PATH=general disables it
+    {
+        const char* pth = std::getenv("WC_IK_PATH");
+        const bool fast = cfg->use_com_as_constraint && !(pth && !std::strcmp(pth, "general"));
+        if (fast) {
+            if (cudaMalloc(&h->d.slow_list, (size_t)B * sizeof(int32_t)) != cudaSuccess ||
+                cudaMalloc(&h->d.slow_count, sizeof(int32_t)) != cudaSuccess) { wc_ik_destroy(h); return WC_ERR_ALLOC; }
+            cudaMemset(h->d.slow_count, 0, sizeof(int32_t));
+        }
+    }
     *out = h;
     return WC_OK;
 }
@@ -127,6 +137,8 @@ void wc_ik_destroy(wc_ik* h)
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->model_dev) cudaFree(h->model_dev);
+    if (h->d.slow_list) cudaFree(h->d.slow_list);
+    if (h->d.slow_count) cudaFree(h->d.slow_count);
     if (h->kpos) cudaFree(h->kpos);
     if (h->katt) cudaFree(h->katt);
     if (h->pin_in) cudaFreeHost(h->pin_in);
@@ -160,7 +172,7 @@ static wc_status launch_checked(wc_ik* h, const IkTickIO& io, int mode, cudaStre
     if (h->profiling) { cudaEventCreate(&e0); cudaEventCreate(&e1); h->ev.push_back(e0); h->ev.push_back(e1); cudaEventRecord(e0, s); }
     cudaError_t e = launch_ik(h->d, io, mode, s);
     if (h->profiling) cudaEventRecord(e1, s);
-    h->launches += 1;
+    h->launches += (mode == IK_MODE_TICK && h->d.slow_list) ? 2 : 1;
     if (e != cudaSuccess) {
         std::fprintf(stderr, "[%s] CUDA error: %s\n", who, cudaGetErrorString(e));
         return WC_ERR_CUDA;
