@@ -11,7 +11,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libwc_b200.so")
+LIB_PATH = os.environ.get("WC_LIB_PATH") or os.path.join(_HERE, "libwc_b200.so")  # override: kernel-tuning sweeps only
 CSRC = os.path.join(_HERE, "csrc")
 
 WC_MAX_LINKS = 40

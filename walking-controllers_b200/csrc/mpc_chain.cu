@@ -46,6 +46,12 @@ namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int kIPW = 16; // instances per warp
+// stages per trip of the forward / backward loops: enough straight-line code for ptxas to overlap the
+// loads of later stages with the FMA chain of the current one, small enough to stay in the instruction cache
+#ifndef WC_CHAIN_UNROLL
+#define WC_CHAIN_UNROLL 6
+#endif
+constexpr int kChainUnroll = WC_CHAIN_UNROLL;
 
 __device__ __forceinline__ double limit_scaling_c(double v)
 {
@@ -791,7 +797,7 @@ __global__ void __launch_bounds__(32) mpc_chain_kernel(MpcDev d, MpcTickIO io)
         if (act) {
             double t1 = 0.0, t2 = 0.0; // t at the previous two chain positions
             double w_next = 0.0, ca_next = 0.0;
-#pragma unroll
+#pragma unroll kChainUnroll
             for (int k = N; k >= 2; k--) {
                 const double wk = rho_e * (0.0 - rho_e_inv * A_(YE, k));
                 double rx = sigma * A_(XX, k) - A_(QX, k);
@@ -872,7 +878,7 @@ __global__ void __launch_bounds__(32) mpc_chain_kernel(MpcDev d, MpcTickIO io)
                 if (KEEP) { A_(WX, 0) = xn - xp; A_(WU, 0) = un - up; }
             }
             double xx_prev = xt_x0, xu_prev = xt_u0;
-#pragma unroll
+#pragma unroll kChainUnroll
             for (int k = 1; k < N; k++) {
                 const double xx = (A_(WX, k) * A_(DIX, k) - A_(L2X, k - 1) * a2) - A_(L1U, k - 1) * a1; // x_k
                 const double xu = (A_(WU, k) * A_(DIU, k) - A_(L2U, k - 1) * a1) - A_(L1X, k) * xx;     // u_k
@@ -908,9 +914,6 @@ __global__ void __launch_bounds__(32) mpc_chain_kernel(MpcDev d, MpcTickIO io)
         // ---- termination / adaptive rho (pair-uniform decisions, warp-uniform barriers)
         if (check_now) {
             update_info();
-#ifdef WC_DEBUG_CHAIN
-            if (d.B == 20 && i == 4 && valid) printf("phase %d a %d iter %d pri %.6e dua %.6e rho %.3e x0 %.6e y0 %.6e zh0 %.6e yh0 %.6e\n", (int)PHASE2, a, iter, pri_res, dua_res, rho, A_(XX, 0), A_(YE, 0), H_(H_ZH, 0), H_(H_YH, 0));
-#endif
             const int stop = check_termination(0);
             if (act && stop) { status = stop; done = true; }
         }
