@@ -145,19 +145,22 @@ __device__ __forceinline__ void solve_corner_c(const double* CF, double* r)
 // (u_0, x_0) corner + the dense 4x4 corner factor, from (D, E, E_hull, c, rho) in HBM to (L1, L2, DI, CF)
 // in HBM.  Called by both lanes of an instance (pair-uniform); `write` masks the stores.
 __device__ __noinline__ void chain_factor(const MpcDev& d, int i, int a, int N, double c, double rho_now, int nh,
-                                          unsigned pmask, bool write)
+                                          unsigned pmask, bool write, const double* Dsrc = nullptr,
+                                          const double* Esrc = nullptr)
 {
     const size_t B = (size_t)d.B;
     const int nA = 2 * N + 1, nR = N + 1;
     const double sigma = d.st.sigma;
     const double rho_e = kRhoEqOverIneq * rho_now;
     const double cQ = c * d.Qd[(size_t)a * B + i], cR = c * d.Rd[(size_t)a * B + i];
-    const double* Dg = d.D + (size_t)(a * nA) * B + i;
-    const double* Eg = d.Eeq + (size_t)(a * nR) * B + i;
+    // D, E of this axis: HBM (stride B) or, in the setup kernel, the shared-memory copy (stride 1)
+    const size_t sB = Dsrc ? (size_t)1 : B;
+    const double* Dg = Dsrc ? Dsrc : d.D + (size_t)(a * nA) * B + i;
+    const double* Eg = Esrc ? Esrc : d.Eeq + (size_t)(a * nR) * B + i;
     double* l1g = d.L1 + (size_t)(a * nA) * B + i;
     double* l2g = d.L2 + (size_t)(a * nA) * B + i;
     double* dig = d.DI + (size_t)(a * nA) * B + i;
-    const double du0 = Dg[(size_t)nR * B];
+    const double du0 = Dg[(size_t)(nR) * sB];
     const double du0o = __shfl_xor_sync(pmask, du0, 16);
     const double dux = a == 0 ? du0 : du0o, duy = a == 0 ? du0o : du0;
     double hd = 0.0, kxy = 0.0;
@@ -172,11 +175,11 @@ __device__ __noinline__ void chain_factor(const MpcDev& d, int i, int a, int N, 
     double Dm1 = 1.0, Dm2 = 1.0, l1m1 = 0.0, e1m1 = 0.0, e2m2 = 0.0, e2m1 = 0.0;
     double ca_next = 0.0; // CA[k+1]
     for (int k = N; k >= 1; k--) {
-        const double e = Eg[(size_t)k * B];
-        const double dx = Dg[(size_t)k * B];
+        const double e = Eg[(size_t)(k) * sB];
+        const double dx = Dg[(size_t)(k) * sB];
         const double cm = -e * dx;
-        const double ca = d.a_dyn * e * Dg[(size_t)(k - 1) * B];
-        const double cb = d.b_dyn * e * Dg[(size_t)(nR + k - 1) * B];
+        const double ca = d.a_dyn * e * Dg[(size_t)((k - 1)) * sB];
+        const double cb = d.b_dyn * e * Dg[(size_t)((nR + k - 1)) * sB];
         { // x_k : d, e1 (with u_{k-1}), e2 (with x_{k-1})
             const double dj = cQ * dx * dx + sigma + rho_e * (cm * cm + (k < N ? ca_next * ca_next : 0.0));
             const double e1j = rho_e * cm * cb, e2j = rho_e * cm * ca;
@@ -188,8 +191,8 @@ __device__ __noinline__ void chain_factor(const MpcDev& d, int i, int a, int N, 
         }
         if (k >= 2) { // u_{k-1} : d, e1 (with x_{k-1}), e2 (with u_{k-2})
             const int ku = k - 1;
-            const double du = Dg[(size_t)(nR + ku) * B];
-            const double dum = Dg[(size_t)(nR + ku - 1) * B];
+            const double du = Dg[(size_t)((nR + ku)) * sB];
+            const double dum = Dg[(size_t)((nR + ku - 1)) * sB];
             const double sc = (ku < N - 1) ? 2.0 : 1.0;
             const double dj = cR * sc * du * du + sigma + rho_e * cb * cb;
             const double e1j = rho_e * ca * cb, e2j = -cR * du * dum;
@@ -203,7 +206,7 @@ __device__ __noinline__ void chain_factor(const MpcDev& d, int i, int a, int N, 
     }
     double S3[3];
     { // corner rows: u_0 then x_0  (Dm1 = pivot of x_1, Dm2 = pivot of u_1)
-        const double e1 = Eg[(size_t)1 * B], e0 = Eg[0];
+        const double e1 = Eg[(size_t)(1) * sB], e0 = Eg[0];
         const double dx0 = Dg[0];
         const double cb1 = d.b_dyn * e1 * du0, ca1 = d.a_dyn * e1 * dx0, cm0 = -e0 * dx0;
         const double sc = (0 < N - 1) ? 2.0 : 1.0;
@@ -233,150 +236,157 @@ __device__ __noinline__ void chain_factor(const MpcDev& d, int i, int a, int N, 
 }
 
 // =====================================================================================
-// osqp_setup -> scale_data for the instances of the setup list: Ruiz equilibration of
-// [[P, A'],[A, 0]] with cost normalisation (OSQP scaling.c), thread per axis chain.
+// osqp_setup for the instances of the setup list (new MPCSolver after a support-phase change):
+// scale_data = Ruiz equilibration of [[P, A'],[A, 0]] with cost normalisation (OSQP scaling.c), then
+// the numeric factorisation.  ONE WARP PER INSTANCE, lanes over the stages: the ten Ruiz passes are
+// ten rounds of independent per-stage norms, so a warp finishes them in a few thousand cycles where a
+// single thread per chain needed 300 us for the ~2 % of instances that change phase in a tick.
 // P and A are never formed: their scaled entries follow from D, E, c in closed form.
-// Shared memory per thread: DX[nR] DU[N] EE[nR] FX[nR] FU[N] FE[nR] QX[nR]; per instance HX HY EH FH [8].
+// Shared memory per warp (doubles): DD[2nA] FD[2nA] QB[2nA] EE[2nR] FE[2nR] HX HY EH FH [8].
 // =====================================================================================
-__global__ void __launch_bounds__(32) mpc_chain_setup_kernel(MpcDev d, int smem_thread_doubles)
+constexpr int kSetupWarps = 4;
+
+__device__ __forceinline__ double warp_max_d(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(kSetupWarps * 32) mpc_chain_setup_kernel(MpcDev d, int warp_doubles)
 {
     extern __shared__ double smem_all[];
-    const int lane = threadIdx.x;
-    const int slot = lane & 15, a = lane >> 4;
-    const unsigned pmask = (1u << slot) | (1u << (slot + 16));
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int count = *d.setup_count;
-    const int li = blockIdx.x * kIPW + slot;
-    if (blockIdx.x * kIPW >= count) return;
-    const bool valid = li < count;
-    const int i = d.setup_list[valid ? li : count - 1];
+    const int e = blockIdx.x * kSetupWarps + warp;
+    if (e >= count) return; // whole warp
+    const int i = d.setup_list[e];
     const size_t B = (size_t)d.B;
     const int N = d.N, nA = 2 * N + 1, nR = N + 1;
     const wc_osqp_settings& st = d.st;
-    double* base = smem_all + lane;
-    double* hb = smem_all + (size_t)smem_thread_doubles * 32 + slot;
-    int p = 0;
-    const int oDX = p; p += nR; const int oDU = p; p += N; const int oEE = p; p += nR;
-    const int oFX = p; p += nR; const int oFU = p; p += N; const int oFE = p; p += nR; const int oQX = p; p += nR;
-#define S_(o, k) base[((o) + (k)) * 32]
-#define SH_(arr, h) hb[((arr) * 8 + (h)) * kIPW]
+    double* DD = smem_all + (size_t)warp * warp_doubles;
+    double* FD = DD + 2 * nA; double* QB = FD + 2 * nA; double* EE = QB + 2 * nA; double* FE = EE + 2 * nR;
+    double* HX = FE + 2 * nR; double* HY = HX + 8; double* EH = HY + 8; double* FH = EH + 8;
     const int nh = d.nhull[i];
-    const double Qa = d.Qd[(size_t)a * B + i], Ra = d.Rd[(size_t)a * B + i];
-    const double upa = d.uprev[(size_t)a * B + i];
+    const double Q[2] = {d.Qd[i], d.Qd[B + i]};
+    const double R[2] = {d.Rd[i], d.Rd[B + i]};
     const int head = d.ring_head;
-    for (int k = 0; k < nR; k++) {
-        S_(oDX, k) = 1.0; S_(oEE, k) = 1.0;
-        const int slot_k = (head + k) % nR;
-        S_(oQX, k) = d.grad[(size_t)(a * nR + slot_k) * B + i];
-    }
-    for (int k = 0; k < N; k++) S_(oDU, k) = 1.0;
-    if (a == 0) {
-        for (int h = 0; h < kMaxHull; h++) {
-            SH_(0, h) = (h < nh) ? d.hullA[(size_t)(2 * h) * B + i] : 0.0;
-            SH_(1, h) = (h < nh) ? d.hullA[(size_t)(2 * h + 1) * B + i] : 0.0;
-            SH_(2, h) = 1.0;
-        }
+    for (int j = lane; j < 2 * nA; j += 32) { DD[j] = 1.0; QB[j] = 0.0; }
+    for (int j = lane; j < 2 * nR; j += 32) EE[j] = 1.0;
+    if (lane < kMaxHull) {
+        EH[lane] = 1.0;
+        HX[lane] = (lane < nh) ? d.hullA[(size_t)(2 * lane) * B + i] : 0.0;
+        HY[lane] = (lane < nh) ? d.hullA[(size_t)(2 * lane + 1) * B + i] : 0.0;
     }
     __syncwarp();
-    const double qu0 = -(Ra * upa); // unscaled gradient of u_0 (G u_prev, MPCSolver.cpp:244-245); other inputs 0
+    // unscaled gradient (MPCSolver::setGradient): state block from the ring, input block G u_prev
+    for (int k = lane; k < nR; k += 32) {
+        const int slot_k = (head + k) % nR;
+        QB[k] = d.grad[(size_t)slot_k * B + i];
+        QB[nA + k] = d.grad[(size_t)(nR + slot_k) * B + i];
+    }
+    if (lane == 0) { // G = -Theta' R~ e1 -> only the u_0 block (MPCSolver.cpp:244-245)
+        QB[nR] = -(R[0] * d.uprev[i]);
+        QB[nA + nR] = -(R[1] * d.uprev[B + i]);
+    }
+    __syncwarp();
     const double ad = fabs(d.a_dyn), bd = fabs(d.b_dyn);
     double c = 1.0;
     for (int it = 0; it < st.scaling; it++) {
-        // column / row norms from the CURRENT D, E (all factors first, then applied)
-        for (int k = 0; k < nR; k++) {
-            const double dx = S_(oDX, k);
-            const double ek = S_(oEE, k);
-            double nrm = fabs(c * Qa * dx * dx);
-            nrm = fmax(nrm, ek * dx);
-            if (k < N) nrm = fmax(nrm, ad * S_(oEE, k + 1) * dx);
-            S_(oFX, k) = 1.0 / sqrt(limit_scaling_c(nrm));
-            if (k < N) {
-                const double du = S_(oDU, k);
-                const double sc = (k < N - 1) ? 2.0 : 1.0;
-                double nu = fabs(c * sc * Ra * du * du);
-                if (k >= 1) nu = fmax(nu, fabs(c * Ra * du * S_(oDU, k - 1)));
-                if (k < N - 1) nu = fmax(nu, fabs(c * Ra * du * S_(oDU, k + 1)));
-                nu = fmax(nu, bd * S_(oEE, k + 1) * du);
-                if (k == 0)
-                    for (int h = 0; h < nh; h++) nu = fmax(nu, fabs(SH_(2, h) * SH_(a, h)) * du);
-                S_(oFU, k) = 1.0 / sqrt(limit_scaling_c(nu));
+        for (int k = lane; k < nR; k += 32) {
+#pragma unroll
+            for (int a = 0; a < 2; a++) {
+                const double* DX = DD + a * nA; const double* DU = DX + nR; const double* Ea = EE + a * nR;
+                const double dx = DX[k];
+                double nrm = fabs(c * Q[a] * dx * dx);
+                nrm = fmax(nrm, Ea[k] * dx);
+                if (k < N) nrm = fmax(nrm, ad * Ea[k + 1] * dx);
+                FD[a * nA + k] = 1.0 / sqrt(limit_scaling_c(nrm));
+                if (k < N) {
+                    const double du = DU[k];
+                    const double sc = (k < N - 1) ? 2.0 : 1.0;
+                    double nu = fabs(c * sc * R[a] * du * du);
+                    if (k >= 1) nu = fmax(nu, fabs(c * R[a] * du * DU[k - 1]));
+                    if (k < N - 1) nu = fmax(nu, fabs(c * R[a] * du * DU[k + 1]));
+                    nu = fmax(nu, bd * Ea[k + 1] * du);
+                    if (k == 0) {
+                        const double* Hc = (a == 0) ? HX : HY;
+                        for (int h = 0; h < nh; h++) nu = fmax(nu, fabs(EH[h] * Hc[h]) * du);
+                    }
+                    FD[a * nA + nR + k] = 1.0 / sqrt(limit_scaling_c(nu));
+                }
+                double nr = Ea[k] * dx;
+                if (k >= 1) {
+                    nr = fmax(nr, ad * Ea[k] * DX[k - 1]);
+                    nr = fmax(nr, bd * Ea[k] * DU[k - 1]);
+                }
+                FE[a * nR + k] = 1.0 / sqrt(limit_scaling_c(nr));
             }
-            double nr = ek * dx;
-            if (k >= 1) {
-                nr = fmax(nr, ad * ek * S_(oDX, k - 1));
-                nr = fmax(nr, bd * ek * S_(oDU, k - 1));
-            }
-            S_(oFE, k) = 1.0 / sqrt(limit_scaling_c(nr));
         }
-        // hull rows: both axes enter the row norm
-        const double du0 = S_(oDU, 0);
-        const double du0o = __shfl_xor_sync(pmask, du0, 16);
-        const double dux = a == 0 ? du0 : du0o, duy = a == 0 ? du0o : du0;
-        if (a == 0) {
-            for (int h = 0; h < nh; h++) {
-                const double nrm = fmax(fabs(SH_(2, h) * SH_(0, h)) * dux, fabs(SH_(2, h) * SH_(1, h)) * duy);
-                SH_(3, h) = 1.0 / sqrt(limit_scaling_c(nrm));
-            }
+        if (lane < nh) {
+            const double nrm = fmax(fabs(EH[lane] * HX[lane]) * DD[nR], fabs(EH[lane] * HY[lane]) * DD[nA + nR]);
+            FH[lane] = 1.0 / sqrt(limit_scaling_c(nrm));
         }
         __syncwarp();
-        for (int k = 0; k < nR; k++) { S_(oDX, k) *= S_(oFX, k); S_(oEE, k) *= S_(oFE, k); }
-        for (int k = 0; k < N; k++) S_(oDU, k) *= S_(oFU, k);
-        if (a == 0)
-            for (int h = 0; h < nh; h++) SH_(2, h) *= SH_(3, h);
+        for (int j = lane; j < 2 * nA; j += 32) DD[j] *= FD[j];
+        for (int j = lane; j < 2 * nR; j += 32) EE[j] *= FE[j];
+        if (lane < nh) EH[lane] *= FH[lane];
         __syncwarp();
         // cost normalisation: c <- c / max(mean_j ||P_j||_inf, ||q||_inf)
         double sum = 0.0, qn = 0.0;
-        for (int k = 0; k < nR; k++) {
-            const double dx = S_(oDX, k);
-            sum += fabs(c * Qa * dx * dx);
-            qn = fmax(qn, fabs(c * dx * S_(oQX, k)));
-            if (k < N) {
-                const double du = S_(oDU, k);
-                const double sc = (k < N - 1) ? 2.0 : 1.0;
-                double nu = fabs(c * sc * Ra * du * du);
-                if (k >= 1) nu = fmax(nu, fabs(c * Ra * du * S_(oDU, k - 1)));
-                if (k < N - 1) nu = fmax(nu, fabs(c * Ra * du * S_(oDU, k + 1)));
-                sum += nu;
-                qn = fmax(qn, fabs(c * du * (k == 0 ? qu0 : 0.0)));
+        for (int k = lane; k < nR; k += 32) {
+#pragma unroll
+            for (int a = 0; a < 2; a++) {
+                const double* DX = DD + a * nA; const double* DU = DX + nR;
+                const double dx = DX[k];
+                sum += fabs(c * Q[a] * dx * dx);
+                qn = fmax(qn, fabs(c * dx * QB[a * nA + k]));
+                if (k < N) {
+                    const double du = DU[k];
+                    const double sc = (k < N - 1) ? 2.0 : 1.0;
+                    double nu = fabs(c * sc * R[a] * du * du);
+                    if (k >= 1) nu = fmax(nu, fabs(c * R[a] * du * DU[k - 1]));
+                    if (k < N - 1) nu = fmax(nu, fabs(c * R[a] * du * DU[k + 1]));
+                    sum += nu;
+                    qn = fmax(qn, fabs(c * du * QB[a * nA + nR + k]));
+                }
             }
         }
-        // x axis first, then y: the same association on both lanes of the pair
-        const double so = __shfl_xor_sync(pmask, sum, 16);
-        sum = a == 0 ? sum + so : so + sum;
-        qn = pair_max(qn, pmask);
+        sum = warp_sum_d(sum);
+        qn = warp_max_d(qn);
         double c_temp = sum / (double)(2 * nA);
         c_temp = fmax(c_temp, limit_scaling_c(qn));
         c_temp = limit_scaling_c(c_temp);
         c *= 1.0 / c_temp;
     }
-    if (valid) {
-        for (int k = 0; k < nR; k++) {
-            const double dx = S_(oDX, k), e = S_(oEE, k);
-            d.D[(size_t)(a * nA + k) * B + i] = dx;
-            d.Dinv[(size_t)(a * nA + k) * B + i] = 1.0 / dx;
-            d.Eeq[(size_t)(a * nR + k) * B + i] = e;
-            d.Einv[(size_t)(a * nR + k) * B + i] = 1.0 / e;
-        }
-        for (int k = 0; k < N; k++) {
-            const double du = S_(oDU, k);
-            d.D[(size_t)(a * nA + nR + k) * B + i] = du;
-            d.Dinv[(size_t)(a * nA + nR + k) * B + i] = 1.0 / du;
-        }
-        if (a == 0) {
-            for (int h = 0; h < kMaxHull; h++) {
-                const double e = SH_(2, h);
-                d.Eh[(size_t)h * B + i] = e;
-                d.Ehinv[(size_t)h * B + i] = 1.0 / e;
-            }
-            d.cscale[i] = c;
-            d.rho[i] = fmin(fmax(st.rho, kRhoMin), kRhoMax);
-            d.inited[i] = 2; // workspace exists, cold start pending (consumed by phase 1)
-        }
+    // publish the scaling of the new workspace (OSQP keeps Dinv, Einv next to D, E)
+    for (int j = lane; j < 2 * nA; j += 32) {
+        const double v = DD[j];
+        d.D[(size_t)j * B + i] = v; d.Dinv[(size_t)j * B + i] = 1.0 / v;
+    }
+    for (int j = lane; j < 2 * nR; j += 32) {
+        const double v = EE[j];
+        d.Eeq[(size_t)j * B + i] = v; d.Einv[(size_t)j * B + i] = 1.0 / v;
+    }
+    if (lane < kMaxHull) {
+        const double v = EH[lane];
+        d.Eh[(size_t)lane * B + i] = v; d.Ehinv[(size_t)lane * B + i] = 1.0 / v;
+    }
+    const double rho0 = fmin(fmax(st.rho, kRhoMin), kRhoMax);
+    if (lane == 0) {
+        d.cscale[i] = c;
+        d.rho[i] = rho0;
+        d.inited[i] = 2; // workspace exists, cold start pending (consumed by phase 1)
     }
     __syncwarp();
-    // numeric factorisation of the new workspace (osqp_setup -> init_linsys_solver)
-    chain_factor(d, i, a, N, c, fmin(fmax(st.rho, kRhoMin), kRhoMax), nh, pmask, valid);
-#undef S_
-#undef SH_
+    // numeric factorisation (osqp_setup -> init_linsys_solver): the two axis chains on lanes 0 and 16
+    if ((lane & 15) == 0) chain_factor(d, i, lane >> 4, N, c, rho0, nh, 0x00010001u, true, DD + (lane >> 4) * nA, EE + (lane >> 4) * nR);
 }
 
 // =====================================================================================
@@ -1042,7 +1052,7 @@ size_t mpc_chain_smem_bytes(int N)
     return ((size_t)O.total * 32 + (size_t)H_COUNT * 8 * kIPW) * sizeof(double);
 }
 
-static size_t mpc_chain_setup_thread_doubles(int N) { return (size_t)(4 * (N + 1) + 2 * N + (N + 1)); }
+static size_t mpc_chain_setup_warp_doubles(int N) { return (size_t)(3 * (4 * N + 2) + 2 * (2 * N + 2) + 32); }
 
 bool mpc_chain_supported(int N)
 {
@@ -1053,8 +1063,8 @@ cudaError_t launch_mpc_chain(const MpcDev& d, const MpcTickIO& io, cudaStream_t 
 {
     const int N = d.N;
     const size_t smem = mpc_chain_smem_bytes(N);
-    const size_t td = mpc_chain_setup_thread_doubles(N);
-    const size_t smem_setup = (td * 32 + 4 * 8 * kIPW) * sizeof(double);
+    const size_t td = mpc_chain_setup_warp_doubles(N);
+    const size_t smem_setup = td * kSetupWarps * sizeof(double);
     cudaError_t e;
     // (the attribute is per function and per device; setting it again is cheap)
     auto k1 = N == 25 ? mpc_chain_kernel<false, 25> : mpc_chain_kernel<false, 0>;
@@ -1066,7 +1076,7 @@ cudaError_t launch_mpc_chain(const MpcDev& d, const MpcTickIO& io, cudaStream_t 
     e = cudaFuncSetAttribute(mpc_chain_setup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_setup);
     if (e != cudaSuccess) return e;
     const int blocks = (d.B + kIPW - 1) / kIPW;
-    mpc_chain_setup_kernel<<<blocks, 32, smem_setup, s>>>(d, (int)td);
+    mpc_chain_setup_kernel<<<(d.B + kSetupWarps - 1) / kSetupWarps, kSetupWarps * 32, smem_setup, s>>>(d, (int)td);
     k1<<<blocks, 32, smem, s>>>(d, io);
     k2<<<blocks, 32, smem, s>>>(d, io);
     return cudaGetLastError();
