@@ -42,10 +42,15 @@ def bytes_per_tick(N):
     return dict(mpc=128 * N + 464, ik=1540)
 
 
-def flops_per_tick(N, iters, refactors, wsc):
+F_IK_FAST = 12500  # FK + Jacobian columns 6.0k, b/g build 0.5k, Woodbury + 9x9 Schur solve 6.0k
+
+
+def flops_per_tick(N, iters, refactors, wsc, slow_frac=1.0):
+    """algorithmic fp64 flops per instance-tick; the IK term is the mix of the fused-tick
+    fast path and the general null-space / active-set path (all instances when the fast path is off)"""
     n, m, nnzA = 4 * N + 2, 2 * N + 10, 6 * N + 18
     f_iter = 4 * nnzA + 21 * n + 12 * (n + m)
-    return iters * f_iter + refactors * 36 * n, 43500 + 3900 * wsc
+    return iters * f_iter + refactors * 36 * n, (1.0 - slow_frac) * F_IK_FAST + slow_frac * 43500 + 3900 * wsc
 
 
 def peaks():
@@ -71,7 +76,7 @@ class ClockSampler:
     def start(self):
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}",
-                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                       "--format=csv,noheader,nounits", "-lms", "50"], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
@@ -277,7 +282,9 @@ def run_ours(args, world, rank, local_rank):
     step_ms = [evs[k].elapsed_time(evs[k + 1]) for k in range(steps)]
     total_ms = evs[0].elapsed_time(evs[steps])
     prep_ms, admm_ms, nt = mpc.kernel_times_ms()
+    setup_ms, phase1_ms, phase2_ms = mpc.kernel_times_detail_ms()
     ik_ms, nik = ik.kernel_times_ms()
+    ik_fast_ms, ik_general_ms = ik.kernel_times_detail_ms()
     mpc.enable_profiling(False); ik.enable_profiling(False)
     # statistics of the last tick (outside the timed region)
     it_mean = mo["iters"].double().mean().item(); it_max = int(mo["iters"].max().item())
@@ -322,17 +329,20 @@ def run_ours(args, world, rank, local_rank):
                 nwsr=torch.empty(B, dtype=torch.int32).pin_memory())
     h2d = sum(v.numel() * v.element_size() for v in h_mpc[0]) + sum(v.numel() * v.element_size() for v in h_ik[0].values())
     d2h = sum(v.numel() * v.element_size() for v in h_mo.values()) + sum(v.numel() * v.element_size() for v in h_io.values())
-    for t in range(e2e_warm):
+    def e2e_tick(t):
+        # both blocks are submitted through the host-pointer C ABI (H2D, kernels, D2H on each handle's stream), then
+        # awaited: the IK inputs upload while the MPC kernels run; the tick is complete when both results are on the host
         a = h_mpc[t]
-        mpc2.tick_host(a[0], a[1], a[2], a[3], a[4], a[5], out=h_mo)
-        ik.tick_host(h_ik[t % len(h_ik)], out=h_io)
+        mpc2.tick_host_async(a[0], a[1], a[2], a[3], a[4], a[5], out=h_mo)
+        ik.tick_host_async(h_ik[t % len(h_ik)], out=h_io)
+        mpc2.sync(); ik.sync()
+
+    for t in range(e2e_warm):
+        e2e_tick(t)
     barrier()
     t0 = time.perf_counter()
     for k in range(e2e_steps):
-        t = e2e_warm + k
-        a = h_mpc[t]
-        mpc2.tick_host(a[0], a[1], a[2], a[3], a[4], a[5], out=h_mo)
-        ik.tick_host(h_ik[t % len(h_ik)], out=h_io)
+        e2e_tick(e2e_warm + k)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     e = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
@@ -348,8 +358,13 @@ def run_ours(args, world, rank, local_rank):
         admm_avg_ms = admm_ms / max(nt, 1)
         ik_avg_ms = ik_ms / max(nik, 1)
         prep_avg_ms = prep_ms / max(nt, 1)
-        achieved = bt["mpc"] * B / (admm_avg_ms * 1e-3) * 1e-9
-        f_mpc, f_ik = flops_per_tick(N, it_mean, 0.0, wsc_mean)
+        # dominant kernel: the ADMM pass every instance goes through (chain path: phase 1; cooperative path: the
+        # single ADMM kernel).  Its algorithmic bytes are the MPC share of SURVEY §8(d): (128 N + 464) B per instance.
+        dom_name = "mpc_chain_kernel<phase 1>" if mpc.path == "chain" else "mpc_admm_kernel"
+        dom_ms = phase1_ms / max(nt, 1)
+        achieved = bt["mpc"] * B / (dom_ms * 1e-3) * 1e-9
+        fast_on = ik_fast_ms > 0 and ik_general_ms > 0
+        f_mpc, f_ik = flops_per_tick(N, it_mean, 0.0, wsc_mean, slow_frac=ws_frac if fast_on else 1.0)
         value = world * B * steps / (total_ms_max * 1e-3)
         line = {
             "metric": "controller_ticks_per_sec", "value": value, "unit": "ticks/s", "n_gpus": world, "steps": steps,
@@ -357,15 +372,18 @@ def run_ours(args, world, rank, local_rank):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "full tick: DCM-MPC (horizon 25) + FK + QP-IK, iCub 23-DoF + floating base "
                                    "(BASELINE configs[2])", "instances_per_gpu": B, "instances_total": world * B,
-                       "horizon": N, "mpc_lanes_per_instance": os.environ.get("WC_MPC_LANES", "auto"),
+                       "horizon": N, "mpc_path": mpc.path,
                        "l2": "per-tick working set (solver state 6 KB x 65536 + inputs) exceeds the 126 MB L2; "
                              "inputs change every tick"},
             "tick_latency_ms": {"p50": pct(step_ms, 0.5), "p99": pct(step_ms, 0.99), "max": max(step_ms)},
-            "kernels_ms": {"mpc_prepare": prep_avg_ms, "mpc_admm": admm_avg_ms, "fk_qpik": ik_avg_ms},
+            "kernels_ms": {"mpc_prepare": prep_avg_ms, "mpc_admm": admm_avg_ms, "fk_qpik": ik_avg_ms,
+                           "mpc_setup": setup_ms / max(nt, 1), "mpc_phase1": phase1_ms / max(nt, 1),
+                           "mpc_phase2": phase2_ms / max(nt, 1), "ik_fast": ik_fast_ms / max(nik, 1),
+                           "ik_general": ik_general_ms / max(nik, 1)},
             "stats": {"osqp_solved_frac": solved, "osqp_iters_mean": it_mean, "osqp_iters_max_last_tick": it_max,
                       "new_solver_frac": new_frac, "qpik_success_frac": ik_ok, "qpik_nwsr_mean": wsc_mean,
                       "qpik_active_set_frac": ws_frac},
-            "roofline": {"bound": "hbm", "kernel": "mpc_admm_kernel", "achieved": achieved, "peak": hbm_peak,
+            "roofline": {"bound": "hbm", "kernel": dom_name, "kernel_ms": dom_ms, "achieved": achieved, "peak": hbm_peak,
                          "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": bt["mpc"] * B,
                          "note": "path is FP64-latency/issue bound, not HBM bound (DESIGN.md); see fp64"},
@@ -394,8 +412,8 @@ def run_ours(args, world, rank, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()

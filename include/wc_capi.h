@@ -166,6 +166,17 @@ wc_status wc_mpc_tick_host(wc_mpc* h,
                            const double* dcm_meas, const double* ref, const uint8_t* reset,
                            double* zmp, int32_t* osqp_status, int32_t* iters, int32_t* flags);
 
+/* Split form of wc_mpc_tick_host: _async enqueues the H2D copies, the kernels and the D2H copies on the
+ * handle's own stream and returns; wc_mpc_sync waits for them.  Buffers must stay valid (and should be
+ * pinned: cudaHostAlloc / torch pin_memory) until wc_mpc_sync returns.  Lets a caller overlap the upload of
+ * the next block's inputs (e.g. the IK handle's) with this handle's kernels. */
+wc_status wc_mpc_tick_host_async(wc_mpc* h,
+                           const double* lf_H, const double* rf_H,
+                           const uint8_t* l_contact, const uint8_t* r_contact,
+                           const double* dcm_meas, const double* ref, const uint8_t* reset,
+                           double* zmp, int32_t* osqp_status, int32_t* iters, int32_t* flags);
+wc_status wc_mpc_sync(wc_mpc* h);
+
 /* Debug / parity taps (device -> host copies, synchronous): full primal solution
  * z = [x_0..x_N, u_0..u_{N-1}] per instance ([n*B], field-major, n = 4N+2), the current
  * rho and number of rho updates of the instance's solver.  Any pointer may be NULL. */
@@ -179,6 +190,12 @@ int64_t wc_mpc_launch_count(const wc_mpc* h);
  * accumulated milliseconds and tick count since the previous call and clears them. */
 wc_status wc_mpc_enable_profiling(wc_mpc* h, int32_t on);
 wc_status wc_mpc_kernel_times_ms(wc_mpc* h, double* prepare_ms, double* admm_ms, int64_t* ticks);
+/* Split of admm_ms of the window closed by the last wc_mpc_kernel_times_ms call: OSQP setup of new
+ * workspaces / ADMM up to the first termination check (all instances) / the compacted remainder.
+ * On the cooperative path (long horizons) everything is reported as phase 1. */
+wc_status wc_mpc_kernel_times_detail_ms(wc_mpc* h, double* setup_ms, double* phase1_ms, double* phase2_ms);
+/* ADMM kernel family of the handle: 1 = chain-per-thread (mpc_chain.cu, short horizons), 0 = cooperative. */
+int32_t wc_mpc_path(const wc_mpc* h);
 
 /* ---------------------------------------------------------------------------------- */
 /* Kinematic model table (replaces the iDynTree::Model loaded from model.urdf,          */
@@ -286,6 +303,18 @@ wc_status wc_ik_tick_host(wc_ik* h,
                           double* dq, double* lf_err, double* rf_err,
                           int32_t* qp_status, int32_t* nwsr);
 
+/* Split form of wc_ik_tick_host (see wc_mpc_tick_host_async). */
+wc_status wc_ik_tick_host_async(wc_ik* h,
+                          const double* q_meas, const double* q_lin,
+                          const double* base_H, const uint8_t* left_is_fixed,
+                          const double* lf_H_des, const double* rf_H_des,
+                          const double* lf_twist, const double* rf_twist,
+                          const double* com_pos_des, const double* com_vel_des,
+                          const double* com_meas, const double* neck_R_des,
+                          double* dq, double* lf_err, double* rf_err,
+                          int32_t* qp_status, int32_t* nwsr);
+wc_status wc_ik_sync(wc_ik* h);
+
 /* Forward kinematics only (WalkingFK getters, WalkingForwardKinematics.cpp:411-454):
  * for each instance the world transforms of l_sole, r_sole [12*B each], neck rotation [9*B],
  * CoM position [3*B] and the four Jacobians in MIXED representation, row-major per
@@ -327,6 +356,9 @@ wc_status wc_ik_solve_with_jacobians_host(wc_ik* h,
 int64_t wc_ik_launch_count(const wc_ik* h);
 wc_status wc_ik_enable_profiling(wc_ik* h, int32_t on);
 wc_status wc_ik_kernel_times_ms(wc_ik* h, double* ik_ms, int64_t* launches);
+/* Split of ik_ms of the window closed by the last wc_ik_kernel_times_ms call: fused-tick fast kernel /
+ * general null-space + active-set kernel (the compacted remainder, or everything when the fast path is off). */
+wc_status wc_ik_kernel_times_detail_ms(wc_ik* h, double* fast_ms, double* general_ms);
 
 /* Measured FP64 FMA throughput of the device (register-resident FMA chains, all SMs), in GFLOP/s:
  * the denominator of the FP64 roofline fraction that bench.py reports next to the HBM one

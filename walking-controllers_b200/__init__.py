@@ -114,11 +114,16 @@ def lib():
     L.wc_mpc_reset.argtypes = [_VP, _VP]; L.wc_mpc_reset.restype = i32
     L.wc_mpc_tick_dev.argtypes = [_VP] + [_VP] * 11 + [_VP]; L.wc_mpc_tick_dev.restype = i32
     L.wc_mpc_tick_host.argtypes = [_VP] + [_VP] * 11; L.wc_mpc_tick_host.restype = i32
+    L.wc_mpc_tick_host_async.argtypes = [_VP] + [_VP] * 11; L.wc_mpc_tick_host_async.restype = i32
+    L.wc_mpc_sync.argtypes = [_VP]; L.wc_mpc_sync.restype = i32
     L.wc_mpc_debug_get_host.argtypes = [_VP, _VP, _VP, _VP]; L.wc_mpc_debug_get_host.restype = i32
     L.wc_mpc_launch_count.argtypes = [_VP]; L.wc_mpc_launch_count.restype = i64
     L.wc_mpc_enable_profiling.argtypes = [_VP, i32]; L.wc_mpc_enable_profiling.restype = i32
     L.wc_mpc_kernel_times_ms.argtypes = [_VP, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i64)]
     L.wc_mpc_kernel_times_ms.restype = i32
+    L.wc_mpc_kernel_times_detail_ms.argtypes = [_VP] + [C.POINTER(C.c_double)] * 3
+    L.wc_mpc_kernel_times_detail_ms.restype = i32
+    L.wc_mpc_path.argtypes = [_VP]; L.wc_mpc_path.restype = i32
     L.wc_measure_fp64_peak.argtypes = [i32, C.POINTER(C.c_double)]; L.wc_measure_fp64_peak.restype = i32
     if hasattr(L, "wc_ik_create"):
         L.wc_ik_create.argtypes = [C.POINTER(IkConfig), C.POINTER(Model), i32, i32, C.POINTER(_VP)]
@@ -128,6 +133,8 @@ def lib():
         L.wc_ik_set_gains_host.argtypes = [_VP, _VP, _VP]; L.wc_ik_set_gains_host.restype = i32
         L.wc_ik_tick_dev.argtypes = [_VP] + [_VP] * 17 + [_VP]; L.wc_ik_tick_dev.restype = i32
         L.wc_ik_tick_host.argtypes = [_VP] + [_VP] * 17; L.wc_ik_tick_host.restype = i32
+        L.wc_ik_tick_host_async.argtypes = [_VP] + [_VP] * 17; L.wc_ik_tick_host_async.restype = i32
+        L.wc_ik_sync.argtypes = [_VP]; L.wc_ik_sync.restype = i32
         L.wc_fk_dev.argtypes = [_VP] + [_VP] * 11 + [_VP]; L.wc_fk_dev.restype = i32
         L.wc_ik_solve_with_jacobians_dev.argtypes = [_VP] + [_VP] * 21 + [_VP]
         L.wc_ik_solve_with_jacobians_dev.restype = i32
@@ -135,6 +142,8 @@ def lib():
         L.wc_ik_enable_profiling.argtypes = [_VP, i32]; L.wc_ik_enable_profiling.restype = i32
         L.wc_ik_kernel_times_ms.argtypes = [_VP, C.POINTER(C.c_double), C.POINTER(i64)]
         L.wc_ik_kernel_times_ms.restype = i32
+        L.wc_ik_kernel_times_detail_ms.argtypes = [_VP] + [C.POINTER(C.c_double)] * 2
+        L.wc_ik_kernel_times_detail_ms.restype = i32
     _LIB = L
     return L
 
@@ -227,6 +236,16 @@ class MpcBatch:
                                       _ptr(out["iters"]), _ptr(out["flags"])), "wc_mpc_tick_host")
         return out
 
+    def tick_host_async(self, lf_H, rf_H, l_contact, r_contact, dcm, ref, out, reset=None):
+        """enqueue copies + kernels on the handle's stream; buffers (pinned) must outlive sync()"""
+        _check(lib().wc_mpc_tick_host_async(self.h, _ptr(lf_H), _ptr(rf_H), _ptr(l_contact), _ptr(r_contact), _ptr(dcm),
+                                            _ptr(ref), _ptr(reset), _ptr(out["zmp"]), _ptr(out["status"]),
+                                            _ptr(out["iters"]), _ptr(out["flags"])), "wc_mpc_tick_host_async")
+        return out
+
+    def sync(self):
+        _check(lib().wc_mpc_sync(self.h), "wc_mpc_sync")
+
     def debug(self):
         import numpy as np
         n = 4 * self.N + 2
@@ -246,6 +265,16 @@ class MpcBatch:
         a, b, n = C.c_double(), C.c_double(), C.c_int64()
         _check(lib().wc_mpc_kernel_times_ms(self.h, C.byref(a), C.byref(b), C.byref(n)), "wc_mpc_kernel_times_ms")
         return a.value, b.value, n.value
+
+    def kernel_times_detail_ms(self):
+        """(setup_ms, phase1_ms, phase2_ms) of the window closed by the last kernel_times_ms() call"""
+        a, b, c = C.c_double(), C.c_double(), C.c_double()
+        _check(lib().wc_mpc_kernel_times_detail_ms(self.h, C.byref(a), C.byref(b), C.byref(c)), "wc_mpc_kernel_times_detail_ms")
+        return a.value, b.value, c.value
+
+    @property
+    def path(self):
+        return "chain" if lib().wc_mpc_path(self.h) == 1 else "coop"
 
 
 IK_INPUT_KEYS = ("q_meas", "q_lin", "base_H", "left_is_fixed", "lf_H_des", "rf_H_des", "lf_twist", "rf_twist",
@@ -306,6 +335,15 @@ class IkBatch:
                                      _ptr(out["rf_err"]), _ptr(out["status"]), _ptr(out["nwsr"])), "wc_ik_tick_host")
         return out
 
+    def tick_host_async(self, inp, out):
+        _check(lib().wc_ik_tick_host_async(self.h, *[_ptr(inp[k]) for k in IK_INPUT_KEYS], _ptr(out["dq"]),
+                                           _ptr(out["lf_err"]), _ptr(out["rf_err"]), _ptr(out["status"]),
+                                           _ptr(out["nwsr"])), "wc_ik_tick_host_async")
+        return out
+
+    def sync(self):
+        _check(lib().wc_ik_sync(self.h), "wc_ik_sync")
+
     def fk(self, q, base_H, left_is_fixed, jacobians=True, stream=None):
         import torch
         dev, B, nV = q.device, self.B, self.nJ + 6
@@ -350,6 +388,12 @@ class IkBatch:
         a, n = C.c_double(), C.c_int64()
         _check(lib().wc_ik_kernel_times_ms(self.h, C.byref(a), C.byref(n)), "wc_ik_kernel_times_ms")
         return a.value, n.value
+
+    def kernel_times_detail_ms(self):
+        """(fast_ms, general_ms) of the window closed by the last kernel_times_ms() call"""
+        a, b = C.c_double(), C.c_double()
+        _check(lib().wc_ik_kernel_times_detail_ms(self.h, C.byref(a), C.byref(b)), "wc_ik_kernel_times_detail_ms")
+        return a.value, b.value
 
 
 def measure_fp64_peak(device=0):

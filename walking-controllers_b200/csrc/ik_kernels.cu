@@ -1096,7 +1096,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, 4) ik_fast_kernel(IkDev d, Ik
 }
 
 template <int NJ, bool COMC>
-cudaError_t launch_t(const IkDev& d, const IkTickIO& io, int mode, cudaStream_t s)
+cudaError_t launch_t(const IkDev& d, const IkTickIO& io, int mode, cudaStream_t s, cudaEvent_t mid)
 {
     using LY = IkLayout<NJ, COMC>;
     const size_t smem = (size_t)LY::TOTAL * sizeof(double) * kWarpsPerBlock;
@@ -1112,6 +1112,7 @@ cudaError_t launch_t(const IkDev& d, const IkTickIO& io, int mode, cudaStream_t 
         e = cudaMemsetAsync(d.slow_count, 0, sizeof(int32_t), s);
         if (e != cudaSuccess) return e;
         ik_fast_kernel<NJ><<<(d.B + kFastWarps - 1) / kFastWarps, kFastWarps * 32, smem_f, s>>>(d, io);
+        if (mid) cudaEventRecord(mid, s); // per-kernel timing (wc_ik_enable_profiling)
         ik_kernel<NJ, COMC><<<blocks, kWarpsPerBlock * 32, smem, s>>>(d, io, mode, 1);
         return cudaGetLastError();
     }
@@ -1123,11 +1124,11 @@ cudaError_t launch_t(const IkDev& d, const IkTickIO& io, int mode, cudaStream_t 
 
 bool ik_supported(int n_dofs) { return n_dofs == 23; }
 
-cudaError_t launch_ik(const IkDev& d, const IkTickIO& io, int mode, cudaStream_t s)
+cudaError_t launch_ik(const IkDev& d, const IkTickIO& io, int mode, cudaStream_t s, cudaEvent_t mid)
 {
     if (d.nJ != 23) return cudaErrorInvalidValue;
-    if (d.cfg.use_com_as_constraint) return launch_t<23, true>(d, io, mode, s);
-    return launch_t<23, false>(d, io, mode, s);
+    if (d.cfg.use_com_as_constraint) return launch_t<23, true>(d, io, mode, s, mid);
+    return launch_t<23, false>(d, io, mode, s, mid);
 }
 
 } // namespace wcb

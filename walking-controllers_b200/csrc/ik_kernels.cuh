@@ -75,7 +75,8 @@ struct IkTickIO {
     double* o_J_lf; double* o_J_rf; double* o_J_neck; double* o_J_com;
 };
 
-cudaError_t launch_ik(const IkDev& d, const IkTickIO& io, int mode, cudaStream_t s);
+// mid (nullable): event recorded between the fast kernel and the general kernel of the fused tick
+cudaError_t launch_ik(const IkDev& d, const IkTickIO& io, int mode, cudaStream_t s, cudaEvent_t mid = nullptr);
 bool ik_supported(int n_dofs);
 
 } // namespace wcb

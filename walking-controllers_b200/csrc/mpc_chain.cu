@@ -1059,7 +1059,7 @@ bool mpc_chain_supported(int N)
     return N >= 2 && mpc_chain_smem_bytes(N) <= (size_t)mpc_admm_max_smem();
 }
 
-cudaError_t launch_mpc_chain(const MpcDev& d, const MpcTickIO& io, cudaStream_t s)
+cudaError_t launch_mpc_chain(const MpcDev& d, const MpcTickIO& io, cudaStream_t s, cudaEvent_t* mid)
 {
     const int N = d.N;
     const size_t smem = mpc_chain_smem_bytes(N);
@@ -1077,7 +1077,9 @@ cudaError_t launch_mpc_chain(const MpcDev& d, const MpcTickIO& io, cudaStream_t 
     if (e != cudaSuccess) return e;
     const int blocks = (d.B + kIPW - 1) / kIPW;
     mpc_chain_setup_kernel<<<(d.B + kSetupWarps - 1) / kSetupWarps, kSetupWarps * 32, smem_setup, s>>>(d, (int)td);
+    if (mid) cudaEventRecord(mid[0], s); // per-kernel timing (wc_mpc_enable_profiling)
     k1<<<blocks, 32, smem, s>>>(d, io);
+    if (mid) cudaEventRecord(mid[1], s);
     k2<<<blocks, 32, smem, s>>>(d, io);
     return cudaGetLastError();
 }

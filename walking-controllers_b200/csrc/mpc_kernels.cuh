@@ -112,6 +112,7 @@ int mpc_admm_max_smem();
 // chain-per-thread path (mpc_chain.cu): setup of new workspaces + phase 1 + phase 2, three launches
 bool mpc_chain_supported(int N);
 size_t mpc_chain_smem_bytes(int N);
-cudaError_t launch_mpc_chain(const MpcDev& d, const MpcTickIO& io, cudaStream_t s);
+// mid (nullable): two events recorded after the setup kernel and after phase 1
+cudaError_t launch_mpc_chain(const MpcDev& d, const MpcTickIO& io, cudaStream_t s, cudaEvent_t* mid);
 
 } // namespace wcb

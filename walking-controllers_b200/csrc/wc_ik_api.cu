@@ -23,7 +23,8 @@ struct wc_ik {
     void* pin_in; void* pin_out; void* dev_in; void* dev_out;
     cudaStream_t host_stream;
     int profiling;
-    std::vector<cudaEvent_t> ev; // pairs
+    std::vector<cudaEvent_t> ev; // triples (start, after the fast kernel, end)
+    double fast_ms_acc, detail[2];
     double ms_acc; int64_t timed;
 };
 
@@ -111,7 +112,7 @@ wc_status wc_ik_create(const wc_ik_config* cfg, const wc_model* model, int32_t B
     if (!h) return WC_ERR_ALLOC;
     h->launches = 0; h->model_dev = nullptr; h->kpos = h->katt = nullptr;
     h->pin_in = h->pin_out = h->dev_in = h->dev_out = nullptr; h->host_stream = nullptr;
-    h->profiling = 0; h->ms_acc = 0; h->timed = 0;
+    h->profiling = 0; h->ms_acc = 0; h->timed = 0; h->fast_ms_acc = 0; h->detail[0] = h->detail[1] = 0;
     std::memset(&h->d, 0, sizeof(h->d));
     h->device = device;
     h->d.B = B; h->d.nJ = cfg->n_dofs; h->d.cfg = *cfg;
@@ -168,9 +169,15 @@ wc_status wc_ik_set_gains_host(wc_ik* h, const double* k_pos_foot, const double*
 
 static wc_status launch_checked(wc_ik* h, const IkTickIO& io, int mode, cudaStream_t s, const char* who)
 {
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
-    if (h->profiling) { cudaEventCreate(&e0); cudaEventCreate(&e1); h->ev.push_back(e0); h->ev.push_back(e1); cudaEventRecord(e0, s); }
-    cudaError_t e = launch_ik(h->d, io, mode, s);
+    cudaEvent_t e0 = nullptr, em = nullptr, e1 = nullptr;
+    if (h->profiling) {
+        cudaEventCreate(&e0); cudaEventCreate(&em); cudaEventCreate(&e1);
+        h->ev.push_back(e0); h->ev.push_back(em); h->ev.push_back(e1);
+        cudaEventRecord(e0, s);
+    }
+    const bool two = mode == IK_MODE_TICK && h->d.slow_list;
+    if (h->profiling && !two) cudaEventRecord(em, s);
+    cudaError_t e = launch_ik(h->d, io, mode, s, (h->profiling && two) ? em : nullptr);
     if (h->profiling) cudaEventRecord(e1, s);
     h->launches += (mode == IK_MODE_TICK && h->d.slow_list) ? 2 : 1;
     if (e != cudaSuccess) {
@@ -234,7 +241,7 @@ wc_status wc_ik_solve_with_jacobians_dev(wc_ik* h, const double* q_meas,
     return launch_checked(h, io, IK_MODE_EXT_KIN, static_cast<cudaStream_t>(stream), "wc_ik_solve_with_jacobians_dev");
 }
 
-wc_status wc_ik_tick_host(wc_ik* h, const double* q_meas, const double* q_lin, const double* base_H,
+wc_status wc_ik_tick_host_async(wc_ik* h, const double* q_meas, const double* q_lin, const double* base_H,
                           const uint8_t* left_is_fixed, const double* lf_H_des, const double* rf_H_des,
                           const double* lf_twist, const double* rf_twist, const double* com_pos_des,
                           const double* com_vel_des, const double* com_meas, const double* neck_R_des,
@@ -279,12 +286,35 @@ wc_status wc_ik_tick_host(wc_ik* h, const double* q_meas, const double* q_lin, c
     D2H(dq, p_dq, nJ * B * 8); D2H(lf_err, p_le, 6 * B * 8); D2H(rf_err, p_re, 6 * B * 8);
     D2H(qp_status, p_st, B * 4); D2H(nwsr, p_nw, B * 4);
 #undef D2H
-    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
     if (e != cudaSuccess) {
-        std::fprintf(stderr, "[wc_ik_tick_host] CUDA error: %s\n", cudaGetErrorString(e));
+        std::fprintf(stderr, "[wc_ik_tick_host_async] CUDA error: %s\n", cudaGetErrorString(e));
         return WC_ERR_CUDA;
     }
     return WC_OK;
+}
+
+wc_status wc_ik_sync(wc_ik* h)
+{
+    if (!h) return WC_ERR_INVALID_ARG;
+    if (!h->host_stream) return WC_OK;
+    if (cudaSetDevice(h->device) != cudaSuccess) return WC_ERR_CUDA;
+    const cudaError_t e = cudaStreamSynchronize(h->host_stream);
+    if (e != cudaSuccess) {
+        std::fprintf(stderr, "[wc_ik_sync] CUDA error: %s\n", cudaGetErrorString(e));
+        return WC_ERR_CUDA;
+    }
+    return WC_OK;
+}
+
+wc_status wc_ik_tick_host(wc_ik* h, const double* q_meas, const double* q_lin, const double* base_H,
+                          const uint8_t* left_is_fixed, const double* lf_H_des, const double* rf_H_des,
+                          const double* lf_twist, const double* rf_twist, const double* com_pos_des,
+                          const double* com_vel_des, const double* com_meas, const double* neck_R_des,
+                          double* dq, double* lf_err, double* rf_err, int32_t* qp_status, int32_t* nwsr)
+{
+    const wc_status rc = wc_ik_tick_host_async(h, q_meas, q_lin, base_H, left_is_fixed, lf_H_des, rf_H_des, lf_twist, rf_twist,
+                                               com_pos_des, com_vel_des, com_meas, neck_R_des, dq, lf_err, rf_err, qp_status, nwsr);
+    return rc != WC_OK ? rc : wc_ik_sync(h);
 }
 
 namespace {
@@ -386,16 +416,26 @@ wc_status wc_ik_kernel_times_ms(wc_ik* h, double* ik_ms, int64_t* launches)
     if (!h) return WC_ERR_INVALID_ARG;
     if (cudaSetDevice(h->device) != cudaSuccess) return WC_ERR_CUDA;
     if (cudaDeviceSynchronize() != cudaSuccess) return WC_ERR_CUDA;
-    for (size_t k = 0; k + 1 < h->ev.size(); k += 2) {
-        float a = 0;
-        cudaEventElapsedTime(&a, h->ev[k], h->ev[k + 1]);
-        h->ms_acc += a; h->timed += 1;
+    for (size_t k = 0; k + 2 < h->ev.size(); k += 3) {
+        float a = 0, f = 0;
+        cudaEventElapsedTime(&a, h->ev[k], h->ev[k + 2]);
+        cudaEventElapsedTime(&f, h->ev[k], h->ev[k + 1]);
+        h->ms_acc += a; h->fast_ms_acc += f; h->timed += 1;
     }
     for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
     h->ev.clear();
     if (ik_ms) *ik_ms = h->ms_acc;
     if (launches) *launches = h->timed;
-    h->ms_acc = 0; h->timed = 0;
+    h->detail[0] = h->fast_ms_acc; h->detail[1] = h->ms_acc - h->fast_ms_acc;
+    h->ms_acc = 0; h->timed = 0; h->fast_ms_acc = 0;
+    return WC_OK;
+}
+
+wc_status wc_ik_kernel_times_detail_ms(wc_ik* h, double* fast_ms, double* general_ms)
+{
+    if (!h) return WC_ERR_INVALID_ARG;
+    if (fast_ms) *fast_ms = h->detail[0];
+    if (general_ms) *general_ms = h->detail[1];
     return WC_OK;
 }
 

@@ -29,9 +29,10 @@ struct wc_mpc {
     cudaStream_t host_stream;
     // optional per-kernel timing (wc_mpc_enable_profiling): events recorded on the launch stream
     int profiling;
-    std::vector<cudaEvent_t> ev; // triples (start, after K1, after K2)
-    double prep_ms_acc, admm_ms_acc;
+    std::vector<cudaEvent_t> ev; // quintuples (start, after K1, after setup, after phase 1, after K2)
+    double prep_ms_acc, admm_ms_acc, setup_ms_acc, phase1_ms_acc, phase2_ms_acc;
     int64_t timed_ticks;
+    double detail[3]; // setup / phase 1 / phase 2 of the last wc_mpc_kernel_times_ms window
 };
 
 namespace {
@@ -84,6 +85,7 @@ wc_status wc_mpc_create(const wc_mpc_config* cfg, int32_t B, int32_t device, wc_
     h->pin_in = h->pin_out = h->dev_in = h->dev_out = nullptr;
     h->host_stream = nullptr;
     h->profiling = 0; h->prep_ms_acc = 0; h->admm_ms_acc = 0; h->timed_ticks = 0;
+    h->setup_ms_acc = h->phase1_ms_acc = h->phase2_ms_acc = 0;
     MpcDev& d = h->d;
     std::memset(&d, 0, sizeof(d));
     d.B = B;
@@ -229,16 +231,23 @@ wc_status wc_mpc_tick_dev(wc_mpc* h, const double* lf_H, const double* rf_H,
     // gradient ring: stage k of this tick lives in slot (head + k) mod (N+1); advancing the head by
     // one per tick is MPCSolver::setGradient's block shift (MPCSolver.cpp:216-221)
     h->d.ring_head = (int)(h->tick % (int64_t)(h->d.N + 1));
-    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     if (h->profiling) {
-        for (int k = 0; k < 3; k++) { cudaEventCreate(&ev[k]); h->ev.push_back(ev[k]); }
+        for (int k = 0; k < 5; k++) { cudaEventCreate(&ev[k]); h->ev.push_back(ev[k]); }
         cudaEventRecord(ev[0], s);
     }
     launch_mpc_prepare(h->d, io, s);
     cudaError_t e = cudaGetLastError();
     if (h->profiling) cudaEventRecord(ev[1], s);
-    if (e == cudaSuccess) e = h->chain ? launch_mpc_chain(h->d, io, s) : launch_mpc_admm(h->d, io, h->lanes, s);
-    if (h->profiling) cudaEventRecord(ev[2], s);
+    if (e == cudaSuccess) {
+        if (h->chain) e = launch_mpc_chain(h->d, io, s, h->profiling ? &ev[2] : nullptr);
+        else {
+            if (h->profiling) { cudaEventRecord(ev[2], s); }
+            e = launch_mpc_admm(h->d, io, h->lanes, s);
+            if (h->profiling) { cudaEventRecord(ev[3], s); }
+        }
+    }
+    if (h->profiling) cudaEventRecord(ev[4], s);
     h->launches += h->chain ? 4 : 2;
     h->tick += 1;
     if (e != cudaSuccess) {
@@ -248,7 +257,7 @@ wc_status wc_mpc_tick_dev(wc_mpc* h, const double* lf_H, const double* rf_H,
     return WC_OK;
 }
 
-wc_status wc_mpc_tick_host(wc_mpc* h, const double* lf_H, const double* rf_H,
+wc_status wc_mpc_tick_host_async(wc_mpc* h, const double* lf_H, const double* rf_H,
                            const uint8_t* l_contact, const uint8_t* r_contact,
                            const double* dcm_meas, const double* ref, const uint8_t* reset,
                            double* zmp, int32_t* osqp_status, int32_t* iters, int32_t* flags)
@@ -294,12 +303,33 @@ wc_status wc_mpc_tick_host(wc_mpc* h, const double* lf_H, const double* rf_H,
 #define D2H(dst, off, bytes) do { if ((dst) && e == cudaSuccess) e = cudaMemcpyAsync((dst), dout + (off), (bytes), cudaMemcpyDeviceToHost, s); } while (0)
     D2H(zmp, p_zmp, 2 * B * 8); D2H(osqp_status, p_st, B * 4); D2H(iters, p_it, B * 4); D2H(flags, p_fl, B * 4);
 #undef D2H
-    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
     if (e != cudaSuccess) {
-        std::fprintf(stderr, "[wc_mpc_tick_host] CUDA error: %s\n", cudaGetErrorString(e));
+        std::fprintf(stderr, "[wc_mpc_tick_host_async] CUDA error: %s\n", cudaGetErrorString(e));
         return WC_ERR_CUDA;
     }
     return WC_OK;
+}
+
+wc_status wc_mpc_sync(wc_mpc* h)
+{
+    if (!h) return WC_ERR_INVALID_ARG;
+    if (!h->host_stream) return WC_OK;
+    if (cudaSetDevice(h->device) != cudaSuccess) return WC_ERR_CUDA;
+    const cudaError_t e = cudaStreamSynchronize(h->host_stream);
+    if (e != cudaSuccess) {
+        std::fprintf(stderr, "[wc_mpc_sync] CUDA error: %s\n", cudaGetErrorString(e));
+        return WC_ERR_CUDA;
+    }
+    return WC_OK;
+}
+
+wc_status wc_mpc_tick_host(wc_mpc* h, const double* lf_H, const double* rf_H,
+                           const uint8_t* l_contact, const uint8_t* r_contact,
+                           const double* dcm_meas, const double* ref, const uint8_t* reset,
+                           double* zmp, int32_t* osqp_status, int32_t* iters, int32_t* flags)
+{
+    const wc_status rc = wc_mpc_tick_host_async(h, lf_H, rf_H, l_contact, r_contact, dcm_meas, ref, reset, zmp, osqp_status, iters, flags);
+    return rc != WC_OK ? rc : wc_mpc_sync(h);
 }
 
 wc_status wc_mpc_debug_get_host(wc_mpc* h, double* primal, double* rho, int32_t* rho_updates)
@@ -336,19 +366,36 @@ wc_status wc_mpc_kernel_times_ms(wc_mpc* h, double* prepare_ms, double* admm_ms,
     if (!h) return WC_ERR_INVALID_ARG;
     if (cudaSetDevice(h->device) != cudaSuccess) return WC_ERR_CUDA;
     if (cudaDeviceSynchronize() != cudaSuccess) return WC_ERR_CUDA;
-    for (size_t k = 0; k + 2 < h->ev.size(); k += 3) {
-        float a = 0, b = 0;
+    for (size_t k = 0; k + 4 < h->ev.size(); k += 5) {
+        float a = 0, b = 0, c1 = 0, c2 = 0, c3 = 0;
         cudaEventElapsedTime(&a, h->ev[k], h->ev[k + 1]);
-        cudaEventElapsedTime(&b, h->ev[k + 1], h->ev[k + 2]);
+        cudaEventElapsedTime(&b, h->ev[k + 1], h->ev[k + 4]);
+        cudaEventElapsedTime(&c1, h->ev[k + 1], h->ev[k + 2]);
+        cudaEventElapsedTime(&c2, h->ev[k + 2], h->ev[k + 3]);
+        cudaEventElapsedTime(&c3, h->ev[k + 3], h->ev[k + 4]);
         h->prep_ms_acc += a; h->admm_ms_acc += b; h->timed_ticks += 1;
+        h->setup_ms_acc += c1; h->phase1_ms_acc += c2; h->phase2_ms_acc += c3;
     }
     for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
     h->ev.clear();
     if (prepare_ms) *prepare_ms = h->prep_ms_acc;
     if (admm_ms) *admm_ms = h->admm_ms_acc;
     if (ticks) *ticks = h->timed_ticks;
+    h->detail[0] = h->setup_ms_acc; h->detail[1] = h->phase1_ms_acc; h->detail[2] = h->phase2_ms_acc;
     h->prep_ms_acc = 0; h->admm_ms_acc = 0; h->timed_ticks = 0;
+    h->setup_ms_acc = h->phase1_ms_acc = h->phase2_ms_acc = 0;
     return WC_OK;
 }
+
+wc_status wc_mpc_kernel_times_detail_ms(wc_mpc* h, double* setup_ms, double* phase1_ms, double* phase2_ms)
+{
+    if (!h) return WC_ERR_INVALID_ARG;
+    if (setup_ms) *setup_ms = h->detail[0];
+    if (phase1_ms) *phase1_ms = h->detail[1];
+    if (phase2_ms) *phase2_ms = h->detail[2];
+    return WC_OK;
+}
+
+int32_t wc_mpc_path(const wc_mpc* h) { return h ? h->chain : -1; }
 
 } // extern "C"
