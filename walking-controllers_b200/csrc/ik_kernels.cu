@@ -625,24 +625,25 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) ik_kernel(IkDev d, IkTick
     bool rank_def = false;
 #pragma unroll 1
     for (int k = 0; k < NC; k++) { // rolled on purpose: the body is ~29 x 8 instructions, 15 copies thrash the I-cache
-        // owner lane k builds the reflector and publishes it (double-buffered) in shared memory
+        // Reflector of column k, built by the whole warp: the owner publishes its column (T is register
+        // resident and k is a run-time index, so one predicated store per row is far cheaper than selecting
+        // T[k..] out of the registers), lane r takes row r, the norm is a warp reduction.
         double* vs = VS + (k & 1) * 32;
         if (lane == k) {
-            double sig = 0.0, tk = 0.0;
 #pragma unroll
-            for (int r = 0; r < NV; r++) { sig += (r >= k) ? T[r] * T[r] : 0.0; tk = (r == k) ? T[r] : tk; }
-            const double nrm = sqrt(sig);
-            const double alpha = tk > 0 ? -nrm : nrm;
-#pragma unroll
-            for (int r = 0; r < NV; r++) vs[r] = (r < k) ? 0.0 : ((r == k) ? tk - alpha : T[r]);
-            vs[29] = nrm;
-            vs[30] = 1.0 / (sig - tk * alpha);
-#pragma unroll
-            for (int r = 0; r < NV; r++) T[r] = (r < k) ? T[r] : ((r == k) ? alpha : 0.0);
+            for (int r = 0; r < NV; r++) vs[r] = T[r];
         }
         __syncwarp();
-        const double nrm_b = vs[29], beta = vs[30];
+        const double xr = (lane >= k && lane < NV) ? vs[lane] : 0.0;
+        const double sig = warp_sum(xr * xr);
+        const double tk = __shfl_sync(FULL, xr, k);
+        const double nrm_b = sqrt(sig);
         if (nrm_b <= kRankTol * (amax > 1.0 ? amax : 1.0)) { rank_def = true; break; }
+        const double alpha = tk > 0 ? -nrm_b : nrm_b;
+        const double beta = 1.0 / (sig - tk * alpha);
+        __syncwarp();
+        vs[lane] = (lane == k) ? tk - alpha : xr;
+        __syncwarp();
         double tauT = 0.0, tauG = 0.0;
 #pragma unroll
         for (int r = 0; r < NV; r++) {
@@ -651,7 +652,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) ik_kernel(IkDev d, IkTick
             tauG += v * G[r];
         }
         tauT *= beta; tauG *= beta;
-        if (!(lane > k && lane < NC)) tauT = 0.0;
+        // the owner's own column is reflected too: it becomes (.., alpha, ~0, ..) up to rounding; the entries
+        // below the diagonal are never read again
+        if (!(lane >= k && lane < NC)) tauT = 0.0;
 #pragma unroll
         for (int r = 0; r < NV; r++) {
             const double v = vs[r];
