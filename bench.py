@@ -112,6 +112,15 @@ class ClockSampler:
         return out
 
 
+def ncu_traffic(kernel):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/ncu_traffic.json)"""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        return json.load(open(p)).get(kernel, {}).get("bytes_per_launch")
+    except Exception:
+        return None
+
+
 def pct(v, q):
     v = sorted(v)
     return v[min(len(v) - 1, int(round(q * (len(v) - 1))))]
@@ -129,7 +138,7 @@ def run_reference(args, world, rank):
     syn = importlib.import_module("walking-controllers_b200.synthetic")
     O.build()
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
-    B, N = CPU_SAMPLE_B, HORIZON
+    B, N = CPU_SAMPLE_B, args.horizon
     steps, warm = args.steps, args.warmup
     T = steps + warm
     g = syn.GaitBatch(B, T, N)
@@ -223,7 +232,7 @@ def run_ours(args, world, rank, local_rank):
     torch.cuda.set_device(dev)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    B, N = B_PER_GPU, HORIZON
+    B, N = args.batch, args.horizon
     steps, warm = args.steps, args.warmup
     T = warm + steps
 
@@ -384,9 +393,18 @@ def run_ours(args, world, rank, local_rank):
                       "new_solver_frac": new_frac, "qpik_success_frac": ik_ok, "qpik_nwsr_mean": wsc_mean,
                       "qpik_active_set_frac": ws_frac},
             "roofline": {"bound": "hbm", "kernel": dom_name, "kernel_ms": dom_ms, "achieved": achieved, "peak": hbm_peak,
-                         "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "unit": "GB/s", "frac": achieved / hbm_peak,
+                         "traffic": ncu_traffic(dom_name) if (B == B_PER_GPU and N == HORIZON) else None,
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": bt["mpc"] * B,
-                         "note": "path is FP64-latency/issue bound, not HBM bound (DESIGN.md); see fp64"},
+                         "note": "the path is not HBM bound (DESIGN.md §5): phase 1 is bound by the shared-memory pipe, see smem / fp64; "
+                                 "traffic exceeds the algorithmic bytes because the LDL' factors and the scaling vectors are "
+                                 "staged from HBM each tick instead of being recomputed"},
+            # shared-memory roofline of the dominant kernel: 650 LDS/STS.64 per thread-iteration
+            "smem": {"bound": "shared memory", "achieved": 650 * 8 * 2 * B * it_mean / (dom_ms * 1e-3) * 1e-9 if mpc.path == "chain" else None,
+                     "peak": 128 * 148 * 1.965, "unit": "GB/s",
+                     "frac": (650 * 8 * 2 * B * it_mean / (dom_ms * 1e-3) * 1e-9) / (128 * 148 * 1.965) if mpc.path == "chain" else None,
+                     "peak_source": "128 B/clk/SM x 148 SMs x 1.965 GHz (B300_MICROARCH.md smem crossbar), N = 25 access count"},
             "fp64": {"peak_gflops_measured": fp64_peak,
                      "mpc_admm_gflops": f_mpc * B / (admm_avg_ms * 1e-3) * 1e-9,
                      "fk_qpik_gflops": f_ik * B / (ik_avg_ms * 1e-3) * 1e-9,
@@ -416,6 +434,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--horizon", type=int, default=HORIZON, help="MPC horizon N (default: BASELINE configs[2], 25)")
+    ap.add_argument("--batch", type=int, default=B_PER_GPU, help="instances per GPU (default 65536)")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

@@ -13,12 +13,13 @@ REL = 1e-6
 
 @pytest.fixture(autouse=True, params=["auto", "coop"])
 def mpc_path(request, monkeypatch):
-    """every test runs on both ADMM kernels: "auto" = chain-per-thread kernel where the horizon fits in
-    shared memory (mpc_chain.cu) else the cooperative kernel; "coop" = cooperative kernel (mpc_kernels.cu)"""
+    """every test runs on both ADMM kernel families: "auto" = chain-per-thread kernels (mpc_chain.cu; forced with
+    WC_MPC_PATH=chain so that long horizons with 8, 4, ... instances per CTA are covered too, N = 1 falls back),
+    "coop" = cooperative kernel (mpc_kernels.cu)"""
     if request.param == "coop":
         monkeypatch.setenv("WC_MPC_PATH", "coop")
     else:
-        monkeypatch.delenv("WC_MPC_PATH", raising=False)
+        monkeypatch.setenv("WC_MPC_PATH", "chain")
     return request.param
 
 
@@ -32,6 +33,9 @@ def run_both(wc, syn, oracle, cuda_device, B, T, N, seed=0x5EED, host_api=False,
         for k, v in settings.items():
             setattr(cfg_o.osqp, k, v); setattr(cfg_g.osqp, k, v)
     mo = oracle.MpcBatch(cfg_o, B)
+    if N < 2:
+        import os
+        os.environ.pop("WC_MPC_PATH", None)  # the chain kernels need N >= 2: default (cooperative) path
     mg = wc.MpcBatch(cfg_g, B)
     if weights is not None:
         q, r = weights
@@ -84,7 +88,7 @@ def test_mpc_parity_host_api(wc, syn, oracle, cuda_device):
     run_both(wc, syn, oracle, cuda_device, B=33, T=40, N=25, host_api=True, seed=7)
 
 
-@pytest.mark.parametrize("N", [1, 2, 10, 50, 100])
+@pytest.mark.parametrize("N", [1, 2, 10, 50, 100, 200])
 def test_mpc_parity_horizons(wc, syn, oracle, cuda_device, N):
     run_both(wc, syn, oracle, cuda_device, B=20, T=30, N=N, seed=100 + N)
 

@@ -45,7 +45,7 @@ namespace wcb {
 namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
-constexpr int kIPW = 16; // instances per warp
+constexpr int kIPWmax = 16; // instances per warp at short horizons; 8, 4, 2, 1 as the per-chain working set grows
 // stages per trip of the forward / backward loops: enough straight-line code for ptxas to overlap the
 // loads of later stages with the FMA chain of the current one, small enough to stay in the instruction cache
 #ifndef WC_CHAIN_UNROLL
@@ -60,13 +60,14 @@ __device__ __forceinline__ double limit_scaling_c(double v)
     return v;
 }
 
-// lane-interleaved per-thread arrays
+// lane-interleaved per-thread arrays; IPW = instances per CTA (one partial warp of 2*IPW threads)
+template <int IPW>
 struct ChainSmem {
     double* base;  // + lane
     double* hbase; // per-instance block, + slot
     int nR, N;
-    __device__ __forceinline__ double& at(int arr_off, int k) const { return base[(arr_off + k) * 32]; }
-    __device__ __forceinline__ double& hat(int arr, int h) const { return hbase[(arr * 8 + h) * kIPW]; }
+    __device__ __forceinline__ double& at(int arr_off, int k) const { return base[(arr_off + k) * (2 * IPW)]; }
+    __device__ __forceinline__ double& hat(int arr, int h) const { return hbase[(arr * 8 + h) * IPW]; }
 };
 
 // array offsets (in elements per thread) for horizon N
@@ -101,7 +102,7 @@ __device__ __forceinline__ void cp_async_wait_all()
 
 // exchanges between the two axis lanes of an instance: always under the PAIR mask, so that they are
 // legal inside branches that are uniform for the pair but not for the warp
-__device__ __forceinline__ double pair_max(double v, unsigned pm) { return fmax(v, __shfl_xor_sync(pm, v, 16)); }
+__device__ __forceinline__ double pair_max(double v, unsigned pm, int dist) { return fmax(v, __shfl_xor_sync(pm, v, dist)); }
 
 // dense 4x4 LDL' of the corner, order [u0x, u0y, x0x, x0y]; CF: L (6 strict-lower, row-major) + 4 Dinv
 __device__ __forceinline__ void factor_corner_c(const double* Sx, const double* Sy, double kxy, double* CF)
@@ -146,7 +147,7 @@ __device__ __forceinline__ void solve_corner_c(const double* CF, double* r)
 // in HBM.  Called by both lanes of an instance (pair-uniform); `write` masks the stores.
 __device__ __noinline__ void chain_factor(const MpcDev& d, int i, int a, int N, double c, double rho_now, int nh,
                                           unsigned pmask, bool write, const double* Dsrc = nullptr,
-                                          const double* Esrc = nullptr)
+                                          const double* Esrc = nullptr, int pair_dist = 16)
 {
     const size_t B = (size_t)d.B;
     const int nA = 2 * N + 1, nR = N + 1;
@@ -161,7 +162,7 @@ __device__ __noinline__ void chain_factor(const MpcDev& d, int i, int a, int N, 
     double* l2g = d.L2 + (size_t)(a * nA) * B + i;
     double* dig = d.DI + (size_t)(a * nA) * B + i;
     const double du0 = Dg[(size_t)(nR) * sB];
-    const double du0o = __shfl_xor_sync(pmask, du0, 16);
+    const double du0o = __shfl_xor_sync(pmask, du0, pair_dist);
     const double dux = a == 0 ? du0 : du0o, duy = a == 0 ? du0o : du0;
     double hd = 0.0, kxy = 0.0;
     for (int h = 0; h < nh; h++) {
@@ -226,7 +227,7 @@ __device__ __noinline__ void chain_factor(const MpcDev& d, int i, int a, int N, 
     }
     double So[3], CF[10];
 #pragma unroll
-    for (int r = 0; r < 3; r++) So[r] = __shfl_xor_sync(pmask, S3[r], 16);
+    for (int r = 0; r < 3; r++) So[r] = __shfl_xor_sync(pmask, S3[r], pair_dist);
     if (a == 0) factor_corner_c(S3, So, kxy, CF);
     else factor_corner_c(So, S3, kxy, CF);
     if (write && a == 0) {
@@ -393,13 +394,16 @@ __global__ void __launch_bounds__(kSetupWarps * 32) mpc_chain_setup_kernel(MpcDe
 // ADMM.  PHASE2 == false: all instances, iterations 1 .. first termination check.
 //        PHASE2 == true : the instances of the continuation list, until osqp_solve returns.
 // =====================================================================================
-template <bool PHASE2, int NT>
-__global__ void __launch_bounds__(32) mpc_chain_kernel(MpcDev d, MpcTickIO io)
+template <bool PHASE2, int NT, int IPW>
+__global__ void __launch_bounds__(2 * IPW) mpc_chain_kernel(MpcDev d, MpcTickIO io)
 {
     extern __shared__ double smem_all[];
+    // one (partial) warp per CTA: lanes [0, IPW) the x axes, [IPW, 2 IPW) the y axes of the same IPW instances
+    constexpr int kIPW = IPW;
+    constexpr unsigned WMASK = (2 * IPW == 32) ? 0xffffffffu : ((1u << (2 * IPW)) - 1u);
     const int lane = threadIdx.x;
-    const int slot = lane & 15, a = lane >> 4;
-    const unsigned pmask = (1u << slot) | (1u << (slot + 16));
+    const int slot = lane % IPW, a = lane / IPW;
+    const unsigned pmask = (1u << slot) | (1u << (slot + IPW));
     const size_t B = (size_t)d.B;
     const int N = NT > 0 ? NT : d.N, nA = 2 * N + 1, nR = N + 1; // NT > 0: compile-time horizon
     const Off O(N);
@@ -417,7 +421,7 @@ __global__ void __launch_bounds__(32) mpc_chain_kernel(MpcDev d, MpcTickIO io)
         valid = ii < (long long)d.B;
         i = valid ? (int)ii : d.B - 1;
     }
-    ChainSmem s{smem_all + lane, smem_all + (size_t)O.total * 32 + slot, nR, N};
+    ChainSmem<IPW> s{smem_all + lane, smem_all + (size_t)O.total * (2 * IPW) + slot, nR, N};
 #define A_(o, k) s.at(O.o, (k))
 #define H_(arr, h) s.hat((arr), (h))
 
@@ -503,7 +507,7 @@ __global__ void __launch_bounds__(32) mpc_chain_kernel(MpcDev d, MpcTickIO io)
         A_(QX, k) = (A_(QX, k) * dx) * c;
     }
     const double qu0 = ((-(Ra * upa)) * du0_scale) * c; // scaled q of u_0; the other input entries are zero
-    const double du0_other = __shfl_xor_sync(pmask, du0_scale, 16);
+    const double du0_other = __shfl_xor_sync(pmask, du0_scale, IPW);
     if (a == 0) {
         const double dux = du0_scale, duy = du0_other;
 #pragma unroll
@@ -518,7 +522,7 @@ __global__ void __launch_bounds__(32) mpc_chain_kernel(MpcDev d, MpcTickIO io)
     // equality row 0: l = u = -dcm (MPCSolver.cpp:143-146), scaled by E
     const double lb0 = -dcm_a * e0;
     double z0prev = (cold || PHASE2) ? (PHASE2 ? lb0 : 0.0) : z0_in;
-    __syncwarp();
+    __syncwarp(WMASK);
 
     // ------------------------------------------------------------------ ADMM (osqp_solve)
     int status = WC_OSQP_UNSOLVED;
@@ -622,7 +626,7 @@ __global__ void __launch_bounds__(32) mpc_chain_kernel(MpcDev d, MpcTickIO io)
         // hull rows: split between the two lanes of the pair
         {
             const double xu0 = A_(XU, 0);
-            const double xu0o = __shfl_xor_sync(pmask, xu0, 16);
+            const double xu0o = __shfl_xor_sync(pmask, xu0, IPW);
             const double ux = a == 0 ? xu0 : xu0o, uy = a == 0 ? xu0o : xu0;
             for (int h = a; h < nh; h += 2) {
                 const double ax = H_(H_HX, h) * ux + H_(H_HY, h) * uy;
@@ -634,13 +638,13 @@ __global__ void __launch_bounds__(32) mpc_chain_kernel(MpcDev d, MpcTickIO io)
                 m_ax_s = fmax(m_ax_s, fabs(ax)); m_ax_u = fmax(m_ax_u, fabs(einv * ax));
             }
         }
-        pri_res = pair_max(m_rp_u, pmask); rp_s = pair_max(m_rp_s, pmask);
-        nz_u = pair_max(m_z_u, pmask); nz_s = pair_max(m_z_s, pmask);
-        nAx_u = pair_max(m_ax_u, pmask); nAx_s = pair_max(m_ax_s, pmask);
-        dua_res = cinv * pair_max(m_rd_u, pmask); rd_s = pair_max(m_rd_s, pmask);
-        nq_u = cinv * pair_max(m_q_u, pmask); nq_s = pair_max(m_q_s, pmask);
-        nAty_u = cinv * pair_max(m_aty_u, pmask); nAty_s = pair_max(m_aty_s, pmask);
-        nPx_u = cinv * pair_max(m_px_u, pmask); nPx_s = pair_max(m_px_s, pmask);
+        pri_res = pair_max(m_rp_u, pmask, IPW); rp_s = pair_max(m_rp_s, pmask, IPW);
+        nz_u = pair_max(m_z_u, pmask, IPW); nz_s = pair_max(m_z_s, pmask, IPW);
+        nAx_u = pair_max(m_ax_u, pmask, IPW); nAx_s = pair_max(m_ax_s, pmask, IPW);
+        dua_res = cinv * pair_max(m_rd_u, pmask, IPW); rd_s = pair_max(m_rd_s, pmask, IPW);
+        nq_u = cinv * pair_max(m_q_u, pmask, IPW); nq_s = pair_max(m_q_s, pmask, IPW);
+        nAty_u = cinv * pair_max(m_aty_u, pmask, IPW); nAty_s = pair_max(m_aty_s, pmask, IPW);
+        nPx_u = cinv * pair_max(m_px_u, pmask, IPW); nPx_s = pair_max(m_px_s, pmask, IPW);
     };
 
     // is_primal_infeasible (OSQP auxil.c) on delta_y (global scratch written by the last iteration)
@@ -667,12 +671,12 @@ __global__ void __launch_bounds__(32) mpc_chain_kernel(MpcDev d, MpcTickIO io)
                 lhs += uh * fmax(dy, 0.0) + lh * fmin(dy, 0.0);
             }
         }
-        nrm = pair_max(nrm, pmask);
+        nrm = pair_max(nrm, pmask, IPW);
         {
-            const double lo = __shfl_xor_sync(pmask, lhs, 16);
+            const double lo = __shfl_xor_sync(pmask, lhs, IPW);
             lhs = a == 0 ? lhs + lo : lo + lhs;
         }
-        __syncwarp();
+        __syncwarp(WMASK);
         int res = 0;
         if (nrm > 1.0 / infty && lhs < -eps * nrm) {
             const double* Dig = d.Dinv + (size_t)(a * nA) * B + i;
@@ -688,7 +692,7 @@ __global__ void __launch_bounds__(32) mpc_chain_kernel(MpcDev d, MpcTickIO io)
                     m = fmax(m, fabs(aty_u * Dig[(size_t)(nR + k) * B]));
                 }
             }
-            m = pair_max(m, pmask);
+            m = pair_max(m, pmask, IPW);
             res = m < eps * nrm;
         }
         return res;
@@ -709,9 +713,9 @@ __global__ void __launch_bounds__(32) mpc_chain_kernel(MpcDev d, MpcTickIO io)
             nrm = fmax(nrm, fabs(Dg[(size_t)(nR + k) * B] * wu));
             if (k == 0) qdx += qu0 * wu;
         }
-        nrm = pair_max(nrm, pmask);
+        nrm = pair_max(nrm, pmask, IPW);
         {
-            const double qo = __shfl_xor_sync(pmask, qdx, 16);
+            const double qo = __shfl_xor_sync(pmask, qdx, IPW);
             qdx = a == 0 ? qdx + qo : qo + qdx;
         }
         int res = 0;
@@ -731,7 +735,7 @@ __global__ void __launch_bounds__(32) mpc_chain_kernel(MpcDev d, MpcTickIO io)
                     m = fmax(m, fabs(px_u * Dig[(size_t)(nR + k) * B]));
                 }
             }
-            m = pair_max(m, pmask);
+            m = pair_max(m, pmask, IPW);
             if (m < c * eps * nrm) {
                 int bad = 0;
                 for (int k = 0; k < nR; k++) {
@@ -742,7 +746,7 @@ __global__ void __launch_bounds__(32) mpc_chain_kernel(MpcDev d, MpcTickIO io)
                 }
                 {
                     const double wu0 = A_(WU, 0);
-                    const double wu0o = __shfl_xor_sync(pmask, wu0, 16);
+                    const double wu0o = __shfl_xor_sync(pmask, wu0, IPW);
                     const double ux = a == 0 ? wu0 : wu0o, uy = a == 0 ? wu0o : wu0;
                     for (int h = a; h < nh; h += 2) {
                         double ax = H_(H_HX, h) * ux + H_(H_HY, h) * uy;
@@ -752,7 +756,7 @@ __global__ void __launch_bounds__(32) mpc_chain_kernel(MpcDev d, MpcTickIO io)
                         if ((uh < infty * kMinScaling && ax > eps * nrm) || (lh > -infty * kMinScaling && ax < -eps * nrm)) bad = 1;
                     }
                 }
-                bad = (int)pair_max((double)bad, pmask);
+                bad = (int)pair_max((double)bad, pmask, IPW);
                 res = !bad;
             }
         }
@@ -772,8 +776,8 @@ __global__ void __launch_bounds__(32) mpc_chain_kernel(MpcDev d, MpcTickIO io)
         if (dua_res < eps_dual) drc = 1;
         const bool live = !done && !non_cvx;
         const bool need_pi = live && !prc, need_di = live && !drc;
-        if (__any_sync(FULL, need_pi)) { const int r = primal_infeasible(epi); if (need_pi) prim_inf = r; }
-        if (__any_sync(FULL, need_di)) { const int r = dual_infeasible(edi); if (need_di) dual_inf = r; }
+        if (__any_sync(WMASK, need_pi)) { const int r = primal_infeasible(epi); if (need_pi) prim_inf = r; }
+        if (__any_sync(WMASK, need_di)) { const int r = dual_infeasible(edi); if (need_di) dual_inf = r; }
         if (non_cvx) return WC_OSQP_NON_CVX;
         if (prc && drc) return approximate ? WC_OSQP_SOLVED_INACCURATE : WC_OSQP_SOLVED;
         if (prim_inf) return approximate ? WC_OSQP_PRIMAL_INFEASIBLE_INACCURATE : WC_OSQP_PRIMAL_INFEASIBLE;
@@ -792,7 +796,7 @@ __global__ void __launch_bounds__(32) mpc_chain_kernel(MpcDev d, MpcTickIO io)
     int iter = PHASE2 ? phase1_len : 0;
     int to_check = chk ? chk - (iter % chk) : 0;
     int to_adapt = adaptive ? rint - (iter % rint) : 0;
-    bool warp_busy = __any_sync(FULL, !done);
+    bool warp_busy = __any_sync(WMASK, !done);
     while (warp_busy) {
         iter++;
         const bool act = !done;
@@ -848,7 +852,7 @@ __global__ void __launch_bounds__(32) mpc_chain_kernel(MpcDev d, MpcTickIO io)
         // ---- corner: dense 4x4 on [u0x, u0y, x0x, x0y], redundantly on both lanes of the pair
         double xt_x0;
         {
-            const double ou = __shfl_xor_sync(pmask, xt_u0, 16), ox = __shfl_xor_sync(pmask, xt_u0o, 16);
+            const double ou = __shfl_xor_sync(pmask, xt_u0, IPW), ox = __shfl_xor_sync(pmask, xt_u0o, IPW);
             double r[4];
             if (a == 0) { r[0] = xt_u0; r[1] = ou; r[2] = xt_u0o; r[3] = ox; }
             else { r[0] = ou; r[1] = xt_u0; r[2] = ox; r[3] = xt_u0o; }
@@ -856,7 +860,7 @@ __global__ void __launch_bounds__(32) mpc_chain_kernel(MpcDev d, MpcTickIO io)
             xt_u0 = (a == 0) ? r[0] : r[1];
             xt_x0 = (a == 0) ? r[2] : r[3];
             // ---- hull rows (z~ = A x~): update_z / update_y, rows split between the two lanes
-            __syncwarp(); // all reads of ZH / YH by the forward pass are done
+            __syncwarp(WMASK); // all reads of ZH / YH by the forward pass are done
             if (act) {
                 for (int h = a; h < nh; h += 2) {
                     const double zt = H_(H_HX, h) * r[0] + H_(H_HY, h) * r[1];
@@ -920,7 +924,7 @@ __global__ void __launch_bounds__(32) mpc_chain_kernel(MpcDev d, MpcTickIO io)
             if (keep_delta) backward(std::true_type{});
             else backward(std::false_type{});
         }
-        __syncwarp(); // hull z / y of this iteration visible to both lanes
+        __syncwarp(WMASK); // hull z / y of this iteration visible to both lanes
         // ---- termination / adaptive rho (pair-uniform decisions, warp-uniform barriers)
         if (check_now) {
             update_info();
@@ -940,15 +944,15 @@ __global__ void __launch_bounds__(32) mpc_chain_kernel(MpcDev d, MpcTickIO io)
                     rho_updates++;
                 }
             }
-            __syncwarp();
+            __syncwarp(WMASK);
             // warp-uniform; pairs whose rho did not change recompute the same factors
-            chain_factor(d, i, a, N, c, rho, nh, pmask, !skip);
-            __syncwarp();
+            chain_factor(d, i, a, N, c, rho, nh, pmask, !skip, nullptr, nullptr, IPW);
+            __syncwarp(WMASK);
             load_factor();
             cp_async_wait_all();
 #pragma unroll
             for (int r = 0; r < 10; r++) CF[r] = d.CF[(size_t)r * B + i];
-            __syncwarp();
+            __syncwarp(WMASK);
         }
         if (iter >= max_iter) { // warp-uniform: osqp_solve leaves the loop
             if (!check_now) {
@@ -965,9 +969,9 @@ __global__ void __launch_bounds__(32) mpc_chain_kernel(MpcDev d, MpcTickIO io)
             }
         }
         if (!PHASE2 && iter >= phase1_len) break; // unfinished instances go to the continuation list
-        warp_busy = __any_sync(FULL, !done);
+        warp_busy = __any_sync(WMASK, !done);
     }
-    __syncwarp();
+    __syncwarp(WMASK);
 
     // ------------------------------------------------------------------ epilogue: store_solution + controller checks
     const bool unfinished = !skip && !done; // phase 1 only
@@ -991,8 +995,8 @@ __global__ void __launch_bounds__(32) mpc_chain_kernel(MpcDev d, MpcTickIO io)
     }
     // desired ZMP of both axes on the x lane
     const double u0_mine = A_(XU, 0) * du0_scale;
-    const double u0_other = __shfl_xor_sync(pmask, u0_mine, 16);
-    const double up_other = __shfl_xor_sync(pmask, upa, 16);
+    const double u0_other = __shfl_xor_sync(pmask, u0_mine, IPW);
+    const double up_other = __shfl_xor_sync(pmask, upa, IPW);
     if (a == 0 && valid) {
         if (unfinished) {
             const int idx = atomicAdd(d.cont_count, 1);
@@ -1046,17 +1050,47 @@ __global__ void __launch_bounds__(32) mpc_chain_kernel(MpcDev d, MpcTickIO io)
 }
 
 // ------------------------------------------------------------------------------------------------
+// instances per CTA for horizon N: as many as fit in one CTA's shared memory (16 at N <= 53, ... 1 at N <= ~880)
+int mpc_chain_ipw(int N)
+{
+    const Off O(N);
+    const size_t maxs = (size_t)mpc_admm_max_smem();
+    for (int ipw = kIPWmax; ipw >= 1; ipw >>= 1)
+        if (((size_t)O.total * 2 * ipw + (size_t)H_COUNT * 8 * ipw) * sizeof(double) <= maxs) return ipw;
+    return 0;
+}
+
 size_t mpc_chain_smem_bytes(int N)
 {
     const Off O(N);
-    return ((size_t)O.total * 32 + (size_t)H_COUNT * 8 * kIPW) * sizeof(double);
+    const int ipw = mpc_chain_ipw(N);
+    return ((size_t)O.total * 2 * ipw + (size_t)H_COUNT * 8 * ipw) * sizeof(double);
 }
 
 static size_t mpc_chain_setup_warp_doubles(int N) { return (size_t)(3 * (4 * N + 2) + 2 * (2 * N + 2) + 32); }
 
+// the chain kernels run any horizon whose per-chain working set fits one CTA (1 instance per CTA at N ~ 880)
 bool mpc_chain_supported(int N)
 {
-    return N >= 2 && mpc_chain_smem_bytes(N) <= (size_t)mpc_admm_max_smem();
+    return N >= 2 && mpc_chain_ipw(N) >= 1 &&
+           mpc_chain_setup_warp_doubles(N) * kSetupWarps * sizeof(double) <= (size_t)mpc_admm_max_smem();
+}
+
+template <int NT, int IPW>
+static cudaError_t launch_chain_t(const MpcDev& d, const MpcTickIO& io, cudaStream_t s, cudaEvent_t* mid, size_t smem)
+{
+    auto k1 = mpc_chain_kernel<false, NT, IPW>;
+    auto k2 = mpc_chain_kernel<true, NT, IPW>;
+    cudaError_t e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const int blocks = (d.B + IPW - 1) / IPW;
+    if (mid) cudaEventRecord(mid[0], s); // per-kernel timing (wc_mpc_enable_profiling)
+    k1<<<blocks, 2 * IPW, smem, s>>>(d, io);
+    if (mid) cudaEventRecord(mid[1], s);
+    k2<<<blocks, 2 * IPW, smem, s>>>(d, io);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_mpc_chain(const MpcDev& d, const MpcTickIO& io, cudaStream_t s, cudaEvent_t* mid)
@@ -1065,23 +1099,22 @@ cudaError_t launch_mpc_chain(const MpcDev& d, const MpcTickIO& io, cudaStream_t 
     const size_t smem = mpc_chain_smem_bytes(N);
     const size_t td = mpc_chain_setup_warp_doubles(N);
     const size_t smem_setup = td * kSetupWarps * sizeof(double);
-    cudaError_t e;
-    // (the attribute is per function and per device; setting it again is cheap)
-    auto k1 = N == 25 ? mpc_chain_kernel<false, 25> : mpc_chain_kernel<false, 0>;
-    auto k2 = N == 25 ? mpc_chain_kernel<true, 25> : mpc_chain_kernel<true, 0>;
-    e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(mpc_chain_setup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_setup);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(mpc_chain_setup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_setup);
-    if (e != cudaSuccess) return e;
-    const int blocks = (d.B + kIPW - 1) / kIPW;
     mpc_chain_setup_kernel<<<(d.B + kSetupWarps - 1) / kSetupWarps, kSetupWarps * 32, smem_setup, s>>>(d, (int)td);
-    if (mid) cudaEventRecord(mid[0], s); // per-kernel timing (wc_mpc_enable_profiling)
-    k1<<<blocks, 32, smem, s>>>(d, io);
-    if (mid) cudaEventRecord(mid[1], s);
-    k2<<<blocks, 32, smem, s>>>(d, io);
-    return cudaGetLastError();
+    switch (mpc_chain_ipw(N)) {
+    case 16: return N == 25 ? launch_chain_t<25, 16>(d, io, s, mid, smem) : launch_chain_t<0, 16>(d, io, s, mid, smem);
+    case 8: return launch_chain_t<0, 8>(d, io, s, mid, smem);
+    case 4: return launch_chain_t<0, 4>(d, io, s, mid, smem);
+    case 2: return launch_chain_t<0, 2>(d, io, s, mid, smem);
+    case 1: return launch_chain_t<0, 1>(d, io, s, mid, smem);
+    default: return cudaErrorInvalidConfiguration;
+    }
 }
+
+// default choice of wc_mpc_create: measured on B200 (tools/sweep_horizon.sh) the chain kernels win while at least 8
+// instances share a CTA (N <= 106: 1.2x at N = 50, 1.1x at N = 100); beyond that both families are bound by the
+// sequential sweeps of a few resident instances per SM and tie (N = 200), and the cooperative kernel is kept.
+bool mpc_chain_preferred(int N) { return mpc_chain_supported(N) && mpc_chain_ipw(N) >= 8; }
 
 } // namespace wcb

@@ -111,6 +111,7 @@ void launch_mpc_export_primal(const MpcDev& d, double* primal_out, cudaStream_t 
 int mpc_admm_max_smem();
 // chain-per-thread path (mpc_chain.cu): setup of new workspaces + phase 1 + phase 2, three launches
 bool mpc_chain_supported(int N);
+bool mpc_chain_preferred(int N);
 size_t mpc_chain_smem_bytes(int N);
 // mid (nullable): two events recorded after the setup kernel and after phase 1
 cudaError_t launch_mpc_chain(const MpcDev& d, const MpcTickIO& io, cudaStream_t s, cudaEvent_t* mid);

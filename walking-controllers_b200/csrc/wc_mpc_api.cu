@@ -150,10 +150,13 @@ wc_status wc_mpc_create(const wc_mpc_config* cfg, int32_t B, int32_t device, wc_
     h->lanes = lanes;
     // short horizons: one thread per axis chain (16 instances per warp) when the working set of a warp
     // fits in shared memory; WC_MPC_PATH=coop|chain overrides (tuning / tests)
-    h->chain = mpc_chain_supported(d.N) ? 1 : 0;
+    h->chain = mpc_chain_preferred(d.N) ? 1 : 0;
     if (const char* pth = std::getenv("WC_MPC_PATH")) {
         if (!std::strcmp(pth, "coop")) h->chain = 0;
-        else if (!std::strcmp(pth, "chain") && !mpc_chain_supported(d.N)) { wc_mpc_destroy(h); return WC_ERR_UNSUPPORTED; }
+        else if (!std::strcmp(pth, "chain")) {
+            if (!mpc_chain_supported(d.N)) { wc_mpc_destroy(h); return WC_ERR_UNSUPPORTED; }
+            h->chain = 1;
+        }
     }
     if (h->chain) {
         cudaError_t e2 = cudaSuccess;
