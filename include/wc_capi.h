@@ -360,6 +360,42 @@ wc_status wc_ik_kernel_times_ms(wc_ik* h, double* ik_ms, int64_t* launches);
  * general null-space + active-set kernel (the compacted remainder, or everything when the fast path is off). */
 wc_status wc_ik_kernel_times_detail_ms(wc_ik* h, double* fast_ms, double* general_ms);
 
+/* ---------------------------------------------------------------------------------- */
+/* Closed-loop glue between the two blocks: replaces, batched,     */
+/* StableDCMModel (StableDCMModel.cpp:58-90), WalkingZMPController::evaluateControl      */
+/* (WalkingZMPController.cpp:126-172) and the joint-velocity integration of updateModule */
+/* (WalkingModule.cpp:741-744); iCub::ctrl::Integrator restated as the Tustin rule.      */
+/* Gain scheduling (minJerkTrajGen) is the caller's: gains are constants or per-instance */
+/* input arrays.                                                                         */
+/* ---------------------------------------------------------------------------------- */
+typedef struct wc_glue wc_glue;
+typedef struct wc_glue_config {
+    int32_t n_dofs;        /* actuated joints integrated by wc_glue_integrate_joints_dev */
+    int32_t reserved;
+    double sampling_time;  /* integrators' Ts */
+    double com_height;     /* omega = sqrt(gravity / com_height) (StableDCMModel.cpp:31-37) */
+    double gravity;
+    double k_zmp;          /* kZMP_walking (zmpControllerParams.ini) */
+    double k_com;          /* kCoM_walking */
+} wc_glue_config;
+void wc_glue_default_config(wc_glue_config* cfg); /* iCubGazeboV2_5 values */
+wc_status wc_glue_create(const wc_glue_config* cfg, int32_t B, int32_t device, wc_glue** out);
+void wc_glue_destroy(wc_glue* h);
+/* StableDCMModel::reset + WalkingZMPController::reset (both with com_xy [2*B], WalkingModule.cpp:470-471) and the
+ * joint integrator reset (q [nJ*B]); either pointer may be NULL to leave that part untouched.  Device pointers. */
+wc_status wc_glue_reset_dev(wc_glue* h, const double* com_xy, const double* q, void* stream);
+/* One tick of: m_stableDCMModel->setInput(dcm_des); integrateModel(); ZMP-CoM controller with feedback
+ * (zmp_meas [2*B], com_meas [>=2*B], xy rows used) and reference (zmp_des [2*B] = MPC output, LIPM CoM position /
+ * velocity) -> com_pos_des, com_vel_des [3*B] (z rows = com_z_des / com_z_vel_des [B], 0 if NULL) as passed to
+ * setDesiredCoMPosition / setDesiredCoMVelocity.  k_zmp, k_com [B] or NULL (configured constants). */
+wc_status wc_glue_com_reference_dev(wc_glue* h, const double* dcm_des, const double* zmp_des, const double* zmp_meas,
+                                    const double* com_meas, const double* com_z_des, const double* com_z_vel_des,
+                                    const double* k_zmp, const double* k_com, double* com_pos_des, double* com_vel_des,
+                                    void* stream);
+/* m_qDesired = integrator(m_dqDesired): dq [nJ*B] -> q_des [nJ*B] (may be NULL: state only). */
+wc_status wc_glue_integrate_joints_dev(wc_glue* h, const double* dq, double* q_des, void* stream);
+int64_t wc_glue_launch_count(const wc_glue* h);
+
 /* Measured FP64 FMA throughput of the device (register-resident FMA chains, all SMs), in GFLOP/s:
  * the denominator of the FP64 roofline fraction that bench.py reports next to the HBM one
  * (MEASURED_PEAKS.json carries no FP64 entry). */

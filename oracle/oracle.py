@@ -329,3 +329,56 @@ def ik_batch_tick(cfg, model, inp, kpos=None, katt=None, threads=1):
                         _dp(a["com_pos_des"]), _dp(a["com_vel_des"]), _dp(a["com_meas"]), _dp(a["neck_R_des"]),
                         _dp(kp), _dp(ka), _dp(dq), _dp(le), _dp(re), _ip(st), _ip(nw), threads)
     return dict(dq=dq, lf_err=le, rf_err=re, status=st, nwsr=nw)
+
+
+# ---- closed-loop glue (StableDCMModel + WalkingZMPController + joint integrator) -------------------------------
+class GlueConfig(C.Structure):
+    _fields_ = [("n_dofs", C.c_int32), ("reserved", C.c_int32), ("sampling_time", C.c_double),
+                ("com_height", C.c_double), ("gravity", C.c_double), ("k_zmp", C.c_double), ("k_com", C.c_double)]
+
+
+def glue_default_config():
+    L = lib()
+    L.wc_glue_default_config.argtypes = [C.POINTER(GlueConfig)]
+    cfg = GlueConfig()
+    L.wc_glue_default_config(C.byref(cfg))
+    return cfg
+
+
+class GlueBatch:
+    """numpy SoA batch: the checker of walking-controllers_b200.GlueBatch"""
+
+    def __init__(self, cfg, B):
+        L = lib()
+        dp = C.POINTER(C.c_double)
+        L.wco_glue_create.argtypes = [C.POINTER(GlueConfig), C.c_int]; L.wco_glue_create.restype = C.c_void_p
+        L.wco_glue_free.argtypes = [C.c_void_p]
+        L.wco_glue_reset.argtypes = [C.c_void_p, dp, dp]
+        L.wco_glue_com_reference.argtypes = [C.c_void_p] + [dp] * 10
+        L.wco_glue_integrate_joints.argtypes = [C.c_void_p, dp, dp]
+        self.L, self.cfg, self.B, self.nJ = L, cfg, B, cfg.n_dofs
+        self.h = L.wco_glue_create(C.byref(cfg), B)
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.L.wco_glue_free(self.h); self.h = None
+        except Exception:
+            pass
+
+    def reset(self, com_xy=None, q=None):
+        a = _f64(com_xy) if com_xy is not None else None
+        b = _f64(q) if q is not None else None
+        self.L.wco_glue_reset(self.h, _dp(a), _dp(b))
+
+    def com_reference(self, dcm_des, zmp_des, zmp_meas, com_meas, com_z_des=None, com_z_vel_des=None, k_zmp=None, k_com=None):
+        arrs = [None if x is None else _f64(x) for x in (dcm_des, zmp_des, zmp_meas, com_meas, com_z_des, com_z_vel_des, k_zmp, k_com)]
+        pos = np.zeros((3, self.B)); vel = np.zeros((3, self.B))
+        self.L.wco_glue_com_reference(self.h, *[_dp(x) for x in arrs], _dp(pos), _dp(vel))
+        return dict(com_pos_des=pos, com_vel_des=vel)
+
+    def integrate_joints(self, dq):
+        dq = _f64(dq)
+        out = np.zeros((self.nJ, self.B))
+        self.L.wco_glue_integrate_joints(self.h, _dp(dq), _dp(out))
+        return out

@@ -88,6 +88,16 @@ int wco_osqp_solve_dense(int n, int m, const double* P, const double* A, const d
                          const double* l, const double* u, const wc_osqp_settings* settings,
                          int linsys_kind, double* x_out, double* y_out, double* info_out);
 
+/* ---- closed-loop glue (StableDCMModel, WalkingZMPController, joint integrator); batch SoA ---- */
+typedef struct wco_glue wco_glue;
+wco_glue* wco_glue_create(const wc_glue_config* cfg, int B);
+void wco_glue_free(wco_glue* g);
+void wco_glue_reset(wco_glue* g, const double* com_xy, const double* q);
+void wco_glue_com_reference(wco_glue* g, const double* dcm_des, const double* zmp_des, const double* zmp_meas,
+                            const double* com_meas, const double* com_z_des, const double* com_z_vel_des,
+                            const double* k_zmp, const double* k_com, double* com_pos_des, double* com_vel_des);
+void wco_glue_integrate_joints(wco_glue* g, const double* dq, double* q_des);
+
 #ifdef __cplusplus
 }
 #endif

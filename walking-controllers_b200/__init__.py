@@ -75,6 +75,11 @@ class IkConfig(C.Structure):
                 ("nwsr", C.c_int32), ("reserved", C.c_int32)]
 
 
+class GlueConfig(C.Structure):
+    _fields_ = [("n_dofs", C.c_int32), ("reserved", C.c_int32), ("sampling_time", C.c_double),
+                ("com_height", C.c_double), ("gravity", C.c_double), ("k_zmp", C.c_double), ("k_com", C.c_double)]
+
+
 def build(verbose=False):
     """Compile libwc_b200.so for sm_100a with nvcc (cross-compiles without a GPU)."""
     out = subprocess.run(["make", "-C", CSRC], capture_output=True, text=True)
@@ -124,6 +129,13 @@ def lib():
     L.wc_mpc_kernel_times_detail_ms.argtypes = [_VP] + [C.POINTER(C.c_double)] * 3
     L.wc_mpc_kernel_times_detail_ms.restype = i32
     L.wc_mpc_path.argtypes = [_VP]; L.wc_mpc_path.restype = i32
+    L.wc_glue_default_config.argtypes = [C.POINTER(GlueConfig)]
+    L.wc_glue_create.argtypes = [C.POINTER(GlueConfig), i32, i32, C.POINTER(_VP)]; L.wc_glue_create.restype = i32
+    L.wc_glue_destroy.argtypes = [_VP]
+    L.wc_glue_reset_dev.argtypes = [_VP, _VP, _VP, _VP]; L.wc_glue_reset_dev.restype = i32
+    L.wc_glue_com_reference_dev.argtypes = [_VP] + [_VP] * 10 + [_VP]; L.wc_glue_com_reference_dev.restype = i32
+    L.wc_glue_integrate_joints_dev.argtypes = [_VP, _VP, _VP, _VP]; L.wc_glue_integrate_joints_dev.restype = i32
+    L.wc_glue_launch_count.argtypes = [_VP]; L.wc_glue_launch_count.restype = i64
     L.wc_measure_fp64_peak.argtypes = [i32, C.POINTER(C.c_double)]; L.wc_measure_fp64_peak.restype = i32
     if hasattr(L, "wc_ik_create"):
         L.wc_ik_create.argtypes = [C.POINTER(IkConfig), C.POINTER(Model), i32, i32, C.POINTER(_VP)]
@@ -394,6 +406,65 @@ class IkBatch:
         a, b = C.c_double(), C.c_double()
         _check(lib().wc_ik_kernel_times_detail_ms(self.h, C.byref(a), C.byref(b)), "wc_ik_kernel_times_detail_ms")
         return a.value, b.value
+
+
+def glue_default_config():
+    cfg = GlueConfig()
+    lib().wc_glue_default_config(C.byref(cfg))
+    return cfg
+
+
+class GlueBatch:
+    """Batched StableDCMModel + WalkingZMPController + joint integrator (torch CUDA tensors, field-major SoA)."""
+
+    def __init__(self, cfg, B, device=0):
+        self.cfg, self.B, self.nJ, self.device = cfg, B, cfg.n_dofs, device
+        h = _VP()
+        _check(lib().wc_glue_create(C.byref(cfg), B, device, C.byref(h)), "wc_glue_create")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().wc_glue_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @staticmethod
+    def _stream(stream):
+        import torch
+        return (stream or torch.cuda.current_stream()).cuda_stream
+
+    def reset(self, com_xy=None, q=None, stream=None):
+        _check(lib().wc_glue_reset_dev(self.h, _ptr(com_xy), _ptr(q), self._stream(stream)), "wc_glue_reset_dev")
+
+    def com_reference(self, dcm_des, zmp_des, zmp_meas, com_meas, com_z_des=None, com_z_vel_des=None, k_zmp=None,
+                      k_com=None, out=None, stream=None):
+        import torch
+        if out is None:
+            out = dict(com_pos_des=torch.empty(3, self.B, dtype=torch.float64, device=dcm_des.device),
+                       com_vel_des=torch.empty(3, self.B, dtype=torch.float64, device=dcm_des.device))
+        _check(lib().wc_glue_com_reference_dev(self.h, _ptr(dcm_des), _ptr(zmp_des), _ptr(zmp_meas), _ptr(com_meas),
+                                               _ptr(com_z_des), _ptr(com_z_vel_des), _ptr(k_zmp), _ptr(k_com),
+                                               _ptr(out["com_pos_des"]), _ptr(out["com_vel_des"]), self._stream(stream)),
+               "wc_glue_com_reference_dev")
+        return out
+
+    def integrate_joints(self, dq, out=None, stream=None):
+        import torch
+        if out is None:
+            out = torch.empty(self.nJ, self.B, dtype=torch.float64, device=dq.device)
+        _check(lib().wc_glue_integrate_joints_dev(self.h, _ptr(dq), _ptr(out), self._stream(stream)),
+               "wc_glue_integrate_joints_dev")
+        return out
+
+    @property
+    def launches(self):
+        return lib().wc_glue_launch_count(self.h)
 
 
 def measure_fp64_peak(device=0):

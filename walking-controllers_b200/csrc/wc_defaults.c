@@ -154,3 +154,16 @@ void wc_model_icub_like(wc_model* m)
     m->neck_R[2] = 1.0; m->neck_R[3] = 1.0; m->neck_R[7] = 1.0;
     m->neck_p[0] = 0.0; m->neck_p[1] = 0.0; m->neck_p[2] = 0.03;
 }
+
+/* iCubGazeboV2_5: dcmWalkingCoordinator.ini:20 (sampling_time), GENERAL com_height, zmpControllerParams.ini
+ * (kZMP_walking, kCoM_walking: the gains used when gain scheduling is off) */
+void wc_glue_default_config(wc_glue_config* c)
+{
+    if (!c) return;
+    c->n_dofs = 23; c->reserved = 0;
+    c->sampling_time = 0.01;
+    c->com_height = 0.53;
+    c->gravity = 9.81;
+    c->k_zmp = 3.0;
+    c->k_com = 9.0;
+}
