@@ -167,15 +167,19 @@ wc_status wc_mpc_tick_host(wc_mpc* h,
                            double* zmp, int32_t* osqp_status, int32_t* iters, int32_t* flags);
 
 /* Split form of wc_mpc_tick_host: _async enqueues the H2D copies, the kernels and the D2H copies on the
- * handle's own stream and returns; wc_mpc_sync waits for them.  Buffers must stay valid (and should be
- * pinned: cudaHostAlloc / torch pin_memory) until wc_mpc_sync returns.  Lets a caller overlap the upload of
- * the next block's inputs (e.g. the IK handle's) with this handle's kernels. */
+ * handle's own upload / compute / download streams and returns.  Staging is double-buffered: up to TWO ticks may
+ * be in flight (a third _async call first retires the oldest), so the upload of tick t+1 and the download of
+ * tick t-1 overlap the kernels of tick t; another handle's (e.g. the IK's) traffic overlaps as well.
+ * wc_mpc_sync_one retires the oldest tick in flight (its outputs are then valid), wc_mpc_sync all of them.
+ * Input and output buffers of a tick must stay valid (and should be pinned: cudaHostAlloc / torch pin_memory)
+ * until that tick is retired; ticks in flight need distinct output buffers. */
 wc_status wc_mpc_tick_host_async(wc_mpc* h,
                            const double* lf_H, const double* rf_H,
                            const uint8_t* l_contact, const uint8_t* r_contact,
                            const double* dcm_meas, const double* ref, const uint8_t* reset,
                            double* zmp, int32_t* osqp_status, int32_t* iters, int32_t* flags);
 wc_status wc_mpc_sync(wc_mpc* h);
+wc_status wc_mpc_sync_one(wc_mpc* h);
 
 /* Debug / parity taps (device -> host copies, synchronous): full primal solution
  * z = [x_0..x_N, u_0..u_{N-1}] per instance ([n*B], field-major, n = 4N+2), the current
@@ -314,6 +318,7 @@ wc_status wc_ik_tick_host_async(wc_ik* h,
                           double* dq, double* lf_err, double* rf_err,
                           int32_t* qp_status, int32_t* nwsr);
 wc_status wc_ik_sync(wc_ik* h);
+wc_status wc_ik_sync_one(wc_ik* h);
 
 /* Forward kinematics only (WalkingFK getters, WalkingForwardKinematics.cpp:411-454):
  * for each instance the world transforms of l_sole, r_sole [12*B each], neck rotation [9*B],

@@ -121,6 +121,7 @@ def lib():
     L.wc_mpc_tick_host.argtypes = [_VP] + [_VP] * 11; L.wc_mpc_tick_host.restype = i32
     L.wc_mpc_tick_host_async.argtypes = [_VP] + [_VP] * 11; L.wc_mpc_tick_host_async.restype = i32
     L.wc_mpc_sync.argtypes = [_VP]; L.wc_mpc_sync.restype = i32
+    L.wc_mpc_sync_one.argtypes = [_VP]; L.wc_mpc_sync_one.restype = i32
     L.wc_mpc_debug_get_host.argtypes = [_VP, _VP, _VP, _VP]; L.wc_mpc_debug_get_host.restype = i32
     L.wc_mpc_launch_count.argtypes = [_VP]; L.wc_mpc_launch_count.restype = i64
     L.wc_mpc_enable_profiling.argtypes = [_VP, i32]; L.wc_mpc_enable_profiling.restype = i32
@@ -147,6 +148,7 @@ def lib():
         L.wc_ik_tick_host.argtypes = [_VP] + [_VP] * 17; L.wc_ik_tick_host.restype = i32
         L.wc_ik_tick_host_async.argtypes = [_VP] + [_VP] * 17; L.wc_ik_tick_host_async.restype = i32
         L.wc_ik_sync.argtypes = [_VP]; L.wc_ik_sync.restype = i32
+        L.wc_ik_sync_one.argtypes = [_VP]; L.wc_ik_sync_one.restype = i32
         L.wc_fk_dev.argtypes = [_VP] + [_VP] * 11 + [_VP]; L.wc_fk_dev.restype = i32
         L.wc_ik_solve_with_jacobians_dev.argtypes = [_VP] + [_VP] * 21 + [_VP]
         L.wc_ik_solve_with_jacobians_dev.restype = i32
@@ -258,6 +260,10 @@ class MpcBatch:
     def sync(self):
         _check(lib().wc_mpc_sync(self.h), "wc_mpc_sync")
 
+    def sync_one(self):
+        """retire the oldest host tick in flight (up to two may be)"""
+        _check(lib().wc_mpc_sync_one(self.h), "wc_mpc_sync_one")
+
     def debug(self):
         import numpy as np
         n = 4 * self.N + 2
@@ -355,6 +361,9 @@ class IkBatch:
 
     def sync(self):
         _check(lib().wc_ik_sync(self.h), "wc_ik_sync")
+
+    def sync_one(self):
+        _check(lib().wc_ik_sync_one(self.h), "wc_ik_sync_one")
 
     def fk(self, q, base_H, left_is_fixed, jacobians=True, stream=None):
         import torch

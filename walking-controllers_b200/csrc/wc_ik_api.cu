@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 
 #include "../../include/wc_capi.h"
+#include "host_pipe.cuh"
 #include "ik_kernels.cuh"
 
 using namespace wcb;
@@ -20,8 +21,7 @@ struct wc_ik {
     int64_t launches;
     IkModelDev* model_dev;
     double* kpos; double* katt;
-    void* pin_in; void* pin_out; void* dev_in; void* dev_out;
-    cudaStream_t host_stream;
+    HostPipe pipe; // double-buffered staging of the host-pointer tick
     int profiling;
     std::vector<cudaEvent_t> ev; // triples (start, after the fast kernel, end)
     double fast_ms_acc, detail[2];
@@ -111,7 +111,6 @@ wc_status wc_ik_create(const wc_ik_config* cfg, const wc_model* model, int32_t B
     wc_ik* h = new (std::nothrow) wc_ik();
     if (!h) return WC_ERR_ALLOC;
     h->launches = 0; h->model_dev = nullptr; h->kpos = h->katt = nullptr;
-    h->pin_in = h->pin_out = h->dev_in = h->dev_out = nullptr; h->host_stream = nullptr;
     h->profiling = 0; h->ms_acc = 0; h->timed = 0; h->fast_ms_acc = 0; h->detail[0] = h->detail[1] = 0;
     std::memset(&h->d, 0, sizeof(h->d));
     h->device = device;
@@ -142,11 +141,7 @@ void wc_ik_destroy(wc_ik* h)
     if (h->d.slow_count) cudaFree(h->d.slow_count);
     if (h->kpos) cudaFree(h->kpos);
     if (h->katt) cudaFree(h->katt);
-    if (h->pin_in) cudaFreeHost(h->pin_in);
-    if (h->pin_out) cudaFreeHost(h->pin_out);
-    if (h->dev_in) cudaFree(h->dev_in);
-    if (h->dev_out) cudaFree(h->dev_out);
-    if (h->host_stream) cudaStreamDestroy(h->host_stream);
+    h->pipe.destroy();
     for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
     delete h;
 }
@@ -261,31 +256,33 @@ wc_status wc_ik_tick_host_async(wc_ik* h, const double* q_meas, const double* q_
     const size_t in_bytes = o_flag + align_up(B, 8);
     const size_t p_dq = 0, p_le = p_dq + nJ * B * 8, p_re = p_le + 6 * B * 8, p_st = p_re + 6 * B * 8;
     const size_t p_nw = p_st + align_up(B * 4, 8), out_bytes = p_nw + align_up(B * 4, 8);
-    if (!h->dev_in) {
-        if (cudaMalloc(&h->dev_in, in_bytes) != cudaSuccess) return WC_ERR_ALLOC;
-        if (cudaMalloc(&h->dev_out, out_bytes) != cudaSuccess) return WC_ERR_ALLOC;
-        if (cudaStreamCreateWithFlags(&h->host_stream, cudaStreamNonBlocking) != cudaSuccess) return WC_ERR_CUDA;
-    }
+    if (h->pipe.init(in_bytes, out_bytes) != cudaSuccess) return WC_ERR_ALLOC;
     // direct copies from / to the caller's (ideally pinned) buffers
-    cudaStream_t s = h->host_stream;
-    char* dbase = static_cast<char*>(h->dev_in);
+    cudaError_t ce = cudaSuccess;
+    const int slot = h->pipe.begin(&ce);
+    if (ce != cudaSuccess) return WC_ERR_CUDA;
+    cudaStream_t s = h->pipe.up;
+    char* dbase = static_cast<char*>(h->pipe.dev_in[slot]);
     for (int k = 0; k < 11; k++)
         if (cudaMemcpyAsync(dbase + off[k], src[k], rows[k] * B * 8, cudaMemcpyHostToDevice, s) != cudaSuccess) return WC_ERR_CUDA;
     if (cudaMemcpyAsync(dbase + o_flag, left_is_fixed, B, cudaMemcpyHostToDevice, s) != cudaSuccess) return WC_ERR_CUDA;
-    const char* di = static_cast<const char*>(h->dev_in);
-    char* dout = static_cast<char*>(h->dev_out);
+    if (h->pipe.before_run(slot) != cudaSuccess) return WC_ERR_CUDA;
+    const char* di = dbase;
+    char* dout = static_cast<char*>(h->pipe.dev_out[slot]);
     auto D = [&](int k) { return reinterpret_cast<const double*>(di + off[k]); };
     wc_status rc = wc_ik_tick_dev(h, D(0), D(1), D(2), reinterpret_cast<const uint8_t*>(di + o_flag), D(3), D(4), D(5), D(6),
                                   D(7), D(8), D(9), D(10),
                                   reinterpret_cast<double*>(dout + p_dq), reinterpret_cast<double*>(dout + p_le),
                                   reinterpret_cast<double*>(dout + p_re), reinterpret_cast<int32_t*>(dout + p_st),
-                                  reinterpret_cast<int32_t*>(dout + p_nw), s);
+                                  reinterpret_cast<int32_t*>(dout + p_nw), h->pipe.run);
     if (rc != WC_OK) return rc;
-    cudaError_t e = cudaSuccess;
+    cudaError_t e = h->pipe.before_down(slot);
+    s = h->pipe.down;
 #define D2H(dst, off_, bytes) do { if ((dst) && e == cudaSuccess) e = cudaMemcpyAsync((dst), dout + (off_), (bytes), cudaMemcpyDeviceToHost, s); } while (0)
     D2H(dq, p_dq, nJ * B * 8); D2H(lf_err, p_le, 6 * B * 8); D2H(rf_err, p_re, 6 * B * 8);
     D2H(qp_status, p_st, B * 4); D2H(nwsr, p_nw, B * 4);
 #undef D2H
+    if (e == cudaSuccess) e = h->pipe.end(slot);
     if (e != cudaSuccess) {
         std::fprintf(stderr, "[wc_ik_tick_host_async] CUDA error: %s\n", cudaGetErrorString(e));
         return WC_ERR_CUDA;
@@ -296,14 +293,22 @@ wc_status wc_ik_tick_host_async(wc_ik* h, const double* q_meas, const double* q_
 wc_status wc_ik_sync(wc_ik* h)
 {
     if (!h) return WC_ERR_INVALID_ARG;
-    if (!h->host_stream) return WC_OK;
+    if (!h->pipe.ready) return WC_OK;
     if (cudaSetDevice(h->device) != cudaSuccess) return WC_ERR_CUDA;
-    const cudaError_t e = cudaStreamSynchronize(h->host_stream);
+    const cudaError_t e = h->pipe.sync_all();
     if (e != cudaSuccess) {
         std::fprintf(stderr, "[wc_ik_sync] CUDA error: %s\n", cudaGetErrorString(e));
         return WC_ERR_CUDA;
     }
     return WC_OK;
+}
+
+wc_status wc_ik_sync_one(wc_ik* h)
+{
+    if (!h) return WC_ERR_INVALID_ARG;
+    if (!h->pipe.ready) return WC_OK;
+    if (cudaSetDevice(h->device) != cudaSuccess) return WC_ERR_CUDA;
+    return h->pipe.sync_one() == cudaSuccess ? WC_OK : WC_ERR_CUDA;
 }
 
 wc_status wc_ik_tick_host(wc_ik* h, const double* q_meas, const double* q_lin, const double* base_H,

@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 
 #include "../../include/wc_capi.h"
+#include "host_pipe.cuh"
 #include "mpc_kernels.cuh"
 
 using namespace wcb;
@@ -24,9 +25,7 @@ struct wc_mpc {
     int64_t tick;
     std::vector<void*> allocs;
     // staging for the *_host entry points
-    void* pin_in; void* pin_out; void* dev_in; void* dev_out;
-    size_t in_bytes, out_bytes;
-    cudaStream_t host_stream;
+    HostPipe pipe; // double-buffered staging of the host-pointer entry points
     // optional per-kernel timing (wc_mpc_enable_profiling): events recorded on the launch stream
     int profiling;
     std::vector<cudaEvent_t> ev; // quintuples (start, after K1, after setup, after phase 1, after K2)
@@ -82,8 +81,6 @@ wc_status wc_mpc_create(const wc_mpc_config* cfg, int32_t B, int32_t device, wc_
     h->device = device;
     h->launches = 0;
     h->tick = 0;
-    h->pin_in = h->pin_out = h->dev_in = h->dev_out = nullptr;
-    h->host_stream = nullptr;
     h->profiling = 0; h->prep_ms_acc = 0; h->admm_ms_acc = 0; h->timed_ticks = 0;
     h->setup_ms_acc = h->phase1_ms_acc = h->phase2_ms_acc = 0;
     MpcDev& d = h->d;
@@ -183,11 +180,7 @@ void wc_mpc_destroy(wc_mpc* h)
     if (!h) return;
     cudaSetDevice(h->device);
     for (void* p : h->allocs) cudaFree(p);
-    if (h->pin_in) cudaFreeHost(h->pin_in);
-    if (h->pin_out) cudaFreeHost(h->pin_out);
-    if (h->dev_in) cudaFree(h->dev_in);
-    if (h->dev_out) cudaFree(h->dev_out);
-    if (h->host_stream) cudaStreamDestroy(h->host_stream);
+    h->pipe.destroy();
     for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
     delete h;
 }
@@ -275,37 +268,37 @@ wc_status wc_mpc_tick_host_async(wc_mpc* h, const double* lf_H, const double* rf
     const size_t in_bytes = o_rs + align_up(B, 8);
     const size_t p_zmp = 0, p_st = p_zmp + 2 * B * 8, p_it = p_st + align_up(B * 4, 8), p_fl = p_it + align_up(B * 4, 8);
     const size_t out_bytes = p_fl + align_up(B * 4, 8);
-    if (!h->dev_in) {
-        if (cudaMalloc(&h->dev_in, in_bytes) != cudaSuccess) return WC_ERR_ALLOC;
-        if (cudaMalloc(&h->dev_out, out_bytes) != cudaSuccess) return WC_ERR_ALLOC;
-        if (cudaStreamCreateWithFlags(&h->host_stream, cudaStreamNonBlocking) != cudaSuccess) return WC_ERR_CUDA;
-        h->in_bytes = in_bytes; h->out_bytes = out_bytes;
-    }
+    if (h->pipe.init(in_bytes, out_bytes) != cudaSuccess) return WC_ERR_ALLOC;
     // copies go straight from / to the caller's buffers: pinned buffers (cudaHostAlloc / torch
     // pin_memory) make them true async DMA transfers, pageable ones are staged by the driver
-    cudaStream_t s = h->host_stream;
-    char* dbase = static_cast<char*>(h->dev_in);
     cudaError_t ce = cudaSuccess;
+    const int slot = h->pipe.begin(&ce);
+    if (ce != cudaSuccess) return WC_ERR_CUDA;
+    cudaStream_t s = h->pipe.up;
+    char* dbase = static_cast<char*>(h->pipe.dev_in[slot]);
 #define H2D(off, src, bytes) do { if (ce == cudaSuccess) ce = cudaMemcpyAsync(dbase + (off), (src), (bytes), cudaMemcpyHostToDevice, s); } while (0)
     H2D(o_lf, lf_H, 12 * B * 8); H2D(o_rf, rf_H, 12 * B * 8); H2D(o_dcm, dcm_meas, 2 * B * 8);
     H2D(o_ref, ref, (size_t)2 * (N + 1) * B * 8); H2D(o_lc, l_contact, B); H2D(o_rc, r_contact, B);
     if (reset) H2D(o_rs, reset, B);
     else if (ce == cudaSuccess) ce = cudaMemsetAsync(dbase + o_rs, 0, B, s);
 #undef H2D
+    if (ce == cudaSuccess) ce = h->pipe.before_run(slot);
     if (ce != cudaSuccess) return WC_ERR_CUDA;
-    char* di = static_cast<char*>(h->dev_in);
-    char* dout = static_cast<char*>(h->dev_out);
+    char* di = dbase;
+    char* dout = static_cast<char*>(h->pipe.dev_out[slot]);
     wc_status rc = wc_mpc_tick_dev(h, (const double*)(di + o_lf), (const double*)(di + o_rf),
                                    (const uint8_t*)(di + o_lc), (const uint8_t*)(di + o_rc),
                                    (const double*)(di + o_dcm), (const double*)(di + o_ref),
                                    (const uint8_t*)(di + o_rs),
                                    (double*)(dout + p_zmp), (int32_t*)(dout + p_st), (int32_t*)(dout + p_it),
-                                   (int32_t*)(dout + p_fl), s);
+                                   (int32_t*)(dout + p_fl), h->pipe.run);
     if (rc != WC_OK) return rc;
-    cudaError_t e = cudaSuccess;
+    cudaError_t e = h->pipe.before_down(slot);
+    s = h->pipe.down;
 #define D2H(dst, off, bytes) do { if ((dst) && e == cudaSuccess) e = cudaMemcpyAsync((dst), dout + (off), (bytes), cudaMemcpyDeviceToHost, s); } while (0)
     D2H(zmp, p_zmp, 2 * B * 8); D2H(osqp_status, p_st, B * 4); D2H(iters, p_it, B * 4); D2H(flags, p_fl, B * 4);
 #undef D2H
+    if (e == cudaSuccess) e = h->pipe.end(slot);
     if (e != cudaSuccess) {
         std::fprintf(stderr, "[wc_mpc_tick_host_async] CUDA error: %s\n", cudaGetErrorString(e));
         return WC_ERR_CUDA;
@@ -316,14 +309,22 @@ wc_status wc_mpc_tick_host_async(wc_mpc* h, const double* lf_H, const double* rf
 wc_status wc_mpc_sync(wc_mpc* h)
 {
     if (!h) return WC_ERR_INVALID_ARG;
-    if (!h->host_stream) return WC_OK;
+    if (!h->pipe.ready) return WC_OK;
     if (cudaSetDevice(h->device) != cudaSuccess) return WC_ERR_CUDA;
-    const cudaError_t e = cudaStreamSynchronize(h->host_stream);
+    const cudaError_t e = h->pipe.sync_all();
     if (e != cudaSuccess) {
         std::fprintf(stderr, "[wc_mpc_sync] CUDA error: %s\n", cudaGetErrorString(e));
         return WC_ERR_CUDA;
     }
     return WC_OK;
+}
+
+wc_status wc_mpc_sync_one(wc_mpc* h)
+{
+    if (!h) return WC_ERR_INVALID_ARG;
+    if (!h->pipe.ready) return WC_OK;
+    if (cudaSetDevice(h->device) != cudaSuccess) return WC_ERR_CUDA;
+    return h->pipe.sync_one() == cudaSuccess ? WC_OK : WC_ERR_CUDA;
 }
 
 wc_status wc_mpc_tick_host(wc_mpc* h, const double* lf_H, const double* rf_H,
