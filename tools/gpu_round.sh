@@ -9,11 +9,11 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O
 timeout 900 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu_$TAG.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/pytest_gpu_$TAG.log
 timeout 600 python bench.py > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err; echo "bench rc=$?"
 timeout 300 python bench.py --impl reference --steps 6 --warmup 3 > $OUT/bench_ref_$TAG.json 2> $OUT/bench_ref_$TAG.err; echo "bench ref rc=$?"
-CMD="python bench.py --steps 3 --warmup 3 --no-cpu"
+CMD="python bench.py --steps 3 --warmup 12 --no-cpu"
 $CMD > $OUT/plain_$TAG.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file $OUT/launches_$TAG.csv $CMD > $OUT/ncu1_$TAG.log 2>&1
 $CMD > $OUT/plain2_$TAG.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:"mpc_chain|mpc_prepare|ik_fast|ik_kernel" -s 14 -c 7 -f -o $OUT/prof_$TAG $CMD > $OUT/ncu2_$TAG.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"mpc_chain|mpc_prepare|ik_fast|ik_kernel" -s 86 -c 6 -f -o $OUT/prof_$TAG $CMD > $OUT/ncu2_$TAG.log 2>&1
 echo done
 tail -c 1500 $OUT/pytest_gpu_$TAG.log
 cat $OUT/bench_$TAG.json | head -c 3000

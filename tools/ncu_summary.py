@@ -20,7 +20,7 @@ if os.path.exists(lp):
         except ValueError: continue
         a = agg.setdefault(short(r[ki]), [0, 0.0]); a[0] += 1; a[1] += v
     tot = sum(a[1] for a in agg.values())
-    out.append(f"## launch list ({tag}): ncu --metrics gpu__time_duration.sum --clock-control none, `python bench.py --steps 3 --warmup 3 --no-cpu`\n")
+    out.append(f"## launch list ({tag}): ncu --metrics gpu__time_duration.sum --clock-control none, `python bench.py --steps 3 --warmup 12 --no-cpu`\n")
     out.append("| kernel | launches | total ms | mean us | share |\n|---|---|---|---|---|")
     for k, (n, ns) in sorted(agg.items(), key=lambda x: -x[1][1]):
         out.append(f"| {k} | {n} | {ns/1e6:.3f} | {ns/n/1e3:.1f} | {100*ns/tot:.1f}% |")
