@@ -796,12 +796,13 @@ __global__ void __launch_bounds__(2 * IPW) mpc_chain_kernel(MpcDev d, MpcTickIO 
     int iter = PHASE2 ? phase1_len : 0;
     int to_check = chk ? chk - (iter % chk) : 0;
     int to_adapt = adaptive ? rint - (iter % rint) : 0;
+    // 1 / rho_e, 1 / rho: divisions hoisted out of the iteration (rho changes in adapt_rho only)
+    double rho_e_inv = 1.0 / (kRhoEqOverIneq * rho), rho_inv = 1.0 / rho;
     bool warp_busy = __any_sync(WMASK, !done);
     while (warp_busy) {
         iter++;
         const bool act = !done;
         const double rho_e = kRhoEqOverIneq * rho;
-        const double rho_e_inv = 1.0 / rho_e, rho_inv = 1.0 / rho;
         bool check_now = false, adapt_now = false;
         if (chk) { if (--to_check == 0) { check_now = true; to_check = chk; } }
         if (adaptive) { if (--to_adapt == 0) { adapt_now = true; to_adapt = rint; } }
@@ -942,6 +943,7 @@ __global__ void __launch_bounds__(2 * IPW) mpc_chain_kernel(MpcDev d, MpcTickIO 
                 if (rn > rho * st.adaptive_rho_tolerance || rn < rho / st.adaptive_rho_tolerance) {
                     rho = rn;
                     rho_updates++;
+                    rho_e_inv = 1.0 / (kRhoEqOverIneq * rho); rho_inv = 1.0 / rho;
                 }
             }
             __syncwarp(WMASK);
@@ -1015,22 +1017,34 @@ __global__ void __launch_bounds__(2 * IPW) mpc_chain_kernel(MpcDev d, MpcTickIO 
                     out[0] = u0_mine; out[1] = u0_other;
                     d.uprev[i] = out[0]; d.uprev[B + i] = out[1];
                     // ConvexHullProjectionConstraint::computeMargin (Controller.cpp:513-517)
+                    // margin < -tol  <=>  outside the polygon AND farther than tol from its boundary: the distance to
+                    // the hull segments is only needed for a ZMP that violates a hull row
                     bool inside = true;
                     double best = INFINITY;
-                    for (int h = 0; h < nh; h++) {
-                        const double a0 = d.hullA[(size_t)(2 * h) * B + i], a1 = d.hullA[(size_t)(2 * h + 1) * B + i];
-                        if (!(a0 * out[0] + a1 * out[1] <= d.hullb[(size_t)h * B + i])) inside = false;
+                    {
+                        double a0[kMaxHull], a1[kMaxHull], bb[kMaxHull];
+#pragma unroll
+                        for (int h = 0; h < kMaxHull; h++) { // one batch of loads
+                            a0[h] = h < nh ? d.hullA[(size_t)(2 * h) * B + i] : 0.0;
+                            a1[h] = h < nh ? d.hullA[(size_t)(2 * h + 1) * B + i] : 0.0;
+                            bb[h] = h < nh ? d.hullb[(size_t)h * B + i] : 0.0;
+                        }
+#pragma unroll
+                        for (int h = 0; h < kMaxHull; h++)
+                            if (h < nh && !(a0[h] * out[0] + a1[h] * out[1] <= bb[h])) inside = false;
                     }
-                    for (int h = 0; h < nh; h++) {
-                        const int h1 = (h + 1) % nh;
-                        const double p0x = d.hullv[(size_t)(2 * h) * B + i], p0y = d.hullv[(size_t)(2 * h + 1) * B + i];
-                        const double p1x = d.hullv[(size_t)(2 * h1) * B + i], p1y = d.hullv[(size_t)(2 * h1 + 1) * B + i];
-                        const double dx = p1x - p0x, dy = p1y - p0y;
-                        const double len2 = dx * dx + dy * dy;
-                        double t = len2 > 0 ? ((out[0] - p0x) * dx + (out[1] - p0y) * dy) / len2 : 0.0;
-                        t = t < 0 ? 0 : (t > 1 ? 1 : t);
-                        const double ex = out[0] - (p0x + t * dx), ey = out[1] - (p0y + t * dy);
-                        best = fmin(best, sqrt(ex * ex + ey * ey));
+                    if (!inside) {
+                        for (int h = 0; h < nh; h++) {
+                            const int h1 = (h + 1) % nh;
+                            const double p0x = d.hullv[(size_t)(2 * h) * B + i], p0y = d.hullv[(size_t)(2 * h + 1) * B + i];
+                            const double p1x = d.hullv[(size_t)(2 * h1) * B + i], p1y = d.hullv[(size_t)(2 * h1 + 1) * B + i];
+                            const double dx = p1x - p0x, dy = p1y - p0y;
+                            const double len2 = dx * dx + dy * dy;
+                            double t = len2 > 0 ? ((out[0] - p0x) * dx + (out[1] - p0y) * dy) / len2 : 0.0;
+                            t = t < 0 ? 0 : (t > 1 ? 1 : t);
+                            const double ex = out[0] - (p0x + t * dx), ey = out[1] - (p0y + t * dy);
+                            best = fmin(best, sqrt(ex * ex + ey * ey));
+                        }
                     }
                     const double margin = inside ? best : -best;
                     if (margin < -d.hull_tol) flags |= WC_MPC_FLAG_OUTSIDE_HULL;
