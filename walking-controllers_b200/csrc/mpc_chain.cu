@@ -265,8 +265,7 @@ __global__ void __launch_bounds__(kSetupWarps * 32) mpc_chain_setup_kernel(MpcDe
     extern __shared__ double smem_all[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int count = *d.setup_count;
-    const int e = blockIdx.x * kSetupWarps + warp;
-    if (e >= count) return; // whole warp
+    for (int e = blockIdx.x * kSetupWarps + warp; e < count; e += gridDim.x * kSetupWarps) { // whole warps
     const int i = d.setup_list[e];
     const size_t B = (size_t)d.B;
     const int N = d.N, nA = 2 * N + 1, nR = N + 1;
@@ -388,6 +387,8 @@ __global__ void __launch_bounds__(kSetupWarps * 32) mpc_chain_setup_kernel(MpcDe
     __syncwarp();
     // numeric factorisation (osqp_setup -> init_linsys_solver): the two axis chains on lanes 0 and 16
     if ((lane & 15) == 0) chain_factor(d, i, lane >> 4, N, c, rho0, nh, 0x00010001u, true, DD + (lane >> 4) * nA, EE + (lane >> 4) * nR);
+    __syncwarp();
+    } // list entries
 }
 
 // =====================================================================================
@@ -407,23 +408,18 @@ __global__ void __launch_bounds__(2 * IPW) mpc_chain_kernel(MpcDev d, MpcTickIO 
     const size_t B = (size_t)d.B;
     const int N = NT > 0 ? NT : d.N, nA = 2 * N + 1, nR = N + 1; // NT > 0: compile-time horizon
     const Off O(N);
-    int i;
-    bool valid;
-    if (PHASE2) {
-        const int count = *d.cont_count;
-        if (blockIdx.x * kIPW >= count) return;
-        const int li = blockIdx.x * kIPW + slot;
-        valid = li < count;
-        i = d.cont_list[valid ? li : count - 1];
-    } else {
-        if (blockIdx.x == 0 && lane == 0) *d.setup_count = 0; // consumed by the setup kernel of this tick
-        const long long ii = (long long)blockIdx.x * kIPW + slot;
-        valid = ii < (long long)d.B;
-        i = valid ? (int)ii : d.B - 1;
-    }
+    if (!PHASE2 && blockIdx.x == 0 && lane == 0) *d.setup_count = 0; // consumed by the setup kernel of this tick
+    // Phase 1: one group of IPW instances per CTA.  Phase 2: a small grid strides over the (few) groups of the
+    // continuation list, instead of thousands of CTAs whose only work is to find the list empty.
+    const int count = PHASE2 ? *d.cont_count : d.B;
+    const int ngroups = (count + kIPW - 1) / kIPW;
     ChainSmem<IPW> s{smem_all + lane, smem_all + (size_t)O.total * (2 * IPW) + slot, nR, N};
 #define A_(o, k) s.at(O.o, (k))
 #define H_(arr, h) s.hat((arr), (h))
+    for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+    const int li = grp * kIPW + slot;
+    const bool valid = li < count;
+    const int i = PHASE2 ? d.cont_list[valid ? li : count - 1] : (valid ? li : d.B - 1);
 
     const wc_osqp_settings& st = d.st;
     const double sigma = st.sigma, alpha = st.alpha, infty = st.infty;
@@ -1059,6 +1055,8 @@ __global__ void __launch_bounds__(2 * IPW) mpc_chain_kernel(MpcDev d, MpcTickIO 
             d.tick_flags[i] = flags;
         }
     }
+    __syncwarp(WMASK); // the next group of this CTA reuses the shared-memory working set
+    } // groups
 #undef A_
 #undef H_
 }
@@ -1103,7 +1101,7 @@ static cudaError_t launch_chain_t(const MpcDev& d, const MpcTickIO& io, cudaStre
     if (mid) cudaEventRecord(mid[0], s); // per-kernel timing (wc_mpc_enable_profiling)
     k1<<<blocks, 2 * IPW, smem, s>>>(d, io);
     if (mid) cudaEventRecord(mid[1], s);
-    k2<<<blocks, 2 * IPW, smem, s>>>(d, io);
+    k2<<<blocks < 2 * 148 ? blocks : 2 * 148, 2 * IPW, smem, s>>>(d, io); // grid-stride over the continuation list
     return cudaGetLastError();
 }
 
@@ -1115,7 +1113,10 @@ cudaError_t launch_mpc_chain(const MpcDev& d, const MpcTickIO& io, cudaStream_t 
     const size_t smem_setup = td * kSetupWarps * sizeof(double);
     cudaError_t e = cudaFuncSetAttribute(mpc_chain_setup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_setup);
     if (e != cudaSuccess) return e;
-    mpc_chain_setup_kernel<<<(d.B + kSetupWarps - 1) / kSetupWarps, kSetupWarps * 32, smem_setup, s>>>(d, (int)td);
+    {
+        const int need = (d.B + kSetupWarps - 1) / kSetupWarps;
+        mpc_chain_setup_kernel<<<need < 4 * 148 ? need : 4 * 148, kSetupWarps * 32, smem_setup, s>>>(d, (int)td); // grid-stride over setup_list
+    }
     switch (mpc_chain_ipw(N)) {
     case 16: return N == 25 ? launch_chain_t<25, 16>(d, io, s, mid, smem) : launch_chain_t<0, 16>(d, io, s, mid, smem);
     case 8: return launch_chain_t<0, 8>(d, io, s, mid, smem);
