@@ -54,6 +54,16 @@ def flops_per_tick(N, iters, refactors, wsc, slow_frac=1.0):
     return iters * f_iter + refactors * 36 * n, (1.0 - slow_frac) * F_IK_FAST + slow_frac * 43500 + 3900 * wsc
 
 
+METRIC = "MPC+QP-IK controller ticks/sec at B=65536 iCub instances"   # BASELINE.json metric (p99 latency: tick_latency_ms)
+
+
+def workload_config(world, B, N):
+    """`config` of both arms (ours and --impl reference): BASELINE configs[2]"""
+    return {"workload": f"full tick: DCM-MPC (horizon {N}) + FK + QP-IK, iCub 23-DoF + floating base (BASELINE configs[2])",
+            "instances_per_gpu": B, "instances_total": world * B, "horizon": N,
+            "l2": "per-tick working set (solver state 10 KB x 65536 + inputs) exceeds the 126 MB L2; inputs change every tick"}
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -169,12 +179,13 @@ def run_reference(args, world, rank):
     tot = sum(times)
     val = B * len(times) / tot
     sample = f"{B} instances x {len(times)} ticks of the same synthetic workload (N={N}), one instance per thread"
-    line = {"impl": "reference", "metric": "controller_ticks_per_sec", "value": val, "unit": "ticks/s",
+    cfg = workload_config(world, B_PER_GPU, N)
+    cfg["note"] = ("CPU restatement of the reference path (osqp-eigen/qpOASES/iDynTree cannot be built offline), "
+                   f"timed on a bounded sample of the workload: {B} instances per step")
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "ticks/s",
             "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": tot / len(times) * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "full tick: DCM-MPC (N=25) + FK + QP-IK, iCub 23-DoF", "instances": B,
-                       "horizon": N, "note": "CPU restatement of the reference path (osqp-eigen/qpOASES/iDynTree "
-                                             "cannot be built offline)"},
+            "config": cfg,
             "cpu_baseline": {"value": val, "unit": "ticks/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "ticks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -392,14 +403,10 @@ def run_ours(args, world, rank, local_rank):
         f_mpc, f_ik = flops_per_tick(N, it_mean, 0.0, wsc_mean, slow_frac=ws_frac if fast_on else 1.0)
         value = world * B * steps / (total_ms_max * 1e-3)
         line = {
-            "metric": "controller_ticks_per_sec", "value": value, "unit": "ticks/s", "n_gpus": world, "steps": steps,
+            "metric": METRIC, "value": value, "unit": "ticks/s", "n_gpus": world, "steps": steps,
             "warmup": warm, "ms_per_step": total_ms_max / steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "full tick: DCM-MPC (horizon 25) + FK + QP-IK, iCub 23-DoF + floating base "
-                                   "(BASELINE configs[2])", "instances_per_gpu": B, "instances_total": world * B,
-                       "horizon": N, "mpc_path": mpc.path,
-                       "l2": "per-tick working set (solver state 6 KB x 65536 + inputs) exceeds the 126 MB L2; "
-                             "inputs change every tick"},
+            "config": dict(workload_config(world, B, N), mpc_path=mpc.path),
             "tick_latency_ms": {"p50": pct(step_ms, 0.5), "p99": pct(step_ms, 0.99), "max": max(step_ms)},
             "kernels_ms": {"mpc_prepare": prep_avg_ms, "mpc_admm": admm_avg_ms, "fk_qpik": ik_avg_ms,
                            "mpc_setup": setup_ms / max(nt, 1), "mpc_phase1": phase1_ms / max(nt, 1),

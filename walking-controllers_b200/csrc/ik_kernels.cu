@@ -55,6 +55,17 @@ __device__ __forceinline__ void rot_error(const double* R, const double* Rdes, d
     e[1] = 0.5 * (M[2] - M[6]);
     e[2] = 0.5 * (M[3] - M[1]);
 }
+// 8-byte asynchronous copy HBM -> shared (LDGSTS): the per-instance inputs are fetched while the kinematics runs
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc)
+{
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all()
+{
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+}
 __device__ __forceinline__ double warp_sum(double v)
 {
 #pragma unroll
@@ -76,7 +87,8 @@ __device__ __forceinline__ double warp_max(double v)
 template <int NV>
 __device__ __forceinline__ void fk_stage(const IkModelDev& M, const IkTickIO& io, int i, size_t B, int lane,
                                          double* WL, double* MC, double* colLf, double* colRf, double* colN,
-                                         double* colC, double* lfH, double* rfH, double* nR, double* com, double* pBo)
+                                         double* colC, double* lfH, double* rfH, double* nR, double* com, double* pBo,
+                                         const double* base_H_s = nullptr)
 {
     const int j = lane;
     const int left = io.left_is_fixed[i] ? 1 : 0;
@@ -144,9 +156,12 @@ __device__ __forceinline__ void fk_stage(const IkModelDev& M, const IkTickIO& io
 #pragma unroll
         for (int r = 0; r < 3; r++) pi[r] = -(Ri[3 * r] * ps[0] + Ri[3 * r + 1] * ps[1] + Ri[3 * r + 2] * ps[2]);
         double bR[9], bp[3];
-        bR[0] = io.base_H[0 * B + i]; bR[1] = io.base_H[1 * B + i]; bR[2] = io.base_H[2 * B + i]; bp[0] = io.base_H[3 * B + i];
-        bR[3] = io.base_H[4 * B + i]; bR[4] = io.base_H[5 * B + i]; bR[5] = io.base_H[6 * B + i]; bp[1] = io.base_H[7 * B + i];
-        bR[6] = io.base_H[8 * B + i]; bR[7] = io.base_H[9 * B + i]; bR[8] = io.base_H[10 * B + i]; bp[2] = io.base_H[11 * B + i];
+        // stance-sole transform: from HBM, or from the shared-memory copy the caller prefetched
+        const double* bH = base_H_s ? base_H_s : io.base_H + i;
+        const size_t bs = base_H_s ? (size_t)1 : B;
+        bR[0] = bH[0 * bs]; bR[1] = bH[1 * bs]; bR[2] = bH[2 * bs]; bp[0] = bH[3 * bs];
+        bR[3] = bH[4 * bs]; bR[4] = bH[5 * bs]; bR[5] = bH[6 * bs]; bp[1] = bH[7 * bs];
+        bR[6] = bH[8 * bs]; bR[7] = bH[9 * bs]; bR[8] = bH[10 * bs]; bp[2] = bH[11 * bs];
         xf_mul(bR, bp, Ri, pi, wR, wp);
     }
     __syncwarp();
@@ -244,15 +259,16 @@ __device__ __forceinline__ void fk_stage(const IkModelDev& M, const IkTickIO& io
 // ---- K3b: the vectors of the QP: equality right-hand side b (setBounds), gradient entry g_j of this
 // lane's variable (setGradientVector), regularisation weight Lambda_jj (WalkingQPIK::initializeMatrices).
 template <bool COMC>
-__device__ __forceinline__ void qp_vectors(const IkDev& d, const IkTickIO& io, int i, size_t B, int lane,
+__device__ __forceinline__ void qp_vectors(const IkDev& d, const IkTickIO& io, int i, size_t B, int ig, int lane,
                                            const double* lfH, const double* rfH, const double* nR,
                                            const double* colN, const double* colC, double* bvec, double& gj, double& lam)
 {
     const wc_ik_config& cfg = d.cfg;
     const int j = lane;
     const bool isjoint = j >= 6 && j < d.nJ + 6;
-    const double kpos = d.kpos ? d.kpos[i] : cfg.k_pos_foot;
-    const double katt = d.katt ? d.katt[i] : cfg.k_att_foot;
+    // io may point at a one-instance shared-memory copy (i = 0, B = 1); ig is the instance for the gain arrays
+    const double kpos = d.kpos ? d.kpos[ig] : cfg.k_pos_foot;
+    const double katt = d.katt ? d.katt[ig] : cfg.k_att_foot;
     // equality right-hand side (setBounds, _qpOASES.cpp:216-282)
     double Hd[12], tw[6], R[9], Rd[9], e[3];
 #pragma unroll
@@ -587,7 +603,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) ik_kernel(IkDev d, IkTick
     double gj, lam;
     {
         double bvec[15];
-        qp_vectors<COMC>(d, io, i, B, lane, lfH, rfH, nR, colN, colC, bvec, gj, lam);
+        qp_vectors<COMC>(d, io, i, B, i, lane, lfH, rfH, nR, colN, colC, bvec, gj, lam);
         TS[lane] = isvar ? gj : 0.0; // g parked in TS
         if (lane < 15) {
 #pragma unroll
@@ -876,7 +892,12 @@ struct IkFastLayout {
     static constexpr int O_GK = O_GR + 32;          // G K   [27]
     static constexpr int O_SS = O_GK + 28;          // S     [81]
     static constexpr int QP = O_SS + 82;
-    static constexpr int TOTAL = ((KIN > QP ? KIN : QP) + 15) / 16 * 16 + 8;
+    static constexpr int WORK = ((KIN > QP ? KIN : QP) + 15) / 16 * 16;
+    // per-instance inputs prefetched by cp.async while the kinematics runs (one-instance SoA, stride 1)
+    static constexpr int I_BASE = WORK, I_LFD = I_BASE + 12, I_RFD = I_LFD + 12, I_LTW = I_RFD + 12, I_RTW = I_LTW + 6;
+    static constexpr int I_CPD = I_RTW + 6, I_CVD = I_CPD + 3, I_CM = I_CVD + 3, I_NRD = I_CM + 3, I_QM = I_NRD + 9;
+    static constexpr int TOTAL = (I_QM + NJ + 15) / 16 * 16 + 8;
+    static constexpr int MODEL_DOUBLES = (int)((sizeof(IkModelDev) + 7) / 8); // per-CTA copy of the model table
 };
 
 template <int NJ>
@@ -888,24 +909,52 @@ __global__ void __launch_bounds__(kFastWarps * 32, 4) ik_fast_kernel(IkDev d, Ik
     extern __shared__ double smem_all[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
+    // model table: one shared-memory copy per CTA (every lane indexes it by its own link / joint)
+    double* sm_model = smem_all + (size_t)kFastWarps * LY::TOTAL;
+    {
+        const double* src = reinterpret_cast<const double*>(d.model);
+        for (int k = threadIdx.x; k < LY::MODEL_DOUBLES; k += kFastWarps * 32) sm_model[k] = src[k];
+    }
+    __syncthreads();
     const long long inst = (long long)blockIdx.x * kFastWarps + warp;
     if (inst >= d.B) return;
     const int i = (int)inst;
     const size_t B = (size_t)d.B;
     double* sm = smem_all + (size_t)warp * LY::TOTAL;
+    // ---- prefetch the instance's task inputs (they are first needed after the kinematics)
+    {
+        auto pf = [&](int off, const double* src, int rows) {
+            for (int r = lane; r < rows; r += 32) cp_async8(sm + off + r, src + (size_t)r * B + i);
+        };
+        pf(LY::I_BASE, io.base_H, 12); pf(LY::I_LFD, io.lf_H_des, 12); pf(LY::I_RFD, io.rf_H_des, 12);
+        pf(LY::I_LTW, io.lf_twist, 6); pf(LY::I_RTW, io.rf_twist, 6); pf(LY::I_CPD, io.com_pos_des, 3);
+        pf(LY::I_CVD, io.com_vel_des, 3); pf(LY::I_CM, io.com_meas, 3); pf(LY::I_NRD, io.neck_R_des, 9);
+        pf(LY::I_QM, io.q_meas, NJ);
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+    }
     double* WL = sm; double* MC = sm + WC_MAX_LINKS * 12;
     double* AS = sm + LY::O_AS; double* UT = sm + LY::O_UT; double* HS = sm + LY::O_HS;
     double* GR = sm + LY::O_GR; double* GK = sm + LY::O_GK; double* SS = sm + LY::O_SS;
-    const IkModelDev& M = *d.model;
+    const IkModelDev& M = *reinterpret_cast<const IkModelDev*>(sm_model);
     const wc_ik_config& cfg = d.cfg;
     const int j = lane;
     const bool isj = j >= 6 && j < NV;
 
     double colLf[6] = {0, 0, 0, 0, 0, 0}, colRf[6] = {0, 0, 0, 0, 0, 0}, colN[3] = {0, 0, 0}, colC[3] = {0, 0, 0};
     double lfH[12], rfH[12], nR[9], com[3], pB[3];
+    // (the stance-sole transform is needed half way through the kinematics: wait for the prefetch there would
+    // serialise, so base_H alone still comes from HBM inside fk_stage; everything else arrives meanwhile)
     fk_stage<NV>(M, io, i, B, lane, WL, MC, colLf, colRf, colN, colC, lfH, rfH, nR, com, pB);
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    __syncwarp();
     double bvec[15], gj, lam;
-    qp_vectors<true>(d, io, i, B, lane, lfH, rfH, nR, colN, colC, bvec, gj, lam);
+    {
+        IkTickIO ios = io; // one-instance view of the prefetched inputs: element k at ptr[k] (B = 1, i = 0)
+        ios.lf_H_des = sm + LY::I_LFD; ios.rf_H_des = sm + LY::I_RFD; ios.lf_twist = sm + LY::I_LTW; ios.rf_twist = sm + LY::I_RTW;
+        ios.com_pos_des = sm + LY::I_CPD; ios.com_vel_des = sm + LY::I_CVD; ios.com_meas = sm + LY::I_CM;
+        ios.neck_R_des = sm + LY::I_NRD; ios.q_meas = sm + LY::I_QM;
+        qp_vectors<true>(d, ios, 0, 1, i, lane, lfH, rfH, nR, colN, colC, bvec, gj, lam);
+    }
     const bool left = io.left_is_fixed[i] != 0;
 
     // ---- base twist from the stance-foot rows: v_lin + w x r_s = b_lin, w = b_ang
@@ -1109,7 +1158,7 @@ cudaError_t launch_t(const IkDev& d, const IkTickIO& io, int mode, cudaStream_t 
     if (COMC && mode == IK_MODE_TICK && d.slow_list) {
         // fast path for every instance, then the general kernel on the compacted remainder
         using LF = IkFastLayout<NJ>;
-        const size_t smem_f = (size_t)LF::TOTAL * sizeof(double) * kFastWarps;
+        const size_t smem_f = ((size_t)LF::TOTAL * kFastWarps + LF::MODEL_DOUBLES) * sizeof(double);
         e = cudaFuncSetAttribute(ik_fast_kernel<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f);
         if (e != cudaSuccess) return e;
         e = cudaMemsetAsync(d.slow_count, 0, sizeof(int32_t), s);
