@@ -1,4 +1,4 @@
-// mpc_chain.cu — "chain-per-thread" variant of the batched OSQP-equivalent ADMM (K2) for short horizons.
+// mpc_chain.cu — "chain-per-thread" variant of the batched OSQP-equivalent ADMM (K2); the benchmark path.
 //
 // Same mathematics, same iterates as mpc_admm_kernel (mpc_kernels.cu; mapping to the reference in
 // mpc_kernels.cuh): OSQP's KKT solve done on the reduced system (P + sI + A' rho A) x~ = rhs, which is
@@ -11,7 +11,9 @@
 // instances; the pair meets by shfl_xor 16 for the corner and the hull rows).  Every lane is a
 // sweeper, and because a thread walks its chain stage by stage anyway, the right-hand-side build is
 // fused into the forward sweep and the z / y / x updates into the backward sweep: one pass down, one
-// pass up per ADMM iteration, ~20x fewer warp instructions per instance-iteration.
+// pass up per ADMM iteration, ~8x fewer warp instructions per instance-tick (ncu, profiles/r1a vs r1g).
+// Longer horizons use the same kernels with 8, 4, 2 or 1 instances per CTA (a partial warp), whatever fits
+// one CTA's shared memory; wc_mpc_create prefers them while at least 8 instances share a CTA (N <= 106).
 //
 // Shared memory: every per-thread array is lane-interleaved (element k of lane l at [k*32 + l]) so
 // all accesses are bank-conflict free and the HBM <-> shared staging is coalesced (field-major SoA
@@ -26,14 +28,15 @@
 // so they live in HBM next to the rest of the workspace (OSQP keeps its factorisation in the workspace
 // too) and are staged in with it; chain_factor runs in the setup kernel and after adapt_rho only.
 // The horizon is a template parameter for the benchmark configuration (N = 25): all shared-memory
-// offsets fold into immediates and the stage loops unroll completely, which lets ptxas hoist the
-// loads of later stages above the dependent FMA chain of the current one.
+// offsets fold into immediates and the stage loops unroll 6x, which lets ptxas hoist the loads of later
+// stages above the dependent FMA chain of the current one.  What bounds the kernel (shared-memory pipe,
+// two lone warps per SM) and what was tried against it is in DESIGN.md §5.
 //
 // Work distribution: instances whose OSQP workspace is new (support phase changed, ~2 %/tick) are
 // compacted into a list by K1 and equilibrated by mpc_chain_setup_kernel; phase 1 runs every
 // instance up to the first termination check; the few that have not converged are compacted again
-// and finished by phase 2.  A warp therefore never idles 15 lanes while one instance runs the Ruiz
-// passes or another 25 iterations.
+// and finished by phase 2 (a small grid striding over the list).  A warp therefore never idles 15 lanes
+// while one instance runs the Ruiz passes or another 25 iterations.
 #include "mpc_kernels.cuh"
 
 #include <cmath>

@@ -5,10 +5,6 @@
 
 namespace wcb {
 
-// (legacy chain-order helpers; K2 uses the split stage-indexed layout)
-__device__ __forceinline__ int cx(int N, int k) { return 2 * (N - k); }
-__device__ __forceinline__ int cu(int N, int k) { return 2 * (N - k) - 1; }
-
 __device__ __forceinline__ double limit_scaling(double v)
 {
     v = v < kMinScaling ? 1.0 : v;
@@ -82,7 +78,7 @@ __global__ void __launch_bounds__(128) mpc_prepare_kernel(MpcDev d, MpcTickIO io
     if (i >= d.B) return;
     if (i == 0 && d.cont_count) *d.cont_count = 0; // consumed by phase 2 of the previous tick
     const size_t B = (size_t)d.B;
-    const int N = d.N, nA = 2 * N + 1, nR = N + 1;
+    const int N = d.N, nR = N + 1;
     const uint8_t cur = (uint8_t)((io.l_contact[i] ? 1 : 0) | (io.r_contact[i] ? 2 : 0));
     int flags = 0;
     if (cur != d.feet[i]) {
@@ -112,7 +108,6 @@ __global__ void __launch_bounds__(128) mpc_prepare_kernel(MpcDev d, MpcTickIO io
     if (!inited && d.setup_list) d.setup_list[atomicAdd(d.setup_count, 1)] = i; // osqp_setup pending
     const bool reset = io.reset ? (io.reset[i] != 0) : false;
     const double Q[2] = {d.Qd[i], d.Qd[B + i]};
-    const double R[2] = {d.Rd[i], d.Rd[B + i]};
     const int head = d.ring_head;
 
     // ---- MPCSolver::setGradient (state block; the input block -R u_prev is formed in K2)
