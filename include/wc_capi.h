@@ -401,6 +401,36 @@ wc_status wc_glue_com_reference_dev(wc_glue* h, const double* dcm_des, const dou
 wc_status wc_glue_integrate_joints_dev(wc_glue* h, const double* dq, double* q_des, void* stream);
 int64_t wc_glue_launch_count(const wc_glue* h);
 
+/* ---- the alternative DCM controller, the measured-ZMP / DCM evaluation and the logger row ---- */
+/* WalkingDCMReactiveController::evaluateControl (WalkingDCMReactiveController.cpp:63-81), stateless:
+ *   zmp_des = dcm_des - dcm_vel_des / omega - kDCM (dcm_des - dcm_meas)      all [2*B]
+ * omega = sqrt(gravity / com_height) of the handle (:38-42); k_dcm [B] per-instance gains or NULL (k_dcm_const, `kDCM`
+ * of dcmReactiveControllerParams.ini). */
+wc_status wc_glue_reactive_dcm_dev(wc_glue* h, double k_dcm_const, const double* k_dcm, const double* dcm_des,
+                                   const double* dcm_vel_des, const double* dcm_meas, double* zmp_des, void* stream);
+/* same with host pointers (synchronous; what the host class WalkingDCMReactiveController calls) */
+wc_status wc_glue_reactive_dcm_host(wc_glue* h, double k_dcm_const, const double* k_dcm, const double* dcm_des,
+                                    const double* dcm_vel_des, const double* dcm_meas, double* zmp_des);
+/* WalkingFK::evaluateDCM, unfiltered branch (WalkingForwardKinematics.cpp:312-340): com, com_vel [>=2*B] -> dcm [2*B]. */
+wc_status wc_glue_evaluate_dcm_dev(wc_glue* h, const double* com, const double* com_vel, double* dcm, void* stream);
+/* WalkingModule::evaluateZMP (WalkingModule.cpp:824-876): l_wrench, r_wrench [6*B] (force then torque, foot frame),
+ * lf_H, rf_H [12*B] -> zmp [2*B]; ok [B] (may be NULL) = 0 where the reference returns false (total fz < 0.1). */
+wc_status wc_glue_evaluate_zmp_dev(wc_glue* h, const double* l_wrench, const double* r_wrench, const double* lf_H,
+                                   const double* rf_H, double* zmp, int32_t* ok, void* stream);
+/* The row WalkingModule::updateModule sends to the WalkingLogger (WalkingModule.cpp:793-803) in the column order of
+ * startRecord (:1231-1250): rows [WC_LOG_COLUMNS*B], column c of instance i at [c*B+i].  Poses are [12*B] transforms
+ * written as position + Rotation::asRPY; NULL inputs give zero columns.  The text format of the logger module
+ * (WalkingLoggerModule.cpp:54-90,142-171) is written by the host class WalkingLogger. */
+#define WC_LOG_COLUMNS 53
+typedef struct wc_log_inputs {
+    const double *dcm, *dcm_des, *dcm_vel_des, *zmp, *zmp_des; /* [2*B] */
+    const double *com;                                         /* [3*B] */
+    const double *com_des_xy, *com_vel_des_xy;                 /* [>=2*B] */
+    const double *lf_H, *rf_H, *lf_H_des, *rf_H_des;           /* [12*B] */
+    const double *lf_err, *rf_err;                             /* [6*B] getLeftFootError / getRightFootError */
+} wc_log_inputs;
+wc_status wc_glue_log_pack_dev(wc_glue* h, const wc_log_inputs* in, double* rows, void* stream);
+
 /* Measured FP64 FMA throughput of the device (register-resident FMA chains, all SMs), in GFLOP/s:
  * the denominator of the FP64 roofline fraction that bench.py reports next to the HBM one
  * (MEASURED_PEAKS.json carries no FP64 entry). */

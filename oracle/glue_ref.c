@@ -6,9 +6,18 @@
  *   joint integration                       modules/Walking_module/src/WalkingModule.cpp:741-744
  * iCub::ctrl::Integrator (external, iCub ctrlLib, not vendored) is restated from its published rule: Tustin
  * integration y_k = y_{k-1} + Ts/2 (x_k + x_{k-1}), reset(y0) sets y = y0 and x_old = 0.
+ * and (rank 4):
+ *   WalkingDCMReactiveController::evaluateControl   modules/Walking_module/src/WalkingDCMReactiveController.cpp:63-81
+ *   WalkingModule::evaluateZMP                       modules/Walking_module/src/WalkingModule.cpp:824-876
+ *   WalkingFK::evaluateDCM                           modules/Walking_module/src/WalkingForwardKinematics.cpp:312-340
+ *   the logger row of updateModule                   modules/Walking_module/src/WalkingModule.cpp:793-803, 1231-1250
+ *     (iDynTree::Rotation::asRPY is external: restated from its documented convention R = Rz(yaw) Ry(pitch) Rx(roll))
  * PARITY UNPINNED (no reference tests / golden vectors); checked against closed forms in tests/test_glue.py.
  */
 #include <math.h>
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
 #include <stdlib.h>
 #include <string.h>
 
@@ -88,5 +97,78 @@ void wco_glue_integrate_joints(wco_glue* g, const double* dq, double* q_des)
     for (size_t k = 0; k < n; k++) {
         const double y = tustin(&g->q_y[k], &g->q_v[k], dq[k], g->cfg.sampling_time);
         if (q_des) q_des[k] = y;
+    }
+}
+
+/* WalkingDCMReactiveController.cpp:74-77 */
+void wco_reactive_dcm(int B, double omega, double k_const, const double* k_dcm, const double* dcm_des,
+                      const double* dcm_vel_des, const double* dcm_meas, double* zmp_des)
+{
+    for (int i = 0; i < B; i++) {
+        const double k = k_dcm ? k_dcm[i] : k_const;
+        for (int a = 0; a < 2; a++) {
+            const size_t j = (size_t)a * B + i;
+            zmp_des[j] = dcm_des[j] - 1 / omega * dcm_vel_des[j] - k * (dcm_des[j] - dcm_meas[j]);
+        }
+    }
+}
+
+/* WalkingForwardKinematics.cpp:329-335 (m_useFilters == false) */
+void wco_evaluate_dcm(int B, double omega, const double* com, const double* com_vel, double* dcm)
+{
+    for (int i = 0; i < B; i++)
+        for (int a = 0; a < 2; a++) dcm[(size_t)a * B + i] = com[(size_t)a * B + i] + com_vel[(size_t)a * B + i] / omega;
+}
+
+/* WalkingModule.cpp:824-876; wrenches [6][B] force then torque, transforms [12][B] row-major 3x4 */
+void wco_evaluate_zmp(int B, const double* lw, const double* rw, const double* lf_H, const double* rf_H, double* zmp, int* ok)
+{
+    for (int i = 0; i < B; i++) {
+        const size_t Bz = (size_t)B;
+        double zl[3] = {0, 0, 0}, zr[3] = {0, 0, 0}, ld = 0.0, rd = 0.0;
+        const double fzr = rw[2 * Bz + i], fzl = lw[2 * Bz + i];
+        if (!(fzr < 0.001)) { zr[0] = -rw[4 * Bz + i] / fzr; zr[1] = rw[3 * Bz + i] / fzr; rd = 1.0; }
+        if (!(fzl < 0.001)) { zl[0] = -lw[4 * Bz + i] / fzl; zl[1] = lw[3 * Bz + i] / fzl; ld = 1.0; }
+        const double totalZ = fzr + fzl;
+        zmp[i] = 0.0; zmp[Bz + i] = 0.0;
+        if (totalZ < 0.1) { if (ok) ok[i] = 0; continue; }
+        double wl[2], wr[2];
+        for (int r = 0; r < 2; r++) {
+            wl[r] = lf_H[(4 * r) * Bz + i] * zl[0] + lf_H[(4 * r + 1) * Bz + i] * zl[1] + lf_H[(4 * r + 2) * Bz + i] * zl[2] + lf_H[(4 * r + 3) * Bz + i];
+            wr[r] = rf_H[(4 * r) * Bz + i] * zr[0] + rf_H[(4 * r + 1) * Bz + i] * zr[1] + rf_H[(4 * r + 2) * Bz + i] * zr[2] + rf_H[(4 * r + 3) * Bz + i];
+        }
+        for (int r = 0; r < 2; r++) zmp[(size_t)r * Bz + i] = ((fzl * ld) / totalZ) * wl[r] + ((fzr * rd) / totalZ) * wr[r];
+        if (ok) ok[i] = 1;
+    }
+}
+
+static void as_rpy(const double* H, size_t B, size_t i, double* rpy)
+{
+#define R_(r, c) H[(size_t)(4 * (r) + (c)) * B + i]
+    if (R_(2, 0) < 1.0) {
+        if (R_(2, 0) > -1.0) { rpy[0] = atan2(R_(2, 1), R_(2, 2)); rpy[1] = asin(-R_(2, 0)); rpy[2] = atan2(R_(1, 0), R_(0, 0)); }
+        else { rpy[0] = 0.0; rpy[1] = M_PI / 2.0; rpy[2] = -atan2(-R_(1, 2), R_(1, 1)); }
+    } else { rpy[0] = 0.0; rpy[1] = -M_PI / 2.0; rpy[2] = atan2(-R_(1, 2), R_(1, 1)); }
+#undef R_
+}
+
+/* the 53 columns of WalkingModule.cpp:1231-1250 from the arguments of sendData (:793-803); out [53][B] */
+void wco_log_pack(int B, const wc_log_inputs* in, double* out)
+{
+    const size_t Bz = (size_t)B;
+    for (size_t i = 0; i < Bz; i++) {
+        int c = 0;
+#define PUT(v) do { out[(size_t)c * Bz + i] = (v); c++; } while (0)
+#define PUTN(p, n) do { for (int k_ = 0; k_ < (n); k_++) PUT((p) ? (p)[(size_t)k_ * Bz + i] : 0.0); } while (0)
+#define PUTPOSE(Hp) do { if (!(Hp)) { for (int k_ = 0; k_ < 6; k_++) PUT(0.0); } else { double rpy_[3]; \
+        PUT((Hp)[3 * Bz + i]); PUT((Hp)[7 * Bz + i]); PUT((Hp)[11 * Bz + i]); as_rpy((Hp), Bz, i, rpy_); \
+        PUT(rpy_[0]); PUT(rpy_[1]); PUT(rpy_[2]); } } while (0)
+        PUTN(in->dcm, 2); PUTN(in->dcm_des, 2); PUTN(in->dcm_vel_des, 2); PUTN(in->zmp, 2); PUTN(in->zmp_des, 2);
+        PUTN(in->com, 3); PUTN(in->com_des_xy, 2); PUTN(in->com_vel_des_xy, 2);
+        PUTPOSE(in->lf_H); PUTPOSE(in->rf_H); PUTPOSE(in->lf_H_des); PUTPOSE(in->rf_H_des);
+        PUTN(in->lf_err, 6); PUTN(in->rf_err, 6);
+#undef PUT
+#undef PUTN
+#undef PUTPOSE
     }
 }

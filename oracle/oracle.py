@@ -382,3 +382,54 @@ class GlueBatch:
         out = np.zeros((self.nJ, self.B))
         self.L.wco_glue_integrate_joints(self.h, _dp(dq), _dp(out))
         return out
+
+
+# ---- rank 4: WalkingDCMReactiveController, evaluateDCM, evaluateZMP, logger row ---------------------------------
+LOG_COLUMNS = 53
+LOG_FIELDS = ("dcm", "dcm_des", "dcm_vel_des", "zmp", "zmp_des", "com", "com_des_xy", "com_vel_des_xy",
+              "lf_H", "rf_H", "lf_H_des", "rf_H_des", "lf_err", "rf_err")
+
+
+class LogInputs(C.Structure):
+    _fields_ = [(k, C.POINTER(C.c_double)) for k in LOG_FIELDS]
+
+
+def reactive_dcm(omega, k_dcm, dcm_des, dcm_vel_des, dcm_meas):
+    """k_dcm: float or [B] array"""
+    L = lib(); dp = C.POINTER(C.c_double)
+    L.wco_reactive_dcm.argtypes = [C.c_int, C.c_double, C.c_double, dp, dp, dp, dp, dp]
+    a, b, c = _f64(dcm_des), _f64(dcm_vel_des), _f64(dcm_meas)
+    B = a.shape[1]
+    karr = None if np.isscalar(k_dcm) else _f64(k_dcm)
+    out = np.zeros((2, B))
+    L.wco_reactive_dcm(B, omega, float(k_dcm) if karr is None else 0.0, _dp(karr), _dp(a), _dp(b), _dp(c), _dp(out))
+    return out
+
+
+def evaluate_dcm(omega, com, com_vel):
+    L = lib(); dp = C.POINTER(C.c_double)
+    L.wco_evaluate_dcm.argtypes = [C.c_int, C.c_double, dp, dp, dp]
+    a, b = _f64(com), _f64(com_vel)
+    out = np.zeros((2, a.shape[1]))
+    L.wco_evaluate_dcm(a.shape[1], omega, _dp(a), _dp(b), _dp(out))
+    return out
+
+
+def evaluate_zmp(l_wrench, r_wrench, lf_H, rf_H):
+    L = lib(); dp = C.POINTER(C.c_double)
+    L.wco_evaluate_zmp.argtypes = [C.c_int, dp, dp, dp, dp, dp, C.POINTER(C.c_int)]
+    a, b, c, d = _f64(l_wrench), _f64(r_wrench), _f64(lf_H), _f64(rf_H)
+    B = a.shape[1]
+    out = np.zeros((2, B)); ok = np.zeros(B, dtype=np.int32)
+    L.wco_evaluate_zmp(B, _dp(a), _dp(b), _dp(c), _dp(d), _dp(out), ok.ctypes.data_as(C.POINTER(C.c_int)))
+    return out, ok
+
+
+def log_pack(B, **fields):
+    L = lib()
+    L.wco_log_pack.argtypes = [C.c_int, C.POINTER(LogInputs), C.POINTER(C.c_double)]
+    keep = {k: _f64(v) for k, v in fields.items() if v is not None}
+    li = LogInputs(**{k: _dp(keep.get(k)) for k in LOG_FIELDS})
+    out = np.zeros((LOG_COLUMNS, B))
+    L.wco_log_pack(B, C.byref(li), _dp(out))
+    return out

@@ -97,6 +97,12 @@ void wco_glue_com_reference(wco_glue* g, const double* dcm_des, const double* zm
                             const double* com_meas, const double* com_z_des, const double* com_z_vel_des,
                             const double* k_zmp, const double* k_com, double* com_pos_des, double* com_vel_des);
 void wco_glue_integrate_joints(wco_glue* g, const double* dq, double* q_des);
+/* rank 4: WalkingDCMReactiveController, WalkingFK::evaluateDCM, WalkingModule::evaluateZMP, the logger row */
+void wco_reactive_dcm(int B, double omega, double k_const, const double* k_dcm, const double* dcm_des,
+                      const double* dcm_vel_des, const double* dcm_meas, double* zmp_des);
+void wco_evaluate_dcm(int B, double omega, const double* com, const double* com_vel, double* dcm);
+void wco_evaluate_zmp(int B, const double* lw, const double* rw, const double* lf_H, const double* rf_H, double* zmp, int* ok);
+void wco_log_pack(int B, const wc_log_inputs* in, double* out);
 
 #ifdef __cplusplus
 }

@@ -80,6 +80,32 @@ class GlueConfig(C.Structure):
                 ("com_height", C.c_double), ("gravity", C.c_double), ("k_zmp", C.c_double), ("k_com", C.c_double)]
 
 
+LOG_COLUMNS = 53
+LOG_FIELDS = ("dcm", "dcm_des", "dcm_vel_des", "zmp", "zmp_des", "com", "com_des_xy", "com_vel_des_xy",
+              "lf_H", "rf_H", "lf_H_des", "rf_H_des", "lf_err", "rf_err")
+# column names of the logger file, WalkingModule.cpp:1231-1250
+LOG_NAMES = ("dcm_x dcm_y dcm_des_x dcm_des_y dcm_des_dx dcm_des_dy zmp_x zmp_y zmp_des_x zmp_des_y com_x com_y com_z "
+             "com_des_x com_des_y com_des_dx com_des_dy lf_x lf_y lf_z lf_roll lf_pitch lf_yaw rf_x rf_y rf_z rf_roll "
+             "rf_pitch rf_yaw lf_des_x lf_des_y lf_des_z lf_des_roll lf_des_pitch lf_des_yaw rf_des_x rf_des_y rf_des_z "
+             "rf_des_roll rf_des_pitch rf_des_yaw lf_err_x lf_err_y lf_err_z lf_err_roll lf_err_pitch lf_err_yaw rf_err_x "
+             "rf_err_y rf_err_z rf_err_roll rf_err_pitch rf_err_yaw").split()
+
+
+class LogInputs(C.Structure):
+    _fields_ = [(k, C.POINTER(C.c_double)) for k in LOG_FIELDS]
+
+
+def write_dataset(path, times, rows):
+    """Text file in the WalkingLogger module's format (WalkingLoggerModule.cpp:62-84 header, :163-168 rows):
+    `time name ... ` then one `t v0 v1 ... ` line per tick, C++ ostream default formatting (%g, 6 digits).
+    rows: [T, 53] host array of one instance."""
+    assert len(LOG_NAMES) == LOG_COLUMNS
+    with open(path, "w") as f:
+        f.write("time " + "".join(n + " " for n in LOG_NAMES) + "\n")
+        for t, r in zip(times, rows):
+            f.write("%g " % t + "".join("%g " % float(v) for v in r) + "\n")
+
+
 def build(verbose=False):
     """Compile libwc_b200.so for sm_100a with nvcc (cross-compiles without a GPU)."""
     out = subprocess.run(["make", "-C", CSRC], capture_output=True, text=True)
@@ -137,6 +163,11 @@ def lib():
     L.wc_glue_com_reference_dev.argtypes = [_VP] + [_VP] * 10 + [_VP]; L.wc_glue_com_reference_dev.restype = i32
     L.wc_glue_integrate_joints_dev.argtypes = [_VP, _VP, _VP, _VP]; L.wc_glue_integrate_joints_dev.restype = i32
     L.wc_glue_launch_count.argtypes = [_VP]; L.wc_glue_launch_count.restype = i64
+    L.wc_glue_reactive_dcm_dev.argtypes = [_VP, C.c_double] + [_VP] * 6; L.wc_glue_reactive_dcm_dev.restype = i32
+    L.wc_glue_reactive_dcm_host.argtypes = [_VP, C.c_double] + [_VP] * 5; L.wc_glue_reactive_dcm_host.restype = i32
+    L.wc_glue_evaluate_dcm_dev.argtypes = [_VP] * 5; L.wc_glue_evaluate_dcm_dev.restype = i32
+    L.wc_glue_evaluate_zmp_dev.argtypes = [_VP] * 8; L.wc_glue_evaluate_zmp_dev.restype = i32
+    L.wc_glue_log_pack_dev.argtypes = [_VP, C.POINTER(LogInputs), _VP, _VP]; L.wc_glue_log_pack_dev.restype = i32
     L.wc_measure_fp64_peak.argtypes = [i32, C.POINTER(C.c_double)]; L.wc_measure_fp64_peak.restype = i32
     if hasattr(L, "wc_ik_create"):
         L.wc_ik_create.argtypes = [C.POINTER(IkConfig), C.POINTER(Model), i32, i32, C.POINTER(_VP)]
@@ -469,6 +500,44 @@ class GlueBatch:
             out = torch.empty(self.nJ, self.B, dtype=torch.float64, device=dq.device)
         _check(lib().wc_glue_integrate_joints_dev(self.h, _ptr(dq), _ptr(out), self._stream(stream)),
                "wc_glue_integrate_joints_dev")
+        return out
+
+    # ---- SURVEY §8(f) rank 4
+    def reactive_dcm(self, k_dcm, dcm_des, dcm_vel_des, dcm_meas, out=None, stream=None):
+        """WalkingDCMReactiveController::evaluateControl; k_dcm: float or [B] tensor"""
+        import torch
+        if out is None:
+            out = torch.empty(2, self.B, dtype=torch.float64, device=dcm_des.device)
+        kt = k_dcm if isinstance(k_dcm, torch.Tensor) else None
+        _check(lib().wc_glue_reactive_dcm_dev(self.h, 0.0 if kt is not None else float(k_dcm), _ptr(kt), _ptr(dcm_des),
+                                              _ptr(dcm_vel_des), _ptr(dcm_meas), _ptr(out), self._stream(stream)),
+               "wc_glue_reactive_dcm_dev")
+        return out
+
+    def evaluate_dcm(self, com, com_vel, out=None, stream=None):
+        import torch
+        if out is None:
+            out = torch.empty(2, self.B, dtype=torch.float64, device=com.device)
+        _check(lib().wc_glue_evaluate_dcm_dev(self.h, _ptr(com), _ptr(com_vel), _ptr(out), self._stream(stream)),
+               "wc_glue_evaluate_dcm_dev")
+        return out
+
+    def evaluate_zmp(self, l_wrench, r_wrench, lf_H, rf_H, stream=None):
+        import torch
+        zmp = torch.empty(2, self.B, dtype=torch.float64, device=lf_H.device)
+        ok = torch.empty(self.B, dtype=torch.int32, device=lf_H.device)
+        _check(lib().wc_glue_evaluate_zmp_dev(self.h, _ptr(l_wrench), _ptr(r_wrench), _ptr(lf_H), _ptr(rf_H), _ptr(zmp),
+                                              _ptr(ok), self._stream(stream)), "wc_glue_evaluate_zmp_dev")
+        return zmp, ok
+
+    def log_pack(self, out=None, stream=None, **fields):
+        """the 53 logger columns of one tick -> [53, B] (fields: LOG_FIELDS, missing ones give zero columns)"""
+        import torch
+        dev = next(v.device for v in fields.values() if v is not None)
+        if out is None:
+            out = torch.empty(LOG_COLUMNS, self.B, dtype=torch.float64, device=dev)
+        li = LogInputs(**{k: C.cast(_ptr(fields.get(k)), C.POINTER(C.c_double)) for k in LOG_FIELDS})
+        _check(lib().wc_glue_log_pack_dev(self.h, C.byref(li), _ptr(out), self._stream(stream)), "wc_glue_log_pack_dev")
         return out
 
     @property

@@ -5,6 +5,11 @@
 //                                                     modules/Walking_module/src/WalkingZMPController.cpp:126-172
 //   joint-velocity integration of updateModule        modules/Walking_module/src/WalkingModule.cpp:741-744
 //   iCub::ctrl::Integrator (external, ctrlLib): Tustin rule y_k = y_{k-1} + Ts/2 (x_k + x_{k-1}), reset(y0): x_old = 0
+// and the alternative DCM controller and the logger row:
+//   WalkingDCMReactiveController::evaluateControl     modules/Walking_module/src/WalkingDCMReactiveController.cpp:63-81
+//   WalkingModule::evaluateZMP                        modules/Walking_module/src/WalkingModule.cpp:824-876
+//   WalkingFK::evaluateDCM                            modules/Walking_module/src/WalkingForwardKinematics.cpp:312-340
+//   the 53 columns of m_walkingLogger->sendData       modules/Walking_module/src/WalkingModule.cpp:793-803, 1231-1250
 // The gain scheduling of WalkingZMPController::setPhase (iCub::ctrl::minJerkTrajGen, external) is not restated:
 // gains are inputs (constants from the configuration, or per-instance arrays the caller schedules).
 // One thread per instance; every array is field-major SoA fp64; the kernels are HBM-streaming.
@@ -84,6 +89,107 @@ __global__ void glue_integrate_joints_kernel(size_t n, double half_dt, const dou
     if (q_des) q_des[k] = y;
 }
 
+// WalkingDCMReactiveController::evaluateControl: u = xi_des - dxi_des / omega - kDCM (xi_des - xi)
+__global__ void glue_reactive_dcm_kernel(int B, double omega, double k_c, const double* k_dcm, const double* dcm_des,
+                                         const double* dcm_vel_des, const double* dcm_meas, double* zmp_des)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    const size_t Bz = (size_t)B;
+    const double k = k_dcm ? k_dcm[i] : k_c;
+#pragma unroll
+    for (int a = 0; a < 2; a++) {
+        const double xd = dcm_des[a * Bz + i];
+        zmp_des[a * Bz + i] = xd - 1 / omega * dcm_vel_des[a * Bz + i] - k * (xd - dcm_meas[a * Bz + i]);
+    }
+}
+
+// WalkingFK::evaluateDCM (unfiltered branch): the xy projection of com + com_vel / omega
+__global__ void glue_evaluate_dcm_kernel(int B, double omega, const double* com, const double* com_vel, double* dcm)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    const size_t Bz = (size_t)B;
+    dcm[i] = com[i] + com_vel[i] / omega;
+    dcm[Bz + i] = com[Bz + i] + com_vel[Bz + i] / omega;
+}
+
+// WalkingModule::evaluateZMP: per-foot centre of pressure from the contact wrench (force, torque in the foot frame),
+// moved to the world frame and averaged with the normal forces as weights.  ok = 0 where the reference returns false
+// (total normal force < 0.1 N); the output of such an instance is left at 0.
+__global__ void glue_evaluate_zmp_kernel(int B, const double* lw, const double* rw, const double* lf_H, const double* rf_H,
+                                         double* zmp, int32_t* ok)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    const size_t Bz = (size_t)B;
+    const double fzl = lw[2 * Bz + i], fzr = rw[2 * Bz + i];
+    double out[2] = {0.0, 0.0};
+    const double totalZ = fzr + fzl;
+    const bool good = !(totalZ < 0.1);
+    if (good) {
+        double w[2][2] = {{0.0, 0.0}, {0.0, 0.0}}; // world xy of the left / right local ZMP (undefined -> local origin)
+        double defd[2];
+        for (int f = 0; f < 2; f++) {
+            const double* W = f == 0 ? lw : rw;
+            const double* H = f == 0 ? lf_H : rf_H;
+            const double fz = f == 0 ? fzl : fzr;
+            double px = 0.0, py = 0.0;
+            defd[f] = 0.0;
+            if (!(fz < 0.001)) {
+                px = -W[4 * Bz + i] / fz;
+                py = W[3 * Bz + i] / fz;
+                defd[f] = 1.0;
+            }
+            for (int r = 0; r < 2; r++) // Transform * Position with z = 0
+                w[f][r] = H[(4 * r + 0) * Bz + i] * px + H[(4 * r + 1) * Bz + i] * py + H[(4 * r + 3) * Bz + i];
+        }
+        for (int r = 0; r < 2; r++)
+            out[r] = ((fzl * defd[0]) / totalZ) * w[0][r] + ((fzr * defd[1]) / totalZ) * w[1][r];
+    }
+    zmp[i] = out[0]; zmp[Bz + i] = out[1];
+    if (ok) ok[i] = good ? 1 : 0;
+}
+
+// iDynTree::Rotation::asRPY (external; restated from its documented convention R = Rz(y) Ry(p) Rx(r))
+__device__ __forceinline__ void rot_as_rpy(const double* H, size_t Bz, int i, double* rpy)
+{
+    const double r20 = H[8 * Bz + i];
+    if (r20 < 1.0) {
+        if (r20 > -1.0) {
+            rpy[0] = atan2(H[9 * Bz + i], H[10 * Bz + i]);
+            rpy[1] = asin(-r20);
+            rpy[2] = atan2(H[4 * Bz + i], H[0 * Bz + i]);
+        } else { // not unique: yaw - roll = atan2(-R12, R11)
+            rpy[0] = 0.0; rpy[1] = M_PI / 2.0; rpy[2] = -atan2(-H[6 * Bz + i], H[5 * Bz + i]);
+        }
+    } else { // not unique: yaw + roll = atan2(-R12, R11)
+        rpy[0] = 0.0; rpy[1] = -M_PI / 2.0; rpy[2] = atan2(-H[6 * Bz + i], H[5 * Bz + i]);
+    }
+}
+
+// one logger row per instance, column-major [WC_LOG_COLUMNS][B] in the order of startRecord (WalkingModule.cpp:1231-1250)
+__global__ void glue_log_pack_kernel(int B, wc_log_inputs in, double* out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    const size_t Bz = (size_t)B;
+    int c = 0;
+    auto put = [&](double v) { out[(size_t)c * Bz + i] = v; c++; };
+    auto put_n = [&](const double* p, int n) { for (int k = 0; k < n; k++) put(p ? p[k * Bz + i] : 0.0); };
+    auto put_pose = [&](const double* H) {
+        if (!H) { for (int k = 0; k < 6; k++) put(0.0); return; }
+        put(H[3 * Bz + i]); put(H[7 * Bz + i]); put(H[11 * Bz + i]);
+        double rpy[3]; rot_as_rpy(H, Bz, i, rpy);
+        put(rpy[0]); put(rpy[1]); put(rpy[2]);
+    };
+    put_n(in.dcm, 2); put_n(in.dcm_des, 2); put_n(in.dcm_vel_des, 2);
+    put_n(in.zmp, 2); put_n(in.zmp_des, 2); put_n(in.com, 3);
+    put_n(in.com_des_xy, 2); put_n(in.com_vel_des_xy, 2);
+    put_pose(in.lf_H); put_pose(in.rf_H); put_pose(in.lf_H_des); put_pose(in.rf_H_des);
+    put_n(in.lf_err, 6); put_n(in.rf_err, 6);
+}
+
 } // namespace
 
 extern "C" {
@@ -155,6 +261,65 @@ wc_status wc_glue_integrate_joints_dev(wc_glue* h, const double* dq, double* q_d
         n, 0.5 * h->cfg.sampling_time, dq, h->q_y, h->q_v, q_des);
     h->launches += 1;
     return cudaGetLastError() == cudaSuccess ? WC_OK : WC_ERR_CUDA;
+}
+
+wc_status wc_glue_reactive_dcm_dev(wc_glue* h, double k_dcm_const, const double* k_dcm, const double* dcm_des,
+                                   const double* dcm_vel_des, const double* dcm_meas, double* zmp_des, void* stream)
+{
+    if (!h || !dcm_des || !dcm_vel_des || !dcm_meas || !zmp_des) return WC_ERR_INVALID_ARG;
+    if (cudaSetDevice(h->device) != cudaSuccess) return WC_ERR_CUDA;
+    glue_reactive_dcm_kernel<<<(h->B + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        h->B, h->omega, k_dcm_const, k_dcm, dcm_des, dcm_vel_des, dcm_meas, zmp_des);
+    h->launches += 1;
+    return cudaGetLastError() == cudaSuccess ? WC_OK : WC_ERR_CUDA;
+}
+
+wc_status wc_glue_evaluate_dcm_dev(wc_glue* h, const double* com, const double* com_vel, double* dcm, void* stream)
+{
+    if (!h || !com || !com_vel || !dcm) return WC_ERR_INVALID_ARG;
+    if (cudaSetDevice(h->device) != cudaSuccess) return WC_ERR_CUDA;
+    glue_evaluate_dcm_kernel<<<(h->B + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(h->B, h->omega, com, com_vel, dcm);
+    h->launches += 1;
+    return cudaGetLastError() == cudaSuccess ? WC_OK : WC_ERR_CUDA;
+}
+
+wc_status wc_glue_evaluate_zmp_dev(wc_glue* h, const double* l_wrench, const double* r_wrench, const double* lf_H,
+                                   const double* rf_H, double* zmp, int32_t* ok, void* stream)
+{
+    if (!h || !l_wrench || !r_wrench || !lf_H || !rf_H || !zmp) return WC_ERR_INVALID_ARG;
+    if (cudaSetDevice(h->device) != cudaSuccess) return WC_ERR_CUDA;
+    glue_evaluate_zmp_kernel<<<(h->B + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        h->B, l_wrench, r_wrench, lf_H, rf_H, zmp, ok);
+    h->launches += 1;
+    return cudaGetLastError() == cudaSuccess ? WC_OK : WC_ERR_CUDA;
+}
+
+wc_status wc_glue_log_pack_dev(wc_glue* h, const wc_log_inputs* in, double* rows, void* stream)
+{
+    if (!h || !in || !rows) return WC_ERR_INVALID_ARG;
+    if (cudaSetDevice(h->device) != cudaSuccess) return WC_ERR_CUDA;
+    glue_log_pack_kernel<<<(h->B + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(h->B, *in, rows);
+    h->launches += 1;
+    return cudaGetLastError() == cudaSuccess ? WC_OK : WC_ERR_CUDA;
+}
+
+// WalkingDCMReactiveController for the host classes: a batch of one (or a few) instances with host pointers
+wc_status wc_glue_reactive_dcm_host(wc_glue* h, double k_dcm_const, const double* k_dcm, const double* dcm_des,
+                                    const double* dcm_vel_des, const double* dcm_meas, double* zmp_des)
+{
+    if (!h || !dcm_des || !dcm_vel_des || !dcm_meas || !zmp_des) return WC_ERR_INVALID_ARG;
+    if (cudaSetDevice(h->device) != cudaSuccess) return WC_ERR_CUDA;
+    const size_t Bz = (size_t)h->B;
+    double* d = nullptr;
+    if (cudaMalloc(&d, 9 * Bz * sizeof(double)) != cudaSuccess) return WC_ERR_ALLOC;
+    cudaMemcpy(d, dcm_des, 2 * Bz * sizeof(double), cudaMemcpyHostToDevice);
+    cudaMemcpy(d + 2 * Bz, dcm_vel_des, 2 * Bz * sizeof(double), cudaMemcpyHostToDevice);
+    cudaMemcpy(d + 4 * Bz, dcm_meas, 2 * Bz * sizeof(double), cudaMemcpyHostToDevice);
+    if (k_dcm) cudaMemcpy(d + 8 * Bz, k_dcm, Bz * sizeof(double), cudaMemcpyHostToDevice);
+    wc_status st = wc_glue_reactive_dcm_dev(h, k_dcm_const, k_dcm ? d + 8 * Bz : nullptr, d, d + 2 * Bz, d + 4 * Bz, d + 6 * Bz, nullptr);
+    if (st == WC_OK && cudaMemcpy(zmp_des, d + 6 * Bz, 2 * Bz * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) st = WC_ERR_CUDA;
+    cudaFree(d);
+    return st;
 }
 
 } // extern "C"

@@ -6,10 +6,14 @@
 #include <cstdio>
 #include <cstring>
 #include <deque>
+#include <fstream>
+#include <string>
 #include <vector>
 
 #include "../../oracle/wc_oracle.h"
 #include "WalkingDCMModelPredictiveController.hpp"
+#include "WalkingDCMReactiveController.hpp"
+#include "WalkingLogger.hpp"
 #include "WalkingForwardKinematics.hpp"
 #include "WalkingQPInverseKinematics.hpp"
 
@@ -146,7 +150,39 @@ int main(int argc, char** argv)
         dcmDeque.pop_front();
         { double r[2]; dcm_ref(t + N + 1, r); iDynTree::Vector2 v; v(0) = r[0]; v(1) = r[1]; dcmDeque.push_back(v); }
     }
+    // ======== use_mpc off: WalkingDCMReactiveController (WalkingModule.cpp:638-655) + the logger row (:793-803)
+    double worst_reactive = 0.0;
+    {
+        yarp::os::Searchable rcCfg, logCfg;
+        rcCfg.put("kDCM", 1.5); rcCfg.put("com_height", 0.53);
+        WalkingDCMReactiveController reactive;
+        iDynTree::Vector2 out;
+        if (reactive.evaluateControl() || reactive.getControllerOutput(out)) { std::fprintf(stderr, "reactive: latches\n"); failures++; }
+        if (!reactive.initialize(rcCfg)) { std::fprintf(stderr, "reactive: initialize failed\n"); failures++; }
+        logCfg.put("sampling_time", dT); logCfg.put("file_name", std::string("/tmp/wc_dropin_dataset.txt"));
+        WalkingLogger logger;
+        bool lok = logger.configure(logCfg, "test") && logger.startRecord({"record", "dcm_x", "dcm_y", "dcm_des_x", "dcm_des_y", "zmp_des_x", "zmp_des_y"});
+        for (int t = 0; t < 20; t++) {
+            iDynTree::Vector2 xd, vd, x;
+            double r0[2], r1[2]; dcm_ref(t, r0); dcm_ref(t + 1, r1);
+            for (int a = 0; a < 2; a++) { xd(a) = r0[a]; vd(a) = (r1[a] - r0[a]) / dT; x(a) = r0[a] + 0.002 * std::sin(0.3 * t + a); }
+            reactive.setFeedback(x); reactive.setReferenceSignal(xd, vd);
+            if (!reactive.evaluateControl() || !reactive.getControllerOutput(out)) { std::fprintf(stderr, "reactive: tick %d failed\n", t); failures++; continue; }
+            double want[2];
+            wco_reactive_dcm(1, omega, 1.5, nullptr, xd.data(), vd.data(), x.data(), want);
+            for (int a = 0; a < 2; a++) worst_reactive = std::fmax(worst_reactive, std::fabs(out(a) - want[a]));
+            logger.sendData(x, xd, out);
+        }
+        logger.quit();
+        std::ifstream f(logger.fileName()); std::string line; int rows = 0;
+        std::getline(f, line);
+        if (!lok || line != "time dcm_x dcm_y dcm_des_x dcm_des_y zmp_des_x zmp_des_y ") { std::fprintf(stderr, "logger: header '%s'\n", line.c_str()); failures++; }
+        while (std::getline(f, line)) rows++;
+        if (rows != 20) { std::fprintf(stderr, "logger: %d rows\n", rows); failures++; }
+    }
     wco_mpc_free(ompc);
+    std::printf("reactive controller: worst abs err %.3e\n", worst_reactive);
+    if (worst_reactive > 1e-13) failures++;
     std::printf("drop-in test: %d ticks, horizon %d, worst rel ZMP err %.3e, worst dq err %.3e rad/s, failures %d\n", T, N, worst_zmp,
                 worst_dq, failures);
     return (failures == 0 && worst_zmp <= 1e-6 && worst_dq <= 1e-5) ? 0 : 1;

@@ -110,6 +110,7 @@ public:
     bool check(const std::string& k) const { return num_.count(k) || str_.count(k); }
     const std::vector<double>& list(const std::string& k) const { static const std::vector<double> e; auto it = num_.find(k); return it == num_.end() ? e : it->second; }
     double number(const std::string& k, double dflt) const { auto it = num_.find(k); return (it == num_.end() || it->second.empty()) ? dflt : it->second[0]; }
+    std::string string(const std::string& k, const std::string& dflt) const { auto it = str_.find(k); return it == str_.end() ? dflt : it->second; }
     void put(const std::string& k, const std::vector<double>& v) { num_[k] = v; }
     void put(const std::string& k, double v) { num_[k] = {v}; }
     void put(const std::string& k, const std::string& v) { str_[k] = v; }
