@@ -431,6 +431,59 @@ typedef struct wc_log_inputs {
 } wc_log_inputs;
 wc_status wc_glue_log_pack_dev(wc_glue* h, const wc_log_inputs* in, double* rows, void* stream);
 
+/* ---------------------------------------------------------------------------------- */
+/* On-device producer of the path's per-tick inputs: the signals  */
+/* WalkingModule reads from TrajectoryGenerator (TrajectoryGenerator.cpp:501-598) for a */
+/* batch of periodic gaits.  The reference's producer is the UnicyclePlanner library    */
+/* (external); this is the synthetic workload of SURVEY §8(d) with the shipped planner  */
+/* parameters (plannerParams.ini), not a restatement of the unicycle footstep planner.  */
+/* ---------------------------------------------------------------------------------- */
+typedef struct wc_traj wc_traj;
+typedef struct wc_traj_config {
+    int32_t step_ticks;     /* nominalDuration / sampling_time (0.9 s / 0.01 s) */
+    int32_t ds_ticks;       /* double-support ticks per step: switchOverSwingRatio r -> r / (1 + r) of the step */
+    int32_t n_steps;        /* footsteps tabulated per instance (k = -2 .. n_steps-1); queries beyond clamp */
+    int32_t reserved;
+    double sampling_time;   /* sampling_time */
+    double com_height;      /* com_height: omega = sqrt(gravity / com_height), CoM height trajectory */
+    double gravity;
+    double nominal_width;   /* nominalWidth */
+    double step_height;     /* stepHeight */
+    double zmp_delta[2];    /* leftZMPDelta = (dx, -dy), rightZMPDelta = (dx, +dy) */
+} wc_traj_config;
+/* iCubGazeboV2_5 plannerParams.ini; n_steps sized for `n_ticks` ticks + `horizon` look-ahead samples */
+void wc_traj_default_config(wc_traj_config* cfg, int32_t n_ticks, int32_t horizon);
+wc_status wc_traj_create(const wc_traj_config* cfg, int32_t B, int32_t device, wc_traj** out);
+void wc_traj_destroy(wc_traj* h);
+/* Per-instance gait (device pointers): phase [B] (tick offset into the step cycle, NULL = 0), step_len [B] (m),
+ * dtheta [B] (heading change per step, NULL = 0), theta0 [B] (initial heading, NULL = 0), first_left [B]
+ * (1 = even footsteps are left, NULL = 1).  Builds the footstep / ZMP / end-of-step DCM tables. */
+wc_status wc_traj_set_gait_dev(wc_traj* h, const int32_t* phase, const double* step_len, const double* dtheta,
+                               const double* theta0, const uint8_t* first_left, void* stream);
+/* DCM reference position / velocity (either may be NULL) of samples first_sample .. first_sample+n_samples-1:
+ * sample s, axis a of instance i at [(2*(s-first_sample)+a)*B+i].  With first_sample = t, n_samples = horizon+1 the
+ * position rows are the `dcm_ref` argument of wc_mpc_tick_dev at tick t (getDCMPositionTrajectory, :501-511). */
+wc_status wc_traj_dcm_dev(wc_traj* h, int32_t first_sample, int32_t n_samples, double* dcm_pos, double* dcm_vel, void* stream);
+/* Reference DCM at `tick` + N(0, sigma^2) per axis, Philox-4x32-10 with key = seed, counter = (instance, tick): dcm [2*B]. */
+wc_status wc_traj_measured_dcm_dev(wc_traj* h, int32_t tick, double sigma, uint64_t seed, double* dcm, void* stream);
+/* Feet signals at `tick` (any pointer may be NULL): getFeetTrajectories, getFeetTwist (mixed), getFeetStandingPeriods,
+ * getWhenUseLeftAsFixed, getCoMHeightTrajectory / getCoMHeightVelocity (:513-598). */
+typedef struct wc_traj_feet {
+    double *lf_H, *rf_H;             /* [12*B] */
+    double *lf_twist, *rf_twist;     /* [6*B] */
+    uint8_t *l_contact, *r_contact;  /* [B] */
+    uint8_t *left_is_fixed;          /* [B] */
+    double *com_height, *com_height_vel; /* [B] */
+} wc_traj_feet;
+wc_status wc_traj_feet_dev(wc_traj* h, int32_t tick, const wc_traj_feet* out, void* stream);
+/* Host pointers, synchronous (drop-in class TrajectoryGenerator): sets the gait and returns n_samples ticks of every
+ * signal, element e of sample s of instance i at [(s*E+e)*B+i] (E = 2, 12, 6, 1); outputs may be NULL. */
+wc_status wc_traj_generate_host(wc_traj* h, const int32_t* phase, const double* step_len, const double* dtheta, const double* theta0,
+                                const uint8_t* first_left, int32_t first_sample, int32_t n_samples, double* dcm_pos, double* dcm_vel,
+                                double* lf_H, double* rf_H, double* lf_twist, double* rf_twist, uint8_t* l_contact,
+                                uint8_t* r_contact, uint8_t* left_is_fixed, double* com_height, double* com_height_vel);
+int64_t wc_traj_launch_count(const wc_traj* h);
+
 /* Measured FP64 FMA throughput of the device (register-resident FMA chains, all SMs), in GFLOP/s:
  * the denominator of the FP64 roofline fraction that bench.py reports next to the HBM one
  * (MEASURED_PEAKS.json carries no FP64 entry). */

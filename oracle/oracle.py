@@ -433,3 +433,76 @@ def log_pack(B, **fields):
     out = np.zeros((LOG_COLUMNS, B))
     L.wco_log_pack(B, C.byref(li), _dp(out))
     return out
+
+
+# ---- rank 3: synthetic producer of the path's inputs (CPU twin of wc_traj_*) ---------------------------------------
+class TrajConfig(C.Structure):
+    _fields_ = [("step_ticks", C.c_int32), ("ds_ticks", C.c_int32), ("n_steps", C.c_int32), ("reserved", C.c_int32),
+                ("sampling_time", C.c_double), ("com_height", C.c_double), ("gravity", C.c_double),
+                ("nominal_width", C.c_double), ("step_height", C.c_double), ("zmp_delta", C.c_double * 2)]
+
+
+class TrajFeet(C.Structure):
+    _fields_ = [("lf_H", C.c_void_p), ("rf_H", C.c_void_p), ("lf_twist", C.c_void_p), ("rf_twist", C.c_void_p),
+                ("l_contact", C.c_void_p), ("r_contact", C.c_void_p), ("left_is_fixed", C.c_void_p),
+                ("com_height", C.c_void_p), ("com_height_vel", C.c_void_p)]
+
+
+def traj_default_config(n_ticks, horizon):
+    L = lib()
+    L.wc_traj_default_config.argtypes = [C.POINTER(TrajConfig), C.c_int32, C.c_int32]
+    cfg = TrajConfig()
+    L.wc_traj_default_config(C.byref(cfg), n_ticks, horizon)
+    return cfg
+
+
+def philox4x32_10(counter, key):
+    L = lib()
+    L.wco_philox4x32_10.argtypes = [C.POINTER(C.c_uint32), C.c_uint32, C.c_uint32]
+    c = (C.c_uint32 * 4)(*counter)
+    L.wco_philox4x32_10(c, key[0], key[1])
+    return list(c)
+
+
+class TrajBatch:
+    def __init__(self, cfg, B):
+        L = lib()
+        L.wco_traj_create.argtypes = [C.POINTER(TrajConfig), C.c_int]; L.wco_traj_create.restype = C.c_void_p
+        L.wco_traj_free.argtypes = [C.c_void_p]
+        L.wco_traj_set_gait.argtypes = [C.c_void_p] + [C.c_void_p] * 5
+        L.wco_traj_dcm.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.wco_traj_measured_dcm.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_uint64, C.c_void_p]
+        L.wco_traj_feet.argtypes = [C.c_void_p, C.c_int, C.POINTER(TrajFeet)]
+        self.L, self.cfg, self.B = L, cfg, B
+        self.h = L.wco_traj_create(C.byref(cfg), B)
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.L.wco_traj_free(self.h); self.h = None
+        except Exception:
+            pass
+
+    def set_gait(self, step_len, phase=None, dtheta=None, theta0=None, first_left=None):
+        p = lambda a, dt: None if a is None else np.ascontiguousarray(a, dtype=dt)
+        arrs = [p(phase, np.int32), p(step_len, np.float64), p(dtheta, np.float64), p(theta0, np.float64), p(first_left, np.uint8)]
+        self.L.wco_traj_set_gait(self.h, *[None if a is None else a.ctypes.data for a in arrs])
+
+    def dcm(self, first_sample, n_samples):
+        pos = np.zeros((2 * n_samples, self.B)); vel = np.zeros((2 * n_samples, self.B))
+        self.L.wco_traj_dcm(self.h, first_sample, n_samples, pos.ctypes.data, vel.ctypes.data)
+        return pos, vel
+
+    def measured_dcm(self, tick, sigma, seed):
+        out = np.zeros((2, self.B))
+        self.L.wco_traj_measured_dcm(self.h, tick, sigma, seed, out.ctypes.data)
+        return out
+
+    def feet(self, tick):
+        B = self.B
+        o = dict(lf_H=np.zeros((12, B)), rf_H=np.zeros((12, B)), lf_twist=np.zeros((6, B)), rf_twist=np.zeros((6, B)),
+                 l_contact=np.zeros(B, np.uint8), r_contact=np.zeros(B, np.uint8), left_is_fixed=np.zeros(B, np.uint8),
+                 com_height=np.zeros(B), com_height_vel=np.zeros(B))
+        f = TrajFeet(**{k: v.ctypes.data for k, v in o.items()})
+        self.L.wco_traj_feet(self.h, tick, C.byref(f))
+        return o

@@ -104,6 +104,17 @@ void wco_evaluate_dcm(int B, double omega, const double* com, const double* com_
 void wco_evaluate_zmp(int B, const double* lw, const double* rw, const double* lf_H, const double* rf_H, double* zmp, int* ok);
 void wco_log_pack(int B, const wc_log_inputs* in, double* out);
 
+/* ---- rank 3: synthetic producer of the path's inputs (CPU twin of wc_traj_*) ---- */
+typedef struct wco_traj wco_traj;
+wco_traj* wco_traj_create(const wc_traj_config* cfg, int B);
+void wco_traj_free(wco_traj* g);
+void wco_traj_set_gait(wco_traj* g, const int32_t* phase, const double* step_len, const double* dtheta, const double* theta0,
+                       const uint8_t* first_left);
+void wco_traj_dcm(const wco_traj* g, int first_sample, int n_samples, double* pos_out, double* vel_out);
+void wco_traj_measured_dcm(const wco_traj* g, int tick, double sigma, uint64_t seed, double* out);
+void wco_traj_feet(const wco_traj* g, int tick, const wc_traj_feet* out);
+void wco_philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1);
+
 #ifdef __cplusplus
 }
 #endif

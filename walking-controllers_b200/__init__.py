@@ -91,6 +91,18 @@ LOG_NAMES = ("dcm_x dcm_y dcm_des_x dcm_des_y dcm_des_dx dcm_des_dy zmp_x zmp_y 
              "rf_err_y rf_err_z rf_err_roll rf_err_pitch rf_err_yaw").split()
 
 
+class TrajConfig(C.Structure):
+    _fields_ = [("step_ticks", C.c_int32), ("ds_ticks", C.c_int32), ("n_steps", C.c_int32), ("reserved", C.c_int32),
+                ("sampling_time", C.c_double), ("com_height", C.c_double), ("gravity", C.c_double),
+                ("nominal_width", C.c_double), ("step_height", C.c_double), ("zmp_delta", C.c_double * 2)]
+
+
+class TrajFeet(C.Structure):
+    _fields_ = [("lf_H", C.c_void_p), ("rf_H", C.c_void_p), ("lf_twist", C.c_void_p), ("rf_twist", C.c_void_p),
+                ("l_contact", C.c_void_p), ("r_contact", C.c_void_p), ("left_is_fixed", C.c_void_p),
+                ("com_height", C.c_void_p), ("com_height_vel", C.c_void_p)]
+
+
 class LogInputs(C.Structure):
     _fields_ = [(k, C.POINTER(C.c_double)) for k in LOG_FIELDS]
 
@@ -163,6 +175,15 @@ def lib():
     L.wc_glue_com_reference_dev.argtypes = [_VP] + [_VP] * 10 + [_VP]; L.wc_glue_com_reference_dev.restype = i32
     L.wc_glue_integrate_joints_dev.argtypes = [_VP, _VP, _VP, _VP]; L.wc_glue_integrate_joints_dev.restype = i32
     L.wc_glue_launch_count.argtypes = [_VP]; L.wc_glue_launch_count.restype = i64
+    L.wc_traj_default_config.argtypes = [C.POINTER(TrajConfig), i32, i32]
+    L.wc_traj_create.argtypes = [C.POINTER(TrajConfig), i32, i32, C.POINTER(_VP)]; L.wc_traj_create.restype = i32
+    L.wc_traj_destroy.argtypes = [_VP]
+    L.wc_traj_set_gait_dev.argtypes = [_VP] * 7; L.wc_traj_set_gait_dev.restype = i32
+    L.wc_traj_dcm_dev.argtypes = [_VP, i32, i32, _VP, _VP, _VP]; L.wc_traj_dcm_dev.restype = i32
+    L.wc_traj_measured_dcm_dev.argtypes = [_VP, i32, C.c_double, C.c_uint64, _VP, _VP]; L.wc_traj_measured_dcm_dev.restype = i32
+    L.wc_traj_feet_dev.argtypes = [_VP, i32, C.POINTER(TrajFeet), _VP]; L.wc_traj_feet_dev.restype = i32
+    L.wc_traj_generate_host.argtypes = [_VP] * 6 + [i32, i32] + [_VP] * 11; L.wc_traj_generate_host.restype = i32
+    L.wc_traj_launch_count.argtypes = [_VP]; L.wc_traj_launch_count.restype = i64
     L.wc_glue_reactive_dcm_dev.argtypes = [_VP, C.c_double] + [_VP] * 6; L.wc_glue_reactive_dcm_dev.restype = i32
     L.wc_glue_reactive_dcm_host.argtypes = [_VP, C.c_double] + [_VP] * 5; L.wc_glue_reactive_dcm_host.restype = i32
     L.wc_glue_evaluate_dcm_dev.argtypes = [_VP] * 5; L.wc_glue_evaluate_dcm_dev.restype = i32
@@ -543,6 +564,80 @@ class GlueBatch:
     @property
     def launches(self):
         return lib().wc_glue_launch_count(self.h)
+
+
+def traj_default_config(n_ticks, horizon):
+    cfg = TrajConfig()
+    lib().wc_traj_default_config(C.byref(cfg), n_ticks, horizon)
+    return cfg
+
+
+class TrajBatch:
+    """On-device producer of the path's per-tick inputs for B periodic gaits (torch CUDA tensors,
+    field-major SoA): DCM reference window / velocity, measured DCM, feet poses / twists / contacts, CoM height."""
+
+    def __init__(self, cfg, B, device=0):
+        self.cfg, self.B, self.device = cfg, B, device
+        h = _VP()
+        _check(lib().wc_traj_create(C.byref(cfg), B, device, C.byref(h)), "wc_traj_create")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().wc_traj_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @staticmethod
+    def _stream(stream):
+        import torch
+        return (stream or torch.cuda.current_stream()).cuda_stream
+
+    def set_gait(self, step_len, phase=None, dtheta=None, theta0=None, first_left=None, stream=None):
+        """step_len [B] f64; phase [B] int32; dtheta, theta0 [B] f64; first_left [B] uint8 (device tensors)"""
+        self._keep = (step_len, phase, dtheta, theta0, first_left)
+        _check(lib().wc_traj_set_gait_dev(self.h, _ptr(phase), _ptr(step_len), _ptr(dtheta), _ptr(theta0), _ptr(first_left),
+                                          self._stream(stream)), "wc_traj_set_gait_dev")
+
+    def dcm(self, first_sample, n_samples, pos=None, vel=None, want_vel=True, stream=None):
+        import torch
+        dev = torch.device("cuda", self.device)
+        if pos is None:
+            pos = torch.empty(2 * n_samples, self.B, dtype=torch.float64, device=dev)
+        if vel is None and want_vel:
+            vel = torch.empty(2 * n_samples, self.B, dtype=torch.float64, device=dev)
+        _check(lib().wc_traj_dcm_dev(self.h, first_sample, n_samples, _ptr(pos), _ptr(vel), self._stream(stream)), "wc_traj_dcm_dev")
+        return pos, vel
+
+    def measured_dcm(self, tick, sigma, seed, out=None, stream=None):
+        import torch
+        if out is None:
+            out = torch.empty(2, self.B, dtype=torch.float64, device=torch.device("cuda", self.device))
+        _check(lib().wc_traj_measured_dcm_dev(self.h, tick, sigma, seed, _ptr(out), self._stream(stream)), "wc_traj_measured_dcm_dev")
+        return out
+
+    def feet(self, tick, out=None, stream=None):
+        import torch
+        dev = torch.device("cuda", self.device)
+        if out is None:
+            f64, u8, B = torch.float64, torch.uint8, self.B
+            out = dict(lf_H=torch.empty(12, B, dtype=f64, device=dev), rf_H=torch.empty(12, B, dtype=f64, device=dev),
+                       lf_twist=torch.empty(6, B, dtype=f64, device=dev), rf_twist=torch.empty(6, B, dtype=f64, device=dev),
+                       l_contact=torch.empty(B, dtype=u8, device=dev), r_contact=torch.empty(B, dtype=u8, device=dev),
+                       left_is_fixed=torch.empty(B, dtype=u8, device=dev), com_height=torch.empty(B, dtype=f64, device=dev),
+                       com_height_vel=torch.empty(B, dtype=f64, device=dev))
+        f = TrajFeet(**{k: _ptr(out.get(k)) for k, _ in TrajFeet._fields_})
+        _check(lib().wc_traj_feet_dev(self.h, tick, C.byref(f), self._stream(stream)), "wc_traj_feet_dev")
+        return out
+
+    @property
+    def launches(self):
+        return lib().wc_traj_launch_count(self.h)
 
 
 def measure_fp64_peak(device=0):

@@ -167,3 +167,19 @@ void wc_glue_default_config(wc_glue_config* c)
     c->k_zmp = 3.0;
     c->k_com = 9.0;
 }
+
+/* iCubGazeboV2_5 plannerParams.ini: nominalDuration 0.9, switchOverSwingRatio 0.7 (double support = 0.7 / 1.7 of a
+ * step = 37 ticks), nominalWidth 0.16, stepHeight 0.025, left/rightZMPDelta (0.03, -/+0.005); dcmWalkingCoordinator.ini
+ * sampling_time 0.01, com_height 0.53.  Eight look-ahead steps truncate the backward DCM recursion at e^{-omega 7.2}. */
+void wc_traj_default_config(wc_traj_config* c, int32_t n_ticks, int32_t horizon)
+{
+    if (!c) return;
+    c->step_ticks = 90; c->ds_ticks = 37; c->reserved = 0;
+    c->n_steps = (n_ticks + horizon + 90) / 90 + 8 + 3;
+    c->sampling_time = 0.01;
+    c->com_height = 0.53;
+    c->gravity = 9.81;
+    c->nominal_width = 0.16;
+    c->step_height = 0.025;
+    c->zmp_delta[0] = 0.03; c->zmp_delta[1] = 0.005;
+}

@@ -14,6 +14,7 @@
 #include "WalkingDCMModelPredictiveController.hpp"
 #include "WalkingDCMReactiveController.hpp"
 #include "WalkingLogger.hpp"
+#include "TrajectoryGenerator.hpp"
 #include "WalkingForwardKinematics.hpp"
 #include "WalkingQPInverseKinematics.hpp"
 
@@ -180,6 +181,44 @@ int main(int argc, char** argv)
         while (std::getline(f, line)) rows++;
         if (rows != 20) { std::fprintf(stderr, "logger: %d rows\n", rows); failures++; }
     }
+    // ======== TrajectoryGenerator stand-in (periodic gait on the device) against the CPU twin
+    double worst_traj = 0.0;
+    {
+        yarp::os::Searchable plCfg;
+        plCfg.put("sampling_time", dT); plCfg.put("plannerHorizon", 3.0); plCfg.put("nominalDuration", 0.9); plCfg.put("switchOverSwingRatio", 0.7);
+        plCfg.put("nominalWidth", 0.16); plCfg.put("stepHeight", 0.025); plCfg.put("com_height", 0.53);
+        plCfg.put("leftZMPDelta", std::vector<double>{0.03, -0.005}); plCfg.put("rightZMPDelta", std::vector<double>{0.03, 0.005});
+        TrajectoryGenerator gen;
+        std::vector<iDynTree::Vector2> dcmPos;
+        if (gen.getDCMPositionTrajectory(dcmPos)) { std::fprintf(stderr, "trajectory: getter before generation\n"); failures++; }
+        if (!gen.initialize(plCfg)) { std::fprintf(stderr, "trajectory: initialize failed\n"); failures++; }
+        gen.setGait(0.12, 0.05, 0.3);
+        std::vector<iDynTree::Transform> lT, rT; std::vector<bool> lC, rC, lFix; std::vector<double> comH;
+        if (!gen.generateFirstTrajectories() || !gen.getDCMPositionTrajectory(dcmPos) || !gen.getFeetTrajectories(lT, rT) ||
+            !gen.getFeetStandingPeriods(lC, rC) || !gen.getWhenUseLeftAsFixed(lFix) || !gen.getCoMHeightTrajectory(comH)) {
+            std::fprintf(stderr, "trajectory: generation failed\n"); failures++;
+        } else {
+            wc_traj_config tc; wc_traj_default_config(&tc, 300, 0);
+            wco_traj* tw = wco_traj_create(&tc, 1);
+            const int32_t ph = 0; const double L = 0.12, dth = 0.05, th0 = 0.3; const uint8_t fl = 0;
+            wco_traj_set_gait(tw, &ph, &L, &dth, &th0, &fl);
+            std::vector<double> pos(2 * 300);
+            wco_traj_dcm(tw, 0, 300, pos.data(), nullptr);
+            if (dcmPos.size() != 300 || lT.size() != 300) { std::fprintf(stderr, "trajectory: %zu samples\n", dcmPos.size()); failures++; }
+            for (size_t s = 0; s < dcmPos.size() && s < 300; s++) {
+                for (int a = 0; a < 2; a++) worst_traj = std::fmax(worst_traj, std::fabs(dcmPos[s](a) - pos[2 * s + a]));
+                double lf[12], rf[12], got[12]; uint8_t lc, rc, lfix;
+                wc_traj_feet f = {lf, rf, nullptr, nullptr, &lc, &rc, &lfix, nullptr, nullptr};
+                wco_traj_feet(tw, (int)s, &f);
+                lT[s].toH12(got);
+                for (int e = 0; e < 12; e++) worst_traj = std::fmax(worst_traj, std::fabs(got[e] - lf[e]));
+                if (lC[s] != (lc != 0) || rC[s] != (rc != 0) || lFix[s] != (lfix != 0)) { std::fprintf(stderr, "trajectory: flags at %zu\n", s); failures++; break; }
+            }
+            wco_traj_free(tw);
+        }
+    }
+    std::printf("trajectory generator: worst abs err %.3e\n", worst_traj);
+    if (worst_traj > 1e-12) failures++;
     wco_mpc_free(ompc);
     std::printf("reactive controller: worst abs err %.3e\n", worst_reactive);
     if (worst_reactive > 1e-13) failures++;
