@@ -358,6 +358,25 @@ wc_status wc_ik_solve_with_jacobians_host(wc_ik* h,
                          double* dq, double* lf_err, double* rf_err,
                          int32_t* qp_status, int32_t* nwsr);
 
+/* ---- WalkingQPIK_osqp: the reference selects between its two WalkingQPIK subclasses at run time
+ * (`use_osqp`, WalkingModule.cpp:124-126, 721-740); so does the handle.  With WC_IK_SOLVER_OSQP every tick entry point
+ * (wc_ik_tick_*, wc_ik_solve_with_jacobians_*) builds the QP of WalkingQPInverseKinematics_osqp.cpp:135-347 (extra k_attFoot
+ * on the neck gradient, bare-twist bounds for a foot with zero desired twist, EMPTY velocity-limit rows) and solves it with
+ * the batched OSQP-equivalent ADMM; the OSQP workspace of every instance (scaled iterates, rho, Hessian pattern) persists
+ * between ticks as osqp-eigen's solver object does.  Outputs then mean: qp_status = OSQP status (WC_OSQP_*), nwsr = OSQP
+ * iterations.  settings NULL = OSQP defaults (what osqp-eigen leaves in place besides verbosity).  Switching solver or
+ * calling wc_ik_reset_solver drops the workspaces (a new WalkingQPIK_osqp object). */
+enum { WC_IK_SOLVER_QPOASES = 0, WC_IK_SOLVER_OSQP = 1 };
+wc_status wc_ik_set_solver(wc_ik* h, int32_t solver, const wc_osqp_settings* settings);
+wc_status wc_ik_reset_solver(wc_ik* h);
+/* Optional per-instance outputs of the osqp variant, device pointers [B] (NULL = not wanted), written by the next ticks:
+ * flags bit 0 = m_optimizerSolver->solve() false (non-convex), bit 1 = isSolutionFeasible false (:395-408; the
+ * reference's solve() returns false if any bit is set); setups = osqp_setup calls so far (first solve + every change of
+ * the Hessian's sparsity pattern, i.e. of the stance foot). */
+wc_status wc_ik_osqp_outputs_dev(wc_ik* h, int32_t* flags, int32_t* setups);
+/* the same two arrays of the last tick, copied to host pointers [B] (synchronises the device; either may be NULL) */
+wc_status wc_ik_osqp_info_host(wc_ik* h, int32_t* flags, int32_t* setups);
+
 int64_t wc_ik_launch_count(const wc_ik* h);
 wc_status wc_ik_enable_profiling(wc_ik* h, int32_t on);
 wc_status wc_ik_kernel_times_ms(wc_ik* h, double* ik_ms, int64_t* launches);

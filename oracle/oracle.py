@@ -506,3 +506,51 @@ class TrajBatch:
         f = TrajFeet(**{k: v.ctypes.data for k, v in o.items()})
         self.L.wco_traj_feet(self.h, tick, C.byref(f))
         return o
+
+
+# ---- rank 2: WalkingQPIK_osqp (persistent per-instance OSQP solvers) ----------------------------------------------
+IK_KEYS = ("q_meas", "q_lin", "base_H", "lf_H_des", "rf_H_des", "lf_twist", "rf_twist", "com_pos_des", "com_vel_des",
+           "com_meas", "neck_R_des")
+
+
+def ik_build_qp(cfg, variant, q_meas, lf_H, rf_H, neck_R, com_meas, J_lf, J_rf, J_neck, J_com, lf_H_des, rf_H_des, lf_twist,
+                rf_twist, com_pos_des, com_vel_des, neck_R_des):
+    """H, g, A, b of the QP-IK (variant 0 = qpOASES, 1 = osqp) for one instance"""
+    L = _bind_ik()
+    nV = cfg.n_dofs + 6; nC = 15 if cfg.use_com_as_constraint else 12
+    a = [_f64(v) for v in (q_meas, lf_H, rf_H, neck_R, com_meas, J_lf, J_rf, J_neck, J_com, lf_H_des, rf_H_des,
+                           lf_twist, rf_twist, com_pos_des, com_vel_des, neck_R_des)]
+    H = np.zeros((nV, nV)); g = np.zeros(nV); A = np.zeros((nC, nV)); b = np.zeros(nC)
+    L.wco_ik_build_qp.argtypes = [C.c_void_p, C.c_int] + [C.POINTER(C.c_double)] * 20
+    L.wco_ik_build_qp(C.byref(cfg), variant, *[_dp(x) for x in a], _dp(H), _dp(g), _dp(A), _dp(b))
+    return H, g, A, b
+
+
+class IkOsqpBatch:
+    def __init__(self, cfg, model, B, settings=None):
+        L = _bind_ik()
+        dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+        L.wco_ikosqp_batch_create.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]; L.wco_ikosqp_batch_create.restype = C.c_void_p
+        L.wco_ikosqp_batch_free.argtypes = [C.c_void_p]
+        L.wco_ikosqp_batch_tick.argtypes = [C.c_void_p, dp, dp, dp, C.POINTER(C.c_ubyte)] + [dp] * 8 + [dp] * 3 + [ip] * 4
+        self.L, self.cfg, self.B = L, cfg, B
+        self.h = L.wco_ikosqp_batch_create(C.byref(cfg), None if settings is None else C.byref(settings), C.byref(model), B)
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.L.wco_ikosqp_batch_free(self.h); self.h = None
+        except Exception:
+            pass
+
+    def tick(self, inp):
+        B, nJ = self.B, self.cfg.n_dofs
+        a = {k: _f64(inp[k]) for k in IK_KEYS}
+        lif = _u8(inp["left_is_fixed"])
+        dq = np.zeros((nJ, B)); le = np.zeros((6, B)); re = np.zeros((6, B))
+        st = np.zeros(B, np.int32); it = np.zeros(B, np.int32); fl = np.zeros(B, np.int32); su = np.zeros(B, np.int32)
+        self.L.wco_ikosqp_batch_tick(self.h, _dp(a["q_meas"]), _dp(a["q_lin"]), _dp(a["base_H"]), _up(lif),
+                                     _dp(a["lf_H_des"]), _dp(a["rf_H_des"]), _dp(a["lf_twist"]), _dp(a["rf_twist"]),
+                                     _dp(a["com_pos_des"]), _dp(a["com_vel_des"]), _dp(a["com_meas"]), _dp(a["neck_R_des"]),
+                                     _dp(dq), _dp(le), _dp(re), _ip(st), _ip(it), _ip(fl), _ip(su))
+        return dict(dq=dq, lf_err=le, rf_err=re, status=st, iters=it, flags=fl, setups=su)

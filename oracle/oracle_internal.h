@@ -61,6 +61,11 @@ int wco_osqp_m(const wco_osqp* w);
 /* linear-system back end: 0 = KKT LDL^T (QDLDL, what OSQP does), 1 = dense Cholesky of the
  * reduced system P+sigma I+A' rho A (used to quantify the effect of the solve method). */
 void wco_osqp_set_linsys(wco_osqp* w, int kind);
+/* osqp_update_P / osqp_update_A with all values of the (unchanged) pattern, in CSC order */
+int wco_osqp_update_P(wco_osqp* w, const double* Px_new);
+int wco_osqp_update_A(wco_osqp* w, const double* Ax_new);
+void wco_osqp_get_iterate(const wco_osqp* w, double* x_scaled, double* y_scaled);
+void wco_osqp_warm_start(wco_osqp* w, const double* x, const double* y);
 
 #ifdef __cplusplus
 }

@@ -476,6 +476,69 @@ void wco_osqp_free(wco_osqp* w)
     free(w);
 }
 
+static void reset_info(wco_osqp* w);
+/* ------------------------------------------------------------------ matrix updates (osqp osqp.c: osqp_update_P / osqp_update_A)
+ * OSQP 0.6 unscales the WHOLE problem with the current D, E, c, overwrites the matrix values, and runs scale_data again
+ * (a fresh Ruiz equilibration from D = E = 1), then refactors and resets the info; the iterates x, z, y are left as they
+ * are (scaled with the previous D, E, c) and rho_vec is kept. */
+static void unscale_data(wco_osqp* w)
+{
+    const int n = w->n, m = w->m;
+    int i, j, p;
+    for (p = 0; p < w->P->nnz; p++) w->P->x[p] *= w->cinv;
+    for (j = 0; j < n; j++)
+        for (p = w->P->p[j]; p < w->P->p[j + 1]; p++) w->P->x[p] *= w->Dinv[w->P->i[p]];
+    for (j = 0; j < n; j++)
+        for (p = w->P->p[j]; p < w->P->p[j + 1]; p++) w->P->x[p] *= w->Dinv[j];
+    for (i = 0; i < n; i++) w->q[i] *= w->cinv;
+    for (i = 0; i < n; i++) w->q[i] *= w->Dinv[i];
+    for (j = 0; j < n; j++)
+        for (p = w->A->p[j]; p < w->A->p[j + 1]; p++) w->A->x[p] *= w->Einv[w->A->i[p]];
+    for (j = 0; j < n; j++)
+        for (p = w->A->p[j]; p < w->A->p[j + 1]; p++) w->A->x[p] *= w->Dinv[j];
+    for (i = 0; i < m; i++) { w->l[i] *= w->Einv[i]; w->u[i] *= w->Einv[i]; }
+}
+
+int wco_osqp_update_P(wco_osqp* w, const double* Px_new)
+{
+    if (w->s.scaling) unscale_data(w);
+    memcpy(w->P->x, Px_new, sizeof(double) * (size_t)w->P->nnz);
+    if (w->s.scaling) scale_data(w);
+    const int rc = linsys_factor(w, 1);
+    reset_info(w);
+    return rc;
+}
+
+int wco_osqp_update_A(wco_osqp* w, const double* Ax_new)
+{
+    if (w->s.scaling) unscale_data(w);
+    memcpy(w->A->x, Ax_new, sizeof(double) * (size_t)w->A->nnz);
+    if (w->s.scaling) scale_data(w);
+    const int rc = linsys_factor(w, 1);
+    reset_info(w);
+    return rc;
+}
+
+/* the (scaled) iterates of the workspace, as OsqpEigen::Solver::getPrimalVariable / getDualVariable map them */
+void wco_osqp_get_iterate(const wco_osqp* w, double* x, double* y)
+{
+    memcpy(x, w->x, sizeof(double) * (size_t)w->n);
+    memcpy(y, w->y, sizeof(double) * (size_t)w->m);
+}
+
+/* osqp_warm_start: copy, scale with the CURRENT D, E, c, z = A x */
+void wco_osqp_warm_start(wco_osqp* w, const double* x, const double* y)
+{
+    memcpy(w->x, x, sizeof(double) * (size_t)w->n);
+    memcpy(w->y, y, sizeof(double) * (size_t)w->m);
+    if (w->s.scaling) {
+        for (int i = 0; i < w->n; i++) w->x[i] *= w->Dinv[i];
+        for (int i = 0; i < w->m; i++) w->y[i] *= w->Einv[i];
+        for (int i = 0; i < w->m; i++) w->y[i] *= w->c;
+    }
+    mat_vec(w->A, w->x, w->z, 0);
+}
+
 /* ------------------------------------------------------------------ updates (osqp osqp.c) */
 static void reset_info(wco_osqp* w)
 {

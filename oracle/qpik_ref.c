@@ -263,18 +263,18 @@ static void rot_error(const double* R, const double* Rdes, double* e)
     e[2] = 0.5 * (M[3] - M[1]);
 }
 
-/* One QP-IK solve with caller-supplied kinematics (all row-major, single instance). */
-int wco_ik_solve(const wc_ik_config* cfg,
-                 const double* q_meas, const double* lf_H, const double* rf_H, const double* neck_R, const double* com_meas,
-                 const double* J_lf, const double* J_rf, const double* J_neck6, const double* J_com,
-                 const double* lf_H_des, const double* rf_H_des, const double* lf_twist, const double* rf_twist,
-                 const double* com_pos_des, const double* com_vel_des, const double* neck_R_des,
-                 double* dq, double* lf_err, double* rf_err, int* nwsr,
-                 double* H_out, double* g_out, double* A_out, double* b_out, double* v_out)
+/* H, g, A (nC x nV, task rows), b of the QP-IK from caller-supplied kinematics (all row-major, single instance).
+ * variant 0 = WalkingQPIK_qpOASES; variant 1 = WalkingQPIK_osqp, which differs in two places of the build
+ * (SURVEY quirk 10): the neck term of the gradient carries an extra k_attFoot factor (…_osqp.cpp:183,193) and a foot whose
+ * desired twist has twist(0) == twist(1) == 0 gets the bare twist as bound, without the pose correction (:286-306). */
+void wco_ik_build_qp(const wc_ik_config* cfg, int variant,
+                     const double* q_meas, const double* lf_H, const double* rf_H, const double* neck_R, const double* com_meas,
+                     const double* J_lf, const double* J_rf, const double* J_neck6, const double* J_com,
+                     const double* lf_H_des, const double* rf_H_des, const double* lf_twist, const double* rf_twist,
+                     const double* com_pos_des, const double* com_vel_des, const double* neck_R_des,
+                     double* H, double* g, double* A, double* b)
 {
     const int nJ = cfg->n_dofs, nV = nJ + 6;
-    const int nC = cfg->use_com_as_constraint ? 15 : 12;
-    double H[QP_MAXN * QP_MAXN], g[QP_MAXN], A[15 * QP_MAXN], b[15], lb[QP_MAXN], ub[QP_MAXN], v[QP_MAXN];
     const double* Jn = J_neck6 + 3 * nV; /* setNeckJacobian keeps rows 3..5 (QPIK.cpp:214-215) */
     int i, j, r, c;
     /* ---- setHessianMatrix (…_qpOASES.cpp:135-153) */
@@ -301,9 +301,10 @@ int wco_ik_solve(const wc_ik_config* cfg,
     double Rdes[9], en[3], We[3];
     mat3_mul(neck_R_des, cfg->additional_rotation, Rdes); /* setDesiredNeckOrientation (QPIK.cpp:143-146) */
     rot_error(neck_R, Rdes, en);
+    const double kn = variant == 1 ? cfg->k_att_foot : 1.0;
     for (r = 0; r < 3; r++)
-        We[r] = cfg->neck_weight[3 * r] * (-cfg->k_neck * en[0]) + cfg->neck_weight[3 * r + 1] * (-cfg->k_neck * en[1]) +
-                cfg->neck_weight[3 * r + 2] * (-cfg->k_neck * en[2]);
+        We[r] = cfg->neck_weight[3 * r] * (kn * (-cfg->k_neck * en[0])) + cfg->neck_weight[3 * r + 1] * (kn * (-cfg->k_neck * en[1])) +
+                cfg->neck_weight[3 * r + 2] * (kn * (-cfg->k_neck * en[2]));
     for (i = 0; i < nV; i++) {
         double s = -(Jn[i] * We[0] + Jn[nV + i] * We[1] + Jn[2 * nV + i] * We[2]);
         if (i >= 6) s -= cfg->joint_reg_weight[i - 6] * (cfg->joint_reg_gain[i - 6] * (cfg->joint_reg_rad[i - 6] - q_meas[i - 6]));
@@ -328,14 +329,32 @@ int wco_ik_solve(const wc_ik_config* cfg,
             double R[9], Rd[9], e[3];
             for (r = 0; r < 3; r++) for (c = 0; c < 3; c++) { R[3 * r + c] = Hs[f][4 * r + c]; Rd[3 * r + c] = Hd[f][4 * r + c]; }
             rot_error(R, Rd, e);
+            const int bare = variant == 1 && tw[f][0] == tw[f][1] && tw[f][0] == 0.0;
             for (r = 0; r < 3; r++) {
-                b[6 * f + r] = tw[f][r] - cfg->k_pos_foot * (Hs[f][4 * r + 3] - Hd[f][4 * r + 3]);
-                b[6 * f + 3 + r] = tw[f][3 + r] - cfg->k_att_foot * e[r];
+                b[6 * f + r] = bare ? tw[f][r] : tw[f][r] - cfg->k_pos_foot * (Hs[f][4 * r + 3] - Hd[f][4 * r + 3]);
+                b[6 * f + 3 + r] = bare ? tw[f][3 + r] : tw[f][3 + r] - cfg->k_att_foot * e[r];
             }
         }
         if (cfg->use_com_as_constraint)
             for (r = 0; r < 3; r++) b[12 + r] = com_vel_des[r] - cfg->k_pos_com * (com_meas[r] - com_pos_des[r]);
     }
+}
+
+/* One QP-IK solve with caller-supplied kinematics (all row-major, single instance). */
+int wco_ik_solve(const wc_ik_config* cfg,
+                 const double* q_meas, const double* lf_H, const double* rf_H, const double* neck_R, const double* com_meas,
+                 const double* J_lf, const double* J_rf, const double* J_neck6, const double* J_com,
+                 const double* lf_H_des, const double* rf_H_des, const double* lf_twist, const double* rf_twist,
+                 const double* com_pos_des, const double* com_vel_des, const double* neck_R_des,
+                 double* dq, double* lf_err, double* rf_err, int* nwsr,
+                 double* H_out, double* g_out, double* A_out, double* b_out, double* v_out)
+{
+    const int nJ = cfg->n_dofs, nV = nJ + 6;
+    const int nC = cfg->use_com_as_constraint ? 15 : 12;
+    double H[QP_MAXN * QP_MAXN], g[QP_MAXN], A[15 * QP_MAXN], b[15], lb[QP_MAXN], ub[QP_MAXN], v[QP_MAXN];
+    int i, r, c;
+    wco_ik_build_qp(cfg, 0, q_meas, lf_H, rf_H, neck_R, com_meas, J_lf, J_rf, J_neck6, J_com, lf_H_des, rf_H_des, lf_twist, rf_twist,
+                    com_pos_des, com_vel_des, neck_R_des, H, g, A, b);
     /* ---- setVelocityBounds (:23-51) */
     for (i = 0; i < 6; i++) { lb[i] = -DBL_MAX; ub[i] = DBL_MAX; }
     for (i = 0; i < nJ; i++) { lb[6 + i] = cfg->min_vel[i]; ub[6 + i] = cfg->max_vel[i]; }

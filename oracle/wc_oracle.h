@@ -104,6 +104,32 @@ void wco_evaluate_dcm(int B, double omega, const double* com, const double* com_
 void wco_evaluate_zmp(int B, const double* lw, const double* rw, const double* lf_H, const double* rf_H, double* zmp, int* ok);
 void wco_log_pack(int B, const wc_log_inputs* in, double* out);
 
+/* ---- rank 2: WalkingQPIK_osqp (qpik_osqp_ref.c) ---- */
+void wco_ik_build_qp(const wc_ik_config* cfg, int variant,
+                     const double* q_meas, const double* lf_H, const double* rf_H, const double* neck_R, const double* com_meas,
+                     const double* J_lf, const double* J_rf, const double* J_neck6, const double* J_com,
+                     const double* lf_H_des, const double* rf_H_des, const double* lf_twist, const double* rf_twist,
+                     const double* com_pos_des, const double* com_vel_des, const double* neck_R_des,
+                     double* H, double* g, double* A, double* b);
+typedef struct wco_ikosqp wco_ikosqp;
+wco_ikosqp* wco_ikosqp_create(const wc_ik_config* cfg, const wc_osqp_settings* st);
+void wco_ikosqp_free(wco_ikosqp* h);
+int wco_ikosqp_setups(const wco_ikosqp* h);
+int wco_ikosqp_solve(wco_ikosqp* h,
+                     const double* q_meas, const double* lf_H, const double* rf_H, const double* neck_R, const double* com_meas,
+                     const double* J_lf, const double* J_rf, const double* J_neck6, const double* J_com,
+                     const double* lf_H_des, const double* rf_H_des, const double* lf_twist, const double* rf_twist,
+                     const double* com_pos_des, const double* com_vel_des, const double* neck_R_des,
+                     double* dq, double* lf_err, double* rf_err, int* osqp_status, int* iters, int* flags);
+typedef struct wco_ikosqp_batch wco_ikosqp_batch;
+wco_ikosqp_batch* wco_ikosqp_batch_create(const wc_ik_config* cfg, const wc_osqp_settings* st, const wc_model* model, int B);
+void wco_ikosqp_batch_free(wco_ikosqp_batch* b);
+void wco_ikosqp_batch_tick(wco_ikosqp_batch* b, const double* q_meas, const double* q_lin, const double* base_H,
+                           const unsigned char* left_is_fixed, const double* lf_H_des, const double* rf_H_des,
+                           const double* lf_twist, const double* rf_twist, const double* com_pos_des, const double* com_vel_des,
+                           const double* com_meas, const double* neck_R_des,
+                           double* dq, double* lf_err, double* rf_err, int* status, int* iters, int* flags, int* setups);
+
 /* ---- rank 3: synthetic producer of the path's inputs (CPU twin of wc_traj_*) ---- */
 typedef struct wco_traj wco_traj;
 wco_traj* wco_traj_create(const wc_traj_config* cfg, int B);

@@ -205,6 +205,10 @@ def lib():
         L.wc_ik_solve_with_jacobians_dev.argtypes = [_VP] + [_VP] * 21 + [_VP]
         L.wc_ik_solve_with_jacobians_dev.restype = i32
         L.wc_ik_launch_count.argtypes = [_VP]; L.wc_ik_launch_count.restype = i64
+        L.wc_ik_set_solver.argtypes = [_VP, i32, C.POINTER(OsqpSettings)]; L.wc_ik_set_solver.restype = i32
+        L.wc_ik_reset_solver.argtypes = [_VP]; L.wc_ik_reset_solver.restype = i32
+        L.wc_ik_osqp_outputs_dev.argtypes = [_VP, _VP, _VP]; L.wc_ik_osqp_outputs_dev.restype = i32
+        L.wc_ik_osqp_info_host.argtypes = [_VP, _VP, _VP]; L.wc_ik_osqp_info_host.restype = i32
         L.wc_ik_enable_profiling.argtypes = [_VP, i32]; L.wc_ik_enable_profiling.restype = i32
         L.wc_ik_kernel_times_ms.argtypes = [_VP, C.POINTER(C.c_double), C.POINTER(i64)]
         L.wc_ik_kernel_times_ms.restype = i32
@@ -351,6 +355,9 @@ IK_INPUT_KEYS = ("q_meas", "q_lin", "base_H", "left_is_fixed", "lf_H_des", "rf_H
                  "com_pos_des", "com_vel_des", "com_meas", "neck_R_des")
 
 
+SOLVER_QPOASES, SOLVER_OSQP = 0, 1
+
+
 class IkBatch:
     """Batched FK + QP-IK handle (mirrors WalkingFK + WalkingQPIK_qpOASES for B instances)."""
 
@@ -373,6 +380,19 @@ class IkBatch:
 
     def set_gains(self, k_pos_foot, k_att_foot):
         _check(lib().wc_ik_set_gains_host(self.h, _ptr(k_pos_foot), _ptr(k_att_foot)), "wc_ik_set_gains_host")
+
+    def set_solver(self, solver, settings=None):
+        """SOLVER_QPOASES (WalkingQPIK_qpOASES, default) or SOLVER_OSQP (WalkingQPIK_osqp, `use_osqp`): with the latter the
+        tick outputs mean status = OSQP status, nwsr = OSQP iterations, and the OSQP workspaces persist between ticks."""
+        _check(lib().wc_ik_set_solver(self.h, solver, None if settings is None else C.byref(settings)), "wc_ik_set_solver")
+
+    def reset_solver(self):
+        _check(lib().wc_ik_reset_solver(self.h), "wc_ik_reset_solver")
+
+    def osqp_outputs(self, flags=None, setups=None):
+        """device int32 [B] tensors written by the following ticks of the osqp variant (None = not wanted)"""
+        self._osqp_keep = (flags, setups)
+        _check(lib().wc_ik_osqp_outputs_dev(self.h, _ptr(flags), _ptr(setups)), "wc_ik_osqp_outputs_dev")
 
     def _outs(self, dev):
         import torch

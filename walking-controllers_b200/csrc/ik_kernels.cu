@@ -258,7 +258,9 @@ __device__ __forceinline__ void fk_stage(const IkModelDev& M, const IkTickIO& io
 
 // ---- K3b: the vectors of the QP: equality right-hand side b (setBounds), gradient entry g_j of this
 // lane's variable (setGradientVector), regularisation weight Lambda_jj (WalkingQPIK::initializeMatrices).
-template <bool COMC>
+// VARIANT 1 = WalkingQPIK_osqp: the neck term of the gradient carries an extra k_attFoot factor (_osqp.cpp:183,193) and a
+// foot whose desired twist has twist(0) == twist(1) == 0 is constrained to the bare twist (_osqp.cpp:286-306).
+template <bool COMC, int VARIANT = 0>
 __device__ __forceinline__ void qp_vectors(const IkDev& d, const IkTickIO& io, int i, size_t B, int ig, int lane,
                                            const double* lfH, const double* rfH, const double* nR,
                                            const double* colN, const double* colC, double* bvec, double& gj, double& lam)
@@ -285,10 +287,11 @@ __device__ __forceinline__ void qp_vectors(const IkDev& d, const IkTickIO& io, i
 #pragma unroll
             for (int c = 0; c < 3; c++) { R[3 * r + c] = Hc[4 * r + c]; Rd[3 * r + c] = Hd[4 * r + c]; }
         rot_error(R, Rd, e);
+        const bool bare = VARIANT == 1 && tw[0] == tw[1] && tw[0] == 0.0;
 #pragma unroll
         for (int r = 0; r < 3; r++) {
-            bvec[6 * f + r] = tw[r] - kpos * (Hc[4 * r + 3] - Hd[4 * r + 3]);
-            bvec[6 * f + 3 + r] = tw[3 + r] - katt * e[r];
+            bvec[6 * f + r] = bare ? tw[r] : tw[r] - kpos * (Hc[4 * r + 3] - Hd[4 * r + 3]);
+            bvec[6 * f + 3 + r] = bare ? tw[3 + r] : tw[3 + r] - katt * e[r];
         }
     }
     double cv[3];
@@ -308,10 +311,11 @@ __device__ __forceinline__ void qp_vectors(const IkDev& d, const IkTickIO& io, i
     mat3_mul(nd, cfg.additional_rotation, Rdes); // setDesiredNeckOrientation (QPIK.cpp:143-146)
     rot_error(nR, Rdes, en);
     // W * (-k_neck e_n): with colN it gives this lane's neck term; also returned for the base elimination
+    const double kn = VARIANT == 1 ? katt : 1.0;
 #pragma unroll
     for (int r = 0; r < 3; r++)
-        We[r] = cfg.neck_weight[3 * r] * (-cfg.k_neck * en[0]) + cfg.neck_weight[3 * r + 1] * (-cfg.k_neck * en[1]) +
-                cfg.neck_weight[3 * r + 2] * (-cfg.k_neck * en[2]);
+        We[r] = cfg.neck_weight[3 * r] * (kn * (-cfg.k_neck * en[0])) + cfg.neck_weight[3 * r + 1] * (kn * (-cfg.k_neck * en[1])) +
+                cfg.neck_weight[3 * r + 2] * (kn * (-cfg.k_neck * en[2]));
     gj = -(colN[0] * We[0] + colN[1] * We[1] + colN[2] * We[2]);
     lam = 0.0;
     if (isjoint) {
@@ -1147,9 +1151,12 @@ __global__ void __launch_bounds__(kFastWarps * 32, 4) ik_fast_kernel(IkDev d, Ik
     }
 }
 
+#include "ik_osqp.inl"
+
 template <int NJ, bool COMC>
 cudaError_t launch_t(const IkDev& d, const IkTickIO& io, int mode, cudaStream_t s, cudaEvent_t mid)
 {
+    if (d.solver == WC_IK_SOLVER_OSQP && mode != IK_MODE_FK_ONLY) return launch_osqp_t<NJ, COMC>(d, io, mode, s);
     using LY = IkLayout<NJ, COMC>;
     const size_t smem = (size_t)LY::TOTAL * sizeof(double) * kWarpsPerBlock;
     cudaError_t e = cudaFuncSetAttribute(ik_kernel<NJ, COMC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -56,6 +56,15 @@ struct IkDev {
     // fused-tick fast path (ik_fast_kernel): instances handed over to the general kernel
     int32_t* slow_list;      // [B] or nullptr (fast path disabled)
     int32_t* slow_count;     // [1]
+    // WalkingQPIK_osqp (wc_ik_set_solver): OSQP settings and the persistent workspace of every instance, field-major
+    int solver;              // WC_IK_SOLVER_*
+    wc_osqp_settings osqp;
+    double* ox; double* oy; double* oz; // scaled iterates [NV][B], [M][B], [M][B]  (M = task rows + nJ velocity rows)
+    double* orho;            // [B]
+    uint32_t* omask;         // [NV][B] upper-triangular nonzero pattern of the Hessian of the live solver, column per word
+    uint8_t* oinit;          // [B] solver exists
+    int32_t* osetups;        // [B] number of osqp_setup calls so far
+    int32_t* oflags;         // [B]: bit 0 = solver error (non-convex), bit 1 = isSolutionFeasible failed
 };
 
 enum { IK_MODE_TICK = 0, IK_MODE_FK_ONLY = 1, IK_MODE_EXT_KIN = 2 };

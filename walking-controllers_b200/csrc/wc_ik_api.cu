@@ -21,6 +21,8 @@ struct wc_ik {
     int64_t launches;
     IkModelDev* model_dev;
     double* kpos; double* katt;
+    double* osqp_state; // one allocation behind d.ox .. d.osetups
+    int32_t* user_setups; int32_t* user_flags;
     HostPipe pipe; // double-buffered staging of the host-pointer tick
     int profiling;
     std::vector<cudaEvent_t> ev; // triples (start, after the fast kernel, end)
@@ -110,7 +112,7 @@ wc_status wc_ik_create(const wc_ik_config* cfg, const wc_model* model, int32_t B
     if (!build_model(model, &hm)) return WC_ERR_INVALID_ARG;
     wc_ik* h = new (std::nothrow) wc_ik();
     if (!h) return WC_ERR_ALLOC;
-    h->launches = 0; h->model_dev = nullptr; h->kpos = h->katt = nullptr;
+    h->launches = 0; h->model_dev = nullptr; h->kpos = h->katt = nullptr; h->osqp_state = nullptr; h->user_setups = nullptr; h->user_flags = nullptr;
     h->profiling = 0; h->ms_acc = 0; h->timed = 0; h->fast_ms_acc = 0; h->detail[0] = h->detail[1] = 0;
     std::memset(&h->d, 0, sizeof(h->d));
     h->device = device;
@@ -141,6 +143,7 @@ void wc_ik_destroy(wc_ik* h)
     if (h->d.slow_count) cudaFree(h->d.slow_count);
     if (h->kpos) cudaFree(h->kpos);
     if (h->katt) cudaFree(h->katt);
+    if (h->osqp_state) cudaFree(h->osqp_state);
     h->pipe.destroy();
     for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
     delete h;
@@ -162,6 +165,60 @@ wc_status wc_ik_set_gains_host(wc_ik* h, const double* k_pos_foot, const double*
     return WC_OK;
 }
 
+wc_status wc_ik_reset_solver(wc_ik* h)
+{
+    if (!h) return WC_ERR_INVALID_ARG;
+    if (!h->osqp_state) return WC_OK;
+    if (cudaSetDevice(h->device) != cudaSuccess) return WC_ERR_CUDA;
+    const size_t B = (size_t)h->d.B;
+    // oinit and osetups: no solver yet
+    if (cudaMemset(h->d.oinit, 0, B) != cudaSuccess || cudaMemset(h->d.osetups, 0, B * sizeof(int32_t)) != cudaSuccess) return WC_ERR_CUDA;
+    return WC_OK;
+}
+
+wc_status wc_ik_set_solver(wc_ik* h, int32_t solver, const wc_osqp_settings* settings)
+{
+    if (!h || (solver != WC_IK_SOLVER_QPOASES && solver != WC_IK_SOLVER_OSQP)) return WC_ERR_INVALID_ARG;
+    if (cudaSetDevice(h->device) != cudaSuccess) return WC_ERR_CUDA;
+    if (solver == WC_IK_SOLVER_OSQP) {
+        if (settings) h->d.osqp = *settings; else wc_osqp_default_settings(&h->d.osqp);
+        if (h->d.osqp.max_iter < 1 || h->d.osqp.scaling < 0 || h->d.osqp.check_termination < 0) return WC_ERR_INVALID_ARG;
+        if (!h->osqp_state) {
+            const size_t B = (size_t)h->d.B, nV = (size_t)h->d.nJ + 6, M = 15 + (size_t)h->d.nJ;
+            const size_t doubles = (nV + 2 * M + 1) * B;
+            const size_t bytes = doubles * sizeof(double) + nV * B * sizeof(uint32_t) + 2 * B * sizeof(int32_t) + align_up(B, 16);
+            if (cudaMalloc(&h->osqp_state, bytes) != cudaSuccess) return WC_ERR_ALLOC;
+            cudaMemset(h->osqp_state, 0, bytes);
+            h->d.ox = h->osqp_state; h->d.oy = h->d.ox + nV * B; h->d.oz = h->d.oy + M * B; h->d.orho = h->d.oz + M * B;
+            h->d.omask = reinterpret_cast<uint32_t*>(h->d.orho + B);
+            h->d.osetups = reinterpret_cast<int32_t*>(h->d.omask + nV * B);
+            h->d.oflags = h->d.osetups + B;
+            h->d.oinit = reinterpret_cast<uint8_t*>(h->d.oflags + B);
+        }
+    }
+    h->d.solver = solver;
+    return wc_ik_reset_solver(h);
+}
+
+wc_status wc_ik_osqp_outputs_dev(wc_ik* h, int32_t* flags, int32_t* setups)
+{
+    if (!h) return WC_ERR_INVALID_ARG;
+    h->user_flags = flags;
+    h->user_setups = setups;
+    return WC_OK;
+}
+
+wc_status wc_ik_osqp_info_host(wc_ik* h, int32_t* flags, int32_t* setups)
+{
+    if (!h || !h->osqp_state) return WC_ERR_STATE;
+    if (cudaSetDevice(h->device) != cudaSuccess) return WC_ERR_CUDA;
+    if (cudaDeviceSynchronize() != cudaSuccess) return WC_ERR_CUDA;
+    const size_t bytes = (size_t)h->d.B * sizeof(int32_t);
+    if (flags && cudaMemcpy(flags, h->d.oflags, bytes, cudaMemcpyDeviceToHost) != cudaSuccess) return WC_ERR_CUDA;
+    if (setups && cudaMemcpy(setups, h->d.osetups, bytes, cudaMemcpyDeviceToHost) != cudaSuccess) return WC_ERR_CUDA;
+    return WC_OK;
+}
+
 static wc_status launch_checked(wc_ik* h, const IkTickIO& io, int mode, cudaStream_t s, const char* who)
 {
     cudaEvent_t e0 = nullptr, em = nullptr, e1 = nullptr;
@@ -170,11 +227,16 @@ static wc_status launch_checked(wc_ik* h, const IkTickIO& io, int mode, cudaStre
         h->ev.push_back(e0); h->ev.push_back(em); h->ev.push_back(e1);
         cudaEventRecord(e0, s);
     }
-    const bool two = mode == IK_MODE_TICK && h->d.slow_list;
+    const bool osqp = h->d.solver == WC_IK_SOLVER_OSQP && mode != IK_MODE_FK_ONLY;
+    const bool two = mode == IK_MODE_TICK && h->d.slow_list && !osqp;
     if (h->profiling && !two) cudaEventRecord(em, s);
     cudaError_t e = launch_ik(h->d, io, mode, s, (h->profiling && two) ? em : nullptr);
     if (h->profiling) cudaEventRecord(e1, s);
-    h->launches += (mode == IK_MODE_TICK && h->d.slow_list) ? 2 : 1;
+    if (osqp && h->user_setups && e == cudaSuccess)
+        e = cudaMemcpyAsync(h->user_setups, h->d.osetups, (size_t)h->d.B * sizeof(int32_t), cudaMemcpyDeviceToDevice, s);
+    if (osqp && h->user_flags && e == cudaSuccess)
+        e = cudaMemcpyAsync(h->user_flags, h->d.oflags, (size_t)h->d.B * sizeof(int32_t), cudaMemcpyDeviceToDevice, s);
+    h->launches += two ? 2 : 1;
     if (e != cudaSuccess) {
         std::fprintf(stderr, "[%s] CUDA error: %s\n", who, cudaGetErrorString(e));
         return WC_ERR_CUDA;

@@ -77,4 +77,27 @@ public:
     int32_t workingSetRecalculations() const { return m_nwsr; }
 };
 
+// Drop-in for WalkingQPIK_osqp (modules/Walking_module/include/WalkingQPInverseKinematics_osqp.hpp): the same handle with
+// wc_ik_set_solver(WC_IK_SOLVER_OSQP); the OSQP workspace lives on the device between solve() calls as osqp-eigen's does.
+// solve() is false when OSQP reports an error or isSolutionFeasible fails (_osqp.cpp:349-393), NOT when OSQP merely stops
+// at max_iter: that is the reference's behaviour (it only tests m_optimizerSolver->solve()).
+class WalkingQPIK_osqp : public WalkingQPIK {
+    wc_ik* m_handle{nullptr};
+    wc_model m_model{};
+    std::vector<double> m_dq, m_lfErr, m_rfErr;
+    int32_t m_status{0}, m_iters{0}, m_flags{0}, m_setups{0};
+
+public:
+    ~WalkingQPIK_osqp() override;
+    bool initialize(const yarp::os::Searchable& config, const int& actuatedDOFs, const iDynTree::VectorDynSize& minJointsLimit,
+                    const iDynTree::VectorDynSize& maxJointsLimit) final;
+    bool solve() final;
+    bool getSolution(iDynTree::VectorDynSize& output) final;
+    bool getLeftFootError(iDynTree::VectorDynSize& output) final;
+    bool getRightFootError(iDynTree::VectorDynSize& output) final;
+    int32_t osqpStatus() const { return m_status; }
+    int32_t osqpIterations() const { return m_iters; }
+    int32_t solverSetups() const { return m_setups; }
+};
+
 #endif
