@@ -387,6 +387,53 @@ def run_ours(args, world, rank, local_rank):
     e2e_s = e.item()
     barrier()
 
+    # ---------------- SURVEY §8(f) rows built next to the headline path: device times of one tick at the same batch
+    # (outside the timed regions above; N = 1 only)
+    next_rows = None
+    if world == 1 and not args.no_extras:
+        def timed(fn, n_warm=3, n=10):
+            for k in range(n_warm):
+                fn(k)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for k in range(n):
+                fn(n_warm + k)
+            e1.record(); torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / n
+        ik2 = wc.IkBatch(icfg, model, B, device=local_rank)
+        ik2.set_solver(wc.SOLVER_OSQP)
+        o2 = {}
+        def f_osqp(k):
+            o2["o"] = ik2.tick(ik_in[k % IK_RING], out=o2.get("o"))
+        osqp_ms = timed(f_osqp)
+        osqp_it = o2["o"]["nwsr"].double().mean().item(); osqp_ok = (o2["o"]["status"] == 1).double().mean().item()
+        ik2.close()
+        tj = wc.TrajBatch(wc.traj_default_config(T, N), B, device=local_rank)
+        tj.set_gait(g.step_len, g.phase.to(torch.int32), g.dtheta, g.theta0, g.first_left.to(torch.uint8))
+        tb = {}
+        def f_traj(k):
+            tb["f"] = tj.feet(k, out=tb.get("f"))
+            tb["p"], _ = tj.dcm(k, N + 1, pos=tb.get("p"), want_vel=False)
+            tb["m"] = tj.measured_dcm(k, 0.002, 0x5EED, out=tb.get("m"))
+        traj_ms = timed(f_traj)
+        tj.close()
+        gl = wc.GlueBatch(wc.glue_default_config(), B, device=local_rank)
+        z2 = torch.zeros(2, B, dtype=torch.float64, device=dev); c3 = torch.zeros(3, B, dtype=torch.float64, device=dev)
+        gb = {}
+        def f_glue(k):
+            gb["c"] = gl.com_reference(z2, mo["zmp"], z2, c3, out=gb.get("c"))
+            gb["q"] = gl.integrate_joints(io_["dq"], out=gb.get("q"))
+            gb["r"] = gl.reactive_dcm(1.5, z2, z2, z2, out=gb.get("r"))
+        glue_ms = timed(f_glue)
+        gl.close()
+        next_rows = {"ik_osqp_tick_ms": osqp_ms, "ik_osqp_iters_mean": osqp_it, "ik_osqp_solved_frac": osqp_ok,
+                     "ik_osqp_ticks_per_s": B / (osqp_ms * 1e-3),
+                     "traj_producer_tick_ms": traj_ms, "glue_tick_ms": glue_ms,
+                     "note": "FK + WalkingQPIK_osqp tick (rank 2), on-device input producer: feet + DCM window + measured DCM "
+                             "(rank 3), LIPM / ZMP-CoM law + joint integrator + reactive DCM law (ranks 1, 4); B instances, device "
+                             "resident, CUDA events"}
+
     if rank == 0:
         hbm_peak, peak_src = peaks()
         fp64_peak = wc.measure_fp64_peak(local_rank)
@@ -441,6 +488,8 @@ def run_ours(args, world, rank, local_rank):
         }
         if gather_ms is not None:
             line["nccl_gather_ms"] = gather_ms
+        if next_rows is not None:
+            line["next_rows"] = next_rows
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline_leg(N)
         print(json.dumps(line), flush=True)
@@ -457,6 +506,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extras", action="store_true", help="skip the timings of the SURVEY 8(f) rows (next_rows)")
     ap.add_argument("--horizon", type=int, default=HORIZON, help="MPC horizon N (default: BASELINE configs[2], 25)")
     ap.add_argument("--batch", type=int, default=B_PER_GPU, help="instances per GPU (default 65536)")
     args = ap.parse_args()

@@ -14,6 +14,7 @@ $CMD > $OUT/plain_$TAG.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file $OUT/launches_$TAG.csv $CMD > $OUT/ncu1_$TAG.log 2>&1
 $CMD > $OUT/plain2_$TAG.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:"mpc_chain|mpc_prepare|ik_fast|ik_kernel" -s 86 -c 6 -f -o $OUT/prof_$TAG $CMD > $OUT/ncu2_$TAG.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"ik_osqp" -s 4 -c 1 -f -o $OUT/prof_osqp_$TAG $CMD > $OUT/ncu3_$TAG.log 2>&1
 echo done
 tail -c 1500 $OUT/pytest_gpu_$TAG.log
 cat $OUT/bench_$TAG.json | head -c 3000

@@ -90,8 +90,10 @@ void WalkingQPIK::setDesiredCoMPosition(const iDynTree::Position& p) { m_desired
 // ------------------------------------------------------------------------------------------ qpOASES variant
 WalkingQPIK_qpOASES::~WalkingQPIK_qpOASES() { wc_ik_destroy(m_handle); }
 
-bool WalkingQPIK_qpOASES::initialize(const yarp::os::Searchable& config, const int& actuatedDOFs,
-                                     const iDynTree::VectorDynSize& minJointsLimit, const iDynTree::VectorDynSize& maxJointsLimit)
+bool WalkingQPIK::initializeDevice(const yarp::os::Searchable& config, const int& actuatedDOFs,
+                                   const iDynTree::VectorDynSize& minJointsLimit, const iDynTree::VectorDynSize& maxJointsLimit,
+                                   int solver, wc_ik*& m_handle, wc_model& m_model, std::vector<double>& m_dq,
+                                   std::vector<double>& m_lfErr, std::vector<double>& m_rfErr)
 {
     m_actuatedDOFs = actuatedDOFs;
     if (config.isNull()) { std::cerr << "[initialize] Empty configuration for QP-IK solver.\n"; return false; } // _qpOASES.cpp:60-64
@@ -126,8 +128,16 @@ bool WalkingQPIK_qpOASES::initialize(const yarp::os::Searchable& config, const i
     wc_ik_destroy(m_handle); m_handle = nullptr;
     const wc_status rc = wc_ik_create(&m_cfg, &m_model, 1, 0, &m_handle);
     if (rc != WC_OK) { std::cerr << "[initialize] wc_ik_create failed with status " << rc << "\n"; return false; }
+    if (solver != WC_IK_SOLVER_QPOASES && wc_ik_set_solver(m_handle, solver, nullptr) != WC_OK) return false; // OSQP defaults (_osqp.cpp:127-131)
+    if (solver == WC_IK_SOLVER_OSQP) m_numberOfConstraints += m_actuatedDOFs;                                   // _osqp.cpp:77-82
     m_dq.assign(m_actuatedDOFs, 0.0); m_lfErr.assign(6, 0.0); m_rfErr.assign(6, 0.0);
     return true;
+}
+
+bool WalkingQPIK_qpOASES::initialize(const yarp::os::Searchable& config, const int& actuatedDOFs,
+                                     const iDynTree::VectorDynSize& minJointsLimit, const iDynTree::VectorDynSize& maxJointsLimit)
+{
+    return initializeDevice(config, actuatedDOFs, minJointsLimit, maxJointsLimit, WC_IK_SOLVER_QPOASES, m_handle, m_model, m_dq, m_lfErr, m_rfErr);
 }
 
 bool WalkingQPIK_qpOASES::solve()
@@ -167,3 +177,61 @@ bool WalkingQPIK_qpOASES::getSolution(iDynTree::VectorDynSize& output)
 }
 bool WalkingQPIK_qpOASES::getLeftFootError(iDynTree::VectorDynSize& output) { if (output.size() != 6) output.resize(6); for (int i = 0; i < 6; i++) output(i) = m_lfErr[i]; return true; }
 bool WalkingQPIK_qpOASES::getRightFootError(iDynTree::VectorDynSize& output) { if (output.size() != 6) output.resize(6); for (int i = 0; i < 6; i++) output(i) = m_rfErr[i]; return true; }
+
+// ------------------------------------------------------------------------------------------ osqp variant
+WalkingQPIK_osqp::~WalkingQPIK_osqp() { wc_ik_destroy(m_handle); }
+
+bool WalkingQPIK_osqp::initialize(const yarp::os::Searchable& config, const int& actuatedDOFs,
+                                  const iDynTree::VectorDynSize& minJointsLimit, const iDynTree::VectorDynSize& maxJointsLimit)
+{
+    return initializeDevice(config, actuatedDOFs, minJointsLimit, maxJointsLimit, WC_IK_SOLVER_OSQP, m_handle, m_model, m_dq, m_lfErr, m_rfErr);
+}
+
+bool WalkingQPIK_osqp::solve()
+{
+    m_isSolutionEvaluated = false;                                                                              // _osqp.cpp:351
+    if (!m_handle) return false;
+    bool changed = false;
+    for (int i = 0; i < m_actuatedDOFs; i++) if (m_cfg.joint_reg_rad[i] != m_regularizationTerm(i)) { m_cfg.joint_reg_rad[i] = m_regularizationTerm(i); changed = true; }
+    if (changed) { // a new regularisation target needs a new device configuration; the OSQP workspace starts over
+        wc_ik_destroy(m_handle); m_handle = nullptr;
+        if (wc_ik_create(&m_cfg, &m_model, 1, 0, &m_handle) != WC_OK || wc_ik_set_solver(m_handle, WC_IK_SOLVER_OSQP, nullptr) != WC_OK) return false;
+    }
+    double lfH[12], rfH[12], lfd[12], rfd[12];
+    m_leftFootToWorldTransform.toH12(lfH); m_rightFootToWorldTransform.toH12(rfH);
+    m_desiredLeftFootToWorldTransform.toH12(lfd); m_desiredRightFootToWorldTransform.toH12(rfd);
+    const wc_status rc = wc_ik_solve_with_jacobians_host(
+        m_handle, m_jointPosition.data(), lfH, rfH, m_neckOrientation.data(), m_comPosition.data(),
+        m_leftFootJacobian.data(), m_rightFootJacobian.data(), m_neckJacobian.data(), m_comJacobian.data(),
+        lfd, rfd, m_leftFootTwist.data(), m_rightFootTwist.data(), m_desiredComPosition.data(), m_comVelocity.data(),
+        m_desiredNeckOrientation.data(), m_dq.data(), m_lfErr.data(), m_rfErr.data(), &m_status, &m_iters);
+    if (rc != WC_OK || wc_ik_osqp_info_host(m_handle, &m_flags, &m_setups) != WC_OK) return false;
+    if (m_flags & 1) { std::cerr << "[solve] Unable to solve the problem.\n"; return false; }                 // :377-381
+    if (m_flags & 2) { std::cerr << "[solve] The solution is not feasible.\n"; return false; }                // :384-388
+    m_isSolutionEvaluated = true;
+    return true;
+}
+
+bool WalkingQPIK_osqp::getSolution(iDynTree::VectorDynSize& output)
+{
+    if (!m_isSolutionEvaluated) {                                                                               // :412-417
+        std::cerr << "[getSolution] The solution is not evaluated. Please call 'solve()' method.\n"; return false;
+    }
+    if (static_cast<int>(output.size()) != m_actuatedDOFs) output.resize(m_actuatedDOFs);
+    for (int i = 0; i < m_actuatedDOFs; i++) output(i) = m_dq[i];                                               // no latch reset in this variant
+    return true;
+}
+bool WalkingQPIK_osqp::getLeftFootError(iDynTree::VectorDynSize& output)
+{
+    if (!m_isSolutionEvaluated) { std::cerr << "[getLeftFootError] The solution is not evaluated. Please call 'solve()' method.\n"; return false; } // :432-437
+    if (output.size() != 6) output.resize(6);
+    for (int i = 0; i < 6; i++) output(i) = m_lfErr[i];
+    return true;
+}
+bool WalkingQPIK_osqp::getRightFootError(iDynTree::VectorDynSize& output)
+{
+    if (!m_isSolutionEvaluated) { std::cerr << "[getRightFootError] The solution is not evaluated. Please call 'solve()' method.\n"; return false; } // :445-450
+    if (output.size() != 6) output.resize(6);
+    for (int i = 0; i < 6; i++) output(i) = m_rfErr[i];
+    return true;
+}

@@ -27,6 +27,10 @@ protected:
     wc_ik_config m_cfg{};
 
     virtual bool initializeMatrices(const yarp::os::Searchable& config);
+    // shared body of the two subclasses' initialize(): configuration parsing + device handle with the chosen solver
+    bool initializeDevice(const yarp::os::Searchable& config, const int& actuatedDOFs, const iDynTree::VectorDynSize& minJointsLimit,
+                          const iDynTree::VectorDynSize& maxJointsLimit, int solver, wc_ik*& handle, wc_model& model,
+                          std::vector<double>& dq, std::vector<double>& lfErr, std::vector<double>& rfErr);
 
 public:
     virtual ~WalkingQPIK();

@@ -49,11 +49,12 @@ int main(int argc, char** argv)
 
     WalkingController controller;
     WalkingQPIK_qpOASES ik;
+    WalkingQPIK_osqp ikOsqp;            // `use_osqp on` (iCubGenova04 / iCubGazeboV2_5 dcmWalkingCoordinator.ini)
     WalkingFK fk;
     wc_model model; wc_model_icub_like(&model);
     iDynTree::VectorDynSize vmin(23), vmax(23);
     for (int i = 0; i < 23; i++) { vmin(i) = -20.0; vmax(i) = 20.0; } // wide limits: the synthetic swing-foot targets start far from the posture
-    if (!controller.initialize(mpcCfg) || !ik.initialize(ikCfg, 23, vmin, vmax) || !fk.initialize(fkCfg, model)) {
+    if (!controller.initialize(mpcCfg) || !ik.initialize(ikCfg, 23, vmin, vmax) || !ikOsqp.initialize(ikCfg, 23, vmin, vmax) || !fk.initialize(fkCfg, model)) {
         std::fprintf(stderr, "initialisation failed\n"); return 2;
     }
     // ---- oracle twins
@@ -79,7 +80,9 @@ int main(int argc, char** argv)
 
     iDynTree::VectorDynSize qDesired(23), dqDesired(23), qMeas(23);
     for (int i = 0; i < 23; i++) qDesired(i) = oik.joint_reg_rad[i];
-    double worst_zmp = 0.0, worst_dq = 0.0;
+    double worst_zmp = 0.0, worst_dq = 0.0, worst_dq_osqp = 0.0;
+    wco_ikosqp* oikOsqp = wco_ikosqp_create(&oik, nullptr);
+    int osqpSetups = 0;
     int failures = 0;
     for (int t = 0; t < T; t++) {
         const int k = t / STEP, i = t % STEP;
@@ -145,6 +148,31 @@ int main(int argc, char** argv)
                                       nullptr, nullptr, nullptr);
         if (ok != (ost2 == 0) || ik.qpStatus() != ost2) { std::fprintf(stderr, "tick %d: IK status mismatch %d/%d\n", t, ik.qpStatus(), ost2); failures++; }
         for (int j = 0; j < 23; j++) worst_dq = std::fmax(worst_dq, std::fabs(dqDesired(j) - odq[j]));
+        // ======== the same tick through WalkingQPIK_osqp (WalkingModule.cpp:721-731), against its restatement
+        {
+            iDynTree::VectorDynSize dqOsqp(23);
+            bool ok2 = ikOsqp.setRobotState(qMeas, fk.getLeftFootToWorldTransform(), fk.getRightFootToWorldTransform(), fk.getNeckOrientation(), comMeas);
+            ikOsqp.setDesiredNeckOrientation(yawRotation.inverse());
+            ikOsqp.setDesiredFeetTransformation(leftTraj.front(), rightTraj.front());
+            ikOsqp.setDesiredFeetTwist(lTw, rTw);
+            ikOsqp.setDesiredCoMVelocity(comVel);
+            ikOsqp.setDesiredCoMPosition(comDes);
+            fk.getLeftFootJacobian(jac); ok2 = ok2 && ikOsqp.setLeftFootJacobian(jac);
+            fk.getRightFootJacobian(jac); ok2 = ok2 && ikOsqp.setRightFootJacobian(jac);
+            fk.getNeckJacobian(jac); ok2 = ok2 && ikOsqp.setNeckJacobian(jac);
+            ok2 = ok2 && ikOsqp.setCoMJacobian(comJac);
+            ok2 = ok2 && ikOsqp.solve() && ikOsqp.getSolution(dqOsqp);
+            double odq2[23], ole2[6], ore2[6]; int ost3 = 0, oit3 = 0, ofl3 = 0;
+            wco_ikosqp_solve(oikOsqp, qMeas.data(), olf, orf, onR, comMeas.data(), Jl, Jr, Jn, Jc, lfd, rfd, lTw.data(), rTw.data(),
+                             comDes.data(), comVel.data(), yawRotation.inverse().data(), odq2, ole2, ore2, &ost3, &oit3, &ofl3);
+            if (ok2 != (ofl3 == 0) || ikOsqp.osqpStatus() != ost3 || ikOsqp.osqpIterations() != oit3 || ikOsqp.solverSetups() != wco_ikosqp_setups(oikOsqp)) {
+                std::fprintf(stderr, "tick %d: osqp IK mismatch (ok %d/%d status %d/%d iters %d/%d setups %d/%d)\n", t, ok2, ofl3 == 0,
+                             ikOsqp.osqpStatus(), ost3, ikOsqp.osqpIterations(), oit3, ikOsqp.solverSetups(), wco_ikosqp_setups(oikOsqp));
+                failures++;
+            }
+            for (int j = 0; j < 23; j++) worst_dq_osqp = std::fmax(worst_dq_osqp, std::fabs(dqOsqp(j) - odq2[j]));
+            osqpSetups = ikOsqp.solverSetups();
+        }
         for (int j = 0; j < 23; j++) qDesired(j) += dT * dqDesired(j);   // stand-in for iCub::ctrl::Integrator (:741-744)
 
         // advanceReferenceSignals (WalkingModule.cpp:35-96)
@@ -220,6 +248,9 @@ int main(int argc, char** argv)
     std::printf("trajectory generator: worst abs err %.3e\n", worst_traj);
     if (worst_traj > 1e-12) failures++;
     wco_mpc_free(ompc);
+    wco_ikosqp_free(oikOsqp);
+    std::printf("WalkingQPIK_osqp: worst dq err %.3e rad/s, %d solver set-ups (stance changes + 1)\n", worst_dq_osqp, osqpSetups);
+    if (worst_dq_osqp > 1e-5) failures++;
     std::printf("reactive controller: worst abs err %.3e\n", worst_reactive);
     if (worst_reactive > 1e-13) failures++;
     std::printf("drop-in test: %d ticks, horizon %d, worst rel ZMP err %.3e, worst dq err %.3e rad/s, failures %d\n", T, N, worst_zmp,
