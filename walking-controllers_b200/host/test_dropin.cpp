@@ -157,14 +157,20 @@ int main(int argc, char** argv)
             ikOsqp.setDesiredFeetTwist(lTw, rTw);
             ikOsqp.setDesiredCoMVelocity(comVel);
             ikOsqp.setDesiredCoMPosition(comDes);
-            fk.getLeftFootJacobian(jac); ok2 = ok2 && ikOsqp.setLeftFootJacobian(jac);
-            fk.getRightFootJacobian(jac); ok2 = ok2 && ikOsqp.setRightFootJacobian(jac);
-            fk.getNeckJacobian(jac); ok2 = ok2 && ikOsqp.setNeckJacobian(jac);
+            // The restatement gets the very Jacobians the class is given (the WalkingFK getters, i.e. the device FK): which entries
+            // of the Hessian are EXACTLY zero decides whether osqp-eigen re-initialises the solver, so parity of the solver life
+            // cycle is only defined on bit-identical inputs (noise-level entries flip between 0 and 1e-17 as the posture moves).
+            iDynTree::MatrixDynSize jl, jr, jn;
+            fk.getLeftFootJacobian(jl); ok2 = ok2 && ikOsqp.setLeftFootJacobian(jl);
+            fk.getRightFootJacobian(jr); ok2 = ok2 && ikOsqp.setRightFootJacobian(jr);
+            fk.getNeckJacobian(jn); ok2 = ok2 && ikOsqp.setNeckJacobian(jn);
             ok2 = ok2 && ikOsqp.setCoMJacobian(comJac);
             ok2 = ok2 && ikOsqp.solve() && ikOsqp.getSolution(dqOsqp);
-            double odq2[23], ole2[6], ore2[6]; int ost3 = 0, oit3 = 0, ofl3 = 0;
-            wco_ikosqp_solve(oikOsqp, qMeas.data(), olf, orf, onR, comMeas.data(), Jl, Jr, Jn, Jc, lfd, rfd, lTw.data(), rTw.data(),
-                             comDes.data(), comVel.data(), yawRotation.inverse().data(), odq2, ole2, ore2, &ost3, &oit3, &ofl3);
+            double odq2[23], ole2[6], ore2[6], glf[12], grf[12]; int ost3 = 0, oit3 = 0, ofl3 = 0;
+            fk.getLeftFootToWorldTransform().toH12(glf); fk.getRightFootToWorldTransform().toH12(grf);
+            wco_ikosqp_solve(oikOsqp, qMeas.data(), glf, grf, fk.getNeckOrientation().data(), comMeas.data(), jl.data(), jr.data(), jn.data(),
+                             comJac.data(), lfd, rfd, lTw.data(), rTw.data(), comDes.data(), comVel.data(), yawRotation.inverse().data(),
+                             odq2, ole2, ore2, &ost3, &oit3, &ofl3);
             if (ok2 != (ofl3 == 0) || ikOsqp.osqpStatus() != ost3 || ikOsqp.osqpIterations() != oit3 || ikOsqp.solverSetups() != wco_ikosqp_setups(oikOsqp)) {
                 std::fprintf(stderr, "tick %d: osqp IK mismatch (ok %d/%d status %d/%d iters %d/%d setups %d/%d)\n", t, ok2, ofl3 == 0,
                              ikOsqp.osqpStatus(), ost3, ikOsqp.osqpIterations(), oit3, ikOsqp.solverSetups(), wco_ikosqp_setups(oikOsqp));
