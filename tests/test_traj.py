@@ -122,3 +122,70 @@ def test_mpc_fed_by_device_producer(wc, oracle, syn, cuda_device):
         zg = out["zmp"].cpu().numpy()
         assert (np.abs(zg - zo) / np.maximum(1.0, np.abs(zo))).max() <= 1e-6
     mg.close(); tg.close()
+
+
+@pytest.mark.gpu
+def test_device_resident_rollout_all_blocks(wc, oracle, syn, cuda_device):
+    """The whole tick on the device with no host generator and no host round trip: input producer -> DCM-MPC (and the reactive
+    controller beside it) -> LIPM / ZMP-CoM law -> FK + QP-IK about the integrated posture -> joint integration -> logger row;
+    the CPU chain (producer twin + oracle) runs the same sequence independently."""
+    B, N, T = 96, 25, 10
+    g, par = _gait(syn, B, T, N, seed=17)
+    dev = cuda_device
+    d = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+    tw = oracle.TrajBatch(oracle.traj_default_config(T, N), B); tw.set_gait(**par)
+    tg = wc.TrajBatch(wc.traj_default_config(T, N), B); tg.set_gait(**{k: d(v) for k, v in par.items()})
+    mo = oracle.MpcBatch(oracle.mpc_default_config(N), B); mg = wc.MpcBatch(wc.mpc_default_config(N), B)
+    go = oracle.GlueBatch(oracle.glue_default_config(), B); gg = wc.GlueBatch(wc.glue_default_config(), B)
+    icfg_o, model_o, icfg_g = oracle.ik_default_config(), oracle.model_icub_like(), wc.ik_default_config()
+    for j in range(23):
+        icfg_o.min_vel[j], icfg_o.max_vel[j] = -50.0, 50.0
+        icfg_g.min_vel[j], icfg_g.max_vel[j] = -50.0, 50.0
+    ik = wc.IkBatch(icfg_g, wc.model_icub_like(), B)
+    omega = math.sqrt(go.cfg.gravity / go.cfg.com_height)
+    q0 = np.tile(np.array(icfg_o.joint_reg_rad[:23])[:, None], (1, B)) + 0.01 * np.random.default_rng(2).normal(size=(23, B))
+    f0 = tw.feet(0)
+    base0 = np.where(f0["left_is_fixed"][None, :] != 0, f0["lf_H"], f0["rf_H"])
+    com0 = oracle.fk_batch(model_o, q0, base0, f0["left_is_fixed"], jacobians=False)["com"]
+    go.reset(com0[:2], q0); gg.reset(d(com0[:2]), d(q0))
+    q_o, q_g = q0.copy(), d(q0)
+    eye = np.tile(np.eye(3).reshape(9, 1), (1, B)); eye_g = d(eye)
+    for t in range(T):
+        # ---- CPU chain
+        fo = tw.feet(t); ro, vo = tw.dcm(t, N + 1); do = tw.measured_dcm(t, 0.002, 99)
+        zo, so, io_, _ = mo.tick(fo["lf_H"], fo["rf_H"], fo["l_contact"], fo["r_contact"], do, ro)
+        zr_o = oracle.reactive_dcm(omega, 1.5, ro[0:2], vo[0:2], do)
+        base_o = np.where(fo["left_is_fixed"][None, :] != 0, fo["lf_H"], fo["rf_H"])
+        ko = oracle.fk_batch(model_o, q_o, base_o, fo["left_is_fixed"], jacobians=False)
+        co = go.com_reference(ro[0:2], zo, zo + 0.001, ko["com"], fo["com_height"], fo["com_height_vel"])
+        ino = dict(q_meas=q_o, q_lin=q_o, base_H=base_o, left_is_fixed=fo["left_is_fixed"], lf_H_des=fo["lf_H"], rf_H_des=fo["rf_H"],
+                   lf_twist=fo["lf_twist"], rf_twist=fo["rf_twist"], com_pos_des=co["com_pos_des"], com_vel_des=co["com_vel_des"],
+                   com_meas=ko["com"], neck_R_des=eye)
+        oo = oracle.ik_batch_tick(icfg_o, model_o, ino)
+        q_o = go.integrate_joints(oo["dq"])
+        row_o = oracle.log_pack(B, dcm=do, dcm_des=ro[0:2], dcm_vel_des=vo[0:2], zmp=zo + 0.001, zmp_des=zo, com=ko["com"],
+                                com_des_xy=co["com_pos_des"], com_vel_des_xy=co["com_vel_des"], lf_H=ko["lf_H"], rf_H=ko["rf_H"],
+                                lf_H_des=fo["lf_H"], rf_H_des=fo["rf_H"], lf_err=oo["lf_err"], rf_err=oo["rf_err"])
+        # ---- device chain: every tensor stays on the GPU
+        fg = tg.feet(t); rg, vg = tg.dcm(t, N + 1); dg = tg.measured_dcm(t, 0.002, 99)
+        mgo = mg.tick(fg["lf_H"], fg["rf_H"], fg["l_contact"], fg["r_contact"], dg, rg)
+        zr_g = gg.reactive_dcm(1.5, rg[0:2], vg[0:2], dg)
+        base_g = torch.where(fg["left_is_fixed"][None, :] != 0, fg["lf_H"], fg["rf_H"]).contiguous()
+        kg = ik.fk(q_g, base_g, fg["left_is_fixed"], jacobians=False)
+        cg = gg.com_reference(rg[0:2], mgo["zmp"], mgo["zmp"] + 0.001, kg["com"], fg["com_height"], fg["com_height_vel"])
+        ing = dict(q_meas=q_g, q_lin=q_g, base_H=base_g, left_is_fixed=fg["left_is_fixed"], lf_H_des=fg["lf_H"], rf_H_des=fg["rf_H"],
+                   lf_twist=fg["lf_twist"], rf_twist=fg["rf_twist"], com_pos_des=cg["com_pos_des"], com_vel_des=cg["com_vel_des"],
+                   com_meas=kg["com"], neck_R_des=eye_g)
+        og = ik.tick(ing)
+        q_g = gg.integrate_joints(og["dq"])
+        row_g = gg.log_pack(dcm=dg, dcm_des=rg[0:2], dcm_vel_des=vg[0:2], zmp=mgo["zmp"] + 0.001, zmp_des=mgo["zmp"], com=kg["com"],
+                            com_des_xy=cg["com_pos_des"], com_vel_des_xy=cg["com_vel_des"], lf_H=kg["lf_H"], rf_H=kg["rf_H"],
+                            lf_H_des=fg["lf_H"], rf_H_des=fg["rf_H"], lf_err=og["lf_err"], rf_err=og["rf_err"])
+        torch.cuda.synchronize()
+        assert np.array_equal(mgo["status"].cpu().numpy(), so) and np.array_equal(mgo["iters"].cpu().numpy(), io_), t
+        assert np.array_equal(og["status"].cpu().numpy(), oo["status"]), t
+        assert np.abs(mgo["zmp"].cpu().numpy() - zo).max() <= 1e-6 and np.abs(zr_g.cpu().numpy() - zr_o).max() <= 1e-11
+        assert np.abs(og["dq"].cpu().numpy() - oo["dq"]).max() <= 1e-5, t
+        assert np.abs(q_g.cpu().numpy() - q_o).max() <= 1e-7
+        assert np.abs(row_g.cpu().numpy() - row_o).max() <= 1e-5
+    mg.close(); ik.close(); gg.close(); tg.close()

@@ -3,7 +3,10 @@ import csv, sys
 path = sys.argv[1]; top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
 rows = list(csv.reader(open(path)))
 hdr = None; data = {}; tot = 0; inst_tot = 0
+fname = ''
 for r in rows:
+    if r and r[0] == 'File Path':
+        fname = r[1].rsplit('/', 1)[-1] if len(r) > 1 else ''; continue
     if r and r[0] == 'Line No':
         hdr = r; continue
     if hdr is None or len(r) < len(hdr) - 5: continue
@@ -13,7 +16,7 @@ for r in rows:
         w = int(r[4]); n = int(r[7])
     except Exception:
         continue
-    ln = r[0]
+    ln = (fname + ':' if fname else '') + r[0]
     stall = {h: int(v) for h, v in zip(hdr[32:49], r[32:49]) if v.isdigit()}
     d = data.setdefault(ln, [0, 0, r[1][:100], {}])
     d[0] += w; d[1] += n
@@ -26,4 +29,4 @@ for ln, (w, n, s, st) in data.items():
 print('stall mix:', ', '.join(f"{k[6:]}={100*v/max(tot,1):.1f}%" for k, v in sorted(agg.items(), key=lambda x: -x[1])[:8]))
 for ln, (w, n, s, st) in sorted(data.items(), key=lambda x: -x[1][0])[:top]:
     main = sorted(st.items(), key=lambda x: -x[1])[:2]
-    print(f"{w:7d} {100*w/max(tot,1):5.1f}% inst={n:10d} L{ln:>4}: {s[:90]}  [{', '.join(k[6:]+':'+str(v) for k,v in main)}]")
+    print(f"{w:7d} {100*w/max(tot,1):5.1f}% inst={n:10d} {ln:>22}: {s[:90]}  [{', '.join(k[6:]+':'+str(v) for k,v in main)}]")

@@ -25,32 +25,35 @@ if os.path.exists(lp):
     for k, (n, ns) in sorted(agg.items(), key=lambda x: -x[1][1]):
         out.append(f"| {k} | {n} | {ns/1e6:.3f} | {ns/n/1e3:.1f} | {100*ns/tot:.1f}% |")
     out.append("")
-rp = os.path.join(go, f"prof_{tag}.ncu-rep")
-if os.path.exists(rp):
-    raw = subprocess.run(["ncu", "-i", rp, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(raw.splitlines()))
-    hdr, units = rows[0], rows[1]
-    want = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
-            "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_registers",
-            "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
-            "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
-            "smsp__thread_inst_executed_per_inst_executed.ratio", "dram__bytes_read.sum", "dram__bytes_write.sum",
-            "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
-            "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
-            "lts__t_sector_hit_rate.pct"]
-    out.append(f"## ncu --set full ({tag}), per captured launch\n")
-    for r in rows[2:]:
-        out.append(f"### {short(r[hdr.index('Kernel Name')])}\n")
-        for w in want:
-            if w in hdr:
-                out.append(f"- {w}: {r[hdr.index(w)]} {units[hdr.index(w)]}")
-        st = [(h, float(r[i])) for i, h in enumerate(hdr) if h.startswith("smsp__average_warps_issue_stalled") and h.endswith("_per_issue_active.ratio") and r[i]]
-        st.sort(key=lambda x: -x[1])
-        out.append("- top stalls (warps stalled per issue-active cycle): " + ", ".join(f"{h.split('issue_stalled_')[1].split('_per_issue')[0]}={v:.2f}" for h, v in st[:7]))
-        out.append("")
+for rp in (os.path.join(go, f"prof_{tag}.ncu-rep"), os.path.join(go, f"prof_osqp_{tag}.ncu-rep")):
+  if os.path.exists(rp):
+      raw = subprocess.run(["ncu", "-i", rp, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+      rows = list(csv.reader(raw.splitlines()))
+      hdr, units = rows[0], rows[1]
+      want = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+              "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_registers",
+              "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+              "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
+              "smsp__thread_inst_executed_per_inst_executed.ratio", "dram__bytes_read.sum", "dram__bytes_write.sum",
+              "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+              "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+              "lts__t_sector_hit_rate.pct"]
+      out.append(f"## ncu --set full ({tag}), per captured launch\n")
+      for r in rows[2:]:
+          out.append(f"### {short(r[hdr.index('Kernel Name')])}\n")
+          for w in want:
+              if w in hdr:
+                  out.append(f"- {w}: {r[hdr.index(w)]} {units[hdr.index(w)]}")
+          st = [(h, float(r[i])) for i, h in enumerate(hdr) if h.startswith("smsp__average_warps_issue_stalled") and h.endswith("_per_issue_active.ratio") and r[i]]
+          st.sort(key=lambda x: -x[1])
+          out.append("- top stalls (warps stalled per issue-active cycle): " + ", ".join(f"{h.split('issue_stalled_')[1].split('_per_issue')[0]}={v:.2f}" for h, v in st[:7]))
+          out.append("")
 bp = os.path.join(go, f"bench_{tag}.json")
 if os.path.exists(bp):
     out.append(f"## bench line of the same visit ({tag}, not under ncu)\n\n```\n" + open(bp).read().strip() + "\n```\n")
+bp = os.path.join(go, f"bench_524k_{tag}.json")
+if os.path.exists(bp):
+    out.append(f"## 524 288 instances on one GPU (BASELINE configs[3] size; {tag})\n\n```\n" + open(bp).read().strip() + "\n```\n")
 bp = os.path.join(go, f"bench_ref_{tag}.json")
 if os.path.exists(bp):
     out.append(f"## --impl reference line ({tag})\n\n```\n" + open(bp).read().strip() + "\n```\n")

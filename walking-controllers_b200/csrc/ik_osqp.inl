@@ -12,7 +12,7 @@
 // empty "velocity limit" row v (23 rows with no entries: they only take part in the norms).  Every tick the problem data
 // change, so every tick runs OSQP's scale_data (ten Ruiz passes, in place, same operation order as OSQP), rebuilds the
 // reduced KKT matrix K = P + sigma I + rho_eq A'A (29 x 29, instead of the 67 x 67 quasi-definite KKT matrix: same x~, z~ = A x~)
-// and its Cholesky factor; the ADMM iterates (x, z, y; scaled) and rho persist in HBM between ticks as OSQP's workspace does.
+// and its Cholesky factor L, inverts L once (column per lane) so that every K x~ = rhs is two triangular mat-vecs; the ADMM iterates (x, z, y; scaled) and rho persist in HBM between ticks as OSQP's workspace does.
 // Shared memory per warp: P [29][33], A [15][33], K/L [29][33] (aliases the kinematics scratch), five 32-vectors = 20.6 KB.
 
 template <int NJ, bool COMC>
@@ -38,6 +38,33 @@ __device__ __forceinline__ double osqp_limit_scaling(double v)
     v = v < kOsqpMinScaling ? 1.0 : v;
     v = v > kOsqpMaxScaling ? kOsqpMaxScaling : v;
     return v;
+}
+
+
+// reductions with four independent chains: a warp has at most one other warp to hide the 8-cycle DFMA / DMNMX latency behind
+template <int N, int SA>
+__device__ __forceinline__ double osqp_dot(const double* a, const double* b)
+{
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+    for (int k = 0; k + 3 < N; k += 4) {
+        s0 += a[k * SA] * b[k]; s1 += a[(k + 1) * SA] * b[k + 1]; s2 += a[(k + 2) * SA] * b[k + 2]; s3 += a[(k + 3) * SA] * b[k + 3];
+    }
+#pragma unroll
+    for (int k = N - N % 4; k < N; k++) s0 += a[k * SA] * b[k];
+    return (s0 + s1) + (s2 + s3);
+}
+template <int N, int SA>
+__device__ __forceinline__ double osqp_absmax(const double* a)
+{
+    double m0 = 0.0, m1 = 0.0, m2 = 0.0, m3 = 0.0;
+#pragma unroll
+    for (int k = 0; k + 3 < N; k += 4) {
+        m0 = fmax(m0, fabs(a[k * SA])); m1 = fmax(m1, fabs(a[(k + 1) * SA])); m2 = fmax(m2, fabs(a[(k + 2) * SA])); m3 = fmax(m3, fabs(a[(k + 3) * SA]));
+    }
+#pragma unroll
+    for (int k = N - N % 4; k < N; k++) m0 = fmax(m0, fabs(a[k * SA]));
+    return fmax(fmax(m0, m1), fmax(m2, m3));
 }
 
 template <int NJ, bool COMC>
@@ -139,29 +166,49 @@ __global__ void __launch_bounds__(kOsqpWarps * 32) ik_osqp_kernel(IkDev d, IkTic
 
     // ---- scale_data (OSQP scaling.c), in place; D of this lane's variable, E of this lane's task row (velocity rows: E = 1)
     double Dj = 1.0, Er = 1.0, c = 1.0, qj = isvar ? gj : 0.0;
+    double c_pend = 1.0; // cost scaling of the previous pass, applied to P while the next pass reads it for its norms
     for (int it = 0; it < st.scaling; it++) {
         double dn = 0.0, en = 0.0;
         if (isvar) {
-            for (int r = 0; r < NV; r++) dn = fmax(dn, fabs(PS[r * LD + j]));
+            double m0 = 0.0, m1 = 0.0, m2 = 0.0, m3 = 0.0;
 #pragma unroll
-            for (int r = 0; r < NC; r++) dn = fmax(dn, fabs(acol[r]));
+            for (int r = 0; r + 3 < NV; r += 4) {
+                const double v0 = PS[r * LD + j] * c_pend, v1 = PS[(r + 1) * LD + j] * c_pend, v2 = PS[(r + 2) * LD + j] * c_pend,
+                             v3 = PS[(r + 3) * LD + j] * c_pend;
+                PS[r * LD + j] = v0; PS[(r + 1) * LD + j] = v1; PS[(r + 2) * LD + j] = v2; PS[(r + 3) * LD + j] = v3;
+                m0 = fmax(m0, fabs(v0)); m1 = fmax(m1, fabs(v1)); m2 = fmax(m2, fabs(v2)); m3 = fmax(m3, fabs(v3));
+            }
+#pragma unroll
+            for (int r = NV - NV % 4; r < NV; r++) { const double v = PS[r * LD + j] * c_pend; PS[r * LD + j] = v; m0 = fmax(m0, fabs(v)); }
+            dn = fmax(fmax(m0, m1), fmax(m2, m3));
+            double an0 = 0.0, an1 = 0.0;
+#pragma unroll
+            for (int r = 0; r + 1 < NC; r += 2) { an0 = fmax(an0, fabs(acol[r])); an1 = fmax(an1, fabs(acol[r + 1])); }
+            if (NC % 2) an0 = fmax(an0, fabs(acol[NC - 1]));
+            dn = fmax(dn, fmax(an0, an1));
         }
-        if (isrow)
-            for (int k = 0; k < NV; k++) en = fmax(en, fabs(AS[lane * LD + k]));
+        if (isrow) en = osqp_absmax<NV, 1>(AS + lane * LD);
         const double dt = 1.0 / sqrt(osqp_limit_scaling(dn)), et = 1.0 / sqrt(osqp_limit_scaling(en));
         DT[lane] = dt; ET[lane] = et;
         __syncwarp();
+        double pn = 0.0;
         if (isvar) {
-            for (int r = 0; r < NV; r++) PS[r * LD + j] = (PS[r * LD + j] * DT[r]) * dt;
+            double m0 = 0.0, m1 = 0.0, m2 = 0.0, m3 = 0.0;
+#pragma unroll
+            for (int r = 0; r + 3 < NV; r += 4) {
+                const double v0 = (PS[r * LD + j] * DT[r]) * dt, v1 = (PS[(r + 1) * LD + j] * DT[r + 1]) * dt,
+                             v2 = (PS[(r + 2) * LD + j] * DT[r + 2]) * dt, v3 = (PS[(r + 3) * LD + j] * DT[r + 3]) * dt;
+                PS[r * LD + j] = v0; PS[(r + 1) * LD + j] = v1; PS[(r + 2) * LD + j] = v2; PS[(r + 3) * LD + j] = v3;
+                m0 = fmax(m0, fabs(v0)); m1 = fmax(m1, fabs(v1)); m2 = fmax(m2, fabs(v2)); m3 = fmax(m3, fabs(v3));
+            }
+#pragma unroll
+            for (int r = NV - NV % 4; r < NV; r++) { const double v = (PS[r * LD + j] * DT[r]) * dt; PS[r * LD + j] = v; m0 = fmax(m0, fabs(v)); }
+            pn = fmax(fmax(m0, m1), fmax(m2, m3));
 #pragma unroll
             for (int r = 0; r < NC; r++) { acol[r] = (acol[r] * ET[r]) * dt; AS[r * LD + j] = acol[r]; }
             qj *= dt; Dj *= dt;
         }
         if (isrow) Er *= et;
-        __syncwarp();
-        double pn = 0.0;
-        if (isvar)
-            for (int r = 0; r < NV; r++) pn = fmax(pn, fabs(PS[r * LD + j]));
         NR[lane] = pn;
         __syncwarp();
         double c_temp = 0.0;
@@ -171,11 +218,13 @@ __global__ void __launch_bounds__(kOsqpWarps * 32) ik_osqp_kernel(IkDev d, IkTic
         qn = osqp_limit_scaling(qn);
         c_temp = qn > c_temp ? qn : c_temp;
         c_temp = 1.0 / osqp_limit_scaling(c_temp);
-        if (isvar)
-            for (int r = 0; r < NV; r++) PS[r * LD + j] *= c_temp;
+        c_pend = c_temp;
         qj *= c_temp; c *= c_temp;
         __syncwarp();
     }
+    if (isvar && st.scaling > 0)
+        for (int r = 0; r < NV; r++) PS[r * LD + j] *= c_pend;
+    __syncwarp();
     const double cinv = 1.0 / c, Dinv = 1.0 / Dj, Einv = 1.0 / Er;
     // bounds (setBounds :264-347, setVelocityBounds :23-51), scaled by E
     double b_r = 0.0;
@@ -205,11 +254,7 @@ __global__ void __launch_bounds__(kOsqpWarps * 32) ik_osqp_kernel(IkDev d, IkTic
             if (isvel) yv = d.oy[(size_t)(NC + lane) * B + i] * c;
             XT[lane] = x;
             __syncwarp();
-            if (isrow) {
-                double a = 0.0;
-                for (int k = 0; k < NV; k++) a += AS[lane * LD + k] * XT[k];
-                zt = a;
-            }
+            if (isrow) zt = osqp_dot<NV, 1>(AS + lane * LD, XT);
             zv = 0.0;
             __syncwarp();
         }
@@ -222,27 +267,52 @@ __global__ void __launch_bounds__(kOsqpWarps * 32) ik_osqp_kernel(IkDev d, IkTic
         const double rho_e = kOsqpRhoEq * rho_now;
         if (isvar) {
             for (int r = 0; r < NV; r++) {
-                double acc = 0.0;
+                double c0 = 0.0, c1 = 0.0, c2 = 0.0;
 #pragma unroll
-                for (int k = 0; k < NC; k++) acc += AS[k * LD + r] * acol[k];
+                for (int k = 0; k < NC; k += 3) { c0 += AS[k * LD + r] * acol[k]; c1 += AS[(k + 1) * LD + r] * acol[k + 1]; c2 += AS[(k + 2) * LD + r] * acol[k + 2]; }
+                const double acc = (c0 + c1) + c2;
                 KS[r * LD + j] = (PS[r * LD + j] + (r == j ? st.sigma : 0.0)) + rho_e * acc;
             }
         }
         __syncwarp();
+        // left-looking Cholesky: column k needs rows i >= k minus the dot product of rows i and k over the finished columns
+        // (row i on lane i: conflict-free; row k: broadcast) — reads only, one store per entry, one barrier per column
         for (int k = 0; k < NV; k++) {
-            const double pk = KS[k * LD + k];
+            double sv = 0.0;
+            if (isvar && lane >= k) {
+                const double* ri = KS + lane * LD; const double* rk = KS + k * LD;
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+                int p = 0;
+                for (; p + 3 < k; p += 4) { a0 += ri[p] * rk[p]; a1 += ri[p + 1] * rk[p + 1]; a2 += ri[p + 2] * rk[p + 2]; a3 += ri[p + 3] * rk[p + 3]; }
+                for (; p < k; p++) a0 += ri[p] * rk[p];
+                sv = ri[k] - ((a0 + a1) + (a2 + a3));
+            }
+            const double pk = __shfl_sync(FULL, sv, k);
             if (!(pk > 0.0)) spd = false;
             const double piv = sqrt(pk), pinv = 1.0 / piv;
-            __syncwarp();
-            double lik = 0.0;
-            if (lane == k) KS[k * LD + k] = piv;
-            if (lane > k && isvar) { lik = KS[lane * LD + k] * pinv; KS[lane * LD + k] = lik; }
-            __syncwarp();
-            if (lane > k && isvar)
-                for (int jj = k + 1; jj <= lane; jj++) KS[lane * LD + jj] -= lik * KS[jj * LD + k];
+            if (isvar && lane >= k) KS[lane * LD + k] = lane == k ? piv : sv * pinv;
             __syncwarp();
         }
         dinv = isvar ? 1.0 / KS[lane * LD + lane] : 1.0;
+        // X = L^-1 (lower triangular), column c by lane c, stored transposed in the free upper triangle of the same buffer
+        // (X[i][c] at KS[c * LD + i], i > c; X[c][c] = dinv stays in a register): the 25+ solves of the ADMM loop then are two
+        // triangular mat-vecs with independent lanes instead of 2 x 29 shuffle-serialised substitution steps
+        DT[lane] = dinv;
+        __syncwarp();
+        if (isvar) {
+            for (int r = 1; r < NV; r++) {
+                double a0 = 0.0, a1 = 0.0;
+                int p = 0;
+                for (; p + 1 < r; p += 2) {
+                    const double x0 = p > lane ? KS[lane * LD + p] : (p == lane ? dinv : 0.0);
+                    const double x1 = p + 1 > lane ? KS[lane * LD + p + 1] : (p + 1 == lane ? dinv : 0.0);
+                    a0 += KS[r * LD + p] * x0; a1 += KS[r * LD + p + 1] * x1;
+                }
+                if (p < r) a0 += KS[r * LD + p] * (p > lane ? KS[lane * LD + p] : (p == lane ? dinv : 0.0));
+                if (r > lane) KS[lane * LD + r] = -(a0 + a1) * DT[r];
+            }
+        }
+        __syncwarp();
     };
     factor(rho);
 
@@ -253,8 +323,7 @@ __global__ void __launch_bounds__(kOsqpWarps * 32) ik_osqp_kernel(IkDev d, IkTic
         XT[lane] = x; WV[lane] = isrow ? yt : 0.0;
         __syncwarp();
         double ax = 0.0;
-        if (isrow)
-            for (int k = 0; k < NV; k++) ax += AS[lane * LD + k] * XT[k];
+        if (isrow) ax = osqp_dot<NV, 1>(AS + lane * LD, XT);
         const double rp_t = ax - zt, rp_v = 0.0 - zv;
         rp_s = warp_max(fmax(isrow ? fabs(rp_t) : 0.0, isvel ? fabs(rp_v) : 0.0));
         pri_res = warp_max(fmax(isrow ? fabs(Einv * rp_t) : 0.0, isvel ? fabs(rp_v) : 0.0));
@@ -264,9 +333,11 @@ __global__ void __launch_bounds__(kOsqpWarps * 32) ik_osqp_kernel(IkDev d, IkTic
         nAx_u = warp_max(isrow ? fabs(Einv * ax) : 0.0);
         double px = 0.0, aty = 0.0;
         if (isvar) {
-            for (int r = 0; r < NV; r++) px += PS[r * LD + j] * XT[r];
+            px = osqp_dot<NV, LD>(PS + j, XT);
+            double y0 = 0.0, y1 = 0.0, y2 = 0.0;
 #pragma unroll
-            for (int r = 0; r < NC; r++) aty += acol[r] * WV[r];
+            for (int r = 0; r < NC; r += 3) { y0 += acol[r] * WV[r]; y1 += acol[r + 1] * WV[r + 1]; y2 += acol[r + 2] * WV[r + 2]; }
+            aty = (y0 + y1) + y2;
         }
         const double rd = (qj + px) + aty;
         rd_s = warp_max(fabs(rd)); dua_res = cinv * warp_max(fabs(Dinv * rd));
@@ -305,10 +376,8 @@ __global__ void __launch_bounds__(kOsqpWarps * 32) ik_osqp_kernel(IkDev d, IkTic
         XT[lane] = dx;
         __syncwarp();
         double pdx = 0.0, adx = 0.0;
-        if (isvar)
-            for (int r = 0; r < NV; r++) pdx += PS[r * LD + j] * XT[r];
-        if (isrow)
-            for (int k = 0; k < NV; k++) adx += AS[lane * LD + k] * XT[k];
+        if (isvar) pdx = osqp_dot<NV, LD>(PS + j, XT);
+        if (isrow) adx = osqp_dot<NV, 1>(AS + lane * LD, XT);
         const double m = warp_max(fabs(pdx * Dinv));
         __syncwarp();
         if (!(m < c * eps * nrm)) return false;
@@ -348,24 +417,38 @@ __global__ void __launch_bounds__(kOsqpWarps * 32) ik_osqp_kernel(IkDev d, IkTic
         WV[lane] = isrow ? rho_e * (zt_prev - rho_e_inv * yt) : 0.0;
         __syncwarp();
         double t = sigma * x_prev - qj;
+        {
+            double r0 = 0.0, r1 = 0.0, r2 = 0.0;
 #pragma unroll
-        for (int r = 0; r < NC; r++) t += acol[r] * WV[r];
+            for (int r = 0; r < NC; r += 3) { r0 += acol[r] * WV[r]; r1 += acol[r + 1] * WV[r + 1]; r2 += acol[r + 2] * WV[r + 2]; }
+            t += (r0 + r1) + r2;
+        }
         if (!isvar) t = 0.0;
-        for (int k = 0; k < NV; k++) {
-            const double tk = __shfl_sync(FULL, t * dinv, k);
-            if (lane > k && isvar) t -= KS[lane * LD + k] * tk;
-            if (lane == k) t = tk;
+        XT[lane] = t;
+        __syncwarp();
+        { // L^-1 rhs, then L^-T of that
+            double u0 = dinv * t, u1 = 0.0;
+            if (isvar) {
+                int k = 0;
+                for (; k + 1 < lane; k += 2) { u0 += KS[k * LD + lane] * XT[k]; u1 += KS[(k + 1) * LD + lane] * XT[k + 1]; }
+                if (k < lane) u0 += KS[k * LD + lane] * XT[k];
+            }
+            const double tf = isvar ? u0 + u1 : 0.0;
+            ET[lane] = tf;
+            __syncwarp();
+            double v0 = dinv * tf, v1 = 0.0;
+            if (isvar) {
+                int k = lane + 1;
+                for (; k + 1 < NV; k += 2) { v0 += KS[lane * LD + k] * ET[k]; v1 += KS[lane * LD + k + 1] * ET[k + 1]; }
+                if (k < NV) v0 += KS[lane * LD + k] * ET[k];
+            }
+            t = isvar ? v0 + v1 : 0.0;
         }
-        for (int k = NV - 1; k >= 0; k--) {
-            const double xk = __shfl_sync(FULL, t * dinv, k);
-            if (lane < k) t -= KS[k * LD + lane] * xk;
-            if (lane == k) t = xk;
-        }
+        __syncwarp();
         XT[lane] = t; // x~
         __syncwarp();
         double zt_t = 0.0; // z~ = A x~ (zero on the velocity rows)
-        if (isrow)
-            for (int k = 0; k < NV; k++) zt_t += AS[lane * LD + k] * XT[k];
+        if (isrow) zt_t = osqp_dot<NV, 1>(AS + lane * LD, XT);
         // update_x, update_z, update_y
         x = alpha * t + (1.0 - alpha) * x_prev;
         dx = x - x_prev;
