@@ -426,23 +426,29 @@ __global__ void __launch_bounds__(kOsqpWarps * 32) ik_osqp_kernel(IkDev d, IkTic
         if (!isvar) t = 0.0;
         XT[lane] = t;
         __syncwarp();
-        { // L^-1 rhs, then L^-T of that
-            double u0 = dinv * t, u1 = 0.0;
-            if (isvar) {
-                int k = 0;
-                for (; k + 1 < lane; k += 2) { u0 += KS[k * LD + lane] * XT[k]; u1 += KS[(k + 1) * LD + lane] * XT[k + 1]; }
-                if (k < lane) u0 += KS[k * LD + lane] * XT[k];
+        { // L^-1 rhs, then L^-T of that: uniform, fully unrolled, predicated on the triangle (no per-lane trip counts)
+            double u0 = dinv * t, u1 = 0.0, u2 = 0.0, u3 = 0.0;
+            const double* xc = KS + lane; // X[lane][k] at KS[k * LD + lane], k < lane
+#pragma unroll
+            for (int k = 0; k + 3 < NV - 1; k += 4) {
+                u0 += (k < lane ? xc[k * LD] : 0.0) * XT[k]; u1 += (k + 1 < lane ? xc[(k + 1) * LD] : 0.0) * XT[k + 1];
+                u2 += (k + 2 < lane ? xc[(k + 2) * LD] : 0.0) * XT[k + 2]; u3 += (k + 3 < lane ? xc[(k + 3) * LD] : 0.0) * XT[k + 3];
             }
-            const double tf = isvar ? u0 + u1 : 0.0;
+#pragma unroll
+            for (int k = (NV - 1) - (NV - 1) % 4; k < NV - 1; k++) u0 += (k < lane ? xc[k * LD] : 0.0) * XT[k];
+            const double tf = isvar ? (u0 + u1) + (u2 + u3) : 0.0;
             ET[lane] = tf;
             __syncwarp();
-            double v0 = dinv * tf, v1 = 0.0;
-            if (isvar) {
-                int k = lane + 1;
-                for (; k + 1 < NV; k += 2) { v0 += KS[lane * LD + k] * ET[k]; v1 += KS[lane * LD + k + 1] * ET[k + 1]; }
-                if (k < NV) v0 += KS[lane * LD + k] * ET[k];
+            double v0 = dinv * tf, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+            const double* xr = KS + (isvar ? lane : 0) * LD; // X[k][lane] at KS[lane * LD + k], k > lane
+#pragma unroll
+            for (int k = 1; k + 3 < NV; k += 4) {
+                v0 += (k > lane ? xr[k] : 0.0) * ET[k]; v1 += (k + 1 > lane ? xr[k + 1] : 0.0) * ET[k + 1];
+                v2 += (k + 2 > lane ? xr[k + 2] : 0.0) * ET[k + 2]; v3 += (k + 3 > lane ? xr[k + 3] : 0.0) * ET[k + 3];
             }
-            t = isvar ? v0 + v1 : 0.0;
+#pragma unroll
+            for (int k = 1 + ((NV - 1) / 4) * 4; k < NV; k++) v0 += (k > lane ? xr[k] : 0.0) * ET[k];
+            t = isvar ? (v0 + v1) + (v2 + v3) : 0.0;
         }
         __syncwarp();
         XT[lane] = t; // x~
