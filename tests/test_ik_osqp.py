@@ -159,3 +159,87 @@ def test_ik_osqp_gpu_external_jacobians_and_reset(wc, oracle, syn, cuda_device):
     torch.cuda.synchronize()
     assert np.array_equal(oq["status"].cpu().numpy(), ref["status"]) and np.abs(oq["dq"].cpu().numpy() - ref["dq"]).max() <= 1e-8
     ik.close()
+
+
+def _ext_kin_pair(wc, oracle, syn, cuda_device, B, seed, settings_o=None, settings_g=None, mutate=None):
+    """one tick of both sides on caller-supplied (possibly doctored) kinematics"""
+    cfg_o, model_o = oracle.ik_default_config(), oracle.model_icub_like()
+    ino = _inputs(syn, oracle, B, seed)
+    kin = oracle.fk_batch(model_o, ino["q_lin"], ino["base_H"], ino["left_is_fixed"])
+    if mutate:
+        mutate(kin, ino)
+    out_o = dict(status=np.zeros(B, np.int32), iters=np.zeros(B, np.int32), flags=np.zeros(B, np.int32), dq=np.zeros((23, B)))
+    for i in range(B):
+        col = lambda a: np.ascontiguousarray(a[:, i])
+        L = oracle.lib()
+        h = L.wco_ikosqp_create
+        h.argtypes = [__import__("ctypes").c_void_p, __import__("ctypes").c_void_p]; h.restype = __import__("ctypes").c_void_p
+        C = __import__("ctypes")
+        obj = L.wco_ikosqp_create(C.byref(cfg_o), None if settings_o is None else C.byref(settings_o))
+        dp = C.POINTER(C.c_double)
+        L.wco_ikosqp_solve.argtypes = [C.c_void_p] + [dp] * 16 + [dp] * 3 + [C.POINTER(C.c_int)] * 3
+        L.wco_ikosqp_free.argtypes = [C.c_void_p]
+        args = [col(ino["q_meas"]), col(kin["lf_H"]), col(kin["rf_H"]), col(kin["neck_R"]), col(ino["com_meas"]), col(kin["J_lf"]),
+                col(kin["J_rf"]), col(kin["J_neck"]), col(kin["J_com"]), col(ino["lf_H_des"]), col(ino["rf_H_des"]), col(ino["lf_twist"]),
+                col(ino["rf_twist"]), col(ino["com_pos_des"]), col(ino["com_vel_des"]), col(ino["neck_R_des"])]
+        dq = np.zeros(23); le = np.zeros(6); re = np.zeros(6)
+        st, it, fl = C.c_int(0), C.c_int(0), C.c_int(0)
+        L.wco_ikosqp_solve(obj, *[a.ctypes.data_as(dp) for a in args], dq.ctypes.data_as(dp), le.ctypes.data_as(dp),
+                           re.ctypes.data_as(dp), C.byref(st), C.byref(it), C.byref(fl))
+        L.wco_ikosqp_free(obj)
+        out_o["status"][i], out_o["iters"][i], out_o["flags"][i] = st.value, it.value, fl.value
+        out_o["dq"][:, i] = dq
+    ik = wc.IkBatch(wc.ik_default_config(), wc.model_icub_like(), B)
+    ik.set_solver(wc.SOLVER_OSQP, settings_g)
+    flags = torch.zeros(B, dtype=torch.int32, device=cuda_device)
+    ik.osqp_outputs(flags, None)
+    og = ik.solve_with_jacobians({k: torch.from_numpy(np.ascontiguousarray(v)).to(cuda_device) for k, v in kin.items()},
+                                 {k: torch.from_numpy(np.ascontiguousarray(v)).to(cuda_device) for k, v in ino.items()})
+    torch.cuda.synchronize()
+    out_g = dict(status=og["status"].cpu().numpy(), iters=og["nwsr"].cpu().numpy(), flags=flags.cpu().numpy(), dq=og["dq"].cpu().numpy())
+    ik.close()
+    return out_o, out_g
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rho0", [1e-4, 50.0])
+def test_ik_osqp_gpu_adaptive_rho(wc, oracle, syn, cuda_device, rho0):
+    """a badly chosen initial rho with the rho update every 10 iterations: the estimate moves rho by more than the 5x tolerance,
+    so the re-factorisation path (new K, Cholesky, L^-1 inside the loop) runs; checks every 5 iterations, eps 1e-8"""
+    def settings(mod):
+        c = mod.mpc_default_config(25)
+        s = c.osqp
+        s.eps_abs = 1e-8; s.eps_rel = 1e-8; s.check_termination = 5; s.adaptive_rho_interval = 10; s.rho = rho0
+        return c, s
+    (co, so), (cg, sg) = settings(oracle), settings(wc)
+    o, g = _ext_kin_pair(wc, oracle, syn, cuda_device, 48, 21, so, sg)
+    co2, so2 = settings(oracle); so2.adaptive_rho = 0
+    o_fixed, _ = _ext_kin_pair(wc, oracle, syn, cuda_device, 4, 21, so2, sg)
+    assert not np.array_equal(o_fixed["iters"], o["iters"][:4]), "rho was never updated: the test does not reach the path it is for"
+    assert (o["status"] == 1).all()
+    assert np.array_equal(g["status"], o["status"]) and np.array_equal(g["iters"], o["iters"]) and np.array_equal(g["flags"], o["flags"])
+    assert np.abs(g["dq"] - o["dq"]).max() <= 1e-8
+
+
+@pytest.mark.gpu
+def test_ik_osqp_gpu_max_iter_and_inaccurate(wc, oracle, syn, cuda_device):
+    """max_iter below the first termination check: OSQP_MAX_ITER_REACHED or SOLVED_INACCURATE, decided by the 10x tolerances"""
+    so, sg = oracle.mpc_default_config(25).osqp, wc.mpc_default_config(25).osqp
+    for s in (so, sg):
+        s.max_iter = 7; s.eps_abs = 1e-6; s.eps_rel = 1e-6
+    o, g = _ext_kin_pair(wc, oracle, syn, cuda_device, 48, 22, so, sg)
+    assert set(np.unique(o["status"])) <= {2, -2} and (o["iters"] == 7).all()
+    assert np.array_equal(g["status"], o["status"]) and np.array_equal(g["iters"], o["iters"])
+    assert np.abs(g["dq"] - o["dq"]).max() <= 1e-6
+
+
+@pytest.mark.gpu
+def test_ik_osqp_gpu_primal_infeasible(wc, oracle, syn, cuda_device):
+    """identical feet Jacobians with different right-hand sides: contradictory equality rows -> OSQP_PRIMAL_INFEASIBLE"""
+    def mutate(kin, ino):
+        kin["J_rf"] = kin["J_lf"].copy()
+        ino["rf_twist"] = ino["lf_twist"] + 1.0
+    o, g = _ext_kin_pair(wc, oracle, syn, cuda_device, 32, 23, mutate=mutate)
+    assert (o["status"] == -3).all(), np.unique(o["status"])
+    assert np.array_equal(g["status"], o["status"]) and np.array_equal(g["iters"], o["iters"]) and np.array_equal(g["flags"], o["flags"])
+    assert np.isnan(g["dq"]).all() and np.isnan(o["dq"]).all()
