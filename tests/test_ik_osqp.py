@@ -202,20 +202,20 @@ def _ext_kin_pair(wc, oracle, syn, cuda_device, B, seed, settings_o=None, settin
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("rho0", [1e-4, 50.0])
-def test_ik_osqp_gpu_adaptive_rho(wc, oracle, syn, cuda_device, rho0):
-    """a badly chosen initial rho with the rho update every 10 iterations: the estimate moves rho by more than the 5x tolerance,
-    so the re-factorisation path (new K, Cholesky, L^-1 inside the loop) runs; checks every 5 iterations, eps 1e-8"""
+def test_ik_osqp_gpu_adaptive_rho(wc, oracle, syn, cuda_device, rho0=1e-4):
+    """a badly chosen initial rho (1e-4) with the rho update every 10 iterations: the estimate moves rho by far more than the 5x
+    tolerance, so the re-factorisation path (new K, Cholesky, L^-1 inside the loop) runs — with it OSQP needs ~30 iterations,
+    without it > 1000; checks every 5 iterations, eps 1e-5 (well above the 1e-10 noise between the two linear-system methods)"""
     def settings(mod):
         c = mod.mpc_default_config(25)
         s = c.osqp
-        s.eps_abs = 1e-8; s.eps_rel = 1e-8; s.check_termination = 5; s.adaptive_rho_interval = 10; s.rho = rho0
+        s.eps_abs = 1e-5; s.eps_rel = 1e-5; s.check_termination = 5; s.adaptive_rho_interval = 10; s.rho = rho0
         return c, s
     (co, so), (cg, sg) = settings(oracle), settings(wc)
     o, g = _ext_kin_pair(wc, oracle, syn, cuda_device, 48, 21, so, sg)
     co2, so2 = settings(oracle); so2.adaptive_rho = 0
     o_fixed, _ = _ext_kin_pair(wc, oracle, syn, cuda_device, 4, 21, so2, sg)
-    assert not np.array_equal(o_fixed["iters"], o["iters"][:4]), "rho was never updated: the test does not reach the path it is for"
+    assert (o_fixed["iters"] > 10 * o["iters"][:4]).all(), "rho was never updated: the test does not reach the path it is for"
     assert (o["status"] == 1).all()
     assert np.array_equal(g["status"], o["status"]) and np.array_equal(g["iters"], o["iters"]) and np.array_equal(g["flags"], o["flags"])
     assert np.abs(g["dq"] - o["dq"]).max() <= 1e-8
