@@ -432,6 +432,17 @@ wc_status wc_glue_reactive_dcm_host(wc_glue* h, double k_dcm_const, const double
                                     const double* dcm_vel_des, const double* dcm_meas, double* zmp_des);
 /* WalkingFK::evaluateDCM, unfiltered branch (WalkingForwardKinematics.cpp:312-340): com, com_vel [>=2*B] -> dcm [2*B]. */
 wc_status wc_glue_evaluate_dcm_dev(wc_glue* h, const double* com, const double* com_vel, double* dcm, void* stream);
+/* WalkingFK::evaluateCoM + evaluateDCM with the joint velocities (WalkingForwardKinematics.cpp:278-340; the measured DCM that
+ * WalkingController::setFeedback receives, WalkingModule.cpp:559-570): com [3*B] and J_com [3*(nJ+6)*B] from wc_fk_*, dq [nJ*B]
+ * measured joint velocities; CoM velocity = J_com [0; dq] (zero base twist, :258-276).  cut_frequency > 0 runs the two
+ * first-order low-pass filters of WalkingFK (iCub::ctrl::FirstOrderLowPassFilter, external, restated; state in the handle,
+ * wc_glue_reset_com_filter_dev = their init at (0, 0, com_height) / 0, :153-160); use_filters selects the filtered pair for the
+ * outputs (`use_filters` of forwardKinematics.ini).  Outputs may be NULL: com_out, com_vel_out [3*B], dcm_out [2*B]. */
+wc_status wc_glue_evaluate_com_dev(wc_glue* h, const double* com, const double* J_com, const double* dq, double cut_frequency,
+                                   int32_t use_filters, double* com_out, double* com_vel_out, double* dcm_out, void* stream);
+wc_status wc_glue_evaluate_com_host(wc_glue* h, const double* com, const double* J_com, const double* dq, double cut_frequency,
+                                    int32_t use_filters, double* com_out, double* com_vel_out, double* dcm_out);
+wc_status wc_glue_reset_com_filter_dev(wc_glue* h, void* stream);
 /* WalkingModule::evaluateZMP (WalkingModule.cpp:824-876): l_wrench, r_wrench [6*B] (force then torque, foot frame),
  * lf_H, rf_H [12*B] -> zmp [2*B]; ok [B] (may be NULL) = 0 where the reference returns false (total fz < 0.1). */
 wc_status wc_glue_evaluate_zmp_dev(wc_glue* h, const double* l_wrench, const double* r_wrench, const double* lf_H,

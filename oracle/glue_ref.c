@@ -28,6 +28,7 @@ struct wco_glue {
     int B;
     double omega;
     double *lipm_c, *lipm_v, *zc_y, *zc_v, *q_y, *q_v;
+    double* cf; /* [12][B] CoM filters of WalkingFK: position y, u_old, velocity y, u_old */
 };
 
 wco_glue* wco_glue_create(const wc_glue_config* cfg, int B)
@@ -38,13 +39,15 @@ wco_glue* wco_glue_create(const wc_glue_config* cfg, int B)
     g->lipm_c = (double*)calloc(n2, sizeof(double)); g->lipm_v = (double*)calloc(n2, sizeof(double));
     g->zc_y = (double*)calloc(n2, sizeof(double)); g->zc_v = (double*)calloc(n2, sizeof(double));
     g->q_y = (double*)calloc(nq, sizeof(double)); g->q_v = (double*)calloc(nq, sizeof(double));
+    g->cf = (double*)calloc(12 * (size_t)B, sizeof(double));
+    for (int i = 0; i < B; i++) { g->cf[2 * (size_t)B + i] = cfg->com_height; g->cf[5 * (size_t)B + i] = cfg->com_height; }
     return g;
 }
 
 void wco_glue_free(wco_glue* g)
 {
     if (!g) return;
-    free(g->lipm_c); free(g->lipm_v); free(g->zc_y); free(g->zc_v); free(g->q_y); free(g->q_v); free(g);
+    free(g->lipm_c); free(g->lipm_v); free(g->zc_y); free(g->zc_v); free(g->q_y); free(g->q_v); free(g->cf); free(g);
 }
 
 /* Integrator::reset for the three integrators (WalkingModule.cpp:470-471) */
@@ -170,5 +173,46 @@ void wco_log_pack(int B, const wc_log_inputs* in, double* out)
 #undef PUT
 #undef PUTN
 #undef PUTPOSE
+    }
+}
+
+/* WalkingFK::evaluateCoM / evaluateDCM (WalkingForwardKinematics.cpp:278-340) with iCub::ctrl::FirstOrderLowPassFilter (external
+ * ctrlLib, filters.cpp: num = [Ts, Ts], den = [2 tau + Ts, Ts - 2 tau], tau = 1 / (2 pi fc); init(y0): y = y0, u_old = y0) */
+void wco_glue_reset_com_filter(wco_glue* g)
+{
+    const size_t B = (size_t)g->B;
+    memset(g->cf, 0, 12 * B * sizeof(double));
+    for (size_t i = 0; i < B; i++) { g->cf[2 * B + i] = g->cfg.com_height; g->cf[5 * B + i] = g->cfg.com_height; }
+}
+
+void wco_glue_evaluate_com(wco_glue* g, const double* com, const double* J_com, const double* dq, double cut_frequency,
+                           int use_filters, double* com_out, double* vel_out, double* dcm_out)
+{
+    const size_t B = (size_t)g->B;
+    const int nJ = g->cfg.n_dofs, nV = nJ + 6;
+    const double Ts = g->cfg.sampling_time;
+    const int filt = cut_frequency > 0.0;
+    double fa = 0.0, fb = 0.0;
+    if (filt) {
+        const double tau = 1.0 / (2.0 * M_PI * cut_frequency);
+        fa = (Ts - 2.0 * tau) / (2.0 * tau + Ts); fb = Ts / (2.0 * tau + Ts);
+    }
+    for (size_t i = 0; i < B; i++) {
+        double c[3], v[3] = {0, 0, 0}, cfil[3], vfil[3];
+        for (int r = 0; r < 3; r++) c[r] = com[r * B + i];
+        for (int j = 0; j < nJ; j++)
+            for (int r = 0; r < 3; r++) v[r] += J_com[(size_t)(r * nV + 6 + j) * B + i] * dq[(size_t)j * B + i];
+        for (int r = 0; r < 3; r++) {
+            cfil[r] = c[r]; vfil[r] = v[r];
+            if (filt) {
+                double *py = g->cf + r * B + i, *pu = g->cf + (3 + r) * B + i, *vy = g->cf + (6 + r) * B + i, *vu = g->cf + (9 + r) * B + i;
+                cfil[r] = (fb * (c[r] + *pu) - fa * *py); *py = cfil[r]; *pu = c[r];
+                vfil[r] = (fb * (v[r] + *vu) - fa * *vy); *vy = vfil[r]; *vu = v[r];
+            }
+        }
+        const double* co = (filt && use_filters) ? cfil : c;
+        const double* vo = (filt && use_filters) ? vfil : v;
+        for (int r = 0; r < 3; r++) { if (com_out) com_out[r * B + i] = co[r]; if (vel_out) vel_out[r * B + i] = vo[r]; }
+        if (dcm_out) { dcm_out[i] = co[0] + vo[0] / g->omega; dcm_out[B + i] = co[1] + vo[1] / g->omega; }
     }
 }

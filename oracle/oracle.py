@@ -383,6 +383,19 @@ class GlueBatch:
         self.L.wco_glue_integrate_joints(self.h, _dp(dq), _dp(out))
         return out
 
+    def reset_com_filter(self):
+        self.L.wco_glue_reset_com_filter.argtypes = [C.c_void_p]
+        self.L.wco_glue_reset_com_filter(self.h)
+
+    def evaluate_com(self, com, J_com, dq, cut_frequency=0.0, use_filters=False):
+        """WalkingFK::evaluateCoM + evaluateDCM -> dict(com, com_vel [3,B], dcm [2,B])"""
+        dp = C.POINTER(C.c_double)
+        self.L.wco_glue_evaluate_com.argtypes = [C.c_void_p, dp, dp, dp, C.c_double, C.c_int, dp, dp, dp]
+        a, b, c = _f64(com), _f64(J_com), _f64(dq)
+        o = dict(com=np.zeros((3, self.B)), com_vel=np.zeros((3, self.B)), dcm=np.zeros((2, self.B)))
+        self.L.wco_glue_evaluate_com(self.h, _dp(a), _dp(b), _dp(c), cut_frequency, int(use_filters), _dp(o["com"]), _dp(o["com_vel"]), _dp(o["dcm"]))
+        return o
+
 
 # ---- rank 4: WalkingDCMReactiveController, evaluateDCM, evaluateZMP, logger row ---------------------------------
 LOG_COLUMNS = 53

@@ -103,6 +103,9 @@ void wco_reactive_dcm(int B, double omega, double k_const, const double* k_dcm, 
 void wco_evaluate_dcm(int B, double omega, const double* com, const double* com_vel, double* dcm);
 void wco_evaluate_zmp(int B, const double* lw, const double* rw, const double* lf_H, const double* rf_H, double* zmp, int* ok);
 void wco_log_pack(int B, const wc_log_inputs* in, double* out);
+void wco_glue_reset_com_filter(wco_glue* g);
+void wco_glue_evaluate_com(wco_glue* g, const double* com, const double* J_com, const double* dq, double cut_frequency,
+                           int use_filters, double* com_out, double* vel_out, double* dcm_out);
 
 /* ---- rank 2: WalkingQPIK_osqp (qpik_osqp_ref.c) ---- */
 void wco_ik_build_qp(const wc_ik_config* cfg, int variant,

@@ -132,3 +132,53 @@ def test_rank4_gpu_parity(wc, oracle, cuda_device):
     rg = gg.log_pack(dcm=d(x)).cpu().numpy()
     assert np.array_equal(rg[:2], x) and not rg[2:].any()
     gg.close()
+
+
+def test_evaluate_com_filters_closed_form(oracle):
+    """CoM velocity = J_com [0; dq]; the low-pass filters have unit DC gain, start at (0, 0, com_height) / 0 and follow the
+    bilinear-transform recurrence; use_filters only selects the outputs (the filter state advances either way)"""
+    rng = np.random.default_rng(4)
+    B, nJ, nV = 6, 23, 29
+    cfg = oracle.glue_default_config()
+    g = oracle.GlueBatch(cfg, B)
+    omega = math.sqrt(cfg.gravity / cfg.com_height)
+    J = rng.normal(size=(3 * nV, B)); dq = rng.normal(size=(nJ, B)); com = rng.normal(size=(3, B)) * 0.1 + np.array([[0.0], [0.0], [0.5]])
+    o = g.evaluate_com(com, J, dq)
+    v = np.einsum("rjb,jb->rb", J.reshape(3, nV, B)[:, 6:], dq)
+    assert np.allclose(o["com_vel"], v, rtol=1e-13, atol=1e-14) and np.array_equal(o["com"], com)
+    assert np.allclose(o["dcm"], (com + v / omega)[:2], rtol=1e-13, atol=1e-14)
+    fc, Ts = 10.0, cfg.sampling_time
+    tau = 1 / (2 * math.pi * fc)
+    y = np.zeros((3, B)); y[2] = cfg.com_height; u = y.copy(); yv = np.zeros((3, B)); uv = np.zeros((3, B))
+    g.reset_com_filter()
+    for k in range(60):
+        o = g.evaluate_com(com, J, dq, cut_frequency=fc, use_filters=True)
+        y = (Ts * (com + u) - (Ts - 2 * tau) * y) / (2 * tau + Ts); u = com
+        yv = (Ts * (v + uv) - (Ts - 2 * tau) * yv) / (2 * tau + Ts); uv = v
+        assert np.allclose(o["com"], y, rtol=1e-12, atol=1e-13) and np.allclose(o["com_vel"], yv, rtol=1e-12, atol=1e-13)
+    assert np.abs(o["com"] - com).max() < 0.05 * np.abs(com - np.array([[0], [0], [cfg.com_height]])).max() + 1e-6   # settles on the input (DC gain 1)
+    raw = g.evaluate_com(com, J, dq, cut_frequency=fc, use_filters=False)
+    assert np.array_equal(raw["com"], com)
+
+
+@pytest.mark.gpu
+def test_evaluate_com_gpu_parity(wc, oracle, cuda_device):
+    rng = np.random.default_rng(5)
+    B, nJ, nV = 2000, 23, 29
+    d = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(cuda_device)
+    go = oracle.GlueBatch(oracle.glue_default_config(), B); gg = wc.GlueBatch(wc.glue_default_config(), B)
+    for k in range(12):
+        J = rng.normal(size=(3 * nV, B)); dq = rng.normal(size=(nJ, B)); com = rng.normal(size=(3, B)) * 0.1
+        if k == 6:
+            go.reset_com_filter(); gg.reset_com_filter()
+        fc, uf = (10.0, True) if k % 3 else ((0.0, False) if k % 2 else (10.0, False))
+        oo = go.evaluate_com(com, J, dq, fc, uf); og = gg.evaluate_com(d(com), d(J), d(dq), fc, uf)
+        for key in ("com", "com_vel", "dcm"):
+            assert np.abs(og[key].cpu().numpy() - oo[key]).max() <= 1e-12, (k, key)
+    g1 = wc.GlueBatch(wc.glue_default_config(), 1)
+    co, vo, do = np.zeros((3, 1)), np.zeros((3, 1)), np.zeros((2, 1))
+    J1, dq1, c1 = np.ascontiguousarray(J[:, :1]), np.ascontiguousarray(dq[:, :1]), np.ascontiguousarray(com[:, :1])
+    st = wc.lib().wc_glue_evaluate_com_host(g1.h, c1.ctypes.data, J1.ctypes.data, dq1.ctypes.data, 0.0, 0, co.ctypes.data, vo.ctypes.data, do.ctypes.data)
+    ref = oracle.GlueBatch(oracle.glue_default_config(), 1).evaluate_com(c1, J1, dq1)
+    assert st == 0 and np.abs(vo - ref["com_vel"]).max() <= 1e-12 and np.abs(do - ref["dcm"]).max() <= 1e-12
+    g1.close(); gg.close()

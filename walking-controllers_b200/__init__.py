@@ -187,6 +187,9 @@ def lib():
     L.wc_glue_reactive_dcm_dev.argtypes = [_VP, C.c_double] + [_VP] * 6; L.wc_glue_reactive_dcm_dev.restype = i32
     L.wc_glue_reactive_dcm_host.argtypes = [_VP, C.c_double] + [_VP] * 5; L.wc_glue_reactive_dcm_host.restype = i32
     L.wc_glue_evaluate_dcm_dev.argtypes = [_VP] * 5; L.wc_glue_evaluate_dcm_dev.restype = i32
+    L.wc_glue_evaluate_com_dev.argtypes = [_VP, _VP, _VP, _VP, C.c_double, i32, _VP, _VP, _VP, _VP]; L.wc_glue_evaluate_com_dev.restype = i32
+    L.wc_glue_evaluate_com_host.argtypes = [_VP, _VP, _VP, _VP, C.c_double, i32, _VP, _VP, _VP]; L.wc_glue_evaluate_com_host.restype = i32
+    L.wc_glue_reset_com_filter_dev.argtypes = [_VP, _VP]; L.wc_glue_reset_com_filter_dev.restype = i32
     L.wc_glue_evaluate_zmp_dev.argtypes = [_VP] * 8; L.wc_glue_evaluate_zmp_dev.restype = i32
     L.wc_glue_log_pack_dev.argtypes = [_VP, C.POINTER(LogInputs), _VP, _VP]; L.wc_glue_log_pack_dev.restype = i32
     L.wc_measure_fp64_peak.argtypes = [i32, C.POINTER(C.c_double)]; L.wc_measure_fp64_peak.restype = i32
@@ -562,6 +565,21 @@ class GlueBatch:
         _check(lib().wc_glue_evaluate_dcm_dev(self.h, _ptr(com), _ptr(com_vel), _ptr(out), self._stream(stream)),
                "wc_glue_evaluate_dcm_dev")
         return out
+
+    def reset_com_filter(self, stream=None):
+        _check(lib().wc_glue_reset_com_filter_dev(self.h, self._stream(stream)), "wc_glue_reset_com_filter_dev")
+
+    def evaluate_com(self, com, J_com, dq, cut_frequency=0.0, use_filters=False, stream=None):
+        """WalkingFK::evaluateCoM + evaluateDCM: CoM velocity from the CoM Jacobian and the joint velocities, the two
+        low-pass filters, the measured DCM -> dict(com, com_vel [3,B], dcm [2,B])"""
+        import torch
+        o = dict(com=torch.empty(3, self.B, dtype=torch.float64, device=com.device),
+                 com_vel=torch.empty(3, self.B, dtype=torch.float64, device=com.device),
+                 dcm=torch.empty(2, self.B, dtype=torch.float64, device=com.device))
+        _check(lib().wc_glue_evaluate_com_dev(self.h, _ptr(com), _ptr(J_com), _ptr(dq), float(cut_frequency), int(use_filters),
+                                              _ptr(o["com"]), _ptr(o["com_vel"]), _ptr(o["dcm"]), self._stream(stream)),
+               "wc_glue_evaluate_com_dev")
+        return o
 
     def evaluate_zmp(self, l_wrench, r_wrench, lf_H, rf_H, stream=None):
         import torch

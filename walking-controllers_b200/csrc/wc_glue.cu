@@ -31,6 +31,7 @@ struct wc_glue {
     double* zc_v;     // [2][B] its x_old
     double* q_y;      // [nJ][B] joint integrator output (m_qDesired)
     double* q_v;      // [nJ][B] its x_old
+    double* cf;       // [12][B] WalkingFK's CoM filters: position y, u_old; velocity y, u_old (3 rows each)
     int64_t launches;
 };
 
@@ -190,6 +191,57 @@ __global__ void glue_log_pack_kernel(int B, wc_log_inputs in, double* out)
     put_n(in.lf_err, 6); put_n(in.rf_err, 6);
 }
 
+// WalkingFK::evaluateCoM + evaluateDCM (WalkingForwardKinematics.cpp:278-340): CoM velocity = J_com [0 ; dq] (the base is the
+// fixed stance foot: setInternalRobotState passes a zero base twist, :258-276), both signals through
+// iCub::ctrl::FirstOrderLowPassFilter (external ctrlLib, restated: bilinear transform of 1 / (1 + s / (2 pi fc)),
+// y_k = (Ts (u_k + u_{k-1}) - (Ts - 2 tau) y_{k-1}) / (2 tau + Ts), tau = 1 / (2 pi fc)), DCM = xy of com + com_vel / omega
+// from the filtered or the raw pair (m_useFilters).
+__global__ void glue_evaluate_com_kernel(int B, int nJ, double omega, double fa, double fb, int filt, int use_filters,
+                                         const double* com, const double* J_com, const double* dq, double* cf,
+                                         double* com_out, double* vel_out, double* dcm_out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    const size_t Bz = (size_t)B;
+    const int nV = nJ + 6;
+    double c[3], v[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int r = 0; r < 3; r++) c[r] = com[r * Bz + i];
+    for (int j = 0; j < nJ; j++) {
+        const double d = dq[j * Bz + i];
+#pragma unroll
+        for (int r = 0; r < 3; r++) v[r] += J_com[(size_t)(r * nV + 6 + j) * Bz + i] * d;
+    }
+    double cfil[3], vfil[3];
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+        cfil[r] = c[r]; vfil[r] = v[r];
+        if (filt) {
+            double* py = cf + (size_t)r * Bz + i; double* pu = cf + (size_t)(3 + r) * Bz + i;
+            double* vy = cf + (size_t)(6 + r) * Bz + i; double* vu = cf + (size_t)(9 + r) * Bz + i;
+            cfil[r] = (fb * (c[r] + *pu) - fa * *py); *py = cfil[r]; *pu = c[r];
+            vfil[r] = (fb * (v[r] + *vu) - fa * *vy); *vy = vfil[r]; *vu = v[r];
+        }
+    }
+    const double* co = (filt && use_filters) ? cfil : c;
+    const double* vo = (filt && use_filters) ? vfil : v;
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+        if (com_out) com_out[r * Bz + i] = co[r];
+        if (vel_out) vel_out[r * Bz + i] = vo[r];
+    }
+    if (dcm_out) { dcm_out[i] = co[0] + vo[0] / omega; dcm_out[Bz + i] = co[1] + vo[1] / omega; }
+}
+
+__global__ void glue_reset_com_filter_kernel(int B, double com_height, double* cf)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    const size_t Bz = (size_t)B;
+    for (int r = 0; r < 12; r++) cf[(size_t)r * Bz + i] = 0.0;
+    cf[2 * Bz + i] = com_height; cf[5 * Bz + i] = com_height; // y = u_old = (0, 0, com_height): Filter::init at steady state
+}
+
 } // namespace
 
 extern "C" {
@@ -209,11 +261,13 @@ wc_status wc_glue_create(const wc_glue_config* cfg, int32_t B, int32_t device, w
     h->omega = std::sqrt(cfg->gravity / cfg->com_height);
     const size_t Bz = (size_t)B, nJ = (size_t)cfg->n_dofs;
     double* base = nullptr;
-    const size_t total = (8 + 2 * nJ) * Bz;
+    const size_t total = (8 + 2 * nJ + 12) * Bz;
     if (cudaMalloc(&base, total * sizeof(double)) != cudaSuccess) { delete h; return WC_ERR_ALLOC; }
     cudaMemset(base, 0, total * sizeof(double));
     h->lipm_c = base; h->lipm_v = base + 2 * Bz; h->zc_y = base + 4 * Bz; h->zc_v = base + 6 * Bz;
-    h->q_y = base + 8 * Bz; h->q_v = h->q_y + nJ * Bz;
+    h->q_y = base + 8 * Bz; h->q_v = h->q_y + nJ * Bz; h->cf = h->q_v + nJ * Bz;
+    glue_reset_com_filter_kernel<<<(B + 127) / 128, 128>>>(B, cfg->com_height, h->cf); // the filters' init of WalkingFK::initialize
+    if (cudaDeviceSynchronize() != cudaSuccess) { cudaFree(base); delete h; return WC_ERR_CUDA; }
     *out = h;
     return WC_OK;
 }
@@ -318,6 +372,53 @@ wc_status wc_glue_reactive_dcm_host(wc_glue* h, double k_dcm_const, const double
     if (k_dcm) cudaMemcpy(d + 8 * Bz, k_dcm, Bz * sizeof(double), cudaMemcpyHostToDevice);
     wc_status st = wc_glue_reactive_dcm_dev(h, k_dcm_const, k_dcm ? d + 8 * Bz : nullptr, d, d + 2 * Bz, d + 4 * Bz, d + 6 * Bz, nullptr);
     if (st == WC_OK && cudaMemcpy(zmp_des, d + 6 * Bz, 2 * Bz * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) st = WC_ERR_CUDA;
+    cudaFree(d);
+    return st;
+}
+
+wc_status wc_glue_reset_com_filter_dev(wc_glue* h, void* stream)
+{
+    if (!h) return WC_ERR_INVALID_ARG;
+    if (cudaSetDevice(h->device) != cudaSuccess) return WC_ERR_CUDA;
+    glue_reset_com_filter_kernel<<<(h->B + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(h->B, h->cfg.com_height, h->cf);
+    h->launches += 1;
+    return cudaGetLastError() == cudaSuccess ? WC_OK : WC_ERR_CUDA;
+}
+
+wc_status wc_glue_evaluate_com_dev(wc_glue* h, const double* com, const double* J_com, const double* dq, double cut_frequency,
+                                   int32_t use_filters, double* com_out, double* com_vel_out, double* dcm_out, void* stream)
+{
+    if (!h || !com || !J_com || !dq) return WC_ERR_INVALID_ARG;
+    if (cudaSetDevice(h->device) != cudaSuccess) return WC_ERR_CUDA;
+    const double Ts = h->cfg.sampling_time;
+    const int filt = cut_frequency > 0.0;
+    double fa = 0.0, fb = 0.0;
+    if (filt) {
+        const double tau = 1.0 / (2.0 * 3.14159265358979323846 * cut_frequency);
+        fa = (Ts - 2.0 * tau) / (2.0 * tau + Ts); fb = Ts / (2.0 * tau + Ts);
+    }
+    glue_evaluate_com_kernel<<<(h->B + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        h->B, h->cfg.n_dofs, h->omega, fa, fb, filt, use_filters, com, J_com, dq, h->cf, com_out, com_vel_out, dcm_out);
+    h->launches += 1;
+    return cudaGetLastError() == cudaSuccess ? WC_OK : WC_ERR_CUDA;
+}
+
+wc_status wc_glue_evaluate_com_host(wc_glue* h, const double* com, const double* J_com, const double* dq, double cut_frequency,
+                                    int32_t use_filters, double* com_out, double* com_vel_out, double* dcm_out)
+{
+    if (!h || !com || !J_com || !dq) return WC_ERR_INVALID_ARG;
+    if (cudaSetDevice(h->device) != cudaSuccess) return WC_ERR_CUDA;
+    const size_t Bz = (size_t)h->B, nJ = (size_t)h->cfg.n_dofs, nV = nJ + 6;
+    const size_t n_in = (3 + 3 * nV + nJ) * Bz;
+    double* d = nullptr;
+    if (cudaMalloc(&d, (n_in + 8 * Bz) * sizeof(double)) != cudaSuccess) return WC_ERR_ALLOC;
+    double* d_com = d; double* d_J = d + 3 * Bz; double* d_dq = d_J + 3 * nV * Bz; double* d_o = d + n_in;
+    cudaMemcpy(d_com, com, 3 * Bz * sizeof(double), cudaMemcpyHostToDevice);
+    cudaMemcpy(d_J, J_com, 3 * nV * Bz * sizeof(double), cudaMemcpyHostToDevice);
+    cudaMemcpy(d_dq, dq, nJ * Bz * sizeof(double), cudaMemcpyHostToDevice);
+    wc_status st = wc_glue_evaluate_com_dev(h, d_com, d_J, d_dq, cut_frequency, use_filters, d_o, d_o + 3 * Bz, d_o + 6 * Bz, nullptr);
+    auto back = [&](double* dst, const double* src, size_t n) { if (dst && st == WC_OK && cudaMemcpy(dst, src, n * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) st = WC_ERR_CUDA; };
+    back(com_out, d_o, 3 * Bz); back(com_vel_out, d_o + 3 * Bz, 3 * Bz); back(dcm_out, d_o + 6 * Bz, 2 * Bz);
     cudaFree(d);
     return st;
 }

@@ -3,7 +3,7 @@
 #include <cstring>
 #include <iostream>
 
-WalkingFK::~WalkingFK() { wc_ik_destroy(m_handle); }
+WalkingFK::~WalkingFK() { wc_ik_destroy(m_handle); wc_glue_destroy(m_glue); }
 
 bool WalkingFK::initialize(const yarp::os::Searchable& config, const wc_model& model)
 {
@@ -16,6 +16,18 @@ bool WalkingFK::initialize(const yarp::os::Searchable& config, const wc_model& m
     m_q.assign(m_nJ, 0.0); m_lfH.assign(12, 0.0); m_rfH.assign(12, 0.0); m_neckR.assign(9, 0.0); m_com.assign(3, 0.0);
     m_Jl.assign(6 * nV, 0.0); m_Jr.assign(6 * nV, 0.0); m_Jn.assign(6 * nV, 0.0); m_Jc.assign(3 * nV, 0.0);
     m_firstStep = true; m_prevContactLeft = false;
+    // CoM filters and the DCM (:131-162): sampling_time, com_height (omega), cut_frequency, use_filters
+    m_dq.assign(m_nJ, 0.0);
+    wc_glue_config gc; wc_glue_default_config(&gc);
+    gc.n_dofs = m_nJ;
+    gc.sampling_time = config.number("sampling_time", gc.sampling_time);
+    gc.com_height = config.number("com_height", gc.com_height);
+    gc.gravity = config.number("gravity_acceleration", 9.81);
+    m_cutFrequency = config.number("cut_frequency", 0.0);
+    m_useFilters = config.number("use_filters", 0.0) != 0.0;
+    wc_glue_destroy(m_glue); m_glue = nullptr;
+    if (wc_glue_create(&gc, 1, 0, &m_glue) != WC_OK) { std::cerr << "[initialize] Unable to create the CoM filters.\n"; return false; }
+    m_comEvaluated = m_dcmEvaluated = false;
     return true;
 }
 
@@ -31,10 +43,11 @@ bool WalkingFK::evaluateWorldToBaseTransformation(const iDynTree::Transform& lef
     return true;
 }
 
-bool WalkingFK::setInternalRobotState(const iDynTree::VectorDynSize& q, const iDynTree::VectorDynSize&)
+bool WalkingFK::setInternalRobotState(const iDynTree::VectorDynSize& q, const iDynTree::VectorDynSize& dq)
 {
     if (static_cast<int>(q.size()) != m_nJ) { std::cerr << "[setInternalRobotState] Error while updating the state.\n"; return false; }
     for (int i = 0; i < m_nJ; i++) m_q[i] = q(i);
+    for (int i = 0; i < m_nJ; i++) m_dq[i] = static_cast<int>(dq.size()) == m_nJ ? dq(i) : 0.0;
     m_firstStep = true; // as the reference (:273)
     m_evaluated = false;
     return true;
@@ -56,7 +69,47 @@ bool WalkingFK::evaluate()
 iDynTree::Transform WalkingFK::getLeftFootToWorldTransform() { evaluate(); return iDynTree::Transform::fromH12(m_lfH.data()); }
 iDynTree::Transform WalkingFK::getRightFootToWorldTransform() { evaluate(); return iDynTree::Transform::fromH12(m_rfH.data()); }
 iDynTree::Rotation WalkingFK::getNeckOrientation() { evaluate(); iDynTree::Rotation R; std::memcpy(R.data(), m_neckR.data(), 9 * sizeof(double)); return R; }
-bool WalkingFK::getCoMPosition(iDynTree::Position& c) { if (!evaluate()) return false; for (int k = 0; k < 3; k++) c(k) = m_com[k]; return true; }
+bool WalkingFK::getCoMPosition(iDynTree::Position& c)
+{
+    if (!evaluate()) return false;
+    for (int k = 0; k < 3; k++) c(k) = (m_comEvaluated && m_useFilters) ? m_comOut[k] : m_com[k];
+    return true;
+}
+
+bool WalkingFK::evaluateCoM()
+{
+    m_comEvaluated = false;
+    if (!evaluate() || !m_glue) { std::cerr << "[evaluateCoM] The KinDynComputations solver is not initialized.\n"; return false; }
+    if (wc_glue_evaluate_com_host(m_glue, m_com.data(), m_Jc.data(), m_dq.data(), m_cutFrequency, m_useFilters ? 1 : 0, m_comOut, m_comVel,
+                                  m_dcmOut) != WC_OK)
+        return false;
+    m_comEvaluated = true;
+    return true;
+}
+
+bool WalkingFK::evaluateDCM()
+{
+    m_dcmEvaluated = false;
+    if (!m_comEvaluated) {
+        std::cerr << "[evaluateDCM] The CoM position and velocity is not evaluated. Please call evaluateCoM method.\n"; return false;
+    }
+    m_dcmEvaluated = true; // the DCM of this CoM / CoM velocity pair was computed by the same device call
+    return true;
+}
+
+bool WalkingFK::getDCM(iDynTree::Vector2& dcm)
+{
+    if (!m_dcmEvaluated) { std::cerr << "[getDCM] The dcm is not evaluated. Please call evaluateDCM() method.\n"; return false; }
+    dcm(0) = m_dcmOut[0]; dcm(1) = m_dcmOut[1];
+    return true;
+}
+
+bool WalkingFK::getCoMVelocity(iDynTree::Vector3& v)
+{
+    if (!m_comEvaluated) { std::cerr << "[getCoMVelocity] The CoM is not evaluated. Please call evaluateCoM() method.\n"; return false; }
+    for (int k = 0; k < 3; k++) v(k) = m_comVel[k];
+    return true;
+}
 
 static bool copy_jac(const std::vector<double>& src, size_t rows, size_t cols, iDynTree::MatrixDynSize& J)
 {

@@ -16,7 +16,11 @@ class WalkingFK {
     iDynTree::Transform m_worldToBaseSole; // world_H_sole of the current stance foot
     bool m_prevContactLeft{false}, m_firstStep{true}, m_evaluated{false};
     int m_nJ{0};
-    std::vector<double> m_q, m_lfH, m_rfH, m_neckR, m_com, m_Jl, m_Jr, m_Jn, m_Jc;
+    std::vector<double> m_q, m_dq, m_lfH, m_rfH, m_neckR, m_com, m_Jl, m_Jr, m_Jn, m_Jc;
+    // evaluateCoM / evaluateDCM (WalkingForwardKinematics.cpp:278-340): CoM velocity, low-pass filters, measured DCM
+    wc_glue* m_glue{nullptr};
+    double m_cutFrequency{0.0}, m_comOut[3]{}, m_comVel[3]{}, m_dcmOut[2]{};
+    bool m_useFilters{false}, m_comEvaluated{false}, m_dcmEvaluated{false};
     bool evaluate();
 
 public:
@@ -25,13 +29,17 @@ public:
     // WalkingForwardKinematics.cpp:217-256
     bool evaluateWorldToBaseTransformation(const iDynTree::Transform& leftFootTransform,
                                            const iDynTree::Transform& rightFootTransform, const bool& isLeftFixedFrame);
-    // :258-276 (joint velocities only enter the CoM velocity, which is not on the hot path)
+    // :258-276 (the joint velocities enter the CoM velocity, hence the measured DCM)
     bool setInternalRobotState(const iDynTree::VectorDynSize& positionFeedbackInRadians,
                                const iDynTree::VectorDynSize& velocityFeedbackInRadians);
     iDynTree::Transform getLeftFootToWorldTransform();
     iDynTree::Transform getRightFootToWorldTransform();
     iDynTree::Rotation getNeckOrientation();
-    bool getCoMPosition(iDynTree::Position& comPosition);
+    bool getCoMPosition(iDynTree::Position& comPosition); // filtered if use_filters and evaluateCoM() was called
+    bool evaluateCoM();                                      // :278-310
+    bool evaluateDCM();                                      // :312-340
+    bool getDCM(iDynTree::Vector2& dcm);                     // :342-352
+    bool getCoMVelocity(iDynTree::Vector3& comVelocity);     // :376-394
     bool getLeftFootJacobian(iDynTree::MatrixDynSize& jacobian);
     bool getRightFootJacobian(iDynTree::MatrixDynSize& jacobian);
     bool getNeckJacobian(iDynTree::MatrixDynSize& jacobian);

@@ -80,7 +80,7 @@ int main(int argc, char** argv)
 
     iDynTree::VectorDynSize qDesired(23), dqDesired(23), qMeas(23);
     for (int i = 0; i < 23; i++) qDesired(i) = oik.joint_reg_rad[i];
-    double worst_zmp = 0.0, worst_dq = 0.0, worst_dq_osqp = 0.0;
+    double worst_zmp = 0.0, worst_dq = 0.0, worst_dq_osqp = 0.0, worst_fk_dcm = 0.0;
     wco_ikosqp* oikOsqp = wco_ikosqp_create(&oik, nullptr);
     int osqpSetups = 0;
     int failures = 0;
@@ -120,6 +120,18 @@ int main(int argc, char** argv)
         for (int j = 0; j < 23; j++) qMeas(j) = qDesired(j) + 0.003 * std::sin(0.1 * t + j);
         ok = fk.evaluateWorldToBaseTransformation(leftTraj.front(), rightTraj.front(), stanceLeft) && fk.setInternalRobotState(qDesired, dqDesired);
         iDynTree::Position comMeas; fk.getCoMPosition(comMeas);
+        { // WalkingModule::evaluateCoM / evaluateDCM (WalkingModule.cpp:559-570): the measured DCM of the MPC feedback
+            iDynTree::Vector2 dcmFk; iDynTree::Vector3 comVelFk; iDynTree::MatrixDynSize jc;
+            if (!fk.evaluateCoM() || !fk.evaluateDCM() || !fk.getDCM(dcmFk) || !fk.getCoMVelocity(comVelFk) || !fk.getCoMJacobian(jc)) {
+                std::fprintf(stderr, "tick %d: evaluateCoM / evaluateDCM failed\n", t); failures++;
+            } else {
+                for (int a = 0; a < 2; a++) {
+                    double v = 0.0;
+                    for (int j = 0; j < 23; j++) v += jc(a, 6 + j) * dqDesired(j);
+                    worst_fk_dcm = std::fmax(worst_fk_dcm, std::fabs(dcmFk(a) - (comMeas(a) + v / omega)));
+                }
+            }
+        }
         iDynTree::Position comDes = comMeas; comDes(0) += 0.002; comDes(1) -= 0.001;
         iDynTree::Vector3 comVel; comVel(0) = 0.02; comVel(1) = 0.01 * std::sin(0.05 * t); comVel(2) = 0.0;
         iDynTree::Twist lTw, rTw; lTw.zero(); rTw.zero();
@@ -255,6 +267,8 @@ int main(int argc, char** argv)
     if (worst_traj > 1e-12) failures++;
     wco_mpc_free(ompc);
     wco_ikosqp_free(oikOsqp);
+    std::printf("WalkingFK::evaluateDCM: worst abs err %.3e\n", worst_fk_dcm);
+    if (worst_fk_dcm > 1e-12) failures++;
     std::printf("WalkingQPIK_osqp: worst dq err %.3e rad/s, %d solver set-ups (stance changes + 1)\n", worst_dq_osqp, osqpSetups);
     if (worst_dq_osqp > 1e-5) failures++;
     std::printf("reactive controller: worst abs err %.3e\n", worst_reactive);
