@@ -86,7 +86,7 @@ struct Off {
         total = p;
     }
 };
-enum { H_HX = 0, H_HY, H_UH, H_ZH, H_YH, H_EH, H_COUNT };
+enum { H_HX = 0, H_HY, H_UH, H_ZH, H_YH, H_EH, H_RX, H_RY, H_RB, H_COUNT }; // H_R*: the unscaled hull rows (epilogue margin test)
 
 // 8-byte asynchronous copy HBM -> shared (LDGSTS): no register staging, so a thread can keep its whole
 // ~340-element stage-in in flight at once (two warps per SM cannot cover HBM latency with plain loads).
@@ -480,9 +480,9 @@ __global__ void __launch_bounds__(2 * IPW) mpc_chain_kernel(MpcDev d, MpcTickIO 
 #pragma unroll
             for (int h = 0; h < kMaxHull; h++) {
                 cp_async8(&H_(H_EH, h), d.Eh + (size_t)h * B + i, true);
-                cp_async8(&H_(H_HX, h), d.hullA + (size_t)(2 * h) * B + i, true);
-                cp_async8(&H_(H_HY, h), d.hullA + (size_t)(2 * h + 1) * B + i, true);
-                cp_async8(&H_(H_UH, h), d.hullb + (size_t)h * B + i, true);
+                cp_async8(&H_(H_RX, h), d.hullA + (size_t)(2 * h) * B + i, true);
+                cp_async8(&H_(H_RY, h), d.hullA + (size_t)(2 * h + 1) * B + i, true);
+                cp_async8(&H_(H_RB, h), d.hullb + (size_t)h * B + i, true);
                 cp_async8(&H_(H_YH, h), d.yh + (size_t)h * B + i, !cold);
                 cp_async8(&H_(H_ZH, h), d.zh + (size_t)h * B + i, !cold);
             }
@@ -513,9 +513,9 @@ __global__ void __launch_bounds__(2 * IPW) mpc_chain_kernel(MpcDev d, MpcTickIO 
         for (int h = 0; h < kMaxHull; h++) {
             const bool on = h < nh;
             const double e = H_(H_EH, h);
-            H_(H_HX, h) = on ? e * H_(H_HX, h) * dux : 0.0;
-            H_(H_HY, h) = on ? e * H_(H_HY, h) * duy : 0.0;
-            H_(H_UH, h) = on ? e * H_(H_UH, h) : 0.0;
+            H_(H_HX, h) = on ? e * H_(H_RX, h) * dux : 0.0;
+            H_(H_HY, h) = on ? e * H_(H_RY, h) * duy : 0.0;
+            H_(H_UH, h) = on ? e * H_(H_RB, h) : 0.0;
         }
     }
     // equality row 0: l = u = -dcm (MPCSolver.cpp:143-146), scaled by E
@@ -546,7 +546,9 @@ __global__ void __launch_bounds__(2 * IPW) mpc_chain_kernel(MpcDev d, MpcTickIO 
     };
 
     // update_info + the norms of check_termination for the CURRENT (x, z, y)
-    auto update_info = [&]() {
+    // SC: also the norms of the SCALED residuals (compute_rho_estimate); only an adaptive-rho iteration needs them
+    auto update_info = [&](auto sc_tag) {
+        constexpr bool SC = decltype(sc_tag)::value;
         double m_rp_u = 0, m_rp_s = 0, m_z_u = 0, m_z_s = 0, m_ax_u = 0, m_ax_s = 0;
         double m_rd_u = 0, m_rd_s = 0, m_q_u = 0, m_q_s = 0, m_aty_u = 0, m_aty_s = 0, m_px_u = 0, m_px_s = 0;
         const double* Dg = d.D + (size_t)(a * nA) * B + i;
@@ -585,9 +587,9 @@ __global__ void __launch_bounds__(2 * IPW) mpc_chain_kernel(MpcDev d, MpcTickIO 
             const double z = (k == 0) ? lb0 : 0.0;
             const double einv = EIv(k);
             const double r = ax - z;
-            m_rp_s = fmax(m_rp_s, fabs(r)); m_rp_u = fmax(m_rp_u, fabs(einv * r));
-            m_z_s = fmax(m_z_s, fabs(z)); m_z_u = fmax(m_z_u, fabs(einv * z));
-            m_ax_s = fmax(m_ax_s, fabs(ax)); m_ax_u = fmax(m_ax_u, fabs(einv * ax));
+            if (SC) m_rp_s = fmax(m_rp_s, fabs(r)); m_rp_u = fmax(m_rp_u, fabs(einv * r));
+            if (SC) m_z_s = fmax(m_z_s, fabs(z)); m_z_u = fmax(m_z_u, fabs(einv * z));
+            if (SC) m_ax_s = fmax(m_ax_s, fabs(ax)); m_ax_u = fmax(m_ax_u, fabs(einv * ax));
             const double yk = A_(YE, k);
             const double yk1 = (k < N) ? A_(YE, k + 1) : 0.0;
             {
@@ -596,10 +598,10 @@ __global__ void __launch_bounds__(2 * IPW) mpc_chain_kernel(MpcDev d, MpcTickIO 
                 const double aty_x = cm * yk + (k < N ? A_(CA, k + 1) * yk1 : 0.0);
                 const double q = A_(QX, k), dinv = DIXv(k);
                 const double rr = q + px_x + aty_x;
-                m_rd_s = fmax(m_rd_s, fabs(rr)); m_rd_u = fmax(m_rd_u, fabs(dinv * rr));
-                m_q_s = fmax(m_q_s, fabs(q)); m_q_u = fmax(m_q_u, fabs(dinv * q));
-                m_aty_s = fmax(m_aty_s, fabs(aty_x)); m_aty_u = fmax(m_aty_u, fabs(dinv * aty_x));
-                m_px_s = fmax(m_px_s, fabs(px_x)); m_px_u = fmax(m_px_u, fabs(dinv * px_x));
+                if (SC) m_rd_s = fmax(m_rd_s, fabs(rr)); m_rd_u = fmax(m_rd_u, fabs(dinv * rr));
+                if (SC) m_q_s = fmax(m_q_s, fabs(q)); m_q_u = fmax(m_q_u, fabs(dinv * q));
+                if (SC) m_aty_s = fmax(m_aty_s, fabs(aty_x)); m_aty_u = fmax(m_aty_u, fabs(dinv * aty_x));
+                if (SC) m_px_s = fmax(m_px_s, fabs(px_x)); m_px_u = fmax(m_px_u, fabs(dinv * px_x));
             }
             if (k < N) {
                 const double du_p1 = (k < N - 1) ? DUv(k + 1) : 0.0;
@@ -613,10 +615,10 @@ __global__ void __launch_bounds__(2 * IPW) mpc_chain_kernel(MpcDev d, MpcTickIO 
                 if (k == 0) aty_u += aty_hull(nullptr, false);
                 const double q = (k == 0) ? qu0 : 0.0, dinv = DIUv(k);
                 const double rr = q + px_u + aty_u;
-                m_rd_s = fmax(m_rd_s, fabs(rr)); m_rd_u = fmax(m_rd_u, fabs(dinv * rr));
-                m_q_s = fmax(m_q_s, fabs(q)); m_q_u = fmax(m_q_u, fabs(dinv * q));
-                m_aty_s = fmax(m_aty_s, fabs(aty_u)); m_aty_u = fmax(m_aty_u, fabs(dinv * aty_u));
-                m_px_s = fmax(m_px_s, fabs(px_u)); m_px_u = fmax(m_px_u, fabs(dinv * px_u));
+                if (SC) m_rd_s = fmax(m_rd_s, fabs(rr)); m_rd_u = fmax(m_rd_u, fabs(dinv * rr));
+                if (SC) m_q_s = fmax(m_q_s, fabs(q)); m_q_u = fmax(m_q_u, fabs(dinv * q));
+                if (SC) m_aty_s = fmax(m_aty_s, fabs(aty_u)); m_aty_u = fmax(m_aty_u, fabs(dinv * aty_u));
+                if (SC) m_px_s = fmax(m_px_s, fabs(px_u)); m_px_u = fmax(m_px_u, fabs(dinv * px_u));
                 xu_prev = vu_k;
                 du_m1 = du_k; vu_m1 = vu_k; du_k = du_p1; vu_k = vu_p1;
             }
@@ -632,18 +634,18 @@ __global__ void __launch_bounds__(2 * IPW) mpc_chain_kernel(MpcDev d, MpcTickIO 
                 const double z = H_(H_ZH, h);
                 const double einv = 1.0 / H_(H_EH, h); // = Ehinv of osqp_setup
                 const double r = ax - z;
-                m_rp_s = fmax(m_rp_s, fabs(r)); m_rp_u = fmax(m_rp_u, fabs(einv * r));
-                m_z_s = fmax(m_z_s, fabs(z)); m_z_u = fmax(m_z_u, fabs(einv * z));
-                m_ax_s = fmax(m_ax_s, fabs(ax)); m_ax_u = fmax(m_ax_u, fabs(einv * ax));
+                if (SC) m_rp_s = fmax(m_rp_s, fabs(r)); m_rp_u = fmax(m_rp_u, fabs(einv * r));
+                if (SC) m_z_s = fmax(m_z_s, fabs(z)); m_z_u = fmax(m_z_u, fabs(einv * z));
+                if (SC) m_ax_s = fmax(m_ax_s, fabs(ax)); m_ax_u = fmax(m_ax_u, fabs(einv * ax));
             }
         }
-        pri_res = pair_max(m_rp_u, pmask, IPW); rp_s = pair_max(m_rp_s, pmask, IPW);
-        nz_u = pair_max(m_z_u, pmask, IPW); nz_s = pair_max(m_z_s, pmask, IPW);
-        nAx_u = pair_max(m_ax_u, pmask, IPW); nAx_s = pair_max(m_ax_s, pmask, IPW);
-        dua_res = cinv * pair_max(m_rd_u, pmask, IPW); rd_s = pair_max(m_rd_s, pmask, IPW);
-        nq_u = cinv * pair_max(m_q_u, pmask, IPW); nq_s = pair_max(m_q_s, pmask, IPW);
-        nAty_u = cinv * pair_max(m_aty_u, pmask, IPW); nAty_s = pair_max(m_aty_s, pmask, IPW);
-        nPx_u = cinv * pair_max(m_px_u, pmask, IPW); nPx_s = pair_max(m_px_s, pmask, IPW);
+        pri_res = pair_max(m_rp_u, pmask, IPW); if (SC) rp_s = pair_max(m_rp_s, pmask, IPW);
+        nz_u = pair_max(m_z_u, pmask, IPW); if (SC) nz_s = pair_max(m_z_s, pmask, IPW);
+        nAx_u = pair_max(m_ax_u, pmask, IPW); if (SC) nAx_s = pair_max(m_ax_s, pmask, IPW);
+        dua_res = cinv * pair_max(m_rd_u, pmask, IPW); if (SC) rd_s = pair_max(m_rd_s, pmask, IPW);
+        nq_u = cinv * pair_max(m_q_u, pmask, IPW); if (SC) nq_s = pair_max(m_q_s, pmask, IPW);
+        nAty_u = cinv * pair_max(m_aty_u, pmask, IPW); if (SC) nAty_s = pair_max(m_aty_s, pmask, IPW);
+        nPx_u = cinv * pair_max(m_px_u, pmask, IPW); if (SC) nPx_s = pair_max(m_px_s, pmask, IPW);
     };
 
     // is_primal_infeasible (OSQP auxil.c) on delta_y (global scratch written by the last iteration)
@@ -927,12 +929,12 @@ __global__ void __launch_bounds__(2 * IPW) mpc_chain_kernel(MpcDev d, MpcTickIO 
         __syncwarp(WMASK); // hull z / y of this iteration visible to both lanes
         // ---- termination / adaptive rho (pair-uniform decisions, warp-uniform barriers)
         if (check_now) {
-            update_info();
+            if (adapt_now) update_info(std::true_type{}); else update_info(std::false_type{});
             const int stop = check_termination(0);
             if (act && stop) { status = stop; done = true; }
         }
         if (adapt_now) {
-            if (!check_now) update_info();
+            if (!check_now) update_info(std::true_type{});
             if (act && !done) {
                 // compute_rho_estimate + adapt_rho
                 const double pr = rp_s / (fmax(nz_s, nAx_s) + 1e-10);
@@ -957,7 +959,7 @@ __global__ void __launch_bounds__(2 * IPW) mpc_chain_kernel(MpcDev d, MpcTickIO 
         }
         if (iter >= max_iter) { // warp-uniform: osqp_solve leaves the loop
             if (!check_now) {
-                update_info();
+                update_info(std::false_type{});
                 const int stop = check_termination(0);
                 if (act && !done && stop) { status = stop; done = true; }
             }
@@ -1018,21 +1020,20 @@ __global__ void __launch_bounds__(2 * IPW) mpc_chain_kernel(MpcDev d, MpcTickIO 
                     // ConvexHullProjectionConstraint::computeMargin (Controller.cpp:513-517)
                     // margin < -tol  <=>  outside the polygon AND farther than tol from its boundary: the distance to
                     // the hull segments is only needed for a ZMP that violates a hull row
+                    // A ZMP on an active hull row violates it by OSQP's tolerance (~1e-4 m): the hull is the convex hull of
+                    // foot rectangles, every interior angle is >= 90 degrees, so the distance to the polygon is at most
+                    // sqrt(2) x the largest normalised row violation; only a violation that could reach the tolerance
+                    // takes the exact point-to-segment distances (and their dependent loads of the vertices)
                     bool inside = true;
-                    double best = INFINITY;
-                    {
-                        double a0[kMaxHull], a1[kMaxHull], bb[kMaxHull];
+                    double best = INFINITY, vmax = 0.0;
 #pragma unroll
-                        for (int h = 0; h < kMaxHull; h++) { // one batch of loads
-                            a0[h] = h < nh ? d.hullA[(size_t)(2 * h) * B + i] : 0.0;
-                            a1[h] = h < nh ? d.hullA[(size_t)(2 * h + 1) * B + i] : 0.0;
-                            bb[h] = h < nh ? d.hullb[(size_t)h * B + i] : 0.0;
-                        }
-#pragma unroll
-                        for (int h = 0; h < kMaxHull; h++)
-                            if (h < nh && !(a0[h] * out[0] + a1[h] * out[1] <= bb[h])) inside = false;
+                    for (int h = 0; h < kMaxHull; h++) {
+                        const double a0 = H_(H_RX, h), a1 = H_(H_RY, h), bb = H_(H_RB, h);
+                        const double viol = (a0 * out[0] + a1 * out[1]) - bb;
+                        if (h < nh && !(viol <= 0.0)) { inside = false; vmax = fmax(vmax, viol / sqrt(a0 * a0 + a1 * a1)); }
                     }
-                    if (!inside) {
+                    const bool exact = !inside && !(4.0 * vmax < d.hull_tol);
+                    if (exact) {
                         for (int h = 0; h < nh; h++) {
                             const int h1 = (h + 1) % nh;
                             const double p0x = d.hullv[(size_t)(2 * h) * B + i], p0y = d.hullv[(size_t)(2 * h + 1) * B + i];
@@ -1044,6 +1045,8 @@ __global__ void __launch_bounds__(2 * IPW) mpc_chain_kernel(MpcDev d, MpcTickIO 
                             const double ex = out[0] - (p0x + t * dx), ey = out[1] - (p0y + t * dy);
                             best = fmin(best, sqrt(ex * ex + ey * ey));
                         }
+                    } else if (!inside) {
+                        best = 0.0; // outside by less than the tolerance: not flagged
                     }
                     const double margin = inside ? best : -best;
                     if (margin < -d.hull_tol) flags |= WC_MPC_FLAG_OUTSIDE_HULL;
