@@ -326,7 +326,10 @@ def run_ours(args, world, rank, local_rank):
         res = torch.cat([mo["zmp"], io_["dq"]], 0).contiguous()
         outbuf = [torch.empty_like(res) for _ in range(world)] if rank == 0 else None
         stats = torch.tensor([solved, ik_ok, it_mean, wsc_mean], dtype=torch.float64, device=dev)
-        torch.cuda.synchronize(); t0 = time.perf_counter()
+        # the first gather sets up the point-to-point NCCL connections (seconds at 8 ranks): not part of the collection time
+        warm = [torch.empty(8, device=dev) for _ in range(world)] if rank == 0 else None
+        dist.gather(torch.zeros(8, device=dev), warm, dst=0)
+        torch.cuda.synchronize(); dist.barrier(); t0 = time.perf_counter()
         dist.gather(res, outbuf, dst=0)
         dist.all_reduce(stats, op=dist.ReduceOp.SUM)
         torch.cuda.synchronize(); gather_ms = (time.perf_counter() - t0) * 1e3
