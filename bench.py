@@ -327,8 +327,8 @@ def run_ours(args, world, rank, local_rank):
         outbuf = [torch.empty_like(res) for _ in range(world)] if rank == 0 else None
         stats = torch.tensor([solved, ik_ok, it_mean, wsc_mean], dtype=torch.float64, device=dev)
         # the first gather sets up the point-to-point NCCL connections (seconds at 8 ranks): not part of the collection time
-        warm = [torch.empty(8, device=dev) for _ in range(world)] if rank == 0 else None
-        dist.gather(torch.zeros(8, device=dev), warm, dst=0)
+        gather_warm = [torch.empty(8, device=dev) for _ in range(world)] if rank == 0 else None
+        dist.gather(torch.zeros(8, device=dev), gather_warm, dst=0)
         torch.cuda.synchronize(); dist.barrier(); t0 = time.perf_counter()
         dist.gather(res, outbuf, dst=0)
         dist.all_reduce(stats, op=dist.ReduceOp.SUM)
