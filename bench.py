@@ -231,6 +231,26 @@ def cpu_baseline_leg(N):
 
 
 # ------------------------------------------------------------------------------------------------
+def pin_to_gpu_numa_node(gpu_index):
+    """Bind this rank's process (hence the first touch of its pinned host buffers) to the CPUs NVML reports as local to
+    its GPU: with one rank per GPU the host->device copies of the e2e arm then read NUMA-local memory instead of crossing
+    the socket interconnect.  Returns the number of CPUs kept, or None when the affinity could not be applied."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return None
+
+
 def run_ours(args, world, rank, local_rank):
     import numpy as np
     import torch
@@ -242,6 +262,7 @@ def run_ours(args, world, rank, local_rank):
         raise RuntimeError("bench.py needs a CUDA device: the product has no CPU fallback")
     dev = torch.device(f"cuda:{local_rank}")
     torch.cuda.set_device(dev)
+    numa_cpus = pin_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B, N = args.batch, args.horizon
@@ -456,7 +477,7 @@ def run_ours(args, world, rank, local_rank):
             "metric": METRIC, "value": value, "unit": "ticks/s", "n_gpus": world, "steps": steps,
             "warmup": warm, "ms_per_step": total_ms_max / steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": dict(workload_config(world, B, N), mpc_path=mpc.path),
+            "config": dict(workload_config(world, B, N), mpc_path=mpc.path, **({"rank_cpu_affinity": numa_cpus} if world > 1 else {})),
             "tick_latency_ms": {"p50": pct(step_ms, 0.5), "p99": pct(step_ms, 0.99), "max": max(step_ms)},
             "kernels_ms": {"mpc_prepare": prep_avg_ms, "mpc_admm": admm_avg_ms, "fk_qpik": ik_avg_ms,
                            "mpc_setup": setup_ms / max(nt, 1), "mpc_phase1": phase1_ms / max(nt, 1),
