@@ -120,7 +120,7 @@ def write_dataset(path, times, rows):
 
 def build(verbose=False):
     """Compile libwc_b200.so for sm_100a with nvcc (cross-compiles without a GPU)."""
-    out = subprocess.run(["make", "-C", CSRC], capture_output=True, text=True)
+    out = subprocess.run(["make", "-j8", "-C", CSRC], capture_output=True, text=True)
     if verbose or out.returncode != 0:
         print(out.stdout[-4000:])
         print(out.stderr[-4000:])
