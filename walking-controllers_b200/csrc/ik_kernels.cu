@@ -192,8 +192,12 @@ __device__ __forceinline__ void fk_stage(const IkModelDev& M, const IkTickIO& io
         rfH[8] = R[6]; rfH[9] = R[7]; rfH[10] = R[8]; rfH[11] = p[2];
         mat3_mul(WL + M.frame_link[2] * 12, M.frame_R[2], nR);
     }
+    // total first moment: lane partials + butterfly (every lane ends with the same bits); the serial loop over all
+    // links on every lane was 6 % of the fused tick's samples (profiles/r1o_hot_lines.md)
     double Mc[3] = {0, 0, 0};
-    for (int k = 0; k < L; k++) { Mc[0] += MC[k * 4]; Mc[1] += MC[k * 4 + 1]; Mc[2] += MC[k * 4 + 2]; }
+    for (int k = lane; k < L; k += 32) { Mc[0] += MC[k * 4]; Mc[1] += MC[k * 4 + 1]; Mc[2] += MC[k * 4 + 2]; }
+#pragma unroll
+    for (int r = 0; r < 3; r++) Mc[r] = warp_sum(Mc[r]);
     const double Mtot = M.total_mass;
 #pragma unroll
     for (int r = 0; r < 3; r++) com[r] = Mc[r] / Mtot;
@@ -889,10 +893,13 @@ template <int NJ>
 struct IkFastLayout {
     static constexpr int NV = NJ + 6;
     static constexpr int KIN = WC_MAX_LINKS * 12 + WC_MAX_LINKS * 4;
-    static constexpr int O_AS = 0;                  // a_j   [9][32]
-    static constexpr int O_UT = O_AS + 9 * 32;      // u~_j  [3][32]
-    static constexpr int O_HS = O_UT + 3 * 32;      // h_j   [9][32]
-    static constexpr int O_GR = O_HS + 9 * 32;      // g_r   [32]
+    // rows of AS / UT / HS are read both lane-per-column and lane-per-ROW (G, S, rhs below): a row stride of 33
+    // keeps the second pattern bank-conflict free (stride 32 put every row on the same bank pair, profiles/r1o)
+    static constexpr int LDQ = 33;
+    static constexpr int O_AS = 0;                  // a_j   [9][LDQ]
+    static constexpr int O_UT = O_AS + 9 * LDQ;     // u~_j  [3][LDQ]
+    static constexpr int O_HS = O_UT + 3 * LDQ;     // h_j   [9][LDQ]
+    static constexpr int O_GR = O_HS + 9 * LDQ;     // g_r   [32]
     static constexpr int O_GK = O_GR + 32;          // G K   [27]
     static constexpr int O_SS = O_GK + 28;          // S     [81]
     static constexpr int QP = O_SS + 82;
@@ -909,6 +916,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, 4) ik_fast_kernel(IkDev d, Ik
 {
     using LY = IkFastLayout<NJ>;
     constexpr int NV = LY::NV;
+    constexpr int LDQ = LY::LDQ;
     constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ double smem_all[];
     const int lane = threadIdx.x & 31;
@@ -1020,17 +1028,17 @@ __global__ void __launch_bounds__(kFastWarps * 32, 4) ik_fast_kernel(IkDev d, Ik
     }
     __syncwarp(); // kinematics scratch is dead
 #pragma unroll
-    for (int r = 0; r < 9; r++) AS[r * 32 + lane] = a[r];
+    for (int r = 0; r < 9; r++) AS[r * LDQ + lane] = a[r];
 #pragma unroll
-    for (int r = 0; r < 3; r++) UT[r * 32 + lane] = ut[r];
+    for (int r = 0; r < 3; r++) UT[r * LDQ + lane] = ut[r];
     GR[lane] = gr;
     __syncwarp();
     // ---- G = A_r Lambda^-1 U' (9x3), lane r < 9 owns row r, then the row of G K
     if (lane < 9) {
         double g0 = 0.0, g1 = 0.0, g2 = 0.0;
         for (int jj = 6; jj < NV; jj++) {
-            const double av = AS[lane * 32 + jj];
-            g0 += av * UT[jj]; g1 += av * UT[32 + jj]; g2 += av * UT[64 + jj];
+            const double av = AS[lane * LDQ + jj];
+            g0 += av * UT[jj]; g1 += av * UT[LDQ + jj]; g2 += av * UT[2 * LDQ + jj];
         }
 #pragma unroll
         for (int c = 0; c < 3; c++) GK[lane * 3 + c] = g0 * K3[c] + g1 * K3[3 + c] + g2 * K3[6 + c];
@@ -1041,7 +1049,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, 4) ik_fast_kernel(IkDev d, Ik
 #pragma unroll
     for (int r = 0; r < 9; r++) h[r] = at[r] - (GK[r * 3] * ut[0] + GK[r * 3 + 1] * ut[1] + GK[r * 3 + 2] * ut[2]);
 #pragma unroll
-    for (int r = 0; r < 9; r++) HS[r * 32 + lane] = h[r];
+    for (int r = 0; r < 9; r++) HS[r * LDQ + lane] = h[r];
     __syncwarp();
     // ---- S = A_r H_r^-1 A_r' (upper triangle: 45 entries on 32 lanes, two rounds) and the right-hand side
 #pragma unroll
@@ -1052,14 +1060,14 @@ __global__ void __launch_bounds__(kFastWarps * 32, 4) ik_fast_kernel(IkDev d, Ik
             while (e >= 9 - r) { e -= 9 - r; r++; }
             const int c = r + e;
             double acc = 0.0;
-            for (int jj = 6; jj < NV; jj++) acc += HS[r * 32 + jj] * AS[c * 32 + jj];
+            for (int jj = 6; jj < NV; jj++) acc += HS[r * LDQ + jj] * AS[c * LDQ + jj];
             SS[r * 9 + c] = acc; SS[c * 9 + r] = acc;
         }
     }
     double rhs = 0.0;
     if (lane < 9) {
         double acc = 0.0;
-        for (int jj = 6; jj < NV; jj++) acc += HS[lane * 32 + jj] * GR[jj];
+        for (int jj = 6; jj < NV; jj++) acc += HS[lane * LDQ + jj] * GR[jj];
         double brl = 0.0;
 #pragma unroll
         for (int r = 0; r < 9; r++) brl = (lane == r) ? br[r] : brl;
