@@ -47,6 +47,67 @@ def test_fk_jacobians_parity(wc, syn, oracle, cuda_device):
     ik.close()
 
 
+def _random_tree_model(wc, oracle, n_links, chainy, seed):
+    """23 revolute joints + fixed links on a random tree (parent[i] < i): the same table for the device and the oracle"""
+    import ctypes as C
+    rng = np.random.default_rng(seed)
+    mo = oracle.model_icub_like()
+    L = n_links
+    mo.n_links, mo.n_dofs = L, 23
+    movable = set(rng.choice(np.arange(1, L), 23, replace=False).tolist())
+    dof_next = 0
+
+    def rot():
+        q, _ = np.linalg.qr(rng.standard_normal((3, 3)))
+        return q * np.sign(np.linalg.det(q))
+
+    for i in range(40):
+        par = -1 if i == 0 else (i - 1 if rng.random() < chainy else int(rng.integers(0, i)))
+        mo.parent[i] = par if i < L else 0
+        if i in movable and i < L:
+            mo.dof[i] = dof_next; dof_next += 1
+        else:
+            mo.dof[i] = -1
+        R = np.eye(3) if i == 0 else rot()
+        ax = rng.standard_normal(3); ax /= np.linalg.norm(ax)
+        for k in range(9): mo.joint_R[i][k] = float(R.reshape(-1)[k])
+        for k in range(3):
+            mo.joint_p[i][k] = 0.0 if i == 0 else float(0.1 * rng.standard_normal())
+            mo.axis[i][k] = float(ax[k])
+            mo.com[i][k] = float(0.05 * rng.standard_normal())
+        mo.mass[i] = float(0.2 + rng.random())
+    leaves = [i for i in range(1, L) if i not in [mo.parent[k] for k in range(L)]]
+    pick = rng.choice(leaves if len(leaves) >= 3 else np.arange(1, L), 3, replace=False)
+    mo.l_sole_link, mo.r_sole_link, mo.neck_link = int(pick[0]), int(pick[1]), int(pick[2])
+    mg = wc.model_icub_like()
+    assert C.sizeof(mg) == C.sizeof(mo)
+    C.memmove(C.byref(mg), C.byref(mo), C.sizeof(mo))
+    return mg, mo
+
+
+@pytest.mark.parametrize("n_links,chainy", [(25, 0.5), (32, 0.95), (32, 0.2), (40, 0.9), (24, 1.0)])
+def test_fk_random_trees_parity(wc, oracle, cuda_device, n_links, chainy):
+    """FK / Jacobians on random kinematic trees: deep chains (up to five pointer-jumping rounds), bushy trees with
+    non-contiguous sub-trees, 32 links (the widest tree one lane per link covers) and 40 links (level-by-level path)"""
+    B = 64
+    mg, mo = _random_tree_model(wc, oracle, n_links, chainy, seed=n_links * 7 + int(chainy * 10))
+    g = torch.Generator().manual_seed(n_links)
+    q = (torch.rand(23, B, generator=g, dtype=torch.float64) - 0.5) * 2.0
+    base_H = torch.zeros(12, B, dtype=torch.float64)
+    yaw = torch.rand(B, generator=g, dtype=torch.float64) * 6.28
+    base_H[0], base_H[1], base_H[4], base_H[5], base_H[10] = torch.cos(yaw), -torch.sin(yaw), torch.sin(yaw), torch.cos(yaw), 1.0
+    base_H[3] = torch.rand(B, generator=g, dtype=torch.float64); base_H[7] = torch.rand(B, generator=g, dtype=torch.float64)
+    lif = (torch.rand(B, generator=g) < 0.5).to(torch.uint8)
+    ik = wc.IkBatch(wc.ik_default_config(), mg, B)
+    out = ik.fk(q.to(cuda_device), base_H.to(cuda_device), lif.to(cuda_device))
+    torch.cuda.synchronize()
+    o = oracle.fk_batch(mo, q.numpy(), base_H.numpy(), lif.numpy())
+    for k in ("lf_H", "rf_H", "neck_R", "com", "J_lf", "J_rf", "J_neck", "J_com"):
+        err = np.abs(out[k].cpu().numpy() - o[k]).max()
+        assert err < 1e-11, (k, err)
+    ik.close()
+
+
 def _compare(out_g, out_o, tag=""):
     sg = out_g["status"]; so = out_o["status"]
     assert np.array_equal(sg, so), f"{tag} status differs at {np.nonzero(sg != so)[0][:10]}"

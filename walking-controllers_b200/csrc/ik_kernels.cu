@@ -13,6 +13,16 @@ constexpr double kViolTol = 1e-10;
 constexpr double kRankTol = 1e-11;
 
 constexpr int kWarpsPerBlock = 4;
+// tuning switches (build variants, tools/sweep_ik_variants.sh): pointer-jumping FK, bounded sub-tree loop
+#ifndef WC_IK_JUMP
+#define WC_IK_JUMP 1
+#endif
+#ifndef WC_IK_SUBLOOP
+#define WC_IK_SUBLOOP 1
+#endif
+#ifndef WC_IK_FAST_MINB
+#define WC_IK_FAST_MINB 4 // resident CTAs per SM the fast kernel is compiled for (register cap 128)
+#endif
 
 // ---- small 3x3 / rigid transform helpers (row-major R[9], p[3]) ---------------------------------
 __device__ __forceinline__ void mat3_mul(const double* a, const double* b, double* o)
@@ -84,7 +94,11 @@ __device__ __forceinline__ double warp_max(double v)
 // WalkingForwardKinematics.cpp:278-340,411-454 (iDynTree KinDynComputations restated; MIXED representation).
 // Lane l owns link l (and l + 32) for the transforms, then QP variable j = lane for the columns.
 // WL [links][12] world_H_link and MC [links][4] mass-weighted link CoMs stay in shared memory.
-template <int NV>
+// JUMP: root_H_link by pointer jumping (ceil(log2(depth)) rounds in which EVERY link composes with its current
+// ancestor) instead of one pass per tree level with a handful of active lanes: 3 rounds instead of 7 levels for
+// the iCub tree.  The products associate differently (1e-16 relative), so the OSQP-based variant, whose life cycle
+// is decided on exact zeros of the neck Jacobian, keeps the level order of the CPU restatement (JUMP = false).
+template <int NV, bool JUMP = false>
 __device__ __forceinline__ void fk_stage(const IkModelDev& M, const IkTickIO& io, int i, size_t B, int lane,
                                          double* WL, double* MC, double* colLf, double* colRf, double* colN,
                                          double* colC, double* lfH, double* rfH, double* nR, double* com, double* pBo,
@@ -124,8 +138,30 @@ __device__ __forceinline__ void fk_stage(const IkModelDev& M, const IkTickIO& io
         }
     }
     __syncwarp();
+    const bool jump = JUMP && WC_IK_JUMP && L <= 32 && M.n_jump > 0;
+    if (jump) {
+        // T[l] = anc_H_l; every round T[l] <- T[anc] T[l], anc <- anc(anc) (table from the host), until anc = none
+        double R[9], p[3];
+        const int lk = l < L ? l : 0;
+#pragma unroll
+        for (int k = 0; k < 9; k++) R[k] = WL[lk * 12 + k];
+#pragma unroll
+        for (int k = 0; k < 3; k++) p[k] = WL[lk * 12 + 9 + k];
+        for (int r = 0; r < M.n_jump; r++) {
+            const int an = l < L ? (int)M.jump[r][l] : -1;
+            if (an >= 0) xf_mul(WL + an * 12, WL + an * 12 + 9, R, p, R, p);
+            __syncwarp();
+            if (an >= 0) {
+#pragma unroll
+                for (int k = 0; k < 9; k++) WL[lk * 12 + k] = R[k];
+#pragma unroll
+                for (int k = 0; k < 3; k++) WL[lk * 12 + 9 + k] = p[k];
+            }
+            __syncwarp();
+        }
+    }
     // root_H_link by tree depth (parent[l] < l, depth known on the host)
-    for (int dep = 1; dep <= M.max_depth; dep++) {
+    for (int dep = 1; dep <= (jump ? 0 : M.max_depth); dep++) {
         for (int base = 0; base < L; base += 32) {
             const int lk = base + l;
             if (lk < L && M.depth[lk] == dep) {
@@ -241,7 +277,10 @@ __device__ __forceinline__ void fk_stage(const IkModelDev& M, const IkTickIO& io
         // base link sits inside that sub-tree)
         double S[3] = {0, 0, 0};
         const unsigned long long mask = M.sub_mask[c];
-        for (int k = 0; k < L; k++)
+        // links of the sub-tree in ascending order, between its first and last member only (one contiguous run for
+        // a depth-first numbered tree); the warp runs as many trips as its largest sub-tree needs
+        const int k1 = 63 - __clzll((long long)mask);
+        for (int k = WC_IK_SUBLOOP ? __ffsll((long long)mask) - 1 : 0; k <= (WC_IK_SUBLOOP ? k1 : L - 1); k++)
             if ((mask >> k) & 1ull) { S[0] += MC[k * 4]; S[1] += MC[k * 4 + 1]; S[2] += MC[k * 4 + 2]; }
         const double ms = M.sub_mass[c];
         double mom[3];
@@ -542,7 +581,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) ik_kernel(IkDev d, IkTick
     double lfH[12], rfH[12], nR[9], com[3], pBv[3] = {0, 0, 0};
 
     if (mode != IK_MODE_EXT_KIN) {
-        fk_stage<NV>(M, io, i, B, lane, WL, MC, colLf, colRf, colN, colC, lfH, rfH, nR, com, pBv);
+        fk_stage<NV, true>(M, io, i, B, lane, WL, MC, colLf, colRf, colN, colC, lfH, rfH, nR, com, pBv);
         if (mode == IK_MODE_FK_ONLY) {
             if (lane < 12) {
                 if (io.o_lf_H) io.o_lf_H[(size_t)lane * B + i] = lfH[lane];
@@ -912,7 +951,7 @@ struct IkFastLayout {
 };
 
 template <int NJ>
-__global__ void __launch_bounds__(kFastWarps * 32, 4) ik_fast_kernel(IkDev d, IkTickIO io)
+__global__ void __launch_bounds__(kFastWarps * 32, WC_IK_FAST_MINB) ik_fast_kernel(IkDev d, IkTickIO io)
 {
     using LY = IkFastLayout<NJ>;
     constexpr int NV = LY::NV;
@@ -928,6 +967,8 @@ __global__ void __launch_bounds__(kFastWarps * 32, 4) ik_fast_kernel(IkDev d, Ik
         for (int k = threadIdx.x; k < LY::MODEL_DOUBLES; k += kFastWarps * 32) sm_model[k] = src[k];
     }
     __syncthreads();
+    // (a one-wave grid striding over the instances, to stage the model table once per CTA, was measured: the loop
+    // costs more registers / spills than the copy's latency it saves, 0.71 -> 0.74 ms)
     const long long inst = (long long)blockIdx.x * kFastWarps + warp;
     if (inst >= d.B) return;
     const int i = (int)inst;
@@ -956,7 +997,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, 4) ik_fast_kernel(IkDev d, Ik
     double lfH[12], rfH[12], nR[9], com[3], pB[3];
     // (the stance-sole transform is needed half way through the kinematics: wait for the prefetch there would
     // serialise, so base_H alone still comes from HBM inside fk_stage; everything else arrives meanwhile)
-    fk_stage<NV>(M, io, i, B, lane, WL, MC, colLf, colRf, colN, colC, lfH, rfH, nR, com, pB);
+    fk_stage<NV, true>(M, io, i, B, lane, WL, MC, colLf, colRf, colN, colC, lfH, rfH, nR, com, pB);
     asm volatile("cp.async.wait_group 0;\n" ::: "memory");
     __syncwarp();
     double bvec[15], gj, lam;

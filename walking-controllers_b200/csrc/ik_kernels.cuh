@@ -23,6 +23,8 @@
 
 namespace wcb {
 
+constexpr int WC_MAX_JUMP = 6; // 2^6 >= WC_MAX_LINKS
+
 struct IkModelDev {
     int n_links, n_dofs, max_depth, pad0;
     int parent[WC_MAX_LINKS];
@@ -45,6 +47,10 @@ struct IkModelDev {
     // per base choice and dof: path signs of the three task frames, and "base inside the joint's subtree"
     signed char s_frame[2][3][WC_MAX_DOFS];
     signed char base_in_sub[2][WC_MAX_DOFS];
+    // pointer-jumping schedule of the transform composition: jump[r][l] = the ancestor link l composes with in
+    // round r (its 2^r-th ancestor), -1 = l is already expressed in the root frame; n_jump rounds in all
+    int n_jump, pad2;
+    signed char jump[WC_MAX_JUMP][WC_MAX_LINKS];
 };
 
 struct IkDev {

@@ -70,6 +70,23 @@ bool build_model(const wc_model* m, IkModelDev* o)
         for (int k = 0; k < L; k++) if (anc_or_self(m, c, k)) { mask |= 1ull << k; ms += m->mass[k]; }
         o->sub_mask[c] = mask; o->sub_mass[c] = ms;
     }
+    { // pointer-jumping schedule (fk_stage<., true>)
+        int anc[WC_MAX_LINKS];
+        for (int i = 0; i < L; i++) anc[i] = m->parent[i];
+        int r = 0;
+        for (; r < WC_MAX_JUMP; r++) {
+            bool any = false;
+            for (int i = 0; i < L; i++) { o->jump[r][i] = (signed char)anc[i]; any = any || anc[i] >= 0; }
+            if (!any) break;
+            int nxt[WC_MAX_LINKS];
+            for (int i = 0; i < L; i++) nxt[i] = anc[i] >= 0 ? anc[anc[i]] : -1;
+            for (int i = 0; i < L; i++) anc[i] = nxt[i];
+        }
+        o->n_jump = r;
+        bool left_over = false;
+        for (int i = 0; i < L; i++) left_over = left_over || anc[i] >= 0;
+        if (left_over) o->n_jump = 0; // deeper than 2^WC_MAX_JUMP: level-by-level composition
+    }
     const int fl[3] = {m->l_sole_link, m->r_sole_link, m->neck_link};
     for (int f = 0; f < 3; f++) if (fl[f] < 0 || fl[f] >= L) return false;
     o->base_link[1] = m->l_sole_link; o->base_link[0] = m->r_sole_link;
