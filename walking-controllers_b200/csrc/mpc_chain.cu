@@ -103,6 +103,44 @@ __device__ __forceinline__ void cp_async_wait_all()
     asm volatile("cp.async.wait_group 0;\n" ::: "memory");
 }
 
+// Bulk asynchronous copies (cp.async.bulk, the TMA engine's 1-D form; SASS UBLKCP) completing on an mbarrier: one
+// instruction moves the 128-byte half row that 16 lanes otherwise fetch with 16 LDGSTS and their address arithmetic
+// (714 copies per CTA, 23 per lane, instead of ~340 LDGSTS per lane).  MEASURED AND SWITCHED OFF (-DWC_CHAIN_BULK=1
+// builds it): parity green, but phase 1 went from 1.64 to 1.92 ms at B = 65 536 -- with a field-major layout a row
+// holds only 128 contiguous bytes of one CTA's instances, and 714 requests of 128 bytes per CTA are bound by the
+// copy engine's request rate, not by bytes.  What it needs is fewer, larger requests: a group-major workspace (one
+// contiguous block per 16 instances) or 3-D tensor maps whose box {16 instances, 2 axes, all stages} lands as
+// [stage][axis][16] = this kernel's shared-memory layout.
+#ifndef WC_CHAIN_BULK
+#define WC_CHAIN_BULK 0
+#endif
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
+{
+    unsigned ok;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+// 128 bytes HBM -> shared; both addresses 16-byte aligned
+__device__ __forceinline__ void bulk128(unsigned dst, const double* gsrc, unsigned bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 128, [%2];\n"
+                 ::"r"(dst), "l"(gsrc), "r"(bar) : "memory");
+}
+// generic-proxy accesses to shared memory ordered before the async-proxy writes that follow
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
 // exchanges between the two axis lanes of an instance: always under the PAIR mask, so that they are
 // legal inside branches that are uniform for the pair but not for the warp
 __device__ __forceinline__ double pair_max(double v, unsigned pm, int dist) { return fmax(v, __shfl_xor_sync(pm, v, dist)); }
@@ -419,6 +457,16 @@ __global__ void __launch_bounds__(2 * IPW) mpc_chain_kernel(MpcDev d, MpcTickIO 
     ChainSmem<IPW> s{smem_all + lane, smem_all + (size_t)O.total * (2 * IPW) + slot, nR, N};
 #define A_(o, k) s.at(O.o, (k))
 #define H_(arr, h) s.hat((arr), (h))
+    // bulk staging: phase 1 at 16 instances per CTA, every group full and its rows 16-byte aligned
+    constexpr bool BULK = WC_CHAIN_BULK && !PHASE2 && IPW == 16;
+    const bool bulk = BULK && (d.B % 16) == 0;
+    const unsigned sbase = smem_u32(smem_all);
+    const unsigned sbar = smem_u32(smem_all + (size_t)O.total * (2 * IPW) + (size_t)H_COUNT * 8 * IPW);
+    unsigned bar_parity = 0;
+    if (bulk) {
+        if (lane == 0) mbar_init(sbar, 1);
+        __syncwarp(WMASK);
+    }
     for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
     const int li = grp * kIPW + slot;
     const bool valid = li < count;
@@ -455,7 +503,44 @@ __global__ void __launch_bounds__(2 * IPW) mpc_chain_kernel(MpcDev d, MpcTickIO 
             }
         }
     };
-    {
+    // half row (16 instances of one axis) of array element `el` <- row `grow` of a field-major HBM array
+    const size_t i0 = (size_t)grp * kIPW;
+    auto brow = [&](int el, int aa, const double* gbase, int grow) {
+        bulk128(sbase + (unsigned)((el * 32 + aa * 16) * 8), gbase + (size_t)grow * B + i0, sbar);
+    };
+    if (bulk) {
+        fence_async_smem();
+        if (lane == 0) mbar_expect_tx(sbar, (unsigned)(((8 * nR + 5 * N) * 2 + 6 * kMaxHull) * 128));
+        __syncwarp(WMASK);
+#pragma unroll
+        for (int p = lane; p < 2 * nR; p += 32) { // lane <-> (stage k, axis aa); same parking as the LDGSTS path below
+            const int k = p >> 1, aa = p & 1;
+            const int slot_k = head + k < nR ? head + k : head + k - nR;
+            brow(O.XX + k, aa, d.x, aa * nA + k);
+            brow(O.YE + k, aa, d.yeq, aa * nR + k);
+            brow(O.QX + k, aa, d.grad, aa * nR + slot_k);
+            brow(O.CM + k, aa, d.Eeq, aa * nR + k);
+            brow(O.WX + k, aa, d.D, aa * nA + k);
+            brow(O.L1X + k, aa, d.L1, aa * nA + k);
+            brow(O.L2X + k, aa, d.L2, aa * nA + k);
+            brow(O.DIX + k, aa, d.DI, aa * nA + k);
+            if (k < N) {
+                brow(O.XU + k, aa, d.x, aa * nA + nR + k);
+                brow(O.WU + k, aa, d.D, aa * nA + nR + k);
+                brow(O.L1U + k, aa, d.L1, aa * nA + nR + k);
+                brow(O.L2U + k, aa, d.L2, aa * nA + nR + k);
+                brow(O.DIU + k, aa, d.DI, aa * nA + nR + k);
+            }
+        }
+        for (int cidx = lane; cidx < 6 * kMaxHull; cidx += 32) { // per-instance hull block: rows of 16 doubles
+            const int which = cidx / kMaxHull, h = cidx % kMaxHull;
+            const double* src = which == 0 ? d.Eh + (size_t)h * B : which == 1 ? d.hullA + (size_t)(2 * h) * B
+                              : which == 2 ? d.hullA + (size_t)(2 * h + 1) * B : which == 3 ? d.hullb + (size_t)h * B
+                              : which == 4 ? d.yh + (size_t)h * B : d.zh + (size_t)h * B;
+            const int harr = which == 0 ? H_EH : which == 1 ? H_RX : which == 2 ? H_RY : which == 3 ? H_RB : which == 4 ? H_YH : H_ZH;
+            bulk128(sbase + (unsigned)((O.total * (2 * IPW) + (harr * 8 + h) * IPW) * 8), src + i0, sbar);
+        }
+    } else {
         const double* Dg = d.D + (size_t)(a * nA) * B + i;
         const double* Eg = d.Eeq + (size_t)(a * nR) * B + i;
         const double* xg = d.x + (size_t)(a * nA) * B + i;
@@ -494,6 +579,18 @@ __global__ void __launch_bounds__(2 * IPW) mpc_chain_kernel(MpcDev d, MpcTickIO 
     const double dcm_a = io.dcm[(size_t)a * B + i];
     const double z0_in = d.z0[(size_t)a * B + i];
     cp_async_wait_all();
+    if (bulk) {
+        mbar_wait(sbar, bar_parity); bar_parity ^= 1;
+        if (cold) { // new OSQP workspace: x = y = z = 0 (the LDGSTS path zero-fills instead)
+#pragma unroll
+            for (int k = 0; k < nR; k++) { A_(XX, k) = 0.0; A_(YE, k) = 0.0; if (k < N) A_(XU, k) = 0.0; }
+            if (a == 0) {
+#pragma unroll
+                for (int h = 0; h < kMaxHull; h++) { H_(H_YH, h) = 0.0; H_(H_ZH, h) = 0.0; }
+            }
+        }
+        __syncwarp(WMASK);
+    }
     // scaled problem data from the raw copies: q (osqp_update_lin_cost), rows of A, bounds
     const double dx0_scale = A_(WX, 0), du0_scale = A_(WU, 0); // D of x_0 / u_0
     const double e0 = A_(CM, 0);
@@ -558,6 +655,24 @@ __global__ void __launch_bounds__(2 * IPW) mpc_chain_kernel(MpcDev d, MpcTickIO 
             // Phase 1 evaluates the residuals exactly once, after its last iteration (phase1_len is the
             // first check / rho update / max_iter): the factor arrays are dead (a rho update reloads
             // them), so D, Dinv, Einv land there with every copy in flight at once.
+            if (bulk) {
+                __syncwarp(WMASK); // every lane is done reading the factor rows
+                fence_async_smem();
+                if (lane == 0) mbar_expect_tx(sbar, (unsigned)((3 * nR + 2 * N) * 2 * 128));
+                __syncwarp(WMASK);
+#pragma unroll
+                for (int p = lane; p < 2 * nR; p += 32) {
+                    const int k = p >> 1, aa = p & 1;
+                    brow(O.L1X + k, aa, d.D, aa * nA + k);
+                    brow(O.L2X + k, aa, d.Dinv, aa * nA + k);
+                    brow(O.DIX + k, aa, d.Einv, aa * nR + k);
+                    if (k < N) {
+                        brow(O.L1U + k, aa, d.D, aa * nA + nR + k);
+                        brow(O.L2U + k, aa, d.Dinv, aa * nA + nR + k);
+                    }
+                }
+                mbar_wait(sbar, bar_parity); bar_parity ^= 1;
+            } else {
 #pragma unroll
             for (int k = 0; k < nR; k++) {
                 cp_async8(&A_(L1X, k), Dg + (size_t)k * B, true);
@@ -569,6 +684,7 @@ __global__ void __launch_bounds__(2 * IPW) mpc_chain_kernel(MpcDev d, MpcTickIO 
                 }
             }
             cp_async_wait_all();
+            }
         }
         auto DXv = [&](int k) { return PHASE2 ? Dg[(size_t)k * B] : A_(L1X, k); };
         auto DUv = [&](int k) { return PHASE2 ? Dg[(size_t)(nR + k) * B] : A_(L1U, k); };
@@ -1074,7 +1190,7 @@ int mpc_chain_ipw(int N)
     const Off O(N);
     const size_t maxs = (size_t)mpc_admm_max_smem();
     for (int ipw = kIPWmax; ipw >= 1; ipw >>= 1)
-        if (((size_t)O.total * 2 * ipw + (size_t)H_COUNT * 8 * ipw) * sizeof(double) <= maxs) return ipw;
+        if (((size_t)O.total * 2 * ipw + (size_t)H_COUNT * 8 * ipw + 2) * sizeof(double) <= maxs) return ipw;
     return 0;
 }
 
@@ -1082,7 +1198,7 @@ size_t mpc_chain_smem_bytes(int N)
 {
     const Off O(N);
     const int ipw = mpc_chain_ipw(N);
-    return ((size_t)O.total * 2 * ipw + (size_t)H_COUNT * 8 * ipw) * sizeof(double);
+    return ((size_t)O.total * 2 * ipw + (size_t)H_COUNT * 8 * ipw + 2) * sizeof(double); // + the staging mbarrier
 }
 
 static size_t mpc_chain_setup_warp_doubles(int N) { return (size_t)(3 * (4 * N + 2) + 2 * (2 * N + 2) + 32); }
