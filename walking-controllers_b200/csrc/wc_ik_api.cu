@@ -143,8 +143,9 @@ wc_status wc_ik_create(const wc_ik_config* cfg, const wc_model* model, int32_t B
         const bool fast = cfg->use_com_as_constraint && !(pth && !std::strcmp(pth, "general"));
         if (fast) {
             if (cudaMalloc(&h->d.slow_list, (size_t)B * sizeof(int32_t)) != cudaSuccess ||
-                cudaMalloc(&h->d.slow_count, sizeof(int32_t)) != cudaSuccess) { wc_ik_destroy(h); return WC_ERR_ALLOC; }
-            cudaMemset(h->d.slow_count, 0, sizeof(int32_t));
+                cudaMalloc(&h->d.second_list, (size_t)B * sizeof(int32_t)) != cudaSuccess ||
+                cudaMalloc(&h->d.slow_count, 2 * sizeof(int32_t)) != cudaSuccess) { wc_ik_destroy(h); return WC_ERR_ALLOC; }
+            cudaMemset(h->d.slow_count, 0, 2 * sizeof(int32_t));
         }
     }
     *out = h;
@@ -157,6 +158,7 @@ void wc_ik_destroy(wc_ik* h)
     cudaSetDevice(h->device);
     if (h->model_dev) cudaFree(h->model_dev);
     if (h->d.slow_list) cudaFree(h->d.slow_list);
+    if (h->d.second_list) cudaFree(h->d.second_list);
     if (h->d.slow_count) cudaFree(h->d.slow_count);
     if (h->kpos) cudaFree(h->kpos);
     if (h->katt) cudaFree(h->katt);
@@ -253,7 +255,7 @@ static wc_status launch_checked(wc_ik* h, const IkTickIO& io, int mode, cudaStre
         e = cudaMemcpyAsync(h->user_setups, h->d.osetups, (size_t)h->d.B * sizeof(int32_t), cudaMemcpyDeviceToDevice, s);
     if (osqp && h->user_flags && e == cudaSuccess)
         e = cudaMemcpyAsync(h->user_flags, h->d.oflags, (size_t)h->d.B * sizeof(int32_t), cudaMemcpyDeviceToDevice, s);
-    h->launches += two ? 2 : 1;
+    h->launches += two ? 3 : 1; // fast kernel, its second-pass launch, general kernel
     if (e != cudaSuccess) {
         std::fprintf(stderr, "[%s] CUDA error: %s\n", who, cudaGetErrorString(e));
         return WC_ERR_CUDA;
