@@ -335,6 +335,7 @@ def run_ours(args, world, rank, local_rank):
     ik_ok = (io_["status"] == 0).double().mean().item()
     wsc_mean = io_["nwsr"].double().mean().item()
     ws_frac = (io_["nwsr"] > 0).double().mean().item()
+    ik_second, ik_general_n = ik.path_counts()   # last tick: second pass of the fast kernel / general kernel
 
     t_ms = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -485,7 +486,8 @@ def run_ours(args, world, rank, local_rank):
                            "ik_general": ik_general_ms / max(nik, 1)},
             "stats": {"osqp_solved_frac": solved, "osqp_iters_mean": it_mean, "osqp_iters_max_last_tick": it_max,
                       "new_solver_frac": new_frac, "qpik_success_frac": ik_ok, "qpik_nwsr_mean": wsc_mean,
-                      "qpik_active_set_frac": ws_frac},
+                      "qpik_active_set_frac": ws_frac,
+                      "qpik_second_pass_frac": ik_second / B, "qpik_general_kernel_frac": ik_general_n / B},
             "roofline": {"bound": "hbm", "kernel": dom_name, "kernel_ms": dom_ms, "achieved": achieved, "peak": hbm_peak,
                          "unit": "GB/s", "frac": achieved / hbm_peak,
                          "traffic": ncu_traffic(dom_name) if (B == B_PER_GPU and N == HORIZON) else None,

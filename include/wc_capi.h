@@ -383,6 +383,10 @@ wc_status wc_ik_kernel_times_ms(wc_ik* h, double* ik_ms, int64_t* launches);
 /* Split of ik_ms of the window closed by the last wc_ik_kernel_times_ms call: fused-tick fast kernel /
  * general null-space + active-set kernel (the compacted remainder, or everything when the fast path is off). */
 wc_status wc_ik_kernel_times_detail_ms(wc_ik* h, double* fast_ms, double* general_ms);
+/* Path statistics of the last fused tick (synchronises the device): how many instances took the second pass of the
+ * fast kernel (their equality-constrained optimum violated a velocity bound: first working-set change in closed form)
+ * and how many went on to the general null-space + Goldfarb-Idnani kernel.  Both 0 when the fast path is off. */
+wc_status wc_ik_path_counts_host(wc_ik* h, int32_t* second_pass, int32_t* general);
 
 /* ---------------------------------------------------------------------------------- */
 /* Closed-loop glue between the two blocks: replaces, batched,     */

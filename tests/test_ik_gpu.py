@@ -199,3 +199,27 @@ def test_ik_rank_deficient_rows_flagged(wc, syn, oracle, cuda_device):
     assert np.array_equal(out["status"].cpu().numpy(), np.array(st_o, np.int32))
     assert (np.array(st_o) != 0).all()
     ik.close()
+
+
+def test_fast_path_second_pass_share(wc, syn, oracle, cuda_device, ik_path):
+    """the first working-set change is served by the fast kernel's second pass: with a workload whose bound violators
+    almost all need exactly one bound, the general kernel sees only the instances with two or more changes - and
+    status / nWSR / dq of every instance still equal the oracle's"""
+    if ik_path == "general":
+        pytest.skip("fast path off")
+    B = 2048
+    inp = make_inputs(syn, oracle, B, 11, perturb=0.5)
+    cfg_o = oracle.ik_default_config(); cfg_g = wc.ik_default_config()
+    out_o = oracle.ik_batch_tick(cfg_o, oracle.model_icub_like(), {k: v.numpy() for k, v in inp.items()})
+    ik = wc.IkBatch(cfg_g, wc.model_icub_like(), B)
+    og = ik.tick({k: v.to(cuda_device) for k, v in inp.items()})
+    torch.cuda.synchronize()
+    second, general = ik.path_counts()
+    out_g = {k: v.cpu().numpy() for k, v in og.items()}
+    _compare(out_g, out_o, "second pass")
+    n1 = int((out_o["nwsr"] == 1).sum()); n2 = int((out_o["nwsr"] >= 2).sum())
+    assert n1 > 0, "workload has no single-bound instances"
+    slack = max(2, n1 // 50)   # instances with unsafe Schur pivots go to the general kernel directly
+    assert abs(second - (n1 + n2)) <= slack, (second, n1, n2)   # every violator takes the second pass
+    assert general <= n2 + slack, (general, n1, n2)             # and (almost) only the multi-bound ones go on
+    ik.close()

@@ -217,6 +217,8 @@ def lib():
         L.wc_ik_kernel_times_ms.restype = i32
         L.wc_ik_kernel_times_detail_ms.argtypes = [_VP] + [C.POINTER(C.c_double)] * 2
         L.wc_ik_kernel_times_detail_ms.restype = i32
+        L.wc_ik_path_counts_host.argtypes = [_VP, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+        L.wc_ik_path_counts_host.restype = i32
     _LIB = L
     return L
 
@@ -489,6 +491,12 @@ class IkBatch:
         """(fast_ms, general_ms) of the window closed by the last kernel_times_ms() call"""
         a, b = C.c_double(), C.c_double()
         _check(lib().wc_ik_kernel_times_detail_ms(self.h, C.byref(a), C.byref(b)), "wc_ik_kernel_times_detail_ms")
+        return a.value, b.value
+
+    def path_counts(self):
+        """(second_pass, general): instances of the last fused tick that took the fast kernel's second pass / the general kernel"""
+        a, b = C.c_int32(), C.c_int32()
+        _check(lib().wc_ik_path_counts_host(self.h, C.byref(a), C.byref(b)), "wc_ik_path_counts_host")
         return a.value, b.value
 
 

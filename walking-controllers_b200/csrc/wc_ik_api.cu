@@ -525,4 +525,18 @@ wc_status wc_ik_kernel_times_detail_ms(wc_ik* h, double* fast_ms, double* genera
     return WC_OK;
 }
 
+wc_status wc_ik_path_counts_host(wc_ik* h, int32_t* second_pass, int32_t* general)
+{
+    if (!h) return WC_ERR_INVALID_ARG;
+    int32_t c[2] = {0, 0};
+    if (h->d.slow_count) {
+        cudaSetDevice(h->device);
+        if (cudaDeviceSynchronize() != cudaSuccess ||
+            cudaMemcpy(c, h->d.slow_count, sizeof(c), cudaMemcpyDeviceToHost) != cudaSuccess) return WC_ERR_CUDA;
+    }
+    if (general) *general = c[0];
+    if (second_pass) *second_pass = c[1];
+    return WC_OK;
+}
+
 } // extern "C"
