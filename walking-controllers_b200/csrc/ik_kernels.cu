@@ -951,7 +951,7 @@ struct IkFastLayout {
 };
 
 // SECOND = false: every instance, pass 0 only; an instance whose optimum violates a bound is appended to second_list.
-// SECOND = true : the instances of second_list, both passes.  (Both passes in ONE launch were measured: the 10 % of
+// SECOND = true : the instances of second_list, pass 1 only (the selected bound travels with the list entry).  (Both passes in ONE launch were measured: the 10 % of
 // warps that take the second pass hold their CTA's shared memory and registers 1.4x longer, 0.66 -> 0.83 ms.)
 template <int NJ, bool SECOND>
 __global__ void __launch_bounds__(kFastWarps * 32, WC_IK_FAST_MINB) ik_fast_kernel(IkDev d, IkTickIO io)
@@ -1060,8 +1060,26 @@ __global__ void __launch_bounds__(kFastWarps * 32, WC_IK_FAST_MINB) ik_fast_kern
     for (int r = 0; r < 9; r++) br_e[r] = br[r];
     double nu = 0.0;
     int nws = 0;
+    // fix variable id >> 1 at its lower (id even) or upper (id odd) bound for the next pass
+    auto fix_bound = [&](int id) {
+        const double lb = isj ? cfg.min_vel[j - 6] : -DBL_MAX, ub = isj ? cfg.max_vel[j - 6] : DBL_MAX;
+        const int pvar = id >> 1;
+        fixedl = lane == pvar;
+        beta = __shfl_sync(FULL, (id & 1) ? ub : lb, pvar);
+        double up3[3], wup[3];
+#pragma unroll
+        for (int r = 0; r < 3; r++) up3[r] = __shfl_sync(FULL, u[r], pvar);
+#pragma unroll
+        for (int r = 0; r < 3; r++) wup[r] = Wn[3 * r] * up3[0] + Wn[3 * r + 1] * up3[1] + Wn[3 * r + 2] * up3[2];
+        gr_e = (isj && !fixedl) ? gr + (u[0] * wup[0] + u[1] * wup[1] + u[2] * wup[2]) * beta : 0.0;
+#pragma unroll
+        for (int r = 0; r < 9; r++) br_e[r] = br[r] - __shfl_sync(FULL, a[r], pvar) * beta;
+        nws = 1;
+    };
+    // the second launch starts from the bound the first launch selected (stored next to the list entry)
+    if (SECOND) fix_bound(d.second_list[(size_t)d.B + inst]);
 #pragma unroll 1
-    for (int pass = 0;; pass++) {
+    for (int pass = SECOND ? 1 : 0;; pass++) {
     const double linv = (isj && lam > 0.0 && !fixedl) ? 1.0 / lam : 0.0;
     double ut[3], at[9];
 #pragma unroll
@@ -1195,10 +1213,6 @@ __global__ void __launch_bounds__(kFastWarps * 32, WC_IK_FAST_MINB) ik_fast_kern
         const bool viol = isj && !fixedl && ((lb > -kQpInf && nu < lb - kViolTol) || (ub < kQpInf && nu > ub + kViolTol));
         if (!__any_sync(FULL, viol)) break;       // optimal: nWSR = number of bounds fixed so far
         if (pass == 1) { fallback = true; break; } // a second working-set change: general kernel
-        if (!SECOND) { // hand over to the second launch
-            if (lane == 0) d.second_list[atomicAdd(d.slow_count + 1, 1)] = i;
-            return;
-        }
         // most violated bound, GI's rule: min over (slack, id = 2 j + upper), ties to the smaller id
         double best = INFINITY; int id = 0x7fffffff;
         if (isj) {
@@ -1211,18 +1225,14 @@ __global__ void __launch_bounds__(kFastWarps * 32, WC_IK_FAST_MINB) ik_fast_kern
             const int oi = __shfl_xor_sync(FULL, id, o);
             if (ob < best || (ob == best && oi < id)) { best = ob; id = oi; }
         }
-        const int pvar = id >> 1;
-        fixedl = lane == pvar;
-        beta = __shfl_sync(FULL, (id & 1) ? ub : lb, pvar);
-        double up3[3], wup[3];
-#pragma unroll
-        for (int r = 0; r < 3; r++) up3[r] = __shfl_sync(FULL, u[r], pvar);
-#pragma unroll
-        for (int r = 0; r < 3; r++) wup[r] = Wn[3 * r] * up3[0] + Wn[3 * r + 1] * up3[1] + Wn[3 * r + 2] * up3[2];
-        gr_e = (isj && !fixedl) ? gr + (u[0] * wup[0] + u[1] * wup[1] + u[2] * wup[2]) * beta : 0.0;
-#pragma unroll
-        for (int r = 0; r < 9; r++) br_e[r] = br[r] - __shfl_sync(FULL, a[r], pvar) * beta;
-        nws = 1;
+        if (!SECOND) { // hand over to the second launch, with the selected bound
+            if (lane == 0) {
+                const int idx = atomicAdd(d.slow_count + 1, 1);
+                d.second_list[idx] = i; d.second_list[(size_t)d.B + idx] = id;
+            }
+            return;
+        }
+        fix_bound(id);
         __syncwarp(); // the next pass overwrites the shared-memory operands
     }
     } // passes

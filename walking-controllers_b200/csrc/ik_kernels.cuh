@@ -62,7 +62,8 @@ struct IkDev {
     // fused-tick fast path (ik_fast_kernel): instances handed over to the general kernel
     int32_t* slow_list;      // [B] or nullptr (fast path disabled)
     int32_t* slow_count;     // [2]: [0] = entries of slow_list, [1] = entries of second_list
-    int32_t* second_list;    // [B] instances whose equality-constrained optimum violates a bound (second fast launch)
+    int32_t* second_list;    // [2 B] instances whose equality-constrained optimum violates a bound (second fast launch): [0, B) the
+                             // instance, [B, 2 B) the bound Goldfarb-Idnani adds first (2 * variable + upper)
     // WalkingQPIK_osqp (wc_ik_set_solver): OSQP settings and the persistent workspace of every instance, field-major
     int solver;              // WC_IK_SOLVER_*
     wc_osqp_settings osqp;

@@ -143,7 +143,7 @@ wc_status wc_ik_create(const wc_ik_config* cfg, const wc_model* model, int32_t B
         const bool fast = cfg->use_com_as_constraint && !(pth && !std::strcmp(pth, "general"));
         if (fast) {
             if (cudaMalloc(&h->d.slow_list, (size_t)B * sizeof(int32_t)) != cudaSuccess ||
-                cudaMalloc(&h->d.second_list, (size_t)B * sizeof(int32_t)) != cudaSuccess ||
+                cudaMalloc(&h->d.second_list, (size_t)2 * B * sizeof(int32_t)) != cudaSuccess ||
                 cudaMalloc(&h->d.slow_count, 2 * sizeof(int32_t)) != cudaSuccess) { wc_ik_destroy(h); return WC_ERR_ALLOC; }
             cudaMemset(h->d.slow_count, 0, 2 * sizeof(int32_t));
         }
