@@ -71,11 +71,6 @@ __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc)
     const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gsrc) : "memory");
 }
-__device__ __forceinline__ void cp_async_wait_all()
-{
-    asm volatile("cp.async.commit_group;\n" ::: "memory");
-    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-}
 __device__ __forceinline__ double warp_sum(double v)
 {
 #pragma unroll
