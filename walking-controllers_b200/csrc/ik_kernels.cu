@@ -20,6 +20,9 @@ constexpr int kWarpsPerBlock = 4;
 #ifndef WC_IK_SUBLOOP
 #define WC_IK_SUBLOOP 1
 #endif
+#ifndef WC_IK_MODEL_SMEM
+#define WC_IK_MODEL_SMEM 0 // fast kernel: 1 = model table staged in shared memory per CTA; 0 = read through L1 (measured 0.741 -> 0.731 ms)
+#endif
 #ifndef WC_IK_FAST_MINB
 #define WC_IK_FAST_MINB 4 // resident CTAs per SM the fast kernel is compiled for (register cap 128)
 #endif
@@ -960,12 +963,14 @@ __global__ void __launch_bounds__(kFastWarps * 32, WC_IK_FAST_MINB) ik_fast_kern
     const int warp = threadIdx.x >> 5;
     if (SECOND && (long long)blockIdx.x * kFastWarps >= (long long)d.slow_count[1]) return; // CTA beyond the list
     // model table: one shared-memory copy per CTA (every lane indexes it by its own link / joint)
+#if WC_IK_MODEL_SMEM
     double* sm_model = smem_all + (size_t)kFastWarps * LY::TOTAL;
     {
         const double* src = reinterpret_cast<const double*>(d.model);
         for (int k = threadIdx.x; k < LY::MODEL_DOUBLES; k += kFastWarps * 32) sm_model[k] = src[k];
     }
     __syncthreads();
+#endif
     // (a one-wave grid striding over the instances, to stage the model table once per CTA, was measured: the loop
     // costs more registers / spills than the copy's latency it saves, 0.71 -> 0.74 ms)
     const long long inst = (long long)blockIdx.x * kFastWarps + warp;
@@ -987,7 +992,11 @@ __global__ void __launch_bounds__(kFastWarps * 32, WC_IK_FAST_MINB) ik_fast_kern
     double* WL = sm; double* MC = sm + WC_MAX_LINKS * 12;
     double* AS = sm + LY::O_AS; double* UT = sm + LY::O_UT; double* HS = sm + LY::O_HS;
     double* GR = sm + LY::O_GR; double* GK = sm + LY::O_GK; double* SS = sm + LY::O_SS;
+#if WC_IK_MODEL_SMEM
     const IkModelDev& M = *reinterpret_cast<const IkModelDev*>(sm_model);
+#else
+    const IkModelDev& M = *d.model; // 5 KB table read through L1 (every CTA of the SM shares the lines)
+#endif
     const wc_ik_config& cfg = d.cfg;
     const int j = lane;
     const bool isj = j >= 6 && j < NV;
@@ -1270,7 +1279,7 @@ cudaError_t launch_t(const IkDev& d, const IkTickIO& io, int mode, cudaStream_t 
     if (COMC && mode == IK_MODE_TICK && d.slow_list) {
         // fast path for every instance, then the general kernel on the compacted remainder
         using LF = IkFastLayout<NJ>;
-        const size_t smem_f = ((size_t)LF::TOTAL * kFastWarps + LF::MODEL_DOUBLES) * sizeof(double);
+        const size_t smem_f = ((size_t)LF::TOTAL * kFastWarps + (WC_IK_MODEL_SMEM ? LF::MODEL_DOUBLES : 0)) * sizeof(double);
         e = cudaFuncSetAttribute(ik_fast_kernel<NJ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f);
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(ik_fast_kernel<NJ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f);
