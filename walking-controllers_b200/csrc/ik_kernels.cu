@@ -924,7 +924,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) ik_kernel(IkDev d, IkTick
 // not safely positive definite, are appended to slow_list and solved by ik_kernel (null space +
 // Goldfarb-Idnani) in a second, compacted launch: every status / nWSR decision stays with that kernel.
 // =====================================================================================================
-constexpr int kFastWarps = 4;
+#ifndef WC_IK_FAST_WARPS
+#define WC_IK_FAST_WARPS 4
+#endif
+constexpr int kFastWarps = WC_IK_FAST_WARPS;
 
 template <int NJ>
 struct IkFastLayout {
