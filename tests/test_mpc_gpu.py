@@ -11,15 +11,16 @@ pytestmark = pytest.mark.gpu
 REL = 1e-6
 
 
-@pytest.fixture(autouse=True, params=["auto", "coop"])
+@pytest.fixture(autouse=True, params=["auto", "chain", "coop"])
 def mpc_path(request, monkeypatch):
-    """every test runs on both ADMM kernel families: "auto" = chain-per-thread kernels (mpc_chain.cu; forced with
-    WC_MPC_PATH=chain so that long horizons with 8, 4, ... instances per CTA are covered too, N = 1 falls back),
+    """every test runs on the three ADMM kernel families: "auto" = what wc_mpc_create picks (the split-chain kernels of
+    mpc_split.cu at their compile-time horizons, else chain / cooperative), "chain" = chain-per-thread kernels
+    (mpc_chain.cu; forced so that long horizons with 8, 4, ... instances per CTA are covered too, N = 1 falls back),
     "coop" = cooperative kernel (mpc_kernels.cu)"""
-    if request.param == "coop":
-        monkeypatch.setenv("WC_MPC_PATH", "coop")
+    if request.param == "auto":
+        monkeypatch.delenv("WC_MPC_PATH", raising=False)
     else:
-        monkeypatch.setenv("WC_MPC_PATH", "chain")
+        monkeypatch.setenv("WC_MPC_PATH", request.param)
     return request.param
 
 

@@ -353,7 +353,7 @@ class MpcBatch:
 
     @property
     def path(self):
-        return "chain" if lib().wc_mpc_path(self.h) == 1 else "coop"
+        return {2: "split", 1: "chain"}.get(lib().wc_mpc_path(self.h), "coop")
 
 
 IK_INPUT_KEYS = ("q_meas", "q_lin", "base_H", "left_is_fixed", "lf_H_des", "rf_H_des", "lf_twist", "rf_twist",

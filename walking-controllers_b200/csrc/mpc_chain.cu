@@ -301,7 +301,7 @@ __device__ __forceinline__ double warp_sum_d(double v)
     return v;
 }
 
-__global__ void __launch_bounds__(kSetupWarps * 32) mpc_chain_setup_kernel(MpcDev d, int warp_doubles)
+__global__ void __launch_bounds__(kSetupWarps * 32) mpc_chain_setup_kernel(MpcDev d, int warp_doubles, int do_factor)
 {
     extern __shared__ double smem_all[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -427,7 +427,8 @@ __global__ void __launch_bounds__(kSetupWarps * 32) mpc_chain_setup_kernel(MpcDe
     }
     __syncwarp();
     // numeric factorisation (osqp_setup -> init_linsys_solver): the two axis chains on lanes 0 and 16
-    if ((lane & 15) == 0) chain_factor(d, i, lane >> 4, N, c, rho0, nh, 0x00010001u, true, DD + (lane >> 4) * nA, EE + (lane >> 4) * nR);
+    // (the split-chain kernels, mpc_split.cu, rebuild their factors in the ADMM kernel and skip this)
+    if (do_factor && (lane & 15) == 0) chain_factor(d, i, lane >> 4, N, c, rho0, nh, 0x00010001u, true, DD + (lane >> 4) * nA, EE + (lane >> 4) * nR);
     __syncwarp();
     } // list entries
 }
@@ -1227,18 +1228,24 @@ static cudaError_t launch_chain_t(const MpcDev& d, const MpcTickIO& io, cudaStre
     return cudaGetLastError();
 }
 
+// osqp_setup of the instances K1 listed (Ruiz equilibration; with `factor` also the chain kernels' LDL' to HBM)
+cudaError_t launch_mpc_chain_setup(const MpcDev& d, cudaStream_t s, bool factor)
+{
+    const size_t td = mpc_chain_setup_warp_doubles(d.N);
+    const size_t smem_setup = td * kSetupWarps * sizeof(double);
+    cudaError_t e = cudaFuncSetAttribute(mpc_chain_setup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_setup);
+    if (e != cudaSuccess) return e;
+    const int need = (d.B + kSetupWarps - 1) / kSetupWarps;
+    mpc_chain_setup_kernel<<<need < 4 * 148 ? need : 4 * 148, kSetupWarps * 32, smem_setup, s>>>(d, (int)td, factor ? 1 : 0); // grid-stride over setup_list
+    return cudaGetLastError();
+}
+
 cudaError_t launch_mpc_chain(const MpcDev& d, const MpcTickIO& io, cudaStream_t s, cudaEvent_t* mid)
 {
     const int N = d.N;
     const size_t smem = mpc_chain_smem_bytes(N);
-    const size_t td = mpc_chain_setup_warp_doubles(N);
-    const size_t smem_setup = td * kSetupWarps * sizeof(double);
-    cudaError_t e = cudaFuncSetAttribute(mpc_chain_setup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_setup);
+    cudaError_t e = launch_mpc_chain_setup(d, s, true);
     if (e != cudaSuccess) return e;
-    {
-        const int need = (d.B + kSetupWarps - 1) / kSetupWarps;
-        mpc_chain_setup_kernel<<<need < 4 * 148 ? need : 4 * 148, kSetupWarps * 32, smem_setup, s>>>(d, (int)td); // grid-stride over setup_list
-    }
     switch (mpc_chain_ipw(N)) {
     case 16: return N == 25 ? launch_chain_t<25, 16>(d, io, s, mid, smem) : launch_chain_t<0, 16>(d, io, s, mid, smem);
     case 8: return launch_chain_t<0, 8>(d, io, s, mid, smem);

@@ -115,5 +115,9 @@ bool mpc_chain_preferred(int N);
 size_t mpc_chain_smem_bytes(int N);
 // mid (nullable): two events recorded after the setup kernel and after phase 1
 cudaError_t launch_mpc_chain(const MpcDev& d, const MpcTickIO& io, cudaStream_t s, cudaEvent_t* mid);
+cudaError_t launch_mpc_chain_setup(const MpcDev& d, cudaStream_t s, bool factor);
+// split-chain path (mpc_split.cu): four lanes per instance, iterate in registers; compile-time horizons
+bool mpc_split_supported(int N);
+cudaError_t launch_mpc_split(const MpcDev& d, const MpcTickIO& io, cudaStream_t s, cudaEvent_t* mid);
 
 } // namespace wcb

@@ -1,0 +1,883 @@
+// mpc_split.cu — "split-chain" variant of the batched OSQP-equivalent ADMM (K2): FOUR LANES PER INSTANCE, the
+// iterate in REGISTERS, the problem in UNSCALED variables.  The benchmark path (N = 25).
+//
+// Same QP, same iterates as mpc_chain.cu / mpc_admm_kernel (mapping to the reference in mpc_kernels.cuh:
+// WalkingController::solve -> MPCSolver::solve -> OSQP, WM/src/WalkingDCMModelPredictiveController.cpp:491-521,
+// WM/src/MPCSolver.cpp:295-322).  What changes is how the reduced KKT step is organised on the machine
+// (lane-accurate CPU prototype, checked against dense OSQP iterations: tools/split_lane_proto.py).
+//
+// 1. Unscaled variables.  OSQP iterates on Pb = c D P D, qb = c D q, Ab = E A D.  With X = D xb, Yh = E yb the step
+//        (Pb + sigma I + Ab' rho Ab) xt = sigma xb - qb + Ab' (rho zb - yb)
+//    is, after a left multiplication by D^-1,
+//        (c P + sigma D^-2 + A' (rho E^2) A) Xt = sigma D^-2 X - c q + A' E (rho zb - yb)
+//    in which A carries the CONSTANT coefficients (-1, a, b) of the LIPM recursion: the three coefficient arrays of
+//    the scaled rows disappear, and the unscaled residuals of check_termination need no scaling vectors at all.
+//    The iterates are OSQP's (same scaled problem in exact arithmetic; the persistent workspace in HBM stays OSQP's
+//    scaled x, y, z): iteration counts and status match the oracle on every test.
+// 2. Split chain.  Per axis the unknowns x_N, u_{N-1}, ..., x_1, u_0, x_0 form a pentadiagonal chain.  Two lanes share
+//    it: the TOP lane eliminates x_N, u_{N-1}, ... downwards, the BOTTOM lane x_0, x_1, u_1, ... upwards with u_0
+//    carried as a border column; they meet at a two-unknown separator (x_s, u_{s-1}).  What is left is a dense 6x6 on
+//    (x_s, u_{s-1}, u_0) of both axes (the hull rows couple u_0x and u_0y), whose inverse is kept in shared memory.
+//    A warp = 8 instances x (2 axes x 2 halves); the dependent chain per lane is half as long as in mpc_chain.cu.
+// 3. Registers.  A lane's T = ceil((N+1)/2) slots are fully unrolled (compile-time horizon), so its share of the
+//    iterate (X, U, Yh) and the forward-sweep result live in registers (5 T doubles); shared memory holds constants
+//    only (10 arrays + the border): ~16 LDS per slot and iteration instead of ~30 LDS/STS per stage, which is what
+//    bounded the chain kernel (shared-memory pipe).  ~42 KB per single-warp CTA -> 5 CTAs per SM.
+// 4. The LDL' factors are rebuilt in the kernel every tick from (D, E, c, rho) -- one ADMM iteration's worth of
+//    work out of 25 -- instead of being kept in HBM: no factor arrays, no extra traffic, and a rho update refactors
+//    in place.
+//
+// Slots.  top lane   t = 0..T-1   <-> (x_k, u_{k-1}), equality row k,   k = N - t;  slot T-1 is the separator
+//         bottom lane t = OFF..T-1 <-> (x_j, u_j),     equality row j+1, j = t - OFF; u_0 (slot OFF) is the border,
+//         its last slot holds x_{s-1} and a shadow copy of the separator's u_{s-1} and row s (kept bitwise equal).
+#include "mpc_kernels.cuh"
+
+#include <cmath>
+#include <cstdio>
+#include <type_traits>
+
+namespace wcb {
+
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+#ifndef WC_SPLIT_MINB
+#define WC_SPLIT_MINB 5
+#endif
+
+template <int N>
+struct SplitDims {
+    static constexpr int T = (N + 2) / 2;   // slots per lane
+    static constexpr int TB = N + 1 - T;    // real slots of the bottom lane
+    static constexpr int OFF = T - TB;      // leading dummy slots of the bottom lane (0 or 1)
+    enum { A_SX = 0, A_SU, A_CQ, A_EE, A_L1X, A_L2X, A_DIX, A_L1U, A_L2U, A_DIU, A_COUNT };
+    static constexpr int oLBX = A_COUNT * T * 32; // border multipliers, bottom lanes only: [T][16]
+    static constexpr int oLBU = oLBX + T * 16;
+    static constexpr int kMAxis = 19;              // 3 rows x 6 + 1 pad: the two axes land on complementary banks
+    static constexpr int oM = oLBU + T * 16;       // rows (x_s, u_{s-1}, u_0) of the 6x6 inverse per axis: [2][19][8]
+    enum { H_HXS = 0, H_HYS, H_LO, H_UP, H_EH, H_EHI, H_COUNT };
+    static constexpr int oH = oM + 2 * kMAxis * 8; // hull constants [H_COUNT][8 rows][8 instances]
+    static constexpr int total = oH + H_COUNT * 8 * 8;
+};
+
+__device__ __forceinline__ double sx16(double v) { return __shfl_xor_sync(FULL, v, 16); }
+__device__ __forceinline__ double sx8(double v) { return __shfl_xor_sync(FULL, v, 8); }
+// reductions over the four lanes of an instance (lane bits 3 and 4); symmetric, so all four get the same bits
+__device__ __forceinline__ double inst_max(double v) { v = fmax(v, sx8(v)); return fmax(v, sx16(v)); }
+__device__ __forceinline__ double inst_sum(double v) { v += sx8(v); return v + sx16(v); }
+
+// LDL' of a symmetric 6x6 (lower triangle of M), then rows of the inverse by two triangular solves
+struct Ldl6 {
+    double L[6][6], Dinv[6];
+    __device__ __forceinline__ void factor(const double (*M)[6])
+    {
+        double Dv[6];
+#pragma unroll
+        for (int j = 0; j < 6; j++) {
+            double dj = M[j][j];
+            double lj[6];
+#pragma unroll
+            for (int k = 0; k < j; k++) { lj[k] = L[j][k] * Dv[k]; dj -= L[j][k] * lj[k]; }
+            Dv[j] = dj;
+            Dinv[j] = 1.0 / dj;
+#pragma unroll
+            for (int i = j + 1; i < 6; i++) {
+                double v = M[i][j];
+#pragma unroll
+                for (int k = 0; k < j; k++) v -= L[i][k] * lj[k];
+                L[i][j] = v * Dinv[j];
+            }
+        }
+    }
+    __device__ __forceinline__ void solve(double* r) const
+    {
+#pragma unroll
+        for (int i = 1; i < 6; i++) {
+#pragma unroll
+            for (int k = 0; k < i; k++) r[i] -= L[i][k] * r[k];
+        }
+#pragma unroll
+        for (int i = 0; i < 6; i++) r[i] *= Dinv[i];
+#pragma unroll
+        for (int i = 4; i >= 0; i--) {
+#pragma unroll
+            for (int k = i + 1; k < 6; k++) r[i] -= L[k][i] * r[k];
+        }
+    }
+};
+
+} // namespace
+
+// =====================================================================================
+// ADMM.  PHASE2 == false: all instances, iterations 1 .. first termination check.
+//        PHASE2 == true : the instances of the continuation list, until osqp_solve returns.
+// One warp per CTA, 8 instances per warp: lane = half * 16 + axis * 8 + instance slot.
+// =====================================================================================
+template <bool PHASE2, int NT>
+__global__ void __launch_bounds__(32, WC_SPLIT_MINB) mpc_split_kernel(MpcDev d, MpcTickIO io)
+{
+    using SD = SplitDims<NT>;
+    constexpr int N = NT, T = SD::T, OFF = SD::OFF, nA = 2 * N + 1, nR = N + 1;
+    static_assert(N >= 4, "the split needs a separator away from u_0 / u_1");
+    extern __shared__ double sm[];
+    const int lane = threadIdx.x;
+    const int s8 = lane & 7, a = (lane >> 3) & 1, q4 = lane >> 3;
+    const bool bot = lane >= 16;
+    const size_t B = (size_t)d.B;
+    double* const sl = sm + lane;                    // full arrays: element (arr, t) at sl[(arr * T + t) * 32]
+    double* const sb = sm + SD::oLBX + (lane & 15);  // border arrays (bottom lanes)
+    double* const smr = sm + SD::oM + a * SD::kMAxis * 8 + s8;
+    double* const sh = sm + SD::oH + s8;             // hull constants: (arr, h) at sh[(arr * 8 + h) * 8]
+#define S_(arr, t) sl[((SD::arr) * T + (t)) * 32]
+#define LBX_(t) sb[(t) * 16]
+#define LBU_(t) sb[(T + (t)) * 16]
+#define HC_(arr, h) sh[((SD::arr) * 8 + (h)) * 8]
+    if (!PHASE2 && blockIdx.x == 0 && lane == 0) *d.setup_count = 0; // consumed by the setup kernel of this tick
+    const int count = PHASE2 ? *d.cont_count : d.B;
+    const int ngroups = (count + 7) / 8;
+    const wc_osqp_settings& st = d.st;
+    const double sigma = st.sigma, alpha = st.alpha, infty = st.infty;
+    const double a_ = d.a_dyn, b_ = d.b_dyn;
+    // lane constants of the generic slot program: A'(-Yh) on x = cy0 Yh[t] + cy1 Yh[t-1]; row = b u + (-cy0) x + (-cy1) x_next
+    const double cy0 = bot ? -a_ : 1.0, cy1 = bot ? 1.0 : -a_;
+    const double cx0 = -cy0, cx1 = -cy1;
+    const double k1 = 1.0 / alpha - 1.0;             // X~ = X+ + k1 dX
+
+    for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+    const int li = grp * 8 + s8;
+    const bool valid = li < count;
+    const int i = PHASE2 ? d.cont_list[valid ? li : count - 1] : (valid ? li : d.B - 1);
+    const int kflags = d.tick_flags[i];
+    const bool skip = !valid || (kflags & (WC_MPC_FLAG_NO_CONTACT | WC_MPC_FLAG_NO_SOLVER)) != 0;
+    const int nh = skip ? 0 : d.nhull[i];
+    const double Qa = d.Qd[(size_t)a * B + i], Ra = d.Rd[(size_t)a * B + i];
+    const int init_state = d.inited[i];
+    const bool cold = !PHASE2 && !skip && init_state == 2; // new OSQP workspace: x = y = z = 0
+    const double c = d.cscale[i];
+    double rho = d.rho[i];
+    const double upa = d.uprev[(size_t)a * B + i];
+    const int head = d.ring_head;
+    const double cQ = c * Qa, cR = c * Ra;
+    const double cinv = 1.0 / c;
+    const double cqu0 = c * (-(Ra * upa));           // c q of u_0 (MPCSolver.cpp:244-245: G u_prev, first block only)
+    const double dcm_a = io.dcm[(size_t)a * B + i];
+
+    // ------------------------------------------------------------------ stage in: raw HBM -> registers / constants
+    double X[T], U[T], Y[T], tX[T], tU[T];
+    {
+        const int kx0 = bot ? -OFF : N;              // x index of slot 0; +1 / -1 per slot
+        const ptrdiff_t sB = bot ? (ptrdiff_t)B : -(ptrdiff_t)B;
+        const ptrdiff_t xrow0 = ((ptrdiff_t)(a * nA + kx0)) * (ptrdiff_t)B + i;
+        const ptrdiff_t urow0 = ((ptrdiff_t)(a * nA + nR + kx0 - (bot ? 0 : 1))) * (ptrdiff_t)B + i;
+        const ptrdiff_t erow0 = ((ptrdiff_t)(a * nR + kx0 + (bot ? 1 : 0))) * (ptrdiff_t)B + i;
+        int gs = head + kx0; gs = gs >= nR ? gs - nR : (gs < 0 ? gs + nR : gs); // ring slot of stage kx0
+        const int gstep = bot ? 1 : -1;
+#pragma unroll
+        for (int t = 0; t < T; t++) {
+            const bool real = (t >= OFF) || !bot;
+            double dx = 0, dix = 0, du = 0, diu = 0, e = 0, g = 0, xb = 0, ub = 0, yb = 0;
+            if (real) {
+                const ptrdiff_t xr = xrow0 + t * sB, ur = urow0 + t * sB, er = erow0 + t * sB;
+                dx = d.D[xr]; dix = d.Dinv[xr]; du = d.D[ur]; diu = d.Dinv[ur]; e = d.Eeq[er];
+                g = d.grad[(size_t)(a * nR + gs) * B + i];
+                if (!cold) { xb = d.x[xr]; ub = d.x[ur]; yb = d.yeq[er]; }
+            }
+            gs += gstep; gs = gs >= nR ? gs - nR : (gs < 0 ? gs + nR : gs);
+            S_(A_SX, t) = sigma * (dix * dix);
+            S_(A_SU, t) = sigma * (diu * diu);
+            S_(A_CQ, t) = c * g;
+            S_(A_EE, t) = e * e;
+            X[t] = dx * xb; U[t] = du * ub; Y[t] = e * yb;
+            tX[t] = 0.0; tU[t] = 0.0;
+        }
+    }
+    // bottom lanes: equality row 0 (l = u = -dcm, MPCSolver.cpp:143-146) and its unscaled z
+    double EE0 = 0.0, Y0 = 0.0, Z0 = 0.0, E0 = 1.0;
+    if (bot) {
+        E0 = d.Eeq[(size_t)(a * nR) * B + i];
+        EE0 = E0 * E0;
+        if (!cold) Y0 = E0 * d.yeq[(size_t)(a * nR) * B + i];
+        Z0 = PHASE2 ? -dcm_a : (cold ? 0.0 : d.z0[(size_t)a * B + i] * d.Einv[(size_t)(a * nR) * B + i]);
+    }
+    // hull rows q4 and q4 + 4 of the instance: constants to shared memory, (z, y) in registers (scaled, as OSQP keeps them)
+    double zh[2], yh[2], dyh[2] = {0.0, 0.0};
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        const int h = q4 + 4 * r;
+        const bool on = h < nh;
+        const double e = d.Eh[(size_t)h * B + i];
+        const double hx = d.hullA[(size_t)(2 * h) * B + i], hy = d.hullA[(size_t)(2 * h + 1) * B + i];
+        const double hb = d.hullb[(size_t)h * B + i];
+        HC_(H_HXS, h) = on ? e * hx : 0.0;
+        HC_(H_HYS, h) = on ? e * hy : 0.0;
+        HC_(H_LO, h) = on ? e * (-infty) : -1.0;
+        HC_(H_UP, h) = on ? e * hb : 1.0;
+        HC_(H_EH, h) = on ? e : 1.0;
+        HC_(H_EHI, h) = on ? 1.0 / e : 1.0;
+        zh[r] = (on && !cold) ? d.zh[(size_t)h * B + i] : 0.0;
+        yh[r] = (on && !cold) ? d.yh[(size_t)h * B + i] : 0.0;
+    }
+    __syncwarp();
+
+    // ------------------------------------------------------------------ numeric factorisation (per tick and after a rho update)
+    auto build_factor = [&]() {
+        const double rho_e = kRhoEqOverIneq * rho;
+        const double a2 = a_ * a_, b2 = b_ * b_, ab = a_ * b_;
+        double hxx = 0.0, hyy = 0.0, hxy = 0.0;
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            const double hx = HC_(H_HXS, q4 + 4 * r), hy = HC_(H_HYS, q4 + 4 * r);
+            hxx += hx * hx; hyy += hy * hy; hxy += hx * hy;
+        }
+        hxx = inst_sum(hxx); hyy = inst_sum(hyy); hxy = inst_sum(hxy);
+        const double hd = rho * (a == 0 ? hxx : hyy), kxy = rho * hxy;
+        // carried: multipliers and (multiplier x pivot) of the previous two unknowns of the elimination order
+        double l1p = 0, m1p = 0, l2p = 0, m2p = 0, lbp = 0, l2pp = 0, m2pp = 0, lbpp = 0, Sbb = 0;
+        double Wprev = bot ? rho_e * EE0 : 0.0;
+        double pxx = 0, puu = 0, pxu = 0, p0x = 0, p0u = 0, p00 = 0, g_u0 = 0;
+#pragma unroll
+        for (int t = 0; t < T; t++) {
+            const double W = rho_e * S_(A_EE, t);
+            const double sc = (t == 0) ? (bot ? 2.0 : 1.0) : 2.0; // u_{N-1} (top slot 0) has the single diagonal block of Theta' R Theta
+            double g_x = cQ + S_(A_SX, t) + (bot ? (Wprev + a2 * W) : (W + a2 * Wprev));
+            double g_u = cR * sc + S_(A_SU, t) + b2 * W;
+            double s1x = bot ? ab * W : -b_ * W;
+            double s2x = -a_ * W;
+            double s1u = bot ? -b_ * W : ab * W;
+            double s2u = -cR;
+            double bdx = 0.0, bdu = 0.0;
+            bool u_dummy = false;
+            if (t == OFF) { if (bot) { s1x = 0.0; bdx = ab * W; u_dummy = true; g_u0 = g_u + hd; } }
+            if (t == OFF + 1) { if (bot) { bdx = -b_ * (rho_e * S_(A_EE, OFF)); bdu = -cR; } }
+            if (t < OFF) { if (bot) { g_x = 1.0; g_u = 1.0; s1x = s2x = s1u = s2u = 0.0; u_dummy = true; } }
+            if (t == T - 1) { // the separator seen from the top lane: Schur terms of its last two unknowns
+                if (!bot) {
+                    pxx = g_x - (l1p * m1p + l2pp * m2pp);
+                    puu = g_u - l2p * m2p;
+                    pxu = s1x - l2p * m1p;
+                }
+            }
+            { // x part
+                const double dd = g_x - l1p * m1p - l2pp * m2pp;
+                const double m1 = s1x - l2p * m1p, m2 = s2x, mb = bdx - lbp * m1p - lbpp * m2pp;
+                const double di = 1.0 / dd;
+                const double l1 = m1 * di, l2 = m2 * di, lb = mb * di;
+                S_(A_L1X, t) = l1; S_(A_L2X, t) = l2;
+                S_(A_DIX, t) = (t < OFF) ? (bot ? 0.0 : di) : di;
+                if (bot) LBX_(t) = lb;
+                Sbb += lb * mb;
+                l2pp = l2p; m2pp = m2p; lbpp = lbp;
+                l1p = l1; m1p = m1; l2p = l2; m2p = m2; lbp = lb;
+            }
+            if (t == T - 1) { // bottom: near = u_{s-1}, far = x_s
+                if (bot) {
+                    pxx = -(l2p * m2p);
+                    puu = -(l1p * m1p + l2pp * m2pp);
+                    pxu = -(l2p * m1p);
+                    p0x = -(lbp * m2p);
+                    p0u = ((T - 1 - OFF) == 1 ? -cR : 0.0) - (lbp * m1p + lbpp * m2pp);
+                    p00 = g_u0 - Sbb;
+                }
+                break;
+            }
+            { // u part
+                const double dd = g_u - l1p * m1p - l2pp * m2pp;
+                double m1 = s1u - l2p * m1p, m2 = s2u, mb = bdu - lbp * m1p - lbpp * m2pp;
+                double di = 1.0 / dd;
+                double l1 = m1 * di, l2 = m2 * di, lb = mb * di;
+                if (u_dummy) { m1 = m2 = mb = 0.0; l1 = l2 = lb = 0.0; di = 0.0; }
+                S_(A_L1U, t) = l1; S_(A_L2U, t) = l2; S_(A_DIU, t) = di;
+                if (bot) LBU_(t) = lb;
+                Sbb += lb * mb;
+                l2pp = l2p; m2pp = m2p; lbpp = lbp;
+                l1p = l1; m1p = m1; l2p = l2; m2p = m2; lbp = lb;
+            }
+            if (t >= OFF || !bot) Wprev = W;
+        }
+        S_(A_L1U, T - 1) = 0.0; S_(A_L2U, T - 1) = 0.0; S_(A_DIU, T - 1) = 0.0;
+        if (bot) LBU_(T - 1) = 0.0;
+        // the 6x6 on (x_s, u_{s-1}, u_0) of this axis and of the other one
+        pxx += sx16(pxx); puu += sx16(puu); pxu += sx16(pxu); p0x += sx16(p0x); p0u += sx16(p0u); p00 += sx16(p00);
+        const double oxx = sx8(pxx), ouu = sx8(puu), oxu = sx8(pxu), o0x = sx8(p0x), o0u = sx8(p0u), o00 = sx8(p00);
+        double M[6][6];
+#pragma unroll
+        for (int r = 0; r < 6; r++)
+#pragma unroll
+            for (int cc = 0; cc < 6; cc++) M[r][cc] = 0.0;
+        M[0][0] = pxx; M[1][0] = pxu; M[1][1] = puu; M[2][0] = p0x; M[2][1] = p0u; M[2][2] = p00;
+        M[3][3] = oxx; M[4][3] = oxu; M[4][4] = ouu; M[5][3] = o0x; M[5][4] = o0u; M[5][5] = o00;
+        M[5][2] = kxy;
+        Ldl6 F;
+        F.factor(M);
+        // rows of the inverse: the top lane solves for x_s and u_{s-1}, the bottom lane for u_0
+        double r0[6], r1[6];
+#pragma unroll
+        for (int k = 0; k < 6; k++) { r0[k] = (k == (bot ? 2 : 0)) ? 1.0 : 0.0; r1[k] = (k == 1) ? 1.0 : 0.0; }
+        F.solve(r0);
+        F.solve(r1);
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+            smr[((bot ? 2 : 0) * 6 + k) * 8] = r0[k];
+            if (!bot) smr[(6 + k) * 8] = r1[k];
+        }
+        __syncwarp();
+    };
+    build_factor();
+
+    // ------------------------------------------------------------------ ADMM (osqp_solve)
+    int status = WC_OSQP_UNSOLVED;
+    int iter_done = 0, rho_updates = PHASE2 ? d.rho_updates[i] : 0;
+    bool done = skip;
+    double pri_res = 0.0, dua_res = 0.0;
+    double nz_u = 0, nAx_u = 0, nq_u = 0, nAty_u = 0, nPx_u = 0;
+    double rp_s = 0, rd_s = 0, nz_s = 0, nAx_s = 0, nq_s = 0, nAty_s = 0, nPx_s = 0;
+    double Yext = Y0 - (kRhoEqOverIneq * rho * EE0) * Z0;  // Yh_0 - W_0 Z_0: the row-0 term of x_0's right-hand side
+    double dY0 = 0.0;
+    // hull rows' share of the right-hand side of u_0 (this axis, the other axis), from the current (z, y)
+    double hp_m = 0.0, hp_o = 0.0;
+    auto hull_partials = [&]() {
+        double px = 0.0, py = 0.0;
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            const double v = rho * zh[r] - yh[r];
+            px += HC_(H_HXS, q4 + 4 * r) * v;
+            py += HC_(H_HYS, q4 + 4 * r) * v;
+        }
+        hp_m = a == 0 ? px : py;
+        hp_o = a == 0 ? py : px;
+    };
+    hull_partials();
+
+    // one ADMM iteration on the whole warp; `act` freezes finished instances (phase 2 only)
+    auto iteration = [&](bool act) {
+        const double rho_e = kRhoEqOverIneq * rho, arho = alpha * rho_e, rho_inv = 1.0 / rho;
+        const double oma = 1.0 - alpha;
+        // ---- forward: right-hand side fused with L t = rhs, towards the separator
+        double txp = 0.0, tup = 0.0;                 // t of the previous slot's x and u
+        double n1u = 0.0, n2x = 0.0, n2u = 0.0;      // l1u, l2x, l2u of the previous slot
+        double rb = 0.0, vx = 0.0, vu = 0.0;
+#pragma unroll
+        for (int t = 0; t < T; t++) {
+            double yprev;
+            if (t == OFF) yprev = bot ? Yext : (t == 0 ? 0.0 : Y[t > 0 ? t - 1 : 0]);
+            else yprev = (t == 0) ? 0.0 : Y[t > 0 ? t - 1 : 0];
+            double rx = fma(S_(A_SX, t), X[t], -S_(A_CQ, t));
+            rx = fma(cy0, Y[t], rx);
+            rx = fma(cy1, yprev, rx);
+            double ru = S_(A_SU, t) * U[t];
+            ru = fma(-b_, Y[t], ru);
+            if (t == OFF) { if (bot) rb = ru - cqu0; }
+            const double l1x = S_(A_L1X, t), l2x = S_(A_L2X, t);
+            const double tx = fma(-n1u, tup, fma(-n2x, txp, rx));
+            if (t < T - 1) {
+                const double l1u = S_(A_L1U, t), l2u = S_(A_L2U, t);
+                const double tu = fma(-l1x, tx, fma(-n2u, tup, ru));
+                tX[t] = tx; tU[t] = tu;
+                if (bot) { rb = fma(-LBX_(t), tx, rb); rb = fma(-LBU_(t), tu, rb); }
+                txp = tx; tup = tu; n1u = l1u; n2x = l2x; n2u = l2u;
+            } else {
+                tX[t] = tx;
+                if (bot) rb = fma(-LBX_(t), tx, rb);
+                // contributions to the separator's right-hand side (x_s, u_{s-1})
+                vx = bot ? -(l2x * tx) : tx;
+                vu = bot ? fma(-l1x, tx, -(n2u * tup)) : fma(-n2u, tup, ru);
+            }
+        }
+        // ---- the dense 6x6: gather the right-hand side (own axis first), multiply by the stored rows of the inverse
+        double r6[6];
+        {
+            const double c0m = (bot ? rb : 0.0) + hp_m;
+            const double tx_ = vx + sx16(vx), tu_ = vu + sx16(vu), t0m = c0m + sx16(c0m), t0o = hp_o + sx16(hp_o);
+            r6[0] = tx_; r6[1] = tu_; r6[2] = t0m + sx8(t0o);
+            r6[3] = sx8(tx_); r6[4] = sx8(tu_); r6[5] = sx8(t0m) + t0o;
+        }
+        double Xs = 0.0, Us = 0.0, U0m = 0.0;
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+            Xs = fma(smr[k * 8], r6[k], Xs);
+            Us = fma(smr[(6 + k) * 8], r6[k], Us);
+            U0m = fma(smr[(12 + k) * 8], r6[k], U0m);
+        }
+        const double U0o = sx8(U0m);
+        // ---- hull rows (z~ = A x~): update_z / update_y of rows q4 and q4 + 4
+        {
+            const double ux = a == 0 ? U0m : U0o, uy = a == 0 ? U0o : U0m;
+#pragma unroll
+            for (int r = 0; r < 2; r++) {
+                const int h = q4 + 4 * r;
+                const double zt = HC_(H_HXS, h) * ux + HC_(H_HYS, h) * uy;
+                const double zr = alpha * zt + oma * zh[r];
+                double zn = zr + rho_inv * yh[r];
+                zn = fmax(zn, HC_(H_LO, h));
+                zn = fmin(zn, HC_(H_UP, h));
+                const double dy = rho * (zr - zn);
+                if (!PHASE2 || act) { zh[r] = zn; yh[r] += dy; dyh[r] = dy; }
+            }
+        }
+        // ---- backward: L' x~ = D^-1 t away from the separator, fused with update_y (equality rows) and update_x
+        {
+            const double ub = bot ? U0m : 0.0;
+            double sx = 0.0, su = 0.0;               // x~ of the next slot (towards the separator)
+#pragma unroll
+            for (int t = T - 1; t >= 0; t--) {
+                double xu, xx, sxr;
+                if (t == T - 1) {
+                    xu = Us;
+                    const double xe = fma(-S_(A_L1X, t), Us, fma(-S_(A_L2X, t), Xs, tX[t] * S_(A_DIX, t)));
+                    xx = bot ? fma(-LBX_(T - 1 < 0 ? 0 : T - 1), ub, xe) : Xs;
+                    sxr = sx16(xx);                  // top: x_{s-1} of the bottom lane; bottom: x_s
+                } else {
+                    double pu = fma(-S_(A_L2U, t), su, tU[t] * S_(A_DIU, t));
+                    double px = fma(-S_(A_L2X, t), sx, tX[t] * S_(A_DIX, t));
+                    if (bot) { pu = fma(-LBU_(t), ub, pu); px = fma(-LBX_(t), ub, px); }
+                    xu = fma(-S_(A_L1U, t), sx, pu);
+                    if (t == OFF) { if (bot) xu = U0m; }
+                    xx = fma(-S_(A_L1X, t), xu, px);
+                    sxr = sx;
+                }
+                // slot T-1: the two lanes of the axis hold copies of row s; the sum of two rounded products is
+                // the same number on both (their operands arrive in opposite order), a contracted fma is not
+                const double row = (t == T - 1) ? fma(b_, xu, __dadd_rn(__dmul_rn(cx0, xx), __dmul_rn(cx1, sxr)))
+                                                : fma(b_, xu, cx0 * xx + cx1 * sxr);
+                const double yn = fma(arho, S_(A_EE, t) * row, Y[t]);
+                const double xn = fma(alpha, xx, oma * X[t]);
+                const double un = fma(alpha, xu, oma * U[t]);
+                if (!PHASE2 || act) {
+                    tX[t] = xn - X[t]; tU[t] = un - U[t];
+                    Y[t] = yn; X[t] = xn; U[t] = un;
+                }
+                if (t == OFF) {
+                    if (bot && (!PHASE2 || act)) { // equality row 0: z = l = u = -dcm
+                        const double W0 = rho_e * EE0;
+                        dY0 = W0 * (fma(-alpha, xx, oma * Z0) + dcm_a);
+                        Y0 += dY0;
+                        Z0 = -dcm_a;
+                        Yext = fma(W0, dcm_a, Y0);
+                    }
+                }
+                sx = xx; su = xu;
+            }
+        }
+        if (!PHASE2 || act) hull_partials();
+    };
+
+    // update_info + the norms of check_termination for the CURRENT (x, z, y), all in unscaled quantities;
+    // SC: also the norms of the SCALED residuals (compute_rho_estimate; an adaptive-rho iteration only)
+    auto update_info = [&](auto sc_tag) {
+        constexpr bool SC = decltype(sc_tag)::value;
+        double m_rp_u = 0, m_rp_s = 0, m_z_u = 0, m_z_s = 0, m_ax_u = 0, m_ax_s = 0;
+        double m_rd_u = 0, m_rd_s = 0, m_q_u = 0, m_q_s = 0, m_aty_u = 0, m_aty_s = 0, m_px_u = 0, m_px_s = 0;
+        const double Xpart = sx16(X[T - 1]);         // top: x_{s-1}; bottom: x_s
+        const double Upart = sx16(U[T >= 2 ? T - 2 : 0]); // top: u_{s-2}; bottom: u_s
+        // hull rows' share of (A' y) on u_0 of both axes
+        double hyx = 0.0, hyy = 0.0;
+#pragma unroll
+        for (int r = 0; r < 2; r++) { hyx += HC_(H_HXS, q4 + 4 * r) * yh[r]; hyy += HC_(H_HYS, q4 + 4 * r) * yh[r]; }
+        hyx = inst_sum(hyx); hyy = inst_sum(hyy);
+        const double hy_m = a == 0 ? hyx : hyy;
+        const int kx0 = bot ? -OFF : N;
+        const ptrdiff_t sB = bot ? (ptrdiff_t)B : -(ptrdiff_t)B;
+        const ptrdiff_t xrow0 = ((ptrdiff_t)(a * nA + kx0)) * (ptrdiff_t)B + i;
+        const ptrdiff_t urow0 = ((ptrdiff_t)(a * nA + nR + kx0 - (bot ? 0 : 1))) * (ptrdiff_t)B + i;
+        const ptrdiff_t erow0 = ((ptrdiff_t)(a * nR + kx0 + (bot ? 1 : 0))) * (ptrdiff_t)B + i;
+#pragma unroll
+        for (int t = 0; t < T; t++) {
+            const bool real = (t >= OFF) || !bot;
+            const bool shadow = bot && t == T - 1;   // the bottom lane's copy of (u_{s-1}, row s): counted by the top lane
+            double Dx = 1.0, Du = 1.0, Ek = 1.0;
+            if (SC) { if (real) { Dx = d.D[xrow0 + t * sB]; Du = d.D[urow0 + t * sB]; Ek = d.Eeq[erow0 + t * sB]; } }
+            if (real) { // equality row of the slot: z = l = u = 0
+                const double xn_ = (t < T - 1) ? X[t < T - 1 ? t + 1 : t] : Xpart;
+                const double ax = fma(b_, U[t], cx0 * X[t] + cx1 * xn_);
+                m_rp_u = fmax(m_rp_u, fabs(ax)); m_ax_u = fmax(m_ax_u, fabs(ax));
+                if (SC) { m_rp_s = fmax(m_rp_s, fabs(Ek * ax)); m_ax_s = fmax(m_ax_s, fabs(Ek * ax)); }
+            }
+            { // x unknown
+                double yp;
+                if (t == OFF) yp = bot ? Y0 : (t == 0 ? 0.0 : Y[t > 0 ? t - 1 : 0]);
+                else yp = (t == 0) ? 0.0 : Y[t > 0 ? t - 1 : 0];
+                const double aty = -(cy0 * Y[t] + cy1 * yp);
+                const double px = cQ * X[t], q = S_(A_CQ, t);
+                const double rr = q + px + aty;
+                m_rd_u = fmax(m_rd_u, fabs(rr)); m_q_u = fmax(m_q_u, fabs(q));
+                m_aty_u = fmax(m_aty_u, fabs(aty)); m_px_u = fmax(m_px_u, fabs(px));
+                if (SC) {
+                    m_rd_s = fmax(m_rd_s, fabs(Dx * rr)); m_q_s = fmax(m_q_s, fabs(Dx * q));
+                    m_aty_s = fmax(m_aty_s, fabs(Dx * aty)); m_px_s = fmax(m_px_s, fabs(Dx * px));
+                }
+            }
+            if (!shadow && real) { // u unknown (a dummy's row would pick up its neighbour u_0)
+                const double ua = (t >= 1) ? U[t >= 1 ? t - 1 : 0] : 0.0;
+                const double ubn = (t < T - 1) ? U[t < T - 1 ? t + 1 : t] : Upart;
+                const double sc = (t == 0) ? (bot ? 2.0 : 1.0) : 2.0;
+                const double px = cR * ((sc * U[t] - ua) - ubn);
+                double aty = b_ * Y[t];
+                double q = 0.0;
+                if (t == OFF) { if (bot) { aty += hy_m; q = cqu0; } }
+                const double rr = q + px + aty;
+                m_rd_u = fmax(m_rd_u, fabs(rr)); m_q_u = fmax(m_q_u, fabs(q));
+                m_aty_u = fmax(m_aty_u, fabs(aty)); m_px_u = fmax(m_px_u, fabs(px));
+                if (SC) {
+                    m_rd_s = fmax(m_rd_s, fabs(Du * rr)); m_q_s = fmax(m_q_s, fabs(Du * q));
+                    m_aty_s = fmax(m_aty_s, fabs(Du * aty)); m_px_s = fmax(m_px_s, fabs(Du * px));
+                }
+            }
+        }
+        if (bot) { // equality row 0
+            const double ax = -X[OFF], z = Z0, r = ax - z;
+            m_rp_u = fmax(m_rp_u, fabs(r)); m_z_u = fmax(m_z_u, fabs(z)); m_ax_u = fmax(m_ax_u, fabs(ax));
+            if (SC) { m_rp_s = fmax(m_rp_s, fabs(E0 * r)); m_z_s = fmax(m_z_s, fabs(E0 * z)); m_ax_s = fmax(m_ax_s, fabs(E0 * ax)); }
+        }
+        { // hull rows
+            const double u0x = __shfl_sync(FULL, U[OFF], 16 + s8), u0y = __shfl_sync(FULL, U[OFF], 24 + s8);
+#pragma unroll
+            for (int r = 0; r < 2; r++) {
+                const int h = q4 + 4 * r;
+                const double ax = HC_(H_HXS, h) * u0x + HC_(H_HYS, h) * u0y;
+                const double z = zh[r], einv = HC_(H_EHI, h), rr = ax - z;
+                m_rp_u = fmax(m_rp_u, fabs(einv * rr)); m_z_u = fmax(m_z_u, fabs(einv * z)); m_ax_u = fmax(m_ax_u, fabs(einv * ax));
+                if (SC) { m_rp_s = fmax(m_rp_s, fabs(rr)); m_z_s = fmax(m_z_s, fabs(z)); m_ax_s = fmax(m_ax_s, fabs(ax)); }
+            }
+        }
+        pri_res = inst_max(m_rp_u); nz_u = inst_max(m_z_u); nAx_u = inst_max(m_ax_u);
+        dua_res = cinv * inst_max(m_rd_u); nq_u = cinv * inst_max(m_q_u);
+        nAty_u = cinv * inst_max(m_aty_u); nPx_u = cinv * inst_max(m_px_u);
+        if (SC) {
+            rp_s = inst_max(m_rp_s); nz_s = inst_max(m_z_s); nAx_s = inst_max(m_ax_s);
+            rd_s = inst_max(m_rd_s); nq_s = inst_max(m_q_s); nAty_s = inst_max(m_aty_s); nPx_s = inst_max(m_px_s);
+        }
+    };
+
+    // is_primal_infeasible (OSQP auxil.c) on delta_y of the last iteration, recomputed from X+ and dX
+    // (X~ = X+ + (1/alpha - 1) dX; delta Yh_k = alpha rho_e E_k^2 (A X~)_k on the equality rows)
+    auto primal_infeasible = [&](double eps) -> int {
+        const double arho = alpha * kRhoEqOverIneq * rho;
+        double dY[T];
+        {
+            const double xtl = fma(k1, tX[T - 1], X[T - 1]);
+            const double xpart = sx16(xtl);
+#pragma unroll
+            for (int t = 0; t < T; t++) {
+                const double xt = fma(k1, tX[t], X[t]), ut = fma(k1, tU[t], U[t]);
+                const double xn_ = (t < T - 1) ? fma(k1, tX[t < T - 1 ? t + 1 : t], X[t < T - 1 ? t + 1 : t]) : xpart;
+                dY[t] = arho * (S_(A_EE, t) * fma(b_, ut, cx0 * xt + cx1 * xn_));
+            }
+        }
+        double nrm = 0.0, lhs = 0.0;
+#pragma unroll
+        for (int t = 0; t < T; t++) nrm = fmax(nrm, fabs(dY[t]));
+        if (bot) { nrm = fmax(nrm, fabs(dY0)); lhs += (-dcm_a) * dY0; }
+        double dyp[2];
+#pragma unroll
+        for (int r = 0; r < 2; r++) { // project delta_y of the hull rows on the polar of the recession cone
+            const int h = q4 + 4 * r;
+            double dy = dyh[r];
+            const double e = HC_(H_EH, h), uh = HC_(H_UP, h), lh = HC_(H_LO, h);
+            const bool u_inf = uh > infty * kMinScaling, l_inf = lh < -infty * kMinScaling;
+            if (u_inf) dy = l_inf ? 0.0 : fmin(dy, 0.0);
+            else if (l_inf) dy = fmax(dy, 0.0);
+            if (h >= nh) dy = 0.0;
+            dyp[r] = dy;
+            nrm = fmax(nrm, fabs(e * dy));
+            lhs += uh * fmax(dy, 0.0) + lh * fmin(dy, 0.0);
+        }
+        nrm = inst_max(nrm);
+        lhs = inst_sum(lhs);
+        int res = 0;
+        double hdx = 0.0, hdy = 0.0;
+#pragma unroll
+        for (int r = 0; r < 2; r++) { hdx += HC_(H_HXS, q4 + 4 * r) * dyp[r]; hdy += HC_(H_HYS, q4 + 4 * r) * dyp[r]; }
+        hdx = inst_sum(hdx); hdy = inst_sum(hdy);
+        double m = 0.0;
+#pragma unroll
+        for (int t = 0; t < T; t++) {
+            double yp;
+            if (t == OFF) yp = bot ? dY0 : (t == 0 ? 0.0 : dY[t > 0 ? t - 1 : 0]);
+            else yp = (t == 0) ? 0.0 : dY[t > 0 ? t - 1 : 0];
+            m = fmax(m, fabs(cy0 * dY[t] + cy1 * yp));
+            double aty = b_ * dY[t];
+            if (t == OFF) { if (bot) aty += (a == 0 ? hdx : hdy); }
+            if (!(bot && t == T - 1)) m = fmax(m, fabs(aty));
+        }
+        m = inst_max(m);
+        if (nrm > 1.0 / infty && lhs < -eps * nrm) res = m < eps * nrm;
+        return res;
+    };
+    // is_dual_infeasible on delta_x of the last iteration (dX, dU in tX / tU)
+    auto dual_infeasible = [&](double eps) -> int {
+        double nrm = 0.0, qdx = 0.0;
+#pragma unroll
+        for (int t = 0; t < T; t++) {
+            nrm = fmax(nrm, fabs(tX[t]));
+            qdx = fma(S_(A_CQ, t), tX[t], qdx);
+            if (!(bot && t == T - 1)) nrm = fmax(nrm, fabs(tU[t]));
+        }
+        if (bot) qdx = fma(cqu0, tU[OFF], qdx);
+        nrm = inst_max(nrm);
+        qdx = inst_sum(qdx);
+        const double Xpart = sx16(tX[T - 1]);
+        const double Upart = sx16(tU[T >= 2 ? T - 2 : 0]);
+        double m = 0.0;
+        int bad = 0;
+#pragma unroll
+        for (int t = 0; t < T; t++) {
+            m = fmax(m, fabs(cQ * tX[t]));
+            if (!(bot && (t == T - 1 || t < OFF))) {
+                const double ua = (t >= 1) ? tU[t >= 1 ? t - 1 : 0] : 0.0;
+                const double ubn = (t < T - 1) ? tU[t < T - 1 ? t + 1 : t] : Upart;
+                const double sc = (t == 0) ? (bot ? 2.0 : 1.0) : 2.0;
+                m = fmax(m, fabs(cR * ((sc * tU[t] - ua) - ubn)));
+            }
+            const double xn_ = (t < T - 1) ? tX[t < T - 1 ? t + 1 : t] : Xpart;
+            const double ax = fma(b_, tU[t], cx0 * tX[t] + cx1 * xn_);
+            if (((t >= OFF) || !bot) && (ax > eps * nrm || ax < -eps * nrm)) bad = 1; // both bounds finite on equality rows
+        }
+        if (bot) { const double ax = -tX[OFF]; if (ax > eps * nrm || ax < -eps * nrm) bad = 1; }
+        {
+            const double u0x = __shfl_sync(FULL, tU[OFF], 16 + s8), u0y = __shfl_sync(FULL, tU[OFF], 24 + s8);
+#pragma unroll
+            for (int r = 0; r < 2; r++) {
+                const int h = q4 + 4 * r;
+                const double ax = (HC_(H_HXS, h) * u0x + HC_(H_HYS, h) * u0y) * HC_(H_EHI, h);
+                const double uh = HC_(H_UP, h), lh = HC_(H_LO, h);
+                if (h < nh && ((uh < infty * kMinScaling && ax > eps * nrm) || (lh > -infty * kMinScaling && ax < -eps * nrm))) bad = 1;
+            }
+        }
+        m = inst_max(m);
+        bad = (int)inst_max((double)bad);
+        int res = 0;
+        if (nrm > 1.0 / infty && qdx < -c * eps * nrm) {
+            if (m < c * eps * nrm) res = !bad;
+        }
+        return res;
+    };
+    // check_termination (OSQP auxil.c); called by the whole warp, returns the status to stop with or 0
+    auto check_termination = [&](int approximate) -> int {
+        double eps_abs = st.eps_abs, eps_rel = st.eps_rel, epi = st.eps_prim_inf, edi = st.eps_dual_inf;
+        const bool non_cvx = pri_res > infty || dua_res > infty;
+        if (approximate) { eps_abs *= 10; eps_rel *= 10; epi *= 10; edi *= 10; }
+        int prc = 0, drc = 0, prim_inf = 0, dual_inf = 0;
+        const double eps_prim = eps_abs + eps_rel * fmax(nz_u, nAx_u);
+        if (pri_res < eps_prim) prc = 1;
+        const double eps_dual = eps_abs + eps_rel * fmax(fmax(nq_u, nAty_u), nPx_u);
+        if (dua_res < eps_dual) drc = 1;
+        const bool live = !done && !non_cvx;
+        const bool need_pi = live && !prc, need_di = live && !drc;
+        if (__any_sync(FULL, need_pi)) { const int r = primal_infeasible(epi); if (need_pi) prim_inf = r; }
+        if (__any_sync(FULL, need_di)) { const int r = dual_infeasible(edi); if (need_di) dual_inf = r; }
+        if (non_cvx) return WC_OSQP_NON_CVX;
+        if (prc && drc) return approximate ? WC_OSQP_SOLVED_INACCURATE : WC_OSQP_SOLVED;
+        if (prim_inf) return approximate ? WC_OSQP_PRIMAL_INFEASIBLE_INACCURATE : WC_OSQP_PRIMAL_INFEASIBLE;
+        if (dual_inf) return approximate ? WC_OSQP_DUAL_INFEASIBLE_INACCURATE : WC_OSQP_DUAL_INFEASIBLE;
+        return 0;
+    };
+
+    const int max_iter = st.max_iter;
+    const int chk = st.check_termination;
+    const int rint = d.rho_interval;
+    const bool adaptive = st.adaptive_rho && rint > 0;
+    // phase 1 stops after this many iterations (first termination check / rho update / max_iter)
+    int phase1_len = chk > 0 ? chk : max_iter;
+    if (adaptive && rint < phase1_len) phase1_len = rint;
+    if (phase1_len > max_iter) phase1_len = max_iter;
+    int iter = PHASE2 ? phase1_len : 0;
+    int to_check = chk ? chk - (iter % chk) : 0;
+    int to_adapt = adaptive ? rint - (iter % rint) : 0;
+    bool warp_busy = __any_sync(FULL, !done);
+    while (warp_busy) {
+        iter++;
+        const bool act = !done;
+        bool check_now = false, adapt_now = false;
+        if (chk) { if (--to_check == 0) { check_now = true; to_check = chk; } }
+        if (adaptive) { if (--to_adapt == 0) { adapt_now = true; to_adapt = rint; } }
+        iteration(act);
+        if (act) iter_done = iter;
+        // ---- termination / adaptive rho (instance-uniform decisions, warp-uniform control flow)
+        if (check_now) {
+            if (adapt_now) update_info(std::true_type{}); else update_info(std::false_type{});
+            const int stop = check_termination(0);
+            if (act && stop) { status = stop; done = true; }
+        }
+        if (adapt_now) {
+            if (!check_now) update_info(std::true_type{});
+            if (act && !done) {
+                // compute_rho_estimate + adapt_rho
+                const double pr = rp_s / (fmax(nz_s, nAx_s) + 1e-10);
+                const double dr = rd_s / (fmax(fmax(nq_s, nAty_s), nPx_s) + 1e-10);
+                double rn = rho * sqrt(pr / (dr + 1e-10));
+                rn = fmin(fmax(rn, kRhoMin), kRhoMax);
+                if (rn > rho * st.adaptive_rho_tolerance || rn < rho / st.adaptive_rho_tolerance) {
+                    rho = rn;
+                    rho_updates++;
+                }
+            }
+            __syncwarp();
+            build_factor();                          // warp-uniform; unchanged rho recomputes the same factors
+            Yext = Y0 - (kRhoEqOverIneq * rho * EE0) * Z0;
+            hull_partials();
+        }
+        if (iter >= max_iter) { // warp-uniform: osqp_solve leaves the loop
+            if (!check_now) {
+                update_info(std::false_type{});
+                const int stop = check_termination(0);
+                if (act && !done && stop) { status = stop; done = true; }
+            }
+            {
+                const int stop = check_termination(1);
+                if (act && !done) {
+                    status = stop ? stop : WC_OSQP_MAX_ITER_REACHED;
+                    done = true;
+                }
+            }
+        }
+        if (!PHASE2 && iter >= phase1_len) break; // unfinished instances go to the continuation list
+        warp_busy = __any_sync(FULL, !done);
+    }
+    __syncwarp();
+
+    // ------------------------------------------------------------------ epilogue: store_solution + controller checks
+    const bool unfinished = !skip && !done; // phase 1 only
+    const bool has_sol = !(status == WC_OSQP_PRIMAL_INFEASIBLE || status == WC_OSQP_PRIMAL_INFEASIBLE_INACCURATE ||
+                           status == WC_OSQP_DUAL_INFEASIBLE || status == WC_OSQP_DUAL_INFEASIBLE_INACCURATE ||
+                           status == WC_OSQP_UNSOLVED || status == WC_OSQP_NON_CVX) || unfinished;
+    if (!skip) { // back to OSQP's scaled workspace
+        const int kx0 = bot ? -OFF : N;
+        const ptrdiff_t sB = bot ? (ptrdiff_t)B : -(ptrdiff_t)B;
+        const ptrdiff_t xrow0 = ((ptrdiff_t)(a * nA + kx0)) * (ptrdiff_t)B + i;
+        const ptrdiff_t urow0 = ((ptrdiff_t)(a * nA + nR + kx0 - (bot ? 0 : 1))) * (ptrdiff_t)B + i;
+        const ptrdiff_t erow0 = ((ptrdiff_t)(a * nR + kx0 + (bot ? 1 : 0))) * (ptrdiff_t)B + i;
+#pragma unroll
+        for (int t = 0; t < T; t++) {
+            const bool real = (t >= OFF) || !bot;
+            const bool shadow = bot && t == T - 1;
+            if (real) {
+                const ptrdiff_t xr = xrow0 + t * sB, ur = urow0 + t * sB, er = erow0 + t * sB;
+                d.x[xr] = has_sol ? X[t] * d.Dinv[xr] : 0.0;
+                if (!shadow) {
+                    d.x[ur] = has_sol ? U[t] * d.Dinv[ur] : 0.0;
+                    d.yeq[er] = has_sol ? Y[t] * d.Einv[er] : 0.0;
+                }
+            }
+        }
+        if (bot) {
+            d.yeq[(size_t)(a * nR) * B + i] = has_sol ? Y0 * d.Einv[(size_t)(a * nR) * B + i] : 0.0;
+            d.z0[(size_t)a * B + i] = has_sol ? Z0 * E0 : 0.0;
+        }
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            const int h = q4 + 4 * r;
+            d.yh[(size_t)h * B + i] = has_sol ? yh[r] : 0.0;
+            d.zh[(size_t)h * B + i] = has_sol ? zh[r] : 0.0;
+        }
+    }
+    // desired ZMP (= unscaled u_0) of both axes on every lane; the hull margin split over the four lanes
+    const double zx = __shfl_sync(FULL, U[OFF], 16 + s8), zy = __shfl_sync(FULL, U[OFF], 24 + s8);
+    const double upx = __shfl_sync(FULL, upa, s8), upy = __shfl_sync(FULL, upa, 8 + s8);
+    // ConvexHullProjectionConstraint::computeMargin (Controller.cpp:513-517): margin < -tol  <=>  outside the polygon AND
+    // farther than tol from its boundary.  A ZMP on an active hull row violates it by OSQP's tolerance (~1e-4 m); the hull
+    // is the convex hull of foot rectangles (interior angles >= 90 degrees), so the distance to the polygon is at most
+    // sqrt(2) x the largest normalised row violation: only a violation that could reach the tolerance takes the exact
+    // point-to-segment distances.
+    double vmax = 0.0;
+    int outside = 0;
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        const int h = q4 + 4 * r;
+        if (h < nh) {
+            const double a0 = d.hullA[(size_t)(2 * h) * B + i], a1 = d.hullA[(size_t)(2 * h + 1) * B + i];
+            const double viol = (a0 * zx + a1 * zy) - d.hullb[(size_t)h * B + i];
+            if (!(viol <= 0.0)) { outside = 1; vmax = fmax(vmax, viol / sqrt(a0 * a0 + a1 * a1)); }
+        }
+    }
+    vmax = inst_max(vmax);
+    outside = (int)inst_max((double)outside);
+    if (lane < 8 && valid) {
+        if (unfinished) {
+            const int idx = atomicAdd(d.cont_count, 1);
+            d.cont_list[idx] = i;
+            d.rho[i] = rho;
+            d.rho_updates[i] = rho_updates;
+            if (init_state == 2) d.inited[i] = 1;
+        } else {
+            int flags = kflags;
+            double out[2] = {upx, upy};
+            if (!skip) {
+                d.rho[i] = rho;
+                d.rho_updates[i] = rho_updates;
+                if (init_state == 2) d.inited[i] = 1;
+                if (status == WC_OSQP_SOLVED) {
+                    out[0] = zx; out[1] = zy;
+                    d.uprev[i] = out[0]; d.uprev[B + i] = out[1];
+                    const bool inside = !outside;
+                    double best = INFINITY;
+                    const bool exact = !inside && !(4.0 * vmax < d.hull_tol);
+                    if (exact) {
+                        for (int h = 0; h < nh; h++) {
+                            const int h1 = (h + 1) % nh;
+                            const double p0x = d.hullv[(size_t)(2 * h) * B + i], p0y = d.hullv[(size_t)(2 * h + 1) * B + i];
+                            const double p1x = d.hullv[(size_t)(2 * h1) * B + i], p1y = d.hullv[(size_t)(2 * h1 + 1) * B + i];
+                            const double dx = p1x - p0x, dy = p1y - p0y;
+                            const double len2 = dx * dx + dy * dy;
+                            double tt = len2 > 0 ? ((out[0] - p0x) * dx + (out[1] - p0y) * dy) / len2 : 0.0;
+                            tt = tt < 0 ? 0 : (tt > 1 ? 1 : tt);
+                            const double ex = out[0] - (p0x + tt * dx), ey = out[1] - (p0y + tt * dy);
+                            best = fmin(best, sqrt(ex * ex + ey * ey));
+                        }
+                    } else if (!inside) {
+                        best = 0.0; // outside by less than the tolerance: not flagged
+                    }
+                    const double margin = inside ? best : -best;
+                    if (margin < -d.hull_tol) flags |= WC_MPC_FLAG_OUTSIDE_HULL;
+                } else {
+                    flags |= WC_MPC_FLAG_NOT_SOLVED;
+                }
+            }
+            if (io.zmp) { io.zmp[i] = out[0]; io.zmp[B + i] = out[1]; }
+            if (io.status) io.status[i] = skip ? WC_OSQP_UNSOLVED : status;
+            if (io.iters) io.iters[i] = skip ? 0 : iter_done;
+            if (io.flags) io.flags[i] = flags;
+            d.tick_flags[i] = flags;
+        }
+    }
+    __syncwarp(); // the next group of this CTA reuses the shared-memory working set
+    } // groups
+#undef S_
+#undef LBX_
+#undef LBU_
+#undef HC_
+}
+
+// ------------------------------------------------------------------------------------------------
+template <int NT>
+static cudaError_t launch_split_t(const MpcDev& d, const MpcTickIO& io, cudaStream_t s, cudaEvent_t* mid)
+{
+    constexpr size_t smem = (size_t)SplitDims<NT>::total * sizeof(double);
+    auto k1 = mpc_split_kernel<false, NT>;
+    auto k2 = mpc_split_kernel<true, NT>;
+    cudaError_t e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const int blocks = (d.B + 7) / 8;
+    if (mid) cudaEventRecord(mid[0], s); // per-kernel timing (wc_mpc_enable_profiling)
+    k1<<<blocks, 32, smem, s>>>(d, io);
+    if (mid) cudaEventRecord(mid[1], s);
+    const int cap = WC_SPLIT_MINB * 148;
+    k2<<<blocks < cap ? blocks : cap, 32, smem, s>>>(d, io); // grid-stride over the continuation list
+    return cudaGetLastError();
+}
+
+bool mpc_split_supported(int N) { return N == 25 || N == 10; }
+
+cudaError_t launch_mpc_split(const MpcDev& d, const MpcTickIO& io, cudaStream_t s, cudaEvent_t* mid)
+{
+    cudaError_t e = launch_mpc_chain_setup(d, s, false);
+    if (e != cudaSuccess) return e;
+    switch (d.N) {
+    case 25: return launch_split_t<25>(d, io, s, mid);
+    case 10: return launch_split_t<10>(d, io, s, mid);
+    default: return cudaErrorInvalidConfiguration;
+    }
+}
+
+} // namespace wcb

@@ -20,7 +20,7 @@ struct wc_mpc {
     wc_mpc_config cfg;
     int device;
     int lanes;
-    int chain; // 1: chain-per-thread ADMM path (mpc_chain.cu), 0: cooperative path (mpc_kernels.cu)
+    int chain; // 2: split-chain path (mpc_split.cu), 1: chain-per-thread path (mpc_chain.cu), 0: cooperative path (mpc_kernels.cu)
     int64_t launches;
     int64_t tick;
     std::vector<void*> allocs;
@@ -147,12 +147,16 @@ wc_status wc_mpc_create(const wc_mpc_config* cfg, int32_t B, int32_t device, wc_
     h->lanes = lanes;
     // short horizons: one thread per axis chain (16 instances per warp) when the working set of a warp
     // fits in shared memory; WC_MPC_PATH=coop|chain overrides (tuning / tests)
-    h->chain = mpc_chain_preferred(d.N) ? 1 : 0;
+    // and four lanes per instance with the iterate in registers (mpc_split.cu) at the compile-time horizons
+    h->chain = mpc_split_supported(d.N) ? 2 : (mpc_chain_preferred(d.N) ? 1 : 0);
     if (const char* pth = std::getenv("WC_MPC_PATH")) {
         if (!std::strcmp(pth, "coop")) h->chain = 0;
         else if (!std::strcmp(pth, "chain")) {
             if (!mpc_chain_supported(d.N)) { wc_mpc_destroy(h); return WC_ERR_UNSUPPORTED; }
             h->chain = 1;
+        } else if (!std::strcmp(pth, "split")) {
+            if (!mpc_split_supported(d.N)) { wc_mpc_destroy(h); return WC_ERR_UNSUPPORTED; }
+            h->chain = 2;
         }
     }
     if (h->chain) {
@@ -160,11 +164,13 @@ wc_status wc_mpc_create(const wc_mpc_config* cfg, int32_t B, int32_t device, wc_
         if (e2 == cudaSuccess) e2 = dalloc(h, &d.Dinv, 2 * nA * Bz);
         if (e2 == cudaSuccess) e2 = dalloc(h, &d.Einv, 2 * nR * Bz);
         if (e2 == cudaSuccess) e2 = dalloc(h, &d.Ehinv, 8 * Bz);
-        if (e2 == cudaSuccess) e2 = dalloc(h, &d.dy_scratch, (2 * nR + 8) * Bz);
-        if (e2 == cudaSuccess) e2 = dalloc(h, &d.L1, 2 * nA * Bz);
-        if (e2 == cudaSuccess) e2 = dalloc(h, &d.L2, 2 * nA * Bz);
-        if (e2 == cudaSuccess) e2 = dalloc(h, &d.DI, 2 * nA * Bz);
-        if (e2 == cudaSuccess) e2 = dalloc(h, &d.CF, 10 * Bz);
+        if (h->chain == 1) { // the split-chain kernels keep neither the factors nor delta_y in HBM
+            if (e2 == cudaSuccess) e2 = dalloc(h, &d.dy_scratch, (2 * nR + 8) * Bz);
+            if (e2 == cudaSuccess) e2 = dalloc(h, &d.L1, 2 * nA * Bz);
+            if (e2 == cudaSuccess) e2 = dalloc(h, &d.L2, 2 * nA * Bz);
+            if (e2 == cudaSuccess) e2 = dalloc(h, &d.DI, 2 * nA * Bz);
+            if (e2 == cudaSuccess) e2 = dalloc(h, &d.CF, 10 * Bz);
+        }
         if (e2 == cudaSuccess) e2 = dalloc(h, &d.setup_list, Bz);
         if (e2 == cudaSuccess) e2 = dalloc(h, &d.setup_count, 1);
         if (e2 == cudaSuccess) e2 = dalloc(h, &d.cont_list, Bz);
@@ -236,7 +242,8 @@ wc_status wc_mpc_tick_dev(wc_mpc* h, const double* lf_H, const double* rf_H,
     cudaError_t e = cudaGetLastError();
     if (h->profiling) cudaEventRecord(ev[1], s);
     if (e == cudaSuccess) {
-        if (h->chain) e = launch_mpc_chain(h->d, io, s, h->profiling ? &ev[2] : nullptr);
+        if (h->chain == 2) e = launch_mpc_split(h->d, io, s, h->profiling ? &ev[2] : nullptr);
+        else if (h->chain) e = launch_mpc_chain(h->d, io, s, h->profiling ? &ev[2] : nullptr);
         else {
             if (h->profiling) { cudaEventRecord(ev[2], s); }
             e = launch_mpc_admm(h->d, io, h->lanes, s);
