@@ -178,8 +178,8 @@ __global__ void __launch_bounds__(32, WC_SPLIT_MINB) mpc_split_kernel(MpcDev d, 
             double dx = 0, dix = 0, du = 0, diu = 0, e = 0, g = 0, xb = 0, ub = 0, yb = 0;
             if (real) {
                 const ptrdiff_t xr = xrow0 + t * sB, ur = urow0 + t * sB, er = erow0 + t * sB;
-                dx = d.D[xr]; dix = d.Dinv[xr]; du = d.D[ur]; diu = d.Dinv[ur]; e = d.Eeq[er];
-                g = d.grad[(size_t)(a * nR + gs) * B + i];
+                dx = __ldg(d.D + (xr)); dix = __ldg(d.Dinv + (xr)); du = __ldg(d.D + (ur)); diu = __ldg(d.Dinv + (ur)); e = __ldg(d.Eeq + (er));
+                g = __ldg(d.grad + ((size_t)(a * nR + gs) * B + i));
                 if (!cold) { xb = d.x[xr]; ub = d.x[ur]; yb = d.yeq[er]; }
             }
             gs += gstep; gs = gs >= nR ? gs - nR : (gs < 0 ? gs + nR : gs);
@@ -194,10 +194,10 @@ __global__ void __launch_bounds__(32, WC_SPLIT_MINB) mpc_split_kernel(MpcDev d, 
     // bottom lanes: equality row 0 (l = u = -dcm, MPCSolver.cpp:143-146) and its unscaled z
     double EE0 = 0.0, Y0 = 0.0, Z0 = 0.0, E0 = 1.0;
     if (bot) {
-        E0 = d.Eeq[(size_t)(a * nR) * B + i];
+        E0 = __ldg(d.Eeq + ((size_t)(a * nR) * B + i));
         EE0 = E0 * E0;
         if (!cold) Y0 = E0 * d.yeq[(size_t)(a * nR) * B + i];
-        Z0 = PHASE2 ? -dcm_a : (cold ? 0.0 : d.z0[(size_t)a * B + i] * d.Einv[(size_t)(a * nR) * B + i]);
+        Z0 = PHASE2 ? -dcm_a : (cold ? 0.0 : d.z0[(size_t)a * B + i] * __ldg(d.Einv + ((size_t)(a * nR) * B + i)));
     }
     // hull rows q4 and q4 + 4 of the instance: constants to shared memory, (z, y) in registers (scaled, as OSQP keeps them)
     double zh[2], yh[2], dyh[2] = {0.0, 0.0};
@@ -205,9 +205,9 @@ __global__ void __launch_bounds__(32, WC_SPLIT_MINB) mpc_split_kernel(MpcDev d, 
     for (int r = 0; r < 2; r++) {
         const int h = q4 + 4 * r;
         const bool on = h < nh;
-        const double e = d.Eh[(size_t)h * B + i];
-        const double hx = d.hullA[(size_t)(2 * h) * B + i], hy = d.hullA[(size_t)(2 * h + 1) * B + i];
-        const double hb = d.hullb[(size_t)h * B + i];
+        const double e = __ldg(d.Eh + ((size_t)h * B + i));
+        const double hx = __ldg(d.hullA + ((size_t)(2 * h) * B + i)), hy = __ldg(d.hullA + ((size_t)(2 * h + 1) * B + i));
+        const double hb = __ldg(d.hullb + ((size_t)h * B + i));
         HC_(H_HXS, h) = on ? e * hx : 0.0;
         HC_(H_HYS, h) = on ? e * hy : 0.0;
         HC_(H_LO, h) = on ? e * (-infty) : -1.0;
@@ -322,7 +322,6 @@ __global__ void __launch_bounds__(32, WC_SPLIT_MINB) mpc_split_kernel(MpcDev d, 
         }
         __syncwarp();
     };
-    build_factor();
 
     // ------------------------------------------------------------------ ADMM (osqp_solve)
     int status = WC_OSQP_UNSOLVED;
@@ -331,7 +330,7 @@ __global__ void __launch_bounds__(32, WC_SPLIT_MINB) mpc_split_kernel(MpcDev d, 
     double pri_res = 0.0, dua_res = 0.0;
     double nz_u = 0, nAx_u = 0, nq_u = 0, nAty_u = 0, nPx_u = 0;
     double rp_s = 0, rd_s = 0, nz_s = 0, nAx_s = 0, nq_s = 0, nAty_s = 0, nPx_s = 0;
-    double Yext = Y0 - (kRhoEqOverIneq * rho * EE0) * Z0;  // Yh_0 - W_0 Z_0: the row-0 term of x_0's right-hand side
+    double Yext = 0.0;                               // Yh_0 - W_0 Z_0: the row-0 term of x_0's right-hand side
     double dY0 = 0.0;
     // hull rows' share of the right-hand side of u_0 (this axis, the other axis), from the current (z, y)
     double hp_m = 0.0, hp_o = 0.0;
@@ -346,11 +345,10 @@ __global__ void __launch_bounds__(32, WC_SPLIT_MINB) mpc_split_kernel(MpcDev d, 
         hp_m = a == 0 ? px : py;
         hp_o = a == 0 ? py : px;
     };
-    hull_partials();
 
     // one ADMM iteration on the whole warp; `act` freezes finished instances (phase 2 only)
-    auto iteration = [&](bool act) {
-        const double rho_e = kRhoEqOverIneq * rho, arho = alpha * rho_e, rho_inv = 1.0 / rho;
+    auto iteration = [&](const bool act, const double rho_inv) {
+        const double rho_e = kRhoEqOverIneq * rho, arho = alpha * rho_e;
         const double oma = 1.0 - alpha;
         // ---- forward: right-hand side fused with L t = rhs, towards the separator
         double txp = 0.0, tup = 0.0;                 // t of the previous slot's x and u
@@ -463,8 +461,7 @@ __global__ void __launch_bounds__(32, WC_SPLIT_MINB) mpc_split_kernel(MpcDev d, 
 
     // update_info + the norms of check_termination for the CURRENT (x, z, y), all in unscaled quantities;
     // SC: also the norms of the SCALED residuals (compute_rho_estimate; an adaptive-rho iteration only)
-    auto update_info = [&](auto sc_tag) {
-        constexpr bool SC = decltype(sc_tag)::value;
+    auto update_info = [&](const bool SC) {
         double m_rp_u = 0, m_rp_s = 0, m_z_u = 0, m_z_s = 0, m_ax_u = 0, m_ax_s = 0;
         double m_rd_u = 0, m_rd_s = 0, m_q_u = 0, m_q_s = 0, m_aty_u = 0, m_aty_s = 0, m_px_u = 0, m_px_s = 0;
         const double Xpart = sx16(X[T - 1]);         // top: x_{s-1}; bottom: x_s
@@ -485,7 +482,7 @@ __global__ void __launch_bounds__(32, WC_SPLIT_MINB) mpc_split_kernel(MpcDev d, 
             const bool real = (t >= OFF) || !bot;
             const bool shadow = bot && t == T - 1;   // the bottom lane's copy of (u_{s-1}, row s): counted by the top lane
             double Dx = 1.0, Du = 1.0, Ek = 1.0;
-            if (SC) { if (real) { Dx = d.D[xrow0 + t * sB]; Du = d.D[urow0 + t * sB]; Ek = d.Eeq[erow0 + t * sB]; } }
+            if (SC) { if (real) { Dx = __ldg(d.D + (xrow0 + t * sB)); Du = __ldg(d.D + (urow0 + t * sB)); Ek = __ldg(d.Eeq + (erow0 + t * sB)); } }
             if (real) { // equality row of the slot: z = l = u = 0
                 const double xn_ = (t < T - 1) ? X[t < T - 1 ? t + 1 : t] : Xpart;
                 const double ax = fma(b_, U[t], cx0 * X[t] + cx1 * xn_);
@@ -683,53 +680,58 @@ __global__ void __launch_bounds__(32, WC_SPLIT_MINB) mpc_split_kernel(MpcDev d, 
     int iter = PHASE2 ? phase1_len : 0;
     int to_check = chk ? chk - (iter % chk) : 0;
     int to_adapt = adaptive ? rint - (iter % rint) : 0;
+    bool refactor = true;
     bool warp_busy = __any_sync(FULL, !done);
+    // every rare block below has ONE call site (update_info, check_termination, build_factor are large once inlined:
+    // the instruction footprint of the kernel decides how often the hot loop misses the instruction cache)
+#pragma unroll 1
     while (warp_busy) {
-        iter++;
-        const bool act = !done;
-        bool check_now = false, adapt_now = false;
-        if (chk) { if (--to_check == 0) { check_now = true; to_check = chk; } }
-        if (adaptive) { if (--to_adapt == 0) { adapt_now = true; to_adapt = rint; } }
-        iteration(act);
-        if (act) iter_done = iter;
-        // ---- termination / adaptive rho (instance-uniform decisions, warp-uniform control flow)
-        if (check_now) {
-            if (adapt_now) update_info(std::true_type{}); else update_info(std::false_type{});
-            const int stop = check_termination(0);
-            if (act && stop) { status = stop; done = true; }
-        }
-        if (adapt_now) {
-            if (!check_now) update_info(std::true_type{});
-            if (act && !done) {
-                // compute_rho_estimate + adapt_rho
-                const double pr = rp_s / (fmax(nz_s, nAx_s) + 1e-10);
-                const double dr = rd_s / (fmax(fmax(nq_s, nAty_s), nPx_s) + 1e-10);
-                double rn = rho * sqrt(pr / (dr + 1e-10));
-                rn = fmin(fmax(rn, kRhoMin), kRhoMax);
-                if (rn > rho * st.adaptive_rho_tolerance || rn < rho / st.adaptive_rho_tolerance) {
-                    rho = rn;
-                    rho_updates++;
-                }
-            }
-            __syncwarp();
-            build_factor();                          // warp-uniform; unchanged rho recomputes the same factors
+        if (refactor) { // numeric factorisation: at entry, and again after a rho update (unchanged rho recomputes the same factors)
+            build_factor();
             Yext = Y0 - (kRhoEqOverIneq * rho * EE0) * Z0;
             hull_partials();
+            refactor = false;
         }
-        if (iter >= max_iter) { // warp-uniform: osqp_solve leaves the loop
-            if (!check_now) {
-                update_info(std::false_type{});
-                const int stop = check_termination(0);
-                if (act && !done && stop) { status = stop; done = true; }
-            }
-            {
-                const int stop = check_termination(1);
-                if (act && !done) {
-                    status = stop ? stop : WC_OSQP_MAX_ITER_REACHED;
-                    done = true;
+        // iterations up to the next termination check / rho update / max_iter
+        int run = max_iter - iter;
+        if (chk && to_check < run) run = to_check;
+        if (adaptive && to_adapt < run) run = to_adapt;
+        if (run < 1) run = 1;
+        const bool act = !done;
+        const double rho_inv = 1.0 / rho;
+#pragma unroll 1
+        for (int r = 0; r < run; r++) iteration(act, rho_inv);
+        iter += run;
+        if (act) iter_done = iter;
+        bool check_now = false, adapt_now = false;
+        if (chk) { to_check -= run; if (to_check == 0) { check_now = true; to_check = chk; } }
+        if (adaptive) { to_adapt -= run; if (to_adapt == 0) { adapt_now = true; to_adapt = rint; } }
+        const bool at_max = iter >= max_iter;
+        // ---- termination / adaptive rho (instance-uniform decisions, warp-uniform control flow)
+        update_info(adapt_now);
+#pragma unroll 1
+        for (int approx = 0; approx < 2; approx++) {
+            if (approx == 0) {
+                if (check_now || at_max) {
+                    const int stop = check_termination(0);
+                    if (act && !done && stop) { status = stop; done = true; }
                 }
+                if (adapt_now && act && !done) { // compute_rho_estimate + adapt_rho
+                    const double pr = rp_s / (fmax(nz_s, nAx_s) + 1e-10);
+                    const double dr = rd_s / (fmax(fmax(nq_s, nAty_s), nPx_s) + 1e-10);
+                    double rn = rho * sqrt(pr / (dr + 1e-10));
+                    rn = fmin(fmax(rn, kRhoMin), kRhoMax);
+                    if (rn > rho * st.adaptive_rho_tolerance || rn < rho / st.adaptive_rho_tolerance) {
+                        rho = rn;
+                        rho_updates++;
+                    }
+                }
+            } else if (at_max) { // osqp_solve leaves the loop: approximate criteria, else MAX_ITER_REACHED
+                const int stop = check_termination(1);
+                if (act && !done) { status = stop ? stop : WC_OSQP_MAX_ITER_REACHED; done = true; }
             }
         }
+        if (adapt_now) refactor = true;
         if (!PHASE2 && iter >= phase1_len) break; // unfinished instances go to the continuation list
         warp_busy = __any_sync(FULL, !done);
     }
@@ -752,15 +754,15 @@ __global__ void __launch_bounds__(32, WC_SPLIT_MINB) mpc_split_kernel(MpcDev d, 
             const bool shadow = bot && t == T - 1;
             if (real) {
                 const ptrdiff_t xr = xrow0 + t * sB, ur = urow0 + t * sB, er = erow0 + t * sB;
-                d.x[xr] = has_sol ? X[t] * d.Dinv[xr] : 0.0;
+                d.x[xr] = has_sol ? X[t] * __ldg(d.Dinv + (xr)) : 0.0;
                 if (!shadow) {
-                    d.x[ur] = has_sol ? U[t] * d.Dinv[ur] : 0.0;
-                    d.yeq[er] = has_sol ? Y[t] * d.Einv[er] : 0.0;
+                    d.x[ur] = has_sol ? U[t] * __ldg(d.Dinv + (ur)) : 0.0;
+                    d.yeq[er] = has_sol ? Y[t] * __ldg(d.Einv + (er)) : 0.0;
                 }
             }
         }
         if (bot) {
-            d.yeq[(size_t)(a * nR) * B + i] = has_sol ? Y0 * d.Einv[(size_t)(a * nR) * B + i] : 0.0;
+            d.yeq[(size_t)(a * nR) * B + i] = has_sol ? Y0 * __ldg(d.Einv + ((size_t)(a * nR) * B + i)) : 0.0;
             d.z0[(size_t)a * B + i] = has_sol ? Z0 * E0 : 0.0;
         }
 #pragma unroll
@@ -784,8 +786,8 @@ __global__ void __launch_bounds__(32, WC_SPLIT_MINB) mpc_split_kernel(MpcDev d, 
     for (int r = 0; r < 2; r++) {
         const int h = q4 + 4 * r;
         if (h < nh) {
-            const double a0 = d.hullA[(size_t)(2 * h) * B + i], a1 = d.hullA[(size_t)(2 * h + 1) * B + i];
-            const double viol = (a0 * zx + a1 * zy) - d.hullb[(size_t)h * B + i];
+            const double a0 = __ldg(d.hullA + ((size_t)(2 * h) * B + i)), a1 = __ldg(d.hullA + ((size_t)(2 * h + 1) * B + i));
+            const double viol = (a0 * zx + a1 * zy) - __ldg(d.hullb + ((size_t)h * B + i));
             if (!(viol <= 0.0)) { outside = 1; vmax = fmax(vmax, viol / sqrt(a0 * a0 + a1 * a1)); }
         }
     }
