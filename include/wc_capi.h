@@ -65,7 +65,8 @@ enum {
     WC_MPC_FLAG_OK = 0,
     WC_MPC_FLAG_NO_CONTACT = 1,   /* (false,false) contact pair: "None foot is in contact" (:404-408) */
     WC_MPC_FLAG_NO_SOLVER = 2,    /* no MPCSolver exists yet (reference would dereference null) */
-    WC_MPC_FLAG_NOT_SOLVED = 4,   /* OsqpEigen::Solver::solve() false: status != OSQP_SOLVED */
+    WC_MPC_FLAG_NOT_SOLVED = 4,   /* OsqpEigen::Solver::solve() false: a non-convex problem, or -- with
+                                     osqp_eigen_checks_status -- any status but OSQP_SOLVED; the output keeps m_output */
     WC_MPC_FLAG_OUTSIDE_HULL = 8, /* computeMargin(u0) < -convex_hull_tolerance (:513-517) */
     WC_MPC_FLAG_NEW_SOLVER = 16   /* informational: support phase changed, cold OSQP setup ran */
 };
@@ -91,7 +92,11 @@ typedef struct wc_osqp_settings {
     int32_t adaptive_rho;          /* 1 */
     int32_t adaptive_rho_interval; /* 0 -> 4*check_termination */
     int32_t warm_start;            /* 1 */
-    int32_t reserved0;
+    int32_t osqp_eigen_checks_status; /* what OsqpEigen::Solver::solve() returns (MPCSolver.cpp:309, ..._osqp.cpp:377):
+                                       0 (default) = osqp-eigen as of the reference (2018): true whenever osqp_solve()
+                                           ran, whatever the status -- the caller reads OSQP's stored solution (the last
+                                           iterate for SOLVED_INACCURATE / MAX_ITER_REACHED, NaN for the infeasible statuses);
+                                       1 = osqp-eigen >= 0.4: false unless the status is OSQP_SOLVED.  DESIGN.md section 9 */
     int32_t reserved1;
 } wc_osqp_settings;
 
@@ -370,7 +375,8 @@ enum { WC_IK_SOLVER_QPOASES = 0, WC_IK_SOLVER_OSQP = 1 };
 wc_status wc_ik_set_solver(wc_ik* h, int32_t solver, const wc_osqp_settings* settings);
 wc_status wc_ik_reset_solver(wc_ik* h);
 /* Optional per-instance outputs of the osqp variant, device pointers [B] (NULL = not wanted), written by the next ticks:
- * flags bit 0 = m_optimizerSolver->solve() false (non-convex), bit 1 = isSolutionFeasible false (:395-408; the
+ * flags bit 0 = m_optimizerSolver->solve() false (non-convex; with osqp_eigen_checks_status any status but OSQP_SOLVED),
+ * bit 1 = isSolutionFeasible false (:395-408; the
  * reference's solve() returns false if any bit is set); setups = osqp_setup calls so far (first solve + every change of
  * the Hessian's sparsity pattern, i.e. of the stance foot). */
 wc_status wc_ik_osqp_outputs_dev(wc_ik* h, int32_t* flags, int32_t* setups);

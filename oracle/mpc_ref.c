@@ -309,10 +309,20 @@ int wco_mpc_tick(wco_mpc* c, const double* lf_H, const double* rf_H, int l_conta
     c->last_status = st; c->last_iter = wco_osqp_iter(c->osqp);
     if (osqp_status) *osqp_status = st;
     if (iters) *iters = c->last_iter;
-    if (st != WC_OSQP_SOLVED) return flags | WC_MPC_FLAG_NOT_SOLVED; /* OsqpEigen::Solver::solve() == false */
+    /* OsqpEigen::Solver::solve() (MPCSolver.cpp:309): osqp-eigen of the reference's time returns osqp_solve() == 0, i.e. true
+     * for every status but a non-convex problem; since 0.4 it is false unless the status is OSQP_SOLVED
+     * (wc_osqp_settings::osqp_eigen_checks_status).  The controller then reads OSQP's stored solution (Controller.cpp:509-511):
+     * the last iterate, or NaN for the infeasible statuses (OSQP store_solution). */
+    {
+        const int ok = c->cfg.osqp.osqp_eigen_checks_status ? (st == WC_OSQP_SOLVED)
+                                                            : (st != WC_OSQP_NON_CVX && st != WC_OSQP_UNSOLVED);
+        if (!ok) return flags | WC_MPC_FLAG_NOT_SOLVED;
+    }
+    const int has_sol = !(st == WC_OSQP_PRIMAL_INFEASIBLE || st == WC_OSQP_PRIMAL_INFEASIBLE_INACCURATE ||
+                          st == WC_OSQP_DUAL_INFEASIBLE || st == WC_OSQP_DUAL_INFEASIBLE_INACCURATE);
     const double* sol = wco_osqp_solution_x(c->osqp);
-    c->output[0] = sol[2 * (N + 1)];
-    c->output[1] = sol[2 * (N + 1) + 1];
+    c->output[0] = has_sol ? sol[2 * (N + 1)] : NAN;
+    c->output[1] = has_sol ? sol[2 * (N + 1) + 1] : NAN;
     zmp[0] = c->output[0]; zmp[1] = c->output[1];
     if (wco_hull_margin(c->hull_A, c->hull_b, c->hull_v, c->n_hull, c->output) < -c->cfg.hull_tolerance)
         flags |= WC_MPC_FLAG_OUTSIDE_HULL;

@@ -22,7 +22,9 @@
  *                      in place, and only then updates q, A, bounds; here the new solver is set up directly on this tick's
  *                      data (the intermediate equilibration with stale A / q is not reproduced).
  * A keeps every entry of the task-row block, zeros included (iDynTree::Triplets::addSubMatrix pushes all elements, :206-218),
- * so its pattern never changes.  solve() returns OsqpEigen's exit flag (false only for a non-convex problem) and then applies
+ * so its pattern never changes.  solve() returns what OsqpEigen::Solver::solve() returns -- by default osqp_solve's exit flag
+ * (false only for a non-convex problem: osqp-eigen of the reference's time), with osqp_eigen_checks_status also false for
+ * every status but OSQP_SOLVED (osqp-eigen >= 0.4); the same switch and the same rule as the MPC -- and then applies
  * isSolutionFeasible (:395-408, tolerance 1, `||`).
  * PARITY UNPINNED: neither the reference nor this container holds osqp-eigen / OSQP or any golden vector for this class.
  */
@@ -132,7 +134,9 @@ int wco_ikosqp_solve(wco_ikosqp* h,
     if (iters) *iters = wco_osqp_iter(h->w);
     const double* x = wco_osqp_solution_x(h->w);
     int fl = 0;
-    if (st == WC_OSQP_NON_CVX) fl |= 1; /* osqp_solve's exit flag: the only case m_optimizerSolver->solve() is false */
+    /* m_optimizerSolver->solve() (:377): false for a non-convex problem (osqp_solve's exit flag), and with osqp-eigen >= 0.4
+     * (osqp_eigen_checks_status) for every status but OSQP_SOLVED -- the same rule as the MPC (mpc_ref.c) */
+    if (st == WC_OSQP_NON_CVX || st == WC_OSQP_UNSOLVED || (h->st.osqp_eigen_checks_status && st != WC_OSQP_SOLVED)) fl |= 1;
     /* isSolutionFeasible (:395-408) */
     {
         double mu = -INFINITY, ml = -INFINITY;

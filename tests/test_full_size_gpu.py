@@ -2,7 +2,7 @@
 
 The oracle cannot run 65536 instances in seconds, so at full size the CUDA path is checked by
   * the oracle on a random subset of the batch (instances are independent: a column subset is a valid batch),
-  * agreement of the two independently written ADMM kernels (chain-per-thread vs cooperative) and of the two
+  * agreement of the three independently written ADMM kernel families (split-chain, chain-per-thread, cooperative) and of the two
     IK paths (stance-foot elimination + Schur solve vs null-space / active-set) on every instance,
   * problem-level invariants: ZMP inside the support polygon + tolerance, OSQP solved everywhere, IK task
     residuals ~ 0, joint velocity bounds respected,
@@ -19,10 +19,10 @@ SUB = 192
 
 
 def _mpc_run(wc, g, traj_d, dev, path, monkeypatch):
-    if path == "coop":
-        monkeypatch.setenv("WC_MPC_PATH", "coop")
-    else:
+    if path == "split":   # what wc_mpc_create picks at N = 25
         monkeypatch.delenv("WC_MPC_PATH", raising=False)
+    else:
+        monkeypatch.setenv("WC_MPC_PATH", path)
     m = wc.MpcBatch(wc.mpc_default_config(N), B)
     assert m.path == path
     outs = []
@@ -38,9 +38,10 @@ def _mpc_run(wc, g, traj_d, dev, path, monkeypatch):
 def test_mpc_full_size(wc, syn, oracle, cuda_device, monkeypatch):
     g = syn.GaitBatch(B, T, N, seed=0xB200, device=cuda_device)
     traj = g.trajectory()
-    chain = _mpc_run(wc, g, traj, cuda_device, "chain", monkeypatch)
-    chain2 = _mpc_run(wc, g, traj, cuda_device, "chain", monkeypatch)
+    chain = _mpc_run(wc, g, traj, cuda_device, "split", monkeypatch)
+    chain2 = _mpc_run(wc, g, traj, cuda_device, "split", monkeypatch)
     coop = _mpc_run(wc, g, traj, cuda_device, "coop", monkeypatch)
+    third = _mpc_run(wc, g, traj, cuda_device, "chain", monkeypatch)
     rng = np.random.default_rng(1)
     idx = np.sort(rng.choice(B, SUB, replace=False))
     idx_t = torch.from_numpy(idx).to(cuda_device)
@@ -50,9 +51,10 @@ def test_mpc_full_size(wc, syn, oracle, cuda_device, monkeypatch):
         # determinism: the same launch sequence gives the same bits (atomics only order the work lists)
         for key in ("zmp", "status", "iters", "flags"):
             assert torch.equal(c[key], c2[key]), f"tick {t}: {key} not deterministic"
-        # two independent kernels, every instance
-        assert torch.equal(c["status"], k["status"]) and torch.equal(c["iters"], k["iters"]) and torch.equal(c["flags"], k["flags"])
-        assert (c["zmp"] - k["zmp"]).abs().max().item() <= 1e-9
+        # three independently written kernel families (split-chain, cooperative, chain-per-thread), every instance
+        for other in (k, third[t]):
+            assert torch.equal(c["status"], other["status"]) and torch.equal(c["iters"], other["iters"]) and torch.equal(c["flags"], other["flags"])
+            assert (c["zmp"] - other["zmp"]).abs().max().item() <= 1e-9
         # invariants
         assert (c["status"] == 1).all(), "OSQP did not solve every instance of the nominal workload"
         assert ((c["flags"] & (4 | 8)) == 0).all(), "a solved instance left the support polygon + tolerance"

@@ -234,6 +234,20 @@ def test_ik_osqp_gpu_max_iter_and_inaccurate(wc, oracle, syn, cuda_device):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("checks", [0, 1])
+def test_ik_osqp_gpu_solve_semantics(wc, oracle, syn, cuda_device, checks):
+    """m_optimizerSolver->solve() (..._osqp.cpp:377) under the two osqp-eigen behaviours (osqp_eigen_checks_status, the same
+    switch and rule as the MPC): flag bit 0 is set for every non-SOLVED status only when the status is checked"""
+    so, sg = oracle.mpc_default_config(25).osqp, wc.mpc_default_config(25).osqp
+    for s in (so, sg):
+        s.max_iter = 7; s.eps_abs = 1e-6; s.eps_rel = 1e-6; s.osqp_eigen_checks_status = checks
+    o, g = _ext_kin_pair(wc, oracle, syn, cuda_device, 32, 22, so, sg)
+    assert set(np.unique(o["status"])) <= {2, -2}
+    assert ((o["flags"] & 1) == checks).all()
+    assert np.array_equal(g["status"], o["status"]) and np.array_equal(g["flags"], o["flags"])
+
+
+@pytest.mark.gpu
 def test_ik_osqp_gpu_primal_infeasible(wc, oracle, syn, cuda_device):
     """identical feet Jacobians with different right-hand sides: contradictory equality rows -> OSQP_PRIMAL_INFEASIBLE"""
     def mutate(kin, ino):

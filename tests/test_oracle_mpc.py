@@ -1,5 +1,6 @@
 """The MPC restatement (oracle/mpc_ref.c) checked by independent means."""
 import numpy as np
+import pytest
 import scipy.linalg as sla
 
 
@@ -151,3 +152,36 @@ def test_no_contact_and_reset_paths(oracle, syn):
     mb.reset(np.array([1, 0], np.uint8))
     z, st, it, fl = mb.tick(*args(2, np.array([1, 1], np.uint8), np.array([1, 1], np.uint8)))
     assert fl[0] == 16 and fl[1] == 16
+
+
+@pytest.mark.parametrize("checks", [0, 1])
+def test_osqp_eigen_solve_semantics(oracle, syn, checks):
+    """OsqpEigen::Solver::solve() under the two osqp-eigen behaviours (wc_osqp_settings.osqp_eigen_checks_status):
+    0 = the reference's time, solve() true for SOLVED_INACCURATE / MAX_ITER_REACHED and m_output takes the last iterate;
+    1 = osqp-eigen >= 0.4, solve() false unless OSQP_SOLVED and m_output (= the next tick's u_prev) is kept."""
+    N, B, T = 10, 16, 6
+    g = syn.GaitBatch(B, T, N, seed=9)
+    traj = g.trajectory().numpy()
+    cfg = oracle.mpc_default_config(N)
+    cfg.osqp.eps_abs = cfg.osqp.eps_rel = 1e-5
+    cfg.osqp.max_iter = 25
+    cfg.osqp.osqp_eigen_checks_status = checks
+    mb = oracle.MpcBatch(cfg, B)
+    prev = None
+    seen = set()
+    for t in range(T):
+        f = g.feet(t)
+        z, st, it, fl = mb.tick(f["lf_H"].numpy(), f["rf_H"].numpy(), f["l_contact"].numpy(), f["r_contact"].numpy(),
+                                g.measured_dcm(t).numpy(), np.ascontiguousarray(traj[2 * t: 2 * t + 2 * (N + 1)]))
+        seen |= set(st.tolist())
+        unsolved = st != 1
+        if checks:
+            assert ((fl & 4) != 0)[unsolved].all() and ((fl & 4) == 0)[~unsolved].all()
+            if prev is not None:
+                assert np.array_equal(z[:, unsolved], prev[:, unsolved])          # m_output kept
+        else:
+            assert ((fl & 4) == 0).all()                                          # solve() true for every status met here
+            if prev is not None and unsolved.any():
+                assert not np.array_equal(z[:, unsolved], prev[:, unsolved])      # the last iterate became m_output
+        prev = z.copy()
+    assert {-2, 2} <= seen

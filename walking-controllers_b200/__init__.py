@@ -35,7 +35,7 @@ class OsqpSettings(C.Structure):
                 ("adaptive_rho_tolerance", C.c_double), ("infty", C.c_double),
                 ("max_iter", C.c_int32), ("scaling", C.c_int32), ("check_termination", C.c_int32),
                 ("adaptive_rho", C.c_int32), ("adaptive_rho_interval", C.c_int32),
-                ("warm_start", C.c_int32), ("reserved0", C.c_int32), ("reserved1", C.c_int32)]
+                ("warm_start", C.c_int32), ("osqp_eigen_checks_status", C.c_int32), ("reserved1", C.c_int32)]
 
 
 class MpcConfig(C.Structure):

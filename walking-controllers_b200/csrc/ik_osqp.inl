@@ -515,7 +515,9 @@ __global__ void __launch_bounds__(kOsqpWarps * 32) ik_osqp_kernel(IkDev d, IkTic
 #pragma unroll
         for (int r = 0; r < 3; r++) axc[r] = warp_sum(isvar ? colC[r] * xs : 0.0);
     }
-    int flags = status == WC_OSQP_NON_CVX ? 1 : 0;
+    // bit 0: m_optimizerSolver->solve() false (..._osqp.cpp:377): a non-convex problem, and with osqp-eigen >= 0.4
+    // (osqp_eigen_checks_status) every status but OSQP_SOLVED -- the same rule as the MPC kernels
+    int flags = (status == WC_OSQP_NON_CVX || status == WC_OSQP_UNSOLVED || (st.osqp_eigen_checks_status && status != WC_OSQP_SOLVED)) ? 1 : 0;
     {
         double mu = -INFINITY, ml = -INFINITY;
 #pragma unroll

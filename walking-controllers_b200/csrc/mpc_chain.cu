@@ -1131,8 +1131,8 @@ __global__ void __launch_bounds__(2 * IPW) mpc_chain_kernel(MpcDev d, MpcTickIO 
                 d.rho[i] = rho;
                 d.rho_updates[i] = rho_updates;
                 if (init_state == 2) d.inited[i] = 1;
-                if (status == WC_OSQP_SOLVED) {
-                    out[0] = u0_mine; out[1] = u0_other;
+                if (osqp_eigen_solve_ok(status, st.osqp_eigen_checks_status)) {
+                    out[0] = has_sol ? u0_mine : NAN; out[1] = has_sol ? u0_other : NAN;
                     d.uprev[i] = out[0]; d.uprev[B + i] = out[1];
                     // ConvexHullProjectionConstraint::computeMargin (Controller.cpp:513-517)
                     // margin < -tol  <=>  outside the polygon AND farther than tol from its boundary: the distance to

@@ -858,9 +858,9 @@ __global__ void __launch_bounds__(128) mpc_admm_kernel(MpcDev d, MpcTickIO io, i
             d.z0[B + i] = has_sol ? z0prev[1] : 0.0;
             d.rho[i] = rho;
             d.rho_updates[i] = rho_updates;
-            if (status == WC_OSQP_SOLVED) {
-                out[0] = s.X[nR] * s.DD[nR];
-                out[1] = s.X[nA + nR] * s.DD[nA + nR];
+            if (osqp_eigen_solve_ok(status, st.osqp_eigen_checks_status)) {
+                out[0] = has_sol ? s.X[nR] * s.DD[nR] : NAN;
+                out[1] = has_sol ? s.X[nA + nR] * s.DD[nA + nR] : NAN;
                 d.uprev[i] = out[0]; d.uprev[B + i] = out[1];
                 // ConvexHullProjectionConstraint::computeMargin (Controller.cpp:513-517)
                 bool inside = true;

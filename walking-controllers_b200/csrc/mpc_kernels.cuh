@@ -92,6 +92,22 @@ struct MpcTickIO {
     double* zmp; int32_t* status; int32_t* iters; int32_t* flags;
 };
 
+// What OsqpEigen::Solver::solve() returns for an OSQP status (wc_osqp_settings::osqp_eigen_checks_status): the 2018
+// osqp-eigen returns osqp_solve() == 0 -- true for every status but a non-convex problem; since 0.4 it is false unless the
+// status is OSQP_SOLVED.  The callers (MPCSolver.cpp:309 -> Controller.cpp:503-517, ..._osqp.cpp:377) then read OSQP's
+// stored solution: the last iterate where osqp_has_solution, NaN otherwise (OSQP store_solution).
+__host__ __device__ inline bool osqp_eigen_solve_ok(int status, int checks_status)
+{
+    if (checks_status) return status == WC_OSQP_SOLVED;
+    return status != WC_OSQP_NON_CVX && status != WC_OSQP_UNSOLVED;
+}
+__host__ __device__ inline bool osqp_has_solution(int status)
+{
+    return !(status == WC_OSQP_PRIMAL_INFEASIBLE || status == WC_OSQP_PRIMAL_INFEASIBLE_INACCURATE ||
+             status == WC_OSQP_DUAL_INFEASIBLE || status == WC_OSQP_DUAL_INFEASIBLE_INACCURATE ||
+             status == WC_OSQP_UNSOLVED || status == WC_OSQP_NON_CVX);
+}
+
 __host__ __device__ inline int mpc_nA(int N) { return 2 * N + 1; }
 __host__ __device__ inline int mpc_nR(int N) { return N + 1; }
 // doubles of shared memory per instance in K2

@@ -807,8 +807,8 @@ __global__ void __launch_bounds__(32, WC_SPLIT_MINB) mpc_split_kernel(MpcDev d, 
                 d.rho[i] = rho;
                 d.rho_updates[i] = rho_updates;
                 if (init_state == 2) d.inited[i] = 1;
-                if (status == WC_OSQP_SOLVED) {
-                    out[0] = zx; out[1] = zy;
+                if (osqp_eigen_solve_ok(status, st.osqp_eigen_checks_status)) {
+                    out[0] = has_sol ? zx : NAN; out[1] = has_sol ? zy : NAN;
                     d.uprev[i] = out[0]; d.uprev[B + i] = out[1];
                     const bool inside = !outside;
                     double best = INFINITY;

@@ -31,6 +31,8 @@ void wc_osqp_default_settings(wc_osqp_settings* s)
     s->adaptive_rho = 1;
     s->adaptive_rho_interval = 0;
     s->warm_start = 1;
+    s->osqp_eigen_checks_status = 0; /* osqp-eigen of the reference's time: solve() does not look at the status */
+    s->reserved1 = 0;
 }
 
 void wc_mpc_default_config(wc_mpc_config* cfg, int32_t horizon)
