@@ -164,6 +164,18 @@ wc_status wc_mpc_tick_dev(wc_mpc* h,
                           const double* dcm_meas, const double* ref, const uint8_t* reset,
                           double* zmp, int32_t* osqp_status, int32_t* iters, int32_t* flags,
                           void* stream);
+/* The same tick with the DCM reference window kept in a device-side ring (what MPCSolver::setGradient's block shift does
+ * with the gradient, MPCSolver.cpp:216-239): per tick the caller provides only the NEWEST sample of the window,
+ * ref_newest [2*B] = sample N of this tick's window.  ref_window [(N+1)*2*B] (layout of `ref` above) replaces the whole
+ * ring instead; it is required at the first ring tick and whenever the trajectory was re-planned (the ticks on which
+ * the reference passes resetTrajectory = true) and may be NULL otherwise.  Results are bit-identical to
+ * wc_mpc_tick_dev on the same windows (tests/test_host_pipeline_gpu.py). */
+wc_status wc_mpc_tick_ring_dev(wc_mpc* h, const double* lf_H, const double* rf_H,
+                               const uint8_t* l_contact, const uint8_t* r_contact,
+                               const double* dcm_meas, const double* ref_newest, const double* ref_window,
+                               const uint8_t* reset, double* zmp, int32_t* osqp_status, int32_t* iters, int32_t* flags,
+                               void* stream);
+
 /* Same with HOST pointers (pinned staging + H2D/D2H inside the call, synchronous on return). */
 wc_status wc_mpc_tick_host(wc_mpc* h,
                            const double* lf_H, const double* rf_H,
@@ -185,6 +197,9 @@ wc_status wc_mpc_tick_host_async(wc_mpc* h,
                            double* zmp, int32_t* osqp_status, int32_t* iters, int32_t* flags);
 wc_status wc_mpc_sync(wc_mpc* h);
 wc_status wc_mpc_sync_one(wc_mpc* h);
+/* NOTE (all handles): wc_*_reset*, wc_*_set_weights_host / wc_*_set_gains_host first retire the host ticks in flight
+ * (they touch state those ticks read or write); nothing else orders them against *_dev ticks on caller streams --
+ * synchronise those streams before calling them. */
 
 /* Debug / parity taps (device -> host copies, synchronous): full primal solution
  * z = [x_0..x_N, u_0..u_{N-1}] per instance ([n*B], field-major, n = 4N+2), the current
@@ -274,6 +289,7 @@ typedef struct wc_ik wc_ik;
 wc_status wc_ik_create(const wc_ik_config* cfg, const wc_model* model, int32_t B, int32_t device, wc_ik** out);
 void wc_ik_destroy(wc_ik* h);
 int32_t wc_ik_batch(const wc_ik* h);
+int32_t wc_ik_dofs(const wc_ik* h);
 
 /* Per-instance gain overrides k_pos_foot[B], k_att_foot[B] (gain sweeps). Host pointers. */
 wc_status wc_ik_set_gains_host(wc_ik* h, const double* k_pos_foot, const double* k_att_foot);
@@ -393,6 +409,38 @@ wc_status wc_ik_kernel_times_detail_ms(wc_ik* h, double* fast_ms, double* genera
  * fast kernel (their equality-constrained optimum violated a velocity bound: first working-set change in closed form)
  * and how many went on to the general null-space + Goldfarb-Idnani kernel.  Both 0 when the fast path is off. */
 wc_status wc_ik_path_counts_host(wc_ik* h, int32_t* second_pass, int32_t* general);
+
+/* ---------------------------------------------------------------------------------- */
+/* Fused host tick of both blocks: what one WalkingModule::updateModule iteration hands  */
+/* to WalkingController and WalkingQPIK (WalkingModule.cpp:601-637, 367-425), uploaded    */
+/* ONCE.  m_leftTrajectory.front() / m_rightTrajectory.front() serve the MPC's hull, the */
+/* IK's desired feet and (base_H == NULL) the stance-foot base transform; the DCM         */
+/* reference travels as one new sample per tick (wc_mpc_tick_ring_dev).  836 B instead of */
+/* 1 523 B per instance and tick at nJ = 23.  The MPC kernels and the FK + QP-IK kernels  */
+/* run on two streams of the MPC handle's pipe; staging is double-buffered as for         */
+/* wc_mpc_tick_host_async, and wc_mpc_sync_one / wc_mpc_sync retire fused ticks too.      */
+/* All pointers are HOST pointers (pinned for true asynchrony), layouts as in the         */
+/* per-block entry points; outputs may be NULL.                                           */
+/* ---------------------------------------------------------------------------------- */
+typedef struct wc_tick_host_in {
+    const double *lf_H, *rf_H;                    /* [12*B] desired feet transforms (hull, IK targets, stance base) */
+    const uint8_t *l_contact, *r_contact;         /* [B] */
+    const uint8_t *left_is_fixed;                 /* [B] */
+    const uint8_t *reset;                         /* [B] resetTrajectory, or NULL */
+    const double *dcm_meas;                       /* [2*B] */
+    const double *ref_newest;                     /* [2*B] newest sample of the DCM window (NULL iff ref_window) */
+    const double *ref_window;                     /* [(N+1)*2*B] whole window: first tick / after a re-plan, else NULL */
+    const double *q_meas, *q_lin;                 /* [nJ*B] */
+    const double *base_H;                         /* [12*B] or NULL = stance foot's transform */
+    const double *lf_twist, *rf_twist;            /* [6*B] */
+    const double *com_pos_des, *com_vel_des, *com_meas; /* [3*B] */
+    const double *neck_R_des;                     /* [9*B] */
+} wc_tick_host_in;
+typedef struct wc_tick_host_out {
+    double* zmp; int32_t *osqp_status, *iters, *flags;          /* as wc_mpc_tick_host */
+    double *dq, *lf_err, *rf_err; int32_t *qp_status, *nwsr;    /* as wc_ik_tick_host */
+} wc_tick_host_out;
+wc_status wc_tick_host_async(wc_mpc* mpc, wc_ik* ik, const wc_tick_host_in* in, const wc_tick_host_out* out);
 
 /* ---------------------------------------------------------------------------------- */
 /* Closed-loop glue between the two blocks: replaces, batched,     */

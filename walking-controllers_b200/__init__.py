@@ -6,6 +6,7 @@ device memory / streams.  The directory name is not a Python identifier; import 
     importlib.import_module("walking-controllers_b200")
 There is NO CPU fallback: every compute entry point raises if the CUDA library is missing.
 """
+import collections
 import ctypes as C
 import os
 import subprocess
@@ -26,6 +27,16 @@ OSQP_DUAL_INFEASIBLE = -4
 OSQP_UNSOLVED = -10
 MPC_FLAG_NO_CONTACT, MPC_FLAG_NO_SOLVER, MPC_FLAG_NOT_SOLVED, MPC_FLAG_OUTSIDE_HULL, MPC_FLAG_NEW_SOLVER = 1, 2, 4, 8, 16
 QP_SUCCESSFUL_RETURN, QP_MAX_NWSR_REACHED, QP_INFEASIBLE, QP_NOT_CONVEX = 0, 1, 2, 3
+
+
+class TickHostIn(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("lf_H", "rf_H", "l_contact", "r_contact", "left_is_fixed", "reset", "dcm_meas",
+                                          "ref_newest", "ref_window", "q_meas", "q_lin", "base_H", "lf_twist", "rf_twist",
+                                          "com_pos_des", "com_vel_des", "com_meas", "neck_R_des")]
+
+
+class TickHostOut(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("zmp", "osqp_status", "iters", "flags", "dq", "lf_err", "rf_err", "qp_status", "nwsr")]
 
 
 class OsqpSettings(C.Structure):
@@ -156,6 +167,8 @@ def lib():
     L.wc_mpc_set_weights_host.argtypes = [_VP, _VP, _VP]; L.wc_mpc_set_weights_host.restype = i32
     L.wc_mpc_reset.argtypes = [_VP, _VP]; L.wc_mpc_reset.restype = i32
     L.wc_mpc_tick_dev.argtypes = [_VP] + [_VP] * 11 + [_VP]; L.wc_mpc_tick_dev.restype = i32
+    L.wc_mpc_tick_ring_dev.argtypes = [_VP] + [_VP] * 12 + [_VP]; L.wc_mpc_tick_ring_dev.restype = i32
+    L.wc_tick_host_async.argtypes = [_VP, _VP, C.POINTER(TickHostIn), C.POINTER(TickHostOut)]; L.wc_tick_host_async.restype = i32
     L.wc_mpc_tick_host.argtypes = [_VP] + [_VP] * 11; L.wc_mpc_tick_host.restype = i32
     L.wc_mpc_tick_host_async.argtypes = [_VP] + [_VP] * 11; L.wc_mpc_tick_host_async.restype = i32
     L.wc_mpc_sync.argtypes = [_VP]; L.wc_mpc_sync.restype = i32
@@ -198,6 +211,7 @@ def lib():
         L.wc_ik_create.restype = i32
         L.wc_ik_destroy.argtypes = [_VP]
         L.wc_ik_batch.argtypes = [_VP]; L.wc_ik_batch.restype = i32
+        L.wc_ik_dofs.argtypes = [_VP]; L.wc_ik_dofs.restype = i32
         L.wc_ik_set_gains_host.argtypes = [_VP, _VP, _VP]; L.wc_ik_set_gains_host.restype = i32
         L.wc_ik_tick_dev.argtypes = [_VP] + [_VP] * 17 + [_VP]; L.wc_ik_tick_dev.restype = i32
         L.wc_ik_tick_host.argtypes = [_VP] + [_VP] * 17; L.wc_ik_tick_host.restype = i32
@@ -255,6 +269,47 @@ def _ptr(t):
     return t.ctypes.data
 
 
+_KINDS = {"f64": ("float64", 8), "u8": ("uint8", 1), "i32": ("int32", 4)}
+
+
+def _arg(t, kind, n, where, name):
+    """Validated pointer for the C ABI (which takes raw pointers and sizes and cannot check anything): dtype `kind`
+    ('f64' | 'u8' | 'i32'; bool counts as u8), C-contiguous, at least n elements, and on the side of the bus the entry point
+    expects (where = 'cuda' | 'host').  A wrong dtype, a transposed view, a CPU tensor handed to a *_dev call or a short
+    output buffer raises here instead of reading or writing out of bounds on the device.  None -> NULL."""
+    if t is None:
+        return None
+    dname, _ = _KINDS[kind]
+    if hasattr(t, "data_ptr"):  # torch tensor
+        dt = str(t.dtype).replace("torch.", "")
+        if dt == "bool" and kind == "u8":
+            dt = "uint8"
+        if dt != dname:
+            raise TypeError(f"{name}: dtype {dt}, the C ABI expects {dname}")
+        if not t.is_contiguous():
+            raise ValueError(f"{name}: not contiguous (a transposed / strided view); pass .contiguous()")
+        if t.numel() < n:
+            raise ValueError(f"{name}: {t.numel()} elements, the C ABI reads / writes {n}")
+        on_cuda = t.is_cuda
+        if where == "cuda" and not on_cuda:
+            raise ValueError(f"{name}: a CPU tensor was passed to a device-pointer (*_dev) entry point")
+        if where == "host" and on_cuda:
+            raise ValueError(f"{name}: a CUDA tensor was passed to a host-pointer entry point")
+        return t.data_ptr()
+    dt = str(t.dtype)
+    if dt == "bool" and kind == "u8":
+        dt = "uint8"
+    if dt != dname:
+        raise TypeError(f"{name}: dtype {dt}, the C ABI expects {dname}")
+    if not t.flags["C_CONTIGUOUS"]:
+        raise ValueError(f"{name}: not C-contiguous; pass np.ascontiguousarray(...)")
+    if t.size < n:
+        raise ValueError(f"{name}: {t.size} elements, the C ABI reads / writes {n}")
+    if where == "cuda":
+        raise ValueError(f"{name}: a numpy array was passed to a device-pointer (*_dev) entry point")
+    return t.ctypes.data
+
+
 class MpcBatch:
     """Batched DCM-MPC handle (mirrors WalkingController for B instances).
 
@@ -266,6 +321,7 @@ class MpcBatch:
         h = _VP()
         _check(lib().wc_mpc_create(C.byref(cfg), B, device, C.byref(h)), "wc_mpc_create")
         self.h = h
+        self._inflight = collections.deque()  # buffers of the host ticks in flight (kept alive until retired)
 
     def close(self):
         if getattr(self, "h", None):
@@ -295,9 +351,35 @@ class MpcBatch:
                        flags=torch.empty(B, dtype=torch.int32, device=dev))
         if stream is None:
             stream = torch.cuda.current_stream(lf_H.device).cuda_stream
-        _check(lib().wc_mpc_tick_dev(self.h, _ptr(lf_H), _ptr(rf_H), _ptr(l_contact), _ptr(r_contact), _ptr(dcm),
-                                     _ptr(ref), _ptr(reset), _ptr(out["zmp"]), _ptr(out["status"]),
-                                     _ptr(out["iters"]), _ptr(out["flags"]), stream), "wc_mpc_tick_dev")
+        a = self._args(lf_H, rf_H, l_contact, r_contact, dcm, ref, reset, out, "cuda")
+        _check(lib().wc_mpc_tick_dev(self.h, *a, stream), "wc_mpc_tick_dev")
+        return out
+
+    def _args(self, lf_H, rf_H, l_contact, r_contact, dcm, ref, reset, out, where, ref_rows=None):
+        B, N = self.B, self.N
+        return (_arg(lf_H, "f64", 12 * B, where, "lf_H"), _arg(rf_H, "f64", 12 * B, where, "rf_H"),
+                _arg(l_contact, "u8", B, where, "l_contact"), _arg(r_contact, "u8", B, where, "r_contact"),
+                _arg(dcm, "f64", 2 * B, where, "dcm"),
+                _arg(ref, "f64", (2 * (N + 1) if ref_rows is None else ref_rows) * B, where, "ref"),
+                _arg(reset, "u8", B, where, "reset"), _arg(out["zmp"], "f64", 2 * B, where, "out.zmp"),
+                _arg(out["status"], "i32", B, where, "out.status"), _arg(out["iters"], "i32", B, where, "out.iters"),
+                _arg(out["flags"], "i32", B, where, "out.flags"))
+
+    def tick_ring(self, lf_H, rf_H, l_contact, r_contact, dcm, ref_newest=None, ref_window=None, reset=None, out=None,
+                  stream=None):
+        """wc_mpc_tick_ring_dev: the DCM window lives in a device-side ring; per tick only its newest sample
+        (ref_newest [2, B]) is passed, the whole window (ref_window) on the first tick and after a re-plan"""
+        import torch
+        B, N = self.B, self.N
+        if out is None:
+            dev = lf_H.device
+            out = dict(zmp=torch.empty(2, B, dtype=torch.float64, device=dev), status=torch.empty(B, dtype=torch.int32, device=dev),
+                       iters=torch.empty(B, dtype=torch.int32, device=dev), flags=torch.empty(B, dtype=torch.int32, device=dev))
+        if stream is None:
+            stream = torch.cuda.current_stream(lf_H.device).cuda_stream
+        a = self._args(lf_H, rf_H, l_contact, r_contact, dcm, ref_newest, reset, out, "cuda", ref_rows=2)
+        _check(lib().wc_mpc_tick_ring_dev(self.h, *a[:6], _arg(ref_window, "f64", 2 * (N + 1) * B, "cuda", "ref_window"),
+                                          *a[6:], stream), "wc_mpc_tick_ring_dev")
         return out
 
     def tick_host(self, lf_H, rf_H, l_contact, r_contact, dcm, ref, reset=None, out=None):
@@ -306,24 +388,47 @@ class MpcBatch:
         if out is None:
             out = dict(zmp=np.empty((2, B)), status=np.empty(B, np.int32), iters=np.empty(B, np.int32),
                        flags=np.empty(B, np.int32))
-        _check(lib().wc_mpc_tick_host(self.h, _ptr(lf_H), _ptr(rf_H), _ptr(l_contact), _ptr(r_contact), _ptr(dcm),
-                                      _ptr(ref), _ptr(reset), _ptr(out["zmp"]), _ptr(out["status"]),
-                                      _ptr(out["iters"]), _ptr(out["flags"])), "wc_mpc_tick_host")
+        a = self._args(lf_H, rf_H, l_contact, r_contact, dcm, ref, reset, out, "host")
+        _check(lib().wc_mpc_tick_host(self.h, *a), "wc_mpc_tick_host")
         return out
 
     def tick_host_async(self, lf_H, rf_H, l_contact, r_contact, dcm, ref, out, reset=None):
-        """enqueue copies + kernels on the handle's stream; buffers (pinned) must outlive sync()"""
-        _check(lib().wc_mpc_tick_host_async(self.h, _ptr(lf_H), _ptr(rf_H), _ptr(l_contact), _ptr(r_contact), _ptr(dcm),
-                                            _ptr(ref), _ptr(reset), _ptr(out["zmp"]), _ptr(out["status"]),
-                                            _ptr(out["iters"]), _ptr(out["flags"])), "wc_mpc_tick_host_async")
+        """enqueue copies + kernels on the handle's stream; the handle keeps the buffers referenced until the tick is
+        retired by sync_one() / sync() (a temporary freed before its DMA ran would be read or written after the free)"""
+        a = self._args(lf_H, rf_H, l_contact, r_contact, dcm, ref, reset, out, "host")
+        _check(lib().wc_mpc_tick_host_async(self.h, *a), "wc_mpc_tick_host_async")
+        self._inflight.append((lf_H, rf_H, l_contact, r_contact, dcm, ref, reset, out))
+        return out
+
+    def tick_fused_host_async(self, ik, inp, out):
+        """wc_tick_host_async: one upload for both blocks.  inp: dict of host (pinned) arrays with the keys of
+        wc_tick_host_in (absent / None = NULL where the C ABI allows it); out: dict with the keys of wc_tick_host_out."""
+        B, N, nJ = self.B, self.N, ik.nJ
+        f = TickHostIn(); o = TickHostOut()
+        rows_in = dict(lf_H=12, rf_H=12, dcm_meas=2, ref_newest=2, ref_window=2 * (N + 1), q_meas=nJ, q_lin=nJ, base_H=12,
+                       lf_twist=6, rf_twist=6, com_pos_des=3, com_vel_des=3, com_meas=3, neck_R_des=9)
+        for k, r in rows_in.items():
+            setattr(f, k, _arg(inp.get(k), "f64", r * B, "host", k))
+        for k in ("l_contact", "r_contact", "left_is_fixed", "reset"):
+            setattr(f, k, _arg(inp.get(k), "u8", B, "host", k))
+        rows_out = dict(zmp=2, dq=nJ, lf_err=6, rf_err=6)
+        for k, r in rows_out.items():
+            setattr(o, k, _arg(out.get(k), "f64", r * B, "host", "out." + k))
+        for k in ("osqp_status", "iters", "flags", "qp_status", "nwsr"):
+            setattr(o, k, _arg(out.get(k), "i32", B, "host", "out." + k))
+        _check(lib().wc_tick_host_async(self.h, ik.h, C.byref(f), C.byref(o)), "wc_tick_host_async")
+        self._inflight.append((inp, out))
         return out
 
     def sync(self):
         _check(lib().wc_mpc_sync(self.h), "wc_mpc_sync")
+        self._inflight.clear()
 
     def sync_one(self):
         """retire the oldest host tick in flight (up to two may be)"""
         _check(lib().wc_mpc_sync_one(self.h), "wc_mpc_sync_one")
+        if self._inflight:
+            self._inflight.popleft()
 
     def debug(self):
         import numpy as np
@@ -371,6 +476,7 @@ class IkBatch:
         h = _VP()
         _check(lib().wc_ik_create(C.byref(cfg), C.byref(model), B, device, C.byref(h)), "wc_ik_create")
         self.h = h
+        self._inflight = collections.deque()  # buffers of the host ticks in flight (kept alive until retired)
 
     def close(self):
         if getattr(self, "h", None):
@@ -416,9 +522,18 @@ class IkBatch:
             out = self._outs(dev)
         if stream is None:
             stream = torch.cuda.current_stream(dev).cuda_stream
-        _check(lib().wc_ik_tick_dev(self.h, *[_ptr(inp[k]) for k in IK_INPUT_KEYS], _ptr(out["dq"]), _ptr(out["lf_err"]),
-                                    _ptr(out["rf_err"]), _ptr(out["status"]), _ptr(out["nwsr"]), stream), "wc_ik_tick_dev")
+        _check(lib().wc_ik_tick_dev(self.h, *self._args(inp, out, "cuda"), stream), "wc_ik_tick_dev")
         return out
+
+    def _args(self, inp, out, where):
+        B, nJ = self.B, self.nJ
+        rows = dict(q_meas=nJ, q_lin=nJ, base_H=12, lf_H_des=12, rf_H_des=12, lf_twist=6, rf_twist=6, com_pos_des=3,
+                    com_vel_des=3, com_meas=3, neck_R_des=9)
+        a = [_arg(inp.get(k), "u8", B, where, k) if k == "left_is_fixed" else _arg(inp.get(k), "f64", rows[k] * B, where, k)
+             for k in IK_INPUT_KEYS]
+        return a + [_arg(out["dq"], "f64", nJ * B, where, "out.dq"), _arg(out["lf_err"], "f64", 6 * B, where, "out.lf_err"),
+                    _arg(out["rf_err"], "f64", 6 * B, where, "out.rf_err"), _arg(out["status"], "i32", B, where, "out.status"),
+                    _arg(out["nwsr"], "i32", B, where, "out.nwsr")]
 
     def tick_host(self, inp, out=None):
         import numpy as np
@@ -426,21 +541,23 @@ class IkBatch:
         if out is None:
             out = dict(dq=np.empty((nJ, B)), lf_err=np.empty((6, B)), rf_err=np.empty((6, B)),
                        status=np.empty(B, np.int32), nwsr=np.empty(B, np.int32))
-        _check(lib().wc_ik_tick_host(self.h, *[_ptr(inp[k]) for k in IK_INPUT_KEYS], _ptr(out["dq"]), _ptr(out["lf_err"]),
-                                     _ptr(out["rf_err"]), _ptr(out["status"]), _ptr(out["nwsr"])), "wc_ik_tick_host")
+        _check(lib().wc_ik_tick_host(self.h, *self._args(inp, out, "host")), "wc_ik_tick_host")
         return out
 
     def tick_host_async(self, inp, out):
-        _check(lib().wc_ik_tick_host_async(self.h, *[_ptr(inp[k]) for k in IK_INPUT_KEYS], _ptr(out["dq"]),
-                                           _ptr(out["lf_err"]), _ptr(out["rf_err"]), _ptr(out["status"]),
-                                           _ptr(out["nwsr"])), "wc_ik_tick_host_async")
+        """buffers stay referenced by the handle until sync_one() / sync() retires the tick"""
+        _check(lib().wc_ik_tick_host_async(self.h, *self._args(inp, out, "host")), "wc_ik_tick_host_async")
+        self._inflight.append((inp, out))
         return out
 
     def sync(self):
         _check(lib().wc_ik_sync(self.h), "wc_ik_sync")
+        self._inflight.clear()
 
     def sync_one(self):
         _check(lib().wc_ik_sync_one(self.h), "wc_ik_sync_one")
+        if self._inflight:
+            self._inflight.popleft()
 
     def fk(self, q, base_H, left_is_fixed, jacobians=True, stream=None):
         import torch
@@ -453,6 +570,8 @@ class IkBatch:
                      J_neck=torch.empty(6 * nV, B, dtype=f64, device=dev), J_com=torch.empty(3 * nV, B, dtype=f64, device=dev))
         if stream is None:
             stream = torch.cuda.current_stream(dev).cuda_stream
+        _arg(q, "f64", self.nJ * B, "cuda", "q"); _arg(base_H, "f64", 12 * B, "cuda", "base_H")
+        _arg(left_is_fixed, "u8", B, "cuda", "left_is_fixed")
         _check(lib().wc_fk_dev(self.h, _ptr(q), _ptr(base_H), _ptr(left_is_fixed), _ptr(o["lf_H"]), _ptr(o["rf_H"]),
                                _ptr(o["neck_R"]), _ptr(o["com"]), _ptr(o.get("J_lf")), _ptr(o.get("J_rf")),
                                _ptr(o.get("J_neck")), _ptr(o.get("J_com")), stream), "wc_fk_dev")

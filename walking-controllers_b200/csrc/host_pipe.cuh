@@ -11,7 +11,9 @@ namespace wcb {
 
 struct HostPipe {
     static constexpr int kSlots = 2;
-    cudaStream_t up = nullptr, run = nullptr, down = nullptr;
+    cudaStream_t up = nullptr, run = nullptr, run2 = nullptr, down = nullptr; // run2: a second kernel stream (fused MPC + IK tick)
+    cudaEvent_t fork = nullptr, join = nullptr;
+    size_t in_cap = 0, out_cap = 0;
     void* dev_in[kSlots] = {nullptr, nullptr};
     void* dev_out[kSlots] = {nullptr, nullptr};
     cudaEvent_t up_done[kSlots] = {nullptr, nullptr}, run_done[kSlots] = {nullptr, nullptr}, down_done[kSlots] = {nullptr, nullptr};
@@ -21,11 +23,25 @@ struct HostPipe {
 
     cudaError_t init(size_t in_bytes, size_t out_bytes)
     {
-        if (ready) return cudaSuccess;
+        if (ready && in_bytes <= in_cap && out_bytes <= out_cap) return cudaSuccess;
+        if (ready) { // a larger entry point on the same handle (e.g. the fused MPC + IK tick): drain and re-create
+            const cudaError_t es = sync_all();
+            if (es != cudaSuccess) return es;
+            destroy();
+        }
+        const cudaError_t e = init_once(in_bytes, out_bytes);
+        if (e != cudaSuccess) destroy(); // a partial set of streams / buffers must not leak into the next attempt
+        return e;
+    }
+    cudaError_t init_once(size_t in_bytes, size_t out_bytes)
+    {
         cudaError_t e;
         if ((e = cudaStreamCreateWithFlags(&up, cudaStreamNonBlocking)) != cudaSuccess) return e;
         if ((e = cudaStreamCreateWithFlags(&run, cudaStreamNonBlocking)) != cudaSuccess) return e;
+        if ((e = cudaStreamCreateWithFlags(&run2, cudaStreamNonBlocking)) != cudaSuccess) return e;
         if ((e = cudaStreamCreateWithFlags(&down, cudaStreamNonBlocking)) != cudaSuccess) return e;
+        if ((e = cudaEventCreateWithFlags(&fork, cudaEventDisableTiming)) != cudaSuccess) return e;
+        if ((e = cudaEventCreateWithFlags(&join, cudaEventDisableTiming)) != cudaSuccess) return e;
         for (int k = 0; k < kSlots; k++) {
             if ((e = cudaMalloc(&dev_in[k], in_bytes)) != cudaSuccess) return e;
             if ((e = cudaMalloc(&dev_out[k], out_bytes)) != cudaSuccess) return e;
@@ -33,6 +49,7 @@ struct HostPipe {
             if ((e = cudaEventCreateWithFlags(&run_done[k], cudaEventDisableTiming)) != cudaSuccess) return e;
             if ((e = cudaEventCreateWithFlags(&down_done[k], cudaEventDisableTiming)) != cudaSuccess) return e;
         }
+        in_cap = in_bytes; out_cap = out_bytes;
         ready = true;
         return cudaSuccess;
     }
@@ -44,10 +61,16 @@ struct HostPipe {
             if (up_done[k]) cudaEventDestroy(up_done[k]);
             if (run_done[k]) cudaEventDestroy(run_done[k]);
             if (down_done[k]) cudaEventDestroy(down_done[k]);
+            dev_in[k] = dev_out[k] = nullptr; up_done[k] = run_done[k] = down_done[k] = nullptr; used[k] = false;
         }
         if (up) cudaStreamDestroy(up);
         if (run) cudaStreamDestroy(run);
+        if (run2) cudaStreamDestroy(run2);
         if (down) cudaStreamDestroy(down);
+        if (fork) cudaEventDestroy(fork);
+        if (join) cudaEventDestroy(join);
+        up = run = run2 = down = nullptr; fork = join = nullptr;
+        submitted = retired = 0; in_cap = out_cap = 0;
         ready = false;
     }
     // retire the oldest tick in flight (its outputs are then in the caller's buffers)

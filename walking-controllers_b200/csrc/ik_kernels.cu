@@ -191,7 +191,9 @@ __device__ __forceinline__ void fk_stage(const IkModelDev& M, const IkTickIO& io
         for (int r = 0; r < 3; r++) pi[r] = -(Ri[3 * r] * ps[0] + Ri[3 * r + 1] * ps[1] + Ri[3 * r + 2] * ps[2]);
         double bR[9], bp[3];
         // stance-sole transform: from HBM, or from the shared-memory copy the caller prefetched
-        const double* bH = base_H_s ? base_H_s : io.base_H + i;
+        // (io.base_H == NULL: the desired transform of the stance foot, WalkingFK::evaluateWorldToBaseTransformation,
+        // WalkingForwardKinematics.cpp:217-244 -- the caller then does not upload it a second time)
+        const double* bH = base_H_s ? base_H_s : (io.base_H ? io.base_H : (left ? io.lf_H_des : io.rf_H_des)) + i;
         const size_t bs = base_H_s ? (size_t)1 : B;
         bR[0] = bH[0 * bs]; bR[1] = bH[1 * bs]; bR[2] = bH[2 * bs]; bp[0] = bH[3 * bs];
         bR[3] = bH[4 * bs]; bR[4] = bH[5 * bs]; bR[5] = bH[6 * bs]; bp[1] = bH[7 * bs];
@@ -986,7 +988,8 @@ __global__ void __launch_bounds__(kFastWarps * 32, WC_IK_FAST_MINB) ik_fast_kern
         auto pf = [&](int off, const double* src, int rows) {
             for (int r = lane; r < rows; r += 32) cp_async8(sm + off + r, src + (size_t)r * B + i);
         };
-        pf(LY::I_BASE, io.base_H, 12); pf(LY::I_LFD, io.lf_H_des, 12); pf(LY::I_RFD, io.rf_H_des, 12);
+        if (io.base_H) pf(LY::I_BASE, io.base_H, 12);
+        pf(LY::I_LFD, io.lf_H_des, 12); pf(LY::I_RFD, io.rf_H_des, 12);
         pf(LY::I_LTW, io.lf_twist, 6); pf(LY::I_RTW, io.rf_twist, 6); pf(LY::I_CPD, io.com_pos_des, 3);
         pf(LY::I_CVD, io.com_vel_des, 3); pf(LY::I_CM, io.com_meas, 3); pf(LY::I_NRD, io.neck_R_des, 9);
         pf(LY::I_QM, io.q_meas, NJ);

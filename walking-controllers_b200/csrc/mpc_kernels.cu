@@ -111,19 +111,50 @@ __global__ void __launch_bounds__(128) mpc_prepare_kernel(MpcDev d, MpcTickIO io
     const int head = d.ring_head;
 
     // ---- MPCSolver::setGradient (state block; the input block -R u_prev is formed in K2)
+    // reference sample k of this tick's window: the caller's array, or the device-side ring
+    const double* rbase = io.ref_is_ring ? d.ref_ring : io.ref;
+    auto ref_row = [&](int k) { return io.ref_is_ring ? (head + k) % nR : k; };
     if (!inited || reset) {
         for (int k = 0; k <= N; k++) {
             const int slot = (head + k) % nR;
-            d.grad[(size_t)(slot)*B + i] = -Q[0] * io.ref[(size_t)(2 * k) * B + i];
-            d.grad[(size_t)(nR + slot) * B + i] = -Q[1] * io.ref[(size_t)(2 * k + 1) * B + i];
+            const int rr = ref_row(k);
+            d.grad[(size_t)(slot)*B + i] = -Q[0] * rbase[(size_t)(2 * rr) * B + i];
+            d.grad[(size_t)(nR + slot) * B + i] = -Q[1] * rbase[(size_t)(2 * rr + 1) * B + i];
         }
     } else {
         const int slot = (head + N) % nR;
-        d.grad[(size_t)(slot)*B + i] = -Q[0] * io.ref[(size_t)(2 * N) * B + i];
-        d.grad[(size_t)(nR + slot) * B + i] = -Q[1] * io.ref[(size_t)(2 * N + 1) * B + i];
+        const int rr = ref_row(N);
+        d.grad[(size_t)(slot)*B + i] = -Q[0] * rbase[(size_t)(2 * rr) * B + i];
+        d.grad[(size_t)(nR + slot) * B + i] = -Q[1] * rbase[(size_t)(2 * rr + 1) * B + i];
     }
 
     d.tick_flags[i] = flags;
+}
+
+// the window as a ring over stages: one new sample per tick (slot of stage N), or the whole window after a replan
+__global__ void __launch_bounds__(128) mpc_ref_ring_kernel(MpcDev d, const double* newest, const double* window)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d.B) return;
+    const size_t B = (size_t)d.B;
+    const int N = d.N, nR = N + 1, head = d.ring_head;
+    if (window) {
+        for (int k = 0; k <= N; k++) {
+            const int slot = (head + k) % nR;
+            d.ref_ring[(size_t)(2 * slot) * B + i] = window[(size_t)(2 * k) * B + i];
+            d.ref_ring[(size_t)(2 * slot + 1) * B + i] = window[(size_t)(2 * k + 1) * B + i];
+        }
+    } else {
+        const int slot = (head + N) % nR;
+        d.ref_ring[(size_t)(2 * slot) * B + i] = newest[i];
+        d.ref_ring[(size_t)(2 * slot + 1) * B + i] = newest[B + i];
+    }
+}
+
+void launch_mpc_ref_ring_update(const MpcDev& d, const double* newest, const double* window, cudaStream_t s)
+{
+    const int threads = 128;
+    mpc_ref_ring_kernel<<<(d.B + threads - 1) / threads, threads, 0, s>>>(d, newest, window);
 }
 
 void launch_mpc_prepare(const MpcDev& d, const MpcTickIO& io, cudaStream_t s)

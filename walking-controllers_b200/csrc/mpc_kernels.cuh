@@ -83,6 +83,10 @@ struct MpcDev {
     int32_t* setup_count;// [1]
     int32_t* cont_list;  // [B] instances that did not stop at the first termination check
     int32_t* cont_count; // [1]
+    // device-side ring of the DCM reference window (wc_mpc_tick_ring_*): sample k of this tick's window in slot
+    // (ring_head + k) mod (N+1), so a host that feeds the controller uploads one new sample per tick, as
+    // MPCSolver::setGradient consumes one (MPCSolver.cpp:216-239)
+    double* ref_ring;    // [2*(N+1)][B], allocated on first use
 };
 
 struct MpcTickIO {
@@ -90,6 +94,7 @@ struct MpcTickIO {
     const uint8_t* l_contact; const uint8_t* r_contact;
     const double* dcm; const double* ref; const uint8_t* reset;
     double* zmp; int32_t* status; int32_t* iters; int32_t* flags;
+    int ref_is_ring; // 0: `ref` is this tick's window [(N+1)*2][B]; 1: the window is read from MpcDev::ref_ring
 };
 
 // What OsqpEigen::Solver::solve() returns for an OSQP status (wc_osqp_settings::osqp_eigen_checks_status): the 2018
@@ -122,6 +127,8 @@ __host__ __device__ inline int mpc_smem_doubles(int N)
 }
 
 void launch_mpc_prepare(const MpcDev& d, const MpcTickIO& io, cudaStream_t s);
+// ring maintenance before K1: the newest sample [2][B] into the slot of stage N, or (window != NULL) all N+1 samples
+void launch_mpc_ref_ring_update(const MpcDev& d, const double* newest, const double* window, cudaStream_t s);
 cudaError_t launch_mpc_admm(const MpcDev& d, const MpcTickIO& io, int lanes_per_instance, cudaStream_t s);
 void launch_mpc_export_primal(const MpcDev& d, double* primal_out, cudaStream_t s);
 int mpc_admm_max_smem();

@@ -169,12 +169,14 @@ void wc_ik_destroy(wc_ik* h)
 }
 
 int32_t wc_ik_batch(const wc_ik* h) { return h ? h->d.B : 0; }
+int32_t wc_ik_dofs(const wc_ik* h) { return h ? h->d.nJ : 0; }
 int64_t wc_ik_launch_count(const wc_ik* h) { return h ? h->launches : 0; }
 
 wc_status wc_ik_set_gains_host(wc_ik* h, const double* k_pos_foot, const double* k_att_foot)
 {
     if (!h || !k_pos_foot || !k_att_foot) return WC_ERR_INVALID_ARG;
     cudaSetDevice(h->device);
+    if (h->pipe.ready && h->pipe.sync_all() != cudaSuccess) return WC_ERR_CUDA; // host ticks in flight read the gains
     const size_t bytes = (size_t)h->d.B * sizeof(double);
     if (!h->kpos && cudaMalloc(&h->kpos, bytes) != cudaSuccess) return WC_ERR_ALLOC;
     if (!h->katt && cudaMalloc(&h->katt, bytes) != cudaSuccess) return WC_ERR_ALLOC;
@@ -189,6 +191,7 @@ wc_status wc_ik_reset_solver(wc_ik* h)
     if (!h) return WC_ERR_INVALID_ARG;
     if (!h->osqp_state) return WC_OK;
     if (cudaSetDevice(h->device) != cudaSuccess) return WC_ERR_CUDA;
+    if (h->pipe.ready && h->pipe.sync_all() != cudaSuccess) return WC_ERR_CUDA; // host ticks in flight use the workspaces
     const size_t B = (size_t)h->d.B;
     // oinit and osetups: no solver yet
     if (cudaMemset(h->d.oinit, 0, B) != cudaSuccess || cudaMemset(h->d.osetups, 0, B * sizeof(int32_t)) != cudaSuccess) return WC_ERR_CUDA;
@@ -269,7 +272,8 @@ wc_status wc_ik_tick_dev(wc_ik* h, const double* q_meas, const double* q_lin, co
                          const double* com_vel_des, const double* com_meas, const double* neck_R_des,
                          double* dq, double* lf_err, double* rf_err, int32_t* qp_status, int32_t* nwsr, void* stream)
 {
-    if (!h || !q_meas || !q_lin || !base_H || !left_is_fixed || !lf_H_des || !rf_H_des || !lf_twist || !rf_twist ||
+    // base_H == NULL: the stance foot's desired transform (lf_H_des / rf_H_des by left_is_fixed)
+    if (!h || !q_meas || !q_lin || !left_is_fixed || !lf_H_des || !rf_H_des || !lf_twist || !rf_twist ||
         !com_pos_des || !com_vel_des || !com_meas || !neck_R_des)
         return WC_ERR_INVALID_ARG;
     if (cudaSetDevice(h->device) != cudaSuccess) return WC_ERR_CUDA;

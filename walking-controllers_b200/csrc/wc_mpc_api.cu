@@ -199,6 +199,7 @@ wc_status wc_mpc_set_weights_host(wc_mpc* h, const double* q_diag, const double*
 {
     if (!h || !q_diag || !r_diag) return WC_ERR_INVALID_ARG;
     cudaSetDevice(h->device);
+    if (h->pipe.ready && h->pipe.sync_all() != cudaSuccess) return WC_ERR_CUDA; // host ticks in flight read Qd / Rd
     const size_t bytes = 2 * (size_t)h->d.B * sizeof(double);
     if (cudaMemcpy(h->d.Qd, q_diag, bytes, cudaMemcpyHostToDevice) != cudaSuccess) return WC_ERR_CUDA;
     if (cudaMemcpy(h->d.Rd, r_diag, bytes, cudaMemcpyHostToDevice) != cudaSuccess) return WC_ERR_CUDA;
@@ -209,6 +210,7 @@ wc_status wc_mpc_reset(wc_mpc* h, const uint8_t* mask_host)
 {
     if (!h) return WC_ERR_INVALID_ARG;
     cudaSetDevice(h->device);
+    if (h->pipe.ready && h->pipe.sync_all() != cudaSuccess) return WC_ERR_CUDA; // host ticks in flight read / write `feet`
     const size_t B = (size_t)h->d.B;
     if (!mask_host) {
         if (cudaMemset(h->d.feet, 0, B) != cudaSuccess) return WC_ERR_CUDA;
@@ -221,18 +223,23 @@ wc_status wc_mpc_reset(wc_mpc* h, const uint8_t* mask_host)
     return WC_OK;
 }
 
-wc_status wc_mpc_tick_dev(wc_mpc* h, const double* lf_H, const double* rf_H,
-                          const uint8_t* l_contact, const uint8_t* r_contact,
-                          const double* dcm_meas, const double* ref, const uint8_t* reset,
-                          double* zmp, int32_t* osqp_status, int32_t* iters, int32_t* flags, void* stream)
+} // extern "C"
+
+// one tick on stream s; ring_newest / ring_window != NULL: the reference window lives in the device-side ring
+static wc_status mpc_tick_impl(wc_mpc* h, MpcTickIO io, const double* ring_newest, const double* ring_window, cudaStream_t s)
 {
-    if (!h || !lf_H || !rf_H || !l_contact || !r_contact || !dcm_meas || !ref) return WC_ERR_INVALID_ARG;
-    if (cudaSetDevice(h->device) != cudaSuccess) return WC_ERR_CUDA;
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
-    MpcTickIO io{lf_H, rf_H, l_contact, r_contact, dcm_meas, ref, reset, zmp, osqp_status, iters, flags};
     // gradient ring: stage k of this tick lives in slot (head + k) mod (N+1); advancing the head by
     // one per tick is MPCSolver::setGradient's block shift (MPCSolver.cpp:216-221)
     h->d.ring_head = (int)(h->tick % (int64_t)(h->d.N + 1));
+    if (ring_newest || ring_window) {
+        if (!h->d.ref_ring) {
+            if (!ring_window) return WC_ERR_INVALID_ARG; // the first ring tick needs the whole window
+            if (dalloc(h, &h->d.ref_ring, (size_t)2 * (h->d.N + 1) * (size_t)h->d.B) != cudaSuccess) return WC_ERR_ALLOC;
+        }
+        launch_mpc_ref_ring_update(h->d, ring_newest, ring_window, s);
+        h->launches += 1;
+        io.ref = nullptr; io.ref_is_ring = 1;
+    }
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     if (h->profiling) {
         for (int k = 0; k < 5; k++) { cudaEventCreate(&ev[k]); h->ev.push_back(ev[k]); }
@@ -258,6 +265,31 @@ wc_status wc_mpc_tick_dev(wc_mpc* h, const double* lf_H, const double* rf_H,
         return WC_ERR_CUDA;
     }
     return WC_OK;
+}
+
+extern "C" {
+
+wc_status wc_mpc_tick_dev(wc_mpc* h, const double* lf_H, const double* rf_H,
+                          const uint8_t* l_contact, const uint8_t* r_contact,
+                          const double* dcm_meas, const double* ref, const uint8_t* reset,
+                          double* zmp, int32_t* osqp_status, int32_t* iters, int32_t* flags, void* stream)
+{
+    if (!h || !lf_H || !rf_H || !l_contact || !r_contact || !dcm_meas || !ref) return WC_ERR_INVALID_ARG;
+    if (cudaSetDevice(h->device) != cudaSuccess) return WC_ERR_CUDA;
+    MpcTickIO io{lf_H, rf_H, l_contact, r_contact, dcm_meas, ref, reset, zmp, osqp_status, iters, flags, 0};
+    return mpc_tick_impl(h, io, nullptr, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+wc_status wc_mpc_tick_ring_dev(wc_mpc* h, const double* lf_H, const double* rf_H,
+                               const uint8_t* l_contact, const uint8_t* r_contact,
+                               const double* dcm_meas, const double* ref_newest, const double* ref_window,
+                               const uint8_t* reset, double* zmp, int32_t* osqp_status, int32_t* iters, int32_t* flags,
+                               void* stream)
+{
+    if (!h || !lf_H || !rf_H || !l_contact || !r_contact || !dcm_meas || (!ref_newest && !ref_window)) return WC_ERR_INVALID_ARG;
+    if (cudaSetDevice(h->device) != cudaSuccess) return WC_ERR_CUDA;
+    MpcTickIO io{lf_H, rf_H, l_contact, r_contact, dcm_meas, nullptr, reset, zmp, osqp_status, iters, flags, 1};
+    return mpc_tick_impl(h, io, ref_newest, ref_window, static_cast<cudaStream_t>(stream));
 }
 
 wc_status wc_mpc_tick_host_async(wc_mpc* h, const double* lf_H, const double* rf_H,
@@ -308,6 +340,81 @@ wc_status wc_mpc_tick_host_async(wc_mpc* h, const double* lf_H, const double* rf
     if (e == cudaSuccess) e = h->pipe.end(slot);
     if (e != cudaSuccess) {
         std::fprintf(stderr, "[wc_mpc_tick_host_async] CUDA error: %s\n", cudaGetErrorString(e));
+        return WC_ERR_CUDA;
+    }
+    return WC_OK;
+}
+
+// Fused host tick of both blocks (wc_capi.h): one packed upload, the MPC kernels on the pipe's kernel stream and the
+// FK + QP-IK kernels on its second one (the two blocks of a tick are independent given the host's inputs), one packed
+// download.  The feet transforms are uploaded once for both blocks, the stance-foot transform is selected on the device
+// when base_H is NULL, and the DCM reference travels as ONE new sample per tick (device-side ring).
+wc_status wc_tick_host_async(wc_mpc* h, wc_ik* ik, const wc_tick_host_in* in, const wc_tick_host_out* out)
+{
+    if (!h || !ik || !in || !out) return WC_ERR_INVALID_ARG;
+    if (!in->lf_H || !in->rf_H || !in->l_contact || !in->r_contact || !in->left_is_fixed || !in->dcm_meas ||
+        (!in->ref_newest && !in->ref_window) || !in->q_meas || !in->q_lin || !in->lf_twist || !in->rf_twist ||
+        !in->com_pos_des || !in->com_vel_des || !in->com_meas || !in->neck_R_des)
+        return WC_ERR_INVALID_ARG;
+    if (wc_ik_batch(ik) != h->d.B) return WC_ERR_INVALID_ARG;
+    if (cudaSetDevice(h->device) != cudaSuccess) return WC_ERR_CUDA;
+    const size_t B = (size_t)h->d.B, nJ = (size_t)wc_ik_dofs(ik);
+    const int N = h->d.N;
+    // packed input block: doubles first (rows per instance), then the byte flags
+    enum { I_LF, I_RF, I_DCM, I_REFN, I_QM, I_QL, I_LT, I_RT, I_CP, I_CV, I_CM, I_NR, I_BASE, I_REFW, I_ND };
+    const size_t rows[I_ND] = {12, 12, 2, 2, nJ, nJ, 6, 6, 3, 3, 3, 9, 12, (size_t)2 * (N + 1)};
+    const double* src[I_ND] = {in->lf_H, in->rf_H, in->dcm_meas, in->ref_newest, in->q_meas, in->q_lin, in->lf_twist, in->rf_twist,
+                               in->com_pos_des, in->com_vel_des, in->com_meas, in->neck_R_des, in->base_H, in->ref_window};
+    size_t off[I_ND + 1]; off[0] = 0;
+    for (int k = 0; k < I_ND; k++) off[k + 1] = off[k] + rows[k] * B * 8;
+    const size_t o_lc = off[I_ND], o_rc = o_lc + align_up(B, 8), o_lif = o_rc + align_up(B, 8), o_rs = o_lif + align_up(B, 8);
+    const size_t in_bytes = o_rs + align_up(B, 8);
+    const size_t p_zmp = 0, p_dq = p_zmp + 2 * B * 8, p_le = p_dq + nJ * B * 8, p_re = p_le + 6 * B * 8;
+    const size_t p_st = p_re + 6 * B * 8, p_it = p_st + align_up(B * 4, 8), p_fl = p_it + align_up(B * 4, 8);
+    const size_t p_qs = p_fl + align_up(B * 4, 8), p_nw = p_qs + align_up(B * 4, 8), out_bytes = p_nw + align_up(B * 4, 8);
+    if (h->pipe.init(in_bytes, out_bytes) != cudaSuccess) return WC_ERR_ALLOC;
+    cudaError_t ce = cudaSuccess;
+    const int slot = h->pipe.begin(&ce);
+    if (ce != cudaSuccess) return WC_ERR_CUDA;
+    cudaStream_t s = h->pipe.up;
+    char* di = static_cast<char*>(h->pipe.dev_in[slot]);
+    char* dout = static_cast<char*>(h->pipe.dev_out[slot]);
+    for (int k = 0; k < I_ND; k++)
+        if (src[k] && ce == cudaSuccess) ce = cudaMemcpyAsync(di + off[k], src[k], rows[k] * B * 8, cudaMemcpyHostToDevice, s);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(di + o_lc, in->l_contact, B, cudaMemcpyHostToDevice, s);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(di + o_rc, in->r_contact, B, cudaMemcpyHostToDevice, s);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(di + o_lif, in->left_is_fixed, B, cudaMemcpyHostToDevice, s);
+    if (ce == cudaSuccess) ce = in->reset ? cudaMemcpyAsync(di + o_rs, in->reset, B, cudaMemcpyHostToDevice, s)
+                                          : cudaMemsetAsync(di + o_rs, 0, B, s);
+    if (ce == cudaSuccess) ce = h->pipe.before_run(slot);
+    if (ce != cudaSuccess) return WC_ERR_CUDA;
+    auto dp = [&](int k) { return (const double*)(di + off[k]); };
+    // fork: the IK kernels on the second kernel stream, beside the MPC kernels
+    if (cudaEventRecord(h->pipe.fork, h->pipe.run) != cudaSuccess || cudaStreamWaitEvent(h->pipe.run2, h->pipe.fork, 0) != cudaSuccess)
+        return WC_ERR_CUDA;
+    MpcTickIO io{dp(I_LF), dp(I_RF), (const uint8_t*)(di + o_lc), (const uint8_t*)(di + o_rc), dp(I_DCM), nullptr,
+                 (const uint8_t*)(di + o_rs), (double*)(dout + p_zmp), (int32_t*)(dout + p_st), (int32_t*)(dout + p_it),
+                 (int32_t*)(dout + p_fl), 1};
+    wc_status rc = mpc_tick_impl(h, io, in->ref_window ? nullptr : dp(I_REFN), in->ref_window ? dp(I_REFW) : nullptr, h->pipe.run);
+    if (rc != WC_OK) return rc;
+    const double* base = in->base_H ? dp(I_BASE) : nullptr; // NULL: the stance foot's transform, selected in the kernel
+    rc = wc_ik_tick_dev(ik, dp(I_QM), dp(I_QL), base, (const uint8_t*)(di + o_lif), dp(I_LF), dp(I_RF), dp(I_LT), dp(I_RT),
+                        dp(I_CP), dp(I_CV), dp(I_CM), dp(I_NR), (double*)(dout + p_dq), (double*)(dout + p_le),
+                        (double*)(dout + p_re), (int32_t*)(dout + p_qs), (int32_t*)(dout + p_nw), h->pipe.run2);
+    if (rc != WC_OK) return rc;
+    // join
+    if (cudaEventRecord(h->pipe.join, h->pipe.run2) != cudaSuccess || cudaStreamWaitEvent(h->pipe.run, h->pipe.join, 0) != cudaSuccess)
+        return WC_ERR_CUDA;
+    cudaError_t e = h->pipe.before_down(slot);
+    s = h->pipe.down;
+#define D2H(dst, o, bytes) do { if ((dst) && e == cudaSuccess) e = cudaMemcpyAsync((dst), dout + (o), (bytes), cudaMemcpyDeviceToHost, s); } while (0)
+    D2H(out->zmp, p_zmp, 2 * B * 8); D2H(out->osqp_status, p_st, B * 4); D2H(out->iters, p_it, B * 4); D2H(out->flags, p_fl, B * 4);
+    D2H(out->dq, p_dq, nJ * B * 8); D2H(out->lf_err, p_le, 6 * B * 8); D2H(out->rf_err, p_re, 6 * B * 8);
+    D2H(out->qp_status, p_qs, B * 4); D2H(out->nwsr, p_nw, B * 4);
+#undef D2H
+    if (e == cudaSuccess) e = h->pipe.end(slot);
+    if (e != cudaSuccess) {
+        std::fprintf(stderr, "[wc_tick_host_async] CUDA error: %s\n", cudaGetErrorString(e));
         return WC_ERR_CUDA;
     }
     return WC_OK;
