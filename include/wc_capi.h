@@ -220,6 +220,10 @@ wc_status wc_mpc_kernel_times_ms(wc_mpc* h, double* prepare_ms, double* admm_ms,
 wc_status wc_mpc_kernel_times_detail_ms(wc_mpc* h, double* setup_ms, double* phase1_ms, double* phase2_ms);
 /* ADMM kernel family of the handle: 1 = chain-per-thread (mpc_chain.cu, short horizons), 0 = cooperative. */
 int32_t wc_mpc_path(const wc_mpc* h);
+/* Optional device-side tick source: with tick_dev != NULL the slot of stage 0 in the gradient / reference rings is
+ * (*tick_dev) mod (N+1), read on the device, instead of the handle's own host-side tick count (NULL switches back).
+ * The caller must pass reset = 1 for every instance on the first tick after a switch (the rings are re-filled). */
+wc_status wc_mpc_set_tick_source_dev(wc_mpc* h, const int32_t* tick_dev);
 
 /* ---------------------------------------------------------------------------------- */
 /* Kinematic model table (replaces the iDynTree::Model loaded from model.urdf,          */
@@ -447,18 +451,24 @@ wc_status wc_tick_host_async(wc_mpc* mpc, wc_ik* ik, const wc_tick_host_in* in, 
 /* StableDCMModel (StableDCMModel.cpp:58-90), WalkingZMPController::evaluateControl      */
 /* (WalkingZMPController.cpp:126-172) and the joint-velocity integration of updateModule */
 /* (WalkingModule.cpp:741-744); iCub::ctrl::Integrator restated as the Tustin rule.      */
-/* Gain scheduling (minJerkTrajGen) is the caller's: gains are constants or per-instance */
-/* input arrays.                                                                         */
+/* Gain scheduling (WalkingZMPController::setPhase, :107-126) is wc_glue_set_phase_dev;   */
+/* iCub::ctrl::minJerkTrajGen (external, ctrlLib) is restated as the Tustin              */
+/* discretisation of its third-order filter.                                             */
 /* ---------------------------------------------------------------------------------- */
 typedef struct wc_glue wc_glue;
 typedef struct wc_glue_config {
     int32_t n_dofs;        /* actuated joints integrated by wc_glue_integrate_joints_dev */
-    int32_t reserved;
+    int32_t use_gain_scheduling; /* useGainScheduling (zmpControllerParams.ini:2; on in the shipped iCubGazeboV2_5 /
+                                    icubGazeboSim configurations): the gains start at the stance values and follow
+                                    wc_glue_set_phase_dev; off: the walking values, constant (:86-90) */
     double sampling_time;  /* integrators' Ts */
     double com_height;     /* omega = sqrt(gravity / com_height) (StableDCMModel.cpp:31-37) */
     double gravity;
     double k_zmp;          /* kZMP_walking (zmpControllerParams.ini) */
     double k_com;          /* kCoM_walking */
+    double smoothing_time; /* smoothingTime: T of the two minJerkTrajGen smoothers (:63-81) */
+    double k_zmp_stance;   /* kZMP_stance */
+    double k_com_stance;   /* kCoM_stance */
 } wc_glue_config;
 void wc_glue_default_config(wc_glue_config* cfg); /* iCubGazeboV2_5 values */
 wc_status wc_glue_create(const wc_glue_config* cfg, int32_t B, int32_t device, wc_glue** out);
@@ -474,6 +484,15 @@ wc_status wc_glue_com_reference_dev(wc_glue* h, const double* dcm_des, const dou
                                     const double* com_meas, const double* com_z_des, const double* com_z_vel_des,
                                     const double* k_zmp, const double* k_com, double* com_pos_des, double* com_vel_des,
                                     void* stream);
+/* WalkingZMPController::setPhase (WalkingZMPController.cpp:107-126), called once per tick before
+ * wc_glue_com_reference_dev as updateModule does (WalkingModule.cpp:657-661): the stance flag is stance[i] if given, else
+ * |dcm_vel_des| < 0.001 (the caller's threshold, WalkingModule.cpp:659-660) from dcm_vel_des [2*B]; both smoothers advance
+ * one step towards the stance / walking gains and the per-instance (kZMP, kCoM) they output are what
+ * wc_glue_com_reference_dev uses when its k_zmp / k_com arguments are NULL.  A no-op unless use_gain_scheduling.
+ * minJerkTrajGen(1, Ts, T) restated: F(s) = -a / (s^3 - c s^2 - b s - a) with a = -150.765868956161 / T^3,
+ * b = -84.9812819469538 / T^2, c = -15.9669610709384 / T (90 % of the step at t = T), Tustin-discretised, initialised at
+ * steady state (init(y0): all past inputs and outputs y0). */
+wc_status wc_glue_set_phase_dev(wc_glue* h, const double* dcm_vel_des, const uint8_t* stance, void* stream);
 /* m_qDesired = integrator(m_dqDesired): dq [nJ*B] -> q_des [nJ*B] (may be NULL: state only). */
 wc_status wc_glue_integrate_joints_dev(wc_glue* h, const double* dq, double* q_des, void* stream);
 int64_t wc_glue_launch_count(const wc_glue* h);
@@ -571,6 +590,53 @@ wc_status wc_traj_generate_host(wc_traj* h, const int32_t* phase, const double* 
                                 double* lf_H, double* rf_H, double* lf_twist, double* rf_twist, uint8_t* l_contact,
                                 uint8_t* r_contact, uint8_t* left_is_fixed, double* com_height, double* com_height_vel);
 int64_t wc_traj_launch_count(const wc_traj* h);
+/* Optional device-side tick source: the int32 at tick_dev is ADDED, on the device, to every `tick` / `first_sample`
+ * argument of the calls above (NULL switches it off).  With it a tick's launch sequence does not depend on the tick index
+ * and can be replayed from a CUDA graph (wc_loop_*). */
+wc_status wc_traj_set_tick_source_dev(wc_traj* h, const int32_t* tick_dev);
+
+/* ---------------------------------------------------------------------------------- */
+/* The closed-loop control tick as ONE call: producer -> measured   */
+/* CoM (FK) -> DCM-MPC -> ZMP-CoM controller with gain scheduling -> FK + QP-IK -> joint  */
+/* integrator, in the order and with the data dependence of WalkingModule::updateModule   */
+/* (WalkingModule.cpp:541-745): the IK of tick t consumes the MPC output of tick t.  The  */
+/* plant is synthetic: perfect joint tracking (q_meas = q_des), measured DCM = reference  */
+/* + N(0, sigma^2) (+ an impulsive push per instance, BASELINE configs[3]), measured ZMP  */
+/* = desired ZMP + offset.  The handle BORROWS the four block handles (same B, same       */
+/* device; they must outlive it and must not be ticked directly while it exists) and      */
+/* installs a device-side tick counter in the MPC and the producer, so that a tick's      */
+/* launch sequence is constant and is replayed from a CUDA graph (use_graph).             */
+/* ---------------------------------------------------------------------------------- */
+typedef struct wc_loop wc_loop;
+typedef struct wc_loop_config {
+    double dcm_noise_sigma;  /* std of the Gaussian noise on the measured DCM (0.002 m) */
+    uint64_t noise_seed;     /* Philox key of that noise */
+    double zmp_meas_offset;  /* measured ZMP = desired ZMP + offset on both axes */
+    int32_t use_graph;       /* 1: ticks after the first are replays of one captured CUDA graph */
+    int32_t reserved;
+} wc_loop_config;
+void wc_loop_default_config(wc_loop_config* cfg);
+wc_status wc_loop_create(wc_mpc* mpc, wc_ik* ik, wc_glue* glue, wc_traj* traj, const wc_loop_config* cfg, int32_t device,
+                         wc_loop** out);
+void wc_loop_destroy(wc_loop* h);
+/* Start of a rollout: tick counter 0, MPC reset (WalkingController::reset), integrators at the posture q0 [nJ*B] (device
+ * pointer) and at its CoM about the stance foot of tick 0 (WalkingModule.cpp:470-471).  The gait must be set on `traj`. */
+wc_status wc_loop_reset_dev(wc_loop* h, const double* q0, void* stream);
+/* Impulsive DCM disturbance (BASELINE configs[3]): at tick push_tick[i] (< 0: never) the measured DCM of instance i is
+ * displaced by push_dxy [2*B].  Device pointers, copied. */
+wc_status wc_loop_set_push_dev(wc_loop* h, const int32_t* push_tick, const double* push_dxy, void* stream);
+/* n_ticks closed-loop ticks, asynchronous on `stream`. */
+wc_status wc_loop_run_dev(wc_loop* h, int32_t n_ticks, void* stream);
+int64_t wc_loop_tick_count(const wc_loop* h);
+/* Device pointers to the signals of the LAST tick run (valid until wc_loop_destroy; read them on the rollout's stream):
+ * layouts as the outputs / inputs of the block entry points. */
+typedef struct wc_loop_view {
+    const double *zmp, *dq, *q_des, *com_pos_des, *com_vel_des, *com_meas, *dcm_meas, *lf_err, *rf_err; /* [2|nJ|nJ|3|3|3|2|6|6][B] */
+    const double *lf_H, *rf_H, *ref_pos;            /* producer outputs of the tick: [12*B], [12*B], [(N+1)*2*B] */
+    const int32_t *osqp_status, *iters, *flags;     /* MPC outputs [B] */
+    const int32_t *qp_status, *nwsr;                /* QP-IK outputs [B] */
+} wc_loop_view;
+wc_status wc_loop_view_get(wc_loop* h, wc_loop_view* view);
 
 /* Measured FP64 FMA throughput of the device (register-resident FMA chains, all SMs), in GFLOP/s:
  * the denominator of the FP64 roofline fraction that bench.py reports next to the HBM one

@@ -4,6 +4,10 @@
  *   StableDCMModel::integrateModel          modules/Walking_module/src/StableDCMModel.cpp:63-90
  *   WalkingZMPController::evaluateControl   modules/Walking_module/src/WalkingZMPController.cpp:144-172
  *   joint integration                       modules/Walking_module/src/WalkingModule.cpp:741-744
+ *   WalkingZMPController::setPhase          modules/Walking_module/src/WalkingZMPController.cpp:107-126 (gain scheduling;
+ *     iCub::ctrl::minJerkTrajGen is external (iCub ctrlLib, not vendored): restated as the Tustin discretisation of its
+ *     third-order filter F(s) = -a / (s^3 - c s^2 - b s - a), a = -150.765868956161 / T^3, b = -84.9812819469538 / T^2,
+ *     c = -15.9669610709384 / T, run as ctrlLib's Filter does (direct form, init(y0) = steady state at y0))
  * iCub::ctrl::Integrator (external, iCub ctrlLib, not vendored) is restated from its published rule: Tustin
  * integration y_k = y_{k-1} + Ts/2 (x_k + x_{k-1}), reset(y0) sets y = y0 and x_old = 0.
  * and (rank 4):
@@ -29,6 +33,8 @@ struct wco_glue {
     double omega;
     double *lipm_c, *lipm_v, *zc_y, *zc_v, *q_y, *q_v;
     double* cf; /* [12][B] CoM filters of WalkingFK: position y, u_old, velocity y, u_old */
+    double* gs; /* [14][B] smoothers of kZMP and kCoM (y1..y3, u1..u3 each), current kZMP, kCoM */
+    double fb[4], fa[4];
 };
 
 wco_glue* wco_glue_create(const wc_glue_config* cfg, int B)
@@ -41,13 +47,27 @@ wco_glue* wco_glue_create(const wc_glue_config* cfg, int B)
     g->q_y = (double*)calloc(nq, sizeof(double)); g->q_v = (double*)calloc(nq, sizeof(double));
     g->cf = (double*)calloc(12 * (size_t)B, sizeof(double));
     for (int i = 0; i < B; i++) { g->cf[2 * (size_t)B + i] = cfg->com_height; g->cf[5 * (size_t)B + i] = cfg->com_height; }
+    g->gs = (double*)calloc(14 * (size_t)B, sizeof(double));
+    if (cfg->use_gain_scheduling) {
+        /* minJerkTrajGen(1, Ts, T)::computeCoeffs + init(k*_stance) (WalkingZMPController.cpp:63-83) */
+        const double T = cfg->smoothing_time, k = 2.0 / cfg->sampling_time;
+        const double a = -150.765868956161 / (T * T * T), b = -84.9812819469538 / (T * T), c = -15.9669610709384 / T;
+        const double k2 = k * k, k3 = k2 * k;
+        g->fa[0] = k3 - c * k2 - b * k - a;  g->fa[1] = -3.0 * k3 + c * k2 - b * k - 3.0 * a;
+        g->fa[2] = 3.0 * k3 + c * k2 + b * k - 3.0 * a;  g->fa[3] = -k3 - c * k2 + b * k - a;
+        g->fb[0] = -a; g->fb[1] = -3.0 * a; g->fb[2] = -3.0 * a; g->fb[3] = -a;
+        for (int i = 0; i < B; i++) {
+            for (int r = 0; r < 6; r++) { g->gs[(size_t)r * B + i] = cfg->k_zmp_stance; g->gs[(size_t)(6 + r) * B + i] = cfg->k_com_stance; }
+            g->gs[(size_t)12 * B + i] = cfg->k_zmp_stance; g->gs[(size_t)13 * B + i] = cfg->k_com_stance;
+        }
+    }
     return g;
 }
 
 void wco_glue_free(wco_glue* g)
 {
     if (!g) return;
-    free(g->lipm_c); free(g->lipm_v); free(g->zc_y); free(g->zc_v); free(g->q_y); free(g->q_v); free(g->cf); free(g);
+    free(g->lipm_c); free(g->lipm_v); free(g->zc_y); free(g->zc_v); free(g->q_y); free(g->q_v); free(g->cf); free(g->gs); free(g);
 }
 
 /* Integrator::reset for the three integrators (WalkingModule.cpp:470-471) */
@@ -71,12 +91,38 @@ static double tustin(double* y, double* x_old, double x, double ts)
     return *y;
 }
 
+/* WalkingZMPController::setPhase (:107-126): stance[i], or |dcm_vel_des| < 0.001 (WalkingModule.cpp:659-660) */
+void wco_glue_set_phase(wco_glue* g, const double* dcm_vel_des, const unsigned char* stance)
+{
+    const size_t B = (size_t)g->B;
+    if (!g->cfg.use_gain_scheduling) return;
+    for (size_t i = 0; i < B; i++) {
+        int st;
+        if (stance) st = stance[i] != 0;
+        else st = sqrt(dcm_vel_des[i] * dcm_vel_des[i] + dcm_vel_des[B + i] * dcm_vel_des[B + i]) < 0.001;
+        for (int q = 0; q < 2; q++) {
+            const double u = q == 0 ? (st ? g->cfg.k_zmp_stance : g->cfg.k_zmp) : (st ? g->cfg.k_com_stance : g->cfg.k_com);
+            double* s = g->gs + (size_t)(6 * q) * B + i;
+            /* ctrlLib Filter::filt: y = b0 u; y += b_k u_old[k-1]; y -= a_k y_old[k-1]; y = (1 / a0) y */
+            double y = g->fb[0] * u;
+            y += g->fb[1] * s[3 * B]; y += g->fb[2] * s[4 * B]; y += g->fb[3] * s[5 * B];
+            y -= g->fa[1] * s[0]; y -= g->fa[2] * s[B]; y -= g->fa[3] * s[2 * B];
+            y = (1.0 / g->fa[0]) * y;
+            s[2 * B] = s[B]; s[B] = s[0]; s[0] = y;
+            s[5 * B] = s[4 * B]; s[4 * B] = s[3 * B]; s[3 * B] = u;
+            g->gs[(size_t)(12 + q) * B + i] = y;
+        }
+    }
+}
+
 void wco_glue_com_reference(wco_glue* g, const double* dcm_des, const double* zmp_des, const double* zmp_meas,
                             const double* com_meas, const double* com_z_des, const double* com_z_vel_des,
                             const double* k_zmp, const double* k_com, double* com_pos_des, double* com_vel_des)
 {
     const size_t B = (size_t)g->B;
     const double ts = g->cfg.sampling_time;
+    if (!k_zmp && g->cfg.use_gain_scheduling) k_zmp = g->gs + 12 * B;
+    if (!k_com && g->cfg.use_gain_scheduling) k_com = g->gs + 13 * B;
     for (size_t i = 0; i < B; i++) {
         const double kz = k_zmp ? k_zmp[i] : g->cfg.k_zmp, kc = k_com ? k_com[i] : g->cfg.k_com;
         for (int a = 0; a < 2; a++) {

@@ -333,8 +333,9 @@ def ik_batch_tick(cfg, model, inp, kpos=None, katt=None, threads=1):
 
 # ---- closed-loop glue (StableDCMModel + WalkingZMPController + joint integrator) -------------------------------
 class GlueConfig(C.Structure):
-    _fields_ = [("n_dofs", C.c_int32), ("reserved", C.c_int32), ("sampling_time", C.c_double),
-                ("com_height", C.c_double), ("gravity", C.c_double), ("k_zmp", C.c_double), ("k_com", C.c_double)]
+    _fields_ = [("n_dofs", C.c_int32), ("use_gain_scheduling", C.c_int32), ("sampling_time", C.c_double),
+                ("com_height", C.c_double), ("gravity", C.c_double), ("k_zmp", C.c_double), ("k_com", C.c_double),
+                ("smoothing_time", C.c_double), ("k_zmp_stance", C.c_double), ("k_com_stance", C.c_double)]
 
 
 def glue_default_config():
@@ -370,6 +371,13 @@ class GlueBatch:
         a = _f64(com_xy) if com_xy is not None else None
         b = _f64(q) if q is not None else None
         self.L.wco_glue_reset(self.h, _dp(a), _dp(b))
+
+    def set_phase(self, dcm_vel_des=None, stance=None):
+        """WalkingZMPController::setPhase: stance flags [B], or the |dcm_vel_des| < 0.001 rule of updateModule"""
+        self.L.wco_glue_set_phase.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint8)]
+        v = None if dcm_vel_des is None else _f64(dcm_vel_des)
+        s = None if stance is None else np.ascontiguousarray(stance, dtype=np.uint8)
+        self.L.wco_glue_set_phase(self.h, _dp(v), None if s is None else s.ctypes.data_as(C.POINTER(C.c_uint8)))
 
     def com_reference(self, dcm_des, zmp_des, zmp_meas, com_meas, com_z_des=None, com_z_vel_des=None, k_zmp=None, k_com=None):
         arrs = [None if x is None else _f64(x) for x in (dcm_des, zmp_des, zmp_meas, com_meas, com_z_des, com_z_vel_des, k_zmp, k_com)]
@@ -567,3 +575,61 @@ class IkOsqpBatch:
                                      _dp(a["com_pos_des"]), _dp(a["com_vel_des"]), _dp(a["com_meas"]), _dp(a["neck_R_des"]),
                                      _dp(dq), _dp(le), _dp(re), _ip(st), _ip(it), _ip(fl), _ip(su))
         return dict(dq=dq, lf_err=le, rf_err=re, status=st, iters=it, flags=fl, setups=su)
+
+
+class ClosedLoop:
+    """CHECKER of walking-controllers_b200.LoopBatch: the same closed-loop tick (WalkingModule::updateModule order,
+    WalkingModule.cpp:541-745) stitched from the CPU restatements -- producer twin, kin_ref FK, mpc_ref, glue_ref (with the
+    gain schedule), qpik_ref -- with the same synthetic plant (q_meas = q_des, measured DCM = reference + noise (+ push),
+    measured ZMP = desired + offset)."""
+
+    def __init__(self, mpc_cfg, ik_cfg, model, glue_cfg, traj, B, sigma=0.002, seed=0x5EED, zmp_offset=0.001, threads=1):
+        self.mpc = MpcBatch(mpc_cfg, B)
+        self.glue = GlueBatch(glue_cfg, B)
+        self.ik_cfg, self.model, self.traj, self.B, self.N = ik_cfg, model, traj, B, mpc_cfg.horizon
+        self.sigma, self.seed, self.off, self.threads = sigma, seed, zmp_offset, threads
+        self.t = 0
+        self.push_tick = np.full(B, -1, np.int32); self.push_dxy = np.zeros((2, B))
+
+    @staticmethod
+    def _pre(f):
+        lif = f["left_is_fixed"]
+        base = np.where(lif[None, :] != 0, f["lf_H"], f["rf_H"])
+        yl = np.arctan2(f["lf_H"][4], f["lf_H"][0]); yr = np.arctan2(f["rf_H"][4], f["rf_H"][0])
+        my = np.arctan2(np.sin(yl) + np.sin(yr), np.cos(yl) + np.cos(yr))
+        c, s = np.cos(my), np.sin(my); z, o = np.zeros_like(c), np.ones_like(c)
+        neck = np.stack([c, -s, z, s, c, z, z, z, o])
+        return np.ascontiguousarray(base), neck
+
+    def reset(self, q0):
+        self.q = np.array(q0, dtype=np.float64, copy=True)
+        self.mpc.reset()
+        f = self.traj.feet(0)
+        base, _ = self._pre(f)
+        com = fk_batch(self.model, self.q, base, f["left_is_fixed"], jacobians=False)["com"]
+        self.glue.reset(com[:2], self.q)
+        self.t = 0
+
+    def set_push(self, push_tick, push_dxy):
+        self.push_tick = np.asarray(push_tick, np.int32).copy(); self.push_dxy = np.asarray(push_dxy, np.float64).copy()
+
+    def tick(self):
+        t, N = self.t, self.N
+        f = self.traj.feet(t)
+        ref, vel = self.traj.dcm(t, N + 1)
+        dcm = self.traj.measured_dcm(t, self.sigma, self.seed)
+        hit = self.push_tick == t
+        dcm[:, hit] += self.push_dxy[:, hit]
+        base, neck = self._pre(f)
+        com = fk_batch(self.model, self.q, base, f["left_is_fixed"], jacobians=False)["com"]
+        z, st, it, fl = self.mpc.tick(f["lf_H"], f["rf_H"], f["l_contact"], f["r_contact"], dcm, ref, threads=self.threads)
+        self.glue.set_phase(dcm_vel_des=vel[0:2])
+        co = self.glue.com_reference(ref[0:2], z, z + self.off, com, f["com_height"], f["com_height_vel"])
+        inp = dict(q_meas=self.q, q_lin=self.q, base_H=base, left_is_fixed=f["left_is_fixed"], lf_H_des=f["lf_H"], rf_H_des=f["rf_H"],
+                   lf_twist=f["lf_twist"], rf_twist=f["rf_twist"], com_pos_des=co["com_pos_des"], com_vel_des=co["com_vel_des"],
+                   com_meas=com, neck_R_des=neck)
+        oo = ik_batch_tick(self.ik_cfg, self.model, inp, threads=self.threads)
+        self.q = self.glue.integrate_joints(oo["dq"])
+        self.t += 1
+        return dict(zmp=z, osqp_status=st, iters=it, flags=fl, dq=oo["dq"], qp_status=oo["status"], nwsr=oo["nwsr"], q_des=self.q,
+                    com_pos_des=co["com_pos_des"], com_vel_des=co["com_vel_des"], com_meas=com, dcm_meas=dcm)

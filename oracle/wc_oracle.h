@@ -93,6 +93,7 @@ typedef struct wco_glue wco_glue;
 wco_glue* wco_glue_create(const wc_glue_config* cfg, int B);
 void wco_glue_free(wco_glue* g);
 void wco_glue_reset(wco_glue* g, const double* com_xy, const double* q);
+void wco_glue_set_phase(wco_glue* g, const double* dcm_vel_des, const unsigned char* stance);
 void wco_glue_com_reference(wco_glue* g, const double* dcm_des, const double* zmp_des, const double* zmp_meas,
                             const double* com_meas, const double* com_z_des, const double* com_z_vel_des,
                             const double* k_zmp, const double* k_com, double* com_pos_des, double* com_vel_des);

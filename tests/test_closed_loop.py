@@ -1,0 +1,136 @@
+"""The closed-loop control tick as one call (wc_loop_*): producer -> measured CoM -> DCM-MPC -> ZMP-CoM
+law with gain scheduling -> FK + QP-IK -> joint integrator, device resident and CUDA-graph replayed, against the same loop
+stitched from the CPU restatements (oracle.ClosedLoop), with the data dependence of WalkingModule::updateModule
+(WalkingModule.cpp:541-745: the IK of tick t consumes the MPC output of tick t) and the SHIPPED joint velocity limits, so
+that the QP-IK's active set is exercised in closed loop."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+
+def _gait(B, seed):
+    rng = np.random.default_rng(seed)
+    return dict(step_len=rng.uniform(0.05, 0.20, B), phase=rng.integers(0, 90, B).astype(np.int32),
+                dtheta=np.deg2rad(rng.uniform(-10, 10, B)), theta0=rng.uniform(-0.5, 0.5, B),
+                first_left=rng.integers(0, 2, B).astype(np.uint8))
+
+
+def _make(wc, oracle, syn, cuda_device, B, T, N, seed, use_graph, push=None, gain_sweep=False, vmax=None, prepared=True):
+    """both sides of the loop.  prepared: the posture of syn.prepare_posture (CoM at the start of the DCM reference, above the
+    feet of tick 0) at the model's own LIPM height; vmax: joint velocity limit (default: the closed-loop workload's)"""
+    vmax = syn.CL_VMAX if vmax is None else vmax
+    h = syn.CL_COM_HEIGHT
+    par = _gait(B, seed)
+    d = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(cuda_device)
+    tco, tcg = oracle.traj_default_config(T, N), wc.traj_default_config(T, N)
+    mco, mcg = oracle.mpc_default_config(N), wc.mpc_default_config(N)
+    gco, gcg = oracle.glue_default_config(), wc.glue_default_config()
+    icfg_o, icfg_g, icfg_open = oracle.ik_default_config(), wc.ik_default_config(), oracle.ik_default_config()
+    for c in (tco, tcg, mco, mcg, gco, gcg):
+        c.com_height = h
+    for j in range(23):
+        icfg_o.min_vel[j], icfg_o.max_vel[j] = -vmax, vmax
+        icfg_g.min_vel[j], icfg_g.max_vel[j] = -vmax, vmax
+        icfg_open.min_vel[j], icfg_open.max_vel[j] = -50.0, 50.0
+    model_o = oracle.model_icub_like()
+    tw = oracle.TrajBatch(tco, B); tw.set_gait(**par)
+    tg = wc.TrajBatch(tcg, B); tg.set_gait(**{k: d(v) for k, v in par.items()})
+    mg = wc.MpcBatch(mcg, B)
+    ig = wc.IkBatch(icfg_g, wc.model_icub_like(), B)
+    gg = wc.GlueBatch(gcg, B)
+    cfg = wc.loop_default_config(); cfg.use_graph = 1 if use_graph else 0
+    lg = wc.LoopBatch(mg, ig, gg, tg, cfg)
+    lo = oracle.ClosedLoop(mco, icfg_o, model_o, gco, tw, B, sigma=cfg.dcm_noise_sigma, seed=cfg.noise_seed,
+                           zmp_offset=cfg.zmp_meas_offset, threads=8)
+    rng = np.random.default_rng(seed + 1)
+    qreg = np.array(icfg_o.joint_reg_rad[:23])
+    if prepared:
+        T_ = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+        fk = lambda q, b, l: {k: T_(v) for k, v in oracle.fk_batch(model_o, q.numpy(), b.numpy(), l.numpy(), jacobians=False).items()}
+        ikt = lambda inp: {k: T_(v) for k, v in oracle.ik_batch_tick(icfg_open, model_o, {k: v.numpy() for k, v in inp.items()}, threads=8).items()}
+        ref0, _ = tw.dcm(0, 1)
+        tgt = T_(np.concatenate([ref0[0:2], np.full((1, B), h)]))
+        q0 = syn.prepare_posture(fk, ikt, torch.from_numpy(qreg), {k: T_(v) for k, v in tw.feet(0).items()}, tgt).numpy()
+    else:
+        q0 = np.tile(qreg[:, None], (1, B)) + 0.01 * rng.normal(size=(23, B))
+    if gain_sweep:  # BASELINE configs[3]: Q, R, k_posFoot, k_attFoot per instance
+        q = 7500.0 * rng.choice([0.1, 0.3, 1, 3, 10], size=B); r = 9e6 * rng.choice([0.1, 1, 10], size=B)
+        kp = rng.choice([2.5, 4.0, 7.0], size=B); ka = rng.choice([2.0, 5.0], size=B)
+        qd, rd = np.stack([q, q]), np.stack([r, r])
+        lo.mpc.set_weights(qd, rd); mg.set_weights(np.ascontiguousarray(qd), np.ascontiguousarray(rd))
+        lo.ik_gains = (kp, ka); ig.set_gains(np.ascontiguousarray(kp), np.ascontiguousarray(ka))
+    if push is not None:
+        pt, pd = push
+        lo.set_push(pt, pd); lg.set_push(d(pt), d(pd))
+    lo.reset(q0); lg.reset(d(q0))
+    return lo, lg, (mg, ig, gg, tg)
+
+
+def _compare(o, v, t, stats, dq_tol=1e-5):
+    zg = v["zmp"].cpu().numpy()
+    assert np.array_equal(v["osqp_status"].cpu().numpy(), o["osqp_status"]), t
+    assert np.array_equal(v["iters"].cpu().numpy(), o["iters"]), t
+    assert np.array_equal(v["flags"].cpu().numpy(), o["flags"]), t
+    assert np.array_equal(v["qp_status"].cpu().numpy(), o["qp_status"]), t
+    both = np.isfinite(zg) & np.isfinite(o["zmp"])
+    assert np.array_equal(np.isfinite(zg), np.isfinite(o["zmp"]))
+    assert (np.abs(zg - o["zmp"])[both] / np.maximum(1.0, np.abs(o["zmp"][both]))).max(initial=0.0) <= 1e-6, t
+    assert np.abs(v["dq"].cpu().numpy() - o["dq"]).max() <= dq_tol, t
+    assert np.abs(v["q_des"].cpu().numpy() - o["q_des"]).max() <= 1e-6, t
+    stats["ik_fail"] += int((o["qp_status"] != 0).sum())
+    stats["new"] += int(((o["flags"] & 16) != 0).sum())
+    stats["active"] += int((o["nwsr"] > 0).sum())
+    stats["nwsr_diff"] += int((v["nwsr"].cpu().numpy() != o["nwsr"]).sum())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("use_graph", [0, 1])
+def test_closed_loop_short(wc, oracle, syn, cuda_device, use_graph):
+    B, N, T = 64, 25, 40
+    lo, lg, keep = _make(wc, oracle, syn, cuda_device, B, T, N, seed=5, use_graph=use_graph)
+    stats = dict(new=0, active=0, nwsr_diff=0, ik_fail=0)
+    for t in range(T):
+        o = lo.tick(); lg.run(1); torch.cuda.synchronize()
+        _compare(o, lg.view(), t, stats)
+    assert lg.tick == T and stats["ik_fail"] == 0
+    lg.close()
+
+
+@pytest.mark.gpu
+def test_closed_loop_1000_ticks(wc, oracle, syn, cuda_device):
+    """SURVEY config 1 at B = 1024: 1000 ticks of periodic walking (about 11 steps, >= 20 support-phase changes per
+    instance) from the prepared posture; the joint velocity bounds are active on ~8 % of the instance-ticks and all but a
+    0.2 % tail of the QP-IK problems are feasible.  Every tick of every instance is compared (status, iterations, flags, working-set changes, ZMP, dq, q)."""
+    B, N, T = 1024, 25, 1000
+    lo, lg, keep = _make(wc, oracle, syn, cuda_device, B, T, N, seed=6, use_graph=1)
+    stats = dict(new=0, active=0, nwsr_diff=0, ik_fail=0)
+    for t in range(T):
+        o = lo.tick(); lg.run(1); torch.cuda.synchronize()
+        _compare(o, lg.view(), t, stats)
+    print("closed loop:", stats)
+    assert stats["new"] >= 20 * B, stats                 # >= 20 phase changes per instance on average
+    assert stats["ik_fail"] < 0.01 * B * T, stats        # a walking regime (a small infeasible tail is matched too)
+    assert 0.02 * B * T < stats["active"] < 0.5 * B * T, stats   # the active set was exercised in closed loop
+    assert stats["nwsr_diff"] <= 1e-4 * B * T, stats
+    # the same rollout in ONE call (graph replay without host round trips) ends in the same state, bit for bit
+    q_end = lg.view()["q_des"].clone()
+    lo2, lg2, keep2 = _make(wc, oracle, syn, cuda_device, B, T, N, seed=6, use_graph=1)
+    lg2.run(T); torch.cuda.synchronize()
+    assert torch.equal(lg2.view()["q_des"], q_end)
+    lg.close(); lg2.close()
+
+
+@pytest.mark.gpu
+def test_closed_loop_infeasible_tail(wc, oracle, syn, cuda_device):
+    """The shipped placeholder limit (+-1 rad/s) from an unprepared posture: the synthetic model cannot follow, most QP-IK
+    problems are infeasible (WC_QP_INFEASIBLE, dq = 0) -- the failure path in closed loop must match the oracle too."""
+    B, N, T = 256, 25, 150
+    lo, lg, keep = _make(wc, oracle, syn, cuda_device, B, T, N, seed=8, use_graph=1, vmax=1.0, prepared=False)
+    stats = dict(new=0, active=0, nwsr_diff=0, ik_fail=0)
+    for t in range(T):
+        o = lo.tick(); lg.run(1); torch.cuda.synchronize()
+        _compare(o, lg.view(), t, stats)
+    assert stats["ik_fail"] > 0.5 * B * T, stats
+    lg.close()

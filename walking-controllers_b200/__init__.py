@@ -39,6 +39,21 @@ class TickHostOut(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in ("zmp", "osqp_status", "iters", "flags", "dq", "lf_err", "rf_err", "qp_status", "nwsr")]
 
 
+class LoopConfig(C.Structure):
+    _fields_ = [("dcm_noise_sigma", C.c_double), ("noise_seed", C.c_uint64), ("zmp_meas_offset", C.c_double),
+                ("use_graph", C.c_int32), ("reserved", C.c_int32)]
+
+
+LOOP_VIEW = (("zmp", 2, "f8"), ("dq", "nJ", "f8"), ("q_des", "nJ", "f8"), ("com_pos_des", 3, "f8"), ("com_vel_des", 3, "f8"),
+             ("com_meas", 3, "f8"), ("dcm_meas", 2, "f8"), ("lf_err", 6, "f8"), ("rf_err", 6, "f8"), ("lf_H", 12, "f8"),
+             ("rf_H", 12, "f8"), ("ref_pos", "2N", "f8"), ("osqp_status", 1, "i4"), ("iters", 1, "i4"), ("flags", 1, "i4"),
+             ("qp_status", 1, "i4"), ("nwsr", 1, "i4"))
+
+
+class LoopView(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k, _, _ in LOOP_VIEW]
+
+
 class OsqpSettings(C.Structure):
     _fields_ = [("rho", C.c_double), ("sigma", C.c_double), ("alpha", C.c_double),
                 ("eps_abs", C.c_double), ("eps_rel", C.c_double),
@@ -87,8 +102,9 @@ class IkConfig(C.Structure):
 
 
 class GlueConfig(C.Structure):
-    _fields_ = [("n_dofs", C.c_int32), ("reserved", C.c_int32), ("sampling_time", C.c_double),
-                ("com_height", C.c_double), ("gravity", C.c_double), ("k_zmp", C.c_double), ("k_com", C.c_double)]
+    _fields_ = [("n_dofs", C.c_int32), ("use_gain_scheduling", C.c_int32), ("sampling_time", C.c_double),
+                ("com_height", C.c_double), ("gravity", C.c_double), ("k_zmp", C.c_double), ("k_com", C.c_double),
+                ("smoothing_time", C.c_double), ("k_zmp_stance", C.c_double), ("k_com_stance", C.c_double)]
 
 
 LOG_COLUMNS = 53
@@ -186,6 +202,7 @@ def lib():
     L.wc_glue_destroy.argtypes = [_VP]
     L.wc_glue_reset_dev.argtypes = [_VP, _VP, _VP, _VP]; L.wc_glue_reset_dev.restype = i32
     L.wc_glue_com_reference_dev.argtypes = [_VP] + [_VP] * 10 + [_VP]; L.wc_glue_com_reference_dev.restype = i32
+    L.wc_glue_set_phase_dev.argtypes = [_VP, _VP, _VP, _VP]; L.wc_glue_set_phase_dev.restype = i32
     L.wc_glue_integrate_joints_dev.argtypes = [_VP, _VP, _VP, _VP]; L.wc_glue_integrate_joints_dev.restype = i32
     L.wc_glue_launch_count.argtypes = [_VP]; L.wc_glue_launch_count.restype = i64
     L.wc_traj_default_config.argtypes = [C.POINTER(TrajConfig), i32, i32]
@@ -206,6 +223,16 @@ def lib():
     L.wc_glue_evaluate_zmp_dev.argtypes = [_VP] * 8; L.wc_glue_evaluate_zmp_dev.restype = i32
     L.wc_glue_log_pack_dev.argtypes = [_VP, C.POINTER(LogInputs), _VP, _VP]; L.wc_glue_log_pack_dev.restype = i32
     L.wc_measure_fp64_peak.argtypes = [i32, C.POINTER(C.c_double)]; L.wc_measure_fp64_peak.restype = i32
+    L.wc_loop_default_config.argtypes = [C.POINTER(LoopConfig)]
+    L.wc_loop_create.argtypes = [_VP, _VP, _VP, _VP, C.POINTER(LoopConfig), i32, C.POINTER(_VP)]; L.wc_loop_create.restype = i32
+    L.wc_loop_destroy.argtypes = [_VP]
+    L.wc_loop_reset_dev.argtypes = [_VP, _VP, _VP]; L.wc_loop_reset_dev.restype = i32
+    L.wc_loop_set_push_dev.argtypes = [_VP, _VP, _VP, _VP]; L.wc_loop_set_push_dev.restype = i32
+    L.wc_loop_run_dev.argtypes = [_VP, i32, _VP]; L.wc_loop_run_dev.restype = i32
+    L.wc_loop_tick_count.argtypes = [_VP]; L.wc_loop_tick_count.restype = i64
+    L.wc_loop_view_get.argtypes = [_VP, C.POINTER(LoopView)]; L.wc_loop_view_get.restype = i32
+    L.wc_mpc_set_tick_source_dev.argtypes = [_VP, _VP]; L.wc_mpc_set_tick_source_dev.restype = i32
+    L.wc_traj_set_tick_source_dev.argtypes = [_VP, _VP]; L.wc_traj_set_tick_source_dev.restype = i32
     if hasattr(L, "wc_ik_create"):
         L.wc_ik_create.argtypes = [C.POINTER(IkConfig), C.POINTER(Model), i32, i32, C.POINTER(_VP)]
         L.wc_ik_create.restype = i32
@@ -653,6 +680,12 @@ class GlueBatch:
     def reset(self, com_xy=None, q=None, stream=None):
         _check(lib().wc_glue_reset_dev(self.h, _ptr(com_xy), _ptr(q), self._stream(stream)), "wc_glue_reset_dev")
 
+    def set_phase(self, dcm_vel_des=None, stance=None, stream=None):
+        """WalkingZMPController::setPhase (gain scheduling): stance flags [B] uint8, or the |dcm_vel_des| < 0.001 rule"""
+        _check(lib().wc_glue_set_phase_dev(self.h, _arg(dcm_vel_des, "f64", 2 * self.B, "cuda", "dcm_vel_des"),
+                                           _arg(stance, "u8", self.B, "cuda", "stance"), self._stream(stream)),
+               "wc_glue_set_phase_dev")
+
     def com_reference(self, dcm_des, zmp_des, zmp_meas, com_meas, com_z_des=None, com_z_vel_des=None, k_zmp=None,
                       k_com=None, out=None, stream=None):
         import torch
@@ -810,3 +843,74 @@ def measure_fp64_peak(device=0):
     g = C.c_double()
     _check(lib().wc_measure_fp64_peak(device, C.byref(g)), "wc_measure_fp64_peak")
     return g.value
+
+
+def loop_default_config():
+    c = LoopConfig()
+    lib().wc_loop_default_config(C.byref(c))
+    return c
+
+
+class _DevArray:
+    """a raw device pointer as a CUDA-array-interface object (torch.as_tensor wraps it without a copy)"""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": shape, "typestr": "<" + typestr, "data": (ptr, False), "version": 2}
+
+
+class LoopBatch:
+    """The closed-loop control tick as one call (wc_loop_*): producer -> measured CoM -> DCM-MPC -> ZMP-CoM law with gain
+    scheduling -> FK + QP-IK -> joint integrator, device resident, CUDA-graph replayed.  Borrows the four block handles."""
+
+    def __init__(self, mpc, ik, glue, traj, cfg=None, device=0):
+        self.mpc, self.ik, self.glue, self.traj = mpc, ik, glue, traj  # keep the borrowed handles alive
+        self.cfg = cfg if cfg is not None else loop_default_config()
+        self.B, self.N, self.nJ, self.device = mpc.B, mpc.N, ik.nJ, device
+        h = _VP()
+        _check(lib().wc_loop_create(mpc.h, ik.h, glue.h, traj.h, C.byref(self.cfg), device, C.byref(h)), "wc_loop_create")
+        self.h = h
+        self._view = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().wc_loop_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self, stream):
+        import torch
+        return torch.cuda.current_stream(self.device).cuda_stream if stream is None else stream
+
+    def reset(self, q0, stream=None):
+        _check(lib().wc_loop_reset_dev(self.h, _arg(q0, "f64", self.nJ * self.B, "cuda", "q0"), self._stream(stream)), "wc_loop_reset_dev")
+
+    def set_push(self, push_tick, push_dxy, stream=None):
+        _check(lib().wc_loop_set_push_dev(self.h, _arg(push_tick, "i32", self.B, "cuda", "push_tick"),
+                                          _arg(push_dxy, "f64", 2 * self.B, "cuda", "push_dxy"), self._stream(stream)),
+               "wc_loop_set_push_dev")
+
+    def run(self, n_ticks=1, stream=None):
+        _check(lib().wc_loop_run_dev(self.h, int(n_ticks), self._stream(stream)), "wc_loop_run_dev")
+
+    @property
+    def tick(self):
+        return lib().wc_loop_tick_count(self.h)
+
+    def view(self):
+        """dict of torch tensors aliasing the handle's device buffers (signals of the last tick run; no copy)"""
+        import torch
+        if self._view is None:
+            v = LoopView()
+            _check(lib().wc_loop_view_get(self.h, C.byref(v)), "wc_loop_view_get")
+            out = {}
+            for k, rows, ts in LOOP_VIEW:
+                r = self.nJ if rows == "nJ" else (2 * (self.N + 1) if rows == "2N" else rows)
+                shape = (self.B,) if (ts == "i4") else (r, self.B)
+                out[k] = torch.as_tensor(_DevArray(getattr(v, k), shape, ts), device=f"cuda:{self.device}")
+            self._view = out
+        return self._view

@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(kSetupWarps * 32) mpc_chain_setup_kernel(MpcDe
     const int nh = d.nhull[i];
     const double Q[2] = {d.Qd[i], d.Qd[B + i]};
     const double R[2] = {d.Rd[i], d.Rd[B + i]};
-    const int head = d.ring_head;
+    const int head = mpc_ring_head(d);
     for (int j = lane; j < 2 * nA; j += 32) { DD[j] = 1.0; QB[j] = 0.0; }
     for (int j = lane; j < 2 * nR; j += 32) EE[j] = 1.0;
     if (lane < kMaxHull) {
@@ -484,7 +484,7 @@ __global__ void __launch_bounds__(2 * IPW) mpc_chain_kernel(MpcDev d, MpcTickIO 
     const double c = d.cscale[i];
     double rho = d.rho[i];
     const double upa = d.uprev[(size_t)a * B + i];
-    const int head = d.ring_head;
+    const int head = mpc_ring_head(d);
     const double cQ = c * Qa, cR = c * Ra;
 
     // ------------------------------------------------------------------ stage in (all copies in flight at once)

@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(128) mpc_prepare_kernel(MpcDev d, MpcTickIO io
     if (!inited && d.setup_list) d.setup_list[atomicAdd(d.setup_count, 1)] = i; // osqp_setup pending
     const bool reset = io.reset ? (io.reset[i] != 0) : false;
     const double Q[2] = {d.Qd[i], d.Qd[B + i]};
-    const int head = d.ring_head;
+    const int head = mpc_ring_head(d);
 
     // ---- MPCSolver::setGradient (state block; the input block -R u_prev is formed in K2)
     // reference sample k of this tick's window: the caller's array, or the device-side ring
@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(128) mpc_ref_ring_kernel(MpcDev d, const doubl
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= d.B) return;
     const size_t B = (size_t)d.B;
-    const int N = d.N, nR = N + 1, head = d.ring_head;
+    const int N = d.N, nR = N + 1, head = mpc_ring_head(d);
     if (window) {
         for (int k = 0; k <= N; k++) {
             const int slot = (head + k) % nR;
@@ -384,7 +384,7 @@ __global__ void __launch_bounds__(128) mpc_admm_kernel(MpcDev d, MpcTickIO io, i
     double c = setup ? 1.0 : d.cscale[i];
     double rho = setup ? fmin(fmax(st.rho, kRhoMin), kRhoMax) : d.rho[i];
     const double up[2] = {d.uprev[i], d.uprev[B + i]};
-    const int head = d.ring_head;
+    const int head = mpc_ring_head(d);
 
     // ------------------------------------------------------------------ stage in
     for (int j = gl; j < 2 * nA; j += G) {

@@ -87,7 +87,15 @@ struct MpcDev {
     // (ring_head + k) mod (N+1), so a host that feeds the controller uploads one new sample per tick, as
     // MPCSolver::setGradient consumes one (MPCSolver.cpp:216-239)
     double* ref_ring;    // [2*(N+1)][B], allocated on first use
+    // optional device-side tick counter (wc_mpc_set_tick_source_dev): the ring head is then read on the device, so a tick's
+    // launch sequence no longer depends on the tick index and can be replayed from a CUDA graph (wc_loop.cu)
+    const int32_t* tick_dev;
 };
+
+__device__ __forceinline__ int mpc_ring_head(const MpcDev& d)
+{
+    return d.tick_dev ? (int)((unsigned)(*d.tick_dev) % (unsigned)(d.N + 1)) : d.ring_head;
+}
 
 struct MpcTickIO {
     const double* lf_H; const double* rf_H;

@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(32, WC_SPLIT_MINB) mpc_split_kernel(MpcDev d, 
     const double c = d.cscale[i];
     double rho = d.rho[i];
     const double upa = d.uprev[(size_t)a * B + i];
-    const int head = d.ring_head;
+    const int head = mpc_ring_head(d);
     const double cQ = c * Qa, cR = c * Ra;
     const double cinv = 1.0 / c;
     const double cqu0 = c * (-(Ra * upa));           // c q of u_0 (MPCSolver.cpp:244-245: G u_prev, first block only)

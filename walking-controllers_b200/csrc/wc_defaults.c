@@ -162,12 +162,16 @@ void wc_model_icub_like(wc_model* m)
 void wc_glue_default_config(wc_glue_config* c)
 {
     if (!c) return;
-    c->n_dofs = 23; c->reserved = 0;
+    c->n_dofs = 23;
+    c->use_gain_scheduling = 1; /* zmpControllerParams.ini:2 */
     c->sampling_time = 0.01;
     c->com_height = 0.53;
     c->gravity = 9.81;
     c->k_zmp = 3.0;
     c->k_com = 9.0;
+    c->smoothing_time = 0.05;
+    c->k_zmp_stance = 0.9;
+    c->k_com_stance = 6.0;
 }
 
 /* iCubGazeboV2_5 plannerParams.ini: nominalDuration 0.9, switchOverSwingRatio 0.7 (double support = 0.7 / 1.7 of a

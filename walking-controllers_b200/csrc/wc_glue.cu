@@ -10,8 +10,8 @@
 //   WalkingModule::evaluateZMP                        modules/Walking_module/src/WalkingModule.cpp:824-876
 //   WalkingFK::evaluateDCM                            modules/Walking_module/src/WalkingForwardKinematics.cpp:312-340
 //   the 53 columns of m_walkingLogger->sendData       modules/Walking_module/src/WalkingModule.cpp:793-803, 1231-1250
-// The gain scheduling of WalkingZMPController::setPhase (iCub::ctrl::minJerkTrajGen, external) is not restated:
-// gains are inputs (constants from the configuration, or per-instance arrays the caller schedules).
+//   WalkingZMPController::setPhase (gain scheduling) modules/Walking_module/src/WalkingZMPController.cpp:107-126
+//   iCub::ctrl::minJerkTrajGen (external, ctrlLib): F(s) = -a / (s^3 - c s^2 - b s - a), Tustin-discretised (wc_capi.h)
 // One thread per instance; every array is field-major SoA fp64; the kernels are HBM-streaming.
 #include <cmath>
 #include <cstdio>
@@ -32,6 +32,8 @@ struct wc_glue {
     double* q_y;      // [nJ][B] joint integrator output (m_qDesired)
     double* q_v;      // [nJ][B] its x_old
     double* cf;       // [12][B] WalkingFK's CoM filters: position y, u_old; velocity y, u_old (3 rows each)
+    double* gs;       // [14][B] gain scheduling: (y1..y3, u1..u3) of the kZMP and of the kCoM smoother, then the current kZMP, kCoM
+    double fnum[4], fden[4]; // minJerkTrajGen position filter: y a0 = sum b_k u_{n-k} - sum a_k y_{n-k}
     int64_t launches;
 };
 
@@ -49,6 +51,41 @@ __global__ void glue_reset_kernel(int B, int nJ, const double* com_xy, const dou
     }
     if (q)
         for (int j = 0; j < nJ; j++) { q_y[j * Bz + i] = q[j * Bz + i]; q_v[j * Bz + i] = 0.0; }
+}
+
+struct GsCoef { double b[4], a[4]; };
+
+// WalkingZMPController::setPhase: one step of both smoothers towards the gains of the phase
+__global__ void glue_set_phase_kernel(int B, GsCoef f, double kz_stance, double kc_stance, double kz_walk, double kc_walk,
+                                      const double* dcm_vel_des, const uint8_t* stance, double* gs)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    const size_t Bz = (size_t)B;
+    bool st;
+    if (stance) st = stance[i] != 0;
+    else { const double vx = dcm_vel_des[i], vy = dcm_vel_des[Bz + i]; st = sqrt(vx * vx + vy * vy) < 0.001; }
+#pragma unroll
+    for (int g = 0; g < 2; g++) {
+        const double u = g == 0 ? (st ? kz_stance : kz_walk) : (st ? kc_stance : kc_walk);
+        double* s = gs + (size_t)(6 * g) * Bz + i;
+        const double y1 = s[0], y2 = s[Bz], y3 = s[2 * Bz], u1 = s[3 * Bz], u2 = s[4 * Bz], u3 = s[5 * Bz];
+        double y = f.b[0] * u;
+        y += f.b[1] * u1; y += f.b[2] * u2; y += f.b[3] * u3;
+        y -= f.a[1] * y1; y -= f.a[2] * y2; y -= f.a[3] * y3;
+        y = (1.0 / f.a[0]) * y;
+        s[0] = y; s[Bz] = y1; s[2 * Bz] = y2; s[3 * Bz] = u; s[4 * Bz] = u1; s[5 * Bz] = u2;
+        gs[(size_t)(12 + g) * Bz + i] = y;
+    }
+}
+
+__global__ void glue_gs_init_kernel(int B, double kz, double kc, double* gs)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    const size_t Bz = (size_t)B;
+    for (int r = 0; r < 6; r++) { gs[(size_t)r * Bz + i] = kz; gs[(size_t)(6 + r) * Bz + i] = kc; }
+    gs[(size_t)12 * Bz + i] = kz; gs[(size_t)13 * Bz + i] = kc;
 }
 
 // LIPM reference + ZMP-CoM control law (WalkingModule.cpp:578-597, 657-695)
@@ -261,12 +298,24 @@ wc_status wc_glue_create(const wc_glue_config* cfg, int32_t B, int32_t device, w
     h->omega = std::sqrt(cfg->gravity / cfg->com_height);
     const size_t Bz = (size_t)B, nJ = (size_t)cfg->n_dofs;
     double* base = nullptr;
-    const size_t total = (8 + 2 * nJ + 12) * Bz;
+    const size_t total = (8 + 2 * nJ + 12 + 14) * Bz;
     if (cudaMalloc(&base, total * sizeof(double)) != cudaSuccess) { delete h; return WC_ERR_ALLOC; }
     cudaMemset(base, 0, total * sizeof(double));
     h->lipm_c = base; h->lipm_v = base + 2 * Bz; h->zc_y = base + 4 * Bz; h->zc_v = base + 6 * Bz;
-    h->q_y = base + 8 * Bz; h->q_v = h->q_y + nJ * Bz; h->cf = h->q_v + nJ * Bz;
+    h->q_y = base + 8 * Bz; h->q_v = h->q_y + nJ * Bz; h->cf = h->q_v + nJ * Bz; h->gs = h->cf + 12 * Bz;
     glue_reset_com_filter_kernel<<<(B + 127) / 128, 128>>>(B, cfg->com_height, h->cf); // the filters' init of WalkingFK::initialize
+    if (cfg->use_gain_scheduling) {
+        if (!(cfg->smoothing_time > 0)) { cudaFree(base); delete h; return WC_ERR_INVALID_ARG; }
+        // minJerkTrajGen(1, Ts, T): F(s) = -a / (s^3 - c s^2 - b s - a) with s = (2 / Ts)(z - 1)/(z + 1)
+        const double T = cfg->smoothing_time, k = 2.0 / cfg->sampling_time;
+        const double a = -150.765868956161 / (T * T * T), b = -84.9812819469538 / (T * T), c = -15.9669610709384 / T;
+        const double k2 = k * k, k3 = k2 * k;
+        h->fden[0] = k3 - c * k2 - b * k - a;  h->fden[1] = -3.0 * k3 + c * k2 - b * k - 3.0 * a;
+        h->fden[2] = 3.0 * k3 + c * k2 + b * k - 3.0 * a;  h->fden[3] = -k3 - c * k2 + b * k - a;
+        h->fnum[0] = -a; h->fnum[1] = -3.0 * a; h->fnum[2] = -3.0 * a; h->fnum[3] = -a;
+        // m_kZMPSmoother->init(kZMP_stance), m_kCoMSmoother->init(kCoM_stance) (:78-83)
+        glue_gs_init_kernel<<<(B + 127) / 128, 128>>>(B, cfg->k_zmp_stance, cfg->k_com_stance, h->gs);
+    }
     if (cudaDeviceSynchronize() != cudaSuccess) { cudaFree(base); delete h; return WC_ERR_CUDA; }
     *out = h;
     return WC_OK;
@@ -299,9 +348,26 @@ wc_status wc_glue_com_reference_dev(wc_glue* h, const double* dcm_des, const dou
 {
     if (!h || !dcm_des || !zmp_des || !zmp_meas || !com_meas || !com_pos_des || !com_vel_des) return WC_ERR_INVALID_ARG;
     if (cudaSetDevice(h->device) != cudaSuccess) return WC_ERR_CUDA;
+    // gains: the caller's per-instance arrays, else the scheduled ones (setPhase), else the walking constants
+    const size_t Bz = (size_t)h->B;
+    if (!k_zmp && h->cfg.use_gain_scheduling) k_zmp = h->gs + 12 * Bz;
+    if (!k_com && h->cfg.use_gain_scheduling) k_com = h->gs + 13 * Bz;
     glue_com_reference_kernel<<<(h->B + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
         h->B, h->omega, 0.5 * h->cfg.sampling_time, h->cfg.k_zmp, h->cfg.k_com, dcm_des, zmp_des, zmp_meas, com_meas,
         com_z_des, com_z_vel_des, k_zmp, k_com, h->lipm_c, h->lipm_v, h->zc_y, h->zc_v, com_pos_des, com_vel_des);
+    h->launches += 1;
+    return cudaGetLastError() == cudaSuccess ? WC_OK : WC_ERR_CUDA;
+}
+
+wc_status wc_glue_set_phase_dev(wc_glue* h, const double* dcm_vel_des, const uint8_t* stance, void* stream)
+{
+    if (!h || (!dcm_vel_des && !stance)) return WC_ERR_INVALID_ARG;
+    if (!h->cfg.use_gain_scheduling) return WC_OK;
+    if (cudaSetDevice(h->device) != cudaSuccess) return WC_ERR_CUDA;
+    GsCoef f;
+    for (int k = 0; k < 4; k++) { f.b[k] = h->fnum[k]; f.a[k] = h->fden[k]; }
+    glue_set_phase_kernel<<<(h->B + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        h->B, f, h->cfg.k_zmp_stance, h->cfg.k_com_stance, h->cfg.k_zmp, h->cfg.k_com, dcm_vel_des, stance, h->gs);
     h->launches += 1;
     return cudaGetLastError() == cudaSuccess ? WC_OK : WC_ERR_CUDA;
 }

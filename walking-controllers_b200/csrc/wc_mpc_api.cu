@@ -516,4 +516,11 @@ wc_status wc_mpc_kernel_times_detail_ms(wc_mpc* h, double* setup_ms, double* pha
 
 int32_t wc_mpc_path(const wc_mpc* h) { return h ? h->chain : -1; }
 
+wc_status wc_mpc_set_tick_source_dev(wc_mpc* h, const int32_t* tick_dev)
+{
+    if (!h) return WC_ERR_INVALID_ARG;
+    h->d.tick_dev = tick_dev;
+    return WC_OK;
+}
+
 } // extern "C"

@@ -31,6 +31,7 @@ struct wc_traj {
     uint8_t* first_left; // [B]
     int64_t launches;
     bool gait_set;
+    const int32_t* tick_dev; // optional device-side tick offset added to every tick / first_sample argument
 };
 
 namespace {
@@ -41,7 +42,9 @@ struct TrajDev {
     int B, S2, step_ticks, ds_ticks;
     double dt, omega, width, step_height, zmp_dx, zmp_dy, com_height;
     double* tbl; int32_t* phase; uint8_t* first_left;
+    const int32_t* tick_dev;
 };
+__device__ __forceinline__ int tick_of(const TrajDev& d, int t) { return d.tick_dev ? t + *d.tick_dev : t; }
 
 __device__ __forceinline__ double tb(const TrajDev& d, int f, int k, int i)
 {
@@ -108,8 +111,9 @@ __device__ __forceinline__ void dcm_at(const TrajDev& d, int s, int i, double* p
 
 // samples s0 .. s0+n-1 of the DCM reference (and velocity): sample s, axis a of instance i at [(2 (s - s0) + a) B + i] —
 // rows [0, 2 (N+1)) with s0 = t are the deque WalkingController::setReferenceSignal reads at tick t
-__global__ void traj_dcm_kernel(TrajDev d, int s0, int n, double* pos_out, double* vel_out)
+__global__ void traj_dcm_kernel(TrajDev d, int s0_arg, int n, double* pos_out, double* vel_out)
 {
+    const int s0 = tick_of(d, s0_arg);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int r = blockIdx.y;
     if (i >= d.B || r >= n) return;
@@ -133,8 +137,9 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32
     }
 }
 
-__global__ void traj_measured_dcm_kernel(TrajDev d, int t, double sigma, uint64_t seed, double* out)
+__global__ void traj_measured_dcm_kernel(TrajDev d, int t_arg, double sigma, uint64_t seed, double* out)
 {
+    const int t = tick_of(d, t_arg);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= d.B) return;
     double p[2];
@@ -158,8 +163,9 @@ __device__ __forceinline__ void put_H(double* H, size_t B, int i, double x, doub
 }
 
 // feet poses, twists (mixed: linear then angular), contact flags and the fixed-foot flag at tick t
-__global__ void traj_feet_kernel(TrajDev d, int t, wc_traj_feet o)
+__global__ void traj_feet_kernel(TrajDev d, int t_arg, wc_traj_feet o)
 {
+    const int t = tick_of(d, t_arg);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= d.B) return;
     const size_t B = (size_t)d.B;
@@ -203,6 +209,7 @@ TrajDev dev_view(const wc_traj* h)
     d.dt = h->cfg.sampling_time; d.omega = h->omega; d.width = h->cfg.nominal_width; d.step_height = h->cfg.step_height;
     d.zmp_dx = h->cfg.zmp_delta[0]; d.zmp_dy = h->cfg.zmp_delta[1]; d.com_height = h->cfg.com_height;
     d.tbl = h->tbl; d.phase = h->phase; d.first_left = h->first_left;
+    d.tick_dev = h->tick_dev;
     return d;
 }
 
@@ -222,7 +229,7 @@ wc_status wc_traj_create(const wc_traj_config* cfg, int32_t B, int32_t device, w
     if (cudaSetDevice(device) != cudaSuccess) return WC_ERR_CUDA;
     wc_traj* h = new (std::nothrow) wc_traj();
     if (!h) return WC_ERR_ALLOC;
-    h->cfg = *cfg; h->B = B; h->device = device; h->launches = 0; h->gait_set = false;
+    h->cfg = *cfg; h->B = B; h->device = device; h->launches = 0; h->gait_set = false; h->tick_dev = nullptr;
     h->S2 = cfg->n_steps + 2;
     h->omega = std::sqrt(cfg->gravity / cfg->com_height);
     const size_t Bz = (size_t)B;
@@ -252,6 +259,13 @@ wc_status wc_traj_set_gait_dev(wc_traj* h, const int32_t* phase, const double* s
     traj_tables_kernel<<<(h->B + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(dev_view(h), phase, step_len, dtheta, theta0, first_left);
     h->launches += 1; h->gait_set = true;
     return cudaGetLastError() == cudaSuccess ? WC_OK : WC_ERR_CUDA;
+}
+
+wc_status wc_traj_set_tick_source_dev(wc_traj* h, const int32_t* tick_dev)
+{
+    if (!h) return WC_ERR_INVALID_ARG;
+    h->tick_dev = tick_dev;
+    return WC_OK;
 }
 
 wc_status wc_traj_dcm_dev(wc_traj* h, int32_t first_sample, int32_t n_samples, double* dcm_pos, double* dcm_vel, void* stream)

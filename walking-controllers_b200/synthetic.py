@@ -218,3 +218,39 @@ def ik_inputs(B, seed, q_reg, fk, device="cpu", perturb=1.0):
     return dict(q_meas=c(q_meas), q_lin=c(q_lin), base_H=c(base_H), left_is_fixed=left_is_fixed,
                 lf_H_des=c(lf_des), rf_H_des=c(rf_des), lf_twist=c(lf_tw), rf_twist=c(rf_tw),
                 com_pos_des=c(com_des), com_vel_des=c(com_vel), com_meas=c(com_meas), neck_R_des=c(neck_des))
+
+
+# The closed-loop workload (wc_loop_*, tests/test_closed_loop.py, bench.py `closed_loop`).  The synthetic 23-DoF model
+# (wc_model_icub_like) stands 0.34 m tall at its regularisation posture, not the iCub's 0.53 m: the LIPM height of the
+# closed loop is the model's own.  The shipped +-1 rad/s velocity limit is a placeholder (the reference reads the real
+# limits from the robot, RobotHelper.cpp:288-298) under which this model cannot follow the gait at all; +-2 rad/s keeps
+# every instance feasible while ~9 % of the instance-ticks hit a bound (the share of the open-loop benchmark workload).
+CL_COM_HEIGHT = 0.34
+CL_VMAX = 2.0
+CL_PREP_ITERS = 400
+
+
+def prepare_posture(fk, ik_tick, q_reg, feet, com_target, iters=CL_PREP_ITERS, dt=DT):
+    """The analogue of WalkingModule::prepareRobot (WalkingModule.cpp:452-540: an initial joint configuration that puts the
+    CoM where the trajectory starts, above the desired feet) for the synthetic model: iterate the QP-IK itself, with joint
+    velocity limits the caller has opened, from the regularisation posture -- q <- q + dt dq with the feet held at `feet`
+    (the producer's signals of tick 0) and the CoM drawn to com_target [3, B] -- until it has converged.
+    fk(q, base_H, left_is_fixed) -> dict(com=...), ik_tick(inp) -> dict(dq=...): the product's IkBatch or the oracle's
+    restatement behind torch adapters.  Returns q0 [nJ, B]."""
+    B = com_target.shape[1]
+    dev = com_target.device
+    q = q_reg.to(dev)[:, None].repeat(1, B).contiguous()
+    lif = feet["left_is_fixed"]
+    base = torch.where(lif[None, :] != 0, feet["lf_H"], feet["rf_H"]).contiguous()
+    yl = torch.atan2(feet["lf_H"][4], feet["lf_H"][0]); yr = torch.atan2(feet["rf_H"][4], feet["rf_H"][0])
+    my = torch.atan2(torch.sin(yl) + torch.sin(yr), torch.cos(yl) + torch.cos(yr))
+    neck = rotz(my).contiguous()
+    zero6 = torch.zeros(6, B, dtype=torch.float64, device=dev)
+    zero3 = torch.zeros(3, B, dtype=torch.float64, device=dev)
+    for _ in range(iters):
+        com = fk(q, base, lif)["com"]
+        inp = dict(q_meas=q, q_lin=q, base_H=base, left_is_fixed=lif, lf_H_des=feet["lf_H"], rf_H_des=feet["rf_H"],
+                   lf_twist=zero6, rf_twist=zero6, com_pos_des=com_target.contiguous(), com_vel_des=zero3, com_meas=com,
+                   neck_R_des=neck)
+        q = (q + dt * ik_tick(inp)["dq"]).contiguous()
+    return q
