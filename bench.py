@@ -65,7 +65,7 @@ METRIC = "MPC+QP-IK controller ticks/sec at B=65536 iCub instances"   # BASELINE
 
 
 def workload_config(world, B, N):
-    """`config` of both arms (ours and --impl reference): BASELINE configs[2]"""
+    """`config` of both arms (ours and --impl reference), key for key: BASELINE configs[2]"""
     return {"workload": f"full tick: DCM-MPC (horizon {N}) + FK + QP-IK, iCub 23-DoF + floating base (BASELINE configs[2])",
             "instances_per_gpu": B, "instances_total": world * B, "horizon": N,
             "l2": "per-tick working set (solver state 10 KB x 65536 + inputs) exceeds the 126 MB L2; inputs change every tick"}
@@ -130,11 +130,13 @@ class ClockSampler:
         return out
 
 
-def ncu_traffic(kernel):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/ncu_traffic.json)"""
+def ncu_counter(kernel, key="bytes_per_launch"):
+    """per-launch counters of the dominant kernel from the committed `ncu --set full` capture (profiles/ncu_traffic.json):
+    DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) and shared-memory wavefronts
+    (l1tex__data_pipe_lsu_wavefronts_mem_shared.sum)"""
     p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     try:
-        return json.load(open(p)).get(kernel, {}).get("bytes_per_launch")
+        return json.load(open(p)).get(kernel, {}).get(key)
     except Exception:
         return None
 
@@ -156,9 +158,13 @@ def run_reference(args, world, rank):
     syn = importlib.import_module("walking-controllers_b200.synthetic")
     O.build()
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
-    B, N = CPU_SAMPLE_B, args.horizon
+    N = args.horizon
     steps, warm = args.steps, args.warmup
     T = steps + warm
+    # instances per step: the workload's own batch when the whole run then fits ~3 minutes at the port's ~11 k ticks/s
+    # per core, else a bounded sample of it (stated in `sample_instances_per_step`, outside `config`)
+    budget = int(180.0 * 11000.0 * cores / max(T, 1))
+    B = max(CPU_SAMPLE_B, min(args.batch, budget // 1024 * 1024))
     g = syn.GaitBatch(B, T, N)
     traj = g.trajectory().numpy()
     model = O.model_icub_like(); icfg = O.ik_default_config()
@@ -186,10 +192,11 @@ def run_reference(args, world, rank):
     tot = sum(times)
     val = B * len(times) / tot
     sample = f"{B} instances x {len(times)} ticks of the same synthetic workload (N={N}), one instance per thread"
-    cfg = workload_config(world, B_PER_GPU, N)
-    cfg["note"] = ("CPU restatement of the reference path (osqp-eigen/qpOASES/iDynTree cannot be built offline), "
-                   f"timed on a bounded sample of the workload: {B} instances per step")
+    cfg = workload_config(world, args.batch, N)
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "ticks/s",
+            "sample_instances_per_step": B,
+            "note": ("CPU restatement of the reference path (osqp-eigen / qpOASES / iDynTree cannot be built offline), one "
+                     f"instance per thread on {cores} host threads, {B} instances of the workload per step"),
             "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": tot / len(times) * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": cfg,
@@ -303,6 +310,9 @@ def run_ours(args, world, rank, local_rank):
     # ---------------- arm 1: device-resident inputs
     mpc = wc.MpcBatch(mcfg, B, device=local_rank)
     mo = io_ = None
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()   # before the warm-up: nvidia-smi needs ~100 ms for its first row, the timed region may be shorter
     for t in range(warm):
         a = mpc_in[t]
         mo = mpc.tick(a[0], a[1], a[2], a[3], a[4], traj[2 * t: 2 * t + 2 * (N + 1)], out=mo)
@@ -310,9 +320,6 @@ def run_ours(args, world, rank, local_rank):
     barrier()
     mpc.enable_profiling(True); ik.enable_profiling(True)
     l0 = mpc.launches + ik.launches
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
     it_sum = torch.zeros((), dtype=torch.float64, device=dev)
     it_max = torch.zeros((), dtype=torch.int32, device=dev)
@@ -364,55 +371,115 @@ def run_ours(args, world, rank, local_rank):
         torch.cuda.synchronize(); gather_ms = (time.perf_counter() - t0) * 1e3
         solved, ik_ok, it_mean, wsc_mean = (stats / world).tolist()
 
-    # ---------------- arm 2: end to end through the host-pointer C ABI (pinned host buffers)
-    mpc2 = wc.MpcBatch(mcfg, B, device=local_rank)
+    # ---------------- arm 2: the closed-loop tick (wc_loop_*): producer -> measured CoM -> MPC -> ZMP-CoM law -> FK + QP-IK ->
+    # integrator with the data dependence of WalkingModule::updateModule (the IK of tick t consumes the MPC output of tick t),
+    # one CUDA-graph replay per tick, device resident.  Workload: synthetic.py CL_* (the model's own LIPM height, +-2 rad/s).
+    h_cl = syn.CL_COM_HEIGHT
     e2e_steps = min(steps, 20)
     e2e_warm = min(warm, 5)
     Te = e2e_steps + e2e_warm
+    cl_steps = min(steps, 200)
+    tcfg = wc.traj_default_config(Te + warm + cl_steps + 8, N); tcfg.com_height = h_cl
+    mcfg_cl = wc.mpc_default_config(N); mcfg_cl.com_height = h_cl
+    gcfg = wc.glue_default_config(); gcfg.com_height = h_cl
+    icfg_cl, icfg_open = wc.ik_default_config(), wc.ik_default_config()
+    for j in range(23):
+        icfg_cl.min_vel[j], icfg_cl.max_vel[j] = -syn.CL_VMAX, syn.CL_VMAX
+        icfg_open.min_vel[j], icfg_open.max_vel[j] = -50.0, 50.0
+    tj = wc.TrajBatch(tcfg, B, device=local_rank)
+    tj.set_gait(g.step_len, g.phase.to(torch.int32), g.dtheta, g.theta0, g.first_left.to(torch.uint8))
+    ik_open = wc.IkBatch(icfg_open, model, B, device=local_rank)
+    f0 = tj.feet(0); ref0, _ = tj.dcm(0, 1, want_vel=False)
+    tgt = torch.cat([ref0[0:2], torch.full((1, B), h_cl, dtype=torch.float64, device=dev)], 0).contiguous()
+    q0 = syn.prepare_posture(lambda q, b, l: ik_open.fk(q, b, l, jacobians=False), lambda inp: ik_open.tick(inp), qreg, f0, tgt)
+    torch.cuda.synchronize()
+    ik_open.close()
+    mpc_cl = wc.MpcBatch(mcfg_cl, B, device=local_rank)
+    ik_cl = wc.IkBatch(icfg_cl, model, B, device=local_rank)
+    glue = wc.GlueBatch(gcfg, B, device=local_rank)
+    loop = wc.LoopBatch(mpc_cl, ik_cl, glue, tj, device=local_rank)
+    loop.reset(q0)
+    view = loop.view()
 
     def pin(x):
-        return x.cpu().pin_memory()
+        return x.detach().cpu().contiguous().pin_memory()
 
-    h_mpc = [tuple(pin(v) for v in mpc_in[t]) + (pin(traj[2 * t: 2 * t + 2 * (N + 1)]),) for t in range(Te)]
-    h_ik = [{k: pin(v) for k, v in ik_in[r].items()} for r in range(min(IK_RING, 4))]
-    def mk_mo():
-        return dict(zmp=torch.empty(2, B, dtype=torch.float64).pin_memory(), status=torch.empty(B, dtype=torch.int32).pin_memory(),
-                    iters=torch.empty(B, dtype=torch.int32).pin_memory(), flags=torch.empty(B, dtype=torch.int32).pin_memory())
+    # the first Te ticks are recorded: what a host that feeds the two blocks would upload, and what it would read back
+    h_in, cl_out = [], []
+    for t in range(Te):
+        q_before = view["q_des"].clone()
+        loop.run(1)
+        torch.cuda.synchronize()
+        rec = dict(lf_H=pin(view["lf_H"]), rf_H=pin(view["rf_H"]), l_contact=pin(view["l_contact"]), r_contact=pin(view["r_contact"]),
+                   left_is_fixed=pin(view["left_is_fixed"]), dcm_meas=pin(view["dcm_meas"]), q_meas=pin(q_before), q_lin=pin(q_before),
+                   lf_twist=pin(view["lf_twist"]), rf_twist=pin(view["rf_twist"]), com_pos_des=pin(view["com_pos_des"]),
+                   com_vel_des=pin(view["com_vel_des"]), com_meas=pin(view["com_meas"]), neck_R_des=pin(view["neck_R_des"]))
+        if t == 0:
+            rec["ref_window"] = pin(view["ref_pos"])
+        else:
+            rec["ref_newest"] = pin(view["ref_pos"][2 * N: 2 * N + 2])
+        h_in.append(rec)
+        cl_out.append((view["zmp"].clone(), view["dq"].clone()))
+    for t in range(warm):
+        loop.run(1)
+    barrier()
+    ce0, ce1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ce0.record()
+    loop.run(cl_steps)
+    ce1.record()
+    barrier()
+    cl_ms = torch.tensor([ce0.elapsed_time(ce1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(cl_ms, op=dist.ReduceOp.MAX)
+    cl_ms = cl_ms.item()
+    cl_stats = dict(osqp_solved_frac=(view["osqp_status"] == 1).double().mean().item(),
+                    qpik_success_frac=(view["qp_status"] == 0).double().mean().item(),
+                    qpik_active_set_frac=(view["nwsr"] > 0).double().mean().item())
 
-    def mk_io():
-        return dict(dq=torch.empty(23, B, dtype=torch.float64).pin_memory(), lf_err=torch.empty(6, B, dtype=torch.float64).pin_memory(),
-                    rf_err=torch.empty(6, B, dtype=torch.float64).pin_memory(), status=torch.empty(B, dtype=torch.int32).pin_memory(),
-                    nwsr=torch.empty(B, dtype=torch.int32).pin_memory())
+    # ---------------- arm 3: end to end through the host-pointer C ABI (wc_tick_host_async, pinned host buffers): the
+    # recorded closed-loop ticks replayed by a host that uploads every tick's inputs and reads every tick's results back
+    mpc2 = wc.MpcBatch(mcfg_cl, B, device=local_rank)
+    ik2 = wc.IkBatch(icfg_cl, model, B, device=local_rank)
 
-    h_mos, h_ios = [mk_mo(), mk_mo()], [mk_io(), mk_io()]   # two ticks in flight -> two result buffers
-    h_mo, h_io = h_mos[0], h_ios[0]
-    h2d = sum(v.numel() * v.element_size() for v in h_mpc[0]) + sum(v.numel() * v.element_size() for v in h_ik[0].values())
-    d2h = sum(v.numel() * v.element_size() for v in h_mo.values()) + sum(v.numel() * v.element_size() for v in h_io.values())
+    def mk_out():
+        e = lambda *shape, dt=torch.float64: torch.empty(*shape, dtype=dt).pin_memory()
+        return dict(zmp=e(2, B), osqp_status=e(B, dt=torch.int32), iters=e(B, dt=torch.int32), flags=e(B, dt=torch.int32),
+                    dq=e(23, B), lf_err=e(6, B), rf_err=e(6, B), qp_status=e(B, dt=torch.int32), nwsr=e(B, dt=torch.int32))
+
+    h_outs = [mk_out(), mk_out()]   # two ticks in flight -> two result buffers
+    h2d = sum(v.numel() * v.element_size() for k, v in h_in[1].items())
+    d2h = sum(v.numel() * v.element_size() for v in h_outs[0].values())
+    e2e_match = True
+
     def submit(t):
-        # both blocks go through the host-pointer C ABI (H2D, kernels, D2H on each handle's upload / compute / download
-        # streams).  Staging is double-buffered, so two ticks are in flight: the upload of tick t+1 and the download of
-        # tick t-1 overlap the kernels of tick t, and the IK inputs upload while the MPC kernels run.
-        a = h_mpc[t]
-        mpc2.tick_host_async(a[0], a[1], a[2], a[3], a[4], a[5], out=h_mos[t % 2])
-        ik.tick_host_async(h_ik[t % len(h_ik)], out=h_ios[t % 2])
+        # one packed upload for both blocks (shared feet transforms, stance base selected on the device, one DCM sample per
+        # tick), MPC and IK kernels on the handle's two kernel streams, one download.  Staging is double-buffered: the upload
+        # of tick t+1 and the download of tick t-1 overlap the kernels of tick t.
+        mpc2.tick_fused_host_async(ik2, h_in[t], h_outs[t % 2])
 
-    def retire():
-        mpc2.sync_one(); ik.sync_one()   # results of the oldest tick in flight are now in its pinned host buffers
+    def retire(t):
+        nonlocal e2e_match
+        mpc2.sync_one()   # results of tick t are now in its pinned host buffers
+        if t < e2e_warm:  # (outside the timed region) the replay reproduces the closed loop bit for bit
+            zc, dc = cl_out[t]
+            e2e_match = e2e_match and torch.equal(h_outs[t % 2]["zmp"], zc.cpu()) and torch.equal(h_outs[t % 2]["dq"], dc.cpu())
 
     for t in range(e2e_warm):
         submit(t)
         if t >= 1:
-            retire()
-    mpc2.sync(); ik.sync()
+            retire(t - 1)
+    mpc2.sync()
     barrier()
     t0 = time.perf_counter()
     for k in range(e2e_steps):
         submit(e2e_warm + k)
         if k >= 1:
-            retire()
-    mpc2.sync(); ik.sync()
+            mpc2.sync_one()
+    mpc2.sync()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    zc, dc = cl_out[Te - 1]
+    e2e_match = e2e_match and torch.equal(h_outs[(Te - 1) % 2]["zmp"], zc.cpu()) and torch.equal(h_outs[(Te - 1) % 2]["dq"], dc.cpu())
     e = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e, op=dist.ReduceOp.MAX)
@@ -441,15 +508,15 @@ def run_ours(args, world, rank, local_rank):
         osqp_ms = timed(f_osqp)
         osqp_it = o2["o"]["nwsr"].double().mean().item(); osqp_ok = (o2["o"]["status"] == 1).double().mean().item()
         ik2.close()
-        tj = wc.TrajBatch(wc.traj_default_config(T, N), B, device=local_rank)
-        tj.set_gait(g.step_len, g.phase.to(torch.int32), g.dtheta, g.theta0, g.first_left.to(torch.uint8))
+        tj2 = wc.TrajBatch(wc.traj_default_config(T, N), B, device=local_rank)
+        tj2.set_gait(g.step_len, g.phase.to(torch.int32), g.dtheta, g.theta0, g.first_left.to(torch.uint8))
         tb = {}
         def f_traj(k):
-            tb["f"] = tj.feet(k, out=tb.get("f"))
-            tb["p"], _ = tj.dcm(k, N + 1, pos=tb.get("p"), want_vel=False)
-            tb["m"] = tj.measured_dcm(k, 0.002, 0x5EED, out=tb.get("m"))
+            tb["f"] = tj2.feet(k, out=tb.get("f"))
+            tb["p"], _ = tj2.dcm(k, N + 1, pos=tb.get("p"), want_vel=False)
+            tb["m"] = tj2.measured_dcm(k, 0.002, 0x5EED, out=tb.get("m"))
         traj_ms = timed(f_traj)
-        tj.close()
+        tj2.close()
         gl = wc.GlueBatch(wc.glue_default_config(), B, device=local_rank)
         z2 = torch.zeros(2, B, dtype=torch.float64, device=dev); c3 = torch.zeros(3, B, dtype=torch.float64, device=dev)
         gb = {}
@@ -475,9 +542,17 @@ def run_ours(args, world, rank, local_rank):
         prep_avg_ms = prep_ms / max(nt, 1)
         # dominant kernel: the ADMM pass every instance goes through (chain path: phase 1; cooperative path: the
         # single ADMM kernel).  Its algorithmic bytes are the MPC share of SURVEY §8(d): (128 N + 464) B per instance.
-        dom_name = "mpc_chain_kernel<phase 1>" if mpc.path == "chain" else "mpc_admm_kernel"
+        dom_name = {"split": "mpc_split_kernel<phase 1>", "chain": "mpc_chain_kernel<phase 1>"}.get(mpc.path, "mpc_admm_kernel")
         dom_ms = phase1_ms / max(nt, 1)
         achieved = bt["mpc"] * B / (dom_ms * 1e-3) * 1e-9
+        at_capture_size = B == B_PER_GPU and N == HORIZON
+        # shared-memory pipe of the dominant kernel: wavefronts counted by ncu (l1tex__data_pipe_lsu_wavefronts_mem_shared.sum of
+        # the committed capture, one wavefront = one 128-byte pass of the crossbar) over the kernel time measured HERE
+        wf = ncu_counter(dom_name, "smem_wavefronts_per_launch") if at_capture_size else None
+        smem_peak = 128 * 148 * (clocks["sm_max_mhz"] or 1965.0) * 1e-3 if clocks else 128 * 148 * 1.965
+        smem_ach = wf * 128 / (dom_ms * 1e-3) * 1e-9 if wf else None
+        # FP64 roofline of the same kernel with the flop model of SURVEY 8(d): iterations x F_iter(N) per instance
+        f_p1 = flops_per_tick(N, float(P1_ITERS if mpc.path != "coop" else it_mean), 0.0, 0.0)[0]
         fast_on = ik_fast_ms > 0 and ik_general_ms > 0
         f_mpc, f_ik = flops_per_tick(N, it_mean, 0.0, wsc_mean, slow_frac=(ik_general_n / B) if fast_on else 1.0,
                                      second_frac=(ik_second / B) if fast_on else 0.0)
@@ -486,7 +561,8 @@ def run_ours(args, world, rank, local_rank):
             "metric": METRIC, "value": value, "unit": "ticks/s", "n_gpus": world, "steps": steps,
             "warmup": warm, "ms_per_step": total_ms_max / steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": dict(workload_config(world, B, N), mpc_path=mpc.path, **({"rank_cpu_affinity": numa_cpus} if world > 1 else {})),
+            "config": workload_config(world, B, N),
+            "mpc_path": mpc.path, **({"rank_cpu_affinity": numa_cpus} if world > 1 else {}),
             "tick_latency_ms": {"p50": pct(step_ms, 0.5), "p99": pct(step_ms, 0.99), "max": max(step_ms)},
             "kernels_ms": {"mpc_prepare": prep_avg_ms, "mpc_admm": admm_avg_ms, "fk_qpik": ik_avg_ms,
                            "mpc_setup": setup_ms / max(nt, 1), "mpc_phase1": phase1_ms / max(nt, 1),
@@ -498,17 +574,23 @@ def run_ours(args, world, rank, local_rank):
                       "qpik_second_pass_frac": ik_second / B, "qpik_general_kernel_frac": ik_general_n / B},
             "roofline": {"bound": "hbm", "kernel": dom_name, "kernel_ms": dom_ms, "achieved": achieved, "peak": hbm_peak,
                          "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": ncu_traffic(dom_name) if (B == B_PER_GPU and N == HORIZON) else None,
+                         "traffic": ncu_counter(dom_name) if at_capture_size else None,
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": bt["mpc"] * B,
-                         "note": "the path is not HBM bound (DESIGN.md §5): phase 1 is bound by the shared-memory pipe, see smem / fp64; "
-                                 "traffic exceeds the algorithmic bytes because the LDL' factors and the scaling vectors are "
-                                 "staged from HBM each tick instead of being recomputed"},
-            # shared-memory roofline of the dominant kernel: 650 LDS/STS.64 per thread-iteration
-            "smem": {"bound": "shared memory", "achieved": 650 * 8 * 2 * B * P1_ITERS / (dom_ms * 1e-3) * 1e-9 if mpc.path == "chain" else None,
-                     "peak": 128 * 148 * 1.965, "unit": "GB/s",
-                     "frac": (650 * 8 * 2 * B * P1_ITERS / (dom_ms * 1e-3) * 1e-9) / (128 * 148 * 1.965) if mpc.path == "chain" else None,
-                     "peak_source": "128 B/clk/SM x 148 SMs x 1.965 GHz (B300_MICROARCH.md smem crossbar), N = 25 access count"},
+                         "note": "the path is not HBM bound (DESIGN.md §5): ~5 KB of compulsory traffic against ~0.12 Mflop of "
+                                 "fp64 in dependent chains per instance-tick; see roofline_fp64 / smem.  traffic exceeds the "
+                                 "algorithmic bytes by the Ruiz scaling vectors (D, 1/D, E, 1/E), read every tick"},
+            "roofline_fp64": {"bound": "fp64", "kernel": dom_name, "kernel_ms": dom_ms,
+                              "achieved": f_p1 * B / (dom_ms * 1e-3) * 1e-12, "peak": fp64_peak * 1e-3, "unit": "TFLOP/s",
+                              "frac": f_p1 * B / (dom_ms * 1e-3) * 1e-9 / fp64_peak,
+                              "flops_per_launch": f_p1 * B,
+                              "peak_source": "measured here: wc_measure_fp64_peak, register-resident FMA chains on all SMs "
+                                             "(MEASURED_PEAKS.json has no FP64 entry)",
+                              "model": "SURVEY 8(d): iterations x (4 nnz(A) + 21 n + 12 (n + m)) flops per instance"},
+            "smem": {"bound": "shared memory", "kernel": dom_name, "achieved": smem_ach, "peak": smem_peak, "unit": "GB/s",
+                     "frac": smem_ach / smem_peak if smem_ach else None, "wavefronts_per_launch": wf,
+                     "peak_source": "128 B/clk/SM x 148 SMs x SM clock (B300_MICROARCH.md smem crossbar); wavefronts from the "
+                                    "committed ncu capture (profiles/ncu_traffic.json)"},
             "fp64": {"peak_gflops_measured": fp64_peak,
                      "mpc_admm_gflops": f_mpc * B / (admm_avg_ms * 1e-3) * 1e-9,
                      "fk_qpik_gflops": f_ik * B / (ik_avg_ms * 1e-3) * 1e-9,
@@ -516,7 +598,14 @@ def run_ours(args, world, rank, local_rank):
                      "fk_qpik_frac": f_ik * B / (ik_avg_ms * 1e-3) * 1e-9 / fp64_peak,
                      "flops_per_tick_model": {"mpc": f_mpc, "ik": f_ik}},
             "e2e": {"value": world * B * e2e_steps / e2e_s, "unit": "ticks/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3},
+                    "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3,
+                    "api": "wc_tick_host_async (fused MPC + FK/QP-IK host tick, pinned buffers, two ticks in flight)",
+                    "workload": "the inputs of a recorded closed-loop rollout (wc_loop_*), uploaded tick by tick",
+                    "matches_closed_loop_bitwise": bool(e2e_match)},
+            # the closed-loop tick with the true MPC -> ZMP-CoM law -> IK dependence, one CUDA-graph replay per tick
+            "closed_loop": {"value": world * B * cl_steps / (cl_ms * 1e-3), "unit": "ticks/s", "ms_per_tick": cl_ms / cl_steps,
+                            "steps": cl_steps, "api": "wc_loop_run_dev (CUDA graph)", "stats": cl_stats,
+                            "workload": f"periodic walking from the prepared posture, LIPM height {h_cl} m, |dq| <= {syn.CL_VMAX} rad/s"},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
@@ -527,7 +616,7 @@ def run_ours(args, world, rank, local_rank):
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline_leg(N)
         print(json.dumps(line), flush=True)
-    mpc.close(); mpc2.close(); ik.close()
+    loop.close(); mpc.close(); mpc2.close(); ik.close(); ik2.close(); mpc_cl.close(); ik_cl.close(); glue.close(); tj.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

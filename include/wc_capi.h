@@ -63,7 +63,8 @@ enum {
  * (WalkingDCMModelPredictiveController.cpp:364-435,491-521). */
 enum {
     WC_MPC_FLAG_OK = 0,
-    WC_MPC_FLAG_NO_CONTACT = 1,   /* (false,false) contact pair: "None foot is in contact" (:404-408) */
+    WC_MPC_FLAG_NO_CONTACT = 1,   /* (false,false) contact pair: "None foot is in contact" (:404-408); raised on EVERY
+                                     tick without contact (the reference stops at the first), nothing is solved */
     WC_MPC_FLAG_NO_SOLVER = 2,    /* no MPCSolver exists yet (reference would dereference null) */
     WC_MPC_FLAG_NOT_SOLVED = 4,   /* OsqpEigen::Solver::solve() false: a non-convex problem, or -- with
                                      osqp_eigen_checks_status -- any status but OSQP_SOLVED; the output keeps m_output */
@@ -635,6 +636,9 @@ typedef struct wc_loop_view {
     const double *lf_H, *rf_H, *ref_pos;            /* producer outputs of the tick: [12*B], [12*B], [(N+1)*2*B] */
     const int32_t *osqp_status, *iters, *flags;     /* MPC outputs [B] */
     const int32_t *qp_status, *nwsr;                /* QP-IK outputs [B] */
+    /* the remaining inputs the two blocks consumed in that tick (what a host that feeds them would have uploaded) */
+    const double *lf_twist, *rf_twist, *base_H, *neck_R_des;   /* [6*B], [6*B], [12*B], [9*B] */
+    const uint8_t *l_contact, *r_contact, *left_is_fixed;      /* [B] */
 } wc_loop_view;
 wc_status wc_loop_view_get(wc_loop* h, wc_loop_view* view);
 

@@ -244,9 +244,15 @@ int wco_mpc_tick(wco_mpc* c, const double* lf_H, const double* rf_H, int l_conta
     if (iters) *iters = 0;
 
     /* ---- setConvexHullConstraint (Controller.cpp:364-435) */
+    /* "None foot is in contact" (:404-408) returns false and the module stops; it has no defined behaviour for a second
+     * tick without contact (m_feetStatus would compare equal and the stale hull be solved).  Restated as: flagged on
+     * EVERY tick without contact, nothing solved (wc_capi.h WC_MPC_FLAG_NO_CONTACT). */
+    if (!l_contact && !r_contact) {
+        c->feet_left = 0; c->feet_right = 0;
+        return WC_MPC_FLAG_NO_CONTACT;
+    }
     if (!(c->feet_left == l_contact && c->feet_right == r_contact)) {
         c->feet_left = l_contact; c->feet_right = r_contact;
-        if (!l_contact && !r_contact) return WC_MPC_FLAG_NO_CONTACT;
         double pts[16];
         int npts = 0;
         if (l_contact && r_contact) { foot_points(c, lf_H, pts); foot_points(c, rf_H, pts + 8); npts = 8; }

@@ -38,9 +38,45 @@ def test_lipm_tracks_constant_dcm(oracle):
     for k in range(300):
         out = g.com_reference(xi, z, z, cm)
         v = -omega * (c - xi); c = c + (v + v_old) * ts / 2; v_old = v
-        # ZMP-CoM law with zero ZMP error and com_meas = 0: vd = kCoM c + v
-        assert np.allclose(out["com_vel_des"][:2], cfg.k_com * c + v, rtol=1e-13, atol=1e-15)
+        # ZMP-CoM law with zero ZMP error and com_meas = 0: vd = kCoM c + v; setPhase is never called, so the scheduled
+        # gain stays where WalkingZMPController::initialize leaves it: the stance value (WalkingZMPController.cpp:82-83)
+        kc = cfg.k_com_stance if cfg.use_gain_scheduling else cfg.k_com
+        assert np.allclose(out["com_vel_des"][:2], kc * c + v, rtol=1e-13, atol=1e-15)
     assert np.abs(c - xi).max() < 1e-4
+
+
+def test_gain_schedule_smoother(oracle):
+    """WalkingZMPController::setPhase with the restated minJerkTrajGen: the gains start at the stance values, move to the
+    walking values when the phase flips, reach 90 % of the step after the smoothing time (the filter's design point), settle
+    with unit DC gain, and the two smoothers are the same filter (their normalised responses coincide)."""
+    cfg = oracle.glue_default_config()
+    assert cfg.use_gain_scheduling == 1 and cfg.smoothing_time == 0.05            # zmpControllerParams.ini:2,4
+    assert (cfg.k_zmp, cfg.k_com, cfg.k_zmp_stance, cfg.k_com_stance) == (3.0, 9.0, 0.9, 6.0)
+    B = 2
+    g = oracle.GlueBatch(cfg, B)
+    z = np.zeros((2, B)); c = np.ones((2, B)); cm = np.zeros((3, B))
+    g.reset(com_xy=c)
+
+    # drive: stance flag for instance 0 stays 1 (gains stay at stance), instance 1 walks from tick 0
+    stance = np.array([1, 0], np.uint8)
+    ks = []
+    for k in range(60):
+        g.set_phase(stance=stance)
+        out = g.com_reference(c, z, z, cm)          # dcm_des = c_lipm = 1 -> v = 0, vd = kCoM * 1
+        ks.append(out["com_vel_des"][0].copy())
+    ks = np.array(ks)
+    assert np.allclose(ks[:, 0], cfg.k_com_stance, rtol=1e-12)                      # unit DC gain at rest
+    step = (ks[:, 1] - cfg.k_com_stance) / (cfg.k_com - cfg.k_com_stance)
+    n_T = int(round(cfg.smoothing_time / cfg.sampling_time))
+    assert 0.85 < step[n_T - 1] < 0.95, step[:8]                                    # ~90 % of the step at t = T
+    assert np.all(np.diff(step[:n_T]) > 0) and abs(step[-1] - 1.0) < 1e-6          # monotone rise, settles at the target
+    # the velocity-threshold rule of updateModule: |dcm_vel_des| < 0.001 <=> stance
+    g2 = oracle.GlueBatch(cfg, B); g2.reset(com_xy=c)
+    vel = np.array([[0.0005, 0.002], [0.0, 0.0]])
+    for k in range(60):
+        g2.set_phase(dcm_vel_des=vel)
+        out2 = g2.com_reference(c, z, z, cm)
+    assert np.allclose(out2["com_vel_des"][0], [cfg.k_com_stance, cfg.k_com], rtol=1e-6)
 
 
 @pytest.mark.gpu
@@ -57,6 +93,8 @@ def test_glue_gpu_parity(wc, oracle, cuda_device):
         dcm = rng.normal(size=(2, B)) * 0.05; zd = rng.normal(size=(2, B)) * 0.05; zm = zd + rng.normal(size=(2, B)) * 0.01
         cm = rng.normal(size=(3, B)) * 0.05; hz = 0.53 + rng.normal(size=B) * 0.001; hv = rng.normal(size=B) * 0.01
         use_k = t % 2 == 0
+        vel = rng.normal(size=(2, B)) * 0.0012   # about half of the instances below the 0.001 stance threshold
+        go.set_phase(dcm_vel_des=vel); gg.set_phase(dcm_vel_des=d(vel))
         oo = go.com_reference(dcm, zd, zm, cm, hz, hv, kz if use_k else None, kc if use_k else None)
         og = gg.com_reference(d(dcm), d(zd), d(zm), d(cm), d(hz), d(hv), d(kz) if use_k else None, d(kc) if use_k else None)
         dq = rng.normal(size=(nJ, B))
@@ -66,7 +104,7 @@ def test_glue_gpu_parity(wc, oracle, cuda_device):
         assert np.abs(og["com_pos_des"].cpu().numpy() - oo["com_pos_des"]).max() <= 1e-13
         assert np.abs(og["com_vel_des"].cpu().numpy() - oo["com_vel_des"]).max() <= 1e-13
         assert np.abs(qg.cpu().numpy() - qo).max() <= 1e-13
-    assert gg.launches == 1 + 2 * T
+    assert gg.launches == 1 + 3 * T
     gg.close()
 
 

@@ -145,8 +145,8 @@ def test_mpc_no_contact_and_reset(wc, syn, oracle, cuda_device):
     for t in range(8):
         f = g.feet(t)
         lc = f["l_contact"].numpy().copy(); rc = f["r_contact"].numpy().copy()
-        if t in (0, 4):
-            lc[:3] = 0; rc[:3] = 0       # "None foot is in contact" (Controller.cpp:404-408)
+        if t in (0, 4, 5):
+            lc[:3] = 0; rc[:3] = 0       # "None foot is in contact" (Controller.cpp:404-408), also on two consecutive ticks
         if t == 6:
             mo.reset(np.array([1, 0] * 4, np.uint8)); mg.reset(np.array([1, 0] * 4, np.uint8))
         dcm = g.measured_dcm(t).numpy(); ref = traj[2 * t: 2 * t + 2 * (N + 1)].contiguous().numpy()

@@ -47,7 +47,8 @@ class LoopConfig(C.Structure):
 LOOP_VIEW = (("zmp", 2, "f8"), ("dq", "nJ", "f8"), ("q_des", "nJ", "f8"), ("com_pos_des", 3, "f8"), ("com_vel_des", 3, "f8"),
              ("com_meas", 3, "f8"), ("dcm_meas", 2, "f8"), ("lf_err", 6, "f8"), ("rf_err", 6, "f8"), ("lf_H", 12, "f8"),
              ("rf_H", 12, "f8"), ("ref_pos", "2N", "f8"), ("osqp_status", 1, "i4"), ("iters", 1, "i4"), ("flags", 1, "i4"),
-             ("qp_status", 1, "i4"), ("nwsr", 1, "i4"))
+             ("qp_status", 1, "i4"), ("nwsr", 1, "i4"), ("lf_twist", 6, "f8"), ("rf_twist", 6, "f8"), ("base_H", 12, "f8"),
+             ("neck_R_des", 9, "f8"), ("l_contact", 1, "u1"), ("r_contact", 1, "u1"), ("left_is_fixed", 1, "u1"))
 
 
 class LoopView(C.Structure):
@@ -855,7 +856,8 @@ class _DevArray:
     """a raw device pointer as a CUDA-array-interface object (torch.as_tensor wraps it without a copy)"""
 
     def __init__(self, ptr, shape, typestr):
-        self.__cuda_array_interface__ = {"shape": shape, "typestr": "<" + typestr, "data": (ptr, False), "version": 2}
+        self.__cuda_array_interface__ = {"shape": shape, "typestr": ("|" if typestr == "u1" else "<") + typestr,
+                                         "data": (ptr, False), "version": 2}
 
 
 class LoopBatch:
@@ -910,7 +912,7 @@ class LoopBatch:
             out = {}
             for k, rows, ts in LOOP_VIEW:
                 r = self.nJ if rows == "nJ" else (2 * (self.N + 1) if rows == "2N" else rows)
-                shape = (self.B,) if (ts == "i4") else (r, self.B)
+                shape = (self.B,) if ts in ("i4", "u1") else (r, self.B)
                 out[k] = torch.as_tensor(_DevArray(getattr(v, k), shape, ts), device=f"cuda:{self.device}")
             self._view = out
         return self._view

@@ -81,9 +81,19 @@ __global__ void __launch_bounds__(128) mpc_prepare_kernel(MpcDev d, MpcTickIO io
     const int N = d.N, nR = N + 1;
     const uint8_t cur = (uint8_t)((io.l_contact[i] ? 1 : 0) | (io.r_contact[i] ? 2 : 0));
     int flags = 0;
+    // "None foot is in contact" (Controller.cpp:404-408): the reference returns false on the tick of the transition AND,
+    // because m_feetStatus then equals (false, false), keeps solving with the stale hull on the following no-contact ticks.
+    // Here the instance is flagged on every tick without contact and not solved: a ring slot that was never refreshed and
+    // a stale hull must not produce an output that looks valid.  inited = 0 forces a full gradient refresh (and a new OSQP
+    // workspace) when contact returns, as the reference's new MPCSolver after the next phase change does.
+    if (cur == 0) {
+        d.feet[i] = cur;
+        d.inited[i] = 0;
+        d.tick_flags[i] = WC_MPC_FLAG_NO_CONTACT;
+        return;
+    }
     if (cur != d.feet[i]) {
         d.feet[i] = cur;
-        if (cur == 0) { d.tick_flags[i] = WC_MPC_FLAG_NO_CONTACT; return; }
         double pts[8][2], A[16], b[8], v[16];
         int npts = 0;
         if (cur == 3) { foot_points(d, io.lf_H, B, i, pts); foot_points(d, io.rf_H, B, i, pts + 4); npts = 8; }

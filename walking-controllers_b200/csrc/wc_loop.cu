@@ -284,6 +284,8 @@ wc_status wc_loop_view_get(wc_loop* h, wc_loop_view* v)
     v->com_meas = h->com_meas; v->dcm_meas = h->dcm_meas; v->lf_err = h->lf_err; v->rf_err = h->rf_err;
     v->osqp_status = h->osqp_status; v->iters = h->iters; v->flags = h->flags; v->qp_status = h->qp_status; v->nwsr = h->nwsr;
     v->lf_H = h->lf_H; v->rf_H = h->rf_H; v->ref_pos = h->ref_pos;
+    v->lf_twist = h->lf_tw; v->rf_twist = h->rf_tw; v->base_H = h->base_H; v->neck_R_des = h->neck_R;
+    v->l_contact = h->l_contact; v->r_contact = h->r_contact; v->left_is_fixed = h->lif;
     return WC_OK;
 }
 
