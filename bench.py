@@ -265,6 +265,141 @@ def pin_to_gpu_numa_node(gpu_index):
         return None
 
 
+def build_closed_loop(wc, syn, torch, g, B, N, n_ticks, dev, local_rank, mpc_settings=None):
+    """The closed-loop workload (synthetic.py CL_*): producer + MPC + glue + IK handles on the gait of `g`, the posture of
+    syn.prepare_posture, a wc_loop handle over them.  Returns (loop, handles, configs)."""
+    h_cl = syn.CL_COM_HEIGHT
+    tcfg = wc.traj_default_config(n_ticks + 8, N); tcfg.com_height = h_cl
+    mcfg_cl = wc.mpc_default_config(N); mcfg_cl.com_height = h_cl
+    for k, v in (mpc_settings or {}).items():
+        if k == "hull_tolerance":
+            mcfg_cl.hull_tolerance = v
+        else:
+            setattr(mcfg_cl.osqp, k, v)
+    gcfg = wc.glue_default_config(); gcfg.com_height = h_cl
+    icfg_cl, icfg_open = wc.ik_default_config(), wc.ik_default_config()
+    for j in range(23):
+        icfg_cl.min_vel[j], icfg_cl.max_vel[j] = -syn.CL_VMAX, syn.CL_VMAX
+        icfg_open.min_vel[j], icfg_open.max_vel[j] = -50.0, 50.0
+    model = wc.model_icub_like()
+    qreg = torch.tensor(list(icfg_cl.joint_reg_rad[:23]), dtype=torch.float64)
+    tj = wc.TrajBatch(tcfg, B, device=local_rank)
+    tj.set_gait(g.step_len, g.phase.to(torch.int32), g.dtheta, g.theta0, g.first_left.to(torch.uint8))
+    ik_open = wc.IkBatch(icfg_open, model, B, device=local_rank)
+    f0 = tj.feet(0); ref0, _ = tj.dcm(0, 1, want_vel=False)
+    tgt = torch.cat([ref0[0:2], torch.full((1, B), h_cl, dtype=torch.float64, device=dev)], 0).contiguous()
+    q0 = syn.prepare_posture(lambda q, b, l: ik_open.fk(q, b, l, jacobians=False), lambda inp: ik_open.tick(inp), qreg, f0, tgt)
+    torch.cuda.synchronize()
+    ik_open.close()
+    mpc_cl = wc.MpcBatch(mcfg_cl, B, device=local_rank)
+    ik_cl = wc.IkBatch(icfg_cl, model, B, device=local_rank)
+    glue = wc.GlueBatch(gcfg, B, device=local_rank)
+    loop = wc.LoopBatch(mpc_cl, ik_cl, glue, tj, device=local_rank)
+    return loop, (mpc_cl, ik_cl, glue, tj), (mcfg_cl, icfg_cl, model), q0
+
+
+MC_METRIC = "MPC+QP-IK controller ticks/sec, Monte-Carlo push / gain sweep at B=524288 iCub instances (closed loop)"
+
+
+def run_mc_push(args, world, rank, local_rank):
+    """--config mc_push: BASELINE configs[3].  524 288 instances in total, sharded over the ranks; every instance runs the
+    closed-loop tick (wc_loop_*) with its own Q, R, k_posFoot, k_attFoot and one impulsive DCM push U(0, 0.06) m in a random
+    direction at a random tick.  Results and statistics are collected with NCCL after the timed region."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    wc = importlib.import_module("walking-controllers_b200")
+    syn = importlib.import_module("walking-controllers_b200.synthetic")
+    wc.lib()
+    dev = torch.device(f"cuda:{local_rank}")
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    total = args.batch if args.batch != B_PER_GPU else 524288
+    B, N = total // world, args.horizon
+    steps, warm = args.steps, args.warmup
+    T = warm + steps
+    g = syn.GaitBatch(B, T, N, seed=0x5EED + rank, device=dev)
+    loop, handles, (mcfg_cl, icfg_cl, model), q0 = build_closed_loop(wc, syn, torch, g, B, N, T, dev, local_rank)
+    mpc_cl, ik_cl, glue, tj = handles
+    rng = np.random.default_rng(0xC0FF + rank)
+    q = 7500.0 * rng.choice([0.1, 0.3, 1, 3, 10], size=B); r = 9e6 * rng.choice([0.1, 1, 10], size=B)
+    mpc_cl.set_weights(np.ascontiguousarray(np.stack([q, q])), np.ascontiguousarray(np.stack([r, r])))
+    ik_cl.set_gains(np.ascontiguousarray(rng.choice([2.5, 4.0, 7.0], size=B)), np.ascontiguousarray(rng.choice([2.0, 5.0], size=B)))
+    mag = rng.uniform(0, 0.06, B); ang = rng.uniform(0, 2 * np.pi, B)
+    loop.set_push(torch.from_numpy(rng.integers(0, T, B).astype(np.int32)).to(dev),
+                  torch.from_numpy(np.ascontiguousarray(np.stack([mag * np.cos(ang), mag * np.sin(ang)]))).to(dev))
+    loop.reset(q0)
+    view = loop.view()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    # tails are tallied on the device, tick by tick, outside the graph (a handful of small torch kernels per tick)
+    tally = torch.zeros(5, dtype=torch.float64, device=dev)  # not SOLVED, outside hull, IK infeasible, active set, iterations
+
+    def tick_and_tally():
+        loop.run(1)
+        tally[0] += (view["osqp_status"] != 1).sum(); tally[1] += ((view["flags"] & 8) != 0).sum()
+        tally[2] += (view["qp_status"] != 0).sum(); tally[3] += (view["nwsr"] > 0).sum(); tally[4] += view["iters"].sum()
+
+    for t in range(warm):
+        tick_and_tally()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    loop.run(steps)
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    tally[0] += (view["osqp_status"] != 1).sum(); tally[1] += ((view["flags"] & 8) != 0).sum()
+    tally[2] += (view["qp_status"] != 0).sum(); tally[3] += (view["nwsr"] > 0).sum(); tally[4] += view["iters"].sum()
+    gather_ms = None
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        res = torch.cat([view["zmp"], view["dq"]], 0).contiguous()
+        outbuf = [torch.empty_like(res) for _ in range(world)] if rank == 0 else None
+        warmbuf = [torch.empty(8, device=dev) for _ in range(world)] if rank == 0 else None
+        dist.gather(torch.zeros(8, device=dev), warmbuf, dst=0)
+        torch.cuda.synchronize(); dist.barrier(); t0 = time.perf_counter()
+        dist.gather(res, outbuf, dst=0)
+        dist.all_reduce(tally, op=dist.ReduceOp.SUM)
+        torch.cuda.synchronize(); gather_ms = (time.perf_counter() - t0) * 1e3
+    ms = ms.item()
+    if rank == 0:
+        n_tallied = float(world * B * (warm + 1))
+        tl = tally.tolist()
+        line = {"metric": MC_METRIC, "value": world * B * steps / (ms * 1e-3), "unit": "ticks/s", "n_gpus": world, "steps": steps,
+                "warmup": warm, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "Monte-Carlo push-disturbance / gain sweep in closed loop (BASELINE configs[3])",
+                           "instances_per_gpu": B, "instances_total": world * B, "horizon": N,
+                           "sweep": "Q in 7500 x {0.1, 0.3, 1, 3, 10}, R in 9e6 x {0.1, 1, 10}, k_posFoot in {2.5, 4, 7}, "
+                                    "k_attFoot in {2, 5}; push U(0, 0.06) m, random direction, random tick",
+                           "l2": "solver state 10 KB x instances exceeds the 126 MB L2"},
+                "tails": {"ticks_tallied_per_instance": warm + 1, "osqp_not_solved_frac": tl[0] / n_tallied,
+                          "outside_hull_frac": tl[1] / n_tallied, "qpik_infeasible_frac": tl[2] / n_tallied,
+                          "qpik_active_set_frac": tl[3] / n_tallied, "osqp_iters_mean": tl[4] / n_tallied,
+                          "note": "tallied on the warm-up ticks and the last timed tick (the timed ticks are one graph replay each); "
+                                  "parity of every tail against the oracle: tests/test_closed_loop.py"},
+                "gpu_launches": int(steps), "api": "wc_loop_run_dev (one CUDA-graph replay per tick)", "clocks": clocks}
+        if gather_ms is not None:
+            line["nccl_gather_ms"] = gather_ms
+        print(json.dumps(line), flush=True)
+    loop.close()
+    for h in handles:
+        h.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def run_ours(args, world, rank, local_rank):
     import numpy as np
     import torch
@@ -379,25 +514,8 @@ def run_ours(args, world, rank, local_rank):
     e2e_warm = min(warm, 5)
     Te = e2e_steps + e2e_warm
     cl_steps = min(steps, 200)
-    tcfg = wc.traj_default_config(Te + warm + cl_steps + 8, N); tcfg.com_height = h_cl
-    mcfg_cl = wc.mpc_default_config(N); mcfg_cl.com_height = h_cl
-    gcfg = wc.glue_default_config(); gcfg.com_height = h_cl
-    icfg_cl, icfg_open = wc.ik_default_config(), wc.ik_default_config()
-    for j in range(23):
-        icfg_cl.min_vel[j], icfg_cl.max_vel[j] = -syn.CL_VMAX, syn.CL_VMAX
-        icfg_open.min_vel[j], icfg_open.max_vel[j] = -50.0, 50.0
-    tj = wc.TrajBatch(tcfg, B, device=local_rank)
-    tj.set_gait(g.step_len, g.phase.to(torch.int32), g.dtheta, g.theta0, g.first_left.to(torch.uint8))
-    ik_open = wc.IkBatch(icfg_open, model, B, device=local_rank)
-    f0 = tj.feet(0); ref0, _ = tj.dcm(0, 1, want_vel=False)
-    tgt = torch.cat([ref0[0:2], torch.full((1, B), h_cl, dtype=torch.float64, device=dev)], 0).contiguous()
-    q0 = syn.prepare_posture(lambda q, b, l: ik_open.fk(q, b, l, jacobians=False), lambda inp: ik_open.tick(inp), qreg, f0, tgt)
-    torch.cuda.synchronize()
-    ik_open.close()
-    mpc_cl = wc.MpcBatch(mcfg_cl, B, device=local_rank)
-    ik_cl = wc.IkBatch(icfg_cl, model, B, device=local_rank)
-    glue = wc.GlueBatch(gcfg, B, device=local_rank)
-    loop = wc.LoopBatch(mpc_cl, ik_cl, glue, tj, device=local_rank)
+    loop, (mpc_cl, ik_cl, glue, tj), (mcfg_cl, icfg_cl, _), q0 = build_closed_loop(wc, syn, torch, g, B, N, Te + warm + cl_steps,
+                                                                                    dev, local_rank)
     loop.reset(q0)
     view = loop.view()
 
@@ -631,7 +749,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extras", action="store_true", help="skip the timings of the SURVEY 8(f) rows (next_rows)")
     ap.add_argument("--horizon", type=int, default=HORIZON, help="MPC horizon N (default: BASELINE configs[2], 25)")
-    ap.add_argument("--batch", type=int, default=B_PER_GPU, help="instances per GPU (default 65536)")
+    ap.add_argument("--batch", type=int, default=B_PER_GPU, help="instances per GPU (default 65536; mc_push: in total, default 524288)")
+    ap.add_argument("--config", default="full_tick", choices=["full_tick", "mc_push"],
+                    help="full_tick = BASELINE configs[2] (the headline); mc_push = configs[3], Monte-Carlo push / gain sweep in closed loop")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -641,6 +761,9 @@ def main():
         args.warmup = 3
     if args.impl == "reference":
         run_reference(args, world, rank)
+        return
+    if args.config == "mc_push":
+        run_mc_push(args, world, rank, local_rank)
         return
     run_ours(args, world, rank, local_rank)
 

@@ -34,6 +34,8 @@ struct wco_mpc {
     double *gradient, *lower, *upper; /* MPCSolver::m_gradient / m_lowerBound / m_upperBound */
     double output[2];           /* m_output */
     int linsys_kind;
+    int hull_variant;           /* sensitivity studies only (tools/sensitivity_report.py): bit 0 = unit-normal rows,
+                                   bits 1.. = cyclic rotation of the row order (iDynTree's order / scaling is unknown) */
     int last_status, last_iter;
 };
 
@@ -230,6 +232,7 @@ void wco_mpc_set_weights(wco_mpc* c, const double q_diag[2], const double r_diag
 }
 
 void wco_mpc_set_linsys(wco_mpc* c, int kind) { c->linsys_kind = kind; }
+void wco_mpc_set_hull_variant(wco_mpc* c, int variant) { c->hull_variant = variant; }
 
 int wco_mpc_tick(wco_mpc* c, const double* lf_H, const double* rf_H, int l_contact, int r_contact,
                  const double* dcm, const double* ref, int reset_traj,
@@ -259,6 +262,19 @@ int wco_mpc_tick(wco_mpc* c, const double* lf_H, const double* rf_H, int l_conta
         else if (l_contact) { foot_points(c, lf_H, pts); npts = 4; }
         else { foot_points(c, rf_H, pts); npts = 4; }
         c->n_hull = wco_hull_build(pts, npts, c->hull_A, c->hull_b, c->hull_v);
+        if (c->hull_variant) { /* same polygon, rows re-ordered / re-scaled: what another hull builder might hand to OSQP */
+            const int nh = c->n_hull, rot = (c->hull_variant >> 1) % (nh > 0 ? nh : 1);
+            double A2[WCO_MAX_HULL * 2], b2[WCO_MAX_HULL], v2[WCO_MAX_HULL * 2];
+            for (i = 0; i < nh; i++) {
+                const int s = (i + rot) % nh;
+                double sc = 1.0;
+                if (c->hull_variant & 1) sc = 1.0 / sqrt(c->hull_A[2 * s] * c->hull_A[2 * s] + c->hull_A[2 * s + 1] * c->hull_A[2 * s + 1]);
+                A2[2 * i] = sc * c->hull_A[2 * s]; A2[2 * i + 1] = sc * c->hull_A[2 * s + 1]; b2[i] = sc * c->hull_b[s];
+                v2[2 * i] = c->hull_v[2 * s]; v2[2 * i + 1] = c->hull_v[2 * s + 1];
+            }
+            memcpy(c->hull_A, A2, sizeof(double) * 2 * (size_t)nh); memcpy(c->hull_b, b2, sizeof(double) * (size_t)nh);
+            memcpy(c->hull_v, v2, sizeof(double) * 2 * (size_t)nh);
+        }
         /* new MPCSolver (MPCSolver.cpp:16-52): zero gradient/bounds, hull lower bounds = -INFTY */
         wco_osqp_free(c->osqp);
         c->osqp = NULL;

@@ -191,12 +191,16 @@ def osqp_solve_dense(P, A, q, l, u, settings=None, linsys=0):
 class MpcBatch:
     """Batched oracle MPC with the same SoA layout as wc_mpc_tick_host (include/wc_capi.h)."""
 
-    def __init__(self, cfg, B, linsys=0):
+    def __init__(self, cfg, B, linsys=0, hull_variant=0):
         self.cfg, self.B, self.N = cfg, B, cfg.horizon
         self.h = lib().wco_mpc_batch_create(C.byref(cfg), B)
         if linsys:
             for i in range(B):
                 lib().wco_mpc_set_linsys(lib().wco_mpc_batch_get(self.h, i), linsys)
+        if hull_variant:  # sensitivity studies only: bit 0 = unit-normal hull rows, bits 1.. = cyclic rotation of their order
+            lib().wco_mpc_set_hull_variant.argtypes = [C.c_void_p, C.c_int]
+            for i in range(B):
+                lib().wco_mpc_set_hull_variant(lib().wco_mpc_batch_get(self.h, i), hull_variant)
 
     def __del__(self):
         if getattr(self, "h", None):
@@ -590,6 +594,7 @@ class ClosedLoop:
         self.sigma, self.seed, self.off, self.threads = sigma, seed, zmp_offset, threads
         self.t = 0
         self.push_tick = np.full(B, -1, np.int32); self.push_dxy = np.zeros((2, B))
+        self.ik_gains = None  # per-instance (k_posFoot, k_attFoot) of a gain sweep
 
     @staticmethod
     def _pre(f):
@@ -628,7 +633,8 @@ class ClosedLoop:
         inp = dict(q_meas=self.q, q_lin=self.q, base_H=base, left_is_fixed=f["left_is_fixed"], lf_H_des=f["lf_H"], rf_H_des=f["rf_H"],
                    lf_twist=f["lf_twist"], rf_twist=f["rf_twist"], com_pos_des=co["com_pos_des"], com_vel_des=co["com_vel_des"],
                    com_meas=com, neck_R_des=neck)
-        oo = ik_batch_tick(self.ik_cfg, self.model, inp, threads=self.threads)
+        kp, ka = self.ik_gains if self.ik_gains is not None else (None, None)
+        oo = ik_batch_tick(self.ik_cfg, self.model, inp, kpos=kp, katt=ka, threads=self.threads)
         self.q = self.glue.integrate_joints(oo["dq"])
         self.t += 1
         return dict(zmp=z, osqp_status=st, iters=it, flags=fl, dq=oo["dq"], qp_status=oo["status"], nwsr=oo["nwsr"], q_des=self.q,

@@ -32,6 +32,7 @@ void wco_mpc_free(wco_mpc* c);
 void wco_mpc_reset(wco_mpc* c);
 void wco_mpc_set_weights(wco_mpc* c, const double q_diag[2], const double r_diag[2]);
 void wco_mpc_set_linsys(wco_mpc* c, int kind);
+void wco_mpc_set_hull_variant(wco_mpc* c, int variant); /* sensitivity studies: row order / scaling of the hull rows */
 /* lf_H, rf_H: row-major 3x4; ref: (N+1) samples x 2, sample-major; returns WC_MPC_FLAG_* mask */
 int wco_mpc_tick(wco_mpc* c, const double* lf_H, const double* rf_H, int l_contact, int r_contact,
                  const double* dcm, const double* ref, int reset_traj,

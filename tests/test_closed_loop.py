@@ -17,7 +17,8 @@ def _gait(B, seed):
                 first_left=rng.integers(0, 2, B).astype(np.uint8))
 
 
-def _make(wc, oracle, syn, cuda_device, B, T, N, seed, use_graph, push=None, gain_sweep=False, vmax=None, prepared=True):
+def _make(wc, oracle, syn, cuda_device, B, T, N, seed, use_graph, push=None, gain_sweep=False, vmax=None, prepared=True,
+          mpc_settings=None):
     """both sides of the loop.  prepared: the posture of syn.prepare_posture (CoM at the start of the DCM reference, above the
     feet of tick 0) at the model's own LIPM height; vmax: joint velocity limit (default: the closed-loop workload's)"""
     vmax = syn.CL_VMAX if vmax is None else vmax
@@ -30,6 +31,12 @@ def _make(wc, oracle, syn, cuda_device, B, T, N, seed, use_graph, push=None, gai
     icfg_o, icfg_g, icfg_open = oracle.ik_default_config(), wc.ik_default_config(), oracle.ik_default_config()
     for c in (tco, tcg, mco, mcg, gco, gcg):
         c.com_height = h
+    for k, v in (mpc_settings or {}).items():
+        for c in (mco, mcg):
+            if k == "hull_tolerance":
+                c.hull_tolerance = v
+            else:
+                setattr(c.osqp, k, v)
     for j in range(23):
         icfg_o.min_vel[j], icfg_o.max_vel[j] = -vmax, vmax
         icfg_g.min_vel[j], icfg_g.max_vel[j] = -vmax, vmax
@@ -133,4 +140,31 @@ def test_closed_loop_infeasible_tail(wc, oracle, syn, cuda_device):
         o = lo.tick(); lg.run(1); torch.cuda.synchronize()
         _compare(o, lg.view(), t, stats)
     assert stats["ik_fail"] > 0.5 * B * T, stats
+    lg.close()
+
+
+@pytest.mark.gpu
+def test_closed_loop_monte_carlo_push_and_gain_sweep(wc, oracle, syn, cuda_device):
+    """BASELINE configs[3] in closed loop at B = 2048: an impulsive DCM push U(0, 0.06) m in a random direction at a random tick
+    (5 % of the instances are hit with 0.2 .. 0.5 m), Q in 7500 {0.1 .. 10}, R in 9e6 {0.1, 1, 10}, k_posFoot in {2.5, 4, 7},
+    k_attFoot in {2, 5} per instance.  With max_iter = 25 and a 0.2 mm hull tolerance the run CONTAINS the tails the sweep is
+    about -- OSQP_SOLVED_INACCURATE, OSQP_MAX_ITER_REACHED, ZMP outside the hull tolerance, infeasible QP-IK -- and every one of
+    them must match the oracle (status, iterations, flags, QP status, outputs) on every tick."""
+    B, N, T = 2048, 25, 150
+    rng = np.random.default_rng(3)
+    mag = rng.uniform(0, 0.06, B); big = rng.random(B) < 0.05; mag[big] = rng.uniform(0.2, 0.5, int(big.sum()))
+    ang = rng.uniform(0, 2 * np.pi, B)
+    push = (rng.integers(20, 120, B).astype(np.int32), np.ascontiguousarray(np.stack([mag * np.cos(ang), mag * np.sin(ang)])))
+    lo, lg, keep = _make(wc, oracle, syn, cuda_device, B, T, N, seed=12, use_graph=1, push=push, gain_sweep=True,
+                         mpc_settings=dict(max_iter=25, hull_tolerance=2e-4))
+    stats = dict(new=0, active=0, nwsr_diff=0, ik_fail=0)
+    seen_status, outside = set(), 0
+    for t in range(T):
+        o = lo.tick(); lg.run(1); torch.cuda.synchronize()
+        _compare(o, lg.view(), t, stats)
+        seen_status |= set(np.unique(o["osqp_status"]).tolist())
+        outside += int(((o["flags"] & 8) != 0).sum())
+    print("mc push:", stats, "osqp statuses", seen_status, "outside hull", outside)
+    assert {1, 2, -2} <= seen_status, seen_status     # SOLVED, SOLVED_INACCURATE and MAX_ITER_REACHED all occur
+    assert outside > 0 and stats["ik_fail"] > 0, (outside, stats)
     lg.close()

@@ -145,7 +145,7 @@ def test_no_contact_and_reset_paths(oracle, syn):
     args = lambda t, lc, rc: (f["lf_H"].numpy(), f["rf_H"].numpy(), lc, rc, g.measured_dcm(t).numpy(),
                               np.ascontiguousarray(traj[2 * t: 2 * t + 2 * (N + 1)]))
     z, st, it, fl = mb.tick(*args(0, np.array([0, 1], np.uint8), np.array([0, 1], np.uint8)))
-    assert fl[0] == 2 and st[0] == -10 and it[0] == 0 and (z[:, 0] == 0).all()    # no solver yet
+    assert fl[0] == 1 and st[0] == -10 and it[0] == 0 and (z[:, 0] == 0).all()    # no foot in contact: flagged, nothing solved
     assert fl[1] == 16 and st[1] == 1
     z, st, it, fl = mb.tick(*args(1, np.array([1, 0], np.uint8), np.array([1, 0], np.uint8)))
     assert fl[0] == 16 and fl[1] == 1                                              # "None foot is in contact"
