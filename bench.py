@@ -298,6 +298,24 @@ def build_closed_loop(wc, syn, torch, g, B, N, n_ticks, dev, local_rank, mpc_set
     return loop, (mpc_cl, ik_cl, glue, tj), (mcfg_cl, icfg_cl, model), q0
 
 
+def capi_collect(wc, torch, dist, world, rank, local_rank, B, zmp, dq, osqp_status, iters, qp_status, nwsr, stats_sum):
+    """Result collection through the C ABI (wc_comm_* / wc_gather_*, include/wc_capi.h): all-gather of the per-instance results
+    and all-reduce of the statistics vector over NCCL on the communicator's side stream.  torch.distributed only carries the
+    128-byte NCCL id to the other ranks.  Returns (gathered dict, milliseconds of the timed collection)."""
+    box = [wc.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    comm = wc.Comm(box[0], world, rank, device=local_rank)
+    # the first collective sets up the NCCL connections (seconds at 8 ranks): not part of the collection time
+    w = torch.zeros(1, dtype=torch.float64, device=stats_sum.device)
+    comm.gather(B, 0, stats_sum=w, wait="host")
+    torch.cuda.synchronize(); dist.barrier(); t0 = time.perf_counter()
+    out = comm.gather(B, dq.shape[0], zmp=zmp, dq=dq, osqp_status=osqp_status, iters=iters, qp_status=qp_status, nwsr=nwsr,
+                      stats_sum=stats_sum, wait="host")
+    ms = (time.perf_counter() - t0) * 1e3
+    comm.close()
+    return out, ms
+
+
 MC_METRIC = "MPC+QP-IK controller ticks/sec, Monte-Carlo push / gain sweep at B=524288 iCub instances (closed loop)"
 
 
@@ -363,14 +381,8 @@ def run_mc_push(args, world, rank, local_rank):
     gather_ms = None
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        res = torch.cat([view["zmp"], view["dq"]], 0).contiguous()
-        outbuf = [torch.empty_like(res) for _ in range(world)] if rank == 0 else None
-        warmbuf = [torch.empty(8, device=dev) for _ in range(world)] if rank == 0 else None
-        dist.gather(torch.zeros(8, device=dev), warmbuf, dst=0)
-        torch.cuda.synchronize(); dist.barrier(); t0 = time.perf_counter()
-        dist.gather(res, outbuf, dst=0)
-        dist.all_reduce(tally, op=dist.ReduceOp.SUM)
-        torch.cuda.synchronize(); gather_ms = (time.perf_counter() - t0) * 1e3
+        _, gather_ms = capi_collect(wc, torch, dist, world, rank, local_rank, B, view["zmp"], view["dq"], view["osqp_status"],
+                                    view["iters"], view["qp_status"], view["nwsr"], tally)
     ms = ms.item()
     if rank == 0:
         n_tallied = float(world * B * (warm + 1))
@@ -390,7 +402,7 @@ def run_mc_push(args, world, rank, local_rank):
                                   "parity of every tail against the oracle: tests/test_closed_loop.py"},
                 "gpu_launches": int(steps), "api": "wc_loop_run_dev (one CUDA-graph replay per tick)", "clocks": clocks}
         if gather_ms is not None:
-            line["nccl_gather_ms"] = gather_ms
+            line["nccl_gather_ms"] = gather_ms; line["nccl_gather_api"] = "wc_gather_async (C ABI, side stream)"
         print(json.dumps(line), flush=True)
     loop.close()
     for h in handles:
@@ -494,16 +506,9 @@ def run_ours(args, world, rank, local_rank):
     # ---------------- NCCL result collection (off the tick's critical path)
     gather_ms = None
     if world > 1:
-        res = torch.cat([mo["zmp"], io_["dq"]], 0).contiguous()
-        outbuf = [torch.empty_like(res) for _ in range(world)] if rank == 0 else None
         stats = torch.tensor([solved, ik_ok, it_mean, wsc_mean], dtype=torch.float64, device=dev)
-        # the first gather sets up the point-to-point NCCL connections (seconds at 8 ranks): not part of the collection time
-        gather_warm = [torch.empty(8, device=dev) for _ in range(world)] if rank == 0 else None
-        dist.gather(torch.zeros(8, device=dev), gather_warm, dst=0)
-        torch.cuda.synchronize(); dist.barrier(); t0 = time.perf_counter()
-        dist.gather(res, outbuf, dst=0)
-        dist.all_reduce(stats, op=dist.ReduceOp.SUM)
-        torch.cuda.synchronize(); gather_ms = (time.perf_counter() - t0) * 1e3
+        _, gather_ms = capi_collect(wc, torch, dist, world, rank, local_rank, B, mo["zmp"], io_["dq"], mo["status"], mo["iters"],
+                                    io_["status"], io_["nwsr"], stats)
         solved, ik_ok, it_mean, wsc_mean = (stats / world).tolist()
 
     # ---------------- arm 2: the closed-loop tick (wc_loop_*): producer -> measured CoM -> MPC -> ZMP-CoM law -> FK + QP-IK ->
@@ -728,7 +733,7 @@ def run_ours(args, world, rank, local_rank):
             "clocks": clocks,
         }
         if gather_ms is not None:
-            line["nccl_gather_ms"] = gather_ms
+            line["nccl_gather_ms"] = gather_ms; line["nccl_gather_api"] = "wc_gather_async (C ABI, side stream)"
         if next_rows is not None:
             line["next_rows"] = next_rows
         if world == 1 and not args.no_cpu:

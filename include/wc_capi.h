@@ -642,6 +642,40 @@ typedef struct wc_loop_view {
 } wc_loop_view;
 wc_status wc_loop_view_get(wc_loop* h, wc_loop_view* view);
 
+/* ---------------------------------------------------------------------------------- */
+/* Result collection across the GPUs of one box (SURVEY §8(b) `wc_gather`, §8(e)).       */
+/* Instances are independent, rank g owns a contiguous instance range and there is NO     */
+/* collective on the tick path; at its collection points a Monte-Carlo driver all-gathers  */
+/* the per-instance results and all-reduces a small statistics vector over NCCL (NVLink 5  */
+/* / NVSwitch), on the communicator's own side stream so that the next tick overlaps it.   */
+/* NCCL is bound at run time (dlopen of libnccl.so.2); WC_ERR_UNSUPPORTED if it is absent. */
+/* ---------------------------------------------------------------------------------- */
+typedef struct wc_comm wc_comm;
+#define WC_COMM_ID_BYTES 128
+/* rank 0 creates the id (ncclGetUniqueId) and hands it to the other ranks by whatever means the driver has (a file, MPI,
+ * a torch.distributed store); every rank then joins with it. */
+wc_status wc_comm_unique_id(uint8_t* id /*[WC_COMM_ID_BYTES]*/);
+wc_status wc_comm_create(const uint8_t* id, int32_t world, int32_t rank, int32_t device, wc_comm** out);
+void wc_comm_destroy(wc_comm* c);
+int32_t wc_comm_world(const wc_comm* c);
+int32_t wc_comm_rank(const wc_comm* c);
+/* Device pointers.  Every pair (x, x_all): this rank's block [rows*B] and the gathered array [world][rows*B] (rank-major:
+ * rank r's field-major block at offset r*rows*B); a NULL pair is skipped.  stats_sum / stats_max are reduced IN PLACE. */
+typedef struct wc_gather_io {
+    const double *zmp; double *zmp_all;                      /* rows = 2 */
+    const double *dq; double *dq_all;                        /* rows = n_dofs */
+    const int32_t *osqp_status; int32_t *osqp_status_all;    /* rows = 1 */
+    const int32_t *iters; int32_t *iters_all;
+    const int32_t *qp_status; int32_t *qp_status_all;
+    const int32_t *nwsr; int32_t *nwsr_all;
+    double *stats_sum; int32_t n_stats_sum;                  /* all-reduce (sum) */
+    double *stats_max; int32_t n_stats_max;                  /* all-reduce (max) */
+} wc_gather_io;
+/* One NCCL group on the communicator's side stream, ordered after the work already enqueued on producer_stream. */
+wc_status wc_gather_async(wc_comm* c, const wc_gather_io* io, int32_t B, int32_t n_dofs, void* producer_stream);
+/* block_host = 0: consumer_stream waits for the last wc_gather_async; block_host = 1: the calling thread does. */
+wc_status wc_gather_wait(wc_comm* c, void* consumer_stream, int32_t block_host);
+
 /* Measured FP64 FMA throughput of the device (register-resident FMA chains, all SMs), in GFLOP/s:
  * the denominator of the FP64 roofline fraction that bench.py reports next to the HBM one
  * (MEASURED_PEAKS.json carries no FP64 entry). */

@@ -55,6 +55,13 @@ class LoopView(C.Structure):
     _fields_ = [(k, C.c_void_p) for k, _, _ in LOOP_VIEW]
 
 
+class GatherIO(C.Structure):
+    _fields_ = [("zmp", C.c_void_p), ("zmp_all", C.c_void_p), ("dq", C.c_void_p), ("dq_all", C.c_void_p),
+                ("osqp_status", C.c_void_p), ("osqp_status_all", C.c_void_p), ("iters", C.c_void_p), ("iters_all", C.c_void_p),
+                ("qp_status", C.c_void_p), ("qp_status_all", C.c_void_p), ("nwsr", C.c_void_p), ("nwsr_all", C.c_void_p),
+                ("stats_sum", C.c_void_p), ("n_stats_sum", C.c_int32), ("stats_max", C.c_void_p), ("n_stats_max", C.c_int32)]
+
+
 class OsqpSettings(C.Structure):
     _fields_ = [("rho", C.c_double), ("sigma", C.c_double), ("alpha", C.c_double),
                 ("eps_abs", C.c_double), ("eps_rel", C.c_double),
@@ -224,6 +231,13 @@ def lib():
     L.wc_glue_evaluate_zmp_dev.argtypes = [_VP] * 8; L.wc_glue_evaluate_zmp_dev.restype = i32
     L.wc_glue_log_pack_dev.argtypes = [_VP, C.POINTER(LogInputs), _VP, _VP]; L.wc_glue_log_pack_dev.restype = i32
     L.wc_measure_fp64_peak.argtypes = [i32, C.POINTER(C.c_double)]; L.wc_measure_fp64_peak.restype = i32
+    L.wc_comm_unique_id.argtypes = [_VP]; L.wc_comm_unique_id.restype = i32
+    L.wc_comm_create.argtypes = [_VP, i32, i32, i32, C.POINTER(_VP)]; L.wc_comm_create.restype = i32
+    L.wc_comm_destroy.argtypes = [_VP]
+    L.wc_comm_world.argtypes = [_VP]; L.wc_comm_world.restype = i32
+    L.wc_comm_rank.argtypes = [_VP]; L.wc_comm_rank.restype = i32
+    L.wc_gather_async.argtypes = [_VP, C.POINTER(GatherIO), i32, i32, _VP]; L.wc_gather_async.restype = i32
+    L.wc_gather_wait.argtypes = [_VP, _VP, i32]; L.wc_gather_wait.restype = i32
     L.wc_loop_default_config.argtypes = [C.POINTER(LoopConfig)]
     L.wc_loop_create.argtypes = [_VP, _VP, _VP, _VP, C.POINTER(LoopConfig), i32, C.POINTER(_VP)]; L.wc_loop_create.restype = i32
     L.wc_loop_destroy.argtypes = [_VP]
@@ -916,3 +930,68 @@ class LoopBatch:
                 out[k] = torch.as_tensor(_DevArray(getattr(v, k), shape, ts), device=f"cuda:{self.device}")
             self._view = out
         return self._view
+
+
+COMM_ID_BYTES = 128
+
+
+def comm_unique_id():
+    """bytes of a fresh NCCL unique id (rank 0 creates it and hands it to the other ranks)"""
+    buf = (C.c_uint8 * COMM_ID_BYTES)()
+    _check(lib().wc_comm_unique_id(buf), "wc_comm_unique_id")
+    return bytes(buf)
+
+
+class Comm:
+    """wc_comm_*: NCCL result collection (all-gather of per-instance results + all-reduce of statistics) on a side stream"""
+
+    def __init__(self, uid, world, rank, device=0):
+        self.world, self.rank, self.device = world, rank, device
+        buf = (C.c_uint8 * COMM_ID_BYTES).from_buffer_copy(uid)
+        h = _VP()
+        _check(lib().wc_comm_create(buf, world, rank, device, C.byref(h)), "wc_comm_create")
+        self.h = h
+        self._keep = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().wc_comm_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def gather(self, B, n_dofs, zmp=None, dq=None, osqp_status=None, iters=None, qp_status=None, nwsr=None, stats_sum=None,
+               stats_max=None, stream=None, wait="stream"):
+        """all-gather the given CUDA tensors ([rows, B] blocks -> [world, rows, B]) and all-reduce stats_sum / stats_max in
+        place, after the work on `stream`; wait = "stream" (stream waits), "host" (blocks) or None (call wait() later)"""
+        import torch
+        dev = torch.device(f"cuda:{self.device}")
+        if stream is None:
+            stream = torch.cuda.current_stream(dev).cuda_stream
+        io = GatherIO(); out = {}
+        spec = dict(zmp=(zmp, 2, "f64", torch.float64), dq=(dq, n_dofs, "f64", torch.float64), osqp_status=(osqp_status, 1, "i32", torch.int32),
+                    iters=(iters, 1, "i32", torch.int32), qp_status=(qp_status, 1, "i32", torch.int32), nwsr=(nwsr, 1, "i32", torch.int32))
+        for k, (t, rows, kind, dt) in spec.items():
+            if t is None:
+                continue
+            shape = (self.world, B) if rows == 1 else (self.world, rows, B)
+            out[k] = torch.empty(shape, dtype=dt, device=dev)
+            setattr(io, k, _arg(t, kind, rows * B, "cuda", k)); setattr(io, k + "_all", out[k].data_ptr())
+        if stats_sum is not None:
+            io.stats_sum = _arg(stats_sum, "f64", stats_sum.numel(), "cuda", "stats_sum"); io.n_stats_sum = stats_sum.numel()
+        if stats_max is not None:
+            io.stats_max = _arg(stats_max, "f64", stats_max.numel(), "cuda", "stats_max"); io.n_stats_max = stats_max.numel()
+        self._keep = (zmp, dq, osqp_status, iters, qp_status, nwsr, stats_sum, stats_max, out)
+        _check(lib().wc_gather_async(self.h, C.byref(io), B, n_dofs, stream), "wc_gather_async")
+        if wait == "stream":
+            _check(lib().wc_gather_wait(self.h, stream, 0), "wc_gather_wait")
+        elif wait == "host":
+            _check(lib().wc_gather_wait(self.h, None, 1), "wc_gather_wait")
+        return out
+
+    def wait(self, stream=None):
+        _check(lib().wc_gather_wait(self.h, stream, 1 if stream is None else 0), "wc_gather_wait")
