@@ -1,5 +1,6 @@
 // ik_kernels.cu — see ik_kernels.cuh for the mapping to the reference.
 #include "ik_kernels.cuh"
+#include "ik_math.cuh"
 
 #include <cfloat>
 #include <cmath>
@@ -26,66 +27,6 @@ constexpr int kWarpsPerBlock = 4;
 #ifndef WC_IK_FAST_MINB
 #define WC_IK_FAST_MINB 4 // resident CTAs per SM the fast kernel is compiled for (register cap 128)
 #endif
-
-// ---- small 3x3 / rigid transform helpers (row-major R[9], p[3]) ---------------------------------
-__device__ __forceinline__ void mat3_mul(const double* a, const double* b, double* o)
-{
-#pragma unroll
-    for (int r = 0; r < 3; r++)
-#pragma unroll
-        for (int c = 0; c < 3; c++) o[3 * r + c] = a[3 * r] * b[c] + a[3 * r + 1] * b[3 + c] + a[3 * r + 2] * b[6 + c];
-}
-__device__ __forceinline__ void mat3_mul_bt(const double* a, const double* b, double* o)
-{
-#pragma unroll
-    for (int r = 0; r < 3; r++)
-#pragma unroll
-        for (int c = 0; c < 3; c++) o[3 * r + c] = a[3 * r] * b[3 * c] + a[3 * r + 1] * b[3 * c + 1] + a[3 * r + 2] * b[3 * c + 2];
-}
-__device__ __forceinline__ void xf_mul(const double* Ra, const double* pa, const double* Rb, const double* pb, double* Ro, double* po)
-{
-    double R[9], p[3];
-    mat3_mul(Ra, Rb, R);
-#pragma unroll
-    for (int r = 0; r < 3; r++) p[r] = Ra[3 * r] * pb[0] + Ra[3 * r + 1] * pb[1] + Ra[3 * r + 2] * pb[2] + pa[r];
-#pragma unroll
-    for (int k = 0; k < 9; k++) Ro[k] = R[k];
-#pragma unroll
-    for (int k = 0; k < 3; k++) po[k] = p[k];
-}
-__device__ __forceinline__ void cross3(const double* a, const double* b, double* o)
-{
-    o[0] = a[1] * b[2] - a[2] * b[1];
-    o[1] = a[2] * b[0] - a[0] * b[2];
-    o[2] = a[0] * b[1] - a[1] * b[0];
-}
-// unskew(1/2 (M - M')), M = R Rdes'   (Utils.cpp:22-27 + iDynTree::unskew)
-__device__ __forceinline__ void rot_error(const double* R, const double* Rdes, double* e)
-{
-    double M[9];
-    mat3_mul_bt(R, Rdes, M);
-    e[0] = 0.5 * (M[7] - M[5]);
-    e[1] = 0.5 * (M[2] - M[6]);
-    e[2] = 0.5 * (M[3] - M[1]);
-}
-// 8-byte asynchronous copy HBM -> shared (LDGSTS): the per-instance inputs are fetched while the kinematics runs
-__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc)
-{
-    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ double warp_sum(double v)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-__device__ __forceinline__ double warp_max(double v)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
-}
 
 // ---- K3: floating-base forward kinematics + the Jacobian column of this lane's QP variable ---------
 // WalkingFK::{evaluateWorldToBaseTransformation,setInternalRobotState} + the getters of
@@ -1292,6 +1233,13 @@ cudaError_t launch_t(const IkDev& d, const IkTickIO& io, int mode, cudaStream_t 
         if (e != cudaSuccess) return e;
         e = cudaMemsetAsync(d.slow_count, 0, 2 * sizeof(int32_t), s);
         if (e != cudaSuccess) return e;
+        if (d.tpi_scratch) { // thread-per-instance fast path (ik_tpi.cu): both fast launches, then the general kernel on slow_list
+            e = launch_ik_tpi(d, io, s);
+            if (e != cudaSuccess) return e;
+            if (mid) cudaEventRecord(mid, s);
+            ik_kernel<NJ, COMC><<<blocks, kWarpsPerBlock * 32, smem, s>>>(d, io, mode, 1);
+            return cudaGetLastError();
+        }
         ik_fast_kernel<NJ, false><<<(d.B + kFastWarps - 1) / kFastWarps, kFastWarps * 32, smem_f, s>>>(d, io);
         ik_fast_kernel<NJ, true><<<(d.B + kFastWarps - 1) / kFastWarps, kFastWarps * 32, smem_f, s>>>(d, io);
         if (mid) cudaEventRecord(mid, s); // per-kernel timing (wc_ik_enable_profiling)

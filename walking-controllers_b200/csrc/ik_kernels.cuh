@@ -51,7 +51,17 @@ struct IkModelDev {
     // round r (its 2^r-th ancestor), -1 = l is already expressed in the root frame; n_jump rounds in all
     int n_jump, pad2;
     signed char jump[WC_MAX_JUMP][WC_MAX_LINKS];
+    // thread-per-instance fast path (ik_tpi.cu): schedule of the serial transform composition.  tpi_slot[l] = shared-memory
+    // slot root_H_l is parked in (-1: nobody reads it later), tpi_pslot[l] = where link l finds its parent's transform
+    // (slot id, kTpiPrev: still in registers because parent == l - 1, -1: link 0); the sub-tree of the link of dof d is the
+    // contiguous run of links [link_of_dof[d], tpi_sub_last[d]] (depth-first numbering; checked on the host, tpi_ok = 0 otherwise)
+    int tpi_ok, tpi_slots;
+    signed char tpi_slot[WC_MAX_LINKS];
+    signed char tpi_pslot[WC_MAX_LINKS];
+    signed char tpi_sub_last[WC_MAX_DOFS];
 };
+constexpr int kTpiPrev = -2;
+constexpr int kTpiMaxSlots = 8;
 
 struct IkDev {
     int B, nJ;
@@ -62,6 +72,8 @@ struct IkDev {
     // fused-tick fast path (ik_fast_kernel): instances handed over to the general kernel
     int32_t* slow_list;      // [B] or nullptr (fast path disabled)
     int32_t* slow_count;     // [2]: [0] = entries of slow_list, [1] = entries of second_list
+    double* tpi_scratch;     // thread-per-instance fast path: [tpi_rows][B] per-instance scratch in HBM / L2 (ik_tpi.cu), or nullptr
+    int tpi_slots;           // transform slots of the model's schedule (IkModelDev::tpi_slots), for the launch's shared-memory size
     int32_t* second_list;    // [2 B] instances whose equality-constrained optimum violates a bound (second fast launch): [0, B) the
                              // instance, [B, 2 B) the bound Goldfarb-Idnani adds first (2 * variable + upper)
     // WalkingQPIK_osqp (wc_ik_set_solver): OSQP settings and the persistent workspace of every instance, field-major
@@ -95,5 +107,8 @@ struct IkTickIO {
 // mid (nullable): event recorded between the fast kernel and the general kernel of the fused tick
 cudaError_t launch_ik(const IkDev& d, const IkTickIO& io, int mode, cudaStream_t s, cudaEvent_t mid = nullptr);
 bool ik_supported(int n_dofs);
+// thread-per-instance fast path of the fused tick (ik_tpi.cu)
+int ik_tpi_rows(int n_links, int n_dofs);  // rows of IkDev::tpi_scratch
+cudaError_t launch_ik_tpi(const IkDev& d, const IkTickIO& io, cudaStream_t s);
 
 } // namespace wcb

@@ -89,6 +89,38 @@ bool build_model(const wc_model* m, IkModelDev* o)
     }
     const int fl[3] = {m->l_sole_link, m->r_sole_link, m->neck_link};
     for (int f = 0; f < 3; f++) if (fl[f] < 0 || fl[f] >= L) return false;
+    { // thread-per-instance schedule (ik_tpi.cu): transform slots by linear scan, contiguous sub-trees
+        int last_use[WC_MAX_LINKS]; bool needs[WC_MAX_LINKS];
+        for (int i = 0; i < L; i++) { last_use[i] = i; needs[i] = false; }
+        for (int i = 1; i < L; i++) {
+            const int p = m->parent[i];
+            if (p != i - 1) { needs[p] = true; if (i > last_use[p]) last_use[p] = i; }
+        }
+        for (int f = 0; f < 3; f++) { needs[fl[f]] = true; last_use[fl[f]] = L; } // read after the loop
+        int owner[kTpiMaxSlots]; for (int k = 0; k < kTpiMaxSlots; k++) owner[k] = -1;
+        bool ok = true; int used = 0;
+        for (int i = 0; i < L && ok; i++) {
+            for (int k = 0; k < kTpiMaxSlots; k++) if (owner[k] >= 0 && last_use[owner[k]] < i) owner[k] = -1;
+            o->tpi_pslot[i] = (signed char)(i == 0 ? -1 : (m->parent[i] == i - 1 ? kTpiPrev : o->tpi_slot[m->parent[i]]));
+            o->tpi_slot[i] = -1;
+            if (needs[i]) {
+                int k = 0;
+                while (k < kTpiMaxSlots && owner[k] >= 0) k++;
+                if (k == kTpiMaxSlots) { ok = false; break; }
+                owner[k] = i; o->tpi_slot[i] = (signed char)k; if (k + 1 > used) used = k + 1;
+            }
+        }
+        for (int d = 0; d < m->n_dofs && ok; d++) {
+            const int c = o->link_of_dof[d];
+            int last = c;
+            while (last + 1 < L && ((o->sub_mask[c] >> (last + 1)) & 1ull)) last++;
+            unsigned long long run = 0;
+            for (int k = c; k <= last; k++) run |= 1ull << k;
+            if (run != o->sub_mask[c]) ok = false;
+            o->tpi_sub_last[d] = (signed char)last;
+        }
+        o->tpi_ok = ok ? 1 : 0; o->tpi_slots = used;
+    }
     o->base_link[1] = m->l_sole_link; o->base_link[0] = m->r_sole_link;
     for (int f = 0; f < 3; f++) o->frame_link[f] = fl[f];
     std::memcpy(o->frame_R[0], m->l_sole_R, sizeof(double) * 9); std::memcpy(o->frame_p[0], m->l_sole_p, sizeof(double) * 3);
@@ -146,6 +178,13 @@ wc_status wc_ik_create(const wc_ik_config* cfg, const wc_model* model, int32_t B
                 cudaMalloc(&h->d.second_list, (size_t)2 * B * sizeof(int32_t)) != cudaSuccess ||
                 cudaMalloc(&h->d.slow_count, 2 * sizeof(int32_t)) != cudaSuccess) { wc_ik_destroy(h); return WC_ERR_ALLOC; }
             cudaMemset(h->d.slow_count, 0, 2 * sizeof(int32_t));
+            // thread-per-instance fast kernels (ik_tpi.cu) when the model's link numbering allows their schedule;
+            // WC_IK_PATH=warp keeps the warp-per-instance fast kernel (ik_fast_kernel)
+            if (hm.tpi_ok && !(pth && !std::strcmp(pth, "warp"))) {
+                const size_t rows = (size_t)ik_tpi_rows(hm.n_links, cfg->n_dofs);
+                if (cudaMalloc(&h->d.tpi_scratch, rows * (size_t)B * sizeof(double)) != cudaSuccess) { wc_ik_destroy(h); return WC_ERR_ALLOC; }
+                h->d.tpi_slots = hm.tpi_slots;
+            }
         }
     }
     *out = h;
@@ -159,6 +198,7 @@ void wc_ik_destroy(wc_ik* h)
     if (h->model_dev) cudaFree(h->model_dev);
     if (h->d.slow_list) cudaFree(h->d.slow_list);
     if (h->d.second_list) cudaFree(h->d.second_list);
+    if (h->d.tpi_scratch) cudaFree(h->d.tpi_scratch);
     if (h->d.slow_count) cudaFree(h->d.slow_count);
     if (h->kpos) cudaFree(h->kpos);
     if (h->katt) cudaFree(h->katt);
