@@ -56,8 +56,6 @@ struct TpiRows {
     }
 };
 
-__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-
 // accumulators of the reduced problem over the joints: C = U L^-1 U', G = A L^-1 U', S = A L^-1 A' (upper triangle by rows),
 // ra = A L^-1 g, ru = U L^-1 g
 struct TpiAcc {
@@ -133,21 +131,29 @@ __device__ __forceinline__ int tpi_solve(const IkDev& d, const IkTickIO& io, con
             br_e[3 + r] = br[3 + r] - (ssw * cp[3 + r]) * beta;
             br_e[6 + r] = br[6 + r] - cp[6 + r] * beta;
         }
-        A.clear();
+    }
+    // ---- accumulate over the joints; the ten rows of the next column are requested before the current one is used
+    A.clear();
+    {
+        double nx[10];
+#pragma unroll
+        for (int r = 0; r < 10; r++) nx[r] = colj[(size_t)r * B];
 #pragma unroll 1
         for (int j = 0; j < nJ; j++) {
-            if (j + 1 < nJ) {
-#pragma unroll
-                for (int r = 0; r < 10; r++) prefetch_l1(colj + (size_t)(10 * (j + 1) + r) * B);
-            }
-            if (j == pvar) continue;
-            tpi_signs(M, left, j, ssw, sn);
             double c10[10];
 #pragma unroll
-            for (int r = 0; r < 10; r++) c10[r] = colj[(size_t)(10 * j + r) * B];
+            for (int r = 0; r < 10; r++) c10[r] = nx[r];
+            if (j + 1 < nJ) {
+#pragma unroll
+                for (int r = 0; r < 10; r++) nx[r] = colj[(size_t)(10 * (j + 1) + r) * B];
+            }
+            if (SECOND && j == pvar) continue;
+            double ssw, sn;
+            tpi_signs(M, left, j, ssw, sn);
             const double a[9] = {c10[0], c10[1], c10[2], ssw * c10[3], ssw * c10[4], ssw * c10[5], c10[6], c10[7], c10[8]};
             const double u[3] = {sn * c10[3], sn * c10[4], sn * c10[5]};
-            const double g = c10[9] + (u[0] * wup[0] + u[1] * wup[1] + u[2] * wup[2]) * beta;
+            double g = c10[9];
+            if (SECOND) g += (u[0] * wup[0] + u[1] * wup[1] + u[2] * wup[2]) * beta;
             A.add(a, u, g, 1.0 / cfg.joint_reg_weight[j]);
         }
     }
@@ -194,9 +200,8 @@ __device__ __forceinline__ int tpi_solve(const IkDev& d, const IkTickIO& io, con
     for (int jc = 0; jc < 9; jc++) {
         const double djj = S[SI(jc, jc)];
         if (!(djj > ptol)) return 2;
-        const double piv = sqrt(djj);
-        pinv[jc] = 1.0 / piv;
-        S[SI(jc, jc)] = piv;
+        pinv[jc] = rsqrt(djj);
+        S[SI(jc, jc)] = djj * pinv[jc];
 #pragma unroll
         for (int c = jc + 1; c < 9; c++) S[SI(jc, c)] *= pinv[jc];
 #pragma unroll
@@ -239,17 +244,20 @@ __device__ __forceinline__ int tpi_solve(const IkDev& d, const IkTickIO& io, con
     double ew[6] = {0, 0, 0, 0, 0, 0};
     bool viol = false;
     double best = INFINITY; int id = 0x7fffffff;
+    double nx[10];
+#pragma unroll
+    for (int r = 0; r < 10; r++) nx[r] = colj[(size_t)r * B];
 #pragma unroll 1
     for (int j = 0; j < nJ; j++) {
+        double c10[10];
+#pragma unroll
+        for (int r = 0; r < 10; r++) c10[r] = nx[r];
         if (j + 1 < nJ) {
 #pragma unroll
-            for (int r = 0; r < 10; r++) prefetch_l1(colj + (size_t)(10 * (j + 1) + r) * B);
+            for (int r = 0; r < 10; r++) nx[r] = colj[(size_t)(10 * (j + 1) + r) * B];
         }
         double ssw, sn;
         tpi_signs(M, left, j, ssw, sn);
-        double c10[10];
-#pragma unroll
-        for (int r = 0; r < 10; r++) c10[r] = colj[(size_t)(10 * j + r) * B];
         const double a[9] = {c10[0], c10[1], c10[2], ssw * c10[3], ssw * c10[4], ssw * c10[5], c10[6], c10[7], c10[8]};
         const double u[3] = {sn * c10[3], sn * c10[4], sn * c10[5]};
         double nu;
@@ -297,10 +305,16 @@ __global__ void __launch_bounds__(kTpiThreads, WC_TPI_MINB) ik_tpi_kernel(IkDev 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool live = blockIdx.x * kTpiThreads + threadIdx.x < d.B;
     const int i = live ? blockIdx.x * kTpiThreads + threadIdx.x : d.B - 1; // idle threads of the last CTA shadow its last instance
+    // model table: one copy per CTA (the link loop reads ~25 words of it per link, the same for every lane)
+    __shared__ __align__(16) unsigned long long s_model[(sizeof(IkModelDev) + 7) / 8];
+    {
+        const unsigned long long* src = reinterpret_cast<const unsigned long long*>(d.model);
+        for (int k = threadIdx.x; k < (int)((sizeof(IkModelDev) + 7) / 8); k += kTpiThreads) s_model[k] = src[k];
+    }
     if (threadIdx.x == 0) s_n = 0;
     __syncthreads();
     const size_t B = (size_t)d.B;
-    const IkModelDev& M = *d.model;
+    const IkModelDev& M = *reinterpret_cast<const IkModelDev*>(s_model);
     const wc_ik_config& cfg = d.cfg;
     const int L = M.n_links, nJ = d.nJ;
     const TpiRows rows(L, nJ);
@@ -312,22 +326,19 @@ __global__ void __launch_bounds__(kTpiThreads, WC_TPI_MINB) ik_tpi_kernel(IkDev 
     // ---- root_H_link, serially over the links (parent[l] < l); first-moment prefix; joint axes and origins
     double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, p[3] = {0, 0, 0}; // root_H_(l-1) of the previous iteration
     double P[3] = {0, 0, 0};
-    double qn = 0.0; // joint angle of the next link, requested one link ahead (and its line two links ahead)
+    double qn = 0.0, qn2 = 0.0; // joint angles of the next two links, requested ahead of their use
     {
         const int d0 = M.dof[0];
         if (d0 >= 0) qn = io.q_lin[(size_t)d0 * B + i];
-        if (L > 1 && M.dof[1] >= 0) prefetch_l1(io.q_lin + (size_t)M.dof[1] * B + i);
+        if (L > 1 && M.dof[1] >= 0) qn2 = io.q_lin[(size_t)M.dof[1] * B + i];
     }
 #pragma unroll 1
     for (int l = 0; l < L; l++) {
         const double q = qn;
-        if (l + 1 < L) {
-            const int dn = M.dof[l + 1];
-            if (dn >= 0) qn = io.q_lin[(size_t)dn * B + i];
-        }
+        qn = qn2;
         if (l + 2 < L) {
             const int dn = M.dof[l + 2];
-            if (dn >= 0) prefetch_l1(io.q_lin + (size_t)dn * B + i);
+            if (dn >= 0) qn2 = io.q_lin[(size_t)dn * B + i];
         }
         double Rl[9], pl[3];
 #pragma unroll
@@ -514,32 +525,28 @@ __global__ void __launch_bounds__(kTpiThreads, WC_TPI_MINB) ik_tpi_kernel(IkDev 
     for (int r = 0; r < 3; r++) sc[(size_t)(rows.oINST + 9 + r) * B] = es[r];
     // ---- QP column of every joint (MIXED representation, WalkingForwardKinematics.cpp:31,436-454): into the scratch (in place of
     // the joint's root-frame axis and origin) and straight into the accumulators of the reduced problem
-    TpiAcc A;
-    A.clear();
     bool fallback = false;
-    auto prefetch_joint = [&](int jn) {
+    const double Minv = 1.0 / Mtot;
+    // rows of joint j the column needs: axis / origin (6), two prefix entries (3 + 3), the measured joint position
+    double nx[13];
+    auto request = [&](int jn) {
         const int cn = M.link_of_dof[jn], ln = M.tpi_sub_last[jn];
 #pragma unroll
-        for (int r = 0; r < 6; r++) prefetch_l1(sc + (size_t)(rows.oJ + 10 * jn + r) * B);
+        for (int r = 0; r < 6; r++) nx[r] = sc[(size_t)(rows.oJ + 10 * jn + r) * B];
 #pragma unroll
-        for (int r = 0; r < 3; r++) { prefetch_l1(sc + (size_t)(rows.oP + 3 * (ln + 1) + r) * B); prefetch_l1(sc + (size_t)(rows.oP + 3 * cn + r) * B); }
-        prefetch_l1(io.q_meas + (size_t)jn * B + i);
+        for (int r = 0; r < 3; r++) { nx[6 + r] = sc[(size_t)(rows.oP + 3 * (ln + 1) + r) * B]; nx[9 + r] = sc[(size_t)(rows.oP + 3 * cn + r) * B]; }
+        nx[12] = io.q_meas[(size_t)jn * B + i];
     };
-    prefetch_joint(0);
+    request(0);
 #pragma unroll 1
     for (int j = 0; j < nJ; j++) {
-        if (j + 1 < nJ) prefetch_joint(j + 1);
         const int c = M.link_of_dof[j];
-        const int last = M.tpi_sub_last[j];
         double* cj = sc + (size_t)(rows.oJ + 10 * j) * B;
         double ar[3], orr[3], Sr[3];
 #pragma unroll
-        for (int r = 0; r < 3; r++) {
-            ar[r] = cj[(size_t)r * B];
-            orr[r] = cj[(size_t)(3 + r) * B];
-            Sr[r] = sc[(size_t)(rows.oP + 3 * (last + 1) + r) * B] - sc[(size_t)(rows.oP + 3 * c + r) * B];
-        }
-        const double qm = io.q_meas[(size_t)j * B + i];
+        for (int r = 0; r < 3; r++) { ar[r] = nx[r]; orr[r] = nx[3 + r]; Sr[r] = nx[6 + r] - nx[9 + r]; }
+        const double qm = nx[12];
+        if (j + 1 < nJ) request(j + 1);
         const double ms = M.sub_mass[c];
         double a3[3], o[3], S[3];
 #pragma unroll
@@ -557,7 +564,7 @@ __global__ void __launch_bounds__(kTpiThreads, WC_TPI_MINB) ik_tpi_kernel(IkDev 
         cross3(a3, r3, lin);
 #pragma unroll
         for (int r = 0; r < 3; r++)
-            mom[r] = bis ? -((Mc[r] - S[r]) - (Mtot - ms) * o[r]) / Mtot : (S[r] - ms * o[r]) / Mtot;
+            mom[r] = (bis ? -((Mc[r] - S[r]) - (Mtot - ms) * o[r]) : (S[r] - ms * o[r])) * Minv;
         cross3(a3, mom, cc);
         const double u[3] = {sn * a3[0], sn * a3[1], sn * a3[2]};
         const double lam = cfg.joint_reg_weight[j];
@@ -573,8 +580,8 @@ __global__ void __launch_bounds__(kTpiThreads, WC_TPI_MINB) ik_tpi_kernel(IkDev 
             cj[(size_t)(6 + r) * B] = cc[r];
         }
         cj[(size_t)9 * B] = gr;
-        A.add(a, u, gr, lam > 0.0 ? 1.0 / lam : 0.0);
     }
+    TpiAcc A;
     rc = fallback ? 2 : tpi_solve<false>(d, io, M, A, sc + (size_t)rows.oJ * B, B, i, nJ, br, es, left, -1, 0.0, &id);
     if (rc == 1) { // to the second solve, with the selected bound
         const int k = atomicAdd(&s_n, 1);

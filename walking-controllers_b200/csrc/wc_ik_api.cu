@@ -182,7 +182,7 @@ wc_status wc_ik_create(const wc_ik_config* cfg, const wc_model* model, int32_t B
             // WC_IK_PATH=warp keeps the warp-per-instance fast kernel (ik_fast_kernel)
             if (hm.tpi_ok && !(pth && !std::strcmp(pth, "warp"))) {
                 const size_t rows = (size_t)ik_tpi_rows(hm.n_links, cfg->n_dofs);
-                if (cudaMalloc(&h->d.tpi_scratch, rows * (size_t)B * sizeof(double)) != cudaSuccess) { wc_ik_destroy(h); return WC_ERR_ALLOC; }
+                if (cudaMalloc(&h->d.tpi_scratch, (rows * (size_t)B + 32) * sizeof(double)) != cudaSuccess) { wc_ik_destroy(h); return WC_ERR_ALLOC; }
                 h->d.tpi_slots = hm.tpi_slots;
             }
         }
