@@ -135,19 +135,14 @@ __device__ __forceinline__ int tpi_solve(const IkDev& d, const IkTickIO& io, con
     // ---- accumulate over the joints; the ten rows of the next column are requested before the current one is used
     A.clear();
     {
-        double nx[10];
+        // two column buffers in ping-pong (loop unrolled by two): the loads that fill one are in flight while the other is used,
+        // and the two groups of loads sit on different scoreboards
+        auto load = [&](int jn, double (&buf)[10]) {
 #pragma unroll
-        for (int r = 0; r < 10; r++) nx[r] = colj[(size_t)r * B];
-#pragma unroll 1
-        for (int j = 0; j < nJ; j++) {
-            double c10[10];
-#pragma unroll
-            for (int r = 0; r < 10; r++) c10[r] = nx[r];
-            if (j + 1 < nJ) {
-#pragma unroll
-                for (int r = 0; r < 10; r++) nx[r] = colj[(size_t)(10 * (j + 1) + r) * B];
-            }
-            if (SECOND && j == pvar) continue;
+            for (int r = 0; r < 10; r++) buf[r] = colj[(size_t)(10 * jn + r) * B];
+        };
+        auto use = [&](int j, const double (&c10)[10]) {
+            if (SECOND && j == pvar) return;
             double ssw, sn;
             tpi_signs(M, left, j, ssw, sn);
             const double a[9] = {c10[0], c10[1], c10[2], ssw * c10[3], ssw * c10[4], ssw * c10[5], c10[6], c10[7], c10[8]};
@@ -155,6 +150,17 @@ __device__ __forceinline__ int tpi_solve(const IkDev& d, const IkTickIO& io, con
             double g = c10[9];
             if (SECOND) g += (u[0] * wup[0] + u[1] * wup[1] + u[2] * wup[2]) * beta;
             A.add(a, u, g, 1.0 / cfg.joint_reg_weight[j]);
+        };
+        double bA[10], bB[10];
+        load(0, bA);
+#pragma unroll 1
+        for (int j = 0; j < nJ; j += 2) {
+            if (j + 1 < nJ) load(j + 1, bB);
+            use(j, bA);
+            if (j + 1 < nJ) {
+                if (j + 2 < nJ) load(j + 2, bA);
+                use(j + 1, bB);
+            }
         }
     }
     // ---- Woodbury core K = (I + W C)^-1 W
@@ -244,18 +250,12 @@ __device__ __forceinline__ int tpi_solve(const IkDev& d, const IkTickIO& io, con
     double ew[6] = {0, 0, 0, 0, 0, 0};
     bool viol = false;
     double best = INFINITY; int id = 0x7fffffff;
-    double nx[10];
+    {
+        auto load = [&](int jn, double (&buf)[10]) {
 #pragma unroll
-    for (int r = 0; r < 10; r++) nx[r] = colj[(size_t)r * B];
-#pragma unroll 1
-    for (int j = 0; j < nJ; j++) {
-        double c10[10];
-#pragma unroll
-        for (int r = 0; r < 10; r++) c10[r] = nx[r];
-        if (j + 1 < nJ) {
-#pragma unroll
-            for (int r = 0; r < 10; r++) nx[r] = colj[(size_t)(10 * (j + 1) + r) * B];
-        }
+            for (int r = 0; r < 10; r++) buf[r] = colj[(size_t)(10 * jn + r) * B];
+        };
+        auto use = [&](int j, const double (&c10)[10]) {
         double ssw, sn;
         tpi_signs(M, left, j, ssw, sn);
         const double a[9] = {c10[0], c10[1], c10[2], ssw * c10[3], ssw * c10[4], ssw * c10[5], c10[6], c10[7], c10[8]};
@@ -280,6 +280,18 @@ __device__ __forceinline__ int tpi_solve(const IkDev& d, const IkTickIO& io, con
         if (io.dq) io.dq[(size_t)j * B + i] = nu;
 #pragma unroll
         for (int r = 0; r < 6; r++) ew[r] += a[r] * nu;
+        };
+        double bA[10], bB[10];
+        load(0, bA);
+#pragma unroll 1
+        for (int j = 0; j < nJ; j += 2) {
+            if (j + 1 < nJ) load(j + 1, bB);
+            use(j, bA);
+            if (j + 1 < nJ) {
+                if (j + 2 < nJ) load(j + 2, bA);
+                use(j + 1, bB);
+            }
+        }
     }
     if (viol) { *viol_id = id; return 1; }
     // ---- outputs: get{Left,Right}FootError (:364-401) = b - J nu
@@ -322,6 +334,9 @@ __global__ void __launch_bounds__(kTpiThreads, WC_TPI_MINB) ik_tpi_kernel(IkDev 
     if (live) {
     double* sc = d.tpi_scratch + i;
     double* slots = sm_slots + (size_t)warp * d.tpi_slots * 12 * 32 + lane;
+    // the measured joint positions are needed after the link loop: ask for their lines now (lane k: row k)
+    if (lane < nJ && (lane & 1) * 0 == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(io.q_meas + (size_t)lane * B + (i - lane)));
+    if (lane < nJ && (size_t)(i - lane) + 16 < B) asm volatile("prefetch.global.L2 [%0];" ::"l"(io.q_meas + (size_t)lane * B + (i - lane) + 16));
 #define SLOT(s, k) slots[((s) * 12 + (k)) * 32]
     // ---- root_H_link, serially over the links (parent[l] < l); first-moment prefix; joint axes and origins
     double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, p[3] = {0, 0, 0}; // root_H_(l-1) of the previous iteration
@@ -528,8 +543,7 @@ __global__ void __launch_bounds__(kTpiThreads, WC_TPI_MINB) ik_tpi_kernel(IkDev 
     bool fallback = false;
     const double Minv = 1.0 / Mtot;
     // rows of joint j the column needs: axis / origin (6), two prefix entries (3 + 3), the measured joint position
-    double nx[13];
-    auto request = [&](int jn) {
+    auto request = [&](int jn, double (&nx)[13]) {
         const int cn = M.link_of_dof[jn], ln = M.tpi_sub_last[jn];
 #pragma unroll
         for (int r = 0; r < 6; r++) nx[r] = sc[(size_t)(rows.oJ + 10 * jn + r) * B];
@@ -537,16 +551,13 @@ __global__ void __launch_bounds__(kTpiThreads, WC_TPI_MINB) ik_tpi_kernel(IkDev 
         for (int r = 0; r < 3; r++) { nx[6 + r] = sc[(size_t)(rows.oP + 3 * (ln + 1) + r) * B]; nx[9 + r] = sc[(size_t)(rows.oP + 3 * cn + r) * B]; }
         nx[12] = io.q_meas[(size_t)jn * B + i];
     };
-    request(0);
-#pragma unroll 1
-    for (int j = 0; j < nJ; j++) {
+    auto column = [&](int j, const double (&nx)[13]) {
         const int c = M.link_of_dof[j];
         double* cj = sc + (size_t)(rows.oJ + 10 * j) * B;
         double ar[3], orr[3], Sr[3];
 #pragma unroll
         for (int r = 0; r < 3; r++) { ar[r] = nx[r]; orr[r] = nx[3 + r]; Sr[r] = nx[6 + r] - nx[9 + r]; }
         const double qm = nx[12];
-        if (j + 1 < nJ) request(j + 1);
         const double ms = M.sub_mass[c];
         double a3[3], o[3], S[3];
 #pragma unroll
@@ -580,6 +591,26 @@ __global__ void __launch_bounds__(kTpiThreads, WC_TPI_MINB) ik_tpi_kernel(IkDev 
             cj[(size_t)(6 + r) * B] = cc[r];
         }
         cj[(size_t)9 * B] = gr;
+    };
+    {
+        // three rotating buffers (loop unrolled by three): the rows of joint j + 2 are requested before joint j is used -- half of
+        // these rows come back from HBM, not from L2 (the scratch of the instances in flight is ~100 MB)
+        double bA[13], bB[13], bC[13];
+        request(0, bA);
+        if (nJ > 1) request(1, bB);
+#pragma unroll 1
+        for (int j = 0; j < nJ; j += 3) {
+            if (j + 2 < nJ) request(j + 2, bC);
+            column(j, bA);
+            if (j + 1 < nJ) {
+                if (j + 3 < nJ) request(j + 3, bA);
+                column(j + 1, bB);
+            }
+            if (j + 2 < nJ) {
+                if (j + 4 < nJ) request(j + 4, bB);
+                column(j + 2, bC);
+            }
+        }
     }
     TpiAcc A;
     rc = fallback ? 2 : tpi_solve<false>(d, io, M, A, sc + (size_t)rows.oJ * B, B, i, nJ, br, es, left, -1, 0.0, &id);
