@@ -42,7 +42,10 @@ namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
 #ifndef WC_SPLIT_MINB
-#define WC_SPLIT_MINB 5
+#define WC_SPLIT_MINB 5 // warps resident per SM (shared memory: 42 KB each at N = 25)
+#endif
+#ifndef WC_SPLIT_WARPS
+#define WC_SPLIT_WARPS 1 // warps per CTA; they share nothing but the instruction stream (each has its own working set)
 #endif
 
 template <int N>
@@ -114,13 +117,14 @@ struct Ldl6 {
 // One warp per CTA, 8 instances per warp: lane = half * 16 + axis * 8 + instance slot.
 // =====================================================================================
 template <bool PHASE2, int NT>
-__global__ void __launch_bounds__(32, WC_SPLIT_MINB) mpc_split_kernel(MpcDev d, MpcTickIO io)
+__global__ void __launch_bounds__(32 * WC_SPLIT_WARPS, WC_SPLIT_MINB / WC_SPLIT_WARPS) mpc_split_kernel(MpcDev d, MpcTickIO io)
 {
     using SD = SplitDims<NT>;
     constexpr int N = NT, T = SD::T, OFF = SD::OFF, nA = 2 * N + 1, nR = N + 1;
     static_assert(N >= 4, "the split needs a separator away from u_0 / u_1");
-    extern __shared__ double sm[];
-    const int lane = threadIdx.x;
+    extern __shared__ double sm_all[];
+    const int lane = threadIdx.x & 31;
+    double* const sm = sm_all + (size_t)(threadIdx.x >> 5) * SD::total;
     const int s8 = lane & 7, a = (lane >> 3) & 1, q4 = lane >> 3;
     const bool bot = lane >= 16;
     const size_t B = (size_t)d.B;
@@ -132,7 +136,7 @@ __global__ void __launch_bounds__(32, WC_SPLIT_MINB) mpc_split_kernel(MpcDev d, 
 #define LBX_(t) sb[(t) * 16]
 #define LBU_(t) sb[(T + (t)) * 16]
 #define HC_(arr, h) sh[((SD::arr) * 8 + (h)) * 8]
-    if (!PHASE2 && blockIdx.x == 0 && lane == 0) *d.setup_count = 0; // consumed by the setup kernel of this tick
+    if (!PHASE2 && blockIdx.x == 0 && threadIdx.x == 0) *d.setup_count = 0; // consumed by the setup kernel of this tick
     const int count = PHASE2 ? *d.cont_count : d.B;
     const int ngroups = (count + 7) / 8;
     const wc_osqp_settings& st = d.st;
@@ -143,7 +147,7 @@ __global__ void __launch_bounds__(32, WC_SPLIT_MINB) mpc_split_kernel(MpcDev d, 
     const double cx0 = -cy0, cx1 = -cy1;
     const double k1 = 1.0 / alpha - 1.0;             // X~ = X+ + k1 dX
 
-    for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+    for (int grp = blockIdx.x * WC_SPLIT_WARPS + (threadIdx.x >> 5); grp < ngroups; grp += gridDim.x * WC_SPLIT_WARPS) {
     const int li = grp * 8 + s8;
     const bool valid = li < count;
     const int i = PHASE2 ? d.cont_list[valid ? li : count - 1] : (valid ? li : d.B - 1);
@@ -853,19 +857,19 @@ __global__ void __launch_bounds__(32, WC_SPLIT_MINB) mpc_split_kernel(MpcDev d, 
 template <int NT>
 static cudaError_t launch_split_t(const MpcDev& d, const MpcTickIO& io, cudaStream_t s, cudaEvent_t* mid)
 {
-    constexpr size_t smem = (size_t)SplitDims<NT>::total * sizeof(double);
+    constexpr size_t smem = (size_t)SplitDims<NT>::total * sizeof(double) * WC_SPLIT_WARPS;
     auto k1 = mpc_split_kernel<false, NT>;
     auto k2 = mpc_split_kernel<true, NT>;
     cudaError_t e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    const int blocks = (d.B + 7) / 8;
+    const int blocks = ((d.B + 7) / 8 + WC_SPLIT_WARPS - 1) / WC_SPLIT_WARPS;
     if (mid) cudaEventRecord(mid[0], s); // per-kernel timing (wc_mpc_enable_profiling)
-    k1<<<blocks, 32, smem, s>>>(d, io);
+    k1<<<blocks, 32 * WC_SPLIT_WARPS, smem, s>>>(d, io);
     if (mid) cudaEventRecord(mid[1], s);
-    const int cap = WC_SPLIT_MINB * 148;
-    k2<<<blocks < cap ? blocks : cap, 32, smem, s>>>(d, io); // grid-stride over the continuation list
+    const int cap = (WC_SPLIT_MINB / WC_SPLIT_WARPS) * 148;
+    k2<<<blocks < cap ? blocks : cap, 32 * WC_SPLIT_WARPS, smem, s>>>(d, io); // grid-stride over the continuation list
     return cudaGetLastError();
 }
 
