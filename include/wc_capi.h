@@ -258,7 +258,7 @@ void wc_model_icub_like(wc_model* m);
  * WalkingQPInverseKinematics.cpp:25-116; WalkingQPIK_qpOASES::initialize,
  * WalkingQPInverseKinematics_qpOASES.cpp:53-133; values from qpInverseKinematics.ini). */
 typedef struct wc_ik_config {
-    int32_t n_dofs;                     /* actuatedDOFs (23) */
+    int32_t n_dofs;                     /* actuatedDOFs: 12 .. 26 (23 in every shipped robot) */
     int32_t use_com_as_constraint;      /* useCoMAsConstraint (:66) */
     double com_weight[9];               /* comWeightTriplets as seen by the solver (only if !constraint) */
     double neck_weight[9];              /* neckWeightTriplets as seen by the solver, row-major 3x3 */

@@ -223,3 +223,113 @@ def test_fast_path_second_pass_share(wc, syn, oracle, cuda_device, ik_path):
     assert abs(second - (n1 + n2)) <= slack, (second, n1, n2)   # every violator takes the second pass
     assert general <= n2 + slack, (general, n1, n2)             # and (almost) only the multi-bound ones go on
     ik.close()
+
+
+def _icub_variant(wc, oracle, arms=True, neck=0):
+    """the synthetic iCub-sized tree of wc_model_icub_like with the arms locked and / or 1-3 articulated neck joints:
+    15 (legs + torso) ... 26 actuated joints (WalkingQPIK_qpOASES::initialize reads actuatedDOFs at run time,
+    WM/src/WalkingQPInverseKinematics_qpOASES.cpp:53-80).  Same table for the device and the oracle."""
+    import ctypes as C
+    mo = oracle.model_icub_like()
+    for k in range(40):
+        mo.parent[k] = 0; mo.dof[k] = -1; mo.mass[k] = 0.0
+        for j in range(9): mo.joint_R[k][j] = 0.0
+        for j in range(3): mo.joint_p[k][j] = 0.0; mo.axis[k][j] = 0.0; mo.com[k][j] = 0.0
+    links = []
+
+    def add(parent, dof, p, rpy, ax, mass, com):
+        i = len(links); links.append(i)
+        r, pt, y = rpy
+        cr, sr, cp, sp, cy, sy = np.cos(r), np.sin(r), np.cos(pt), np.sin(pt), np.cos(y), np.sin(y)
+        R = [cy * cp, cy * sp * sr - sy * cr, cy * sp * cr + sy * sr, sy * cp, sy * sp * sr + cy * cr, sy * sp * cr - cy * sr,
+             -sp, cp * sr, cp * cr]
+        mo.parent[i] = parent; mo.dof[i] = dof
+        for j in range(9): mo.joint_R[i][j] = float(R[j])
+        n = float(np.linalg.norm(ax))
+        for j in range(3):
+            mo.joint_p[i][j] = float(p[j]); mo.axis[i][j] = float(ax[j] / n) if n > 0 else 0.0; mo.com[i][j] = float(com[j])
+        mo.mass[i] = float(mass)
+        return i
+
+    nd = [0]
+
+    def dof():
+        nd[0] += 1
+        return nd[0] - 1
+
+    add(-1, -1, (0, 0, 0), (0, 0, 0), (0, 0, 0), 4.72, (0, 0, -0.03))
+    t1 = add(0, dof(), (0, 0, 0.02), (0, 0, 0), (0, 1, 0), 1.1, (0, 0, 0.01))
+    t2 = add(t1, dof(), (0, 0, 0.032), (0, 0, 0), (1, 0, 0), 1.2, (0, 0, 0.02))
+    chest = add(t2, dof(), (0, 0, 0.05), (0, 0, 0), (0, 0, 1), 7.6, (-0.01, 0, 0.09))
+    par = chest
+    for k, ax in enumerate([(0, 1, 0), (1, 0, 0), (0, 0, 1)][:max(neck - 1, 0)]):
+        par = add(par, dof(), (-0.002, 0, 0.09 if k == 0 else 0.02), (0, 0, 0), ax, 0.2, (0, 0, 0.01))
+    head = add(par, dof() if neck >= 1 else -1, (-0.005, 0, 0.21 if neck <= 1 else 0.1), (0, 0.05, 0), (0, 0, 1) if neck >= 1 else (0, 0, 0),
+               2.6, (0.01, 0, 0.08))
+    for s in range(2):
+        sg = 1.0 if s == 0 else -1.0
+        d4 = [dof() if arms else -1 for _ in range(4)]
+        s1 = add(chest, d4[0], (0, sg * 0.11, 0.175), (sg * 0.2618, 0, 0), (0, 1, 0) if arms else (0, 0, 0), 0.9, (0, sg * 0.02, 0))
+        s2 = add(s1, d4[1], (0, sg * 0.03, 0), (0, 0, 0), (1, 0, 0) if arms else (0, 0, 0), 0.6, (0, sg * 0.01, -0.01))
+        ua = add(s2, d4[2], (0, 0, -0.02), (0, 0, 0), (0, 0, 1) if arms else (0, 0, 0), 1.3, (0, 0, -0.07))
+        add(ua, d4[3], (0.015, 0, -0.152), (0, 0, 0), (0, 1, 0) if arms else (0, 0, 0), 1.0, (0, 0, -0.09))
+    foot = [0, 0]
+    for s in range(2):
+        sg = 1.0 if s == 0 else -1.0
+        h1 = add(0, dof(), (0, sg * 0.068, -0.12), (0, 0, 0), (0, 1, 0), 0.75, (0, sg * 0.01, 0))
+        h2 = add(h1, dof(), (0, 0, 0), (0, 0, 0), (1, 0, 0), 0.53, (0, 0, -0.02))
+        ul = add(h2, dof(), (0, 0, -0.04), (0, 0, 0), (0, 0, 1), 2.2, (0, 0, -0.09))
+        ll = add(ul, dof(), (0, 0, -0.2), (0, 0, 0), (0, 1, 0), 1.3, (0, 0, -0.1))
+        a1 = add(ll, dof(), (0, 0, -0.21), (0, 0, 0), (0, 1, 0), 0.75, (0, 0, 0))
+        foot[s] = add(a1, dof(), (0, 0, -0.02), (0, 0, 0), (1, 0, 0), 0.65, (0.025, 0, -0.02))
+    mo.n_links, mo.n_dofs = len(links), nd[0]
+    mo.l_sole_link, mo.r_sole_link, mo.neck_link = foot[0], foot[1], head
+    mg = wc.model_icub_like()
+    assert C.sizeof(mg) == C.sizeof(mo)
+    C.memmove(C.byref(mg), C.byref(mo), C.sizeof(mo))
+    return mg, mo
+
+
+@pytest.mark.parametrize("arms,neck", [(False, 0), (False, 3), (True, 1), (True, 3)])
+def test_runtime_n_dofs(wc, syn, oracle, cuda_device, arms, neck):
+    """15, 18, 24 and 26 actuated joints: FK / Jacobians, the QP-IK tick (fast path and general kernel, with active velocity
+    bounds) and the OSQP-based variant against the oracle"""
+    B = 200
+    mg, mo = _icub_variant(wc, oracle, arms, neck)
+    nJ = mo.n_dofs
+    assert nJ == 15 + (8 if arms else 0) + neck
+    cfg_o = oracle.ik_default_config(); cfg_g = wc.ik_default_config()
+    rng = np.random.default_rng(nJ)
+    reg = rng.uniform(-0.4, 0.4, nJ)
+    for c in (cfg_o, cfg_g):
+        c.n_dofs = nJ
+        for i in range(nJ):
+            c.joint_reg_rad[i] = float(reg[i]); c.joint_reg_weight[i] = 1.0 + (i % 2); c.joint_reg_gain[i] = 5.0
+            c.min_vel[i] = -0.4; c.max_vel[i] = 0.4
+    qreg = torch.tensor(reg, dtype=torch.float64)
+
+    def fkb(ql, bH, lif):
+        o = oracle.fk_batch(mo, ql.numpy(), bH.numpy(), lif.numpy(), jacobians=False)
+        return {k: torch.from_numpy(v) for k, v in o.items()}
+
+    inp = syn.ik_inputs(B, 100 + nJ, qreg, fkb)
+    ik = wc.IkBatch(cfg_g, mg, B)
+    g = ik.fk(inp["q_lin"].to(cuda_device), inp["base_H"].to(cuda_device), inp["left_is_fixed"].to(cuda_device))
+    torch.cuda.synchronize()
+    o = oracle.fk_batch(mo, inp["q_lin"].numpy(), inp["base_H"].numpy(), inp["left_is_fixed"].numpy())
+    for k in ("lf_H", "rf_H", "neck_R", "com", "J_lf", "J_rf", "J_neck", "J_com"):
+        assert np.abs(g[k].cpu().numpy() - o[k]).max() < 1e-12, k
+    out_o = oracle.ik_batch_tick(cfg_o, mo, {k: v.numpy() for k, v in inp.items()})
+    out = ik.tick({k: v.to(cuda_device) for k, v in inp.items()})
+    torch.cuda.synchronize()
+    _compare({k: v.cpu().numpy() for k, v in out.items()}, out_o, f"nJ={nJ}")
+    assert (out_o["nwsr"] > 0).any(), "the case should exercise the working set"
+    ik.close()
+    ik2 = wc.IkBatch(cfg_g, mg, B)
+    ik2.set_solver(wc.SOLVER_OSQP)
+    og = ik2.tick({k: v.to(cuda_device) for k, v in inp.items()})
+    torch.cuda.synchronize()
+    oo = oracle.IkOsqpBatch(cfg_o, mo, B).tick({k: v.numpy() for k, v in inp.items()})
+    assert np.array_equal(og["status"].cpu().numpy(), oo["status"]) and np.array_equal(og["nwsr"].cpu().numpy(), oo["iters"])
+    assert np.abs(og["dq"].cpu().numpy() - oo["dq"]).max() < 1e-5
+    ik2.close()

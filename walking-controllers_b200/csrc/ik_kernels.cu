@@ -1223,28 +1223,30 @@ cudaError_t launch_t(const IkDev& d, const IkTickIO& io, int mode, cudaStream_t 
     cudaError_t e = cudaFuncSetAttribute(ik_kernel<NJ, COMC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int blocks = (d.B + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    if (COMC && mode == IK_MODE_TICK && d.slow_list) {
+    if (COMC && mode == IK_MODE_TICK && d.slow_list && (d.tpi_scratch || NJ == 23)) {
         // fast path for every instance, then the general kernel on the compacted remainder
-        using LF = IkFastLayout<NJ>;
-        const size_t smem_f = ((size_t)LF::TOTAL * kFastWarps + (WC_IK_MODEL_SMEM ? LF::MODEL_DOUBLES : 0)) * sizeof(double);
-        e = cudaFuncSetAttribute(ik_fast_kernel<NJ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(ik_fast_kernel<NJ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f);
-        if (e != cudaSuccess) return e;
         e = cudaMemsetAsync(d.slow_count, 0, 2 * sizeof(int32_t), s);
         if (e != cudaSuccess) return e;
-        if (d.tpi_scratch) { // thread-per-instance fast path (ik_tpi.cu): both fast launches, then the general kernel on slow_list
+        if (d.tpi_scratch) { // thread-per-instance fast path (ik_tpi.cu, any n_dofs), then the general kernel on slow_list
             e = launch_ik_tpi(d, io, s);
             if (e != cudaSuccess) return e;
             if (mid) cudaEventRecord(mid, s);
             ik_kernel<NJ, COMC><<<blocks, kWarpsPerBlock * 32, smem, s>>>(d, io, mode, 1);
             return cudaGetLastError();
         }
-        ik_fast_kernel<NJ, false><<<(d.B + kFastWarps - 1) / kFastWarps, kFastWarps * 32, smem_f, s>>>(d, io);
-        ik_fast_kernel<NJ, true><<<(d.B + kFastWarps - 1) / kFastWarps, kFastWarps * 32, smem_f, s>>>(d, io);
-        if (mid) cudaEventRecord(mid, s); // per-kernel timing (wc_ik_enable_profiling)
-        ik_kernel<NJ, COMC><<<blocks, kWarpsPerBlock * 32, smem, s>>>(d, io, mode, 1);
-        return cudaGetLastError();
+        if constexpr (NJ == 23) { // warp-per-instance fast kernels: instantiated for the 23-DoF iCub set only (WC_IK_PATH=warp)
+            using LF = IkFastLayout<NJ>;
+            const size_t smem_f = ((size_t)LF::TOTAL * kFastWarps + (WC_IK_MODEL_SMEM ? LF::MODEL_DOUBLES : 0)) * sizeof(double);
+            e = cudaFuncSetAttribute(ik_fast_kernel<NJ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f);
+            if (e != cudaSuccess) return e;
+            e = cudaFuncSetAttribute(ik_fast_kernel<NJ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f);
+            if (e != cudaSuccess) return e;
+            ik_fast_kernel<NJ, false><<<(d.B + kFastWarps - 1) / kFastWarps, kFastWarps * 32, smem_f, s>>>(d, io);
+            ik_fast_kernel<NJ, true><<<(d.B + kFastWarps - 1) / kFastWarps, kFastWarps * 32, smem_f, s>>>(d, io);
+            if (mid) cudaEventRecord(mid, s); // per-kernel timing (wc_ik_enable_profiling)
+            ik_kernel<NJ, COMC><<<blocks, kWarpsPerBlock * 32, smem, s>>>(d, io, mode, 1);
+            return cudaGetLastError();
+        }
     }
     ik_kernel<NJ, COMC><<<blocks, kWarpsPerBlock * 32, smem, s>>>(d, io, mode, 0);
     return cudaGetLastError();
@@ -1252,13 +1254,18 @@ cudaError_t launch_t(const IkDev& d, const IkTickIO& io, int mode, cudaStream_t 
 
 } // namespace
 
-bool ik_supported(int n_dofs) { return n_dofs == 23; }
-
-cudaError_t launch_ik(const IkDev& d, const IkTickIO& io, int mode, cudaStream_t s, cudaEvent_t mid)
+// One translation unit per number of actuated joints (-DWC_IK_NJ=n, csrc/Makefile): lane j <-> QP variable j makes the variable
+// count a compile-time size of the warp-per-instance kernels.  launch_ik (wc_ik_api.cu) dispatches on the run-time n_dofs.
+#ifndef WC_IK_NJ
+#define WC_IK_NJ 23
+#endif
+#define WC_IK_CAT2(a, b) a##b
+#define WC_IK_CAT(a, b) WC_IK_CAT2(a, b)
+cudaError_t WC_IK_CAT(launch_ik_nj, WC_IK_NJ)(const IkDev& d, const IkTickIO& io, int mode, cudaStream_t s, cudaEvent_t mid)
 {
-    if (d.nJ != 23) return cudaErrorInvalidValue;
-    if (d.cfg.use_com_as_constraint) return launch_t<23, true>(d, io, mode, s, mid);
-    return launch_t<23, false>(d, io, mode, s, mid);
+    if (d.nJ != WC_IK_NJ) return cudaErrorInvalidValue;
+    if (d.cfg.use_com_as_constraint) return launch_t<WC_IK_NJ, true>(d, io, mode, s, mid);
+    return launch_t<WC_IK_NJ, false>(d, io, mode, s, mid);
 }
 
 } // namespace wcb

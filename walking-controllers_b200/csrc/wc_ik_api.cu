@@ -145,6 +145,26 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 } // namespace
 
+// ---- run-time number of actuated joints (WalkingQPIK_qpOASES::initialize reads actuatedDOFs from the configuration,
+// WM/src/WalkingQPInverseKinematics_qpOASES.cpp:53-80): one instantiation of the warp-per-instance kernels per joint count,
+// 12 (two legs) .. 26 (6 + 26 = 32 QP variables = one warp)
+namespace wcb {
+#define WC_IK_NJ_LIST(X) X(12) X(13) X(14) X(15) X(16) X(17) X(18) X(19) X(20) X(21) X(22) X(23) X(24) X(25) X(26)
+#define WC_IK_DECL(n) cudaError_t launch_ik_nj##n(const IkDev&, const IkTickIO&, int, cudaStream_t, cudaEvent_t);
+WC_IK_NJ_LIST(WC_IK_DECL)
+#undef WC_IK_DECL
+bool ik_supported(int n_dofs) { return n_dofs >= 12 && n_dofs <= 26; }
+cudaError_t launch_ik(const IkDev& d, const IkTickIO& io, int mode, cudaStream_t s, cudaEvent_t mid)
+{
+    switch (d.nJ) {
+#define WC_IK_CASE(n) case n: return launch_ik_nj##n(d, io, mode, s, mid);
+        WC_IK_NJ_LIST(WC_IK_CASE)
+#undef WC_IK_CASE
+    default: return cudaErrorInvalidValue;
+    }
+}
+} // namespace wcb
+
 extern "C" {
 
 wc_status wc_ik_create(const wc_ik_config* cfg, const wc_model* model, int32_t B, int32_t device, wc_ik** out)
@@ -152,7 +172,7 @@ wc_status wc_ik_create(const wc_ik_config* cfg, const wc_model* model, int32_t B
     if (!cfg || !model || !out || B < 1) return WC_ERR_INVALID_ARG;
     *out = nullptr;
     if (cfg->n_dofs != model->n_dofs) return WC_ERR_INVALID_ARG;
-    if (!ik_supported(cfg->n_dofs)) return WC_ERR_UNSUPPORTED; // kernels are instantiated for the 23-DoF iCub set
+    if (!ik_supported(cfg->n_dofs)) return WC_ERR_UNSUPPORTED; // 12 .. 26 actuated joints: 6 + n QP variables fit one warp
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) return WC_ERR_NO_DEVICE;
     if (device < 0 || device >= ndev) return WC_ERR_INVALID_ARG;

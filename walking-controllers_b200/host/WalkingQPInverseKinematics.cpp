@@ -124,7 +124,7 @@ bool WalkingQPIK::initializeDevice(const yarp::os::Searchable& config, const int
     m_cfg.nwsr = 100;                                                                                           // :312
     // the device handle needs a kinematic table only for wc_ik_tick / wc_fk; this class feeds Jacobians itself
     wc_model_icub_like(&m_model);
-    if (m_model.n_dofs != actuatedDOFs) { std::cerr << "[initialize] only the 23-DoF joint set is instantiated on the device\n"; return false; }
+    if (m_model.n_dofs != actuatedDOFs) { std::cerr << "[initialize] actuatedDOFs does not match the kinematic model\n"; return false; }
     wc_ik_destroy(m_handle); m_handle = nullptr;
     const wc_status rc = wc_ik_create(&m_cfg, &m_model, 1, 0, &m_handle);
     if (rc != WC_OK) { std::cerr << "[initialize] wc_ik_create failed with status " << rc << "\n"; return false; }
