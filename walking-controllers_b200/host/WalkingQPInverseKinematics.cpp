@@ -124,7 +124,26 @@ bool WalkingQPIK::initializeDevice(const yarp::os::Searchable& config, const int
     m_cfg.nwsr = 100;                                                                                           // :312
     // the device handle needs a kinematic table only for wc_ik_tick / wc_fk; this class feeds Jacobians itself
     wc_model_icub_like(&m_model);
-    if (m_model.n_dofs != actuatedDOFs) { std::cerr << "[initialize] actuatedDOFs does not match the kinematic model\n"; return false; }
+    if (m_model.n_dofs != actuatedDOFs) {
+        // any other joint set (12 .. 26 joints): a placeholder table of the right size -- a pelvis with two serial chains -- is enough,
+        // since the Jacobians and transforms come from the caller (setRobotState / set*Jacobian)
+        if (actuatedDOFs < 12 || actuatedDOFs > 26) { std::cerr << "[initialize] actuatedDOFs must be in [12, 26].\n"; return false; }
+        std::memset(&m_model, 0, sizeof(m_model));
+        m_model.n_links = actuatedDOFs + 1; m_model.n_dofs = actuatedDOFs;
+        m_model.parent[0] = -1; m_model.dof[0] = -1; m_model.mass[0] = 1.0;
+        m_model.joint_R[0][0] = m_model.joint_R[0][4] = m_model.joint_R[0][8] = 1.0;
+        const int half = actuatedDOFs / 2;
+        for (int i = 1; i <= actuatedDOFs; i++) {
+            m_model.parent[i] = (i == 1 || i == half + 1) ? 0 : i - 1;
+            m_model.dof[i] = i - 1; m_model.mass[i] = 1.0;
+            m_model.joint_R[i][0] = m_model.joint_R[i][4] = m_model.joint_R[i][8] = 1.0;
+            m_model.joint_p[i][2] = -0.1; m_model.axis[i][1] = 1.0;
+        }
+        m_model.l_sole_link = half; m_model.r_sole_link = actuatedDOFs; m_model.neck_link = 0;
+        m_model.l_sole_R[0] = m_model.l_sole_R[4] = m_model.l_sole_R[8] = 1.0;
+        m_model.r_sole_R[0] = m_model.r_sole_R[4] = m_model.r_sole_R[8] = 1.0;
+        m_model.neck_R[0] = m_model.neck_R[4] = m_model.neck_R[8] = 1.0;
+    }
     wc_ik_destroy(m_handle); m_handle = nullptr;
     const wc_status rc = wc_ik_create(&m_cfg, &m_model, 1, 0, &m_handle);
     if (rc != WC_OK) { std::cerr << "[initialize] wc_ik_create failed with status " << rc << "\n"; return false; }
