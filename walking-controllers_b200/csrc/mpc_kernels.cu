@@ -128,14 +128,16 @@ __global__ void __launch_bounds__(128) mpc_prepare_kernel(MpcDev d, MpcTickIO io
         for (int k = 0; k <= N; k++) {
             const int slot = (head + k) % nR;
             const int rr = ref_row(k);
-            d.grad[(size_t)(slot)*B + i] = -Q[0] * rbase[(size_t)(2 * rr) * B + i];
-            d.grad[(size_t)(nR + slot) * B + i] = -Q[1] * rbase[(size_t)(2 * rr + 1) * B + i];
+            const double rx = rbase[(size_t)(2 * rr) * B + i], ry = rbase[(size_t)(2 * rr + 1) * B + i];
+            d.grad[(size_t)(slot)*B + i] = d.coupled ? -(Q[0] * rx + d.Qoff[0] * ry) : -Q[0] * rx;
+            d.grad[(size_t)(nR + slot) * B + i] = d.coupled ? -(d.Qoff[1] * rx + Q[1] * ry) : -Q[1] * ry;
         }
     } else {
         const int slot = (head + N) % nR;
         const int rr = ref_row(N);
-        d.grad[(size_t)(slot)*B + i] = -Q[0] * rbase[(size_t)(2 * rr) * B + i];
-        d.grad[(size_t)(nR + slot) * B + i] = -Q[1] * rbase[(size_t)(2 * rr + 1) * B + i];
+        const double rx = rbase[(size_t)(2 * rr) * B + i], ry = rbase[(size_t)(2 * rr + 1) * B + i];
+        d.grad[(size_t)(slot)*B + i] = d.coupled ? -(Q[0] * rx + d.Qoff[0] * ry) : -Q[0] * rx;
+        d.grad[(size_t)(nR + slot) * B + i] = d.coupled ? -(d.Qoff[1] * rx + Q[1] * ry) : -Q[1] * ry;
     }
 
     d.tick_flags[i] = flags;
@@ -187,9 +189,10 @@ void launch_mpc_prepare(const MpcDev& d, const MpcTickIO& io, cudaStream_t s)
 struct Smem {
     double *X, *QB, *W, *L1, *L2, *DI, *DD, *YE, *DYE, *CM, *CA, *CB, *EE;
     double *HX, *HY, *UH, *LH, *ZH, *YH, *DYH, *EH, *CF, *RS;
+    double *L1C, *L2C, *DIC; // coupled weights only: entry (a, other axis) of the 2x2 blocks of L1, L2, D^-1, at the split index of (a, position)
 };
 
-__device__ __forceinline__ Smem carve(double* base, int N)
+__device__ __forceinline__ Smem carve(double* base, int N, int coupled)
 {
     const int nA = 2 * N + 1, nR = N + 1;
     Smem s;
@@ -200,7 +203,9 @@ __device__ __forceinline__ Smem carve(double* base, int N)
     s.CB = p; p += 2 * nR; s.EE = p; p += 2 * nR;
     s.HX = p; p += 8; s.HY = p; p += 8; s.UH = p; p += 8; s.LH = p; p += 8;
     s.ZH = p; p += 8; s.YH = p; p += 8; s.DYH = p; p += 8; s.EH = p; p += 8;
-    s.CF = p; p += 16; s.RS = p;
+    s.CF = p; p += 16; s.RS = p; p += 8;
+    s.L1C = s.L2C = s.DIC = nullptr;
+    if (coupled) { s.L1C = p; p += 2 * nA; s.L2C = p; p += 2 * nA; s.DIC = p; }
     return s;
 }
 
@@ -360,6 +365,110 @@ __device__ __forceinline__ void sweep_backward(const Smem& s, int a, int N)
     WX[N] = (WX[N] * DIX[N] - L2X[N - 1] * a2) - L1U[N - 1] * a1;
 }
 
+// ---- arbitrary 2x2 weights: the two axis chains couple at every stage, so the reduced KKT matrix is block-pentadiagonal with 2x2
+// blocks in the chain order x_N, u_{N-1}, x_{N-1}, ..., x_1, u_0, x_0 (2N+1 block positions; the hull rows on u_0 are part of that
+// position's diagonal block, no separate corner).  Block LDL' and the two substitutions run on ONE lane: the rare path.
+// Position p: even p = 2m <-> x_{N-m}, odd p = 2m+1 <-> u_{N-1-m}; entry (a, a) of a block lives in L1 / L2 / DI at the split
+// index of (a, p), entry (a, other axis) in L1C / L2C / DIC.
+__device__ __forceinline__ int blk_index(int a, int p, int N) { return a * (2 * N + 1) + ((p & 1) ? (N + 1) + (N - 1 - (p >> 1)) : N - (p >> 1)); }
+
+struct M2 { double a, b, c, d; }; // [[a, b], [c, d]]
+__device__ __forceinline__ M2 m2_mul(const M2& x, const M2& y) { return {x.a * y.a + x.b * y.c, x.a * y.b + x.b * y.d, x.c * y.a + x.d * y.c, x.c * y.b + x.d * y.d}; }
+__device__ __forceinline__ M2 m2_mul_t(const M2& x, const M2& y) { return {x.a * y.a + x.b * y.b, x.a * y.c + x.b * y.d, x.c * y.a + x.d * y.b, x.c * y.c + x.d * y.d}; } // x y'
+__device__ __forceinline__ M2 m2_sub(const M2& x, const M2& y) { return {x.a - y.a, x.b - y.b, x.c - y.c, x.d - y.d}; }
+__device__ __forceinline__ M2 m2_inv_sym(const M2& x) { const double det = x.a * x.d - x.b * x.c, id = 1.0 / det; return {x.d * id, -x.b * id, -x.c * id, x.a * id}; }
+
+__device__ bool factor_block(const Smem& s, int N, const double* cQ, const double* cR, double cqx, double cr01, double cr10, double sigma,
+                             double rho_e, const double* hull_diag, double kxy)
+{
+    const int nA = 2 * N + 1, nR = N + 1;
+    M2 Dm1 = {1, 0, 0, 1}, Dm2 = {1, 0, 0, 1}, Dim1 = {1, 0, 0, 1}, Dim2 = {1, 0, 0, 1}, L1m1 = {0, 0, 0, 0};
+    bool pd = true; // every pivot block positive definite <=> the KKT matrix has OSQP's expected inertia (n positive pivots)
+    for (int p = 0; p <= 2 * N; p++) {
+        const bool isu = p & 1;
+        const int k = isu ? N - 1 - (p >> 1) : N - (p >> 1);
+        M2 Kpp, E1 = {0, 0, 0, 0}, E2 = {0, 0, 0, 0};
+        double dd[2];
+#pragma unroll
+        for (int a = 0; a < 2; a++) {
+            const double* CM = s.CM + a * nR; const double* CA = s.CA + a * nR; const double* CB = s.CB + a * nR;
+            const double* DX = s.DD + a * nA; const double* DU = DX + nR;
+            double e1 = 0.0, e2 = 0.0;
+            if (!isu) {
+                dd[a] = cQ[a] * DX[k] * DX[k] + sigma + rho_e * (CM[k] * CM[k] + (k < N ? CA[k + 1] * CA[k + 1] : 0.0));
+                if (k < N) { e1 = rho_e * CA[k + 1] * CB[k + 1]; e2 = rho_e * CM[k + 1] * CA[k + 1]; } // with u_k (p-1), x_{k+1} (p-2)
+            } else {
+                const double sc = (k < N - 1) ? 2.0 : 1.0;
+                dd[a] = cR[a] * sc * DU[k] * DU[k] + sigma + rho_e * CB[k + 1] * CB[k + 1] + (k == 0 ? hull_diag[a] : 0.0);
+                e1 = rho_e * CM[k + 1] * CB[k + 1];                     // with x_{k+1} (p-1)
+                if (k < N - 1) e2 = -cR[a] * DU[k] * DU[k + 1];         // with u_{k+1} (p-2)
+            }
+            if (a == 0) { E1.a = e1; E2.a = e2; } else { E1.d = e1; E2.d = e2; }
+        }
+        double off;
+        if (!isu) off = cqx * s.DD[k] * s.DD[nA + k];
+        else {
+            const double sc = (k < N - 1) ? 2.0 : 1.0;
+            off = cr01 * sc * s.DD[nR + k] * s.DD[nA + nR + k] + (k == 0 ? kxy : 0.0);
+            if (k < N - 1) { // rows (u_k^x, u_k^y) against columns (u_{k+1}^x, u_{k+1}^y): P(u_k^x, u_{k+1}^y) = -R(0,1), P(u_k^y, u_{k+1}^x) = -R(1,0)
+                E2.b = -cr01 * s.DD[nR + k] * s.DD[nA + nR + k + 1];
+                E2.c = -cr10 * s.DD[nA + nR + k] * s.DD[nR + k + 1];
+            }
+        }
+        Kpp = {dd[0], off, off, dd[1]};
+        M2 L2 = {0, 0, 0, 0}, L1 = {0, 0, 0, 0};
+        if (p >= 2) L2 = m2_mul(E2, Dim2);
+        if (p >= 1) {
+            M2 t = E1;
+            if (p >= 2) t = m2_sub(t, m2_mul_t(m2_mul(L2, Dm2), L1m1));
+            L1 = m2_mul(t, Dim1);
+        }
+        M2 Dp = Kpp;
+        if (p >= 1) Dp = m2_sub(Dp, m2_mul_t(m2_mul(L1, Dm1), L1));
+        if (p >= 2) Dp = m2_sub(Dp, m2_mul_t(m2_mul(L2, Dm2), L2));
+        Dp.b = Dp.c = 0.5 * (Dp.b + Dp.c);
+        if (!(Dp.a > 0.0) || !(Dp.a * Dp.d - Dp.b * Dp.c > 0.0)) pd = false;
+        const M2 Di = m2_inv_sym(Dp);
+        const int i0 = blk_index(0, p, N), i1 = blk_index(1, p, N);
+        s.L1[i0] = L1.a; s.L1C[i0] = L1.b; s.L1C[i1] = L1.c; s.L1[i1] = L1.d;
+        s.L2[i0] = L2.a; s.L2C[i0] = L2.b; s.L2C[i1] = L2.c; s.L2[i1] = L2.d;
+        s.DI[i0] = Di.a; s.DIC[i0] = Di.b; s.DIC[i1] = Di.c; s.DI[i1] = Di.d;
+        Dm2 = Dm1; Dim2 = Dim1; Dm1 = Dp; Dim1 = Di; L1m1 = L1;
+    }
+    return pd;
+}
+
+// (P + sigma I + A' rho A) x~ = W in place, block chain
+__device__ void solve_block(const Smem& s, int N)
+{
+    double t1x = 0, t1y = 0, t2x = 0, t2y = 0;
+    for (int p = 0; p <= 2 * N; p++) { // L t = w
+        const int i0 = blk_index(0, p, N), i1 = blk_index(1, p, N);
+        const double tx = s.W[i0] - (s.L1[i0] * t1x + s.L1C[i0] * t1y) - (s.L2[i0] * t2x + s.L2C[i0] * t2y);
+        const double ty = s.W[i1] - (s.L1C[i1] * t1x + s.L1[i1] * t1y) - (s.L2C[i1] * t2x + s.L2[i1] * t2y);
+        s.W[i0] = tx; s.W[i1] = ty;
+        t2x = t1x; t2y = t1y; t1x = tx; t1y = ty;
+    }
+    double x1x = 0, x1y = 0, x2x = 0, x2y = 0; // solution at p+1, p+2
+    for (int p = 2 * N; p >= 0; p--) { // x_p = D_p^-1 t_p - L1_{p+1}' x_{p+1} - L2_{p+2}' x_{p+2}
+        const int i0 = blk_index(0, p, N), i1 = blk_index(1, p, N);
+        double xx = s.DI[i0] * s.W[i0] + s.DIC[i0] * s.W[i1];
+        double xy = s.DIC[i1] * s.W[i0] + s.DI[i1] * s.W[i1];
+        if (p + 1 <= 2 * N) {
+            const int j0 = blk_index(0, p + 1, N), j1 = blk_index(1, p + 1, N);
+            xx -= s.L1[j0] * x1x + s.L1C[j1] * x1y;
+            xy -= s.L1C[j0] * x1x + s.L1[j1] * x1y;
+        }
+        if (p + 2 <= 2 * N) {
+            const int j0 = blk_index(0, p + 2, N), j1 = blk_index(1, p + 2, N);
+            xx -= s.L2[j0] * x2x + s.L2C[j1] * x2y;
+            xy -= s.L2C[j0] * x2x + s.L2[j1] * x2y;
+        }
+        s.W[i0] = xx; s.W[i1] = xy;
+        x2x = x1x; x2y = x1y; x1x = xx; x1y = xy;
+    }
+}
+
 template <int G>
 __global__ void __launch_bounds__(128) mpc_admm_kernel(MpcDev d, MpcTickIO io, int smem_stride)
 {
@@ -379,7 +488,7 @@ __global__ void __launch_bounds__(128) mpc_admm_kernel(MpcDev d, MpcTickIO io, i
     const unsigned FULL = 0xffffffffu;
     // lanes of this instance's group: group collectives run under group-uniform control flow
     const unsigned gmask = (G == 32) ? FULL : (((1u << G) - 1u) << (grp * G));
-    Smem s = carve(smem_all + (size_t)slot * smem_stride, N);
+    Smem s = carve(smem_all + (size_t)slot * smem_stride, N, d.coupled);
 
     const wc_osqp_settings& st = d.st;
     const double sigma = st.sigma, alpha = st.alpha, infty = st.infty;
@@ -395,6 +504,8 @@ __global__ void __launch_bounds__(128) mpc_admm_kernel(MpcDev d, MpcTickIO io, i
     double rho = setup ? fmin(fmax(st.rho, kRhoMin), kRhoMax) : d.rho[i];
     const double up[2] = {d.uprev[i], d.uprev[B + i]};
     const int head = mpc_ring_head(d);
+    const bool cpl = d.coupled != 0;
+    const double qx = d.Qoff[0], r01 = d.Roff[0], r10 = d.Roff[1]; // the Hessian's cross-axis entries (0 unless cpl)
 
     // ------------------------------------------------------------------ stage in
     for (int j = gl; j < 2 * nA; j += G) {
@@ -424,8 +535,8 @@ __global__ void __launch_bounds__(128) mpc_admm_kernel(MpcDev d, MpcTickIO io, i
         s.QB[nA + k] = d.grad[(size_t)(nR + slot_k) * B + i];
     }
     if (gl == 0) { // G = -Theta' R~ e1 -> only the u_0 block (MPCSolver.cpp:244-245)
-        s.QB[nR] = -(R[0] * up[0]);
-        s.QB[nA + nR] = -(R[1] * up[1]);
+        s.QB[nR] = cpl ? -(R[0] * up[0] + d.Roff[0] * up[1]) : -(R[0] * up[0]);
+        s.QB[nA + nR] = cpl ? -(d.Roff[1] * up[0] + R[1] * up[1]) : -(R[1] * up[1]);
     }
     __syncwarp();
     if (setup) {
@@ -439,7 +550,10 @@ __global__ void __launch_bounds__(128) mpc_admm_kernel(MpcDev d, MpcTickIO io, i
                 for (int a = 0; a < 2; a++) {
                     const double* DX = s.DD + a * nA; const double* DU = DX + nR; const double* Ea = s.EE + a * nR;
                     const double dx = DX[k];
+                    const double* DXo = s.DD + (1 - a) * nA; const double* DUo = DXo + nR; // the other axis
+                    const double rnx = (a == 0) ? r01 : r10, rpv = (a == 0) ? r10 : r01;  // P(u_k^a, u_{k+1}^o), P(u_k^a, u_{k-1}^o)
                     double nrm = fabs(c * Q[a] * dx * dx);
+                    if (cpl) nrm = fmax(nrm, fabs(c * qx * dx * DXo[k]));
                     nrm = fmax(nrm, Ea[k] * dx);
                     if (k < N) nrm = fmax(nrm, ad * Ea[k + 1] * dx);
                     s.W[a * nA + k] = 1.0 / sqrt(limit_scaling(nrm));
@@ -449,6 +563,11 @@ __global__ void __launch_bounds__(128) mpc_admm_kernel(MpcDev d, MpcTickIO io, i
                         double nu = fabs(c * sc * R[a] * du * du);
                         if (k >= 1) nu = fmax(nu, fabs(c * R[a] * du * DU[k - 1]));
                         if (k < N - 1) nu = fmax(nu, fabs(c * R[a] * du * DU[k + 1]));
+                        if (cpl) {
+                            nu = fmax(nu, fabs(c * sc * r01 * du * DUo[k]));
+                            if (k >= 1) nu = fmax(nu, fabs(c * rpv * du * DUo[k - 1]));
+                            if (k < N - 1) nu = fmax(nu, fabs(c * rnx * du * DUo[k + 1]));
+                        }
                         nu = fmax(nu, bd * Ea[k + 1] * du);
                         if (k == 0) {
                             const double* Hc = (a == 0) ? s.HX : s.HY;
@@ -480,7 +599,9 @@ __global__ void __launch_bounds__(128) mpc_admm_kernel(MpcDev d, MpcTickIO io, i
                 for (int a = 0; a < 2; a++) {
                     const double* DX = s.DD + a * nA; const double* DU = DX + nR;
                     const double dx = DX[k];
-                    sum += fabs(c * Q[a] * dx * dx);
+                    const double* DXo = s.DD + (1 - a) * nA; const double* DUo = DXo + nR;
+                    const double rnx = (a == 0) ? r01 : r10, rpv = (a == 0) ? r10 : r01;
+                    sum += cpl ? fmax(fabs(c * Q[a] * dx * dx), fabs(c * qx * dx * DXo[k])) : fabs(c * Q[a] * dx * dx);
                     qn = fmax(qn, fabs(c * dx * s.QB[a * nA + k]));
                     if (k < N) {
                         const double du = DU[k];
@@ -488,6 +609,11 @@ __global__ void __launch_bounds__(128) mpc_admm_kernel(MpcDev d, MpcTickIO io, i
                         double nu = fabs(c * sc * R[a] * du * du);
                         if (k >= 1) nu = fmax(nu, fabs(c * R[a] * du * DU[k - 1]));
                         if (k < N - 1) nu = fmax(nu, fabs(c * R[a] * du * DU[k + 1]));
+                        if (cpl) {
+                            nu = fmax(nu, fabs(c * sc * r01 * du * DUo[k]));
+                            if (k >= 1) nu = fmax(nu, fabs(c * rpv * du * DUo[k - 1]));
+                            if (k < N - 1) nu = fmax(nu, fabs(c * rnx * du * DUo[k + 1]));
+                        }
                         sum += nu;
                         qn = fmax(qn, fabs(c * du * s.QB[a * nA + nR + k]));
                     }
@@ -506,7 +632,7 @@ __global__ void __launch_bounds__(128) mpc_admm_kernel(MpcDev d, MpcTickIO io, i
         for (int j = gl; j < 2 * nA; j += G) d.D[(size_t)j * B + i] = s.DD[j];
         for (int j = gl; j < 2 * nR; j += G) d.Eeq[(size_t)j * B + i] = s.EE[j];
         for (int h = gl; h < kMaxHull; h += G) d.Eh[(size_t)h * B + i] = s.EH[h];
-        if (gl == 0) { d.cscale[i] = c; d.inited[i] = 1; }
+        if (gl == 0) d.cscale[i] = c; // (inited is set once the factorisation below has succeeded)
     }
     __syncwarp();
     const double cinv = 1.0 / c;
@@ -536,8 +662,21 @@ __global__ void __launch_bounds__(128) mpc_admm_kernel(MpcDev d, MpcTickIO io, i
     __syncwarp();
 
     // ------------------------------------------------------------------ factorisation
-    auto factor = [&](double rho_now) {
+    // returns false when the reduced KKT matrix is not positive definite (arbitrary weight triplets can make the problem
+    // non-convex: osqp_setup then fails on the inertia of the KKT factorisation and there is no solver)
+    auto factor = [&](double rho_now) -> bool {
         const double rho_e = kRhoEqOverIneq * rho_now;
+        if (cpl) {
+            int ok = 1;
+            if (gl == 0) {
+                double hd[2] = {0.0, 0.0}, kxy = 0.0;
+                for (int h = 0; h < nh; h++) { hd[0] += rho_now * s.HX[h] * s.HX[h]; hd[1] += rho_now * s.HY[h] * s.HY[h]; kxy += rho_now * s.HX[h] * s.HY[h]; }
+                const double cQ2[2] = {c * Q[0], c * Q[1]}, cR2[2] = {c * R[0], c * R[1]};
+                ok = factor_block(s, N, cQ2, cR2, c * qx, c * r01, c * r10, sigma, rho_e, hd, kxy) ? 1 : 0;
+            }
+            __syncwarp();
+            return __shfl_sync(gmask, ok, grp * G) != 0;
+        }
         if (gl < 2) {
             double hd = 0.0;
             for (int h = 0; h < nh; h++) { const double v = (gl == 0) ? s.HX[h] : s.HY[h]; hd += rho_now * v * v; }
@@ -550,13 +689,15 @@ __global__ void __launch_bounds__(128) mpc_admm_kernel(MpcDev d, MpcTickIO io, i
             factor_corner(s.RS, s.RS + 3, kxy, s.CF);
         }
         __syncwarp();
+        return true;
     };
-    factor(rho);
+    const bool setup_failed = !factor(rho) && setup;
+    if (setup && !setup_failed && gl == 0) d.inited[i] = 1;
 
     // ------------------------------------------------------------------ ADMM (osqp_solve)
     int status = WC_OSQP_UNSOLVED;
     int iter_done = 0, rho_updates = 0;
-    bool done = skip;
+    bool done = skip || setup_failed; // no solver: status stays UNSOLVED, the controller keeps its previous output
     double pri_res = 0.0, dua_res = 0.0;
     // norms kept from the last update_info (needed by check_termination and compute_rho_estimate)
     double nz_u = 0, nAx_u = 0, nq_u = 0, nAty_u = 0, nPx_u = 0;
@@ -571,7 +712,10 @@ __global__ void __launch_bounds__(128) mpc_admm_kernel(MpcDev d, MpcTickIO io, i
         const double* VX = V + a * nA; const double* VU = VX + nR;
         const double* Ya = Yeq + a * nR;
         const double* CMa = s.CM + a * nR; const double* CAa = s.CA + a * nR; const double* CBa = s.CB + a * nR;
+        const double* DXo = s.DD + (1 - a) * nA; const double* DUo = DXo + nR;
+        const double* VXo = V + (1 - a) * nA; const double* VUo = VXo + nR;
         px_x = (c * Q[a]) * DX[k] * DX[k] * VX[k];
+        if (cpl) px_x += (c * qx) * DX[k] * (DXo[k] * VXo[k]);
         aty_x = CMa[k] * Ya[k] + (k < N ? CAa[k + 1] * Ya[k + 1] : 0.0);
         px_u = 0.0; aty_u = 0.0;
         if (k < N) {
@@ -580,6 +724,13 @@ __global__ void __launch_bounds__(128) mpc_admm_kernel(MpcDev d, MpcTickIO io, i
             if (k >= 1) t -= DU[k - 1] * VU[k - 1];
             if (k < N - 1) t -= DU[k + 1] * VU[k + 1];
             px_u = (c * R[a]) * DU[k] * t;
+            if (cpl) {
+                const double rnx = (a == 0) ? r01 : r10, rpv = (a == 0) ? r10 : r01;
+                double tc = sc * r01 * (DUo[k] * VUo[k]);
+                if (k >= 1) tc -= rpv * (DUo[k - 1] * VUo[k - 1]);
+                if (k < N - 1) tc -= rnx * (DUo[k + 1] * VUo[k + 1]);
+                px_u += c * DU[k] * tc;
+            }
             aty_u = CBa[k + 1] * Ya[k + 1];
             if (k == 0) {
                 const double* Hc = (a == 0) ? s.HX : s.HY;
@@ -791,7 +942,10 @@ __global__ void __launch_bounds__(128) mpc_admm_kernel(MpcDev d, MpcTickIO io, i
             }
         }
         __syncwarp();
-        // ---- reduced KKT solve: the two axis chains run on two lanes
+        // ---- reduced KKT solve: the two axis chains run on two lanes (coupled weights: one block chain on one lane)
+        if (cpl) {
+            if (act && gl == 0) solve_block(s, N);
+        } else {
         if (act && gl < 2) sweep_forward(s, gl, N);
         __syncwarp();
         if (act && gl == 0) {
@@ -801,6 +955,7 @@ __global__ void __launch_bounds__(128) mpc_admm_kernel(MpcDev d, MpcTickIO io, i
         }
         __syncwarp();
         if (act && gl < 2) sweep_backward(s, gl, N);
+        }
         __syncwarp();
         // ---- update_z / update_y on the rows (z~ = A x~)
         if (act) {
@@ -947,7 +1102,7 @@ template <int G>
 static cudaError_t launch_admm_t(const MpcDev& d, const MpcTickIO& io, cudaStream_t s)
 {
     constexpr int IPW = 32 / G;
-    int stride = mpc_smem_doubles(d.N);
+    int stride = mpc_smem_doubles(d.N, d.coupled);
     // keep the per-instance stride == 8 (mod 16) doubles so that the two half-warps of a
     // cooperative access hit disjoint bank groups
     while ((stride % 16) != 8) stride++;

@@ -45,7 +45,12 @@ struct MpcDev {
     wc_osqp_settings st;
     int rho_interval; // resolved adaptive_rho_interval
     int ring_head;    // slot of stage 0 in the gradient ring for THIS tick
-    // per-instance weights
+    // per-instance weights (diagonals) and the handle's off-diagonal weight entries (arbitrary 2x2 triplets,
+    // WM/src/WalkingDCMModelPredictiveController.cpp:190-208): Qoff = {Q(0,1), Q(1,0)}, Roff = {R(0,1), R(1,0)}.  The Hessian takes
+    // the upper-triangular entries the reference's triplets produce (oracle/mpc_ref.c build_P), the gradient the full matrices.
+    // coupled != 0 routes the handle to the cooperative kernel's block (2x2) chain solve.
+    double Qoff[2], Roff[2];
+    int coupled;
     double* Qd; // [2][B]
     double* Rd; // [2][B]
     // persistent solver state (chain order per axis: index a*nA + j)
@@ -124,10 +129,10 @@ __host__ __device__ inline bool osqp_has_solution(int status)
 __host__ __device__ inline int mpc_nA(int N) { return 2 * N + 1; }
 __host__ __device__ inline int mpc_nR(int N) { return N + 1; }
 // doubles of shared memory per instance in K2
-__host__ __device__ inline int mpc_smem_doubles(int N)
+__host__ __device__ inline int mpc_smem_doubles(int N, int coupled = 0)
 {
     const int nA = mpc_nA(N), nR = mpc_nR(N);
-    return 2 * nA * 7   // X, QB, W, L1, L2, DI, DD
+    return 2 * nA * (coupled ? 10 : 7)   // X, QB, W, L1, L2, DI, DD (+ the off-diagonal entries of the 2x2 blocks of L1, L2, DI)
          + 2 * nR * 6   // YE, DYE, CM, CA, CB, EE
          + 8 * 8        // HX, HY, UH, LH, ZH, YH, DYH, EH
          + 16           // corner factor + scratch

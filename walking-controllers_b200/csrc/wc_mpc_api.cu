@@ -67,8 +67,9 @@ wc_status wc_mpc_create(const wc_mpc_config* cfg, int32_t B, int32_t device, wc_
 {
     if (!cfg || !out || B < 1 || cfg->horizon < 1) return WC_ERR_INVALID_ARG;
     *out = nullptr;
-    // fast path: diagonal weights (all shipped configurations); see DESIGN.md
-    if (cfg->Q[1] != 0.0 || cfg->Q[2] != 0.0 || cfg->R[1] != 0.0 || cfg->R[2] != 0.0) return WC_ERR_UNSUPPORTED;
+    // diagonal weights (all shipped configurations) take the per-axis chain kernels; arbitrary 2x2 triplets the cooperative kernel's
+    // block chain
+    const bool coupled = cfg->Q[1] != 0.0 || cfg->Q[2] != 0.0 || cfg->R[1] != 0.0 || cfg->R[2] != 0.0;
     if (!(cfg->sampling_time > 0) || !(cfg->com_height > 0) || !(cfg->gravity > 0)) return WC_ERR_INVALID_ARG;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) return WC_ERR_NO_DEVICE;
@@ -103,6 +104,8 @@ wc_status wc_mpc_create(const wc_mpc_config* cfg, int32_t B, int32_t device, wc_
     if (cfg->osqp.adaptive_rho && d.rho_interval == 0)
         d.rho_interval = cfg->osqp.check_termination ? 4 * cfg->osqp.check_termination : 100;
     d.ring_head = 0;
+    d.coupled = coupled ? 1 : 0;
+    d.Qoff[0] = cfg->Q[1]; d.Qoff[1] = cfg->Q[2]; d.Roff[0] = cfg->R[1]; d.Roff[1] = cfg->R[2];
 
     const size_t Bz = (size_t)B;
     const int nA = mpc_nA(d.N), nR = mpc_nR(d.N);
@@ -140,7 +143,7 @@ wc_status wc_mpc_create(const wc_mpc_config* cfg, int32_t B, int32_t device, wc_
     lanes = env_int("WC_MPC_LANES", lanes);
     if (!(lanes == 2 || lanes == 4 || lanes == 8 || lanes == 16 || lanes == 32)) lanes = 8;
     // the per-instance working set must fit in one CTA's shared memory
-    int stride = mpc_smem_doubles(d.N);
+    int stride = mpc_smem_doubles(d.N, d.coupled);
     while ((stride % 16) != 8) stride++;
     while (lanes < 32 && (size_t)stride * 8 * (32 / lanes) > (size_t)mpc_admm_max_smem()) lanes *= 2;
     if ((size_t)stride * 8 * (32 / lanes) > (size_t)mpc_admm_max_smem()) { wc_mpc_destroy(h); return WC_ERR_UNSUPPORTED; }
@@ -148,9 +151,9 @@ wc_status wc_mpc_create(const wc_mpc_config* cfg, int32_t B, int32_t device, wc_
     // short horizons: one thread per axis chain (16 instances per warp) when the working set of a warp
     // fits in shared memory; WC_MPC_PATH=coop|chain overrides (tuning / tests)
     // and four lanes per instance with the iterate in registers (mpc_split.cu) at the compile-time horizons
-    h->chain = mpc_split_supported(d.N) ? 2 : (mpc_chain_preferred(d.N) ? 1 : 0);
+    h->chain = d.coupled ? 0 : (mpc_split_supported(d.N) ? 2 : (mpc_chain_preferred(d.N) ? 1 : 0));
     if (const char* pth = std::getenv("WC_MPC_PATH")) {
-        if (!std::strcmp(pth, "coop")) h->chain = 0;
+        if (!std::strcmp(pth, "coop") || d.coupled) h->chain = 0;
         else if (!std::strcmp(pth, "chain")) {
             if (!mpc_chain_supported(d.N)) { wc_mpc_destroy(h); return WC_ERR_UNSUPPORTED; }
             h->chain = 1;
