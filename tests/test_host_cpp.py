@@ -68,3 +68,30 @@ def test_dropin_classes_follow_the_reference_call_sequence(cuda_device, horizon,
     out = subprocess.run([exe, str(horizon), str(ticks)], capture_output=True, text=True, timeout=600)
     print(out.stdout, out.stderr[-2000:])
     assert out.returncode == 0, out.stdout + out.stderr[-2000:]
+
+
+def test_real_idyntree_binding_compiles(wc):
+    """`make check_real_api`: every drop-in class and a caller of the reference's call sequence compiled with
+    -DWC_USE_REAL_IDYNTREE against host/mock_include, a header set with ONLY genuine iDynTree 0.11 / YARP 3.1 members
+    (WM/include/WalkingQPInverseKinematics.hpp:91-207 for the signatures) -- the binding INTEGRATION.md describes."""
+    wc.build()
+    subprocess.check_call(["make", "-C", HOST, "check_real_api"], stdout=subprocess.DEVNULL)
+    assert os.path.exists(os.path.join(HOST, "real_api_caller"))
+    # the mock must not leak the stand-in API: no member of that name anywhere in it
+    for root, _, files in os.walk(os.path.join(HOST, "mock_include")):
+        for f in files:
+            if f.endswith(".h"):
+                txt = open(os.path.join(root, f)).read()
+                for banned in ("toH12", "fromH12", "fromIniFile", " list(", " number("):
+                    assert banned not in txt, (f, banned)
+
+
+@pytest.mark.gpu
+def test_real_api_caller_runs_one_tick(cuda_device):
+    """the caller written against genuine iDynTree / YARP signatures runs one MPC + QP-IK + reactive-controller tick on the GPU"""
+    exe = os.path.join(HOST, "real_api_caller")
+    if not os.path.exists(exe):
+        _build("check_real_api")
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    print(out.stdout, out.stderr[-2000:])
+    assert out.returncode == 0, out.stdout + out.stderr[-2000:]

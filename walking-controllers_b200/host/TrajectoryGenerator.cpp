@@ -11,24 +11,24 @@ bool TrajectoryGenerator::initialize(const yarp::os::Searchable& config) { retur
 bool TrajectoryGenerator::configurePlanner(const yarp::os::Searchable& config)
 {
     if (config.isNull()) { std::cerr << "[configurePlanner] Empty configuration for unicycle planner.\n"; return false; } // :46-50
-    m_dT = config.number("sampling_time", 0.016);                                                                          // :54
-    m_plannerHorizon = config.number("plannerHorizon", 20.0);                                                              // :55
-    const auto& l = config.list("leftZMPDelta");                                                                           // :65-79
-    const auto& r = config.list("rightZMPDelta");
+    m_dT = wc_compat::cfg_number(config, "sampling_time", 0.016);                                                                          // :54
+    m_plannerHorizon = wc_compat::cfg_number(config, "plannerHorizon", 20.0);                                                              // :55
+    const auto& l = wc_compat::cfg_list(config, "leftZMPDelta");                                                                           // :65-79
+    const auto& r = wc_compat::cfg_list(config, "rightZMPDelta");
     if (l.size() != 2 || r.size() != 2) { std::cerr << "[configurePlanner] Initialization failed while reading the ZMP deltas.\n"; return false; }
-    const double nominalDuration = config.number("nominalDuration", 4.0);                                                  // :97
-    const double switchOverSwingRatio = config.number("switchOverSwingRatio", 0.4);                                        // :99-100
+    const double nominalDuration = wc_compat::cfg_number(config, "nominalDuration", 4.0);                                                  // :97
+    const double switchOverSwingRatio = wc_compat::cfg_number(config, "switchOverSwingRatio", 0.4);                                        // :99-100
     m_samples = static_cast<int>(std::round(m_plannerHorizon / m_dT));
     wc_traj_default_config(&m_cfg, m_samples, 0);
     m_cfg.sampling_time = m_dT;
     m_cfg.step_ticks = static_cast<int32_t>(std::round(nominalDuration / m_dT));
     m_cfg.ds_ticks = static_cast<int32_t>(nominalDuration * switchOverSwingRatio / (1.0 + switchOverSwingRatio) / m_dT);
     m_cfg.n_steps = (m_samples + m_cfg.step_ticks) / m_cfg.step_ticks + 8 + 3;
-    m_cfg.nominal_width = config.number("nominalWidth", 0.04);                                                             // :103
-    m_cfg.step_height = config.number("stepHeight", 0.005);                                                                // :93
-    m_cfg.com_height = config.number("com_height", 0.49);                                                                  // :96
+    m_cfg.nominal_width = wc_compat::cfg_number(config, "nominalWidth", 0.04);                                                             // :103
+    m_cfg.step_height = wc_compat::cfg_number(config, "stepHeight", 0.005);                                                                // :93
+    m_cfg.com_height = wc_compat::cfg_number(config, "com_height", 0.49);                                                                  // :96
     m_cfg.zmp_delta[0] = 0.5 * (l[0] + r[0]); m_cfg.zmp_delta[1] = 0.5 * (r[1] - l[1]);
-    m_swingLeft = config.number("swingLeft", 1.0) != 0.0;                                                                  // :105
+    m_swingLeft = wc_compat::cfg_number(config, "swingLeft", 1.0) != 0.0;                                                                  // :105
     wc_traj_destroy(m_handle); m_handle = nullptr;
     const wc_status rc = wc_traj_create(&m_cfg, 1, 0, &m_handle);
     if (rc != WC_OK) { std::cerr << "[configurePlanner] wc_traj_create failed with status " << rc << "\n"; return false; }
@@ -82,7 +82,7 @@ bool TrajectoryGenerator::getFeetTrajectories(std::vector<iDynTree::Transform>& 
 {
     WC_REQUIRE_COMPUTED("getFeetTrajectories")
     l.resize(m_samples); r.resize(m_samples);
-    for (int s = 0; s < m_samples; s++) { l[s] = iDynTree::Transform::fromH12(&m_lfH[12 * s]); r[s] = iDynTree::Transform::fromH12(&m_rfH[12 * s]); }
+    for (int s = 0; s < m_samples; s++) { l[s] = wc_compat::fromH12(&m_lfH[12 * s]); r[s] = wc_compat::fromH12(&m_rfH[12 * s]); }
     return true;
 }
 

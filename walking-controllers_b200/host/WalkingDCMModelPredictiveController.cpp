@@ -10,19 +10,19 @@ WalkingController::~WalkingController() { wc_mpc_destroy(m_handle); }
 bool WalkingController::initialize(const yarp::os::Searchable& config)
 {
     if (config.isNull()) { std::cerr << "[initialize] Empty configuration for walking controller.\n"; return false; } // :175-179
-    const auto& zmp = config.list("initial_zmp_position");                                                                 // :317-344
+    const auto& zmp = wc_compat::cfg_list(config, "initial_zmp_position");                                                                 // :317-344
     if (zmp.size() != 2) { std::cerr << "[initialize] The dimension set in the configuration file is not 2.\n"; return false; }
     wc_mpc_default_config(&m_cfg, 1);
-    const double dT = config.number("sampling_time", 0.016);                                                               // :182
-    const double horizonSeconds = config.number("controllerHorizon", 2.0);                                                 // :185
+    const double dT = wc_compat::cfg_number(config, "sampling_time", 0.016);                                                               // :182
+    const double horizonSeconds = wc_compat::cfg_number(config, "controllerHorizon", 2.0);                                                 // :185
     m_cfg.horizon = static_cast<int32_t>(std::round(horizonSeconds / dT));                                                 // :187
     m_cfg.sampling_time = dT;
     if (!config.check("com_height")) { std::cerr << "[initialize] Unable to get the double from searchable.\n"; return false; } // :225
-    m_cfg.com_height = config.number("com_height", 0.0);
-    m_cfg.gravity = config.number("gravity_acceleration", 9.81);                                                           // :230
+    m_cfg.com_height = wc_compat::cfg_number(config, "com_height", 0.0);
+    m_cfg.gravity = wc_compat::cfg_number(config, "gravity_acceleration", 9.81);                                                           // :230
     // weight triplets (row, col, value); getTripletsFromValues stores them TRANSPOSED (Utils.cpp:93-101)
     auto triplets = [&](const char* key, double* M) -> bool {
-        const auto& t = config.list(key);
+        const auto& t = wc_compat::cfg_list(config, key);
         if (t.empty() || t.size() % 3) return false;
         for (int k = 0; k < 4; k++) M[k] = 0.0;
         for (size_t k = 0; k < t.size(); k += 3) {
@@ -34,10 +34,10 @@ bool WalkingController::initialize(const yarp::os::Searchable& config)
     };
     if (!triplets("stateWeightTriplets", m_cfg.Q)) { std::cerr << "Initialization failed while reading stateWeightTriplets vector.\n"; return false; }
     if (!triplets("inputWeightTriplets", m_cfg.R)) { std::cerr << "Initialization failed while reading inputWeightTriplets vector.\n"; return false; }
-    const auto& fs = config.list("foot_size");                                                                             // :247-303
+    const auto& fs = wc_compat::cfg_list(config, "foot_size");                                                                             // :247-303
     if (fs.size() != 4) { std::cerr << "Please set the foot_size in the configuration file.\n"; return false; }
     m_cfg.foot_x[0] = fs[0]; m_cfg.foot_x[1] = fs[1]; m_cfg.foot_y[0] = fs[2]; m_cfg.foot_y[1] = fs[3];
-    m_cfg.hull_tolerance = config.number("convex_hull_tolerance", 0.01);                                                   // :306
+    m_cfg.hull_tolerance = wc_compat::cfg_number(config, "convex_hull_tolerance", 0.01);                                                   // :306
     m_cfg.initial_zmp[0] = zmp[0]; m_cfg.initial_zmp[1] = zmp[1];
     m_output(0) = zmp[0]; m_output(1) = zmp[1];
     wc_mpc_destroy(m_handle); m_handle = nullptr;
@@ -54,8 +54,8 @@ bool WalkingController::setConvexHullConstraint(const std::deque<iDynTree::Trans
 {
     if (leftFoot.empty() || rightFoot.empty() || leftInContact.empty() || rightInContact.empty()) return false;
     // only .front() of each deque is read (:369,378-403); hull + solver are (re)built on the device
-    leftFoot.front().toH12(m_lfH);
-    rightFoot.front().toH12(m_rfH);
+    wc_compat::toH12(leftFoot.front(), m_lfH);
+    wc_compat::toH12(rightFoot.front(), m_rfH);
     m_lc = leftInContact.front(); m_rc = rightInContact.front();
     const auto feetStatus = std::make_pair(leftInContact.front(), rightInContact.front());
     if (m_feetStatus == feetStatus) return true;                                                                          // :373-374

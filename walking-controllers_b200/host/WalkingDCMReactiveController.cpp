@@ -10,12 +10,12 @@ bool WalkingDCMReactiveController::initialize(const yarp::os::Searchable& config
 {
     if (config.isNull()) { std::cerr << "[initialize] Empty configuration for DCM controller.\n"; return false; }            // :24-28
     if (!config.check("kDCM")) { std::cerr << "[initialize] Unable to get the double from searchable.\n"; return false; }    // :31-35
-    m_kDCM = config.number("kDCM", 0.0);
+    m_kDCM = wc_compat::cfg_number(config, "kDCM", 0.0);
     if (!config.check("com_height")) { std::cerr << "[initialize] Unable to get the double from searchable.\n"; return false; } // :37-42
     wc_glue_config cfg;
     wc_glue_default_config(&cfg);
-    cfg.com_height = config.number("com_height", 0.0);
-    cfg.gravity = config.number("gravity_acceleration", 9.81);                                                                 // :43-44
+    cfg.com_height = wc_compat::cfg_number(config, "com_height", 0.0);
+    cfg.gravity = wc_compat::cfg_number(config, "gravity_acceleration", 9.81);                                                                 // :43-44
     wc_glue_destroy(m_handle); m_handle = nullptr;
     const wc_status rc = wc_glue_create(&cfg, 1, 0, &m_handle);
     if (rc != WC_OK) { std::cerr << "[initialize] wc_glue_create failed with status " << rc << "\n"; return false; }

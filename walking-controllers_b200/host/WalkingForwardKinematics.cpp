@@ -20,11 +20,11 @@ bool WalkingFK::initialize(const yarp::os::Searchable& config, const wc_model& m
     m_dq.assign(m_nJ, 0.0);
     wc_glue_config gc; wc_glue_default_config(&gc);
     gc.n_dofs = m_nJ;
-    gc.sampling_time = config.number("sampling_time", gc.sampling_time);
-    gc.com_height = config.number("com_height", gc.com_height);
-    gc.gravity = config.number("gravity_acceleration", 9.81);
-    m_cutFrequency = config.number("cut_frequency", 0.0);
-    m_useFilters = config.number("use_filters", 0.0) != 0.0;
+    gc.sampling_time = wc_compat::cfg_number(config, "sampling_time", gc.sampling_time);
+    gc.com_height = wc_compat::cfg_number(config, "com_height", gc.com_height);
+    gc.gravity = wc_compat::cfg_number(config, "gravity_acceleration", 9.81);
+    m_cutFrequency = wc_compat::cfg_number(config, "cut_frequency", 0.0);
+    m_useFilters = wc_compat::cfg_number(config, "use_filters", 0.0) != 0.0;
     wc_glue_destroy(m_glue); m_glue = nullptr;
     if (wc_glue_create(&gc, 1, 0, &m_glue) != WC_OK) { std::cerr << "[initialize] Unable to create the CoM filters.\n"; return false; }
     m_comEvaluated = m_dcmEvaluated = false;
@@ -57,7 +57,7 @@ bool WalkingFK::evaluate()
 {
     if (m_evaluated) return true;
     if (!m_handle) return false;
-    double bH[12]; m_worldToBaseSole.toH12(bH);
+    double bH[12]; wc_compat::toH12(m_worldToBaseSole, bH);
     const uint8_t left = m_prevContactLeft ? 1 : 0;
     if (wc_fk_host(m_handle, m_q.data(), bH, &left, m_lfH.data(), m_rfH.data(), m_neckR.data(), m_com.data(), m_Jl.data(),
                    m_Jr.data(), m_Jn.data(), m_Jc.data()) != WC_OK)
@@ -66,8 +66,8 @@ bool WalkingFK::evaluate()
     return true;
 }
 
-iDynTree::Transform WalkingFK::getLeftFootToWorldTransform() { evaluate(); return iDynTree::Transform::fromH12(m_lfH.data()); }
-iDynTree::Transform WalkingFK::getRightFootToWorldTransform() { evaluate(); return iDynTree::Transform::fromH12(m_rfH.data()); }
+iDynTree::Transform WalkingFK::getLeftFootToWorldTransform() { evaluate(); return wc_compat::fromH12(m_lfH.data()); }
+iDynTree::Transform WalkingFK::getRightFootToWorldTransform() { evaluate(); return wc_compat::fromH12(m_rfH.data()); }
 iDynTree::Rotation WalkingFK::getNeckOrientation() { evaluate(); iDynTree::Rotation R; std::memcpy(R.data(), m_neckR.data(), 9 * sizeof(double)); return R; }
 bool WalkingFK::getCoMPosition(iDynTree::Position& c)
 {

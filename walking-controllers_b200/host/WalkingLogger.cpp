@@ -10,8 +10,8 @@ bool WalkingLogger::configure(const yarp::os::Searchable& config, const std::str
 {
     (void)name;
     if (config.isNull()) { std::cerr << "[configureLogger] Empty configuration for the force torque sensors.\n"; return false; }
-    m_dT = config.number("sampling_time", 0.01);
-    m_fileName = config.check("file_name") ? config.string("file_name", "") : std::string();
+    m_dT = wc_compat::cfg_number(config, "sampling_time", 0.01);
+    m_fileName = config.check("file_name") ? wc_compat::cfg_string(config, "file_name", "") : std::string();
     return true;
 }
 

@@ -9,7 +9,7 @@
 namespace {
 bool triplets3(const yarp::os::Searchable& cfg, const char* key, double* M)
 {
-    const auto& t = cfg.list(key);
+    const auto& t = wc_compat::cfg_list(cfg, key);
     if (t.empty() || t.size() % 3) return false;
     for (int k = 0; k < 9; k++) M[k] = 0.0;
     for (size_t k = 0; k < t.size(); k += 3) {
@@ -31,8 +31,8 @@ bool WalkingQPIK::initializeMatrices(const yarp::os::Searchable& config) // QPIK
     if (!triplets3(config, "neckWeightTriplets", m_cfg.neck_weight)) {
         std::cerr << "Initialization failed while reading neckWeightTriplets vector.\n"; return false;
     }
-    const auto& w = config.list("jointRegularizationWeights");
-    const auto& g = config.list("jointRegularizationGains");
+    const auto& w = wc_compat::cfg_list(config, "jointRegularizationWeights");
+    const auto& g = wc_compat::cfg_list(config, "jointRegularizationGains");
     if (static_cast<int>(w.size()) != m_actuatedDOFs) { std::cerr << "Initialization failed while reading jointRegularizationWeights vector.\n"; return false; }
     if (static_cast<int>(g.size()) != m_actuatedDOFs) { std::cerr << "Initialization failed while reading jointRegularizationGains vector.\n"; return false; }
     for (int i = 0; i < m_actuatedDOFs; i++) { m_cfg.joint_reg_weight[i] = w[i]; m_cfg.joint_reg_gain[i] = g[i]; }
@@ -42,7 +42,7 @@ bool WalkingQPIK::initializeMatrices(const yarp::os::Searchable& config) // QPIK
     double* dst[4] = {&m_cfg.k_pos_foot, &m_cfg.k_att_foot, &m_cfg.k_neck, &m_cfg.k_pos_com};
     for (int k = 0; k < 4; k++) {
         if (!config.check(keys[k])) { std::cerr << "Initialization failed while reading " << keys[k] << ".\n"; return false; }
-        *dst[k] = config.number(keys[k], 0.0);
+        *dst[k] = wc_compat::cfg_number(config, keys[k], 0.0);
     }
     return true;
 }
@@ -100,11 +100,11 @@ bool WalkingQPIK::initializeDevice(const yarp::os::Searchable& config, const int
     if (actuatedDOFs < 1 || actuatedDOFs > WC_MAX_DOFS) return false;
     wc_ik_default_config(&m_cfg);
     m_cfg.n_dofs = actuatedDOFs;
-    m_useCoMAsConstraint = config.number("useCoMAsConstraint", 0.0) != 0.0;                                     // :66
+    m_useCoMAsConstraint = wc_compat::cfg_number(config, "useCoMAsConstraint", 0.0) != 0.0;                                     // :66
     m_cfg.use_com_as_constraint = m_useCoMAsConstraint ? 1 : 0;
     m_numberOfVariables = m_actuatedDOFs + 6;                                                                   // :73
     m_numberOfConstraints = m_useCoMAsConstraint ? 15 : 12;                                                     // :77-80
-    const auto& reg = config.list("jointRegularization");                                                       // :94-103
+    const auto& reg = wc_compat::cfg_list(config, "jointRegularization");                                                       // :94-103
     if (static_cast<int>(reg.size()) != m_actuatedDOFs) {
         std::cerr << "[initialize] Unable to convert a YARP list to an iDynTree::VectorDynSize, joint regularization\n"; return false;
     }
@@ -118,7 +118,7 @@ bool WalkingQPIK::initializeDevice(const yarp::os::Searchable& config, const int
         std::cerr << "[setVelocityBounds] The size of the vector limits has to be equal to the number of the joint\n"; return false;
     }
     for (int i = 0; i < m_actuatedDOFs; i++) { m_cfg.min_vel[i] = minJointsLimit(i); m_cfg.max_vel[i] = maxJointsLimit(i); }
-    const auto& add = config.list("additional_rotation");                                                       // :118
+    const auto& add = wc_compat::cfg_list(config, "additional_rotation");                                                       // :118
     if (add.size() != 9) { std::cerr << "[initialize] Unable to set the additional rotation.\n"; return false; }
     for (int k = 0; k < 9; k++) m_cfg.additional_rotation[k] = add[k];
     m_cfg.nwsr = 100;                                                                                           // :312
@@ -172,12 +172,14 @@ bool WalkingQPIK_qpOASES::solve()
         if (wc_ik_create(&m_cfg, &m_model, 1, 0, &m_handle) != WC_OK) return false;
     }
     double lfH[12], rfH[12], lfd[12], rfd[12];
-    m_leftFootToWorldTransform.toH12(lfH); m_rightFootToWorldTransform.toH12(rfH);
-    m_desiredLeftFootToWorldTransform.toH12(lfd); m_desiredRightFootToWorldTransform.toH12(rfd);
+    wc_compat::toH12(m_leftFootToWorldTransform, lfH); wc_compat::toH12(m_rightFootToWorldTransform, rfH);
+    wc_compat::toH12(m_desiredLeftFootToWorldTransform, lfd); wc_compat::toH12(m_desiredRightFootToWorldTransform, rfd);
+    double ltw[6], rtw[6]; // iDynTree::Twist has no data(): element access only
+    wc_compat::twist6(m_leftFootTwist, ltw); wc_compat::twist6(m_rightFootTwist, rtw);
     const wc_status rc = wc_ik_solve_with_jacobians_host(
         m_handle, m_jointPosition.data(), lfH, rfH, m_neckOrientation.data(), m_comPosition.data(),
         m_leftFootJacobian.data(), m_rightFootJacobian.data(), m_neckJacobian.data(), m_comJacobian.data(),
-        lfd, rfd, m_leftFootTwist.data(), m_rightFootTwist.data(), m_desiredComPosition.data(), m_comVelocity.data(),
+        lfd, rfd, ltw, rtw, m_desiredComPosition.data(), m_comVelocity.data(),
         m_desiredNeckOrientation.data(), m_dq.data(), m_lfErr.data(), m_rfErr.data(), &m_status, &m_nwsr);
     if (rc != WC_OK || m_status != WC_QP_SUCCESSFUL_RETURN) { std::cerr << "[solve] Unable to solve the problem.\n"; return false; } // :316-335
     m_isSolutionEvaluated = true;
@@ -217,12 +219,14 @@ bool WalkingQPIK_osqp::solve()
         if (wc_ik_create(&m_cfg, &m_model, 1, 0, &m_handle) != WC_OK || wc_ik_set_solver(m_handle, WC_IK_SOLVER_OSQP, nullptr) != WC_OK) return false;
     }
     double lfH[12], rfH[12], lfd[12], rfd[12];
-    m_leftFootToWorldTransform.toH12(lfH); m_rightFootToWorldTransform.toH12(rfH);
-    m_desiredLeftFootToWorldTransform.toH12(lfd); m_desiredRightFootToWorldTransform.toH12(rfd);
+    wc_compat::toH12(m_leftFootToWorldTransform, lfH); wc_compat::toH12(m_rightFootToWorldTransform, rfH);
+    wc_compat::toH12(m_desiredLeftFootToWorldTransform, lfd); wc_compat::toH12(m_desiredRightFootToWorldTransform, rfd);
+    double ltw[6], rtw[6]; // iDynTree::Twist has no data(): element access only
+    wc_compat::twist6(m_leftFootTwist, ltw); wc_compat::twist6(m_rightFootTwist, rtw);
     const wc_status rc = wc_ik_solve_with_jacobians_host(
         m_handle, m_jointPosition.data(), lfH, rfH, m_neckOrientation.data(), m_comPosition.data(),
         m_leftFootJacobian.data(), m_rightFootJacobian.data(), m_neckJacobian.data(), m_comJacobian.data(),
-        lfd, rfd, m_leftFootTwist.data(), m_rightFootTwist.data(), m_desiredComPosition.data(), m_comVelocity.data(),
+        lfd, rfd, ltw, rtw, m_desiredComPosition.data(), m_comVelocity.data(),
         m_desiredNeckOrientation.data(), m_dq.data(), m_lfErr.data(), m_rfErr.data(), &m_status, &m_iters);
     if (rc != WC_OK || wc_ik_osqp_info_host(m_handle, &m_flags, &m_setups) != WC_OK) return false;
     if (m_flags & 1) { std::cerr << "[solve] Unable to solve the problem.\n"; return false; }                 // :377-381

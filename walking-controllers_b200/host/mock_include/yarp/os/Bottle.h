@@ -1,0 +1,3 @@
+// MOCK: see Value.h
+#pragma once
+#include <yarp/os/Value.h>

@@ -101,7 +101,7 @@ int main(int argc, char** argv)
                   controller.setFeedback(measuredDCM) && controller.setReferenceSignal(dcmDeque, false) && controller.solve() &&
                   controller.getControllerOutput(desiredZMP);
         double lfH[12], rfH[12], dcm[2] = {measuredDCM(0), measuredDCM(1)}, zo[2];
-        leftTraj.front().toH12(lfH); rightTraj.front().toH12(rfH);
+        wc_compat::toH12(leftTraj.front(), lfH); wc_compat::toH12(rightTraj.front(), rfH);
         std::vector<double> ref(2 * (N + 1));
         for (int s = 0; s <= N; s++) { ref[2 * s] = dcmDeque[s](0); ref[2 * s + 1] = dcmDeque[s](1); }
         int ost = 0, oit = 0;
@@ -151,11 +151,12 @@ int main(int argc, char** argv)
         ok = ok && ik.solve() && ik.getSolution(dqDesired);
         // oracle
         double bH[12], olf[12], orf[12], onR[9], ocom[3], Jl[6 * 29], Jr[6 * 29], Jn[6 * 29], Jc[3 * 29], odq[23], ole[6], ore[6];
-        (stanceLeft ? leftTraj : rightTraj).front().toH12(bH);
+        wc_compat::toH12((stanceLeft ? leftTraj : rightTraj).front(), bH);
         wco_fk(&model, qDesired.data(), bH, stanceLeft, olf, orf, onR, ocom, Jl, Jr, Jn, Jc);
-        double lfd[12], rfd[12]; leftTraj.front().toH12(lfd); rightTraj.front().toH12(rfd);
+        double lfd[12], rfd[12]; wc_compat::toH12(leftTraj.front(), lfd); wc_compat::toH12(rightTraj.front(), rfd);
         int onw = 0;
-        const int ost2 = wco_ik_solve(&oik, qMeas.data(), olf, orf, onR, comMeas.data(), Jl, Jr, Jn, Jc, lfd, rfd, lTw.data(), rTw.data(),
+        double lTw6[6], rTw6[6]; wc_compat::twist6(lTw, lTw6); wc_compat::twist6(rTw, rTw6);
+        const int ost2 = wco_ik_solve(&oik, qMeas.data(), olf, orf, onR, comMeas.data(), Jl, Jr, Jn, Jc, lfd, rfd, lTw6, rTw6,
                                       comDes.data(), comVel.data(), yawRotation.inverse().data(), odq, ole, ore, &onw, nullptr, nullptr,
                                       nullptr, nullptr, nullptr);
         if (ok != (ost2 == 0) || ik.qpStatus() != ost2) { std::fprintf(stderr, "tick %d: IK status mismatch %d/%d\n", t, ik.qpStatus(), ost2); failures++; }
@@ -179,9 +180,9 @@ int main(int argc, char** argv)
             ok2 = ok2 && ikOsqp.setCoMJacobian(comJac);
             ok2 = ok2 && ikOsqp.solve() && ikOsqp.getSolution(dqOsqp);
             double odq2[23], ole2[6], ore2[6], glf[12], grf[12]; int ost3 = 0, oit3 = 0, ofl3 = 0;
-            fk.getLeftFootToWorldTransform().toH12(glf); fk.getRightFootToWorldTransform().toH12(grf);
+            wc_compat::toH12(fk.getLeftFootToWorldTransform(), glf); wc_compat::toH12(fk.getRightFootToWorldTransform(), grf);
             wco_ikosqp_solve(oikOsqp, qMeas.data(), glf, grf, fk.getNeckOrientation().data(), comMeas.data(), jl.data(), jr.data(), jn.data(),
-                             comJac.data(), lfd, rfd, lTw.data(), rTw.data(), comDes.data(), comVel.data(), yawRotation.inverse().data(),
+                             comJac.data(), lfd, rfd, lTw6, rTw6, comDes.data(), comVel.data(), yawRotation.inverse().data(),
                              odq2, ole2, ore2, &ost3, &oit3, &ofl3);
             if (ok2 != (ofl3 == 0) || ikOsqp.osqpStatus() != ost3 || ikOsqp.osqpIterations() != oit3 || ikOsqp.solverSetups() != wco_ikosqp_setups(oikOsqp)) {
                 std::fprintf(stderr, "tick %d: osqp IK mismatch (ok %d/%d status %d/%d iters %d/%d setups %d/%d)\n", t, ok2, ofl3 == 0,
@@ -256,7 +257,7 @@ int main(int argc, char** argv)
                 double lf[12], rf[12], got[12]; uint8_t lc, rc, lfix;
                 wc_traj_feet f = {lf, rf, nullptr, nullptr, &lc, &rc, &lfix, nullptr, nullptr};
                 wco_traj_feet(tw, (int)s, &f);
-                lT[s].toH12(got);
+                wc_compat::toH12(lT[s], got);
                 for (int e = 0; e < 12; e++) worst_traj = std::fmax(worst_traj, std::fabs(got[e] - lf[e]));
                 if (lC[s] != (lc != 0) || rC[s] != (rc != 0) || lFix[s] != (lfix != 0)) { std::fprintf(stderr, "trajectory: flags at %zu\n", s); failures++; break; }
             }

@@ -1,8 +1,13 @@
-// wc_compat.hpp — minimal stand-ins for the iDynTree / YARP value types that appear in the signatures
-// of the reference's hot-path classes (WalkingController, WalkingQPIK, WalkingFK).  iDynTree and YARP are
-// not available in this environment; with the real libraries present define WC_USE_REAL_IDYNTREE and
-// include their headers instead — the drop-in classes only use the tiny API subset declared here
-// (operator(), size(), data(), getRotation()/getPosition(), find()/check()).
+// wc_compat.hpp — the iDynTree / YARP value types that appear in the signatures of the reference's hot-path classes
+// (WalkingController, WalkingQPIK, WalkingFK, ...), in two interchangeable forms:
+//  * default: minimal stand-ins defined here (iDynTree and YARP are not available in this environment);
+//  * -DWC_USE_REAL_IDYNTREE: the real headers (<iDynTree/Core/...>, <yarp/os/...>).
+// The drop-in classes use (a) members that exist with the same signature in both (operator(), size(), data() of the vector /
+// matrix / rotation types, getRotation() / getPosition(), zero(), check(), isNull()) and (b) the free helpers of namespace
+// wc_compat at the end of this file, which have one implementation per form: configuration access (cfg_number / cfg_list /
+// cfg_string over yarp::os::Searchable) and the row-major 3x4 [R|p] view of a transform the C ABI uses (toH12 / fromH12).
+// `make check_real_api` compiles every class with -DWC_USE_REAL_IDYNTREE against mock_include/, a header set that exposes only
+// genuine iDynTree 0.11 / YARP 3.1 members.
 #ifndef WC_COMPAT_HPP
 #define WC_COMPAT_HPP
 
@@ -32,7 +37,15 @@ public:
 using Vector2 = VectorFixSize<2>;
 using Vector3 = VectorFixSize<3>;
 using Position = VectorFixSize<3>;
-using Twist = VectorFixSize<6>; // linear (0..2) then angular (3..5), MIXED representation
+// linear (0..2) then angular (3..5), MIXED representation; like the real class it has operator() but NO data()
+class Twist {
+    std::array<double, 6> m_{};
+public:
+    double& operator()(int i) { return m_[i]; }
+    double operator()(int i) const { return m_[i]; }
+    int size() const { return 6; }
+    void zero() { m_.fill(0.0); }
+};
 
 class Rotation {
     std::array<double, 9> m_{{1, 0, 0, 0, 1, 0, 0, 0, 1}}; // row-major
@@ -60,14 +73,6 @@ public:
     const Position& getPosition() const { return p_; }
     void setRotation(const Rotation& R) { R_ = R; }
     void setPosition(const Position& p) { p_ = p; }
-    // row-major 3x4 [R|p], the layout of include/wc_capi.h
-    void toH12(double* H) const { for (int r = 0; r < 3; r++) { for (int c = 0; c < 3; c++) H[4 * r + c] = R_(r, c); H[4 * r + 3] = p_(r); } }
-    static Transform fromH12(const double* H)
-    {
-        Transform t;
-        for (int r = 0; r < 3; r++) { for (int c = 0; c < 3; c++) t.R_(r, c) = H[4 * r + c]; t.p_(r) = H[4 * r + 3]; }
-        return t;
-    }
 };
 
 class VectorDynSize {
@@ -146,6 +151,60 @@ public:
     }
 };
 }} // namespace yarp::os
+#else // WC_USE_REAL_IDYNTREE
+#include <iDynTree/Core/MatrixDynSize.h>
+#include <iDynTree/Core/Position.h>
+#include <iDynTree/Core/Rotation.h>
+#include <iDynTree/Core/Transform.h>
+#include <iDynTree/Core/Twist.h>
+#include <iDynTree/Core/VectorDynSize.h>
+#include <iDynTree/Core/VectorFixSize.h>
+#include <yarp/os/Bottle.h>
+#include <yarp/os/Searchable.h>
+#include <yarp/os/Value.h>
 #endif // WC_USE_REAL_IDYNTREE
+
+namespace wc_compat {
+// ---- row-major 3x4 [R|p], the layout of include/wc_capi.h (same code for both forms: genuine members only)
+inline void toH12(const iDynTree::Transform& T, double* H)
+{
+    const iDynTree::Rotation& R = T.getRotation(); const iDynTree::Position& p = T.getPosition();
+    for (int r = 0; r < 3; r++) { for (int c = 0; c < 3; c++) H[4 * r + c] = R(r, c); H[4 * r + 3] = p(r); }
+}
+inline iDynTree::Transform fromH12(const double* H)
+{
+    iDynTree::Rotation R; iDynTree::Position p;
+    for (int r = 0; r < 3; r++) { for (int c = 0; c < 3; c++) R(r, c) = H[4 * r + c]; p(r) = H[4 * r + 3]; }
+    return iDynTree::Transform(R, p);
+}
+inline void twist6(const iDynTree::Twist& t, double* out) { for (int k = 0; k < 6; k++) out[k] = t(k); }
+// ---- configuration access
+#ifndef WC_USE_REAL_IDYNTREE
+inline double cfg_number(const yarp::os::Searchable& c, const std::string& key, double dflt) { return c.number(key, dflt); }
+inline std::vector<double> cfg_list(const yarp::os::Searchable& c, const std::string& key) { return c.list(key); }
+inline std::string cfg_string(const yarp::os::Searchable& c, const std::string& key, const std::string& dflt) { return c.string(key, dflt); }
+#else
+inline double cfg_number(const yarp::os::Searchable& c, const std::string& key, double dflt)
+{
+    if (!c.check(key)) return dflt;
+    const yarp::os::Value& v = c.find(key);
+    return v.isBool() ? (v.asBool() ? 1.0 : 0.0) : v.asDouble();
+}
+inline void cfg_flatten(const yarp::os::Value& v, std::vector<double>& out)
+{
+    if (v.isList()) { yarp::os::Bottle* b = v.asList(); for (int i = 0; b && i < (int)b->size(); i++) cfg_flatten(b->get(i), out); }
+    else if (!v.isNull() && !v.isString()) out.push_back(v.asDouble());
+}
+// nested lists flattened in reading order ("((0,0,7500), (1,1,7500))" -> {0,0,7500,1,1,7500})
+inline std::vector<double> cfg_list(const yarp::os::Searchable& c, const std::string& key)
+{
+    std::vector<double> out;
+    if (c.check(key)) cfg_flatten(c.find(key), out);
+    return out;
+}
+inline std::string cfg_string(const yarp::os::Searchable& c, const std::string& key, const std::string& dflt)
+{ return c.check(key) ? std::string(c.find(key).asString()) : dflt; }
+#endif
+} // namespace wc_compat
 
 #endif
