@@ -189,10 +189,11 @@ void launch_mpc_prepare(const MpcDev& d, const MpcTickIO& io, cudaStream_t s)
 struct Smem {
     double *X, *QB, *W, *L1, *L2, *DI, *DD, *YE, *DYE, *CM, *CA, *CB, *EE;
     double *HX, *HY, *UH, *LH, *ZH, *YH, *DYH, *EH, *CF, *RS;
+    double *ZP, *RT, *RED;   // segment-parallel solve only: work vector [2nA], separator right-hand-side parts [2][16][4], reduced factors [2][16][8]
     double *L1C, *L2C, *DIC; // coupled weights only: entry (a, other axis) of the 2x2 blocks of L1, L2, D^-1, at the split index of (a, position)
 };
 
-__device__ __forceinline__ Smem carve(double* base, int N, int coupled)
+__device__ __forceinline__ Smem carve(double* base, int N, int coupled, int par)
 {
     const int nA = 2 * N + 1, nR = N + 1;
     Smem s;
@@ -205,7 +206,9 @@ __device__ __forceinline__ Smem carve(double* base, int N, int coupled)
     s.ZH = p; p += 8; s.YH = p; p += 8; s.DYH = p; p += 8; s.EH = p; p += 8;
     s.CF = p; p += 16; s.RS = p; p += 8;
     s.L1C = s.L2C = s.DIC = nullptr;
-    if (coupled) { s.L1C = p; p += 2 * nA; s.L2C = p; p += 2 * nA; s.DIC = p; }
+    if (coupled) { s.L1C = p; p += 2 * nA; s.L2C = p; p += 2 * nA; s.DIC = p; p += 2 * nA; }
+    s.ZP = s.RT = s.RED = nullptr;
+    if (par) { s.ZP = p; p += 2 * nA; s.RT = p; p += 2 * 16 * 4; s.RED = p; }
     return s;
 }
 
@@ -488,7 +491,7 @@ __global__ void __launch_bounds__(128) mpc_admm_kernel(MpcDev d, MpcTickIO io, i
     const unsigned FULL = 0xffffffffu;
     // lanes of this instance's group: group collectives run under group-uniform control flow
     const unsigned gmask = (G == 32) ? FULL : (((1u << G) - 1u) << (grp * G));
-    Smem s = carve(smem_all + (size_t)slot * smem_stride, N, d.coupled);
+    Smem s = carve(smem_all + (size_t)slot * smem_stride, N, d.coupled, d.par);
 
     const wc_osqp_settings& st = d.st;
     const double sigma = st.sigma, alpha = st.alpha, infty = st.infty;
@@ -661,6 +664,212 @@ __global__ void __launch_bounds__(128) mpc_admm_kernel(MpcDev d, MpcTickIO io, i
     double z0prev[2] = {setup ? 0.0 : d.z0[i], setup ? 0.0 : d.z0[B + i]};
     __syncwarp();
 
+
+    // ------------------------------------------------------------------ segment-parallel chain solve (d.par; long horizons)
+    // Chain positions p = 0 .. 2N per axis (even p = 2m <-> x_{N-m}, odd p = 2m+1 <-> u_{N-1-m}); K is pentadiagonal in p.
+    // Lane (axis ap, segment sg) owns the interior [p_lo, p_hi] of its segment; separator sg = positions p_hi+1, p_hi+2; the last
+    // separator is the corner (u_0, x_0).  Interiors are eliminated in parallel (local pentadiagonal LDL'), what remains is a
+    // block-tridiagonal system over the separators of an axis (2x2 blocks, eliminated serially by the axis' first lane) that
+    // ends in the same (u_0, x_0) Schur complement the serial path hands to the dense 4x4 corner.
+    const bool par = d.par != 0 && !cpl;
+    constexpr int PS = G / 2;                      // segments per axis
+    const int ap = gl / PS, sg = gl % PS;
+    int p_lo = 0, p_hi = -1;
+    {
+        const int nInt = nA - 2 * PS, base = nInt / PS, rem = nInt % PS;
+        p_lo = sg * (base + 2) + (sg < rem ? sg : rem);
+        p_hi = p_lo + base + (sg < rem ? 1 : 0) - 1;
+    }
+    const double cQa = c * Q[ap < 2 ? ap : 0], cRa = c * R[ap < 2 ? ap : 0];
+    auto kdiag = [&](int p, double rho_e, double hd) -> double {
+        const double* CM = s.CM + ap * nR; const double* CA = s.CA + ap * nR; const double* CB = s.CB + ap * nR;
+        const double* DX = s.DD + ap * nA; const double* DU = DX + nR;
+        if (!(p & 1)) { const int k = N - (p >> 1); return cQa * DX[k] * DX[k] + sigma + rho_e * (CM[k] * CM[k] + (k < N ? CA[k + 1] * CA[k + 1] : 0.0)); }
+        const int k = N - 1 - (p >> 1);
+        const double sc = (k < N - 1) ? 2.0 : 1.0;
+        return cRa * sc * DU[k] * DU[k] + sigma + rho_e * CB[k + 1] * CB[k + 1] + (k == 0 ? hd : 0.0);
+    };
+    auto kof1 = [&](int p, double rho_e) -> double { // K[p, p+1], p <= 2N-1
+        const double* CM = s.CM + ap * nR; const double* CA = s.CA + ap * nR; const double* CB = s.CB + ap * nR;
+        if (!(p & 1)) { const int k = N - (p >> 1); return rho_e * CM[k] * CB[k]; }
+        const int k = N - 1 - (p >> 1); return rho_e * CA[k + 1] * CB[k + 1];
+    };
+    auto kof2 = [&](int p, double rho_e) -> double { // K[p, p+2], p <= 2N-2
+        const double* CM = s.CM + ap * nR; const double* CA = s.CA + ap * nR;
+        const double* DU = s.DD + ap * nA + nR;
+        if (!(p & 1)) { const int k = N - (p >> 1); return rho_e * CM[k] * CA[k]; }
+        const int k = N - 1 - (p >> 1); return -cRa * DU[k] * DU[k - 1];
+    };
+    // local solve K_II v = src over the lane's interior (vectors indexed by the split index): forward substitution src -> tmp,
+    // backward substitution on tmp (written back only if STORE); bv = the solution at p_lo, p_lo + 1, p_hi - 1, p_hi.  The split
+    // index of position p is c0 - (p >> 1) for even p (a state) and c1 - (p >> 1) for odd p (an input): walked in pairs.
+    const int c0 = ap * nA + N, c1 = ap * nA + nR + N - 1;
+    auto split_of = [&](int p) { return ((p & 1) ? c1 : c0) - (p >> 1); };
+    auto local_solve = [&](const double* src, double* tmp, const bool STORE, double (&bv)[4]) {
+        double t1 = 0.0, t2 = 0.0;
+        auto fstep = [&](int j) {
+            const double t = (src[j] - s.L2[j] * t2) - s.L1[j] * t1;
+            tmp[j] = t; t2 = t1; t1 = t;
+        };
+        int p = p_lo;
+        if (p & 1) { fstep(c1 - (p >> 1)); p++; }
+        for (; p + 1 <= p_hi; p += 2) { const int hh = p >> 1; fstep(c0 - hh); fstep(c1 - hh); }
+        if (p <= p_hi) fstep(c0 - (p >> 1));
+        double x1 = 0.0, x2 = 0.0, l1n = 0.0, l2n = 0.0, l2nn = 0.0; // multipliers of the rows above: L1[p+1], L2[p+1], L2[p+2]
+        auto bstep = [&](int j) {
+            const double x = (tmp[j] * s.DI[j] - l2nn * x2) - l1n * x1;
+            if (STORE) tmp[j] = x;
+            x2 = x1; x1 = x;
+            l2nn = l2n; l1n = s.L1[j]; l2n = s.L2[j];
+        };
+        bstep(split_of(p_hi)); bv[3] = x1;      // (segments have at least two interior unknowns)
+        bstep(split_of(p_hi - 1)); bv[2] = x1;
+        p = p_hi - 2;
+        if (p >= p_lo && !(p & 1)) { bstep(c0 - (p >> 1)); p--; }
+        for (; p - 1 >= p_lo; p -= 2) { const int hh = p >> 1; bstep(c1 - hh); bstep(c0 - hh); } // p odd: u_k, then the state with the same shift
+        if (p >= p_lo) bstep(c1 - (p >> 1));
+        bv[0] = x1; bv[1] = x2; // the last two values produced: positions p_lo and p_lo + 1
+    };
+    auto factor_par = [&](double rho_now) {
+        const double rho_e = kRhoEqOverIneq * rho_now;
+        double hd = 0.0;
+        for (int h = 0; h < nh; h++) { const double v = (ap == 0) ? s.HX[h] : s.HY[h]; hd += rho_now * v * v; }
+        // ---- local LDL' of the interior: L1[p] = L(p, p-1), L2[p] = L(p, p-2), DI[p] = 1 / D_p
+        {
+            double Dm1 = 1.0, Dm2 = 1.0, l1m1 = 0.0;
+            for (int p = p_lo; p <= p_hi; p++) {
+                const int j = split_of(p);
+                const double e1 = p - 1 >= p_lo ? kof1(p - 1, rho_e) : 0.0, e2 = p - 2 >= p_lo ? kof2(p - 2, rho_e) : 0.0;
+                const double l2 = e2 / Dm2;
+                const double l1 = (e1 - l2 * Dm2 * l1m1) / Dm1;
+                const double Dp = kdiag(p, rho_e, hd) - l1 * l1 * Dm1 - l2 * l2 * Dm2;
+                s.L1[j] = l1; s.L2[j] = l2; s.DI[j] = 1.0 / Dp;
+                Dm2 = Dm1; Dm1 = Dp; l1m1 = l1;
+            }
+        }
+        // ---- G = K_SI K_II^-1 K_IS over the four neighbouring separator unknowns [q0, q1 | r0, r1] (q: p_lo-2, p_lo-1; r: p_hi+1, p_hi+2)
+        // couplings: (q0, p_lo): k2(q0); (q1, p_lo): k1(q1); (q1, p_lo+1): k2(q1); (p_hi, r0): k1(p_hi); (p_hi-1, r0): k2(p_hi-1); (p_hi, r1): k2(p_hi)
+        const bool hasL = sg > 0;
+        const double cq0 = hasL ? kof2(p_lo - 2, rho_e) : 0.0, cq1a = hasL ? kof1(p_lo - 1, rho_e) : 0.0, cq1b = hasL ? kof2(p_lo - 1, rho_e) : 0.0;
+        const double cr0a = kof1(p_hi, rho_e), cr0b = kof2(p_hi - 1, rho_e), cr1 = kof2(p_hi, rho_e);
+        double Gm[4][4];
+        double* Zv = s.ZP;
+#pragma unroll 1
+        for (int col = hasL ? 0 : 2; col < 4; col++) {
+            for (int p = p_lo; p <= p_hi; p++) Zv[split_of(p)] = 0.0;
+            if (col == 0) Zv[split_of(p_lo)] = cq0;
+            else if (col == 1) { Zv[split_of(p_lo)] = cq1a; Zv[split_of(p_lo + 1)] += cq1b; }
+            else if (col == 2) { Zv[split_of(p_hi)] = cr0a; Zv[split_of(p_hi - 1)] += cr0b; }
+            else Zv[split_of(p_hi)] = cr1;
+            double bv[4];
+            local_solve(Zv, Zv, false, bv);
+            const double v0 = bv[0], v1 = bv[1], vm = bv[2], ve = bv[3];
+            Gm[0][col] = cq0 * v0; Gm[1][col] = cq1a * v0 + cq1b * v1; Gm[2][col] = cr0a * ve + cr0b * vm; Gm[3][col] = cr1 * ve;
+        }
+        // publish the lane's contribution (W is free between solves): [RR (3), RL (4), LL (3)] at W[(ap * PS + sg) * 10 ...]
+        double* Gs = s.W + (ap * PS + sg) * 10;
+        Gs[0] = Gm[2][2]; Gs[1] = Gm[2][3]; Gs[2] = Gm[3][3];
+        Gs[3] = hasL ? Gm[2][0] : 0.0; Gs[4] = hasL ? Gm[2][1] : 0.0; Gs[5] = hasL ? Gm[3][0] : 0.0; Gs[6] = hasL ? Gm[3][1] : 0.0;
+        Gs[7] = hasL ? Gm[0][0] : 0.0; Gs[8] = hasL ? Gm[0][1] : 0.0; Gs[9] = hasL ? Gm[1][1] : 0.0;
+        __syncwarp(gmask);
+        // ---- reduced block-tridiagonal system over the separators of the axis: serial block LDL' on the axis' first lane
+        if (sg == 0) {
+            const int nInt = nA - 2 * PS, base = nInt / PS, rem = nInt % PS;
+            M2 Ap = {1, 0, 0, 1}, ApInv = {1, 0, 0, 1};
+            for (int t = 0; t < PS; t++) {
+                const int hi = t * (base + 2) + (t < rem ? t : rem) + base + (t < rem ? 1 : 0) - 1; // p_hi of segment t
+                const int r0 = hi + 1, r1 = hi + 2;
+                const double* Gt = s.W + (ap * PS + t) * 10;
+                M2 A = {kdiag(r0, rho_e, hd) - Gt[0], kof1(r0, rho_e) - Gt[1], kof1(r0, rho_e) - Gt[1], kdiag(r1, rho_e, hd) - Gt[2]};
+                if (t + 1 < PS) { const double* Gn = s.W + (ap * PS + t + 1) * 10; A.a -= Gn[7]; A.b -= Gn[8]; A.c -= Gn[8]; A.d -= Gn[9]; }
+                M2 LB = {0, 0, 0, 0};
+                if (t >= 1) {
+                    const M2 Bt = {-Gt[3], -Gt[4], -Gt[5], -Gt[6]}; // rows (r0, r1) of separator t, columns (q0, q1) = separator t-1
+                    LB = m2_mul(Bt, ApInv);
+                    A = m2_sub(A, m2_mul_t(m2_mul(LB, Ap), LB));
+                    A.b = A.c = 0.5 * (A.b + A.c);
+                }
+                Ap = A;
+                double* Rd = s.RED + (ap * 16 + t) * 8;
+                Rd[0] = LB.a; Rd[1] = LB.b; Rd[2] = LB.c; Rd[3] = LB.d;
+                if (t + 1 < PS) {
+                    ApInv = m2_inv_sym(Ap);
+                    Rd[4] = ApInv.a; Rd[5] = ApInv.b; Rd[6] = ApInv.c; Rd[7] = ApInv.d;
+                } else { // the corner (u_0, x_0): Schur complement for the dense 4x4
+                    s.RS[3 * ap] = Ap.a; s.RS[3 * ap + 1] = Ap.b; s.RS[3 * ap + 2] = Ap.d;
+                }
+            }
+        }
+        __syncwarp(gmask);
+        if (gl == 0) {
+            double kxy = 0.0;
+            for (int h = 0; h < nh; h++) kxy += rho_now * s.HX[h] * s.HY[h];
+            factor_corner(s.RS, s.RS + 3, kxy, s.CF);
+        }
+        __syncwarp(gmask);
+    };
+    // one reduced-KKT solve in place on W (group-uniform; `act` freezes finished instances)
+    auto solve_par = [&](bool act, double rho_now) {
+        const double rho_e = kRhoEqOverIneq * rho_now;
+        const bool hasL = sg > 0;
+        const double cq0 = hasL ? kof2(p_lo - 2, rho_e) : 0.0, cq1a = hasL ? kof1(p_lo - 1, rho_e) : 0.0, cq1b = hasL ? kof2(p_lo - 1, rho_e) : 0.0;
+        const double cr0a = kof1(p_hi, rho_e), cr0b = kof2(p_hi - 1, rho_e), cr1 = kof2(p_hi, rho_e);
+        if (act) { // pass 1: boundary values of K_II^-1 r_I -> the separators' right-hand sides
+            double bv[4];
+            local_solve(s.W, s.ZP, false, bv);
+            const double v0 = bv[0], v1 = bv[1], vm = bv[2], ve = bv[3];
+            double* rt = s.RT + (ap * 16 + sg) * 4;
+            rt[0] = cq0 * v0; rt[1] = cq1a * v0 + cq1b * v1; rt[2] = cr0a * ve + cr0b * vm; rt[3] = cr1 * ve;
+        }
+        __syncwarp(gmask);
+        const int nInt = nA - 2 * PS, base = nInt / PS, rem = nInt % PS;
+        auto sep_r0 = [&](int t) { return t * (base + 2) + (t < rem ? t : rem) + base + (t < rem ? 1 : 0); };
+        if (act && sg == 0) { // reduced forward substitution along the separators of the axis
+            double px = 0.0, py = 0.0;
+            for (int t = 0; t < PS; t++) {
+                const int j0 = split_of(sep_r0(t)), j1 = split_of(sep_r0(t) + 1);
+                const double* rt = s.RT + (ap * 16 + t) * 4;
+                double r0 = s.W[j0] - rt[2], r1 = s.W[j1] - rt[3];
+                if (t + 1 < PS) { const double* rn = s.RT + (ap * 16 + t + 1) * 4; r0 -= rn[0]; r1 -= rn[1]; }
+                const double* Rd = s.RED + (ap * 16 + t) * 8;
+                r0 -= Rd[0] * px + Rd[1] * py; r1 -= Rd[2] * px + Rd[3] * py;
+                s.W[j0] = r0; s.W[j1] = r1; px = r0; py = r1;
+            }
+        }
+        __syncwarp(gmask);
+        if (act && gl == 0) {
+            double r[4] = {s.W[nR], s.W[nA + nR], s.W[0], s.W[nA]};
+            solve_corner(s.CF, r);
+            s.W[nR] = r[0]; s.W[nA + nR] = r[1]; s.W[0] = r[2]; s.W[nA] = r[3];
+        }
+        __syncwarp(gmask);
+        if (act && sg == 0) { // reduced backward substitution
+            double nx = s.W[split_of(sep_r0(PS - 1))], ny = s.W[split_of(sep_r0(PS - 1) + 1)];
+            for (int t = PS - 2; t >= 0; t--) {
+                const int j0 = split_of(sep_r0(t)), j1 = split_of(sep_r0(t) + 1);
+                const double* Rd = s.RED + (ap * 16 + t) * 8; const double* Rn = s.RED + (ap * 16 + t + 1) * 8;
+                const double r0 = s.W[j0], r1 = s.W[j1];
+                const double x0 = (Rd[4] * r0 + Rd[5] * r1) - (Rn[0] * nx + Rn[2] * ny); // A^-1 r - LB_{t+1}' x_{t+1}
+                const double x1 = (Rd[6] * r0 + Rd[7] * r1) - (Rn[1] * nx + Rn[3] * ny);
+                s.W[j0] = x0; s.W[j1] = x1; nx = x0; ny = x1;
+            }
+        }
+        __syncwarp(gmask);
+        if (act) { // pass 2: x_I = K_II^-1 (r_I - K_IS x_S)
+            if (hasL) {
+                const double xq0 = s.W[split_of(p_lo - 2)], xq1 = s.W[split_of(p_lo - 1)];
+                s.W[split_of(p_lo)] -= cq0 * xq0 + cq1a * xq1;
+                s.W[split_of(p_lo + 1)] -= cq1b * xq1;
+            }
+            const double xr0 = s.W[split_of(p_hi + 1)], xr1 = s.W[split_of(p_hi + 2)];
+            s.W[split_of(p_hi)] -= cr0a * xr0 + cr1 * xr1;
+            s.W[split_of(p_hi - 1)] -= cr0b * xr0;
+            double bv[4];
+            local_solve(s.W, s.W, true, bv);
+        }
+        __syncwarp(gmask);
+    };
+
     // ------------------------------------------------------------------ factorisation
     // returns false when the reduced KKT matrix is not positive definite (arbitrary weight triplets can make the problem
     // non-convex: osqp_setup then fails on the inertia of the KKT factorisation and there is no solver)
@@ -677,6 +886,7 @@ __global__ void __launch_bounds__(128) mpc_admm_kernel(MpcDev d, MpcTickIO io, i
             __syncwarp();
             return __shfl_sync(gmask, ok, grp * G) != 0;
         }
+        if (par) { factor_par(rho_now); __syncwarp(); return true; }
         if (gl < 2) {
             double hd = 0.0;
             for (int h = 0; h < nh; h++) { const double v = (gl == 0) ? s.HX[h] : s.HY[h]; hd += rho_now * v * v; }
@@ -691,13 +901,16 @@ __global__ void __launch_bounds__(128) mpc_admm_kernel(MpcDev d, MpcTickIO io, i
         __syncwarp();
         return true;
     };
-    const bool setup_failed = !factor(rho) && setup;
-    if (setup && !setup_failed && gl == 0) d.inited[i] = 1;
+    // (called from ONE site, the top of the ADMM loop, so that it is inlined: a second call site makes it a real function, and
+    // every local it captures by reference -- the shared-memory pointers, rho, c, the segment bounds -- then lives in local
+    // memory for the whole kernel)
+    bool setup_failed = false;
 
     // ------------------------------------------------------------------ ADMM (osqp_solve)
     int status = WC_OSQP_UNSOLVED;
     int iter_done = 0, rho_updates = 0;
-    bool done = skip || setup_failed; // no solver: status stays UNSOLVED, the controller keeps its previous output
+    bool done = skip;
+    bool factor_pending = true, first_factor = true;
     double pri_res = 0.0, dua_res = 0.0;
     // norms kept from the last update_info (needed by check_termination and compute_rho_estimate)
     double nz_u = 0, nAx_u = 0, nq_u = 0, nAty_u = 0, nPx_u = 0;
@@ -904,6 +1117,16 @@ __global__ void __launch_bounds__(128) mpc_admm_kernel(MpcDev d, MpcTickIO io, i
     int to_check = chk, to_adapt = rint; // countdowns instead of modulo in the hot loop
     bool warp_busy = __any_sync(FULL, !done);
     while (warp_busy) {
+        if (factor_pending) { // warp-uniform: the tick's factorisation, then once more after every rho update
+            const bool ok = factor(rho);
+            factor_pending = false;
+            if (first_factor) {
+                first_factor = false;
+                setup_failed = !ok && setup;
+                if (setup && !setup_failed && gl == 0) d.inited[i] = 1;
+                if (setup_failed) done = true; // no solver: status stays UNSOLVED, the controller keeps its previous output
+            }
+        }
         iter++;
         const bool act = !done;
         const double rho_e = kRhoEqOverIneq * rho;
@@ -945,6 +1168,8 @@ __global__ void __launch_bounds__(128) mpc_admm_kernel(MpcDev d, MpcTickIO io, i
         // ---- reduced KKT solve: the two axis chains run on two lanes (coupled weights: one block chain on one lane)
         if (cpl) {
             if (act && gl == 0) solve_block(s, N);
+        } else if (par) {
+            solve_par(act, rho);
         } else {
         if (act && gl < 2) sweep_forward(s, gl, N);
         __syncwarp();
@@ -1018,7 +1243,9 @@ __global__ void __launch_bounds__(128) mpc_admm_kernel(MpcDev d, MpcTickIO io, i
                 }
             }
             __syncwarp();
-            factor(rho); // warp-uniform; a no-op numerically for groups whose rho did not change
+            // warp-uniform; a no-op numerically for groups whose rho did not change.  Not after the last iteration: nothing is
+            // solved any more and the segment-parallel factorisation stages its Schur blocks in W (delta_x of the final checks)
+            if (iter < max_iter) factor_pending = true; // (at the top of the next iteration)
         }
         if (iter >= max_iter) { // warp-uniform: osqp_solve leaves the loop
             if (!check_now) {
@@ -1102,7 +1329,7 @@ template <int G>
 static cudaError_t launch_admm_t(const MpcDev& d, const MpcTickIO& io, cudaStream_t s)
 {
     constexpr int IPW = 32 / G;
-    int stride = mpc_smem_doubles(d.N, d.coupled);
+    int stride = mpc_smem_doubles(d.N, d.coupled, d.par);
     // keep the per-instance stride == 8 (mod 16) doubles so that the two half-warps of a
     // cooperative access hit disjoint bank groups
     while ((stride % 16) != 8) stride++;

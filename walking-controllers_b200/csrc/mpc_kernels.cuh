@@ -51,6 +51,7 @@ struct MpcDev {
     // coupled != 0 routes the handle to the cooperative kernel's block (2x2) chain solve.
     double Qoff[2], Roff[2];
     int coupled;
+    int par; // cooperative kernel: segment-parallel chain solve (long horizons)
     double* Qd; // [2][B]
     double* Rd; // [2][B]
     // persistent solver state (chain order per axis: index a*nA + j)
@@ -129,10 +130,21 @@ __host__ __device__ inline bool osqp_has_solution(int status)
 __host__ __device__ inline int mpc_nA(int N) { return 2 * N + 1; }
 __host__ __device__ inline int mpc_nR(int N) { return N + 1; }
 // doubles of shared memory per instance in K2
-__host__ __device__ inline int mpc_smem_doubles(int N, int coupled = 0)
+// Segment-parallel chain solve of the cooperative kernel (long horizons): every lane owns one segment of one axis chain, the
+// segments are separated by two-unknown separators, the last separator of an axis is its (u_0, x_0) corner.  Needs at least
+// two interior unknowns per segment; P = lanes / 2 segments per axis.
+__host__ __device__ inline bool mpc_par_ok(int N, int lanes)
+{
+    const int P = lanes / 2; // two interior unknowns per segment at least; the 10 P Schur entries per axis are staged in the rhs vector
+    return lanes >= 8 && (2 * N + 1) - 2 * P >= 2 * P && 10 * lanes <= 2 * (2 * N + 1);
+}
+constexpr int kParMinHorizon = 40; // below: the serial two-lane sweeps (fewer barriers)
+__host__ __device__ inline int mpc_par_doubles(int N) { return 2 * mpc_nA(N) + 2 * 16 * (4 + 8); } // Z + separator rhs parts + reduced factors
+__host__ __device__ inline int mpc_smem_doubles(int N, int coupled = 0, int par = 0)
 {
     const int nA = mpc_nA(N), nR = mpc_nR(N);
-    return 2 * nA * (coupled ? 10 : 7)   // X, QB, W, L1, L2, DI, DD (+ the off-diagonal entries of the 2x2 blocks of L1, L2, DI)
+    return (par ? mpc_par_doubles(N) : 0) +
+           2 * nA * (coupled ? 10 : 7)   // X, QB, W, L1, L2, DI, DD (+ the off-diagonal entries of the 2x2 blocks of L1, L2, DI)
          + 2 * nR * 6   // YE, DYE, CM, CA, CB, EE
          + 8 * 8        // HX, HY, UH, LH, ZH, YH, DYH, EH
          + 16           // corner factor + scratch

@@ -147,6 +147,17 @@ wc_status wc_mpc_create(const wc_mpc_config* cfg, int32_t B, int32_t device, wc_
     while ((stride % 16) != 8) stride++;
     while (lanes < 32 && (size_t)stride * 8 * (32 / lanes) > (size_t)mpc_admm_max_smem()) lanes *= 2;
     if ((size_t)stride * 8 * (32 / lanes) > (size_t)mpc_admm_max_smem()) { wc_mpc_destroy(h); return WC_ERR_UNSUPPORTED; }
+    // long horizons: segment-parallel chain solve (every lane one segment of one axis chain) when its extra working set fits;
+    // WC_MPC_PAR=0|1 overrides (tests / tuning)
+    {
+        int want = (d.N >= kParMinHorizon && !d.coupled) ? 1 : 0;
+        want = env_int("WC_MPC_PAR", want);
+        if (want && !d.coupled && mpc_par_ok(d.N, lanes)) {
+            int sp = mpc_smem_doubles(d.N, 0, 1);
+            while ((sp % 16) != 8) sp++;
+            if ((size_t)sp * 8 * (32 / lanes) <= (size_t)mpc_admm_max_smem()) d.par = 1;
+        }
+    }
     h->lanes = lanes;
     // short horizons: one thread per axis chain (16 instances per warp) when the working set of a warp
     // fits in shared memory; WC_MPC_PATH=coop|chain overrides (tuning / tests)
