@@ -140,6 +140,9 @@ wc_status wc_mpc_create(const wc_mpc_config* cfg, int32_t B, int32_t device, wc_
     // lanes per instance for the ADMM kernel: more lanes for longer horizons (more parallel
     // vector work per sequential sweep).  WC_MPC_LANES overrides (tuning / tests).
     int lanes = d.N <= 8 ? 8 : (d.N <= 128 ? 16 : 32);
+    // the segment-parallel chain solve wants a whole warp per instance (16 segments per axis) as soon as its staging fits
+    // (measured at B = 65536: N = 100 2.08e6 ticks/s with 32 lanes against 1.66e6 with 16; N = 128 1.0e6 with 16 lanes)
+    if (!d.coupled && d.N >= kParMinHorizon && mpc_par_ok(d.N, 32)) lanes = 32;
     lanes = env_int("WC_MPC_LANES", lanes);
     if (!(lanes == 2 || lanes == 4 || lanes == 8 || lanes == 16 || lanes == 32)) lanes = 8;
     // the per-instance working set must fit in one CTA's shared memory
