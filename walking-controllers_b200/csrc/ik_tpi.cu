@@ -317,14 +317,29 @@ __global__ void __launch_bounds__(kTpiThreads, WC_TPI_MINB) ik_tpi_kernel(IkDev 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool live = blockIdx.x * kTpiThreads + threadIdx.x < d.B;
     const int i = live ? blockIdx.x * kTpiThreads + threadIdx.x : d.B - 1; // idle threads of the last CTA shadow its last instance
-    // model table: one copy per CTA (the link loop reads ~25 words of it per link, the same for every lane)
-    __shared__ __align__(16) unsigned long long s_model[(sizeof(IkModelDev) + 7) / 8];
-    {
-        const unsigned long long* src = reinterpret_cast<const unsigned long long*>(d.model);
-        for (int k = threadIdx.x; k < (int)((sizeof(IkModelDev) + 7) / 8); k += kTpiThreads) s_model[k] = src[k];
+    // model table: one copy per CTA (the link loop reads ~25 words of it per link, the same for every lane), fetched by ONE bulk
+    // asynchronous copy (cp.async.bulk, the copy engine's 1-D form: SASS UBLKCP) that completes on an mbarrier -- the CTA's
+    // threads issue no loads for it and meet the data at the barrier wait below
+    constexpr unsigned kModelBytes = (unsigned)((sizeof(IkModelDev) + 15) / 16 * 16);
+    __shared__ __align__(16) unsigned long long s_model[kModelBytes / 8];
+    __shared__ __align__(8) unsigned long long s_bar;
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(&s_bar);
+    if (threadIdx.x == 0) {
+        s_n = 0;
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(bar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(kModelBytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                     ::"r"((unsigned)__cvta_generic_to_shared(s_model)), "l"(d.model), "r"(kModelBytes), "r"(bar) : "memory");
     }
-    if (threadIdx.x == 0) s_n = 0;
-    __syncthreads();
+    __syncthreads(); // the barrier is initialised (and s_n is zero) before anybody waits on it
+    {
+        unsigned ok;
+        do {
+            asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0, 1, 0, p;\n}\n"
+                         : "=r"(ok) : "r"(bar) : "memory");
+        } while (!ok);
+    }
     const size_t B = (size_t)d.B;
     const IkModelDev& M = *reinterpret_cast<const IkModelDev*>(s_model);
     const wc_ik_config& cfg = d.cfg;

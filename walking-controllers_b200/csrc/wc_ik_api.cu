@@ -186,7 +186,8 @@ wc_status wc_ik_create(const wc_ik_config* cfg, const wc_model* model, int32_t B
     std::memset(&h->d, 0, sizeof(h->d));
     h->device = device;
     h->d.B = B; h->d.nJ = cfg->n_dofs; h->d.cfg = *cfg;
-    if (cudaMalloc(&h->model_dev, sizeof(IkModelDev)) != cudaSuccess) { delete h; return WC_ERR_ALLOC; }
+    if (cudaMalloc(&h->model_dev, (sizeof(IkModelDev) + 15) / 16 * 16) != cudaSuccess) // (whole 16-byte units: the fast kernel fetches it with one bulk copy)
+        { delete h; return WC_ERR_ALLOC; }
     if (cudaMemcpy(h->model_dev, &hm, sizeof(IkModelDev), cudaMemcpyHostToDevice) != cudaSuccess) { wc_ik_destroy(h); return WC_ERR_CUDA; }
     h->d.model = h->model_dev;
     // fused-tick fast path (ik_fast_kernel) + compacted general solve; WC_IK_PATH=general disables it
