@@ -23,7 +23,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-fi
 fi
 if has full; then
 $CMD > $OUT/plain2_$TAG.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:"mpc_chain|mpc_prepare|ik_fast|ik_kernel" -s 99 -c 7 -f -o $OUT/prof_$TAG $CMD > $OUT/ncu2_$TAG.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"mpc_split|mpc_prepare|mpc_chain_setup|ik_tpi|ik_kernel" -s 60 -c 6 -f -o $OUT/prof_$TAG $CMD > $OUT/ncu2_$TAG.log 2>&1
 fi
 if has osqp; then
 CMD3="python bench.py --steps 3 --warmup 3 --no-cpu"

@@ -1,9 +1,7 @@
 #!/bin/bash
-# horizon sweep (BASELINE configs[4] + the shipped N = 200): full tick on one GPU, chain path vs cooperative path
+# horizon sweep (BASELINE configs[4] + the shipped N = 200): full tick at B = 65536 on one GPU, the kernel family wc_mpc_create picks
 for n in "$@"; do
-  b=65536; if [ $n -ge 100 ]; then b=16384; fi
-  for path in auto coop; do
-    if [ $path = coop ]; then export WC_MPC_PATH=coop; else unset WC_MPC_PATH; fi
-    timeout 400 python bench.py --no-cpu --steps 12 --warmup 4 --horizon $n --batch $b 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('N=$n B=$b', d['config']['mpc_path'], 'ticks/s %.3e' % d['value'], 'mpc_admm ms %.3f' % d['kernels_ms']['mpc_admm'], 'e2e %.3e' % d['e2e']['value'])"
-  done
+  timeout 600 python bench.py --no-cpu --no-extras --steps 8 --warmup 4 --horizon $n 2>/dev/null | tail -1 | python -c "
+import sys,json; d=json.loads(sys.stdin.read()); k=d['kernels_ms']
+print('| $n | %s | %.3e | %.2f | %.2f | %.3e | %.3e |' % (d['mpc_path'], d['value'], k['mpc_admm'] + k['mpc_prepare'], k['fk_qpik'], d['e2e']['value'], d['closed_loop']['value']))"
 done

@@ -165,7 +165,9 @@ wc_status wc_mpc_create(const wc_mpc_config* cfg, int32_t B, int32_t device, wc_
     // short horizons: one thread per axis chain (16 instances per warp) when the working set of a warp
     // fits in shared memory; WC_MPC_PATH=coop|chain overrides (tuning / tests)
     // and four lanes per instance with the iterate in registers (mpc_split.cu) at the compile-time horizons
-    h->chain = d.coupled ? 0 : (mpc_split_supported(d.N) ? 2 : (mpc_chain_preferred(d.N) ? 1 : 0));
+    // (measured at B = 65536: chain 6.5e6 ticks/s at N = 50; from there the cooperative kernel's segment-parallel solve wins --
+    // N = 60: 3.95e6 against 3.2e6, N = 80: 3.2e6 against 2.5e6, N = 100: 2.08e6 against 2.0e6)
+    h->chain = d.coupled ? 0 : (mpc_split_supported(d.N) ? 2 : ((mpc_chain_preferred(d.N) && !(d.par && d.N >= 54)) ? 1 : 0));
     if (const char* pth = std::getenv("WC_MPC_PATH")) {
         if (!std::strcmp(pth, "coop") || d.coupled) h->chain = 0;
         else if (!std::strcmp(pth, "chain")) {
