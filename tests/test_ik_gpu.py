@@ -333,3 +333,17 @@ def test_runtime_n_dofs(wc, syn, oracle, cuda_device, arms, neck):
     assert np.array_equal(og["status"].cpu().numpy(), oo["status"]) and np.array_equal(og["nwsr"].cpu().numpy(), oo["iters"])
     assert np.abs(og["dq"].cpu().numpy() - oo["dq"]).max() < 1e-5
     ik2.close()
+
+
+def test_fk_without_jacobians_parity(wc, syn, oracle, cuda_device, ik_path):
+    """wc_fk_dev asked for transforms / CoM only (the measured CoM of the closed loop) takes the thread-per-instance kinematics"""
+    B = 1000
+    inp = make_inputs(syn, oracle, B, 5)
+    ik = wc.IkBatch(wc.ik_default_config(), wc.model_icub_like(), B)
+    g = ik.fk(inp["q_lin"].to(cuda_device), inp["base_H"].to(cuda_device), inp["left_is_fixed"].to(cuda_device), jacobians=False)
+    torch.cuda.synchronize()
+    o = oracle.fk_batch(oracle.model_icub_like(), inp["q_lin"].numpy(), inp["base_H"].numpy(), inp["left_is_fixed"].numpy(), jacobians=False)
+    for k in ("lf_H", "rf_H", "neck_R", "com"):
+        err = np.abs(g[k].cpu().numpy() - o[k]).max()
+        assert err < 1e-12, (k, err)
+    ik.close()

@@ -110,5 +110,6 @@ bool ik_supported(int n_dofs);
 // thread-per-instance fast path of the fused tick (ik_tpi.cu)
 int ik_tpi_rows(int n_links, int n_dofs);  // rows of IkDev::tpi_scratch
 cudaError_t launch_ik_tpi(const IkDev& d, const IkTickIO& io, cudaStream_t s);
+cudaError_t launch_ik_tpi_fk(const IkDev& d, const IkTickIO& io, cudaStream_t s); // FK without Jacobians (IkTickIO::o_lf_H, o_rf_H, o_neck_R, o_com)
 
 } // namespace wcb

@@ -308,54 +308,17 @@ __device__ __forceinline__ int tpi_solve(const IkDev& d, const IkTickIO& io, con
     return 0;
 }
 
-// ---- kinematics + QP columns + the equality-constrained optimum of every instance; then the violators of the CTA, compacted
-// onto its first threads, are solved once more with the bound Goldfarb-Idnani adds first fixed at its value
-__global__ void __launch_bounds__(kTpiThreads, WC_TPI_MINB) ik_tpi_kernel(IkDev d, IkTickIO io)
-{
-    extern __shared__ double sm_slots[]; // [warp][slot][12][32]
-    __shared__ int s_n, s_i[kTpiThreads], s_id[kTpiThreads];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const bool live = blockIdx.x * kTpiThreads + threadIdx.x < d.B;
-    const int i = live ? blockIdx.x * kTpiThreads + threadIdx.x : d.B - 1; // idle threads of the last CTA shadow its last instance
-    // model table: one copy per CTA (the link loop reads ~25 words of it per link, the same for every lane), fetched by ONE bulk
-    // asynchronous copy (cp.async.bulk, the copy engine's 1-D form: SASS UBLKCP) that completes on an mbarrier -- the CTA's
-    // threads issue no loads for it and meet the data at the barrier wait below
-    constexpr unsigned kModelBytes = (unsigned)((sizeof(IkModelDev) + 15) / 16 * 16);
-    __shared__ __align__(16) unsigned long long s_model[kModelBytes / 8];
-    __shared__ __align__(8) unsigned long long s_bar;
-    const unsigned bar = (unsigned)__cvta_generic_to_shared(&s_bar);
-    if (threadIdx.x == 0) {
-        s_n = 0;
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(bar) : "memory");
-        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(kModelBytes) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
-                     ::"r"((unsigned)__cvta_generic_to_shared(s_model)), "l"(d.model), "r"(kModelBytes), "r"(bar) : "memory");
-    }
-    __syncthreads(); // the barrier is initialised (and s_n is zero) before anybody waits on it
-    {
-        unsigned ok;
-        do {
-            asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0, 1, 0, p;\n}\n"
-                         : "=r"(ok) : "r"(bar) : "memory");
-        } while (!ok);
-    }
-    const size_t B = (size_t)d.B;
-    const IkModelDev& M = *reinterpret_cast<const IkModelDev*>(s_model);
-    const wc_ik_config& cfg = d.cfg;
-    const int L = M.n_links, nJ = d.nJ;
-    const TpiRows rows(L, nJ);
-    int rc = 0, id = 0;
-    if (live) {
-    double* sc = d.tpi_scratch + i;
-    double* slots = sm_slots + (size_t)warp * d.tpi_slots * 12 * 32 + lane;
-    // the measured joint positions are needed after the link loop: ask for their lines now (lane k: row k)
-    if (lane < nJ && (lane & 1) * 0 == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(io.q_meas + (size_t)lane * B + (i - lane)));
-    if (lane < nJ && (size_t)(i - lane) + 16 < B) asm volatile("prefetch.global.L2 [%0];" ::"l"(io.q_meas + (size_t)lane * B + (i - lane) + 16));
 #define SLOT(s, k) slots[((s) * 12 + (k)) * 32]
+// root_H_link of every link, serially (parent[l] < l), with the running first-moment prefix; SCRATCH: the prefix and every
+// joint's axis / origin go to the per-instance scratch.  Returns the total first moment in the root frame in P.
+template <bool SCRATCH>
+__device__ __forceinline__ void tpi_link_loop(const IkModelDev& M, const IkTickIO& io, int i, size_t B, double* slots, double* sc,
+                                              const TpiRows& rows, double (&P)[3])
+{
+    const int L = M.n_links;
     // ---- root_H_link, serially over the links (parent[l] < l); first-moment prefix; joint axes and origins
     double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, p[3] = {0, 0, 0}; // root_H_(l-1) of the previous iteration
-    double P[3] = {0, 0, 0};
+    P[0] = P[1] = P[2] = 0.0;
     double qn = 0.0, qn2 = 0.0; // joint angles of the next two links, requested ahead of their use
     {
         const int d0 = M.dof[0];
@@ -410,12 +373,14 @@ __global__ void __launch_bounds__(kTpiThreads, WC_TPI_MINB) ik_tpi_kernel(IkDev 
 #pragma unroll
             for (int k = 0; k < 3; k++) SLOT(so, 9 + k) = p[k];
         }
+        if (SCRATCH) {
 #pragma unroll
-        for (int r = 0; r < 3; r++) sc[(size_t)(rows.oP + 3 * l + r) * B] = P[r];
+            for (int r = 0; r < 3; r++) sc[(size_t)(rows.oP + 3 * l + r) * B] = P[r];
+        }
         const double m = M.mass[l];
 #pragma unroll
         for (int r = 0; r < 3; r++) P[r] += m * (R[3 * r] * M.com[l][0] + R[3 * r + 1] * M.com[l][1] + R[3 * r + 2] * M.com[l][2] + p[r]);
-        if (dj >= 0) {
+        if (SCRATCH && dj >= 0) {
 #pragma unroll
             for (int r = 0; r < 3; r++) {
                 sc[(size_t)(rows.oJ + 10 * dj + r) * B] = R[3 * r] * ax[0] + R[3 * r + 1] * ax[1] + R[3 * r + 2] * ax[2];
@@ -423,12 +388,18 @@ __global__ void __launch_bounds__(kTpiThreads, WC_TPI_MINB) ik_tpi_kernel(IkDev 
             }
         }
     }
+    if (SCRATCH) {
 #pragma unroll
-    for (int r = 0; r < 3; r++) sc[(size_t)(rows.oP + 3 * L + r) * B] = P[r];
+        for (int r = 0; r < 3; r++) sc[(size_t)(rows.oP + 3 * L + r) * B] = P[r];
+    }
+}
+
+// world_H_root from the stance sole (evaluateWorldToBaseTransformation) and the task frames in the world
+__device__ __forceinline__ void tpi_frames(const IkModelDev& M, const IkTickIO& io, int i, size_t B, const double* slots, bool left,
+                                           double (&wR)[9], double (&wp)[3], double (&lfH)[12], double (&rfH)[12], double (&nR)[9],
+                                           double (&pBr)[3])
+{
     // ---- world_H_root from the stance sole (evaluateWorldToBaseTransformation), task frames in the world
-    const bool left = io.left_is_fixed[i] != 0;
-    double wR[9], wp[3];
-    double lfH[12], rfH[12], nR[9], pBr[3];
     {
         double Rf[2][9], pf[2][3];
 #pragma unroll
@@ -477,7 +448,59 @@ __global__ void __launch_bounds__(kTpiThreads, WC_TPI_MINB) ik_tpi_kernel(IkDev 
         mat3_mul(Rk, M.frame_R[2], Rn);
         mat3_mul(wR, Rn, nR);
     }
+}
 #undef SLOT
+
+// ---- kinematics + QP columns + the equality-constrained optimum of every instance; then the violators of the CTA, compacted
+// onto its first threads, are solved once more with the bound Goldfarb-Idnani adds first fixed at its value
+__global__ void __launch_bounds__(kTpiThreads, WC_TPI_MINB) ik_tpi_kernel(IkDev d, IkTickIO io)
+{
+    extern __shared__ double sm_slots[]; // [warp][slot][12][32]
+    __shared__ int s_n, s_i[kTpiThreads], s_id[kTpiThreads];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool live = blockIdx.x * kTpiThreads + threadIdx.x < d.B;
+    const int i = live ? blockIdx.x * kTpiThreads + threadIdx.x : d.B - 1; // idle threads of the last CTA shadow its last instance
+    // model table: one copy per CTA (the link loop reads ~25 words of it per link, the same for every lane), fetched by ONE bulk
+    // asynchronous copy (cp.async.bulk, the copy engine's 1-D form: SASS UBLKCP) that completes on an mbarrier -- the CTA's
+    // threads issue no loads for it and meet the data at the barrier wait below
+    constexpr unsigned kModelBytes = (unsigned)((sizeof(IkModelDev) + 15) / 16 * 16);
+    __shared__ __align__(16) unsigned long long s_model[kModelBytes / 8];
+    __shared__ __align__(8) unsigned long long s_bar;
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(&s_bar);
+    if (threadIdx.x == 0) {
+        s_n = 0;
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(bar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(kModelBytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                     ::"r"((unsigned)__cvta_generic_to_shared(s_model)), "l"(d.model), "r"(kModelBytes), "r"(bar) : "memory");
+    }
+    __syncthreads(); // the barrier is initialised (and s_n is zero) before anybody waits on it
+    {
+        unsigned ok;
+        do {
+            asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0, 1, 0, p;\n}\n"
+                         : "=r"(ok) : "r"(bar) : "memory");
+        } while (!ok);
+    }
+    const size_t B = (size_t)d.B;
+    const IkModelDev& M = *reinterpret_cast<const IkModelDev*>(s_model);
+    const wc_ik_config& cfg = d.cfg;
+    const int L = M.n_links, nJ = d.nJ;
+    const TpiRows rows(L, nJ);
+    int rc = 0, id = 0;
+    if (live) {
+    double* sc = d.tpi_scratch + i;
+    double* slots = sm_slots + (size_t)warp * d.tpi_slots * 12 * 32 + lane;
+    // the measured joint positions are needed after the link loop: ask for their lines now (lane k: row k)
+    if (lane < nJ && (lane & 1) * 0 == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(io.q_meas + (size_t)lane * B + (i - lane)));
+    if (lane < nJ && (size_t)(i - lane) + 16 < B) asm volatile("prefetch.global.L2 [%0];" ::"l"(io.q_meas + (size_t)lane * B + (i - lane) + 16));
+    double P[3];
+    tpi_link_loop<true>(M, io, i, B, slots, sc, rows, P);
+    const bool left = io.left_is_fixed[i] != 0;
+    double wR[9], wp[3];
+    double lfH[12], rfH[12], nR[9], pBr[3];
+    tpi_frames(M, io, i, B, slots, left, wR, wp, lfH, rfH, nR, pBr);
     const double Mtot = M.total_mass;
     double Mc[3], com[3], pB[3];
 #pragma unroll
@@ -657,6 +680,49 @@ __global__ void __launch_bounds__(kTpiThreads, WC_TPI_MINB) ik_tpi_kernel(IkDev 
     }
 }
 
+
+// ---- forward kinematics only (wc_fk_* without Jacobians: the measured CoM / feet of the closed loop), one thread per instance
+__global__ void __launch_bounds__(kTpiThreads, WC_TPI_MINB) ik_tpi_fk_kernel(IkDev d, IkTickIO io)
+{
+    extern __shared__ double sm_slots[]; // [warp][slot][12][32]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr unsigned kModelBytes = (unsigned)((sizeof(IkModelDev) + 15) / 16 * 16);
+    __shared__ __align__(16) unsigned long long s_model[kModelBytes / 8];
+    {
+        const unsigned long long* src = reinterpret_cast<const unsigned long long*>(d.model);
+        for (int k = threadIdx.x; k < (int)(kModelBytes / 8); k += kTpiThreads) s_model[k] = src[k];
+    }
+    __syncthreads();
+    const int i = blockIdx.x * kTpiThreads + threadIdx.x;
+    if (i >= d.B) return;
+    const size_t B = (size_t)d.B;
+    const IkModelDev& M = *reinterpret_cast<const IkModelDev*>(s_model);
+    double* slots = sm_slots + (size_t)warp * d.tpi_slots * 12 * 32 + lane;
+    const TpiRows rows(M.n_links, d.nJ);
+    double P[3];
+    tpi_link_loop<false>(M, io, i, B, slots, nullptr, rows, P);
+    const bool left = io.left_is_fixed[i] != 0;
+    double wR[9], wp[3], lfH[12], rfH[12], nR[9], pBr[3];
+    tpi_frames(M, io, i, B, slots, left, wR, wp, lfH, rfH, nR, pBr);
+    if (io.o_lf_H) {
+#pragma unroll
+        for (int k = 0; k < 12; k++) io.o_lf_H[(size_t)k * B + i] = lfH[k];
+    }
+    if (io.o_rf_H) {
+#pragma unroll
+        for (int k = 0; k < 12; k++) io.o_rf_H[(size_t)k * B + i] = rfH[k];
+    }
+    if (io.o_neck_R) {
+#pragma unroll
+        for (int k = 0; k < 9; k++) io.o_neck_R[(size_t)k * B + i] = nR[k];
+    }
+    if (io.o_com) {
+        const double Mtot = M.total_mass;
+#pragma unroll
+        for (int r = 0; r < 3; r++) io.o_com[(size_t)r * B + i] = (wR[3 * r] * P[0] + wR[3 * r + 1] * P[1] + wR[3 * r + 2] * P[2] + Mtot * wp[r]) / Mtot;
+    }
+}
+
 } // namespace
 
 int ik_tpi_rows(int n_links, int n_dofs) { return TpiRows(n_links, n_dofs).total; }
@@ -668,6 +734,15 @@ cudaError_t launch_ik_tpi(const IkDev& d, const IkTickIO& io, cudaStream_t s)
     if (e != cudaSuccess) return e;
     const int blocks = (d.B + kTpiThreads - 1) / kTpiThreads;
     ik_tpi_kernel<<<blocks, kTpiThreads, smem, s>>>(d, io);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_ik_tpi_fk(const IkDev& d, const IkTickIO& io, cudaStream_t s)
+{
+    const size_t smem = (size_t)(kTpiThreads / 32) * d.tpi_slots * 12 * 32 * sizeof(double);
+    cudaError_t e = cudaFuncSetAttribute(ik_tpi_fk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    ik_tpi_fk_kernel<<<(d.B + kTpiThreads - 1) / kTpiThreads, kTpiThreads, smem, s>>>(d, io);
     return cudaGetLastError();
 }
 

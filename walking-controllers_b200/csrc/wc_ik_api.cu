@@ -319,7 +319,7 @@ static wc_status launch_checked(wc_ik* h, const IkTickIO& io, int mode, cudaStre
         e = cudaMemcpyAsync(h->user_setups, h->d.osetups, (size_t)h->d.B * sizeof(int32_t), cudaMemcpyDeviceToDevice, s);
     if (osqp && h->user_flags && e == cudaSuccess)
         e = cudaMemcpyAsync(h->user_flags, h->d.oflags, (size_t)h->d.B * sizeof(int32_t), cudaMemcpyDeviceToDevice, s);
-    h->launches += two ? 3 : 1; // fast kernel, its second-pass launch, general kernel
+    h->launches += two ? (h->d.tpi_scratch ? 2 : 3) : 1; // fast kernel (thread per instance: one launch; warp per instance: two), general kernel
     if (e != cudaSuccess) {
         std::fprintf(stderr, "[%s] CUDA error: %s\n", who, cudaGetErrorString(e));
         return WC_ERR_CUDA;
@@ -358,6 +358,13 @@ wc_status wc_fk_dev(wc_ik* h, const double* q, const double* base_H, const uint8
     io.q_lin = q; io.base_H = base_H; io.left_is_fixed = left_is_fixed;
     io.o_lf_H = lf_H; io.o_rf_H = rf_H; io.o_neck_R = neck_R; io.o_com = com;
     io.o_J_lf = J_lf; io.o_J_rf = J_rf; io.o_J_neck = J_neck; io.o_J_com = J_com;
+    if (!J_lf && !J_rf && !J_neck && !J_com && h->d.tpi_scratch) {
+        // transforms / CoM only (the measured CoM of the closed loop): thread-per-instance kinematics, no Jacobian columns
+        const cudaError_t e = launch_ik_tpi_fk(h->d, io, static_cast<cudaStream_t>(stream));
+        h->launches += 1;
+        if (e != cudaSuccess) { std::fprintf(stderr, "[wc_fk_dev] CUDA error: %s\n", cudaGetErrorString(e)); return WC_ERR_CUDA; }
+        return WC_OK;
+    }
     return launch_checked(h, io, IK_MODE_FK_ONLY, static_cast<cudaStream_t>(stream), "wc_fk_dev");
 }
 
