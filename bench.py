@@ -533,14 +533,18 @@ def run_ours(args, world, rank, local_rank):
         q_before = view["q_des"].clone()
         loop.run(1)
         torch.cuda.synchronize()
-        rec = dict(lf_H=pin(view["lf_H"]), rf_H=pin(view["rf_H"]), l_contact=pin(view["l_contact"]), r_contact=pin(view["r_contact"]),
-                   left_is_fixed=pin(view["left_is_fixed"]), dcm_meas=pin(view["dcm_meas"]), q_meas=pin(q_before), q_lin=pin(q_before),
-                   lf_twist=pin(view["lf_twist"]), rf_twist=pin(view["rf_twist"]), com_pos_des=pin(view["com_pos_des"]),
-                   com_vel_des=pin(view["com_vel_des"]), com_meas=pin(view["com_meas"]), neck_R_des=pin(view["neck_R_des"]))
+        # one pinned arena per tick in the packed order of wc_tick_host_async (wc_capi.h): two uploads per tick instead of sixteen
+        rec = wc.host_tick_arena_in(B, N, 23, window=(t == 0))
+        srcs = dict(lf_H=view["lf_H"], rf_H=view["rf_H"], l_contact=view["l_contact"], r_contact=view["r_contact"],
+                    left_is_fixed=view["left_is_fixed"], dcm_meas=view["dcm_meas"], q_meas=q_before, q_lin=q_before,
+                    lf_twist=view["lf_twist"], rf_twist=view["rf_twist"], com_pos_des=view["com_pos_des"],
+                    com_vel_des=view["com_vel_des"], com_meas=view["com_meas"], neck_R_des=view["neck_R_des"])
         if t == 0:
-            rec["ref_window"] = pin(view["ref_pos"])
+            srcs["ref_window"] = view["ref_pos"]
         else:
-            rec["ref_newest"] = pin(view["ref_pos"][2 * N: 2 * N + 2])
+            srcs["ref_newest"] = view["ref_pos"][2 * N: 2 * N + 2]
+        for k_, v_ in srcs.items():
+            rec[k_].copy_(v_.reshape(rec[k_].shape))
         h_in.append(rec)
         cl_out.append((view["zmp"].clone(), view["dq"].clone()))
     for t in range(warm):
@@ -564,45 +568,41 @@ def run_ours(args, world, rank, local_rank):
     mpc2 = wc.MpcBatch(mcfg_cl, B, device=local_rank)
     ik2 = wc.IkBatch(icfg_cl, model, B, device=local_rank)
 
-    def mk_out():
-        e = lambda *shape, dt=torch.float64: torch.empty(*shape, dtype=dt).pin_memory()
-        return dict(zmp=e(2, B), osqp_status=e(B, dt=torch.int32), iters=e(B, dt=torch.int32), flags=e(B, dt=torch.int32),
-                    dq=e(23, B), lf_err=e(6, B), rf_err=e(6, B), qp_status=e(B, dt=torch.int32), nwsr=e(B, dt=torch.int32))
-
-    h_outs = [mk_out(), mk_out()]   # two ticks in flight -> two result buffers
-    h2d = sum(v.numel() * v.element_size() for k, v in h_in[1].items())
-    d2h = sum(v.numel() * v.element_size() for v in h_outs[0].values())
+    DEPTH = 3
+    h_outs = [wc.host_tick_arena_out(B, 23) for _ in range(DEPTH)]   # ticks in flight -> as many result arenas (one download each)
+    h2d = sum(v.numel() * v.element_size() for k, v in h_in[1].items() if k != "_arena")
+    d2h = sum(v.numel() * v.element_size() for k, v in h_outs[0].items() if k != "_arena")
     e2e_match = True
 
     def submit(t):
         # one packed upload for both blocks (shared feet transforms, stance base selected on the device, one DCM sample per
         # tick), MPC and IK kernels on the handle's two kernel streams, one download.  Staging is double-buffered: the upload
         # of tick t+1 and the download of tick t-1 overlap the kernels of tick t.
-        mpc2.tick_fused_host_async(ik2, h_in[t], h_outs[t % 2])
+        mpc2.tick_fused_host_async(ik2, h_in[t], h_outs[t % DEPTH])
 
     def retire(t):
         nonlocal e2e_match
         mpc2.sync_one()   # results of tick t are now in its pinned host buffers
         if t < e2e_warm:  # (outside the timed region) the replay reproduces the closed loop bit for bit
             zc, dc = cl_out[t]
-            e2e_match = e2e_match and torch.equal(h_outs[t % 2]["zmp"], zc.cpu()) and torch.equal(h_outs[t % 2]["dq"], dc.cpu())
+            e2e_match = e2e_match and torch.equal(h_outs[t % DEPTH]["zmp"], zc.cpu()) and torch.equal(h_outs[t % DEPTH]["dq"], dc.cpu())
 
     for t in range(e2e_warm):
         submit(t)
-        if t >= 1:
-            retire(t - 1)
+        if t >= DEPTH - 1:
+            retire(t - (DEPTH - 1))
     mpc2.sync()
     barrier()
     t0 = time.perf_counter()
     for k in range(e2e_steps):
         submit(e2e_warm + k)
-        if k >= 1:
+        if k >= DEPTH - 1:
             mpc2.sync_one()
     mpc2.sync()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     zc, dc = cl_out[Te - 1]
-    e2e_match = e2e_match and torch.equal(h_outs[(Te - 1) % 2]["zmp"], zc.cpu()) and torch.equal(h_outs[(Te - 1) % 2]["dq"], dc.cpu())
+    e2e_match = e2e_match and torch.equal(h_outs[(Te - 1) % DEPTH]["zmp"], zc.cpu()) and torch.equal(h_outs[(Te - 1) % DEPTH]["dq"], dc.cpu())
     e = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e, op=dist.ReduceOp.MAX)
@@ -722,7 +722,7 @@ def run_ours(args, world, rank, local_rank):
                      "flops_per_tick_model": {"mpc": f_mpc, "ik": f_ik}},
             "e2e": {"value": world * B * e2e_steps / e2e_s, "unit": "ticks/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3,
-                    "api": "wc_tick_host_async (fused MPC + FK/QP-IK host tick, pinned buffers, two ticks in flight)",
+                    "api": "wc_tick_host_async (fused MPC + FK/QP-IK host tick, one pinned arena per direction, up to three ticks in flight)",
                     "workload": "the inputs of a recorded closed-loop rollout (wc_loop_*), uploaded tick by tick",
                     "matches_closed_loop_bitwise": bool(e2e_match)},
             # the closed-loop tick with the true MPC -> ZMP-CoM law -> IK dependence, one CUDA-graph replay per tick

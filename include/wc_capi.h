@@ -185,8 +185,8 @@ wc_status wc_mpc_tick_host(wc_mpc* h,
                            double* zmp, int32_t* osqp_status, int32_t* iters, int32_t* flags);
 
 /* Split form of wc_mpc_tick_host: _async enqueues the H2D copies, the kernels and the D2H copies on the
- * handle's own upload / compute / download streams and returns.  Staging is double-buffered: up to TWO ticks may
- * be in flight (a third _async call first retires the oldest), so the upload of tick t+1 and the download of
+ * handle's own upload / compute / download streams and returns.  Staging has three slots: up to THREE ticks may
+ * be in flight (a fourth _async call first retires the oldest), so the upload of tick t+1 and the download of
  * tick t-1 overlap the kernels of tick t; another handle's (e.g. the IK's) traffic overlaps as well.
  * wc_mpc_sync_one retires the oldest tick in flight (its outputs are then valid), wc_mpc_sync all of them.
  * Input and output buffers of a tick must stay valid (and should be pinned: cudaHostAlloc / torch pin_memory)
@@ -426,6 +426,14 @@ wc_status wc_ik_path_counts_host(wc_ik* h, int32_t* second_pass, int32_t* genera
 /* wc_mpc_tick_host_async, and wc_mpc_sync_one / wc_mpc_sync retire fused ticks too.      */
 /* All pointers are HOST pointers (pinned for true asynchrony), layouts as in the         */
 /* per-block entry points; outputs may be NULL.                                           */
+/* Arrays that are contiguous in host memory in the PACKED ORDER are moved by one copy:   */
+/*   inputs : lf_H, rf_H, dcm_meas, ref_newest, q_meas, q_lin, lf_twist, rf_twist,        */
+/*            com_pos_des, com_vel_des, com_meas, neck_R_des [, base_H] [, ref_window];   */
+/*            then l_contact, r_contact, left_is_fixed [, reset], each padded to 8 bytes  */
+/*   outputs: zmp, dq, lf_err, rf_err, osqp_status, iters, flags, qp_status, nwsr         */
+/*            (int32 arrays padded to 8 bytes)                                            */
+/* so a driver that keeps a tick's inputs in one pinned arena pays two uploads and one    */
+/* download per tick instead of sixteen and nine (small copies reach half the PCIe rate). */
 /* ---------------------------------------------------------------------------------- */
 typedef struct wc_tick_host_in {
     const double *lf_H, *rf_H;                    /* [12*B] desired feet transforms (hull, IK targets, stance base) */

@@ -94,10 +94,13 @@ def test_reference_ring_matches_full_window(wc, syn, cuda_device):
     mw.close(); mr.close()
 
 
-def test_fused_host_tick_matches_the_two_blocks(wc, syn, oracle, cuda_device):
+@pytest.mark.parametrize("arena", [False, True])
+def test_fused_host_tick_matches_the_two_blocks(wc, syn, oracle, cuda_device, arena):
     """wc_tick_host_async (one upload for both blocks: shared feet transforms, stance base selected on the device, one DCM
-    sample per tick) gives the results of wc_mpc_tick_host + wc_ik_tick_host on the same data, two ticks in flight."""
-    B, N, T = 200, 25, 12
+    sample per tick) gives the results of wc_mpc_tick_host + wc_ik_tick_host on the same data, two ticks in flight.
+    arena: the tick's inputs / results live in ONE pinned arena each, in the packed order (copies merged into two uploads and
+    one download); otherwise in separately allocated buffers (one copy per array).  B = 203: the byte flags are padded."""
+    B, N, T = 203 if arena else 200, 25, 12
     g = syn.GaitBatch(B, T, N, seed=43)
     traj = g.trajectory()
     icfg, model = wc.ik_default_config(), wc.model_icub_like()
@@ -116,6 +119,8 @@ def test_fused_host_tick_matches_the_two_blocks(wc, syn, oracle, cuda_device):
                  dq=pin(torch.empty(23, B, dtype=torch.float64)), lf_err=pin(torch.empty(6, B, dtype=torch.float64)),
                  rf_err=pin(torch.empty(6, B, dtype=torch.float64)), qp_status=pin(torch.empty(B, dtype=torch.int32)),
                  nwsr=pin(torch.empty(B, dtype=torch.int32))) for _ in range(2)]
+    if arena:
+        outs = [wc.host_tick_arena_out(B, 23) for _ in range(2)]
     refs, got = [], []
     for t in range(T):
         f = g.feet(t)
@@ -137,12 +142,17 @@ def test_fused_host_tick_matches_the_two_blocks(wc, syn, oracle, cuda_device):
             inp["ref_window"] = pin(win)
         else:
             inp["ref_newest"] = pin(win[2 * N: 2 * N + 2])
+        if arena:
+            packed = wc.host_tick_arena_in(B, N, 23, window=(t == 0))
+            for k, v in inp.items():
+                packed[k].copy_(v.reshape(packed[k].shape))
+            inp = packed
         mf.tick_fused_host_async(ik_f, inp, outs[t % 2])
         if t >= 1:
             mf.sync_one()
-            got.append({k: v.numpy().copy() for k, v in outs[(t - 1) % 2].items()})
+            got.append({k: v.numpy().copy() for k, v in outs[(t - 1) % 2].items() if k != "_arena"})
     mf.sync()
-    got.append({k: v.numpy().copy() for k, v in outs[(T - 1) % 2].items()})
+    got.append({k: v.numpy().copy() for k, v in outs[(T - 1) % 2].items() if k != "_arena"})
     for t in range(T):
         rm, ri = refs[t]
         for a, b in (("zmp", "zmp"), ("osqp_status", "status"), ("iters", "iters"), ("flags", "flags")):

@@ -467,7 +467,7 @@ class MpcBatch:
         self._inflight.clear()
 
     def sync_one(self):
-        """retire the oldest host tick in flight (up to two may be)"""
+        """retire the oldest host tick in flight (up to three may be)"""
         _check(lib().wc_mpc_sync_one(self.h), "wc_mpc_sync_one")
         if self._inflight:
             self._inflight.popleft()
@@ -930,6 +930,42 @@ class LoopBatch:
                 out[k] = torch.as_tensor(_DevArray(getattr(v, k), shape, ts), device=f"cuda:{self.device}")
             self._view = out
         return self._view
+
+
+def host_tick_arena_in(B, N, nJ, window=False, base=False, reset=False):
+    """Pinned host buffers for one tick's inputs of wc_tick_host_async, carved out of ONE arena in the packed order the C ABI
+    documents, so that the upload is two copies (the doubles, the byte flags) instead of sixteen.  Returns a dict of views."""
+    import torch
+    rows = [("lf_H", 12), ("rf_H", 12), ("dcm_meas", 2), ("ref_newest", 2), ("q_meas", nJ), ("q_lin", nJ), ("lf_twist", 6),
+            ("rf_twist", 6), ("com_pos_des", 3), ("com_vel_des", 3), ("com_meas", 3), ("neck_R_des", 9)]
+    if window:  # the whole window instead of its newest sample: ref_newest stays NULL, ref_window follows the run
+        rows = [r for r in rows if r[0] != "ref_newest"]
+    tail = ([("base_H", 12)] if base else []) + ([("ref_window", 2 * (N + 1))] if window else [])
+    total = sum(r for _, r in rows + tail)
+    arena = torch.empty(total, B, dtype=torch.float64).pin_memory()
+    out, k = {}, 0
+    for name, r in rows + tail:
+        out[name] = arena[k:k + r]; k += r
+    Bp = (B + 7) // 8 * 8
+    flags = torch.zeros(4 if reset else 3, Bp, dtype=torch.uint8).pin_memory()
+    for j, name in enumerate(("l_contact", "r_contact", "left_is_fixed") + (("reset",) if reset else ())):
+        out[name] = flags[j, :B]
+    out["_arena"] = (arena, flags)
+    return out
+
+
+def host_tick_arena_out(B, nJ):
+    """Pinned host buffers for one tick's results of wc_tick_host_async in ONE arena (one download)."""
+    import torch
+    nd = (2 + nJ + 12) * B
+    ni = (B * 4 + 7) // 8 * 8
+    buf = torch.empty(nd * 8 + 5 * ni, dtype=torch.uint8).pin_memory()
+    dbl = buf[:nd * 8].view(torch.float64).view(2 + nJ + 12, B)
+    out = dict(zmp=dbl[0:2], dq=dbl[2:2 + nJ], lf_err=dbl[2 + nJ:8 + nJ], rf_err=dbl[8 + nJ:14 + nJ])
+    for j, name in enumerate(("osqp_status", "iters", "flags", "qp_status", "nwsr")):
+        out[name] = buf[nd * 8 + j * ni: nd * 8 + j * ni + B * 4].view(torch.int32)
+    out["_arena"] = buf
+    return out
 
 
 COMM_ID_BYTES = 128

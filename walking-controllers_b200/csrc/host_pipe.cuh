@@ -1,6 +1,6 @@
 // host_pipe.cuh — double-buffered staging behind the host-pointer entry points (wc_*_tick_host_async / _sync).
-// Three streams per handle (upload, kernels, download) and two staging slots: the upload of tick t+1 and the
-// download of tick t-1 overlap the kernels of tick t.  Up to two ticks may be in flight; results of a tick are
+// Three streams per handle (upload, kernels, download) and three staging slots: the upload of tick t+1 and the
+// download of tick t-1 overlap the kernels of tick t.  Up to three ticks may be in flight; results of a tick are
 // valid after the wc_*_sync_one / wc_*_sync call that retires it.
 #pragma once
 
@@ -10,7 +10,7 @@
 namespace wcb {
 
 struct HostPipe {
-    static constexpr int kSlots = 2;
+    static constexpr int kSlots = 3;
     cudaStream_t up = nullptr, run = nullptr, run2 = nullptr, down = nullptr; // run2: a second kernel stream (fused MPC + IK tick)
     cudaEvent_t fork = nullptr, join = nullptr;
     size_t in_cap = 0, out_cap = 0;
@@ -87,7 +87,7 @@ struct HostPipe {
         while (retired < submitted && e == cudaSuccess) e = sync_one();
         return e;
     }
-    // slot of the next tick; waits on the host only if both slots are still in flight
+    // slot of the next tick; waits on the host only if all slots are still in flight
     int begin(cudaError_t* err)
     {
         *err = cudaSuccess;

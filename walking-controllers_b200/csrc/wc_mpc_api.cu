@@ -398,13 +398,27 @@ wc_status wc_tick_host_async(wc_mpc* h, wc_ik* ik, const wc_tick_host_in* in, co
     cudaStream_t s = h->pipe.up;
     char* di = static_cast<char*>(h->pipe.dev_in[slot]);
     char* dout = static_cast<char*>(h->pipe.dev_out[slot]);
-    for (int k = 0; k < I_ND; k++)
-        if (src[k] && ce == cudaSuccess) ce = cudaMemcpyAsync(di + off[k], src[k], rows[k] * B * 8, cudaMemcpyHostToDevice, s);
-    if (ce == cudaSuccess) ce = cudaMemcpyAsync(di + o_lc, in->l_contact, B, cudaMemcpyHostToDevice, s);
-    if (ce == cudaSuccess) ce = cudaMemcpyAsync(di + o_rc, in->r_contact, B, cudaMemcpyHostToDevice, s);
-    if (ce == cudaSuccess) ce = cudaMemcpyAsync(di + o_lif, in->left_is_fixed, B, cudaMemcpyHostToDevice, s);
-    if (ce == cudaSuccess) ce = in->reset ? cudaMemcpyAsync(di + o_rs, in->reset, B, cudaMemcpyHostToDevice, s)
-                                          : cudaMemsetAsync(di + o_rs, 0, B, s);
+    // One copy per RUN of arrays that are contiguous on both sides: a caller that keeps its inputs in one arena in the packed
+    // order of this block (wc_capi.h) gets two copies per tick instead of sixteen -- a 1-12 MB copy reaches half the PCIe rate
+    // of a 55 MB one on this box (tools/pcie_probe.py: 24 against 51 GB/s).
+    {
+        struct Seg { size_t dst; const char* src; size_t bytes; };
+        Seg segs[I_ND + 4]; int ns = 0;
+        for (int k = 0; k < I_ND; k++) if (src[k]) segs[ns++] = Seg{off[k], (const char*)src[k], rows[k] * B * 8};
+        segs[ns++] = Seg{o_lc, (const char*)in->l_contact, B};
+        segs[ns++] = Seg{o_rc, (const char*)in->r_contact, B};
+        segs[ns++] = Seg{o_lif, (const char*)in->left_is_fixed, B};
+        if (in->reset) segs[ns++] = Seg{o_rs, (const char*)in->reset, B};
+        for (int k = 0; k < ns && ce == cudaSuccess;) {
+            size_t bytes = segs[k].bytes; int j = k + 1;
+            // (the byte flags sit align_up(B, 8) apart on the device: mergeable when the host keeps the same spacing)
+            while (j < ns && segs[j].src - segs[k].src == (ptrdiff_t)(segs[j].dst - segs[k].dst) && segs[j].dst >= segs[k].dst + bytes &&
+                   segs[j].dst - (segs[k].dst + bytes) < 8) { bytes = segs[j].dst - segs[k].dst + segs[j].bytes; j++; }
+            ce = cudaMemcpyAsync(di + segs[k].dst, segs[k].src, bytes, cudaMemcpyHostToDevice, s);
+            k = j;
+        }
+        if (!in->reset && ce == cudaSuccess) ce = cudaMemsetAsync(di + o_rs, 0, B, s);
+    }
     if (ce == cudaSuccess) ce = h->pipe.before_run(slot);
     if (ce != cudaSuccess) return WC_ERR_CUDA;
     auto dp = [&](int k) { return (const double*)(di + off[k]); };
@@ -426,11 +440,22 @@ wc_status wc_tick_host_async(wc_mpc* h, wc_ik* ik, const wc_tick_host_in* in, co
         return WC_ERR_CUDA;
     cudaError_t e = h->pipe.before_down(slot);
     s = h->pipe.down;
-#define D2H(dst, o, bytes) do { if ((dst) && e == cudaSuccess) e = cudaMemcpyAsync((dst), dout + (o), (bytes), cudaMemcpyDeviceToHost, s); } while (0)
-    D2H(out->zmp, p_zmp, 2 * B * 8); D2H(out->osqp_status, p_st, B * 4); D2H(out->iters, p_it, B * 4); D2H(out->flags, p_fl, B * 4);
-    D2H(out->dq, p_dq, nJ * B * 8); D2H(out->lf_err, p_le, 6 * B * 8); D2H(out->rf_err, p_re, 6 * B * 8);
-    D2H(out->qp_status, p_qs, B * 4); D2H(out->nwsr, p_nw, B * 4);
-#undef D2H
+    { // results: likewise one copy per run that is contiguous on both sides (packed order: zmp, dq, lf_err, rf_err, osqp_status, iters,
+      // flags, qp_status, nwsr)
+        struct Seg { size_t src; char* dst; size_t bytes; };
+        Seg segs[9]; int ns = 0;
+        auto add = [&](void* dst, size_t o, size_t bytes) { if (dst) segs[ns++] = Seg{o, (char*)dst, bytes}; };
+        add(out->zmp, p_zmp, 2 * B * 8); add(out->dq, p_dq, nJ * B * 8); add(out->lf_err, p_le, 6 * B * 8); add(out->rf_err, p_re, 6 * B * 8);
+        add(out->osqp_status, p_st, B * 4); add(out->iters, p_it, B * 4); add(out->flags, p_fl, B * 4);
+        add(out->qp_status, p_qs, B * 4); add(out->nwsr, p_nw, B * 4);
+        for (int k = 0; k < ns && e == cudaSuccess;) {
+            size_t bytes = segs[k].bytes; int j = k + 1;
+            while (j < ns && segs[j].dst - segs[k].dst == (ptrdiff_t)(segs[j].src - segs[k].src) && segs[j].src >= segs[k].src + bytes &&
+                   segs[j].src - (segs[k].src + bytes) < 8) { bytes = segs[j].src - segs[k].src + segs[j].bytes; j++; }
+            e = cudaMemcpyAsync(segs[k].dst, dout + segs[k].src, bytes, cudaMemcpyDeviceToHost, s);
+            k = j;
+        }
+    }
     if (e == cudaSuccess) e = h->pipe.end(slot);
     if (e != cudaSuccess) {
         std::fprintf(stderr, "[wc_tick_host_async] CUDA error: %s\n", cudaGetErrorString(e));
