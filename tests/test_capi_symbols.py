@@ -3,6 +3,8 @@ import ctypes as C
 import os
 import re
 
+import pytest
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -57,3 +59,26 @@ def test_product_has_no_cpu_fallback(wc):
     cfg = wc.mpc_default_config(25)
     rc = wc.lib().wc_mpc_create(C.byref(cfg), 4, 0, C.byref(h))
     assert rc != 0 and not h.value
+
+
+def test_sass_of_the_shipped_library(wc):
+    """What DESIGN.md / profiles/r2d_sass.md claim about the machine code, checked on the library as built here (cuobjdump needs
+    no GPU): sm_100a only, the thread-per-instance IK kernel fetches its model table with a bulk asynchronous copy (UBLKCP)
+    completing on an mbarrier (SYNCS), and the benchmark kernels issue fp64 FMAs (DFMA), not tensor-core instructions."""
+    import shutil
+    import subprocess
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    wc.build()
+    so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "walking-controllers_b200", "libwc_b200.so")
+    elfs = subprocess.run(["cuobjdump", "-lelf", so], capture_output=True, text=True).stdout
+    assert "sm_100a" in elfs and "sm_90" not in elfs and "sm_80" not in elfs
+    names = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
+    fn = [l.split("Function : ")[1].strip() for l in names.splitlines() if "Function : " in l]
+    tpi = [f for f in fn if "ik_tpi_kernel" in f]
+    split = [f for f in fn if "mpc_split_kernelILb0ELi25E" in f]
+    assert len(tpi) == 1 and len(split) == 1
+    sass = subprocess.run(["cuobjdump", "-sass", "-fun", tpi[0], so], capture_output=True, text=True).stdout
+    assert "UBLKCP" in sass and "SYNCS" in sass and "DFMA" in sass
+    sass = subprocess.run(["cuobjdump", "-sass", "-fun", split[0], so], capture_output=True, text=True).stdout
+    assert sass.count("DFMA") > 1000 and "HMMA" not in sass and "UTCMMA" not in sass
