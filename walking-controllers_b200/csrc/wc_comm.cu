@@ -136,17 +136,24 @@ wc_status wc_gather_async(wc_comm* c, const wc_gather_io* io, int32_t B, int32_t
     if (cudaEventRecord(c->ready, ps) != cudaSuccess || cudaStreamWaitEvent(c->side, c->ready, 0) != cudaSuccess) return WC_ERR_CUDA;
     const size_t Bz = (size_t)B;
     NCHECK(N.GroupStart());
-    if (io->zmp && io->zmp_all) NCHECK(N.AllGather(io->zmp, io->zmp_all, 2 * Bz, ncclFloat64, c->comm, c->side));
-    if (io->dq && io->dq_all) NCHECK(N.AllGather(io->dq, io->dq_all, (size_t)n_dofs * Bz, ncclFloat64, c->comm, c->side));
-    if (io->osqp_status && io->osqp_status_all) NCHECK(N.AllGather(io->osqp_status, io->osqp_status_all, Bz, ncclInt32, c->comm, c->side));
-    if (io->iters && io->iters_all) NCHECK(N.AllGather(io->iters, io->iters_all, Bz, ncclInt32, c->comm, c->side));
-    if (io->qp_status && io->qp_status_all) NCHECK(N.AllGather(io->qp_status, io->qp_status_all, Bz, ncclInt32, c->comm, c->side));
-    if (io->nwsr && io->nwsr_all) NCHECK(N.AllGather(io->nwsr, io->nwsr_all, Bz, ncclInt32, c->comm, c->side));
+    // inside the group an error must not return before ncclGroupEnd (the group would stay open on this thread)
+    ncclResult_t bad = 0;
+    auto ok = [&](ncclResult_t r) { if (r != 0 && bad == 0) bad = r; };
+    if (io->zmp && io->zmp_all) ok(N.AllGather(io->zmp, io->zmp_all, 2 * Bz, ncclFloat64, c->comm, c->side));
+    if (io->dq && io->dq_all) ok(N.AllGather(io->dq, io->dq_all, (size_t)n_dofs * Bz, ncclFloat64, c->comm, c->side));
+    if (io->osqp_status && io->osqp_status_all) ok(N.AllGather(io->osqp_status, io->osqp_status_all, Bz, ncclInt32, c->comm, c->side));
+    if (io->iters && io->iters_all) ok(N.AllGather(io->iters, io->iters_all, Bz, ncclInt32, c->comm, c->side));
+    if (io->qp_status && io->qp_status_all) ok(N.AllGather(io->qp_status, io->qp_status_all, Bz, ncclInt32, c->comm, c->side));
+    if (io->nwsr && io->nwsr_all) ok(N.AllGather(io->nwsr, io->nwsr_all, Bz, ncclInt32, c->comm, c->side));
     if (io->stats_sum && io->n_stats_sum > 0)
-        NCHECK(N.AllReduce(io->stats_sum, io->stats_sum, (size_t)io->n_stats_sum, ncclFloat64, ncclSum, c->comm, c->side));
+        ok(N.AllReduce(io->stats_sum, io->stats_sum, (size_t)io->n_stats_sum, ncclFloat64, ncclSum, c->comm, c->side));
     if (io->stats_max && io->n_stats_max > 0)
-        NCHECK(N.AllReduce(io->stats_max, io->stats_max, (size_t)io->n_stats_max, ncclFloat64, ncclMax, c->comm, c->side));
-    NCHECK(N.GroupEnd());
+        ok(N.AllReduce(io->stats_max, io->stats_max, (size_t)io->n_stats_max, ncclFloat64, ncclMax, c->comm, c->side));
+    ok(N.GroupEnd());
+    if (bad != 0) {
+        std::fprintf(stderr, "[wc_gather_async] NCCL error %d (%s)\n", bad, N.GetErrorString ? N.GetErrorString(bad) : "?");
+        return WC_ERR_CUDA;
+    }
     if (cudaEventRecord(c->done, c->side) != cudaSuccess) return WC_ERR_CUDA;
     c->collectives += 1;
     return WC_OK;
