@@ -67,6 +67,17 @@ __device__ __forceinline__ double sx16(double v) { return __shfl_xor_sync(FULL, 
 __device__ __forceinline__ double sx8(double v) { return __shfl_xor_sync(FULL, v, 8); }
 // reductions over the four lanes of an instance (lane bits 3 and 4); symmetric, so all four get the same bits
 __device__ __forceinline__ double inst_max(double v) { v = fmax(v, sx8(v)); return fmax(v, sx16(v)); }
+// running infinity norm as OSQP's vec_norm_inf writes it (`if (|v| > max) max = |v|`): one compare and one select, where fmax on
+// doubles is a seven-instruction sequence (there is no fp64 min/max instruction; the rest is NaN handling).  m is never NaN.
+__device__ __forceinline__ double amax(double m, double v) { const double av = fabs(v); return av > m ? av : m; }
+// the same over the four lanes of an instance, for accumulators built by amax (never NaN, never negative: symmetric)
+__device__ __forceinline__ double inst_amax(double v)
+{
+    const double p = sx8(v);
+    v = p > v ? p : v;
+    const double q = sx16(v);
+    return q > v ? q : v;
+}
 __device__ __forceinline__ double inst_sum(double v) { v += sx8(v); return v + sx16(v); }
 
 // LDL' of a symmetric 6x6 (lower triangle of M), then rows of the inverse by two triangular solves
@@ -410,8 +421,7 @@ __global__ void __launch_bounds__(32 * WC_SPLIT_WARPS, WC_SPLIT_MINB / WC_SPLIT_
                 const double zt = HC_(H_HXS, h) * ux + HC_(H_HYS, h) * uy;
                 const double zr = alpha * zt + oma * zh[r];
                 double zn = zr + rho_inv * yh[r];
-                zn = fmax(zn, HC_(H_LO, h));
-                zn = fmin(zn, HC_(H_UP, h));
+                { const double lo = HC_(H_LO, h), up = HC_(H_UP, h); zn = zn > lo ? zn : lo; zn = zn < up ? zn : up; } // c_min(c_max(.))
                 const double dy = rho * (zr - zn);
                 if (!PHASE2 || act) { zh[r] = zn; yh[r] += dy; dyh[r] = dy; }
             }
@@ -464,70 +474,77 @@ __global__ void __launch_bounds__(32 * WC_SPLIT_WARPS, WC_SPLIT_MINB / WC_SPLIT_
     };
 
     // update_info + the norms of check_termination for the CURRENT (x, z, y), all in unscaled quantities;
-    // SC: also the norms of the SCALED residuals (compute_rho_estimate; an adaptive-rho iteration only)
-    auto update_info = [&](const bool SC) {
-        double m_rp_u = 0, m_rp_s = 0, m_z_u = 0, m_z_s = 0, m_ax_u = 0, m_ax_s = 0;
-        double m_rd_u = 0, m_rd_s = 0, m_q_u = 0, m_q_s = 0, m_aty_u = 0, m_aty_s = 0, m_px_u = 0, m_px_s = 0;
-        const double Xpart = sx16(X[T - 1]);         // top: x_{s-1}; bottom: x_s
-        const double Upart = sx16(U[T >= 2 ? T - 2 : 0]); // top: u_{s-2}; bottom: u_s
-        // hull rows' share of (A' y) on u_0 of both axes
+    // SC: also the norms of the SCALED residuals (compute_rho_estimate; an adaptive-rho iteration only).
+    // SC is a compile-time tag (std::true_type / std::false_type): as a run-time flag every slot's scaled part was a branch over
+    // code that is never fetched otherwise, and each of those jumps landed on a cold instruction-cache line.
+    // The slot body is written once (info_slot) and used in two forms: unrolled over the iterate in registers (phase 2, which goes
+    // back into the ADMM loop afterwards), and ROLLED over a copy of the iterate in shared memory (phase 1, where the factor arrays
+    // are dead once the iterations are done): 13 trips through ~100 instructions that stay in the L0 instruction cache instead of
+    // ~1 500 instructions fetched once from L2 by every warp.
+    struct InfoAcc {
+        double rp_u = 0, rp_s = 0, z_u = 0, z_s = 0, ax_u = 0, ax_s = 0;
+        double rd_u = 0, rd_s = 0, q_u = 0, q_s = 0, aty_u = 0, aty_s = 0, px_u = 0, px_s = 0;
+    };
+    const int kx0_ = bot ? -OFF : N;                 // x index of slot 0; +1 / -1 per slot
+    const ptrdiff_t sB_ = bot ? (ptrdiff_t)B : -(ptrdiff_t)B;
+    const ptrdiff_t xrow0_ = ((ptrdiff_t)(a * nA + kx0_)) * (ptrdiff_t)B + i;
+    const ptrdiff_t urow0_ = ((ptrdiff_t)(a * nA + nR + kx0_ - (bot ? 0 : 1))) * (ptrdiff_t)B + i;
+    const ptrdiff_t erow0_ = ((ptrdiff_t)(a * nR + kx0_ + (bot ? 1 : 0))) * (ptrdiff_t)B + i;
+    // slot t: Xt, Ut, Yt its iterate; Xn / Un the x / u of slot t + 1 (the partner lane's at the separator), Ua the u of slot t - 1
+    // (0 before the first), Yp the multiplier of the previous row (Y0 for the bottom lane's first real slot, 0 before the first)
+    auto info_slot = [&](auto sc_tag, const int t, const double Xt, const double Xn, const double Ua, const double Ut, const double Un,
+                         const double Yt, const double Yp, const double hy_m, InfoAcc& A) {
+        constexpr bool SC = decltype(sc_tag)::value;
+        const bool real = (t >= OFF) || !bot;
+        const bool shadow = bot && t == T - 1;       // the bottom lane's copy of (u_{s-1}, row s): counted by the top lane
+        double Dx = 1.0, Du = 1.0, Ek = 1.0;
+        if (SC) { if (real) { Dx = __ldg(d.D + (xrow0_ + t * sB_)); Du = __ldg(d.D + (urow0_ + t * sB_)); Ek = __ldg(d.Eeq + (erow0_ + t * sB_)); } }
+        if (real) { // equality row of the slot: z = l = u = 0
+            const double ax = fma(b_, Ut, cx0 * Xt + cx1 * Xn);
+            A.rp_u = amax(A.rp_u, ax); A.ax_u = amax(A.ax_u, ax);
+            if (SC) { A.rp_s = amax(A.rp_s, Ek * ax); A.ax_s = amax(A.ax_s, Ek * ax); }
+        }
+        { // x unknown
+            const double aty = -(cy0 * Yt + cy1 * Yp);
+            const double px = cQ * Xt, q = S_(A_CQ, t);
+            const double rr = q + px + aty;
+            A.rd_u = amax(A.rd_u, rr); A.q_u = amax(A.q_u, q);
+            A.aty_u = amax(A.aty_u, aty); A.px_u = amax(A.px_u, px);
+            if (SC) {
+                A.rd_s = amax(A.rd_s, Dx * rr); A.q_s = amax(A.q_s, Dx * q);
+                A.aty_s = amax(A.aty_s, Dx * aty); A.px_s = amax(A.px_s, Dx * px);
+            }
+        }
+        if (!shadow && real) { // u unknown (a dummy's row would pick up its neighbour u_0)
+            const double sc = (t == 0) ? (bot ? 2.0 : 1.0) : 2.0;
+            const double px = cR * ((sc * Ut - Ua) - Un);
+            double aty = b_ * Yt;
+            double q = 0.0;
+            if (t == OFF) { if (bot) { aty += hy_m; q = cqu0; } }
+            const double rr = q + px + aty;
+            A.rd_u = amax(A.rd_u, rr); A.q_u = amax(A.q_u, q);
+            A.aty_u = amax(A.aty_u, aty); A.px_u = amax(A.px_u, px);
+            if (SC) {
+                A.rd_s = amax(A.rd_s, Du * rr); A.q_s = amax(A.q_s, Du * q);
+                A.aty_s = amax(A.aty_s, Du * aty); A.px_s = amax(A.px_s, Du * px);
+            }
+        }
+    };
+    // hull rows' share of (A' y) on u_0 of this lane's axis
+    auto info_hull_aty = [&]() -> double {
         double hyx = 0.0, hyy = 0.0;
 #pragma unroll
         for (int r = 0; r < 2; r++) { hyx += HC_(H_HXS, q4 + 4 * r) * yh[r]; hyy += HC_(H_HYS, q4 + 4 * r) * yh[r]; }
         hyx = inst_sum(hyx); hyy = inst_sum(hyy);
-        const double hy_m = a == 0 ? hyx : hyy;
-        const int kx0 = bot ? -OFF : N;
-        const ptrdiff_t sB = bot ? (ptrdiff_t)B : -(ptrdiff_t)B;
-        const ptrdiff_t xrow0 = ((ptrdiff_t)(a * nA + kx0)) * (ptrdiff_t)B + i;
-        const ptrdiff_t urow0 = ((ptrdiff_t)(a * nA + nR + kx0 - (bot ? 0 : 1))) * (ptrdiff_t)B + i;
-        const ptrdiff_t erow0 = ((ptrdiff_t)(a * nR + kx0 + (bot ? 1 : 0))) * (ptrdiff_t)B + i;
-#pragma unroll
-        for (int t = 0; t < T; t++) {
-            const bool real = (t >= OFF) || !bot;
-            const bool shadow = bot && t == T - 1;   // the bottom lane's copy of (u_{s-1}, row s): counted by the top lane
-            double Dx = 1.0, Du = 1.0, Ek = 1.0;
-            if (SC) { if (real) { Dx = __ldg(d.D + (xrow0 + t * sB)); Du = __ldg(d.D + (urow0 + t * sB)); Ek = __ldg(d.Eeq + (erow0 + t * sB)); } }
-            if (real) { // equality row of the slot: z = l = u = 0
-                const double xn_ = (t < T - 1) ? X[t < T - 1 ? t + 1 : t] : Xpart;
-                const double ax = fma(b_, U[t], cx0 * X[t] + cx1 * xn_);
-                m_rp_u = fmax(m_rp_u, fabs(ax)); m_ax_u = fmax(m_ax_u, fabs(ax));
-                if (SC) { m_rp_s = fmax(m_rp_s, fabs(Ek * ax)); m_ax_s = fmax(m_ax_s, fabs(Ek * ax)); }
-            }
-            { // x unknown
-                double yp;
-                if (t == OFF) yp = bot ? Y0 : (t == 0 ? 0.0 : Y[t > 0 ? t - 1 : 0]);
-                else yp = (t == 0) ? 0.0 : Y[t > 0 ? t - 1 : 0];
-                const double aty = -(cy0 * Y[t] + cy1 * yp);
-                const double px = cQ * X[t], q = S_(A_CQ, t);
-                const double rr = q + px + aty;
-                m_rd_u = fmax(m_rd_u, fabs(rr)); m_q_u = fmax(m_q_u, fabs(q));
-                m_aty_u = fmax(m_aty_u, fabs(aty)); m_px_u = fmax(m_px_u, fabs(px));
-                if (SC) {
-                    m_rd_s = fmax(m_rd_s, fabs(Dx * rr)); m_q_s = fmax(m_q_s, fabs(Dx * q));
-                    m_aty_s = fmax(m_aty_s, fabs(Dx * aty)); m_px_s = fmax(m_px_s, fabs(Dx * px));
-                }
-            }
-            if (!shadow && real) { // u unknown (a dummy's row would pick up its neighbour u_0)
-                const double ua = (t >= 1) ? U[t >= 1 ? t - 1 : 0] : 0.0;
-                const double ubn = (t < T - 1) ? U[t < T - 1 ? t + 1 : t] : Upart;
-                const double sc = (t == 0) ? (bot ? 2.0 : 1.0) : 2.0;
-                const double px = cR * ((sc * U[t] - ua) - ubn);
-                double aty = b_ * Y[t];
-                double q = 0.0;
-                if (t == OFF) { if (bot) { aty += hy_m; q = cqu0; } }
-                const double rr = q + px + aty;
-                m_rd_u = fmax(m_rd_u, fabs(rr)); m_q_u = fmax(m_q_u, fabs(q));
-                m_aty_u = fmax(m_aty_u, fabs(aty)); m_px_u = fmax(m_px_u, fabs(px));
-                if (SC) {
-                    m_rd_s = fmax(m_rd_s, fabs(Du * rr)); m_q_s = fmax(m_q_s, fabs(Du * q));
-                    m_aty_s = fmax(m_aty_s, fabs(Du * aty)); m_px_s = fmax(m_px_s, fabs(Du * px));
-                }
-            }
-        }
+        return a == 0 ? hyx : hyy;
+    };
+    // equality row 0, the hull rows, and the reductions over the four lanes of the instance
+    auto info_finish = [&](auto sc_tag, InfoAcc& A) {
+        constexpr bool SC = decltype(sc_tag)::value;
         if (bot) { // equality row 0
             const double ax = -X[OFF], z = Z0, r = ax - z;
-            m_rp_u = fmax(m_rp_u, fabs(r)); m_z_u = fmax(m_z_u, fabs(z)); m_ax_u = fmax(m_ax_u, fabs(ax));
-            if (SC) { m_rp_s = fmax(m_rp_s, fabs(E0 * r)); m_z_s = fmax(m_z_s, fabs(E0 * z)); m_ax_s = fmax(m_ax_s, fabs(E0 * ax)); }
+            A.rp_u = amax(A.rp_u, r); A.z_u = amax(A.z_u, z); A.ax_u = amax(A.ax_u, ax);
+            if (SC) { A.rp_s = amax(A.rp_s, E0 * r); A.z_s = amax(A.z_s, E0 * z); A.ax_s = amax(A.ax_s, E0 * ax); }
         }
         { // hull rows
             const double u0x = __shfl_sync(FULL, U[OFF], 16 + s8), u0y = __shfl_sync(FULL, U[OFF], 24 + s8);
@@ -536,18 +553,64 @@ __global__ void __launch_bounds__(32 * WC_SPLIT_WARPS, WC_SPLIT_MINB / WC_SPLIT_
                 const int h = q4 + 4 * r;
                 const double ax = HC_(H_HXS, h) * u0x + HC_(H_HYS, h) * u0y;
                 const double z = zh[r], einv = HC_(H_EHI, h), rr = ax - z;
-                m_rp_u = fmax(m_rp_u, fabs(einv * rr)); m_z_u = fmax(m_z_u, fabs(einv * z)); m_ax_u = fmax(m_ax_u, fabs(einv * ax));
-                if (SC) { m_rp_s = fmax(m_rp_s, fabs(rr)); m_z_s = fmax(m_z_s, fabs(z)); m_ax_s = fmax(m_ax_s, fabs(ax)); }
+                A.rp_u = amax(A.rp_u, einv * rr); A.z_u = amax(A.z_u, einv * z); A.ax_u = amax(A.ax_u, einv * ax);
+                if (SC) { A.rp_s = amax(A.rp_s, rr); A.z_s = amax(A.z_s, z); A.ax_s = amax(A.ax_s, ax); }
             }
         }
-        pri_res = inst_max(m_rp_u); nz_u = inst_max(m_z_u); nAx_u = inst_max(m_ax_u);
-        dua_res = cinv * inst_max(m_rd_u); nq_u = cinv * inst_max(m_q_u);
-        nAty_u = cinv * inst_max(m_aty_u); nPx_u = cinv * inst_max(m_px_u);
+        pri_res = inst_amax(A.rp_u); nz_u = inst_amax(A.z_u); nAx_u = inst_amax(A.ax_u);
+        dua_res = cinv * inst_amax(A.rd_u); nq_u = cinv * inst_amax(A.q_u);
+        nAty_u = cinv * inst_amax(A.aty_u); nPx_u = cinv * inst_amax(A.px_u);
         if (SC) {
-            rp_s = inst_max(m_rp_s); nz_s = inst_max(m_z_s); nAx_s = inst_max(m_ax_s);
-            rd_s = inst_max(m_rd_s); nq_s = inst_max(m_q_s); nAty_s = inst_max(m_aty_s); nPx_s = inst_max(m_px_s);
+            rp_s = inst_amax(A.rp_s); nz_s = inst_amax(A.z_s); nAx_s = inst_amax(A.ax_s);
+            rd_s = inst_amax(A.rd_s); nq_s = inst_amax(A.q_s); nAty_s = inst_amax(A.aty_s); nPx_s = inst_amax(A.px_s);
         }
     };
+    // phase 2: the iterate stays in registers
+    auto update_info = [&](auto sc_tag) {
+        InfoAcc A;
+        const double Xpart = sx16(X[T - 1]);         // top: x_{s-1}; bottom: x_s
+        const double Upart = sx16(U[T >= 2 ? T - 2 : 0]); // top: u_{s-2}; bottom: u_s
+        const double hy_m = info_hull_aty();
+#pragma unroll
+        for (int t = 0; t < T; t++) {
+            const double Xn = (t < T - 1) ? X[t < T - 1 ? t + 1 : t] : Xpart;
+            const double Un = (t < T - 1) ? U[t < T - 1 ? t + 1 : t] : Upart;
+            const double Ua = (t >= 1) ? U[t >= 1 ? t - 1 : 0] : 0.0;
+            double Yp;
+            if (t == OFF) Yp = bot ? Y0 : (t == 0 ? 0.0 : Y[t > 0 ? t - 1 : 0]);
+            else Yp = (t == 0) ? 0.0 : Y[t > 0 ? t - 1 : 0];
+            info_slot(sc_tag, t, X[t], Xn, Ua, U[t], Un, Y[t], Yp, hy_m, A);
+        }
+        info_finish(sc_tag, A);
+    };
+    // phase 1: the iterations are over, the six factor arrays are free.  X, U, Y go to three of them (the other three receive
+    // 1 / D and 1 / E for the epilogue, requested asynchronously before this is called) and the slots are walked by a real loop.
+#define DX_(t) sl[((SD::A_L1X) * T + (t)) * 32]
+#define DU_(t) sl[((SD::A_L2X) * T + (t)) * 32]
+#define DY_(t) sl[((SD::A_DIX) * T + (t)) * 32]
+#define DIX_(t) sl[((SD::A_L1U) * T + (t)) * 32]
+#define DIU_(t) sl[((SD::A_L2U) * T + (t)) * 32]
+#define DIE_(t) sl[((SD::A_DIU) * T + (t)) * 32]
+    auto update_info_rolled = [&](auto sc_tag) {
+        InfoAcc A;
+        const double Xpart = sx16(X[T - 1]);
+        const double Upart = sx16(U[T >= 2 ? T - 2 : 0]);
+        const double hy_m = info_hull_aty();
+#pragma unroll
+        for (int t = 0; t < T; t++) { DX_(t) = X[t]; DU_(t) = U[t]; DY_(t) = Y[t]; }
+#pragma unroll 1
+        for (int t = 0; t < T; t++) {
+            const int tn = t < T - 1 ? t + 1 : t, tp = t > 0 ? t - 1 : 0;
+            const double xn = DX_(tn), un = DU_(tn), ua = DU_(tp), ypv = DY_(tp);
+            const double Xn = (t < T - 1) ? xn : Xpart;
+            const double Un = (t < T - 1) ? un : Upart;
+            const double Ua = (t >= 1) ? ua : 0.0;
+            const double Yp = (t == OFF && bot) ? Y0 : (t == 0 ? 0.0 : ypv);
+            info_slot(sc_tag, t, DX_(t), Xn, Ua, DU_(t), Un, DY_(t), Yp, hy_m, A);
+        }
+        info_finish(sc_tag, A);
+    };
+
 
     // is_primal_infeasible (OSQP auxil.c) on delta_y of the last iteration, recomputed from X+ and dX
     // (X~ = X+ + (1/alpha - 1) dX; delta Yh_k = alpha rho_e E_k^2 (A X~)_k on the equality rows)
@@ -566,8 +629,8 @@ __global__ void __launch_bounds__(32 * WC_SPLIT_WARPS, WC_SPLIT_MINB / WC_SPLIT_
         }
         double nrm = 0.0, lhs = 0.0;
 #pragma unroll
-        for (int t = 0; t < T; t++) nrm = fmax(nrm, fabs(dY[t]));
-        if (bot) { nrm = fmax(nrm, fabs(dY0)); lhs += (-dcm_a) * dY0; }
+        for (int t = 0; t < T; t++) nrm = amax(nrm, dY[t]);
+        if (bot) { nrm = amax(nrm, dY0); lhs += (-dcm_a) * dY0; }
         double dyp[2];
 #pragma unroll
         for (int r = 0; r < 2; r++) { // project delta_y of the hull rows on the polar of the recession cone
@@ -579,7 +642,7 @@ __global__ void __launch_bounds__(32 * WC_SPLIT_WARPS, WC_SPLIT_MINB / WC_SPLIT_
             else if (l_inf) dy = fmax(dy, 0.0);
             if (h >= nh) dy = 0.0;
             dyp[r] = dy;
-            nrm = fmax(nrm, fabs(e * dy));
+            nrm = amax(nrm, e * dy);
             lhs += uh * fmax(dy, 0.0) + lh * fmin(dy, 0.0);
         }
         nrm = inst_max(nrm);
@@ -595,10 +658,10 @@ __global__ void __launch_bounds__(32 * WC_SPLIT_WARPS, WC_SPLIT_MINB / WC_SPLIT_
             double yp;
             if (t == OFF) yp = bot ? dY0 : (t == 0 ? 0.0 : dY[t > 0 ? t - 1 : 0]);
             else yp = (t == 0) ? 0.0 : dY[t > 0 ? t - 1 : 0];
-            m = fmax(m, fabs(cy0 * dY[t] + cy1 * yp));
+            m = amax(m, cy0 * dY[t] + cy1 * yp);
             double aty = b_ * dY[t];
             if (t == OFF) { if (bot) aty += (a == 0 ? hdx : hdy); }
-            if (!(bot && t == T - 1)) m = fmax(m, fabs(aty));
+            if (!(bot && t == T - 1)) m = amax(m, aty);
         }
         m = inst_max(m);
         if (nrm > 1.0 / infty && lhs < -eps * nrm) res = m < eps * nrm;
@@ -609,9 +672,9 @@ __global__ void __launch_bounds__(32 * WC_SPLIT_WARPS, WC_SPLIT_MINB / WC_SPLIT_
         double nrm = 0.0, qdx = 0.0;
 #pragma unroll
         for (int t = 0; t < T; t++) {
-            nrm = fmax(nrm, fabs(tX[t]));
+            nrm = amax(nrm, tX[t]);
             qdx = fma(S_(A_CQ, t), tX[t], qdx);
-            if (!(bot && t == T - 1)) nrm = fmax(nrm, fabs(tU[t]));
+            if (!(bot && t == T - 1)) nrm = amax(nrm, tU[t]);
         }
         if (bot) qdx = fma(cqu0, tU[OFF], qdx);
         nrm = inst_max(nrm);
@@ -622,12 +685,12 @@ __global__ void __launch_bounds__(32 * WC_SPLIT_WARPS, WC_SPLIT_MINB / WC_SPLIT_
         int bad = 0;
 #pragma unroll
         for (int t = 0; t < T; t++) {
-            m = fmax(m, fabs(cQ * tX[t]));
+            m = amax(m, cQ * tX[t]);
             if (!(bot && (t == T - 1 || t < OFF))) {
                 const double ua = (t >= 1) ? tU[t >= 1 ? t - 1 : 0] : 0.0;
                 const double ubn = (t < T - 1) ? tU[t < T - 1 ? t + 1 : t] : Upart;
                 const double sc = (t == 0) ? (bot ? 2.0 : 1.0) : 2.0;
-                m = fmax(m, fabs(cR * ((sc * tU[t] - ua) - ubn)));
+                m = amax(m, cR * ((sc * tU[t] - ua) - ubn));
             }
             const double xn_ = (t < T - 1) ? tX[t < T - 1 ? t + 1 : t] : Xpart;
             const double ax = fma(b_, tU[t], cx0 * tX[t] + cx1 * xn_);
@@ -712,7 +775,7 @@ __global__ void __launch_bounds__(32 * WC_SPLIT_WARPS, WC_SPLIT_MINB / WC_SPLIT_
         if (adaptive) { to_adapt -= run; if (to_adapt == 0) { adapt_now = true; to_adapt = rint; } }
         const bool at_max = iter >= max_iter;
         // ---- termination / adaptive rho (instance-uniform decisions, warp-uniform control flow)
-        update_info(adapt_now);
+        if (adapt_now) update_info(std::true_type{}); else update_info(std::false_type{});
 #pragma unroll 1
         for (int approx = 0; approx < 2; approx++) {
             if (approx == 0) {
