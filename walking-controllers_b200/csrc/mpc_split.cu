@@ -139,11 +139,15 @@ __global__ void __launch_bounds__(32 * WC_SPLIT_WARPS, WC_SPLIT_MINB / WC_SPLIT_
     const int s8 = lane & 7, a = (lane >> 3) & 1, q4 = lane >> 3;
     const bool bot = lane >= 16;
     const size_t B = (size_t)d.B;
-    double* const sl = sm + lane;                    // full arrays: element (arr, t) at sl[(arr * T + t) * 32]
-    double* const sb = sm + SD::oLBX + (lane & 15);  // border arrays (bottom lanes)
-    double* const smr = sm + SD::oM + a * SD::kMAxis * 8 + s8;
-    double* const sh = sm + SD::oH + s8;             // hull constants: (arr, h) at sh[(arr * 8 + h) * 8]
+    // (not const: phase 1 adds a run-time zero to them in every iteration, see there)
+    double* sl = sm + lane;                          // full arrays: element (arr, t) at sl[(arr * T + t) * 32]
+    double* sb = sm + SD::oLBX + (lane & 15);        // border arrays (bottom lanes)
+    double* smr = sm + SD::oM + a * SD::kMAxis * 8 + s8;
+    double* sh = sm + SD::oH + s8;                   // hull constants: (arr, h) at sh[(arr * 8 + h) * 8]
 #define S_(arr, t) sl[((SD::arr) * T + (t)) * 32]
+#define SV_(arr, t) (*(volatile const double*)&sl[((SD::arr) * T + (t)) * 32])
+#define LBXV_(t) (*(volatile const double*)&sb[(t) * 16])
+#define LBUV_(t) (*(volatile const double*)&sb[(T + (t)) * 16])
 #define LBX_(t) sb[(t) * 16]
 #define LBU_(t) sb[(T + (t)) * 16]
 #define HC_(arr, h) sh[((SD::arr) * 8 + (h)) * 8]
@@ -426,6 +430,8 @@ __global__ void __launch_bounds__(32 * WC_SPLIT_WARPS, WC_SPLIT_MINB / WC_SPLIT_
                 if (!PHASE2 || act) { zh[r] = zn; yh[r] += dy; dyh[r] = dy; }
             }
         }
+        // (the multipliers both sweeps use are read again here as VOLATILE loads: left to itself ptxas keeps some twenty of them
+        // in registers from the forward sweep and parks parts of the iterate in local memory to make room)
         // ---- backward: L' x~ = D^-1 t away from the separator, fused with update_y (equality rows) and update_x
         {
             const double ub = bot ? U0m : 0.0;
@@ -435,16 +441,16 @@ __global__ void __launch_bounds__(32 * WC_SPLIT_WARPS, WC_SPLIT_MINB / WC_SPLIT_
                 double xu, xx, sxr;
                 if (t == T - 1) {
                     xu = Us;
-                    const double xe = fma(-S_(A_L1X, t), Us, fma(-S_(A_L2X, t), Xs, tX[t] * S_(A_DIX, t)));
-                    xx = bot ? fma(-LBX_(T - 1 < 0 ? 0 : T - 1), ub, xe) : Xs;
+                    const double xe = fma(-SV_(A_L1X, t), Us, fma(-SV_(A_L2X, t), Xs, tX[t] * S_(A_DIX, t)));
+                    xx = bot ? fma(-LBXV_(T - 1 < 0 ? 0 : T - 1), ub, xe) : Xs;
                     sxr = sx16(xx);                  // top: x_{s-1} of the bottom lane; bottom: x_s
                 } else {
-                    double pu = fma(-S_(A_L2U, t), su, tU[t] * S_(A_DIU, t));
-                    double px = fma(-S_(A_L2X, t), sx, tX[t] * S_(A_DIX, t));
-                    if (bot) { pu = fma(-LBU_(t), ub, pu); px = fma(-LBX_(t), ub, px); }
-                    xu = fma(-S_(A_L1U, t), sx, pu);
+                    double pu = fma(-SV_(A_L2U, t), su, tU[t] * S_(A_DIU, t));
+                    double px = fma(-SV_(A_L2X, t), sx, tX[t] * S_(A_DIX, t));
+                    if (bot) { pu = fma(-LBUV_(t), ub, pu); px = fma(-LBXV_(t), ub, px); }
+                    xu = fma(-SV_(A_L1U, t), sx, pu);
                     if (t == OFF) { if (bot) xu = U0m; }
-                    xx = fma(-S_(A_L1X, t), xu, px);
+                    xx = fma(-SV_(A_L1X, t), xu, px);
                     sxr = sx;
                 }
                 // slot T-1: the two lanes of the axis hold copies of row s; the sum of two rounded products is
@@ -485,11 +491,13 @@ __global__ void __launch_bounds__(32 * WC_SPLIT_WARPS, WC_SPLIT_MINB / WC_SPLIT_
         double rp_u = 0, rp_s = 0, z_u = 0, z_s = 0, ax_u = 0, ax_s = 0;
         double rd_u = 0, rd_s = 0, q_u = 0, q_s = 0, aty_u = 0, aty_s = 0, px_u = 0, px_s = 0;
     };
-    const int kx0_ = bot ? -OFF : N;                 // x index of slot 0; +1 / -1 per slot
-    const ptrdiff_t sB_ = bot ? (ptrdiff_t)B : -(ptrdiff_t)B;
-    const ptrdiff_t xrow0_ = ((ptrdiff_t)(a * nA + kx0_)) * (ptrdiff_t)B + i;
-    const ptrdiff_t urow0_ = ((ptrdiff_t)(a * nA + nR + kx0_ - (bot ? 0 : 1))) * (ptrdiff_t)B + i;
-    const ptrdiff_t erow0_ = ((ptrdiff_t)(a * nR + kx0_ + (bot ? 1 : 0))) * (ptrdiff_t)B + i;
+    // workspace rows of the lane's slot 0 and the step per slot: recomputed where they are used (macros, not variables: as
+    // variables they are live across the ADMM loop, eight registers the loop does not have)
+#define kx0_ (bot ? -OFF : N)
+#define sB_ (bot ? (ptrdiff_t)B : -(ptrdiff_t)B)
+#define xrow0_ (((ptrdiff_t)(a * nA + kx0_)) * (ptrdiff_t)B + i)
+#define urow0_ (((ptrdiff_t)(a * nA + nR + kx0_ - (bot ? 0 : 1))) * (ptrdiff_t)B + i)
+#define erow0_ (((ptrdiff_t)(a * nR + kx0_ + (bot ? 1 : 0))) * (ptrdiff_t)B + i)
     // slot t: Xt, Ut, Yt its iterate; Xn / Un the x / u of slot t + 1 (the partner lane's at the separator), Ua the u of slot t - 1
     // (0 before the first), Yp the multiplier of the previous row (Y0 for the bottom lane's first real slot, 0 before the first)
     auto info_slot = [&](auto sc_tag, const int t, const double Xt, const double Xn, const double Ua, const double Ut, const double Un,
@@ -747,6 +755,80 @@ __global__ void __launch_bounds__(32 * WC_SPLIT_WARPS, WC_SPLIT_MINB / WC_SPLIT_
     int iter = PHASE2 ? phase1_len : 0;
     int to_check = chk ? chk - (iter % chk) : 0;
     int to_adapt = adaptive ? rint - (iter % rint) : 0;
+    // the adaptive-rho step of osqp_solve (compute_rho_estimate + adapt_rho) from the scaled norms of update_info
+    auto adapt_rho = [&]() {
+        const double pr = rp_s / (fmax(nz_s, nAx_s) + 1e-10);
+        const double dr = rd_s / (fmax(fmax(nq_s, nAty_s), nPx_s) + 1e-10);
+        double rn = rho * sqrt(pr / (dr + 1e-10));
+        rn = fmin(fmax(rn, kRhoMin), kRhoMax);
+        if (rn > rho * st.adaptive_rho_tolerance || rn < rho / st.adaptive_rho_tolerance) {
+            rho = rn;
+            rho_updates++;
+        }
+    };
+    if constexpr (!PHASE2) {
+        // ---- phase 1 is ONE pass of osqp_solve's loop, written straight: factor, phase1_len iterations, one update_info, the
+        // checks that fall on that iteration.  Everything after the iterations walks the slots with real loops over a copy of the
+        // iterate in shared memory (update_info_rolled, the epilogue), so that the once-per-warp code is a few hundred
+        // instructions instead of several thousand fetched from L2.
+        if (__any_sync(FULL, !done)) {
+        build_factor();
+        Yext = Y0 - (kRhoEqOverIneq * rho * EE0) * Z0;
+        hull_partials();
+        const int run = phase1_len < 1 ? 1 : phase1_len;
+        const bool act = !done;
+        const double rho_inv = 1.0 / rho;
+        // (the shared-memory constants are loop-invariant, and ptxas hoists ~20 of them into registers at the price of spilling
+        // parts of the iterate to local memory inside the loop: the base pointers get a zero it cannot fold)
+#pragma unroll 1
+        for (int r = 0; r < run; r++) {
+            const int z = r >> 30;
+            sl += z; sb += z; smr += z; sh += z;
+            iteration(act, rho_inv);
+        }
+        iter = run;
+        if (act) iter_done = iter;
+        const bool check_now = chk && run == chk;
+        const bool adapt_now = adaptive && run == rint;
+        const bool at_max = iter >= max_iter;
+        // 1 / D and 1 / E of the lane's slots for the epilogue: asked for now (no register is involved), used after the checks
+        {
+            const unsigned s_dix = (unsigned)__cvta_generic_to_shared(&DIX_(0));
+            const unsigned s_diu = (unsigned)__cvta_generic_to_shared(&DIU_(0));
+            const unsigned s_die = (unsigned)__cvta_generic_to_shared(&DIE_(0));
+            const double* gx = d.Dinv + xrow0_;
+            const double* gu = d.Dinv + urow0_;
+            const double* ge = d.Einv + erow0_;
+            const ptrdiff_t sBv = sB_;
+            if (!skip) {
+#pragma unroll 1
+                for (int t = 0; t < T; t++) {
+                    if ((t >= OFF) || !bot) {
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s_dix + t * 256), "l"(gx + t * sBv) : "memory");
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s_diu + t * 256), "l"(gu + t * sBv) : "memory");
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s_die + t * 256), "l"(ge + t * sBv) : "memory");
+                    }
+                }
+            }
+            asm volatile("cp.async.commit_group;\n" ::: "memory");
+        }
+        if (adapt_now) update_info_rolled(std::true_type{}); else update_info_rolled(std::false_type{});
+#pragma unroll 1
+        for (int approx = 0; approx < 2; approx++) {
+            if (approx == 0) {
+                if (check_now || at_max) {
+                    const int stop = check_termination(0);
+                    if (act && !done && stop) { status = stop; done = true; }
+                }
+                if (adapt_now && act && !done) adapt_rho();
+            } else if (at_max) { // osqp_solve leaves the loop: approximate criteria, else MAX_ITER_REACHED
+                const int stop = check_termination(1);
+                if (act && !done) { status = stop ? stop : WC_OSQP_MAX_ITER_REACHED; done = true; }
+            }
+        }
+        asm volatile("cp.async.wait_all;\n" ::: "memory");
+        }
+    } else {
     bool refactor = true;
     bool warp_busy = __any_sync(FULL, !done);
     // every rare block below has ONE call site (update_info, check_termination, build_factor are large once inlined:
@@ -783,24 +865,15 @@ __global__ void __launch_bounds__(32 * WC_SPLIT_WARPS, WC_SPLIT_MINB / WC_SPLIT_
                     const int stop = check_termination(0);
                     if (act && !done && stop) { status = stop; done = true; }
                 }
-                if (adapt_now && act && !done) { // compute_rho_estimate + adapt_rho
-                    const double pr = rp_s / (fmax(nz_s, nAx_s) + 1e-10);
-                    const double dr = rd_s / (fmax(fmax(nq_s, nAty_s), nPx_s) + 1e-10);
-                    double rn = rho * sqrt(pr / (dr + 1e-10));
-                    rn = fmin(fmax(rn, kRhoMin), kRhoMax);
-                    if (rn > rho * st.adaptive_rho_tolerance || rn < rho / st.adaptive_rho_tolerance) {
-                        rho = rn;
-                        rho_updates++;
-                    }
-                }
+                if (adapt_now && act && !done) adapt_rho();
             } else if (at_max) { // osqp_solve leaves the loop: approximate criteria, else MAX_ITER_REACHED
                 const int stop = check_termination(1);
                 if (act && !done) { status = stop ? stop : WC_OSQP_MAX_ITER_REACHED; done = true; }
             }
         }
         if (adapt_now) refactor = true;
-        if (!PHASE2 && iter >= phase1_len) break; // unfinished instances go to the continuation list
         warp_busy = __any_sync(FULL, !done);
+    }
     }
     __syncwarp();
 
@@ -810,21 +883,35 @@ __global__ void __launch_bounds__(32 * WC_SPLIT_WARPS, WC_SPLIT_MINB / WC_SPLIT_
                            status == WC_OSQP_DUAL_INFEASIBLE || status == WC_OSQP_DUAL_INFEASIBLE_INACCURATE ||
                            status == WC_OSQP_UNSOLVED || status == WC_OSQP_NON_CVX) || unfinished;
     if (!skip) { // back to OSQP's scaled workspace
-        const int kx0 = bot ? -OFF : N;
-        const ptrdiff_t sB = bot ? (ptrdiff_t)B : -(ptrdiff_t)B;
-        const ptrdiff_t xrow0 = ((ptrdiff_t)(a * nA + kx0)) * (ptrdiff_t)B + i;
-        const ptrdiff_t urow0 = ((ptrdiff_t)(a * nA + nR + kx0 - (bot ? 0 : 1))) * (ptrdiff_t)B + i;
-        const ptrdiff_t erow0 = ((ptrdiff_t)(a * nR + kx0 + (bot ? 1 : 0))) * (ptrdiff_t)B + i;
+        if constexpr (!PHASE2) { // from the copy of the iterate and the scaling factors in shared memory (see update_info_rolled)
+            double* px = d.x + xrow0_;
+            double* pu = d.x + urow0_;
+            double* pe = d.yeq + erow0_;
+            const ptrdiff_t sBv = sB_;
+#pragma unroll 1
+            for (int t = 0; t < T; t++) {
+                const bool real = (t >= OFF) || !bot;
+                const bool shadow = bot && t == T - 1;
+                if (real) {
+                    px[t * sBv] = has_sol ? DX_(t) * DIX_(t) : 0.0;
+                    if (!shadow) {
+                        pu[t * sBv] = has_sol ? DU_(t) * DIU_(t) : 0.0;
+                        pe[t * sBv] = has_sol ? DY_(t) * DIE_(t) : 0.0;
+                    }
+                }
+            }
+        } else {
 #pragma unroll
-        for (int t = 0; t < T; t++) {
-            const bool real = (t >= OFF) || !bot;
-            const bool shadow = bot && t == T - 1;
-            if (real) {
-                const ptrdiff_t xr = xrow0 + t * sB, ur = urow0 + t * sB, er = erow0 + t * sB;
-                d.x[xr] = has_sol ? X[t] * __ldg(d.Dinv + (xr)) : 0.0;
-                if (!shadow) {
-                    d.x[ur] = has_sol ? U[t] * __ldg(d.Dinv + (ur)) : 0.0;
-                    d.yeq[er] = has_sol ? Y[t] * __ldg(d.Einv + (er)) : 0.0;
+            for (int t = 0; t < T; t++) {
+                const bool real = (t >= OFF) || !bot;
+                const bool shadow = bot && t == T - 1;
+                if (real) {
+                    const ptrdiff_t xr = xrow0_ + t * sB_, ur = urow0_ + t * sB_, er = erow0_ + t * sB_;
+                    d.x[xr] = has_sol ? X[t] * __ldg(d.Dinv + (xr)) : 0.0;
+                    if (!shadow) {
+                        d.x[ur] = has_sol ? U[t] * __ldg(d.Dinv + (ur)) : 0.0;
+                        d.yeq[er] = has_sol ? Y[t] * __ldg(d.Einv + (er)) : 0.0;
+                    }
                 }
             }
         }
@@ -910,6 +997,20 @@ __global__ void __launch_bounds__(32 * WC_SPLIT_WARPS, WC_SPLIT_MINB / WC_SPLIT_
     }
     __syncwarp(); // the next group of this CTA reuses the shared-memory working set
     } // groups
+#undef kx0_
+#undef sB_
+#undef xrow0_
+#undef urow0_
+#undef erow0_
+#undef DX_
+#undef DU_
+#undef DY_
+#undef DIX_
+#undef DIU_
+#undef DIE_
+#undef SV_
+#undef LBXV_
+#undef LBUV_
 #undef S_
 #undef LBX_
 #undef LBU_
