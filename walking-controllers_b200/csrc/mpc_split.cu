@@ -400,7 +400,18 @@ __global__ void __launch_bounds__(32 * WC_SPLIT_WARPS, WC_SPLIT_MINB / WC_SPLIT_
                 vu = bot ? fma(-l1x, tx, -(n2u * tup)) : fma(-n2u, tup, ru);
             }
         }
-        // ---- the dense 6x6: gather the right-hand side (own axis first), multiply by the stored rows of the inverse
+        // ---- the dense 6x6: gather the right-hand side (own axis first), multiply by the stored rows of the inverse.
+        // The 18 entries of the rows and the constants of the two hull rows are asked for HERE, as volatile loads ahead of the
+        // shuffles: placed by the compiler they sit one by one in front of the fma that uses them (register pressure), and the
+        // 26 exposed shared-memory latencies were a fifth of the loop's samples.
+        double mi[18], hcx[2], hcy[2], hlo[2], hup[2];
+#pragma unroll
+        for (int k = 0; k < 18; k++) mi[k] = *(volatile const double*)&smr[k * 8];
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            hcx[r] = *(volatile const double*)&HC_(H_HXS, q4 + 4 * r); hcy[r] = *(volatile const double*)&HC_(H_HYS, q4 + 4 * r);
+            hlo[r] = *(volatile const double*)&HC_(H_LO, q4 + 4 * r); hup[r] = *(volatile const double*)&HC_(H_UP, q4 + 4 * r);
+        }
         double r6[6];
         {
             const double c0m = (bot ? rb : 0.0) + hp_m;
@@ -411,9 +422,9 @@ __global__ void __launch_bounds__(32 * WC_SPLIT_WARPS, WC_SPLIT_MINB / WC_SPLIT_
         double Xs = 0.0, Us = 0.0, U0m = 0.0;
 #pragma unroll
         for (int k = 0; k < 6; k++) {
-            Xs = fma(smr[k * 8], r6[k], Xs);
-            Us = fma(smr[(6 + k) * 8], r6[k], Us);
-            U0m = fma(smr[(12 + k) * 8], r6[k], U0m);
+            Xs = fma(mi[k], r6[k], Xs);
+            Us = fma(mi[6 + k], r6[k], Us);
+            U0m = fma(mi[12 + k], r6[k], U0m);
         }
         const double U0o = sx8(U0m);
         // ---- hull rows (z~ = A x~): update_z / update_y of rows q4 and q4 + 4
@@ -421,11 +432,10 @@ __global__ void __launch_bounds__(32 * WC_SPLIT_WARPS, WC_SPLIT_MINB / WC_SPLIT_
             const double ux = a == 0 ? U0m : U0o, uy = a == 0 ? U0o : U0m;
 #pragma unroll
             for (int r = 0; r < 2; r++) {
-                const int h = q4 + 4 * r;
-                const double zt = HC_(H_HXS, h) * ux + HC_(H_HYS, h) * uy;
+                const double zt = hcx[r] * ux + hcy[r] * uy;
                 const double zr = alpha * zt + oma * zh[r];
                 double zn = zr + rho_inv * yh[r];
-                { const double lo = HC_(H_LO, h), up = HC_(H_UP, h); zn = zn > lo ? zn : lo; zn = zn < up ? zn : up; } // c_min(c_max(.))
+                zn = zn > hlo[r] ? zn : hlo[r]; zn = zn < hup[r] ? zn : hup[r]; // c_min(c_max(.))
                 const double dy = rho * (zr - zn);
                 if (!PHASE2 || act) { zh[r] = zn; yh[r] += dy; dyh[r] = dy; }
             }
