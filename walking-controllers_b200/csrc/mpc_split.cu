@@ -61,6 +61,11 @@ struct SplitDims {
     enum { H_HXS = 0, H_HYS, H_LO, H_UP, H_EH, H_EHI, H_COUNT };
     static constexpr int oH = oM + 2 * kMAxis * 8; // hull constants [H_COUNT][8 rows][8 instances]
     static constexpr int total = oH + H_COUNT * 8 * 8;
+    // copy of the iterate (X, U, Y) and of 1 / D, 1 / E for the rolled update_info / epilogue: phase 1 overlays the six factor arrays
+    // (dead once its iterations are over), phase 2 goes back into the loop and gets six arrays of its own (its occupancy is irrelevant)
+    static constexpr int oDump1 = A_L1X * T * 32;
+    static constexpr int oDump2 = total;
+    static constexpr int total2 = total + 6 * T * 32;
 };
 
 __device__ __forceinline__ double sx16(double v) { return __shfl_xor_sync(FULL, v, 16); }
@@ -135,7 +140,7 @@ __global__ void __launch_bounds__(32 * WC_SPLIT_WARPS, WC_SPLIT_MINB / WC_SPLIT_
     static_assert(N >= 4, "the split needs a separator away from u_0 / u_1");
     extern __shared__ double sm_all[];
     const int lane = threadIdx.x & 31;
-    double* const sm = sm_all + (size_t)(threadIdx.x >> 5) * SD::total;
+    double* const sm = sm_all + (size_t)(threadIdx.x >> 5) * (PHASE2 ? SD::total2 : SD::total);
     const int s8 = lane & 7, a = (lane >> 3) & 1, q4 = lane >> 3;
     const bool bot = lane >= 16;
     const size_t B = (size_t)d.B;
@@ -583,32 +588,15 @@ __global__ void __launch_bounds__(32 * WC_SPLIT_WARPS, WC_SPLIT_MINB / WC_SPLIT_
             rd_s = inst_amax(A.rd_s); nq_s = inst_amax(A.q_s); nAty_s = inst_amax(A.aty_s); nPx_s = inst_amax(A.px_s);
         }
     };
-    // phase 2: the iterate stays in registers
-    auto update_info = [&](auto sc_tag) {
-        InfoAcc A;
-        const double Xpart = sx16(X[T - 1]);         // top: x_{s-1}; bottom: x_s
-        const double Upart = sx16(U[T >= 2 ? T - 2 : 0]); // top: u_{s-2}; bottom: u_s
-        const double hy_m = info_hull_aty();
-#pragma unroll
-        for (int t = 0; t < T; t++) {
-            const double Xn = (t < T - 1) ? X[t < T - 1 ? t + 1 : t] : Xpart;
-            const double Un = (t < T - 1) ? U[t < T - 1 ? t + 1 : t] : Upart;
-            const double Ua = (t >= 1) ? U[t >= 1 ? t - 1 : 0] : 0.0;
-            double Yp;
-            if (t == OFF) Yp = bot ? Y0 : (t == 0 ? 0.0 : Y[t > 0 ? t - 1 : 0]);
-            else Yp = (t == 0) ? 0.0 : Y[t > 0 ? t - 1 : 0];
-            info_slot(sc_tag, t, X[t], Xn, Ua, U[t], Un, Y[t], Yp, hy_m, A);
-        }
-        info_finish(sc_tag, A);
-    };
-    // phase 1: the iterations are over, the six factor arrays are free.  X, U, Y go to three of them (the other three receive
-    // 1 / D and 1 / E for the epilogue, requested asynchronously before this is called) and the slots are walked by a real loop.
-#define DX_(t) sl[((SD::A_L1X) * T + (t)) * 32]
-#define DU_(t) sl[((SD::A_L2X) * T + (t)) * 32]
-#define DY_(t) sl[((SD::A_DIX) * T + (t)) * 32]
-#define DIX_(t) sl[((SD::A_L1U) * T + (t)) * 32]
-#define DIU_(t) sl[((SD::A_L2U) * T + (t)) * 32]
-#define DIE_(t) sl[((SD::A_DIU) * T + (t)) * 32]
+    // X, U, Y go to three arrays of the dump area (the other three receive 1 / D and 1 / E for the epilogue, requested
+    // asynchronously before this is called) and the slots are walked by a real loop.
+    constexpr int oD = PHASE2 ? SD::oDump2 : SD::oDump1;
+#define DX_(t) sl[oD + (0 * T + (t)) * 32]
+#define DU_(t) sl[oD + (1 * T + (t)) * 32]
+#define DY_(t) sl[oD + (2 * T + (t)) * 32]
+#define DIX_(t) sl[oD + (3 * T + (t)) * 32]
+#define DIU_(t) sl[oD + (4 * T + (t)) * 32]
+#define DIE_(t) sl[oD + (5 * T + (t)) * 32]
     auto update_info_rolled = [&](auto sc_tag) {
         InfoAcc A;
         const double Xpart = sx16(X[T - 1]);
@@ -776,6 +764,28 @@ __global__ void __launch_bounds__(32 * WC_SPLIT_WARPS, WC_SPLIT_MINB / WC_SPLIT_
             rho_updates++;
         }
     };
+    // 1 / D and 1 / E of the lane's slots for the epilogue, by cp.async (no register is involved) into the dump area: phase 1 asks
+    // for them when its iterations are over, phase 2 at once
+    auto request_scalings = [&]() {
+        const unsigned s_dix = (unsigned)__cvta_generic_to_shared(&DIX_(0));
+        const unsigned s_diu = (unsigned)__cvta_generic_to_shared(&DIU_(0));
+        const unsigned s_die = (unsigned)__cvta_generic_to_shared(&DIE_(0));
+        const double* gx = d.Dinv + xrow0_;
+        const double* gu = d.Dinv + urow0_;
+        const double* ge = d.Einv + erow0_;
+        const ptrdiff_t sBv = sB_;
+        if (!skip) {
+#pragma unroll 1
+            for (int t = 0; t < T; t++) {
+                if ((t >= OFF) || !bot) {
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s_dix + t * 256), "l"(gx + t * sBv) : "memory");
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s_diu + t * 256), "l"(gu + t * sBv) : "memory");
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s_die + t * 256), "l"(ge + t * sBv) : "memory");
+                }
+            }
+        }
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+    };
     if constexpr (!PHASE2) {
         // ---- phase 1 is ONE pass of osqp_solve's loop, written straight: factor, phase1_len iterations, one update_info, the
         // checks that fall on that iteration.  Everything after the iterations walks the slots with real loops over a copy of the
@@ -801,27 +811,7 @@ __global__ void __launch_bounds__(32 * WC_SPLIT_WARPS, WC_SPLIT_MINB / WC_SPLIT_
         const bool check_now = chk && run == chk;
         const bool adapt_now = adaptive && run == rint;
         const bool at_max = iter >= max_iter;
-        // 1 / D and 1 / E of the lane's slots for the epilogue: asked for now (no register is involved), used after the checks
-        {
-            const unsigned s_dix = (unsigned)__cvta_generic_to_shared(&DIX_(0));
-            const unsigned s_diu = (unsigned)__cvta_generic_to_shared(&DIU_(0));
-            const unsigned s_die = (unsigned)__cvta_generic_to_shared(&DIE_(0));
-            const double* gx = d.Dinv + xrow0_;
-            const double* gu = d.Dinv + urow0_;
-            const double* ge = d.Einv + erow0_;
-            const ptrdiff_t sBv = sB_;
-            if (!skip) {
-#pragma unroll 1
-                for (int t = 0; t < T; t++) {
-                    if ((t >= OFF) || !bot) {
-                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s_dix + t * 256), "l"(gx + t * sBv) : "memory");
-                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s_diu + t * 256), "l"(gu + t * sBv) : "memory");
-                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s_die + t * 256), "l"(ge + t * sBv) : "memory");
-                    }
-                }
-            }
-            asm volatile("cp.async.commit_group;\n" ::: "memory");
-        }
+        request_scalings();
         if (adapt_now) update_info_rolled(std::true_type{}); else update_info_rolled(std::false_type{});
 #pragma unroll 1
         for (int approx = 0; approx < 2; approx++) {
@@ -839,6 +829,7 @@ __global__ void __launch_bounds__(32 * WC_SPLIT_WARPS, WC_SPLIT_MINB / WC_SPLIT_
         asm volatile("cp.async.wait_all;\n" ::: "memory");
         }
     } else {
+    request_scalings();
     bool refactor = true;
     bool warp_busy = __any_sync(FULL, !done);
     // every rare block below has ONE call site (update_info, check_termination, build_factor are large once inlined:
@@ -867,7 +858,7 @@ __global__ void __launch_bounds__(32 * WC_SPLIT_WARPS, WC_SPLIT_MINB / WC_SPLIT_
         if (adaptive) { to_adapt -= run; if (to_adapt == 0) { adapt_now = true; to_adapt = rint; } }
         const bool at_max = iter >= max_iter;
         // ---- termination / adaptive rho (instance-uniform decisions, warp-uniform control flow)
-        if (adapt_now) update_info(std::true_type{}); else update_info(std::false_type{});
+        if (adapt_now) update_info_rolled(std::true_type{}); else update_info_rolled(std::false_type{});
 #pragma unroll 1
         for (int approx = 0; approx < 2; approx++) {
             if (approx == 0) {
@@ -884,6 +875,7 @@ __global__ void __launch_bounds__(32 * WC_SPLIT_WARPS, WC_SPLIT_MINB / WC_SPLIT_
         if (adapt_now) refactor = true;
         warp_busy = __any_sync(FULL, !done);
     }
+    asm volatile("cp.async.wait_all;\n" ::: "memory");
     }
     __syncwarp();
 
@@ -893,7 +885,7 @@ __global__ void __launch_bounds__(32 * WC_SPLIT_WARPS, WC_SPLIT_MINB / WC_SPLIT_
                            status == WC_OSQP_DUAL_INFEASIBLE || status == WC_OSQP_DUAL_INFEASIBLE_INACCURATE ||
                            status == WC_OSQP_UNSOLVED || status == WC_OSQP_NON_CVX) || unfinished;
     if (!skip) { // back to OSQP's scaled workspace
-        if constexpr (!PHASE2) { // from the copy of the iterate and the scaling factors in shared memory (see update_info_rolled)
+        { // from the copy of the iterate and the scaling factors in shared memory (update_info_rolled, request_scalings)
             double* px = d.x + xrow0_;
             double* pu = d.x + urow0_;
             double* pe = d.yeq + erow0_;
@@ -907,20 +899,6 @@ __global__ void __launch_bounds__(32 * WC_SPLIT_WARPS, WC_SPLIT_MINB / WC_SPLIT_
                     if (!shadow) {
                         pu[t * sBv] = has_sol ? DU_(t) * DIU_(t) : 0.0;
                         pe[t * sBv] = has_sol ? DY_(t) * DIE_(t) : 0.0;
-                    }
-                }
-            }
-        } else {
-#pragma unroll
-            for (int t = 0; t < T; t++) {
-                const bool real = (t >= OFF) || !bot;
-                const bool shadow = bot && t == T - 1;
-                if (real) {
-                    const ptrdiff_t xr = xrow0_ + t * sB_, ur = urow0_ + t * sB_, er = erow0_ + t * sB_;
-                    d.x[xr] = has_sol ? X[t] * __ldg(d.Dinv + (xr)) : 0.0;
-                    if (!shadow) {
-                        d.x[ur] = has_sol ? U[t] * __ldg(d.Dinv + (ur)) : 0.0;
-                        d.yeq[er] = has_sol ? Y[t] * __ldg(d.Einv + (er)) : 0.0;
                     }
                 }
             }
@@ -1032,18 +1010,19 @@ template <int NT>
 static cudaError_t launch_split_t(const MpcDev& d, const MpcTickIO& io, cudaStream_t s, cudaEvent_t* mid)
 {
     constexpr size_t smem = (size_t)SplitDims<NT>::total * sizeof(double) * WC_SPLIT_WARPS;
+    constexpr size_t smem2 = (size_t)SplitDims<NT>::total2 * sizeof(double) * WC_SPLIT_WARPS;
     auto k1 = mpc_split_kernel<false, NT>;
     auto k2 = mpc_split_kernel<true, NT>;
     cudaError_t e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
     if (e != cudaSuccess) return e;
     const int blocks = ((d.B + 7) / 8 + WC_SPLIT_WARPS - 1) / WC_SPLIT_WARPS;
     if (mid) cudaEventRecord(mid[0], s); // per-kernel timing (wc_mpc_enable_profiling)
     k1<<<blocks, 32 * WC_SPLIT_WARPS, smem, s>>>(d, io);
     if (mid) cudaEventRecord(mid[1], s);
     const int cap = (WC_SPLIT_MINB / WC_SPLIT_WARPS) * 148;
-    k2<<<blocks < cap ? blocks : cap, 32 * WC_SPLIT_WARPS, smem, s>>>(d, io); // grid-stride over the continuation list
+    k2<<<blocks < cap ? blocks : cap, 32 * WC_SPLIT_WARPS, smem2, s>>>(d, io); // grid-stride over the continuation list
     return cudaGetLastError();
 }
 
