@@ -186,7 +186,16 @@ __global__ void __launch_bounds__(32 * WC_SPLIT_WARPS, WC_SPLIT_MINB / WC_SPLIT_
     const double cqu0 = c * (-(Ra * upa));           // c q of u_0 (MPCSolver.cpp:244-245: G u_prev, first block only)
     const double dcm_a = io.dcm[(size_t)a * B + i];
 
-    // ------------------------------------------------------------------ stage in: raw HBM -> registers / constants
+    // ------------------------------------------------------------------ stage in: raw HBM -> shared memory -> constants / registers
+    // Three passes, the first two real loops: (1) cp.async of the nine raw values per slot straight into shared memory (no
+    // register is involved, so all 9 T requests of a lane are in flight together: one exposed HBM round trip); (2) in place, the
+    // constants of the iteration (sigma D^-2, c q, E^2) and the unscaled warm start; (3) the warm start into registers.
+    //   raw value  ->  array            raw value  ->  array
+    //   1/D (x)        A_SX             D (x)          A_L1X   (then X = D x)
+    //   1/D (u)        A_SU             x (x part)     A_L2X
+    //   gradient       A_CQ             D (u)          A_DIX   (then U = D u)
+    //   E              A_EE             x (u part)     A_L1U
+    //                                   y              A_L2U   (then Y = E y)
     double X[T], U[T], Y[T], tX[T], tU[T];
     {
         const int kx0 = bot ? -OFF : N;              // x index of slot 0; +1 / -1 per slot
@@ -196,22 +205,58 @@ __global__ void __launch_bounds__(32 * WC_SPLIT_WARPS, WC_SPLIT_MINB / WC_SPLIT_
         const ptrdiff_t erow0 = ((ptrdiff_t)(a * nR + kx0 + (bot ? 1 : 0))) * (ptrdiff_t)B + i;
         int gs = head + kx0; gs = gs >= nR ? gs - nR : (gs < 0 ? gs + nR : gs); // ring slot of stage kx0
         const int gstep = bot ? 1 : -1;
-#pragma unroll
+        const unsigned s0 = (unsigned)__cvta_generic_to_shared(sl);
+        constexpr unsigned kArr = (unsigned)T * 256u; // bytes between arrays
+        const double* gDx = d.D + xrow0;
+        const double* gDix = d.Dinv + xrow0;
+        const double* gDu = d.D + urow0;
+        const double* gDiu = d.Dinv + urow0;
+        const double* gE = d.Eeq + erow0;
+        const double* gX = d.x + xrow0;
+        const double* gU = d.x + urow0;
+        const double* gY = d.yeq + erow0;
+        const double* gG = d.grad + ((size_t)(a * nR) * B + i);
+#define WC_CPA8(dst, src) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(dst), "l"(src) : "memory")
+#pragma unroll 1
+        for (int t = 0; t < T; t++) {
+            const bool real = (t >= OFF) || !bot;
+            const unsigned st = s0 + (unsigned)t * 256u;
+            const ptrdiff_t o = t * sB;
+            if (real) {
+                WC_CPA8(st + SD::A_SX * kArr, gDix + o);
+                WC_CPA8(st + SD::A_SU * kArr, gDiu + o);
+                WC_CPA8(st + SD::A_CQ * kArr, gG + (size_t)gs * B);
+                WC_CPA8(st + SD::A_EE * kArr, gE + o);
+                WC_CPA8(st + SD::A_L1X * kArr, gDx + o);
+                WC_CPA8(st + SD::A_DIX * kArr, gDu + o);
+                if (!cold) {
+                    WC_CPA8(st + SD::A_L2X * kArr, gX + o);
+                    WC_CPA8(st + SD::A_L1U * kArr, gU + o);
+                    WC_CPA8(st + SD::A_L2U * kArr, gY + o);
+                }
+            }
+            gs += gstep; gs = gs >= nR ? gs - nR : (gs < 0 ? gs + nR : gs);
+        }
+#undef WC_CPA8
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+        asm volatile("cp.async.wait_all;\n" ::: "memory");
+#pragma unroll 1
         for (int t = 0; t < T; t++) {
             const bool real = (t >= OFF) || !bot;
             double dx = 0, dix = 0, du = 0, diu = 0, e = 0, g = 0, xb = 0, ub = 0, yb = 0;
             if (real) {
-                const ptrdiff_t xr = xrow0 + t * sB, ur = urow0 + t * sB, er = erow0 + t * sB;
-                dx = __ldg(d.D + (xr)); dix = __ldg(d.Dinv + (xr)); du = __ldg(d.D + (ur)); diu = __ldg(d.Dinv + (ur)); e = __ldg(d.Eeq + (er));
-                g = __ldg(d.grad + ((size_t)(a * nR + gs) * B + i));
-                if (!cold) { xb = d.x[xr]; ub = d.x[ur]; yb = d.yeq[er]; }
+                dix = S_(A_SX, t); diu = S_(A_SU, t); g = S_(A_CQ, t); e = S_(A_EE, t); dx = S_(A_L1X, t); du = S_(A_DIX, t);
+                if (!cold) { xb = S_(A_L2X, t); ub = S_(A_L1U, t); yb = S_(A_L2U, t); }
             }
-            gs += gstep; gs = gs >= nR ? gs - nR : (gs < 0 ? gs + nR : gs);
             S_(A_SX, t) = sigma * (dix * dix);
             S_(A_SU, t) = sigma * (diu * diu);
             S_(A_CQ, t) = c * g;
             S_(A_EE, t) = e * e;
-            X[t] = dx * xb; U[t] = du * ub; Y[t] = e * yb;
+            S_(A_L1X, t) = dx * xb; S_(A_DIX, t) = du * ub; S_(A_L2U, t) = e * yb;
+        }
+#pragma unroll
+        for (int t = 0; t < T; t++) {
+            X[t] = S_(A_L1X, t); U[t] = S_(A_DIX, t); Y[t] = S_(A_L2U, t);
             tX[t] = 0.0; tU[t] = 0.0;
         }
     }
