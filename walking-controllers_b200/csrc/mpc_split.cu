@@ -171,42 +171,28 @@ __global__ void __launch_bounds__(32 * WC_SPLIT_WARPS, WC_SPLIT_MINB / WC_SPLIT_
     const int li = grp * 8 + s8;
     const bool valid = li < count;
     const int i = PHASE2 ? d.cont_list[valid ? li : count - 1] : (valid ? li : d.B - 1);
-    const int kflags = d.tick_flags[i];
-    const bool skip = !valid || (kflags & (WC_MPC_FLAG_NO_CONTACT | WC_MPC_FLAG_NO_SOLVER)) != 0;
-    const int nh = skip ? 0 : d.nhull[i];
-    const double Qa = d.Qd[(size_t)a * B + i], Ra = d.Rd[(size_t)a * B + i];
-    const int init_state = d.inited[i];
-    const bool cold = !PHASE2 && !skip && init_state == 2; // new OSQP workspace: x = y = z = 0
-    const double c = d.cscale[i];
-    double rho = d.rho[i];
-    const double upa = d.uprev[(size_t)a * B + i];
-    const int head = mpc_ring_head(d);
-    const double cQ = c * Qa, cR = c * Ra;
-    const double cinv = 1.0 / c;
-    const double cqu0 = c * (-(Ra * upa));           // c q of u_0 (MPCSolver.cpp:244-245: G u_prev, first block only)
-    const double dcm_a = io.dcm[(size_t)a * B + i];
-
     // ------------------------------------------------------------------ stage in: raw HBM -> shared memory -> constants / registers
-    // Three passes, the first two real loops: (1) cp.async of the nine raw values per slot straight into shared memory (no
-    // register is involved, so all 9 T requests of a lane are in flight together: one exposed HBM round trip); (2) in place, the
-    // constants of the iteration (sigma D^-2, c q, E^2) and the unscaled warm start; (3) the warm start into registers.
+    // Everything a group needs from HBM is REQUESTED before anything is waited for (five single-warp CTAs per SM: an exposed
+    // round trip is paid in full): (1a) cp.async of eight raw values per slot straight into shared memory (no register is
+    // involved, so all requests of a lane are in flight together); the scalars of the instance; (1b) the gradient ring, whose
+    // rows depend on the ring head; the hull rows and equality row 0; then ONE wait; (2) in place, by a real loop, the constants
+    // of the iteration (sigma D^-2, c q, E^2) and the unscaled warm start; (3) the warm start into registers.
     //   raw value  ->  array            raw value  ->  array
     //   1/D (x)        A_SX             D (x)          A_L1X   (then X = D x)
     //   1/D (u)        A_SU             x (x part)     A_L2X
     //   gradient       A_CQ             D (u)          A_DIX   (then U = D u)
     //   E              A_EE             x (u part)     A_L1U
     //                                   y              A_L2U   (then Y = E y)
-    double X[T], U[T], Y[T], tX[T], tU[T];
+    // A new OSQP workspace (cold: x = y = z = 0) is applied in pass 2, so that no request depends on a loaded flag.
+#define WC_CPA8(dst, src) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(dst), "l"(src) : "memory")
+    const unsigned s0 = (unsigned)__cvta_generic_to_shared(sl);
+    constexpr unsigned kArr = (unsigned)T * 256u;    // bytes between arrays
     {
         const int kx0 = bot ? -OFF : N;              // x index of slot 0; +1 / -1 per slot
         const ptrdiff_t sB = bot ? (ptrdiff_t)B : -(ptrdiff_t)B;
         const ptrdiff_t xrow0 = ((ptrdiff_t)(a * nA + kx0)) * (ptrdiff_t)B + i;
         const ptrdiff_t urow0 = ((ptrdiff_t)(a * nA + nR + kx0 - (bot ? 0 : 1))) * (ptrdiff_t)B + i;
         const ptrdiff_t erow0 = ((ptrdiff_t)(a * nR + kx0 + (bot ? 1 : 0))) * (ptrdiff_t)B + i;
-        int gs = head + kx0; gs = gs >= nR ? gs - nR : (gs < 0 ? gs + nR : gs); // ring slot of stage kx0
-        const int gstep = bot ? 1 : -1;
-        const unsigned s0 = (unsigned)__cvta_generic_to_shared(sl);
-        constexpr unsigned kArr = (unsigned)T * 256u; // bytes between arrays
         const double* gDx = d.D + xrow0;
         const double* gDix = d.Dinv + xrow0;
         const double* gDu = d.D + urow0;
@@ -215,31 +201,67 @@ __global__ void __launch_bounds__(32 * WC_SPLIT_WARPS, WC_SPLIT_MINB / WC_SPLIT_
         const double* gX = d.x + xrow0;
         const double* gU = d.x + urow0;
         const double* gY = d.yeq + erow0;
-        const double* gG = d.grad + ((size_t)(a * nR) * B + i);
-#define WC_CPA8(dst, src) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(dst), "l"(src) : "memory")
 #pragma unroll 1
         for (int t = 0; t < T; t++) {
-            const bool real = (t >= OFF) || !bot;
             const unsigned st = s0 + (unsigned)t * 256u;
             const ptrdiff_t o = t * sB;
-            if (real) {
+            if ((t >= OFF) || !bot) {
                 WC_CPA8(st + SD::A_SX * kArr, gDix + o);
                 WC_CPA8(st + SD::A_SU * kArr, gDiu + o);
-                WC_CPA8(st + SD::A_CQ * kArr, gG + (size_t)gs * B);
                 WC_CPA8(st + SD::A_EE * kArr, gE + o);
                 WC_CPA8(st + SD::A_L1X * kArr, gDx + o);
                 WC_CPA8(st + SD::A_DIX * kArr, gDu + o);
-                if (!cold) {
-                    WC_CPA8(st + SD::A_L2X * kArr, gX + o);
-                    WC_CPA8(st + SD::A_L1U * kArr, gU + o);
-                    WC_CPA8(st + SD::A_L2U * kArr, gY + o);
-                }
+                WC_CPA8(st + SD::A_L2X * kArr, gX + o);
+                WC_CPA8(st + SD::A_L1U * kArr, gU + o);
+                WC_CPA8(st + SD::A_L2U * kArr, gY + o);
             }
+        }
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+    }
+    const int kflags = d.tick_flags[i];
+    const int nh_l = d.nhull[i];
+    const double Qa = d.Qd[(size_t)a * B + i], Ra = d.Rd[(size_t)a * B + i];
+    const int init_state = d.inited[i];
+    const double c = d.cscale[i];
+    double rho = d.rho[i];
+    const double upa = d.uprev[(size_t)a * B + i];
+    const int head = mpc_ring_head(d);
+    const double dcm_a = io.dcm[(size_t)a * B + i];
+    // equality row 0 (bottom lanes) and the hull rows q4, q4 + 4: raw values
+    const double E0_l = __ldg(d.Eeq + ((size_t)(a * nR) * B + i));
+    const double Y0_l = d.yeq[(size_t)(a * nR) * B + i];
+    const double z0_l = PHASE2 ? 0.0 : d.z0[(size_t)a * B + i];
+    const double Ei0_l = PHASE2 ? 0.0 : __ldg(d.Einv + ((size_t)(a * nR) * B + i));
+    double he_l[2], hx_l[2], hy_l[2], hb_l[2], zh_l[2], yh_l[2];
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        const int h = q4 + 4 * r;
+        he_l[r] = __ldg(d.Eh + ((size_t)h * B + i));
+        hx_l[r] = __ldg(d.hullA + ((size_t)(2 * h) * B + i)); hy_l[r] = __ldg(d.hullA + ((size_t)(2 * h + 1) * B + i));
+        hb_l[r] = __ldg(d.hullb + ((size_t)h * B + i));
+        zh_l[r] = d.zh[(size_t)h * B + i]; yh_l[r] = d.yh[(size_t)h * B + i];
+    }
+    { // (1b) the gradient ring
+        int gs = head + (bot ? -OFF : N); gs = gs >= nR ? gs - nR : (gs < 0 ? gs + nR : gs); // ring slot of slot 0's stage
+        const int gstep = bot ? 1 : -1;
+        const double* gG = d.grad + ((size_t)(a * nR) * B + i);
+#pragma unroll 1
+        for (int t = 0; t < T; t++) {
+            if ((t >= OFF) || !bot) WC_CPA8(s0 + (unsigned)t * 256u + SD::A_CQ * kArr, gG + (size_t)gs * B);
             gs += gstep; gs = gs >= nR ? gs - nR : (gs < 0 ? gs + nR : gs);
         }
-#undef WC_CPA8
         asm volatile("cp.async.commit_group;\n" ::: "memory");
-        asm volatile("cp.async.wait_all;\n" ::: "memory");
+    }
+#undef WC_CPA8
+    const bool skip = !valid || (kflags & (WC_MPC_FLAG_NO_CONTACT | WC_MPC_FLAG_NO_SOLVER)) != 0;
+    const int nh = skip ? 0 : nh_l;
+    const bool cold = !PHASE2 && !skip && init_state == 2; // new OSQP workspace: x = y = z = 0
+    const double cQ = c * Qa, cR = c * Ra;
+    const double cinv = 1.0 / c;
+    const double cqu0 = c * (-(Ra * upa));           // c q of u_0 (MPCSolver.cpp:244-245: G u_prev, first block only)
+    asm volatile("cp.async.wait_all;\n" ::: "memory");
+    double X[T], U[T], Y[T], tX[T], tU[T];
+    {
 #pragma unroll 1
         for (int t = 0; t < T; t++) {
             const bool real = (t >= OFF) || !bot;
@@ -263,10 +285,10 @@ __global__ void __launch_bounds__(32 * WC_SPLIT_WARPS, WC_SPLIT_MINB / WC_SPLIT_
     // bottom lanes: equality row 0 (l = u = -dcm, MPCSolver.cpp:143-146) and its unscaled z
     double EE0 = 0.0, Y0 = 0.0, Z0 = 0.0, E0 = 1.0;
     if (bot) {
-        E0 = __ldg(d.Eeq + ((size_t)(a * nR) * B + i));
+        E0 = E0_l;
         EE0 = E0 * E0;
-        if (!cold) Y0 = E0 * d.yeq[(size_t)(a * nR) * B + i];
-        Z0 = PHASE2 ? -dcm_a : (cold ? 0.0 : d.z0[(size_t)a * B + i] * __ldg(d.Einv + ((size_t)(a * nR) * B + i)));
+        if (!cold) Y0 = E0 * Y0_l;
+        Z0 = PHASE2 ? -dcm_a : (cold ? 0.0 : z0_l * Ei0_l);
     }
     // hull rows q4 and q4 + 4 of the instance: constants to shared memory, (z, y) in registers (scaled, as OSQP keeps them)
     double zh[2], yh[2], dyh[2] = {0.0, 0.0};
@@ -274,17 +296,15 @@ __global__ void __launch_bounds__(32 * WC_SPLIT_WARPS, WC_SPLIT_MINB / WC_SPLIT_
     for (int r = 0; r < 2; r++) {
         const int h = q4 + 4 * r;
         const bool on = h < nh;
-        const double e = __ldg(d.Eh + ((size_t)h * B + i));
-        const double hx = __ldg(d.hullA + ((size_t)(2 * h) * B + i)), hy = __ldg(d.hullA + ((size_t)(2 * h + 1) * B + i));
-        const double hb = __ldg(d.hullb + ((size_t)h * B + i));
+        const double e = he_l[r], hx = hx_l[r], hy = hy_l[r], hb = hb_l[r];
         HC_(H_HXS, h) = on ? e * hx : 0.0;
         HC_(H_HYS, h) = on ? e * hy : 0.0;
         HC_(H_LO, h) = on ? e * (-infty) : -1.0;
         HC_(H_UP, h) = on ? e * hb : 1.0;
         HC_(H_EH, h) = on ? e : 1.0;
         HC_(H_EHI, h) = on ? 1.0 / e : 1.0;
-        zh[r] = (on && !cold) ? d.zh[(size_t)h * B + i] : 0.0;
-        yh[r] = (on && !cold) ? d.yh[(size_t)h * B + i] : 0.0;
+        zh[r] = (on && !cold) ? zh_l[r] : 0.0;
+        yh[r] = (on && !cold) ? yh_l[r] : 0.0;
     }
     __syncwarp();
 
