@@ -76,9 +76,10 @@ def test_sass_of_the_shipped_library(wc):
     names = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
     fn = [l.split("Function : ")[1].strip() for l in names.splitlines() if "Function : " in l]
     tpi = [f for f in fn if "ik_tpi_kernel" in f]
-    split = [f for f in fn if "mpc_split_kernelILb0ELi25E" in f]
+    split = [f for f in fn if "mpc_split_kernelILi0ELi25E" in f]
     assert len(tpi) == 1 and len(split) == 1
     sass = subprocess.run(["cuobjdump", "-sass", "-fun", tpi[0], so], capture_output=True, text=True).stdout
     assert "UBLKCP" in sass and "SYNCS" in sass and "DFMA" in sass
     sass = subprocess.run(["cuobjdump", "-sass", "-fun", split[0], so], capture_output=True, text=True).stdout
     assert sass.count("DFMA") > 1000 and "HMMA" not in sass and "UTCMMA" not in sass
+    assert "LDGSTS" in sass  # the stage-in and the epilogue's scaling factors travel by cp.async

@@ -306,7 +306,8 @@ __global__ void __launch_bounds__(kSetupWarps * 32) mpc_chain_setup_kernel(MpcDe
     extern __shared__ double smem_all[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int count = *d.setup_count;
-    for (int e = blockIdx.x * kSetupWarps + warp; e < count; e += gridDim.x * kSetupWarps) { // whole warps
+    const int cta_warps = blockDim.x >> 5;
+    for (int e = blockIdx.x * cta_warps + warp; e < count; e += gridDim.x * cta_warps) { // whole warps
     const int i = d.setup_list[e];
     const size_t B = (size_t)d.B;
     const int N = d.N, nA = 2 * N + 1, nR = N + 1;
@@ -1232,11 +1233,15 @@ static cudaError_t launch_chain_t(const MpcDev& d, const MpcTickIO& io, cudaStre
 cudaError_t launch_mpc_chain_setup(const MpcDev& d, cudaStream_t s, bool factor)
 {
     const size_t td = mpc_chain_setup_warp_doubles(d.N);
-    const size_t smem_setup = td * kSetupWarps * sizeof(double);
-    cudaError_t e = cudaFuncSetAttribute(mpc_chain_setup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_setup);
+    // next to the split-chain phase 1 (d.setup_overlap) single-warp CTAs: 3.5 KB of shared memory each at N = 25, which fits beside
+    // the five 42 KB CTAs of that kernel on an SM instead of taking the place of one
+    const int warps = d.setup_overlap ? 1 : kSetupWarps;
+    const size_t smem_setup = td * warps * sizeof(double);
+    cudaError_t e = cudaFuncSetAttribute(mpc_chain_setup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(td * kSetupWarps * sizeof(double)));
     if (e != cudaSuccess) return e;
-    const int need = (d.B + kSetupWarps - 1) / kSetupWarps;
-    mpc_chain_setup_kernel<<<need < 4 * 148 ? need : 4 * 148, kSetupWarps * 32, smem_setup, s>>>(d, (int)td, factor ? 1 : 0); // grid-stride over setup_list
+    const int need = (d.B + warps - 1) / warps;
+    const int cap = 4 * 148 * (kSetupWarps / warps);
+    mpc_chain_setup_kernel<<<need < cap ? need : cap, warps * 32, smem_setup, s>>>(d, (int)td, factor ? 1 : 0); // grid-stride over setup_list
     return cudaGetLastError();
 }
 

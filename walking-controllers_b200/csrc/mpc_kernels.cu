@@ -115,7 +115,10 @@ __global__ void __launch_bounds__(128) mpc_prepare_kernel(MpcDev d, MpcTickIO io
     }
     if (!d.have_solver[i]) { d.tick_flags[i] = flags | WC_MPC_FLAG_NO_SOLVER; return; }
     const bool inited = d.inited[i] != 0;
-    if (!inited && d.setup_list) d.setup_list[atomicAdd(d.setup_count, 1)] = i; // osqp_setup pending
+    if (!inited && d.setup_list) { // osqp_setup pending
+        d.setup_list[atomicAdd(d.setup_count, 1)] = i;
+        if (d.setup_overlap) flags |= kMpcFlagSetupPending;
+    }
     const bool reset = io.reset ? (io.reset[i] != 0) : false;
     const double Q[2] = {d.Qd[i], d.Qd[B + i]};
     const int head = mpc_ring_head(d);

@@ -87,6 +87,8 @@ struct MpcDev {
     double* CF;          // [10][B]   dense 4x4 corner factor
     int32_t* setup_list; // [B] instances whose OSQP workspace must be set up this tick (filled by K1)
     int32_t* setup_count;// [1]
+    int setup_overlap;   // split-chain path: osqp_setup of the listed instances and their phase 1 run on a side stream next to the phase 1
+                         // of everyone else; K1 marks the listed instances with kMpcFlagSetupPending in tick_flags
     int32_t* cont_list;  // [B] instances that did not stop at the first termination check
     int32_t* cont_count; // [1]
     // device-side ring of the DCM reference window (wc_mpc_tick_ring_*): sample k of this tick's window in slot
@@ -102,6 +104,9 @@ __device__ __forceinline__ int mpc_ring_head(const MpcDev& d)
 {
     return d.tick_dev ? (int)((unsigned)(*d.tick_dev) % (unsigned)(d.N + 1)) : d.ring_head;
 }
+
+// internal bit of tick_flags (never reaches the caller): the instance is on this tick's setup_list
+constexpr int kMpcFlagSetupPending = 1 << 30;
 
 struct MpcTickIO {
     const double* lf_H; const double* rf_H;
@@ -166,6 +171,8 @@ cudaError_t launch_mpc_chain(const MpcDev& d, const MpcTickIO& io, cudaStream_t 
 cudaError_t launch_mpc_chain_setup(const MpcDev& d, cudaStream_t s, bool factor);
 // split-chain path (mpc_split.cu): four lanes per instance, iterate in registers; compile-time horizons
 bool mpc_split_supported(int N);
-cudaError_t launch_mpc_split(const MpcDev& d, const MpcTickIO& io, cudaStream_t s, cudaEvent_t* mid);
+// side / ev_fork / ev_join: stream and events for the overlapped set-up (d.setup_overlap); nullptr = everything on s
+cudaError_t launch_mpc_split(const MpcDev& d, const MpcTickIO& io, cudaStream_t s, cudaEvent_t* mid, cudaStream_t side = nullptr,
+                             cudaEvent_t ev_fork = nullptr, cudaEvent_t ev_join = nullptr);
 
 } // namespace wcb

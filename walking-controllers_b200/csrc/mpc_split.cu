@@ -34,6 +34,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <type_traits>
 
 namespace wcb {
@@ -132,9 +133,17 @@ struct Ldl6 {
 //        PHASE2 == true : the instances of the continuation list, until osqp_solve returns.
 // One warp per CTA, 8 instances per warp: lane = half * 16 + axis * 8 + instance slot.
 // =====================================================================================
-template <bool PHASE2, int NT>
+// MODE 0: phase 1 of all instances (with d.setup_overlap: except those on this tick's setup_list), 1: phase 2,
+//      2: phase 1 of the instances on the setup_list (side stream, after their osqp_setup)
+template <int MODE, int NT>
 __global__ void __launch_bounds__(32 * WC_SPLIT_WARPS, WC_SPLIT_MINB / WC_SPLIT_WARPS) mpc_split_kernel(MpcDev d, MpcTickIO io)
 {
+    constexpr bool PHASE2 = MODE == 1, LISTED = MODE == 2;
+    // MODE 2 runs NEXT TO the MODE 0 launch, whose CTAs have read the workspace rows of listed instances (and of their neighbours
+    // in the same 32-byte sector) before the set-up kernel rewrote them: an SM's L1 can still hold those lines, and no kernel
+    // boundary separates the two launches on that SM.  Everything the set-up kernel writes (D, 1/D, E, 1/E, c, rho, inited) is
+    // therefore read through L2 here (ld.global.cg; cp.async.cg only moves 16 bytes, so the stage-in is synchronous in this mode).
+    auto ldc = [](const double* p) -> double { return LISTED ? __ldcg(p) : __ldg(p); };
     using SD = SplitDims<NT>;
     constexpr int N = NT, T = SD::T, OFF = SD::OFF, nA = 2 * N + 1, nR = N + 1;
     static_assert(N >= 4, "the split needs a separator away from u_0 / u_1");
@@ -156,8 +165,9 @@ __global__ void __launch_bounds__(32 * WC_SPLIT_WARPS, WC_SPLIT_MINB / WC_SPLIT_
 #define LBX_(t) sb[(t) * 16]
 #define LBU_(t) sb[(T + (t)) * 16]
 #define HC_(arr, h) sh[((SD::arr) * 8 + (h)) * 8]
-    if (!PHASE2 && blockIdx.x == 0 && threadIdx.x == 0) *d.setup_count = 0; // consumed by the setup kernel of this tick
-    const int count = PHASE2 ? *d.cont_count : d.B;
+    // setup_count is consumed by the setup kernel of this tick (and by the MODE 2 launch): cleared by the last kernel of the tick
+    if ((d.setup_overlap ? PHASE2 : MODE == 0) && blockIdx.x == 0 && threadIdx.x == 0) *d.setup_count = 0;
+    const int count = PHASE2 ? *d.cont_count : (LISTED ? *d.setup_count : d.B);
     const int ngroups = (count + 7) / 8;
     const wc_osqp_settings& st = d.st;
     const double sigma = st.sigma, alpha = st.alpha, infty = st.infty;
@@ -170,7 +180,7 @@ __global__ void __launch_bounds__(32 * WC_SPLIT_WARPS, WC_SPLIT_MINB / WC_SPLIT_
     for (int grp = blockIdx.x * WC_SPLIT_WARPS + (threadIdx.x >> 5); grp < ngroups; grp += gridDim.x * WC_SPLIT_WARPS) {
     const int li = grp * 8 + s8;
     const bool valid = li < count;
-    const int i = PHASE2 ? d.cont_list[valid ? li : count - 1] : (valid ? li : d.B - 1);
+    const int i = PHASE2 ? d.cont_list[valid ? li : count - 1] : (LISTED ? d.setup_list[valid ? li : count - 1] : (valid ? li : d.B - 1));
     // ------------------------------------------------------------------ stage in: raw HBM -> shared memory -> constants / registers
     // Everything a group needs from HBM is REQUESTED before anything is waited for (five single-warp CTAs per SM: an exposed
     // round trip is paid in full): (1a) cp.async of eight raw values per slot straight into shared memory (no register is
@@ -184,7 +194,15 @@ __global__ void __launch_bounds__(32 * WC_SPLIT_WARPS, WC_SPLIT_MINB / WC_SPLIT_
     //   E              A_EE             x (u part)     A_L1U
     //                                   y              A_L2U   (then Y = E y)
     // A new OSQP workspace (cold: x = y = z = 0) is applied in pass 2, so that no request depends on a loaded flag.
-#define WC_CPA8(dst, src) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(dst), "l"(src) : "memory")
+#define WC_CPA8(dst, src)                                                                                              \
+    do {                                                                                                               \
+        if (LISTED) {                                                                                                  \
+            const double v_ = __ldcg(src);                                                                             \
+            asm volatile("st.shared.f64 [%0], %1;\n" ::"r"(dst), "d"(v_) : "memory");                                  \
+        } else {                                                                                                       \
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(dst), "l"(src) : "memory");                \
+        }                                                                                                              \
+    } while (0)
     const unsigned s0 = (unsigned)__cvta_generic_to_shared(sl);
     constexpr unsigned kArr = (unsigned)T * 256u;    // bytes between arrays
     {
@@ -201,7 +219,7 @@ __global__ void __launch_bounds__(32 * WC_SPLIT_WARPS, WC_SPLIT_MINB / WC_SPLIT_
         const double* gX = d.x + xrow0;
         const double* gU = d.x + urow0;
         const double* gY = d.yeq + erow0;
-#pragma unroll 1
+#pragma unroll(LISTED ? T : 1)
         for (int t = 0; t < T; t++) {
             const unsigned st = s0 + (unsigned)t * 256u;
             const ptrdiff_t o = t * sB;
@@ -218,25 +236,27 @@ __global__ void __launch_bounds__(32 * WC_SPLIT_WARPS, WC_SPLIT_MINB / WC_SPLIT_
         }
         asm volatile("cp.async.commit_group;\n" ::: "memory");
     }
-    const int kflags = d.tick_flags[i];
+    const int kflags_l = d.tick_flags[i];
+    const bool pending = MODE == 0 && (kflags_l & kMpcFlagSetupPending) != 0; // not this launch's instance
+    const int kflags = kflags_l & ~kMpcFlagSetupPending;
     const int nh_l = d.nhull[i];
     const double Qa = d.Qd[(size_t)a * B + i], Ra = d.Rd[(size_t)a * B + i];
-    const int init_state = d.inited[i];
-    const double c = d.cscale[i];
-    double rho = d.rho[i];
+    const int init_state = LISTED ? __ldcg(d.inited + i) : d.inited[i];
+    const double c = LISTED ? __ldcg(d.cscale + i) : d.cscale[i];
+    double rho = LISTED ? __ldcg(d.rho + i) : d.rho[i];
     const double upa = d.uprev[(size_t)a * B + i];
     const int head = mpc_ring_head(d);
     const double dcm_a = io.dcm[(size_t)a * B + i];
     // equality row 0 (bottom lanes) and the hull rows q4, q4 + 4: raw values
-    const double E0_l = __ldg(d.Eeq + ((size_t)(a * nR) * B + i));
+    const double E0_l = ldc(d.Eeq + ((size_t)(a * nR) * B + i));
     const double Y0_l = d.yeq[(size_t)(a * nR) * B + i];
     const double z0_l = PHASE2 ? 0.0 : d.z0[(size_t)a * B + i];
-    const double Ei0_l = PHASE2 ? 0.0 : __ldg(d.Einv + ((size_t)(a * nR) * B + i));
+    const double Ei0_l = PHASE2 ? 0.0 : ldc(d.Einv + ((size_t)(a * nR) * B + i));
     double he_l[2], hx_l[2], hy_l[2], hb_l[2], zh_l[2], yh_l[2];
 #pragma unroll
     for (int r = 0; r < 2; r++) {
         const int h = q4 + 4 * r;
-        he_l[r] = __ldg(d.Eh + ((size_t)h * B + i));
+        he_l[r] = ldc(d.Eh + ((size_t)h * B + i));
         hx_l[r] = __ldg(d.hullA + ((size_t)(2 * h) * B + i)); hy_l[r] = __ldg(d.hullA + ((size_t)(2 * h + 1) * B + i));
         hb_l[r] = __ldg(d.hullb + ((size_t)h * B + i));
         zh_l[r] = d.zh[(size_t)h * B + i]; yh_l[r] = d.yh[(size_t)h * B + i];
@@ -253,7 +273,7 @@ __global__ void __launch_bounds__(32 * WC_SPLIT_WARPS, WC_SPLIT_MINB / WC_SPLIT_
         asm volatile("cp.async.commit_group;\n" ::: "memory");
     }
 #undef WC_CPA8
-    const bool skip = !valid || (kflags & (WC_MPC_FLAG_NO_CONTACT | WC_MPC_FLAG_NO_SOLVER)) != 0;
+    const bool skip = !valid || pending || (kflags & (WC_MPC_FLAG_NO_CONTACT | WC_MPC_FLAG_NO_SOLVER)) != 0;
     const int nh = skip ? 0 : nh_l;
     const bool cold = !PHASE2 && !skip && init_state == 2; // new OSQP workspace: x = y = z = 0
     const double cQ = c * Qa, cR = c * Ra;
@@ -586,7 +606,7 @@ __global__ void __launch_bounds__(32 * WC_SPLIT_WARPS, WC_SPLIT_MINB / WC_SPLIT_
         const bool real = (t >= OFF) || !bot;
         const bool shadow = bot && t == T - 1;       // the bottom lane's copy of (u_{s-1}, row s): counted by the top lane
         double Dx = 1.0, Du = 1.0, Ek = 1.0;
-        if (SC) { if (real) { Dx = __ldg(d.D + (xrow0_ + t * sB_)); Du = __ldg(d.D + (urow0_ + t * sB_)); Ek = __ldg(d.Eeq + (erow0_ + t * sB_)); } }
+        if (SC) { if (real) { Dx = ldc(d.D + (xrow0_ + t * sB_)); Du = ldc(d.D + (urow0_ + t * sB_)); Ek = ldc(d.Eeq + (erow0_ + t * sB_)); } }
         if (real) { // equality row of the slot: z = l = u = 0
             const double ax = fma(b_, Ut, cx0 * Xt + cx1 * Xn);
             A.rp_u = amax(A.rp_u, ax); A.ax_u = amax(A.ax_u, ax);
@@ -843,9 +863,13 @@ __global__ void __launch_bounds__(32 * WC_SPLIT_WARPS, WC_SPLIT_MINB / WC_SPLIT_
 #pragma unroll 1
             for (int t = 0; t < T; t++) {
                 if ((t >= OFF) || !bot) {
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s_dix + t * 256), "l"(gx + t * sBv) : "memory");
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s_diu + t * 256), "l"(gu + t * sBv) : "memory");
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s_die + t * 256), "l"(ge + t * sBv) : "memory");
+                    if (LISTED) { // through L2 (see ldc)
+                        DIX_(t) = __ldcg(gx + t * sBv); DIU_(t) = __ldcg(gu + t * sBv); DIE_(t) = __ldcg(ge + t * sBv);
+                    } else {
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s_dix + t * 256), "l"(gx + t * sBv) : "memory");
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s_diu + t * 256), "l"(gu + t * sBv) : "memory");
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s_die + t * 256), "l"(ge + t * sBv) : "memory");
+                    }
                 }
             }
         }
@@ -969,7 +993,7 @@ __global__ void __launch_bounds__(32 * WC_SPLIT_WARPS, WC_SPLIT_MINB / WC_SPLIT_
             }
         }
         if (bot) {
-            d.yeq[(size_t)(a * nR) * B + i] = has_sol ? Y0 * __ldg(d.Einv + ((size_t)(a * nR) * B + i)) : 0.0;
+            d.yeq[(size_t)(a * nR) * B + i] = has_sol ? Y0 * ldc(d.Einv + ((size_t)(a * nR) * B + i)) : 0.0;
             d.z0[(size_t)a * B + i] = has_sol ? Z0 * E0 : 0.0;
         }
 #pragma unroll
@@ -1000,7 +1024,7 @@ __global__ void __launch_bounds__(32 * WC_SPLIT_WARPS, WC_SPLIT_MINB / WC_SPLIT_
     }
     vmax = inst_max(vmax);
     outside = (int)inst_max((double)outside);
-    if (lane < 8 && valid) {
+    if (lane < 8 && valid && !pending) {
         if (unfinished) {
             const int idx = atomicAdd(d.cont_count, 1);
             d.cont_list[idx] = i;
@@ -1045,7 +1069,9 @@ __global__ void __launch_bounds__(32 * WC_SPLIT_WARPS, WC_SPLIT_MINB / WC_SPLIT_
             if (io.status) io.status[i] = skip ? WC_OSQP_UNSOLVED : status;
             if (io.iters) io.iters[i] = skip ? 0 : iter_done;
             if (io.flags) io.flags[i] = flags;
-            d.tick_flags[i] = flags;
+            // MODE 2 leaves the marker in place: a MODE 0 CTA that has not started yet must still see the instance as not its own
+            // (K1 rewrites tick_flags on the next tick, phase 2 strips the bit)
+            d.tick_flags[i] = LISTED ? (flags | kMpcFlagSetupPending) : flags;
         }
     }
     __syncwarp(); // the next group of this CTA reuses the shared-memory working set
@@ -1072,34 +1098,65 @@ __global__ void __launch_bounds__(32 * WC_SPLIT_WARPS, WC_SPLIT_MINB / WC_SPLIT_
 
 // ------------------------------------------------------------------------------------------------
 template <int NT>
-static cudaError_t launch_split_t(const MpcDev& d, const MpcTickIO& io, cudaStream_t s, cudaEvent_t* mid)
+static cudaError_t launch_split_t(const MpcDev& d, const MpcTickIO& io, cudaStream_t s, cudaEvent_t* mid, cudaStream_t side,
+                                  cudaEvent_t ev_fork, cudaEvent_t ev_join)
 {
     constexpr size_t smem = (size_t)SplitDims<NT>::total * sizeof(double) * WC_SPLIT_WARPS;
     constexpr size_t smem2 = (size_t)SplitDims<NT>::total2 * sizeof(double) * WC_SPLIT_WARPS;
-    auto k1 = mpc_split_kernel<false, NT>;
-    auto k2 = mpc_split_kernel<true, NT>;
+    auto k1 = mpc_split_kernel<0, NT>;
+    auto k2 = mpc_split_kernel<1, NT>;
+    auto k1l = mpc_split_kernel<2, NT>;
     cudaError_t e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k1l, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
     const int blocks = ((d.B + 7) / 8 + WC_SPLIT_WARPS - 1) / WC_SPLIT_WARPS;
-    if (mid) cudaEventRecord(mid[0], s); // per-kernel timing (wc_mpc_enable_profiling)
-    k1<<<blocks, 32 * WC_SPLIT_WARPS, smem, s>>>(d, io);
-    if (mid) cudaEventRecord(mid[1], s);
     const int cap = (WC_SPLIT_MINB / WC_SPLIT_WARPS) * 148;
+    static const bool dbg = std::getenv("WC_MPC_SIDE_DEBUG") != nullptr; // prints when the side stream's kernels end (ms after the fork)
+    static cudaEvent_t dbe[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    if (dbg && !dbe[0]) for (auto& x : dbe) cudaEventCreate(&x);
+    if (d.setup_overlap) {
+        // osqp_setup of the listed instances (~2 % per tick in a walking gait) and their phase 1 on the side stream, next to the
+        // phase 1 of everyone else; both join before phase 2
+        if ((e = cudaEventRecord(ev_fork, s)) != cudaSuccess) return e;
+        if ((e = cudaStreamWaitEvent(side, ev_fork, 0)) != cudaSuccess) return e;
+        if (dbg) cudaEventRecord(dbe[0], side);
+        if ((e = launch_mpc_chain_setup(d, side, false)) != cudaSuccess) return e;
+        if (dbg) cudaEventRecord(dbe[1], side);
+        k1l<<<blocks < cap ? blocks : cap, 32 * WC_SPLIT_WARPS, smem, side>>>(d, io); // grid-stride over the setup list
+        if (dbg) cudaEventRecord(dbe[2], side);
+        if ((e = cudaEventRecord(ev_join, side)) != cudaSuccess) return e;
+    } else {
+        if ((e = launch_mpc_chain_setup(d, s, false)) != cudaSuccess) return e;
+    }
+    if (mid) cudaEventRecord(mid[0], s); // per-kernel timing (wc_mpc_enable_profiling)
+    if (dbg && d.setup_overlap) cudaEventRecord(dbe[3], s);
+    k1<<<blocks, 32 * WC_SPLIT_WARPS, smem, s>>>(d, io);
+    if (dbg && d.setup_overlap) {
+        cudaEventRecord(dbe[4], s);
+        cudaDeviceSynchronize();
+        float a = 0, b = 0, c = 0, f = 0;
+        cudaEventElapsedTime(&a, dbe[0], dbe[1]); cudaEventElapsedTime(&b, dbe[0], dbe[2]);
+        cudaEventElapsedTime(&c, dbe[0], dbe[3]); cudaEventElapsedTime(&f, dbe[0], dbe[4]);
+        std::fprintf(stderr, "[side] setup ends %.3f ms, listed phase 1 ends %.3f ms; main phase 1 starts %.3f, ends %.3f ms after the fork\n", a, b, c, f);
+    }
+    if (d.setup_overlap && (e = cudaStreamWaitEvent(s, ev_join, 0)) != cudaSuccess) return e;
+    if (mid) cudaEventRecord(mid[1], s);
     k2<<<blocks < cap ? blocks : cap, 32 * WC_SPLIT_WARPS, smem2, s>>>(d, io); // grid-stride over the continuation list
     return cudaGetLastError();
 }
 
 bool mpc_split_supported(int N) { return N == 25 || N == 10; }
 
-cudaError_t launch_mpc_split(const MpcDev& d, const MpcTickIO& io, cudaStream_t s, cudaEvent_t* mid)
+cudaError_t launch_mpc_split(const MpcDev& d, const MpcTickIO& io, cudaStream_t s, cudaEvent_t* mid, cudaStream_t side, cudaEvent_t ev_fork,
+                             cudaEvent_t ev_join)
 {
-    cudaError_t e = launch_mpc_chain_setup(d, s, false);
-    if (e != cudaSuccess) return e;
+    if (d.setup_overlap && (!side || !ev_fork || !ev_join)) return cudaErrorInvalidValue;
     switch (d.N) {
-    case 25: return launch_split_t<25>(d, io, s, mid);
-    case 10: return launch_split_t<10>(d, io, s, mid);
+    case 25: return launch_split_t<25>(d, io, s, mid, side, ev_fork, ev_join);
+    case 10: return launch_split_t<10>(d, io, s, mid, side, ev_fork, ev_join);
     default: return cudaErrorInvalidConfiguration;
     }
 }
