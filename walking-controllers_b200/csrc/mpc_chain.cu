@@ -354,8 +354,8 @@ __global__ void __launch_bounds__(kSetupWarps * 32) mpc_chain_setup_kernel(MpcDe
                     const double du = DU[k];
                     const double sc = (k < N - 1) ? 2.0 : 1.0;
                     double nu = fabs(c * sc * R[a] * du * du);
-                    if (k >= 1) nu = fmax(nu, fabs(c * R[a] * du * DU[k - 1]));
-                    if (k < N - 1) nu = fmax(nu, fabs(c * R[a] * du * DU[k + 1]));
+                    if (k >= 1) nu = amax(nu, c * R[a] * du * DU[k - 1]);
+                    if (k < N - 1) nu = amax(nu, c * R[a] * du * DU[k + 1]);
                     nu = fmax(nu, bd * Ea[k + 1] * du);
                     if (k == 0) {
                         const double* Hc = (a == 0) ? HX : HY;
@@ -388,15 +388,15 @@ __global__ void __launch_bounds__(kSetupWarps * 32) mpc_chain_setup_kernel(MpcDe
                 const double* DX = DD + a * nA; const double* DU = DX + nR;
                 const double dx = DX[k];
                 sum += fabs(c * Q[a] * dx * dx);
-                qn = fmax(qn, fabs(c * dx * QB[a * nA + k]));
+                qn = amax(qn, c * dx * QB[a * nA + k]);
                 if (k < N) {
                     const double du = DU[k];
                     const double sc = (k < N - 1) ? 2.0 : 1.0;
                     double nu = fabs(c * sc * R[a] * du * du);
-                    if (k >= 1) nu = fmax(nu, fabs(c * R[a] * du * DU[k - 1]));
-                    if (k < N - 1) nu = fmax(nu, fabs(c * R[a] * du * DU[k + 1]));
+                    if (k >= 1) nu = amax(nu, c * R[a] * du * DU[k - 1]);
+                    if (k < N - 1) nu = amax(nu, c * R[a] * du * DU[k + 1]);
                     sum += nu;
-                    qn = fmax(qn, fabs(c * du * QB[a * nA + nR + k]));
+                    qn = amax(qn, c * du * QB[a * nA + nR + k]);
                 }
             }
         }
@@ -705,9 +705,9 @@ __global__ void __launch_bounds__(2 * IPW) mpc_chain_kernel(MpcDev d, MpcTickIO 
             const double z = (k == 0) ? lb0 : 0.0;
             const double einv = EIv(k);
             const double r = ax - z;
-            if (SC) m_rp_s = fmax(m_rp_s, fabs(r)); m_rp_u = fmax(m_rp_u, fabs(einv * r));
-            if (SC) m_z_s = fmax(m_z_s, fabs(z)); m_z_u = fmax(m_z_u, fabs(einv * z));
-            if (SC) m_ax_s = fmax(m_ax_s, fabs(ax)); m_ax_u = fmax(m_ax_u, fabs(einv * ax));
+            if (SC) m_rp_s = amax(m_rp_s, r); m_rp_u = amax(m_rp_u, einv * r);
+            if (SC) m_z_s = amax(m_z_s, z); m_z_u = amax(m_z_u, einv * z);
+            if (SC) m_ax_s = amax(m_ax_s, ax); m_ax_u = amax(m_ax_u, einv * ax);
             const double yk = A_(YE, k);
             const double yk1 = (k < N) ? A_(YE, k + 1) : 0.0;
             {
@@ -716,10 +716,10 @@ __global__ void __launch_bounds__(2 * IPW) mpc_chain_kernel(MpcDev d, MpcTickIO 
                 const double aty_x = cm * yk + (k < N ? A_(CA, k + 1) * yk1 : 0.0);
                 const double q = A_(QX, k), dinv = DIXv(k);
                 const double rr = q + px_x + aty_x;
-                if (SC) m_rd_s = fmax(m_rd_s, fabs(rr)); m_rd_u = fmax(m_rd_u, fabs(dinv * rr));
-                if (SC) m_q_s = fmax(m_q_s, fabs(q)); m_q_u = fmax(m_q_u, fabs(dinv * q));
-                if (SC) m_aty_s = fmax(m_aty_s, fabs(aty_x)); m_aty_u = fmax(m_aty_u, fabs(dinv * aty_x));
-                if (SC) m_px_s = fmax(m_px_s, fabs(px_x)); m_px_u = fmax(m_px_u, fabs(dinv * px_x));
+                if (SC) m_rd_s = amax(m_rd_s, rr); m_rd_u = amax(m_rd_u, dinv * rr);
+                if (SC) m_q_s = amax(m_q_s, q); m_q_u = amax(m_q_u, dinv * q);
+                if (SC) m_aty_s = amax(m_aty_s, aty_x); m_aty_u = amax(m_aty_u, dinv * aty_x);
+                if (SC) m_px_s = amax(m_px_s, px_x); m_px_u = amax(m_px_u, dinv * px_x);
             }
             if (k < N) {
                 const double du_p1 = (k < N - 1) ? DUv(k + 1) : 0.0;
@@ -733,10 +733,10 @@ __global__ void __launch_bounds__(2 * IPW) mpc_chain_kernel(MpcDev d, MpcTickIO 
                 if (k == 0) aty_u += aty_hull(nullptr, false);
                 const double q = (k == 0) ? qu0 : 0.0, dinv = DIUv(k);
                 const double rr = q + px_u + aty_u;
-                if (SC) m_rd_s = fmax(m_rd_s, fabs(rr)); m_rd_u = fmax(m_rd_u, fabs(dinv * rr));
-                if (SC) m_q_s = fmax(m_q_s, fabs(q)); m_q_u = fmax(m_q_u, fabs(dinv * q));
-                if (SC) m_aty_s = fmax(m_aty_s, fabs(aty_u)); m_aty_u = fmax(m_aty_u, fabs(dinv * aty_u));
-                if (SC) m_px_s = fmax(m_px_s, fabs(px_u)); m_px_u = fmax(m_px_u, fabs(dinv * px_u));
+                if (SC) m_rd_s = amax(m_rd_s, rr); m_rd_u = amax(m_rd_u, dinv * rr);
+                if (SC) m_q_s = amax(m_q_s, q); m_q_u = amax(m_q_u, dinv * q);
+                if (SC) m_aty_s = amax(m_aty_s, aty_u); m_aty_u = amax(m_aty_u, dinv * aty_u);
+                if (SC) m_px_s = amax(m_px_s, px_u); m_px_u = amax(m_px_u, dinv * px_u);
                 xu_prev = vu_k;
                 du_m1 = du_k; vu_m1 = vu_k; du_k = du_p1; vu_k = vu_p1;
             }
@@ -752,9 +752,9 @@ __global__ void __launch_bounds__(2 * IPW) mpc_chain_kernel(MpcDev d, MpcTickIO 
                 const double z = H_(H_ZH, h);
                 const double einv = 1.0 / H_(H_EH, h); // = Ehinv of osqp_setup
                 const double r = ax - z;
-                if (SC) m_rp_s = fmax(m_rp_s, fabs(r)); m_rp_u = fmax(m_rp_u, fabs(einv * r));
-                if (SC) m_z_s = fmax(m_z_s, fabs(z)); m_z_u = fmax(m_z_u, fabs(einv * z));
-                if (SC) m_ax_s = fmax(m_ax_s, fabs(ax)); m_ax_u = fmax(m_ax_u, fabs(einv * ax));
+                if (SC) m_rp_s = amax(m_rp_s, r); m_rp_u = amax(m_rp_u, einv * r);
+                if (SC) m_z_s = amax(m_z_s, z); m_z_u = amax(m_z_u, einv * z);
+                if (SC) m_ax_s = amax(m_ax_s, ax); m_ax_u = amax(m_ax_u, einv * ax);
             }
         }
         pri_res = pair_max(m_rp_u, pmask, IPW); if (SC) rp_s = pair_max(m_rp_s, pmask, IPW);
@@ -772,7 +772,7 @@ __global__ void __launch_bounds__(2 * IPW) mpc_chain_kernel(MpcDev d, MpcTickIO 
         double nrm = 0.0, lhs = 0.0;
         for (int k = 0; k < nR; k++) {
             const double dy = dyg[(size_t)k * B];
-            nrm = fmax(nrm, fabs(Eg[(size_t)k * B] * dy));
+            nrm = amax(nrm, Eg[(size_t)k * B] * dy);
             const double bnd = (k == 0) ? lb0 : 0.0;
             lhs += bnd * fmax(dy, 0.0) + bnd * fmin(dy, 0.0);
         }
@@ -786,7 +786,7 @@ __global__ void __launch_bounds__(2 * IPW) mpc_chain_kernel(MpcDev d, MpcTickIO 
                 if (u_inf) dy = l_inf ? 0.0 : fmin(dy, 0.0);
                 else if (l_inf) dy = fmax(dy, 0.0);
                 dyhg[(size_t)h * B] = dy;
-                nrm = fmax(nrm, fabs(e * dy));
+                nrm = amax(nrm, e * dy);
                 lhs += uh * fmax(dy, 0.0) + lh * fmin(dy, 0.0);
             }
         }
@@ -804,11 +804,11 @@ __global__ void __launch_bounds__(2 * IPW) mpc_chain_kernel(MpcDev d, MpcTickIO 
                 const double yk = dyg[(size_t)k * B];
                 const double yk1 = (k < N) ? dyg[(size_t)(k + 1) * B] : 0.0;
                 const double aty_x = A_(CM, k) * yk + (k < N ? A_(CA, k + 1) * yk1 : 0.0);
-                m = fmax(m, fabs(aty_x * Dig[(size_t)k * B])); // note: cooperative kernel divides by D
+                m = amax(m, aty_x * Dig[(size_t)k * B]); // note: cooperative kernel divides by D
                 if (k < N) {
                     double aty_u = A_(CB, k + 1) * yk1;
                     if (k == 0) aty_u += aty_hull(dyhg, true);
-                    m = fmax(m, fabs(aty_u * Dig[(size_t)(nR + k) * B]));
+                    m = amax(m, aty_u * Dig[(size_t)(nR + k) * B]);
                 }
             }
             m = pair_max(m, pmask, IPW);
@@ -824,12 +824,12 @@ __global__ void __launch_bounds__(2 * IPW) mpc_chain_kernel(MpcDev d, MpcTickIO 
         double nrm = 0.0, qdx = 0.0;
         for (int k = 0; k < nR; k++) {
             const double wx = A_(WX, k);
-            nrm = fmax(nrm, fabs(Dg[(size_t)k * B] * wx));
+            nrm = amax(nrm, Dg[(size_t)k * B] * wx);
             qdx += A_(QX, k) * wx;
         }
         for (int k = 0; k < N; k++) {
             const double wu = A_(WU, k);
-            nrm = fmax(nrm, fabs(Dg[(size_t)(nR + k) * B] * wu));
+            nrm = amax(nrm, Dg[(size_t)(nR + k) * B] * wu);
             if (k == 0) qdx += qu0 * wu;
         }
         nrm = pair_max(nrm, pmask, IPW);
@@ -843,7 +843,7 @@ __global__ void __launch_bounds__(2 * IPW) mpc_chain_kernel(MpcDev d, MpcTickIO 
             for (int k = 0; k < nR; k++) {
                 const double dx = Dg[(size_t)k * B];
                 const double px_x = cQ * dx * dx * A_(WX, k);
-                m = fmax(m, fabs(px_x * Dig[(size_t)k * B]));
+                m = amax(m, px_x * Dig[(size_t)k * B]);
                 if (k < N) {
                     const double sc = (k < N - 1) ? 2.0 : 1.0;
                     const double du = Dg[(size_t)(nR + k) * B];
@@ -851,7 +851,7 @@ __global__ void __launch_bounds__(2 * IPW) mpc_chain_kernel(MpcDev d, MpcTickIO 
                     if (k >= 1) t -= Dg[(size_t)(nR + k - 1) * B] * A_(WU, k - 1);
                     if (k < N - 1) t -= Dg[(size_t)(nR + k + 1) * B] * A_(WU, k + 1);
                     const double px_u = cR * du * t;
-                    m = fmax(m, fabs(px_u * Dig[(size_t)(nR + k) * B]));
+                    m = amax(m, px_u * Dig[(size_t)(nR + k) * B]);
                 }
             }
             m = pair_max(m, pmask, IPW);

@@ -559,7 +559,7 @@ __global__ void __launch_bounds__(128) mpc_admm_kernel(MpcDev d, MpcTickIO io, i
                     const double* DXo = s.DD + (1 - a) * nA; const double* DUo = DXo + nR; // the other axis
                     const double rnx = (a == 0) ? r01 : r10, rpv = (a == 0) ? r10 : r01;  // P(u_k^a, u_{k+1}^o), P(u_k^a, u_{k-1}^o)
                     double nrm = fabs(c * Q[a] * dx * dx);
-                    if (cpl) nrm = fmax(nrm, fabs(c * qx * dx * DXo[k]));
+                    if (cpl) nrm = amax(nrm, c * qx * dx * DXo[k]);
                     nrm = fmax(nrm, Ea[k] * dx);
                     if (k < N) nrm = fmax(nrm, ad * Ea[k + 1] * dx);
                     s.W[a * nA + k] = 1.0 / sqrt(limit_scaling(nrm));
@@ -567,12 +567,12 @@ __global__ void __launch_bounds__(128) mpc_admm_kernel(MpcDev d, MpcTickIO io, i
                         const double du = DU[k];
                         const double sc = (k < N - 1) ? 2.0 : 1.0;
                         double nu = fabs(c * sc * R[a] * du * du);
-                        if (k >= 1) nu = fmax(nu, fabs(c * R[a] * du * DU[k - 1]));
-                        if (k < N - 1) nu = fmax(nu, fabs(c * R[a] * du * DU[k + 1]));
+                        if (k >= 1) nu = amax(nu, c * R[a] * du * DU[k - 1]);
+                        if (k < N - 1) nu = amax(nu, c * R[a] * du * DU[k + 1]);
                         if (cpl) {
-                            nu = fmax(nu, fabs(c * sc * r01 * du * DUo[k]));
-                            if (k >= 1) nu = fmax(nu, fabs(c * rpv * du * DUo[k - 1]));
-                            if (k < N - 1) nu = fmax(nu, fabs(c * rnx * du * DUo[k + 1]));
+                            nu = amax(nu, c * sc * r01 * du * DUo[k]);
+                            if (k >= 1) nu = amax(nu, c * rpv * du * DUo[k - 1]);
+                            if (k < N - 1) nu = amax(nu, c * rnx * du * DUo[k + 1]);
                         }
                         nu = fmax(nu, bd * Ea[k + 1] * du);
                         if (k == 0) {
@@ -608,20 +608,20 @@ __global__ void __launch_bounds__(128) mpc_admm_kernel(MpcDev d, MpcTickIO io, i
                     const double* DXo = s.DD + (1 - a) * nA; const double* DUo = DXo + nR;
                     const double rnx = (a == 0) ? r01 : r10, rpv = (a == 0) ? r10 : r01;
                     sum += cpl ? fmax(fabs(c * Q[a] * dx * dx), fabs(c * qx * dx * DXo[k])) : fabs(c * Q[a] * dx * dx);
-                    qn = fmax(qn, fabs(c * dx * s.QB[a * nA + k]));
+                    qn = amax(qn, c * dx * s.QB[a * nA + k]);
                     if (k < N) {
                         const double du = DU[k];
                         const double sc = (k < N - 1) ? 2.0 : 1.0;
                         double nu = fabs(c * sc * R[a] * du * du);
-                        if (k >= 1) nu = fmax(nu, fabs(c * R[a] * du * DU[k - 1]));
-                        if (k < N - 1) nu = fmax(nu, fabs(c * R[a] * du * DU[k + 1]));
+                        if (k >= 1) nu = amax(nu, c * R[a] * du * DU[k - 1]);
+                        if (k < N - 1) nu = amax(nu, c * R[a] * du * DU[k + 1]);
                         if (cpl) {
-                            nu = fmax(nu, fabs(c * sc * r01 * du * DUo[k]));
-                            if (k >= 1) nu = fmax(nu, fabs(c * rpv * du * DUo[k - 1]));
-                            if (k < N - 1) nu = fmax(nu, fabs(c * rnx * du * DUo[k + 1]));
+                            nu = amax(nu, c * sc * r01 * du * DUo[k]);
+                            if (k >= 1) nu = amax(nu, c * rpv * du * DUo[k - 1]);
+                            if (k < N - 1) nu = amax(nu, c * rnx * du * DUo[k + 1]);
                         }
                         sum += nu;
-                        qn = fmax(qn, fabs(c * du * s.QB[a * nA + nR + k]));
+                        qn = amax(qn, c * du * s.QB[a * nA + nR + k]);
                     }
                 }
             }
@@ -969,26 +969,26 @@ __global__ void __launch_bounds__(128) mpc_admm_kernel(MpcDev d, MpcTickIO io, i
                 const double z = (k == 0) ? lb0[a] : 0.0;
                 const double einv = 1.0 / s.EE[j];
                 const double r = ax - z;
-                m_rp_s = fmax(m_rp_s, fabs(r)); m_rp_u = fmax(m_rp_u, fabs(einv * r));
-                m_z_s = fmax(m_z_s, fabs(z)); m_z_u = fmax(m_z_u, fabs(einv * z));
-                m_ax_s = fmax(m_ax_s, fabs(ax)); m_ax_u = fmax(m_ax_u, fabs(einv * ax));
+                m_rp_s = amax(m_rp_s, r); m_rp_u = amax(m_rp_u, einv * r);
+                m_z_s = amax(m_z_s, z); m_z_u = amax(m_z_u, einv * z);
+                m_ax_s = amax(m_ax_s, ax); m_ax_u = amax(m_ax_u, einv * ax);
                 double px_x, aty_x, px_u, aty_u;
                 stage_products(a, k, s.X, s.YE, s.YH, px_x, aty_x, px_u, aty_u);
                 {
                     const double q = s.QB[a * nA + k], dinv = 1.0 / s.DD[a * nA + k];
                     const double rr = q + px_x + aty_x;
-                    m_rd_s = fmax(m_rd_s, fabs(rr)); m_rd_u = fmax(m_rd_u, fabs(dinv * rr));
-                    m_q_s = fmax(m_q_s, fabs(q)); m_q_u = fmax(m_q_u, fabs(dinv * q));
-                    m_aty_s = fmax(m_aty_s, fabs(aty_x)); m_aty_u = fmax(m_aty_u, fabs(dinv * aty_x));
-                    m_px_s = fmax(m_px_s, fabs(px_x)); m_px_u = fmax(m_px_u, fabs(dinv * px_x));
+                    m_rd_s = amax(m_rd_s, rr); m_rd_u = amax(m_rd_u, dinv * rr);
+                    m_q_s = amax(m_q_s, q); m_q_u = amax(m_q_u, dinv * q);
+                    m_aty_s = amax(m_aty_s, aty_x); m_aty_u = amax(m_aty_u, dinv * aty_x);
+                    m_px_s = amax(m_px_s, px_x); m_px_u = amax(m_px_u, dinv * px_x);
                 }
                 if (k < N) {
                     const double q = s.QB[a * nA + nR + k], dinv = 1.0 / s.DD[a * nA + nR + k];
                     const double rr = q + px_u + aty_u;
-                    m_rd_s = fmax(m_rd_s, fabs(rr)); m_rd_u = fmax(m_rd_u, fabs(dinv * rr));
-                    m_q_s = fmax(m_q_s, fabs(q)); m_q_u = fmax(m_q_u, fabs(dinv * q));
-                    m_aty_s = fmax(m_aty_s, fabs(aty_u)); m_aty_u = fmax(m_aty_u, fabs(dinv * aty_u));
-                    m_px_s = fmax(m_px_s, fabs(px_u)); m_px_u = fmax(m_px_u, fabs(dinv * px_u));
+                    m_rd_s = amax(m_rd_s, rr); m_rd_u = amax(m_rd_u, dinv * rr);
+                    m_q_s = amax(m_q_s, q); m_q_u = amax(m_q_u, dinv * q);
+                    m_aty_s = amax(m_aty_s, aty_u); m_aty_u = amax(m_aty_u, dinv * aty_u);
+                    m_px_s = amax(m_px_s, px_u); m_px_u = amax(m_px_u, dinv * px_u);
                 }
             }
         }
@@ -997,9 +997,9 @@ __global__ void __launch_bounds__(128) mpc_admm_kernel(MpcDev d, MpcTickIO io, i
             const double z = s.ZH[h];
             const double einv = 1.0 / s.EH[h];
             const double r = ax - z;
-            m_rp_s = fmax(m_rp_s, fabs(r)); m_rp_u = fmax(m_rp_u, fabs(einv * r));
-            m_z_s = fmax(m_z_s, fabs(z)); m_z_u = fmax(m_z_u, fabs(einv * z));
-            m_ax_s = fmax(m_ax_s, fabs(ax)); m_ax_u = fmax(m_ax_u, fabs(einv * ax));
+            m_rp_s = amax(m_rp_s, r); m_rp_u = amax(m_rp_u, einv * r);
+            m_z_s = amax(m_z_s, z); m_z_u = amax(m_z_u, einv * z);
+            m_ax_s = amax(m_ax_s, ax); m_ax_u = amax(m_ax_u, einv * ax);
         }
         const unsigned mk = gmask;
         pri_res = group_max<G>(m_rp_u, mk); rp_s = group_max<G>(m_rp_s, mk);
@@ -1017,7 +1017,7 @@ __global__ void __launch_bounds__(128) mpc_admm_kernel(MpcDev d, MpcTickIO io, i
         double nrm = 0.0, lhs = 0.0;
         for (int j = gl; j < 2 * nR; j += G) {
             const double dy = s.DYE[j];
-            nrm = fmax(nrm, fabs(s.EE[j] * dy));
+            nrm = amax(nrm, s.EE[j] * dy);
             const double bnd = (j == 0) ? lb0[0] : ((j == nR) ? lb0[1] : 0.0);
             lhs += bnd * fmax(dy, 0.0) + bnd * fmin(dy, 0.0);
         }
@@ -1027,7 +1027,7 @@ __global__ void __launch_bounds__(128) mpc_admm_kernel(MpcDev d, MpcTickIO io, i
             if (u_inf) dy = l_inf ? 0.0 : fmin(dy, 0.0);
             else if (l_inf) dy = fmax(dy, 0.0);
             s.DYH[h] = dy;
-            nrm = fmax(nrm, fabs(s.EH[h] * dy));
+            nrm = amax(nrm, s.EH[h] * dy);
             lhs += s.UH[h] * fmax(dy, 0.0) + s.LH[h] * fmin(dy, 0.0);
         }
         nrm = group_max<G>(nrm, gmask);
@@ -1041,8 +1041,8 @@ __global__ void __launch_bounds__(128) mpc_admm_kernel(MpcDev d, MpcTickIO io, i
                 for (int a = 0; a < 2; a++) {
                     double px_x, aty_x, px_u, aty_u;
                     stage_products(a, k, s.X, s.DYE, s.DYH, px_x, aty_x, px_u, aty_u);
-                    m = fmax(m, fabs(aty_x / s.DD[a * nA + k]));
-                    if (k < N) m = fmax(m, fabs(aty_u / s.DD[a * nA + nR + k]));
+                    m = amax(m, aty_x / s.DD[a * nA + k]);
+                    if (k < N) m = amax(m, aty_u / s.DD[a * nA + nR + k]);
                 }
             }
             m = group_max<G>(m, gmask);
@@ -1053,7 +1053,7 @@ __global__ void __launch_bounds__(128) mpc_admm_kernel(MpcDev d, MpcTickIO io, i
     auto dual_infeasible = [&](double eps) -> int {
         double nrm = 0.0, qdx = 0.0;
         for (int j = gl; j < 2 * nA; j += G) {
-            nrm = fmax(nrm, fabs(s.DD[j] * s.W[j]));
+            nrm = amax(nrm, s.DD[j] * s.W[j]);
             qdx += s.QB[j] * s.W[j];
         }
         nrm = group_max<G>(nrm, gmask);
@@ -1066,8 +1066,8 @@ __global__ void __launch_bounds__(128) mpc_admm_kernel(MpcDev d, MpcTickIO io, i
                 for (int a = 0; a < 2; a++) {
                     double px_x, aty_x, px_u, aty_u;
                     stage_products(a, k, s.W, s.YE, s.YH, px_x, aty_x, px_u, aty_u);
-                    m = fmax(m, fabs(px_x / s.DD[a * nA + k]));
-                    if (k < N) m = fmax(m, fabs(px_u / s.DD[a * nA + nR + k]));
+                    m = amax(m, px_x / s.DD[a * nA + k]);
+                    if (k < N) m = amax(m, px_u / s.DD[a * nA + nR + k]);
                 }
             }
             m = group_max<G>(m, gmask);

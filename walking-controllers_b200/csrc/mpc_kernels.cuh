@@ -105,6 +105,10 @@ __device__ __forceinline__ int mpc_ring_head(const MpcDev& d)
     return d.tick_dev ? (int)((unsigned)(*d.tick_dev) % (unsigned)(d.N + 1)) : d.ring_head;
 }
 
+// running infinity norm as OSQP's vec_norm_inf writes it (`if (|v| > max) max = |v|`): one compare and one select, where fmax on
+// doubles is a seven-instruction sequence (there is no fp64 min/max instruction; the rest is NaN handling).  m is never NaN.
+__device__ __forceinline__ double amax(double m, double v) { const double av = fabs(v); return av > m ? av : m; }
+
 // internal bit of tick_flags (never reaches the caller): the instance is on this tick's setup_list
 constexpr int kMpcFlagSetupPending = 1 << 30;
 

@@ -73,9 +73,6 @@ __device__ __forceinline__ double sx16(double v) { return __shfl_xor_sync(FULL, 
 __device__ __forceinline__ double sx8(double v) { return __shfl_xor_sync(FULL, v, 8); }
 // reductions over the four lanes of an instance (lane bits 3 and 4); symmetric, so all four get the same bits
 __device__ __forceinline__ double inst_max(double v) { v = fmax(v, sx8(v)); return fmax(v, sx16(v)); }
-// running infinity norm as OSQP's vec_norm_inf writes it (`if (|v| > max) max = |v|`): one compare and one select, where fmax on
-// doubles is a seven-instruction sequence (there is no fp64 min/max instruction; the rest is NaN handling).  m is never NaN.
-__device__ __forceinline__ double amax(double m, double v) { const double av = fabs(v); return av > m ? av : m; }
 // the same over the four lanes of an instance, for accumulators built by amax (never NaN, never negative: symmetric)
 __device__ __forceinline__ double inst_amax(double v)
 {
