@@ -678,6 +678,23 @@ __global__ void __launch_bounds__(kTpiThreads, WC_TPI_MINB) ik_tpi_kernel(IkDev 
         const int rc2 = tpi_solve<true>(d, io, M, A2, sc2 + (size_t)rows.oJ * B, B, i2, nJ, br, es, left2, pvar, beta, &id3);
         if (rc2 != 0) d.slow_list[atomicAdd(d.slow_count, 1)] = i2; // a second working-set change (or a fallback): general kernel
     }
+#ifdef WC_TPI_DISCARD // measured: 0.203 -> 0.206 ms (the write-backs it saves are not what the kernel waits for); left as a build switch
+    // The scratch of the CTA's instances is dead from here on.  Left alone its lines stay in L2 as dirty data, are written back to
+    // HBM one by one (half of the kernel's DRAM traffic) and crowd out the scratch of the instances still in flight; discarding them
+    // (`discard.global.L2`: the line is dropped, not written back) leaves L2 to the live rows.  Only whole lines that belong to one
+    // warp's instances are discarded: rows are 128-byte aligned when B is a multiple of 16, a full warp's 32 instances are two lines.
+    __syncthreads(); // the second solves of the CTA have read what they need
+    if ((B & 15) == 0) {
+        const size_t i0 = (size_t)blockIdx.x * kTpiThreads + (size_t)warp * 32; // first instance of this warp
+        if (i0 + 32 <= B) {
+            const double* base = d.tpi_scratch + i0;
+            for (int r = lane; r < 2 * rows.total; r += 32) {
+                const double* ln = base + (size_t)(r >> 1) * B + (size_t)(r & 1) * 16;
+                asm volatile("discard.global.L2 [%0], 128;" ::"l"(ln) : "memory");
+            }
+        }
+    }
+#endif
 }
 
 
