@@ -97,9 +97,34 @@ def test_mpc_parity_host_api(wc, syn, oracle, cuda_device):
     run_both(wc, syn, oracle, cuda_device, B=33, T=40, N=25, host_api=True, seed=7)
 
 
-@pytest.mark.parametrize("N", [1, 2, 10, 50, 100, 200])
+@pytest.mark.parametrize("N", [1, 2, 10, 50, 75, 100, 200])
 def test_mpc_parity_horizons(wc, syn, oracle, cuda_device, N):
     run_both(wc, syn, oracle, cuda_device, B=20, T=30, N=N, seed=100 + N)
+
+
+def test_mpc_setup_overlap_option(wc, syn, cuda_device, monkeypatch):
+    """WC_MPC_SETUP_OVERLAP=1 (osqp_setup + phase 1 of the instances with a new workspace on a side stream next to phase 1 of everyone
+    else; measured and left off) must give the bits of the serial launch sequence, on every tick: the first tick
+    sends all 8 192 instances through the side launch (more groups than it has CTAs), the later ones the ~2 % whose support changes."""
+    B, N, T = 8192, 25, 8
+    g = syn.GaitBatch(B, T, N, seed=0xB201, device=cuda_device)
+    traj = g.trajectory()
+    runs = []
+    for ov in ("0", "1"):
+        monkeypatch.setenv("WC_MPC_SETUP_OVERLAP", ov)
+        m = wc.MpcBatch(wc.mpc_default_config(N), B)
+        outs = []
+        for t in range(T):
+            f = g.feet(t)
+            o = m.tick(f["lf_H"], f["rf_H"], f["l_contact"], f["r_contact"], g.measured_dcm(t), traj[2 * t: 2 * t + 2 * (N + 1)])
+            torch.cuda.synchronize()
+            outs.append({k: v.clone() for k, v in o.items()})
+        m.close()
+        runs.append(outs)
+    assert sum(int(((o["flags"] & 16) != 0).sum()) for o in runs[0][1:]) > 0  # later ticks do contain new workspaces
+    for t in range(T):
+        for key in ("zmp", "status", "iters", "flags"):
+            assert torch.equal(runs[0][t][key], runs[1][t][key]), f"tick {t}: {key} differs with the overlapped set-up"
 
 
 def test_mpc_parity_gain_sweep_and_disturbance(wc, syn, oracle, cuda_device):

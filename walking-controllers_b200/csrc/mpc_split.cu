@@ -26,6 +26,13 @@
 // 4. The LDL' factors are rebuilt in the kernel every tick from (D, E, c, rho) -- one ADMM iteration's worth of
 //    work out of 25 -- instead of being kept in HBM: no factor arrays, no extra traffic, and a rho update refactors
 //    in place.
+// 5. Everything outside the iteration loop is written for a small instruction footprint.  With five single-warp CTAs
+//    per SM nothing hides a warp's own latencies, and the once-per-warp code (stage-in, update_info, check_termination,
+//    epilogue), fully unrolled, was half of the kernel's stall samples -- most of them instruction fetches from L2.
+//    Now: raw values travel HBM -> shared memory by cp.async and are turned into constants by a real loop; once the
+//    iterations of a pass are over the iterate is copied to shared memory and update_info / the epilogue walk the
+//    slots with real loops (phase 1 re-uses the dead factor arrays for that, phase 2 has a dump area of its own);
+//    infinity norms are compare + select (OSQP's vec_norm_inf) instead of fmax, a seven-instruction sequence on fp64.
 //
 // Slots.  top lane   t = 0..T-1   <-> (x_k, u_{k-1}), equality row k,   k = N - t;  slot T-1 is the separator
 //         bottom lane t = OFF..T-1 <-> (x_j, u_j),     equality row j+1, j = t - OFF; u_0 (slot OFF) is the border,
@@ -34,7 +41,6 @@
 
 #include <cmath>
 #include <cstdio>
-#include <cstdlib>
 #include <type_traits>
 
 namespace wcb {
@@ -1111,34 +1117,19 @@ static cudaError_t launch_split_t(const MpcDev& d, const MpcTickIO& io, cudaStre
     if (e != cudaSuccess) return e;
     const int blocks = ((d.B + 7) / 8 + WC_SPLIT_WARPS - 1) / WC_SPLIT_WARPS;
     const int cap = (WC_SPLIT_MINB / WC_SPLIT_WARPS) * 148;
-    static const bool dbg = std::getenv("WC_MPC_SIDE_DEBUG") != nullptr; // prints when the side stream's kernels end (ms after the fork)
-    static cudaEvent_t dbe[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-    if (dbg && !dbe[0]) for (auto& x : dbe) cudaEventCreate(&x);
     if (d.setup_overlap) {
         // osqp_setup of the listed instances (~2 % per tick in a walking gait) and their phase 1 on the side stream, next to the
         // phase 1 of everyone else; both join before phase 2
         if ((e = cudaEventRecord(ev_fork, s)) != cudaSuccess) return e;
         if ((e = cudaStreamWaitEvent(side, ev_fork, 0)) != cudaSuccess) return e;
-        if (dbg) cudaEventRecord(dbe[0], side);
         if ((e = launch_mpc_chain_setup(d, side, false)) != cudaSuccess) return e;
-        if (dbg) cudaEventRecord(dbe[1], side);
         k1l<<<blocks < cap ? blocks : cap, 32 * WC_SPLIT_WARPS, smem, side>>>(d, io); // grid-stride over the setup list
-        if (dbg) cudaEventRecord(dbe[2], side);
         if ((e = cudaEventRecord(ev_join, side)) != cudaSuccess) return e;
     } else {
         if ((e = launch_mpc_chain_setup(d, s, false)) != cudaSuccess) return e;
     }
     if (mid) cudaEventRecord(mid[0], s); // per-kernel timing (wc_mpc_enable_profiling)
-    if (dbg && d.setup_overlap) cudaEventRecord(dbe[3], s);
     k1<<<blocks, 32 * WC_SPLIT_WARPS, smem, s>>>(d, io);
-    if (dbg && d.setup_overlap) {
-        cudaEventRecord(dbe[4], s);
-        cudaDeviceSynchronize();
-        float a = 0, b = 0, c = 0, f = 0;
-        cudaEventElapsedTime(&a, dbe[0], dbe[1]); cudaEventElapsedTime(&b, dbe[0], dbe[2]);
-        cudaEventElapsedTime(&c, dbe[0], dbe[3]); cudaEventElapsedTime(&f, dbe[0], dbe[4]);
-        std::fprintf(stderr, "[side] setup ends %.3f ms, listed phase 1 ends %.3f ms; main phase 1 starts %.3f, ends %.3f ms after the fork\n", a, b, c, f);
-    }
     if (d.setup_overlap && (e = cudaStreamWaitEvent(s, ev_join, 0)) != cudaSuccess) return e;
     if (mid) cudaEventRecord(mid[1], s);
     k2<<<blocks < cap ? blocks : cap, 32 * WC_SPLIT_WARPS, smem2, s>>>(d, io); // grid-stride over the continuation list
