@@ -701,8 +701,9 @@ def run_ours(args, world, rank, local_rank):
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": bt["mpc"] * B,
                          "note": "the path is not HBM bound (DESIGN.md §5): ~5 KB of compulsory traffic against ~0.12 Mflop of "
-                                 "fp64 in dependent chains per instance-tick; see roofline_fp64 / smem.  traffic exceeds the "
-                                 "algorithmic bytes by the Ruiz scaling vectors (D, 1/D, E, 1/E), read every tick"},
+                                 "fp64 in dependent chains per instance-tick; the dominant kernel is bound by the shared-memory "
+                                 "data pipe (the `smem` object; ncu: 72 % of its sustained peak), see also roofline_fp64.  traffic "
+                                 "exceeds the algorithmic bytes by the Ruiz scaling vectors (D, 1/D, E, 1/E), read every tick"},
             "roofline_fp64": {"bound": "fp64", "kernel": dom_name, "kernel_ms": dom_ms,
                               "achieved": f_p1 * B / (dom_ms * 1e-3) * 1e-12, "peak": fp64_peak * 1e-3, "unit": "TFLOP/s",
                               "frac": f_p1 * B / (dom_ms * 1e-3) * 1e-9 / fp64_peak,
