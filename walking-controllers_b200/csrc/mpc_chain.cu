@@ -347,8 +347,8 @@ __global__ void __launch_bounds__(kSetupWarps * 32) mpc_chain_setup_kernel(MpcDe
                 const double* DX = DD + a * nA; const double* DU = DX + nR; const double* Ea = EE + a * nR;
                 const double dx = DX[k];
                 double nrm = fabs(c * Q[a] * dx * dx);
-                nrm = fmax(nrm, Ea[k] * dx);
-                if (k < N) nrm = fmax(nrm, ad * Ea[k + 1] * dx);
+                nrm = amax(nrm, Ea[k] * dx);
+                if (k < N) nrm = amax(nrm, ad * Ea[k + 1] * dx);
                 FD[a * nA + k] = 1.0 / sqrt(limit_scaling_c(nrm));
                 if (k < N) {
                     const double du = DU[k];
@@ -356,17 +356,17 @@ __global__ void __launch_bounds__(kSetupWarps * 32) mpc_chain_setup_kernel(MpcDe
                     double nu = fabs(c * sc * R[a] * du * du);
                     if (k >= 1) nu = amax(nu, c * R[a] * du * DU[k - 1]);
                     if (k < N - 1) nu = amax(nu, c * R[a] * du * DU[k + 1]);
-                    nu = fmax(nu, bd * Ea[k + 1] * du);
+                    nu = amax(nu, bd * Ea[k + 1] * du);
                     if (k == 0) {
                         const double* Hc = (a == 0) ? HX : HY;
-                        for (int h = 0; h < nh; h++) nu = fmax(nu, fabs(EH[h] * Hc[h]) * du);
+                        for (int h = 0; h < nh; h++) nu = amax(nu, (EH[h] * Hc[h]) * du); // du > 0: |a| du = |a du|, same bits
                     }
                     FD[a * nA + nR + k] = 1.0 / sqrt(limit_scaling_c(nu));
                 }
                 double nr = Ea[k] * dx;
                 if (k >= 1) {
-                    nr = fmax(nr, ad * Ea[k] * DX[k - 1]);
-                    nr = fmax(nr, bd * Ea[k] * DU[k - 1]);
+                    nr = amax(nr, ad * Ea[k] * DX[k - 1]);
+                    nr = amax(nr, bd * Ea[k] * DU[k - 1]);
                 }
                 FE[a * nR + k] = 1.0 / sqrt(limit_scaling_c(nr));
             }
