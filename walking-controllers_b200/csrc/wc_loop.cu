@@ -38,6 +38,10 @@ struct wc_loop {
     cudaGraphExec_t graph;
     cudaStream_t own;      // capture / replay stream when the caller's stream is the legacy default stream (not capturable)
     cudaEvent_t ev_in, ev_out;
+    // the measured-CoM kinematics (stance base -> FK) depends on the feet and the joint state only: it runs on a side branch next to
+    // the producer's DCM kernels and the latency-bound head of the MPC block (K1, osqp_setup), joined before the ZMP-CoM law
+    cudaStream_t side;
+    cudaEvent_t ev_fork, ev_join;
     bool first;            // the next tick is the first after reset (the MPC rings are re-filled)
 };
 
@@ -94,18 +98,23 @@ wc_status enqueue_tick(wc_loop* h, bool first, cudaStream_t s)
     void* sv = static_cast<void*>(s);
     wc_traj_feet f{h->lf_H, h->rf_H, h->lf_tw, h->rf_tw, h->l_contact, h->r_contact, h->lif, h->com_h, h->com_hv};
     TRY(wc_traj_feet_dev(h->traj, 0, &f, sv));
+    // side branch (also under graph capture: the side stream joins the capture through the event and is joined back below)
+    if (cudaEventRecord(h->ev_fork, s) != cudaSuccess || cudaStreamWaitEvent(h->side, h->ev_fork, 0) != cudaSuccess) return WC_ERR_CUDA;
+    loop_pre_kernel<<<g128, 128, 0, h->side>>>(B, h->lf_H, h->rf_H, h->lif, h->base_H, h->neck_R);
+    // measured CoM: FK about the current (perfectly tracked) posture
+    TRY(wc_fk_dev(h->ik, h->q_des, h->base_H, h->lif, nullptr, nullptr, nullptr, h->com_meas, nullptr, nullptr, nullptr, nullptr,
+                  static_cast<void*>(h->side)));
+    if (cudaEventRecord(h->ev_join, h->side) != cudaSuccess) return WC_ERR_CUDA;
     TRY(wc_traj_dcm_dev(h->traj, 0, N + 1, h->ref_pos, h->ref_vel, sv));
     TRY(wc_traj_measured_dcm_dev(h->traj, 0, h->cfg.dcm_noise_sigma, h->cfg.noise_seed, h->dcm_meas, sv));
     loop_push_kernel<<<g128, 128, 0, s>>>(B, h->tick_dev, h->push_tick, h->push_dxy, h->dcm_meas);
-    loop_pre_kernel<<<g128, 128, 0, s>>>(B, h->lf_H, h->rf_H, h->lif, h->base_H, h->neck_R);
-    // measured CoM: FK about the current (perfectly tracked) posture
-    TRY(wc_fk_dev(h->ik, h->q_des, h->base_H, h->lif, nullptr, nullptr, nullptr, h->com_meas, nullptr, nullptr, nullptr, nullptr, sv));
     // MPC -> desired ZMP
     TRY(wc_mpc_tick_dev(h->mpc, h->lf_H, h->rf_H, h->l_contact, h->r_contact, h->dcm_meas, h->ref_pos, first ? h->reset_all : nullptr,
                         h->zmp, h->osqp_status, h->iters, h->flags, sv));
     // ZMP-CoM controller (consumes the MPC output of THIS tick)
     loop_zmp_meas_kernel<<<(unsigned)((2 * B + 127) / 128), 128, 0, s>>>(B, h->cfg.zmp_meas_offset, h->zmp, h->zmp_meas);
     TRY(wc_glue_set_phase_dev(h->glue, h->ref_vel, nullptr, sv));
+    if (cudaStreamWaitEvent(s, h->ev_join, 0) != cudaSuccess) return WC_ERR_CUDA; // base_H, neck_R, com_meas
     TRY(wc_glue_com_reference_dev(h->glue, h->ref_pos, h->zmp, h->zmp_meas, h->com_meas, h->com_h, h->com_hv, nullptr, nullptr,
                                   h->com_pos_des, h->com_vel_des, sv));
     // FK + QP-IK about the integrated posture (consumes the ZMP-CoM law of THIS tick), then the joint integrator
@@ -142,8 +151,11 @@ wc_status wc_loop_create(wc_mpc* mpc, wc_ik* ik, wc_glue* glue, wc_traj* traj, c
     h->mpc = mpc; h->ik = ik; h->glue = glue; h->traj = traj; h->cfg = *cfg;
     h->B = B; h->N = wc_mpc_horizon(mpc); h->nJ = wc_ik_dofs(ik); h->device = device;
     h->tick = 0; h->launches = 0; h->graph = nullptr; h->first = true;
-    h->own = nullptr; h->ev_in = nullptr; h->ev_out = nullptr;
-    if (cudaStreamCreateWithFlags(&h->own, cudaStreamNonBlocking) != cudaSuccess ||
+    h->own = nullptr; h->ev_in = nullptr; h->ev_out = nullptr; h->side = nullptr; h->ev_fork = nullptr; h->ev_join = nullptr;
+    if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->own, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_out, cudaEventDisableTiming) != cudaSuccess) { delete h; return WC_ERR_CUDA; }
     const size_t Bz = (size_t)B, nJ = (size_t)h->nJ, N = (size_t)h->N;
@@ -183,6 +195,9 @@ void wc_loop_destroy(wc_loop* h)
     wc_traj_set_tick_source_dev(h->traj, nullptr);
     if (h->graph) cudaGraphExecDestroy(h->graph);
     if (h->own) cudaStreamDestroy(h->own);
+    if (h->side) cudaStreamDestroy(h->side);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->ev_in) cudaEventDestroy(h->ev_in);
     if (h->ev_out) cudaEventDestroy(h->ev_out);
     cudaFree(h->buf);
