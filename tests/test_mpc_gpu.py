@@ -148,6 +148,20 @@ def test_mpc_parity_rho_adaptation(wc, syn, oracle, cuda_device):
     assert its.max() > 100
 
 
+@pytest.mark.parametrize("N,settings", [
+    (25, dict(adaptive_rho_interval=25)),                                   # rho estimate at the first termination check
+    (25, dict(adaptive_rho_interval=10, check_termination=5)),              # rho updates between checks, short first pass
+    (25, dict(adaptive_rho_interval=50, check_termination=10, eps_abs=1e-6, eps_rel=1e-6)),
+    (10, dict(adaptive_rho_interval=25, eps_abs=1e-6, eps_rel=1e-6)),
+])
+def test_mpc_parity_rho_interval_and_check_cadence(wc, syn, oracle, cuda_device, N, settings):
+    """adaptive_rho_interval at or below the first termination check puts the scaled-residual part of update_info and adapt_rho into
+    PHASE 1 of the split-chain kernels (the straight pass with the rolled checks); other check cadences change its length"""
+    st = run_both(wc, syn, oracle, cuda_device, B=48, T=16, N=N, seed=21, noise=0.02, settings=settings)
+    its = np.concatenate(st["iters"])
+    print("iteration histogram", np.unique(its, return_counts=True))
+
+
 def test_mpc_max_iter_status(wc, syn, oracle, cuda_device):
     run_both(wc, syn, oracle, cuda_device, B=16, T=6, N=10, seed=9,
              settings=dict(eps_abs=1e-12, eps_rel=1e-12, max_iter=60))
