@@ -323,6 +323,31 @@ wc_status wc_ik_tick_dev(wc_ik* h,
                          const double* com_meas, const double* neck_R_des,
                          double* dq, double* lf_err, double* rf_err,
                          int32_t* qp_status, int32_t* nwsr, void* stream);
+/* The same tick as TWO calls, for a caller that wants the kinematics out of the way before the desired CoM exists.  In
+ * WalkingModule::updateModule the kinematics of the QP-IK is evaluated at the integrated desired posture
+ * (setInternalRobotState(m_qDesired, ...), WalkingModule.cpp:715) and the desired feet / neck come from the trajectory
+ * generator: none of it depends on the MPC output of the tick, only setDesiredCoMPosition / setDesiredCoMVelocity do
+ * (WalkingModule.cpp:660-740).  So
+ *   WC_IK_PART_KINEMATICS  forward kinematics, Jacobian columns of the QP and every task right-hand side except the CoM
+ *                          term (reads q_meas, q_lin, base_H, left_is_fixed, the desired feet / twists / neck; com_* may
+ *                          be NULL); com_out [3*B] or NULL receives the CoM of that posture (what wc_fk_dev returns);
+ *   WC_IK_PART_SOLVE       the CoM term, the QP solves, the outputs (same arguments as wc_ik_tick_dev; the pointers of
+ *                          the kinematics call must still hold the same data)
+ * issued in this order (any streams, ordered by the caller) give bit for bit the result of wc_ik_tick_dev: the kinematics
+ * call can run on another stream next to the MPC block of the same tick.  The split exists for the thread-per-instance
+ * fast path (wc_ik_tick_is_split() == 1: CoM as constraint, qpOASES-based solver); any other configuration does the
+ * whole tick in the SOLVE call and nothing in the KINEMATICS call. */
+enum { WC_IK_PART_KINEMATICS = 1, WC_IK_PART_SOLVE = 2 };
+wc_status wc_ik_tick_part_dev(wc_ik* h, int32_t part,
+                              const double* q_meas, const double* q_lin,
+                              const double* base_H, const uint8_t* left_is_fixed,
+                              const double* lf_H_des, const double* rf_H_des,
+                              const double* lf_twist, const double* rf_twist,
+                              const double* com_pos_des, const double* com_vel_des,
+                              const double* com_meas, const double* neck_R_des, double* com_out,
+                              double* dq, double* lf_err, double* rf_err,
+                              int32_t* qp_status, int32_t* nwsr, void* stream);
+int32_t wc_ik_tick_is_split(const wc_ik* h);
 wc_status wc_ik_tick_host(wc_ik* h,
                           const double* q_meas, const double* q_lin,
                           const double* base_H, const uint8_t* left_is_fixed,

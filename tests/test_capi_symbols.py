@@ -75,7 +75,7 @@ def test_sass_of_the_shipped_library(wc):
     assert "sm_100a" in elfs and "sm_90" not in elfs and "sm_80" not in elfs
     names = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
     fn = [l.split("Function : ")[1].strip() for l in names.splitlines() if "Function : " in l]
-    tpi = [f for f in fn if "ik_tpi_kernel" in f]
+    tpi = [f for f in fn if "ik_tpi_kernelILi0E" in f]  # the whole tick in one launch (ILi1E / ILi2E: its two parts)
     split = [f for f in fn if "mpc_split_kernelILi0ELi25E" in f]
     assert len(tpi) == 1 and len(split) == 1
     sass = subprocess.run(["cuobjdump", "-sass", "-fun", tpi[0], so], capture_output=True, text=True).stdout

@@ -143,6 +143,38 @@ def test_ik_tick_parity(wc, syn, oracle, cuda_device, vmax, perturb):
     ik.close()
 
 
+@pytest.mark.parametrize("vmax,perturb", [(1.0, 1.0), (0.4, 1.0), (0.25, 0.5)])
+def test_ik_tick_as_two_calls(wc, syn, oracle, cuda_device, vmax, perturb, ik_path):
+    """wc_ik_tick_part_dev: the kinematics part (issued without the desired CoM, on another stream) followed by the solve part gives
+    the bits of wc_ik_tick_dev, including the instances that take the second solve and the general kernel; com_out of the
+    kinematics part is the CoM wc_fk_dev returns.  With the general kernel alone there is no split and the solve call does it all."""
+    B = 1500
+    inp = {k: v.to(cuda_device) for k, v in make_inputs(syn, oracle, B, 23, perturb).items()}
+    cfg = wc.ik_default_config()
+    for i in range(23):
+        cfg.min_vel[i] = -vmax; cfg.max_vel[i] = vmax
+    ik = wc.IkBatch(cfg, wc.model_icub_like(), B)
+    assert ik.tick_is_split == (ik_path == "auto")
+    ref = {k: v.clone() for k, v in ik.tick(inp).items()}
+    torch.cuda.synchronize()
+    assert int((ref["nwsr"] > 0).sum()) > 0 or vmax >= 1.0
+    side = torch.cuda.Stream()
+    kin_in = {k: v for k, v in inp.items() if k not in ("com_pos_des", "com_vel_des", "com_meas")}
+    com = torch.full((3, B), float("nan"), dtype=torch.float64, device=cuda_device)
+    with torch.cuda.stream(side):
+        ik.tick_kinematics(kin_in, com_out=com)
+        ev = torch.cuda.Event(); ev.record(side)
+    torch.cuda.current_stream().wait_event(ev)
+    out = ik.tick_solve(inp)
+    torch.cuda.synchronize()
+    for k in ("dq", "lf_err", "rf_err", "status", "nwsr"):
+        assert torch.equal(out[k], ref[k]), k
+    if ik.tick_is_split:
+        fk = ik.fk(inp["q_lin"], inp["base_H"], inp["left_is_fixed"], jacobians=False)
+        assert (com - fk["com"]).abs().max().item() <= 1e-12
+    ik.close()
+
+
 def test_ik_com_in_cost_and_gains(wc, syn, oracle, cuda_device):
     """useCoMAsConstraint = 0 (12 equality rows, CoM task in the cost) and per-instance gains (config 4)."""
     B = 128

@@ -256,6 +256,8 @@ def lib():
         L.wc_ik_dofs.argtypes = [_VP]; L.wc_ik_dofs.restype = i32
         L.wc_ik_set_gains_host.argtypes = [_VP, _VP, _VP]; L.wc_ik_set_gains_host.restype = i32
         L.wc_ik_tick_dev.argtypes = [_VP] + [_VP] * 17 + [_VP]; L.wc_ik_tick_dev.restype = i32
+        L.wc_ik_tick_part_dev.argtypes = [_VP, i32] + [_VP] * 12 + [_VP] + [_VP] * 5 + [_VP]; L.wc_ik_tick_part_dev.restype = i32
+        L.wc_ik_tick_is_split.argtypes = [_VP]; L.wc_ik_tick_is_split.restype = i32
         L.wc_ik_tick_host.argtypes = [_VP] + [_VP] * 17; L.wc_ik_tick_host.restype = i32
         L.wc_ik_tick_host_async.argtypes = [_VP] + [_VP] * 17; L.wc_ik_tick_host_async.restype = i32
         L.wc_ik_sync.argtypes = [_VP]; L.wc_ik_sync.restype = i32
@@ -566,6 +568,45 @@ class IkBatch:
             stream = torch.cuda.current_stream(dev).cuda_stream
         _check(lib().wc_ik_tick_dev(self.h, *self._args(inp, out, "cuda"), stream), "wc_ik_tick_dev")
         return out
+
+    def tick_kinematics(self, inp, com_out=None, stream=None):
+        """first half of tick() (wc_ik_tick_part_dev, WC_IK_PART_KINEMATICS): everything that does not need the desired CoM of the
+        tick -- inp may leave com_pos_des / com_vel_des / com_meas out; com_out [3, B] receives the CoM of the posture"""
+        import torch
+        dev = inp["q_meas"].device
+        if stream is None:
+            stream = torch.cuda.current_stream(dev).cuda_stream
+        B, nJ = self.B, self.nJ
+        rows = dict(q_meas=nJ, q_lin=nJ, base_H=12, lf_H_des=12, rf_H_des=12, lf_twist=6, rf_twist=6, com_pos_des=3,
+                    com_vel_des=3, com_meas=3, neck_R_des=9)
+        a = []
+        for k in IK_INPUT_KEYS:
+            if k in ("com_pos_des", "com_vel_des", "com_meas") and inp.get(k) is None:
+                a.append(None)
+            elif k == "left_is_fixed":
+                a.append(_arg(inp.get(k), "u8", B, "cuda", k))
+            else:
+                a.append(_arg(inp.get(k), "f64", rows[k] * B, "cuda", k))
+        co = _arg(com_out, "f64", 3 * B, "cuda", "com_out") if com_out is not None else None
+        _check(lib().wc_ik_tick_part_dev(self.h, 1, *a, co, None, None, None, None, None, stream), "wc_ik_tick_part_dev")
+        return com_out
+
+    def tick_solve(self, inp, out=None, stream=None):
+        """second half of tick() (WC_IK_PART_SOLVE): the CoM term, the QP solves, the outputs; together with tick_kinematics() on the
+        same inputs it gives the bits of tick()"""
+        import torch
+        dev = inp["q_meas"].device
+        if out is None:
+            out = self._outs(dev)
+        if stream is None:
+            stream = torch.cuda.current_stream(dev).cuda_stream
+        a = self._args(inp, out, "cuda")
+        _check(lib().wc_ik_tick_part_dev(self.h, 2, *a[:12], None, *a[12:], stream), "wc_ik_tick_part_dev")
+        return out
+
+    @property
+    def tick_is_split(self):
+        return bool(lib().wc_ik_tick_is_split(self.h))
 
     def _args(self, inp, out, where):
         B, nJ = self.B, self.nJ

@@ -1217,12 +1217,30 @@ __global__ void __launch_bounds__(kFastWarps * 32, WC_IK_FAST_MINB) ik_fast_kern
 template <int NJ, bool COMC>
 cudaError_t launch_t(const IkDev& d, const IkTickIO& io, int mode, cudaStream_t s, cudaEvent_t mid)
 {
+    if (d.solver == WC_IK_SOLVER_OSQP) { // the OSQP-based variant has no split form: everything happens in the solve call
+        if (mode == IK_MODE_TICK_KIN) return cudaSuccess;
+        if (mode == IK_MODE_TICK_SOLVE) mode = IK_MODE_TICK;
+    }
     if (d.solver == WC_IK_SOLVER_OSQP && mode != IK_MODE_FK_ONLY) return launch_osqp_t<NJ, COMC>(d, io, mode, s);
     using LY = IkLayout<NJ, COMC>;
     const size_t smem = (size_t)LY::TOTAL * sizeof(double) * kWarpsPerBlock;
     cudaError_t e = cudaFuncSetAttribute(ik_kernel<NJ, COMC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int blocks = (d.B + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    // the tick as two calls: with the thread-per-instance fast path the kinematics part is a launch of its own; any other
+    // configuration does the whole tick in the solve call (the kinematics call is then a no-op)
+    const bool split_ok = COMC && d.slow_list && d.tpi_scratch && d.solver != WC_IK_SOLVER_OSQP;
+    if (mode == IK_MODE_TICK_KIN) return split_ok ? launch_ik_tpi(d, io, s, 1) : cudaSuccess;
+    if (mode == IK_MODE_TICK_SOLVE) {
+        if (!split_ok) return launch_t<NJ, COMC>(d, io, IK_MODE_TICK, s, mid);
+        e = cudaMemsetAsync(d.slow_count, 0, 2 * sizeof(int32_t), s);
+        if (e != cudaSuccess) return e;
+        e = launch_ik_tpi(d, io, s, 2);
+        if (e != cudaSuccess) return e;
+        if (mid) cudaEventRecord(mid, s);
+        ik_kernel<NJ, COMC><<<blocks, kWarpsPerBlock * 32, smem, s>>>(d, io, IK_MODE_TICK, 1);
+        return cudaGetLastError();
+    }
     if (COMC && mode == IK_MODE_TICK && d.slow_list && (d.tpi_scratch || NJ == 23)) {
         // fast path for every instance, then the general kernel on the compacted remainder
         e = cudaMemsetAsync(d.slow_count, 0, 2 * sizeof(int32_t), s);

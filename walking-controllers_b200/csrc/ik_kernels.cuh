@@ -87,7 +87,9 @@ struct IkDev {
     int32_t* oflags;         // [B]: bit 0 = solver error (non-convex), bit 1 = isSolutionFeasible failed
 };
 
-enum { IK_MODE_TICK = 0, IK_MODE_FK_ONLY = 1, IK_MODE_EXT_KIN = 2 };
+enum { IK_MODE_TICK = 0, IK_MODE_FK_ONLY = 1, IK_MODE_EXT_KIN = 2,
+       // the tick as two calls (wc_ik_tick_part_dev): what depends on the joint state / base / desired feet only, then the rest
+       IK_MODE_TICK_KIN = 3, IK_MODE_TICK_SOLVE = 4 };
 
 struct IkTickIO {
     // inputs
@@ -109,7 +111,7 @@ cudaError_t launch_ik(const IkDev& d, const IkTickIO& io, int mode, cudaStream_t
 bool ik_supported(int n_dofs);
 // thread-per-instance fast path of the fused tick (ik_tpi.cu)
 int ik_tpi_rows(int n_links, int n_dofs);  // rows of IkDev::tpi_scratch
-cudaError_t launch_ik_tpi(const IkDev& d, const IkTickIO& io, cudaStream_t s);
+cudaError_t launch_ik_tpi(const IkDev& d, const IkTickIO& io, cudaStream_t s, int part = 0); // part: 0 whole tick, 1 kinematics, 2 solve
 cudaError_t launch_ik_tpi_fk(const IkDev& d, const IkTickIO& io, cudaStream_t s); // FK without Jacobians (IkTickIO::o_lf_H, o_rf_H, o_neck_R, o_com)
 
 } // namespace wcb

@@ -51,8 +51,9 @@ struct TpiRows {
         oJ = 0;                 // [nJ][10] link loop: joint axis (3) and origin (3) in the root frame; then, in place, the QP column of
                                 //          the joint: swing-foot linear part s a x (p_sw - o) (3), world axis a (3), CoM part (3), g_r
         oP = oJ + 10 * nJ;      // [L+1][3] prefix of the mass-weighted link CoMs in the root frame (P_l = sum over k < l)
-        oINST = oP + 3 * (L + 1); // [12]   b_r (9) and the stance-foot error (3), for the second solve
-        total = oINST + 12;
+        oINST = oP + 3 * (L + 1); // [13]   b_r (9) and the stance-foot error (3), for the second solve (and for the solve part of the
+                                  //        split tick, whose kinematics part leaves b_r[6..8] without the CoM term); fallback flag
+        total = oINST + 13;
     }
 };
 
@@ -453,9 +454,14 @@ __device__ __forceinline__ void tpi_frames(const IkModelDev& M, const IkTickIO& 
 
 // ---- kinematics + QP columns + the equality-constrained optimum of every instance; then the violators of the CTA, compacted
 // onto its first threads, are solved once more with the bound Goldfarb-Idnani adds first fixed at its value
+// PART 0: the whole tick.  PART 1 / PART 2: the same tick as two launches (wc_ik_tick_part_dev) -- 1 = everything that depends on the
+// joint state, the base and the desired feet / neck only (kinematics, QP columns, the task right-hand sides except the CoM term):
+// it can run before the desired CoM of the tick exists, i.e. beside the MPC block; 2 = the CoM term, the solves, the outputs.
+// The arithmetic is that of PART 0, operation for operation.
+template <int PART>
 __global__ void __launch_bounds__(kTpiThreads, WC_TPI_MINB) ik_tpi_kernel(IkDev d, IkTickIO io)
 {
-    extern __shared__ double sm_slots[]; // [warp][slot][12][32]
+    extern __shared__ double sm_slots[]; // [warp][slot][12][32]  (PART 2: none)
     __shared__ int s_n, s_i[kTpiThreads], s_id[kTpiThreads];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool live = blockIdx.x * kTpiThreads + threadIdx.x < d.B;
@@ -491,13 +497,16 @@ __global__ void __launch_bounds__(kTpiThreads, WC_TPI_MINB) ik_tpi_kernel(IkDev 
     int rc = 0, id = 0;
     if (live) {
     double* sc = d.tpi_scratch + i;
+    const bool left = io.left_is_fixed[i] != 0;
+    double br[9], es[3];
+    bool fallback = false;
+    if constexpr (PART != 2) {
     double* slots = sm_slots + (size_t)warp * d.tpi_slots * 12 * 32 + lane;
     // the measured joint positions are needed after the link loop: ask for their lines now (lane k: row k)
     if (lane < nJ && (lane & 1) * 0 == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(io.q_meas + (size_t)lane * B + (i - lane)));
     if (lane < nJ && (size_t)(i - lane) + 16 < B) asm volatile("prefetch.global.L2 [%0];" ::"l"(io.q_meas + (size_t)lane * B + (i - lane) + 16));
     double P[3];
     tpi_link_loop<true>(M, io, i, B, slots, sc, rows, P);
-    const bool left = io.left_is_fixed[i] != 0;
     double wR[9], wp[3];
     double lfH[12], rfH[12], nR[9], pBr[3];
     tpi_frames(M, io, i, B, slots, left, wR, wp, lfH, rfH, nR, pBr);
@@ -536,7 +545,8 @@ __global__ void __launch_bounds__(kTpiThreads, WC_TPI_MINB) ik_tpi_kernel(IkDev 
     }
 #pragma unroll
     for (int r = 0; r < 3; r++)
-        bvec[12 + r] = io.com_vel_des[(size_t)r * B + i] - cfg.k_pos_com * (io.com_meas[(size_t)r * B + i] - io.com_pos_des[(size_t)r * B + i]);
+        bvec[12 + r] = PART == 1 ? 0.0 // (the solve part adds the CoM term)
+                                 : io.com_vel_des[(size_t)r * B + i] - cfg.k_pos_com * (io.com_meas[(size_t)r * B + i] - io.com_pos_des[(size_t)r * B + i]);
     double We[3];
     {
         double Rdes[9], nd[9], en[3];
@@ -556,7 +566,7 @@ __global__ void __launch_bounds__(kTpiThreads, WC_TPI_MINB) ik_tpi_kernel(IkDev 
     const double pS[3] = {left ? lfH[3] : rfH[3], left ? lfH[7] : rfH[7], left ? lfH[11] : rfH[11]};
     const double pW[3] = {left ? rfH[3] : lfH[3], left ? rfH[7] : lfH[7], left ? rfH[11] : lfH[11]};
     const double om[3] = {bs[3], bs[4], bs[5]};
-    double rS[3], rW[3], rC[3], t3[3], vlin[3], br[9], es[3];
+    double rS[3], rW[3], rC[3], t3[3], vlin[3];
 #pragma unroll
     for (int r = 0; r < 3; r++) { rS[r] = pS[r] - pB[r]; rW[r] = pW[r] - pB[r]; rC[r] = com[r] - pB[r]; }
     cross3(om, rS, t3);
@@ -567,7 +577,7 @@ __global__ void __launch_bounds__(kTpiThreads, WC_TPI_MINB) ik_tpi_kernel(IkDev 
     for (int r = 0; r < 3; r++) { br[r] = bw[r] - (vlin[r] + t3[r]); br[3 + r] = bw[3 + r] - om[r]; }
     cross3(om, rC, t3);
 #pragma unroll
-    for (int r = 0; r < 3; r++) br[6 + r] = bvec[12 + r] - (vlin[r] + t3[r]);
+    for (int r = 0; r < 3; r++) br[6 + r] = PART == 1 ? (vlin[r] + t3[r]) : bvec[12 + r] - (vlin[r] + t3[r]);
     const double* Wn = cfg.neck_weight;
     double Wom[3];
 #pragma unroll
@@ -578,7 +588,6 @@ __global__ void __launch_bounds__(kTpiThreads, WC_TPI_MINB) ik_tpi_kernel(IkDev 
     for (int r = 0; r < 3; r++) sc[(size_t)(rows.oINST + 9 + r) * B] = es[r];
     // ---- QP column of every joint (MIXED representation, WalkingForwardKinematics.cpp:31,436-454): into the scratch (in place of
     // the joint's root-frame axis and origin) and straight into the accumulators of the reduced problem
-    bool fallback = false;
     const double Minv = 1.0 / Mtot;
     // rows of joint j the column needs: axis / origin (6), two prefix entries (3 + 3), the measured joint position
     auto request = [&](int jn, double (&nx)[13]) {
@@ -650,6 +659,27 @@ __global__ void __launch_bounds__(kTpiThreads, WC_TPI_MINB) ik_tpi_kernel(IkDev 
             }
         }
     }
+    if constexpr (PART == 1) {
+        sc[(size_t)(rows.oINST + 12) * B] = fallback ? 1.0 : 0.0;
+        if (io.o_com) { // the CoM the kinematics saw (what wc_fk_* would return for the same posture)
+#pragma unroll
+            for (int r = 0; r < 3; r++) io.o_com[(size_t)r * B + i] = com[r];
+        }
+    }
+    } else { // PART 2: what the kinematics part left in the scratch, plus the CoM term of this tick
+#pragma unroll
+        for (int r = 0; r < 9; r++) br[r] = sc[(size_t)(rows.oINST + r) * B];
+#pragma unroll
+        for (int r = 0; r < 3; r++) es[r] = sc[(size_t)(rows.oINST + 9 + r) * B];
+        fallback = sc[(size_t)(rows.oINST + 12) * B] != 0.0;
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            const double b12 = io.com_vel_des[(size_t)r * B + i] - cfg.k_pos_com * (io.com_meas[(size_t)r * B + i] - io.com_pos_des[(size_t)r * B + i]);
+            br[6 + r] = b12 - br[6 + r];
+            sc[(size_t)(rows.oINST + 6 + r) * B] = br[6 + r]; // the second solve reads b_r from the scratch
+        }
+    }
+    if constexpr (PART != 1) {
     TpiAcc A;
     rc = fallback ? 2 : tpi_solve<false>(d, io, M, A, sc + (size_t)rows.oJ * B, B, i, nJ, br, es, left, -1, 0.0, &id);
     if (rc == 1) { // to the second solve, with the selected bound
@@ -658,7 +688,9 @@ __global__ void __launch_bounds__(kTpiThreads, WC_TPI_MINB) ik_tpi_kernel(IkDev 
     } else if (rc == 2) {
         d.slow_list[atomicAdd(d.slow_count, 1)] = i;
     }
+    }
     } // live
+    if constexpr (PART == 1) return;
     __syncthreads(); // also orders the scratch writes of the CTA's threads before the reads below
     const int n2 = s_n;
     if (threadIdx.x == 0 && n2 > 0) atomicAdd(d.slow_count + 1, n2); // statistics: instances that took the second solve
@@ -744,13 +776,15 @@ __global__ void __launch_bounds__(kTpiThreads, WC_TPI_MINB) ik_tpi_fk_kernel(IkD
 
 int ik_tpi_rows(int n_links, int n_dofs) { return TpiRows(n_links, n_dofs).total; }
 
-cudaError_t launch_ik_tpi(const IkDev& d, const IkTickIO& io, cudaStream_t s)
+// part 0: the whole tick in one launch; 1: its kinematics part; 2: its solve part (ik_tpi_kernel<PART>)
+cudaError_t launch_ik_tpi(const IkDev& d, const IkTickIO& io, cudaStream_t s, int part)
 {
-    const size_t smem = (size_t)(kTpiThreads / 32) * d.tpi_slots * 12 * 32 * sizeof(double);
-    cudaError_t e = cudaFuncSetAttribute(ik_tpi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem = part == 2 ? 0 : (size_t)(kTpiThreads / 32) * d.tpi_slots * 12 * 32 * sizeof(double);
+    auto k = part == 0 ? ik_tpi_kernel<0> : (part == 1 ? ik_tpi_kernel<1> : ik_tpi_kernel<2>);
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int blocks = (d.B + kTpiThreads - 1) / kTpiThreads;
-    ik_tpi_kernel<<<blocks, kTpiThreads, smem, s>>>(d, io);
+    k<<<blocks, kTpiThreads, smem, s>>>(d, io);
     return cudaGetLastError();
 }
 

@@ -311,7 +311,8 @@ static wc_status launch_checked(wc_ik* h, const IkTickIO& io, int mode, cudaStre
         cudaEventRecord(e0, s);
     }
     const bool osqp = h->d.solver == WC_IK_SOLVER_OSQP && mode != IK_MODE_FK_ONLY;
-    const bool two = mode == IK_MODE_TICK && h->d.slow_list && !osqp;
+    const bool kin_part = mode == IK_MODE_TICK_KIN; // a launch of its own only with the thread-per-instance fast path
+    const bool two = (mode == IK_MODE_TICK || mode == IK_MODE_TICK_SOLVE) && h->d.slow_list && !osqp;
     if (h->profiling && !two) cudaEventRecord(em, s);
     cudaError_t e = launch_ik(h->d, io, mode, s, (h->profiling && two) ? em : nullptr);
     if (h->profiling) cudaEventRecord(e1, s);
@@ -319,7 +320,8 @@ static wc_status launch_checked(wc_ik* h, const IkTickIO& io, int mode, cudaStre
         e = cudaMemcpyAsync(h->user_setups, h->d.osetups, (size_t)h->d.B * sizeof(int32_t), cudaMemcpyDeviceToDevice, s);
     if (osqp && h->user_flags && e == cudaSuccess)
         e = cudaMemcpyAsync(h->user_flags, h->d.oflags, (size_t)h->d.B * sizeof(int32_t), cudaMemcpyDeviceToDevice, s);
-    h->launches += two ? (h->d.tpi_scratch ? 2 : 3) : 1; // fast kernel (thread per instance: one launch; warp per instance: two), general kernel
+    if (kin_part) h->launches += (h->d.tpi_scratch && h->d.slow_list && !osqp && h->d.cfg.use_com_as_constraint) ? 1 : 0;
+    else h->launches += two ? (h->d.tpi_scratch ? 2 : 3) : 1; // fast kernel (thread per instance: one launch; warp per instance: two), general kernel
     if (e != cudaSuccess) {
         std::fprintf(stderr, "[%s] CUDA error: %s\n", who, cudaGetErrorString(e));
         return WC_ERR_CUDA;
@@ -345,6 +347,35 @@ wc_status wc_ik_tick_dev(wc_ik* h, const double* q_meas, const double* q_lin, co
     io.com_pos_des = com_pos_des; io.com_vel_des = com_vel_des; io.com_meas = com_meas; io.neck_R_des = neck_R_des;
     io.dq = dq; io.lf_err = lf_err; io.rf_err = rf_err; io.status = qp_status; io.nwsr = nwsr;
     return launch_checked(h, io, IK_MODE_TICK, static_cast<cudaStream_t>(stream), "wc_ik_tick_dev");
+}
+
+wc_status wc_ik_tick_part_dev(wc_ik* h, int32_t part, const double* q_meas, const double* q_lin, const double* base_H,
+                              const uint8_t* left_is_fixed, const double* lf_H_des, const double* rf_H_des,
+                              const double* lf_twist, const double* rf_twist, const double* com_pos_des,
+                              const double* com_vel_des, const double* com_meas, const double* neck_R_des, double* com_out,
+                              double* dq, double* lf_err, double* rf_err, int32_t* qp_status, int32_t* nwsr, void* stream)
+{
+    if (part != WC_IK_PART_KINEMATICS && part != WC_IK_PART_SOLVE) return WC_ERR_INVALID_ARG;
+    if (!h || !q_meas || !q_lin || !left_is_fixed || !lf_H_des || !rf_H_des || !lf_twist || !rf_twist || !neck_R_des)
+        return WC_ERR_INVALID_ARG;
+    if (part == WC_IK_PART_SOLVE && (!com_pos_des || !com_vel_des || !com_meas)) return WC_ERR_INVALID_ARG;
+    if (cudaSetDevice(h->device) != cudaSuccess) return WC_ERR_CUDA;
+    IkTickIO io;
+    std::memset(&io, 0, sizeof(io));
+    io.q_meas = q_meas; io.q_lin = q_lin; io.base_H = base_H; io.left_is_fixed = left_is_fixed;
+    io.lf_H_des = lf_H_des; io.rf_H_des = rf_H_des; io.lf_twist = lf_twist; io.rf_twist = rf_twist;
+    io.com_pos_des = com_pos_des; io.com_vel_des = com_vel_des; io.com_meas = com_meas; io.neck_R_des = neck_R_des;
+    if (part == WC_IK_PART_KINEMATICS) {
+        io.o_com = com_out;
+        return launch_checked(h, io, IK_MODE_TICK_KIN, static_cast<cudaStream_t>(stream), "wc_ik_tick_part_dev (kinematics)");
+    }
+    io.dq = dq; io.lf_err = lf_err; io.rf_err = rf_err; io.status = qp_status; io.nwsr = nwsr;
+    return launch_checked(h, io, IK_MODE_TICK_SOLVE, static_cast<cudaStream_t>(stream), "wc_ik_tick_part_dev (solve)");
+}
+
+int32_t wc_ik_tick_is_split(const wc_ik* h)
+{
+    return (h && h->d.tpi_scratch && h->d.slow_list && h->d.solver != WC_IK_SOLVER_OSQP && h->d.cfg.use_com_as_constraint) ? 1 : 0;
 }
 
 wc_status wc_fk_dev(wc_ik* h, const double* q, const double* base_H, const uint8_t* left_is_fixed,
