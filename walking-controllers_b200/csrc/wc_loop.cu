@@ -101,9 +101,16 @@ wc_status enqueue_tick(wc_loop* h, bool first, cudaStream_t s)
     // side branch (also under graph capture: the side stream joins the capture through the event and is joined back below)
     if (cudaEventRecord(h->ev_fork, s) != cudaSuccess || cudaStreamWaitEvent(h->side, h->ev_fork, 0) != cudaSuccess) return WC_ERR_CUDA;
     loop_pre_kernel<<<g128, 128, 0, h->side>>>(B, h->lf_H, h->rf_H, h->lif, h->base_H, h->neck_R);
-    // measured CoM: FK about the current (perfectly tracked) posture
-    TRY(wc_fk_dev(h->ik, h->q_des, h->base_H, h->lif, nullptr, nullptr, nullptr, h->com_meas, nullptr, nullptr, nullptr, nullptr,
-                  static_cast<void*>(h->side)));
+    // measured CoM: FK about the current (perfectly tracked) posture.  With the split tick (wc_ik_tick_part_dev) the kinematics part
+    // of the QP-IK -- evaluated at the same posture -- delivers it, and one pass over the tree serves both
+    const bool split = wc_ik_tick_is_split(h->ik) != 0;
+    if (split)
+        TRY(wc_ik_tick_part_dev(h->ik, WC_IK_PART_KINEMATICS, h->q_des, h->q_des, h->base_H, h->lif, h->lf_H, h->rf_H, h->lf_tw, h->rf_tw,
+                                nullptr, nullptr, nullptr, h->neck_R, h->com_meas, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                static_cast<void*>(h->side)));
+    else
+        TRY(wc_fk_dev(h->ik, h->q_des, h->base_H, h->lif, nullptr, nullptr, nullptr, h->com_meas, nullptr, nullptr, nullptr, nullptr,
+                      static_cast<void*>(h->side)));
     if (cudaEventRecord(h->ev_join, h->side) != cudaSuccess) return WC_ERR_CUDA;
     TRY(wc_traj_dcm_dev(h->traj, 0, N + 1, h->ref_pos, h->ref_vel, sv));
     TRY(wc_traj_measured_dcm_dev(h->traj, 0, h->cfg.dcm_noise_sigma, h->cfg.noise_seed, h->dcm_meas, sv));
@@ -118,8 +125,13 @@ wc_status enqueue_tick(wc_loop* h, bool first, cudaStream_t s)
     TRY(wc_glue_com_reference_dev(h->glue, h->ref_pos, h->zmp, h->zmp_meas, h->com_meas, h->com_h, h->com_hv, nullptr, nullptr,
                                   h->com_pos_des, h->com_vel_des, sv));
     // FK + QP-IK about the integrated posture (consumes the ZMP-CoM law of THIS tick), then the joint integrator
-    TRY(wc_ik_tick_dev(h->ik, h->q_des, h->q_des, h->base_H, h->lif, h->lf_H, h->rf_H, h->lf_tw, h->rf_tw, h->com_pos_des,
-                       h->com_vel_des, h->com_meas, h->neck_R, h->dq, h->lf_err, h->rf_err, h->qp_status, h->nwsr, sv));
+    if (split)
+        TRY(wc_ik_tick_part_dev(h->ik, WC_IK_PART_SOLVE, h->q_des, h->q_des, h->base_H, h->lif, h->lf_H, h->rf_H, h->lf_tw, h->rf_tw,
+                                h->com_pos_des, h->com_vel_des, h->com_meas, h->neck_R, nullptr, h->dq, h->lf_err, h->rf_err,
+                                h->qp_status, h->nwsr, sv));
+    else
+        TRY(wc_ik_tick_dev(h->ik, h->q_des, h->q_des, h->base_H, h->lif, h->lf_H, h->rf_H, h->lf_tw, h->rf_tw, h->com_pos_des,
+                           h->com_vel_des, h->com_meas, h->neck_R, h->dq, h->lf_err, h->rf_err, h->qp_status, h->nwsr, sv));
     TRY(wc_glue_integrate_joints_dev(h->glue, h->dq, h->q_des, sv));
     loop_advance_kernel<<<1, 1, 0, s>>>(h->tick_dev);
     return cudaGetLastError() == cudaSuccess ? WC_OK : WC_ERR_CUDA;
