@@ -516,8 +516,8 @@ def run_ours(args, world, rank, local_rank):
     # one CUDA-graph replay per tick, device resident.  Workload: synthetic.py CL_* (the model's own LIPM height, +-2 rad/s).
     h_cl = syn.CL_COM_HEIGHT
     # the pipeline's start (one upload with nothing beside it) and drain (the last tick's kernels and download) lie inside the timed
-    # region: 40 steps keep them at ~3 % of it (20 at the larger batches, whose recorded ticks take 8 x the pinned memory)
-    e2e_steps = min(steps, 40 if B <= 65536 else 20)
+    # region: 40 steps keep them at ~3 % of it (20 at the larger batches and with several ranks on one box: pinned memory)
+    e2e_steps = min(steps, 40 if (B <= 65536 and world == 1) else 20)   # (N > 1: host-link bound, and N x the pinned memory on one box)
     e2e_warm = min(warm, 5)
     Te = e2e_steps + e2e_warm
     cl_steps = min(steps, 200)
